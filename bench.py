@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- conv-GAT train-step throughput on B200 (BASELINE.json metric) with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full train step of the reference loop (convolutional_gat/train.py:129-133: forward, loss,
+backward, Adam) of the conv-GAT model on one synthetic batch of the data loaders' shape
+``x, y : [64, 64, 64, 4, 6]`` bf16 per GPU (BASELINE.json configs[1]; weak scaling for N > 1).  Prints ONE JSON
+line on rank 0.  ``value`` is device-resident throughput; ``e2e`` includes the per-step host->device copy of
+x, y from pinned memory and the device->host read of the loss.  L2 is flushed between timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "extended-gan_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "convgat_train_samples_per_sec"
+UNIT = "samples/s"
+SHAPE = (64, 64, 4, 6)  # H, W, T, V: 64x64 coastal-sea crop (data_loader.py:14), 4 frames (:16), 6 KNMI regions
+SEED = 369  # the reference's only seed (dcgan/train.py:181-183)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_batch(n, dtype, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(SEED)
+    x = torch.rand((n,) + SHAPE, generator=g).to(dtype)
+    y = torch.rand((n,) + SHAPE, generator=g).to(dtype)
+    if pin:
+        x, y = x.pin_memory(), y.pin_memory()
+    return x.to(device), y.to(device)
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference arithmetic on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(sample_n: int, steps: int, warmup: int, attention_type: str, mapping: str):
+    from oracle import spec
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(SEED)
+    model = spec.SpecGATMultiHead3D(4, 4, 0.2, 3, type_=attention_type, mapping_type=mapping, n_vertices=SHAPE[3])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.01)  # train.py:212
+    x, y = synth_batch(sample_n, torch.float32)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = model(x)
+        loss = spec.train_loss(out, y)
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return sample_n / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 4  # BASELINE.json configs[0]: small batch on CPU, fp32
+    rate, sec, cores = cpu_reference_step_rate(n, max(1, args.steps), max(1, min(args.warmup, 2)), args.type, args.mapping)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per_gpu_batch=n),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} samples/step of the same workload (fp32, torch CPU, oracle/spec.py restatement; "
+                                   "the reference's own GAT3D layer is absent from its tree)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_batch):
+    H, W, T, V = SHAPE
+    return {
+        "workload": f"convolutional_gat train step: GATMultistream.Model(attention_type={args.type}, mapping_type={args.mapping}), "
+                    f"3 heads, x,y [{per_gpu_batch},{H},{W},{T},{V}] per GPU (BASELINE.json configs[1])",
+        "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "image": [H, W], "time_steps": T,
+        "n_vertices": V, "parallelism": f"dp{args.gpus}",
+        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
+        "optimizer": "Adam(lr=1e-3, weight_decay=0.01) fused, flat fp32 buffers", "cuda_graph": True,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE is 1)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cgat import _lib
+    from cgat.train_step import TrainStep
+    from convolutional_gat.GAT3D.GATMultistream import Model
+
+    H, W, T, V = SHAPE
+    B = args.batch
+    dtype = torch.bfloat16
+    torch.manual_seed(SEED)
+    model = Model(image_width=W, image_height=H, n_vertices=V, attention_type=args.type, mapping_type=args.mapping).to(dev)
+    xh, yh = synth_batch(B, dtype, pin=True)  # host-pinned batch (every rank gets its own shard of a global batch)
+    x, y = xh.to(dev), yh.to(dev)
+    launches0 = _lib.LAUNCHES
+    ts = TrainStep(model, x, y, lr=1e-3, use_graph=True)
+    ts.sync_params()
+    # launches of one step = those captured in the graph (one fwd+bwd pass) + Adam
+    _lib.LAUNCHES = 0
+    ts.graph = None
+    ts._fwd_bwd()
+    per_step_launches = _lib.LAUNCHES + 1
+    ts._capture()
+    torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, K, Wm):
+        for _ in range(Wm):
+            step_fn()
+        barrier()
+        evs = []
+        for _ in range(K):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident throughput ----
+    total_ms = timed(lambda: ts.run(), args.steps, max(3, args.warmup))
+    # ---- end to end: pinned host -> device copies of x, y and a host read of the loss, every step ----
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        ts.load_batch(xh, yh)
+        loss = ts.run()
+        loss_host.copy_(loss, non_blocking=True)
+
+    e2e_ms = timed(e2e_step, args.steps, 3)
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss_host.item())
+
+    # ---- instrumented eager pass: CUDA-event time of every C-ABI kernel (same stream) ----
+    ts.graph = None
+    for _ in range(2):
+        ts.run()
+    torch.cuda.synchronize()
+    _lib.profile_start()
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.zero_()
+        ts.run()
+    torch.cuda.synchronize()
+    prof = _lib.profile_stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    n_pix = B * H * W
+    esz = 2
+    heads = 3
+    rec = T * V
+    # ALGORITHMIC bytes / flops per launch (DESIGN.md section "roofline"): attention reads its input records and
+    # writes its output records once; backward reads input + dout and writes din.
+    pre = args.mapping == "conv"
+    in_rec = heads * rec if pre else rec
+    alg = {
+        "cgat_attn_fwd": ("hbm", n_pix * (in_rec + rec) * esz),
+        "cgat_attn_bwd": ("hbm", n_pix * (2 * in_rec + rec) * esz),
+        "cgat_loss_fwd_bwd": ("hbm", n_pix * rec * 3 * esz),
+    }
+    if pre:
+        cin, cout, k = rec, heads * rec, 3
+        conv_flops = 2.0 * n_pix * cin * cout * k * k  # dense block-diagonal implicit GEMM actually executed
+        conv_bytes = n_pix * (cin + cout) * esz
+        alg["cgat_conv2d_fprop"] = ("hbm", conv_bytes, conv_flops)
+        alg["cgat_conv2d_dgrad"] = ("hbm", conv_bytes, conv_flops)
+        alg["cgat_conv2d_wgrad"] = ("hbm", conv_bytes, conv_flops)
+    kernels = {}
+    for name, (cnt, ms) in sorted(prof.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+        ent = {"launches_per_step": cnt / max(3, min(args.steps, 10)), "ms": ms}
+        if name in alg:
+            ent["gbs"] = alg[name][1] / (ms * 1e-3) / 1e9
+            if len(alg[name]) > 2:
+                ent["tflops"] = alg[name][2] / (ms * 1e-3) / 1e12
+        kernels[name] = ent
+    dom = max((n for n in prof if n in alg), key=lambda n: prof[n][0] * prof[n][1])
+    achieved = alg[dom][1] / (prof[dom][1] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "algorithmic_bytes_per_launch": alg[dom][1], "kernel_ms": prof[dom][1]}
+
+    cpu_rate, cpu_sec, cores = cpu_reference_step_rate(4, 3, 1, args.type, args.mapping) if world == 1 else (None, None, None)
+
+    ms_per_step = total_ms / args.steps
+    line = {
+        "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
+        "e2e": {"value": world * B / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": xh.numel() * xh.element_size() + yh.numel() * yh.element_size(),
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": per_step_launches * args.steps, "gpu_launches_per_step": per_step_launches,
+        "roofline": roofline, "kernels": kernels, "clocks": clocks, "final_loss": final_loss,
+    }
+    if cpu_rate is not None:
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "4 samples/step x 3 steps of the same model (fp32 torch CPU, oracle/spec.py)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
+    ap.add_argument("--type", default="temporal", choices=["temporal", "spatial", "multi_stream"])
+    ap.add_argument("--mapping", default="conv", choices=["conv", "linear"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,205 @@
+"""nn.Modules of the conv-GAT hot path on the CUDA kernels.
+
+Class names, constructor kwargs, attribute names and state_dict keys mirror the reference so that
+the modules drop into ``convolutional_gat/train.py`` unchanged:
+
+* ``GraphAttentionLayer2D`` / ``GATMultiHead2D`` / ``GraphAttentionLayer`` / ``GATMultiHead`` --
+  the in-tree layers of ``convolutional_gat/baseline_model.py:13-197`` (state_dict: ``W``, ``a``, ``B``;
+  heads registered as ``attention_{i}``).
+* ``GATMultiHead3D`` -- the layer ``convolutional_gat/model.py:21-42`` imports from the missing
+  ``GAT3D`` sub-module; semantics defined in DESIGN.md (spec: oracle/spec.py, PARITY UNPINNED).
+
+All arithmetic runs in libcgat_b200.so; there is no PyTorch/CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .functional import AttnConfig, conv2d_nhwc, graph_attention, IMPL_AUTO
+
+
+def _xavier(shape):
+    p = nn.Parameter(torch.empty(*shape))
+    nn.init.xavier_uniform_(p.data, gain=1.414)  # baseline_model.py:19-22
+    return p
+
+
+class _HeadParams(nn.Module):
+    """Parameters of one attention head (keys ``W``/``conv.*``, ``a``, ``B`` as in baseline_model.py:111-116)."""
+
+    def __init__(self, ci: int, co: int, n_nodes: int, alpha: float, mapping_type: str = "linear"):
+        super().__init__()
+        self.in_features, self.out_features, self.alpha = ci, co, alpha
+        self.mapping_type = mapping_type
+        if mapping_type == "linear":
+            self.W = _xavier((ci, co))
+        elif mapping_type == "conv":
+            self.conv = nn.Conv2d(ci, co, 3, padding=1)  # parameter container only; the math runs in our kernels
+        else:
+            raise ValueError(f"mapping_type {mapping_type!r} not supported here")
+        self.a = _xavier((2 * co, 1))
+        self.B = nn.Parameter(torch.zeros(n_nodes, n_nodes) + 1e-6)  # baseline_model.py:24
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} ({self.in_features} -> {self.out_features})"
+
+
+class _GATStream(nn.Module):
+    """All heads of one stream, one fused kernel launch per direction."""
+
+    def __init__(self, ci, co, n_nodes, alpha, nheads, type_, mapping_type="linear", softmax_axis="neighbour",
+                 head_merge="mean", conv_impl=IMPL_AUTO):
+        super().__init__()
+        if type_ not in ("spatial", "temporal"):
+            raise ValueError(type_)
+        if head_merge not in ("mean", "concat"):
+            raise ValueError(head_merge)
+        if softmax_axis not in ("neighbour", "pixel"):
+            raise ValueError(softmax_axis)
+        self.ci, self.co, self.n_nodes, self.alpha, self.nheads = ci, co, n_nodes, alpha, nheads
+        self.type_, self.mapping_type = type_, mapping_type
+        self.softmax_axis, self.head_merge, self.conv_impl = softmax_axis, head_merge, conv_impl
+        self.attentions = [_HeadParams(ci, co, n_nodes, alpha, mapping_type) for _ in range(nheads)]
+        for i, att in enumerate(self.attentions):
+            self.add_module(f"attention_{i}", att)  # baseline_model.py:191-192
+        # all-ones mask == the reference's dense attention; not part of the state_dict
+        self.register_buffer("adj_mask", torch.ones(n_nodes, n_nodes, dtype=torch.uint8), persistent=False)
+
+    # -- dense block-diagonal expansion of the shared per-node conv (see DESIGN.md "node conv") --
+    def _dense_conv_params(self, other: int):
+        w = torch.stack([h.conv.weight for h in self.attentions])  # [k, co, ci, 3, 3]
+        b = torch.stack([h.conv.bias for h in self.attentions])  # [k, co]
+        k, co, ci = w.shape[:3]
+        eye = torch.eye(other, device=w.device, dtype=w.dtype)
+        if self.type_ == "spatial":
+            # rows (k,u,v)  cols (kh,kw,(t,v'))   value w[k,u,t,kh,kw] d(v,v')
+            dense = torch.einsum("kuthw,vx->kuvhwtx", w, eye).reshape(k * co * other, 3, 3, ci * other)
+            bias = b[:, :, None].expand(k, co, other).reshape(-1)
+        else:
+            # rows (k,t,u)  cols (kh,kw,(t',v))   value w[k,u,v,kh,kw] d(t,t')
+            dense = torch.einsum("kuvhw,tx->ktuhwxv", w, eye).reshape(k * other * co, 3, 3, other * ci)
+            bias = b[:, None, :].expand(k, other, co).reshape(-1)
+        return dense, bias
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """``x[N,H,W,T,V]`` -> ``[N,H,W,T,V]`` (mean merge) or heads concatenated on the channel axis."""
+        if x.dim() != 5:
+            raise RuntimeError(f"expected x[N,H,W,T,V], got shape {tuple(x.shape)}")
+        N, H, W, T, V = x.shape
+        spatial = self.type_ == "spatial"
+        nodes, ch = (V, T) if spatial else (T, V)
+        if nodes != self.n_nodes or ch != self.ci:
+            raise RuntimeError(
+                f"{self.type_} stream built for nodes={self.n_nodes}, channels={self.ci}; input has nodes={nodes}, "
+                f"channels={ch}")
+        layout = _lib.LAYOUT_SPATIAL if spatial else _lib.LAYOUT_TEMPORAL
+        merge = _lib.MERGE_MEAN if self.head_merge == "mean" else _lib.MERGE_CONCAT
+        a = torch.stack([h.a.reshape(-1) for h in self.attentions])
+        B = torch.stack([h.B for h in self.attentions])
+        if self.mapping_type == "linear":
+            Wt = torch.stack([h.W for h in self.attentions])
+            inp = x.reshape(N * H * W, T * V)
+            proj = _lib.PROJ_LINEAR
+        else:
+            dense, bias = self._dense_conv_params(nodes)
+            wh = conv2d_nhwc(x.reshape(N, H, W, T * V), dense, bias, stride=1, pad=(1, 1, 1, 1), impl=self.conv_impl)
+            inp = wh.reshape(N * H * W, -1)
+            Wt = None
+            proj = _lib.PROJ_PRE
+        cfg = AttnConfig(nodes=nodes, ci=self.ci, co=self.co, heads=self.nheads, layout=layout, proj=proj, merge=merge,
+                         pix_per_sample=H * W, alpha=self.alpha, softmax_axis=self.softmax_axis)
+        out = graph_attention(inp, Wt, a, B, self.adj_mask, cfg)
+        hm = 1 if self.head_merge == "mean" else self.nheads
+        if spatial:
+            return out.view(N, H, W, hm * self.co, V)
+        return out.view(N, H, W, T, hm * self.co)
+
+
+class GATMultiHead3D(nn.Module):
+    """The conv graph-attention layer of ``convolutional_gat/model.py:21-42`` (source missing upstream).
+
+    ``type_`` "spatial": nodes = V vertices, channels = T frames (``nfeat -> nhid``).
+    "temporal": nodes = T frames, channels = V (``n_vertices -> n_vertices``).
+    "multi_stream": mean of a spatial and a temporal stream.
+    ``mapping_type`` "linear" (``Wh = X.W``, baseline_model.py:127) or "conv" (shared 3x3 conv per node).
+    Extra keyword-only knobs (not in the reference call sites): ``softmax_axis`` ("neighbour" | "pixel"),
+    ``head_merge`` ("mean" keeps the output shape equal to the input shape, which train.py:131 needs;
+    "concat" follows baseline_model.py:196).  The legacy kwarg ``type=`` (model.py:26) is accepted.
+    """
+
+    def __init__(self, nfeat, nhid, alpha, nheads, type_=None, mapping_type="linear", image_height=None,
+                 image_width=None, n_vertices=None, *, softmax_axis="neighbour", head_merge="mean",
+                 conv_impl=IMPL_AUTO, **kwargs):
+        super().__init__()
+        if "type" in kwargs:
+            type_ = kwargs.pop("type")
+        if kwargs:
+            raise TypeError(f"unexpected kwargs {sorted(kwargs)}")
+        if type_ not in ("spatial", "temporal", "multi_stream"):
+            raise ValueError(f"type_ must be spatial|temporal|multi_stream, got {type_!r}")
+        if mapping_type == "smaat_unet":
+            raise NotImplementedError("mapping_type='smaat_unet' is served by convolutional_gat.unet_model.UnetModel")
+        self.type_, self.mapping_type = type_, mapping_type
+        self.image_height, self.image_width, self.n_vertices = image_height, image_width, n_vertices
+        T, V = nfeat, n_vertices
+
+        def stream(tp):
+            if tp == "spatial":
+                return _GATStream(T, nhid, V, alpha, nheads, tp, mapping_type, softmax_axis, head_merge, conv_impl)
+            return _GATStream(V, V, T, alpha, nheads, tp, mapping_type, softmax_axis, head_merge, conv_impl)
+
+        if type_ == "multi_stream":
+            self.spatial_stream = stream("spatial")
+            self.temporal_stream = stream("temporal")
+        else:
+            self.stream = stream(type_)
+
+    def forward(self, x):
+        if self.type_ == "multi_stream":
+            return 0.5 * (self.spatial_stream(x) + self.temporal_stream(x))
+        return self.stream(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-ins for the in-tree layers (convolutional_gat/baseline_model.py)
+# ------------------------------------------------------------------------------------------------
+class GraphAttentionLayer2D(_HeadParams):
+    """``baseline_model.GraphAttentionLayer2D`` (:105-179): per-pixel attention, soft-max over the PIXEL axis."""
+
+    def __init__(self, in_features, out_features, n_vertices, alpha):
+        super().__init__(in_features, out_features, n_vertices, alpha, "linear")
+
+    def forward(self, h):
+        return _gat2d_forward([self], h)
+
+
+def _gat2d_forward(heads, h):
+    if h.dim() != 4:
+        raise RuntimeError(f"expected h[N,C,T,V], got {tuple(h.shape)}")
+    N, C, T, V = h.shape
+    h0 = heads[0]
+    cfg = AttnConfig(nodes=V, ci=T, co=h0.out_features, heads=len(heads), layout=_lib.LAYOUT_SPATIAL,
+                     proj=_lib.PROJ_LINEAR, merge=_lib.MERGE_CONCAT, pix_per_sample=C, alpha=h0.alpha,
+                     softmax_axis="pixel")
+    Wt = torch.stack([m.W for m in heads])
+    a = torch.stack([m.a.reshape(-1) for m in heads])
+    B = torch.stack([m.B for m in heads])
+    out = graph_attention(h.reshape(N * C, T * V), Wt, a, B, None, cfg)
+    return out.view(N, C, len(heads) * h0.out_features, V)  # cat on dim=2 (:196)
+
+
+class GATMultiHead2D(nn.Module):
+    """``baseline_model.GATMultiHead2D`` (:182-197); all heads in one launch."""
+
+    def __init__(self, nfeat, nhid, n_vertices, alpha, nheads):
+        super().__init__()
+        self.attentions = [GraphAttentionLayer2D(nfeat, nhid, n_vertices, alpha) for _ in range(nheads)]
+        for i, att in enumerate(self.attentions):
+            self.add_module(f"attention_{i}", att)
+
+    def forward(self, x):
+        return _gat2d_forward(self.attentions, x)

@@ -1,0 +1,105 @@
+"""The reference train step (convolutional_gat/train.py:129-133, :212) as a replayable device program.
+
+    optimizer.zero_grad(); y_hat = model(x)
+    loss = MSE(y_hat, y) - 0.0005 * sum(y_hat)/numel          (:131)
+    loss.backward(); optimizer.step()                          (Adam(lr, weight_decay=0.01), :212)
+
+* parameters that receive a gradient live in ONE flat fp32 buffer (``flat_param``), their gradients in
+  another (``flat_grad``); ``p.data`` / ``p.grad`` are views, so the model's ``state_dict()`` is unchanged;
+* parameters that never receive a gradient (the reference registers an ``output_layer`` it does not
+  call, model.py:44-47) are left untouched, exactly as ``torch.optim.Adam`` skips ``grad is None``;
+* loss + d loss/d y_hat is one kernel, Adam is one kernel over the flat buffer;
+* data parallel: the batch is sharded over ranks, ``flat_grad`` is all-reduced ONCE per step (NCCL sum over
+  NVLink) and the 1/world scale is folded into the Adam kernel;
+* forward + loss + backward are captured in a CUDA graph (one ``cudaGraphLaunch`` per step); the all-reduce
+  and Adam follow on the same stream.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .functional import adam_step_, loss_and_grad
+from .parallel import FlatParams
+
+
+class TrainStep:
+    def __init__(self, model: torch.nn.Module, example_x: torch.Tensor, example_y: torch.Tensor, lr: float = 1e-3,
+                 weight_decay: float = 0.01, lam: float = 0.0005, betas=(0.9, 0.999), eps: float = 1e-8,
+                 use_graph: bool = True, process_group: Optional[dist.ProcessGroup] = None):
+        self.model = model
+        self.lr, self.weight_decay, self.lam, self.betas, self.eps = lr, weight_decay, lam, betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        self.x = example_x.clone()
+        self.y = example_y.clone()
+        self.device = example_x.device
+        self.loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self.step_count = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self.graph = None
+        self._flatten()
+        if use_graph:
+            self._capture()
+
+    # -- flat buffers ---------------------------------------------------------------------------
+    def _flatten(self):
+        model = self.model
+        for p in model.parameters():
+            p.grad = None
+        # probe which parameters take part in the forward (eager, outside any graph)
+        out = model(self.x)
+        _, dy = loss_and_grad(out, self.y, self.lam)
+        out.backward(dy)
+        self.active = [(n, p) for n, p in model.named_parameters() if p.grad is not None and p.requires_grad]
+        self.inactive = [n for n, p in model.named_parameters() if p.grad is None]
+        self.flat = FlatParams(self.active)
+        self.flat_param, self.flat_grad = self.flat.param, self.flat.grad
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+
+    def sync_params(self):
+        """Broadcast rank 0's parameters (data-parallel start state)."""
+        self.flat.broadcast_params(0, self.pg)
+
+    # -- one step -------------------------------------------------------------------------------
+    def _fwd_bwd(self):
+        self.flat_grad.zero_()
+        self.loss.zero_()
+        out = self.model(self.x)
+        _, dy = loss_and_grad(out, self.y, self.lam, loss_out=self.loss)
+        out.backward(dy)
+
+    def _capture(self):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm up allocator / lazy init on the side stream
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._fwd_bwd()
+
+    def load_batch(self, x: torch.Tensor, y: torch.Tensor):
+        """Copy one batch (host-pinned or device) into the static input buffers."""
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+
+    def run(self) -> torch.Tensor:
+        """One optimisation step on the loaded batch; returns the (device) loss of this rank's shard."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._fwd_bwd()
+        self.flat.all_reduce_grads(self.pg)
+        self.step_count += 1
+        adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                   self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        return self.loss
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.load_batch(x, y)
+        return self.run()

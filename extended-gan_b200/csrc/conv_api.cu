@@ -1,0 +1,47 @@
+// C-ABI entry points of the convolution kernels: argument checks and the direct / tcgen05 switch.
+#include "common.cuh"
+
+namespace cgat {
+int validate_conv(const cgat_conv_desc* d);
+int conv_fprop_direct_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int conv_dgrad_direct_launch(const cgat_conv_desc*, const void*, const void*, void*, cudaStream_t);
+int conv_wgrad_direct_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
+int conv_tc_supported(const cgat_conv_desc* d, int which);
+int conv_fprop_tc_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int conv_dgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, void*, cudaStream_t);
+int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
+}  // namespace cgat
+
+using namespace cgat;
+
+extern "C" int cgat_conv_tc_supported(const cgat_conv_desc* d, int which) {
+  if (validate_conv(d)) return 0;
+  return conv_tc_supported(d, which);
+}
+
+extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                                 int impl, void* stream) {
+  if (int rc = validate_conv(d)) return rc;
+  if (!x || !w || !y) return fail(CGAT_EINVAL, "null x/w/y");
+  if (impl == 0) return conv_fprop_direct_launch(d, x, w, bias, y, (cudaStream_t)stream);
+  if (!conv_tc_supported(d, 0)) return fail(CGAT_EUNSUPPORTED, "tcgen05 fprop does not support this conv shape");
+  return conv_fprop_tc_launch(d, x, w, bias, y, (cudaStream_t)stream);
+}
+
+extern "C" int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, int impl,
+                                 void* stream) {
+  if (int rc = validate_conv(d)) return rc;
+  if (!dy || !w || !dx) return fail(CGAT_EINVAL, "null dy/w/dx");
+  if (impl == 0) return conv_dgrad_direct_launch(d, dy, w, dx, (cudaStream_t)stream);
+  if (!conv_tc_supported(d, 1)) return fail(CGAT_EUNSUPPORTED, "tcgen05 dgrad does not support this conv shape");
+  return conv_dgrad_tc_launch(d, dy, w, dx, (cudaStream_t)stream);
+}
+
+extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                                 int impl, void* stream) {
+  if (int rc = validate_conv(d)) return rc;
+  if (!x || !dy || !dw) return fail(CGAT_EINVAL, "null x/dy/dw");
+  if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
+  if (!conv_tc_supported(d, 2)) return fail(CGAT_EUNSUPPORTED, "tcgen05 wgrad does not support this conv shape");
+  return conv_wgrad_tc_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
+}

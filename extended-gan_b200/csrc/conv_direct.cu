@@ -1,0 +1,201 @@
+// Direct (CUDA-core) NHWC convolution: fprop / dgrad / wgrad for ANY shape.
+//
+// Role: (1) the small-channel convs where an implicit GEMM cannot fill a tensor-core tile (DCGAN
+// generator, 4..32 channels, dcgan/model.py:55-76; conv1 of the discriminators, cin = 4/8), and
+// (2) the on-device cross-check of the tcgen05 implicit-GEMM kernels in conv_tc.cu (tests compare
+// both against the oracle).  fp32 accumulation, weights [cout][kh][kw][cin], leading padding given
+// explicitly so that PyTorch's asymmetric padding="same" for even kernels (left 1 / right 2 for k=4,
+// dcgan/model.py:61-72) is expressible.
+#include "common.cuh"
+
+namespace cgat {
+
+constexpr int CD_THREADS = 256;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case 1: return fmaxf(v, 0.f);
+    case 2: return v > 0.f ? v : 0.2f * v;
+    case 3: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+// one thread per output element, cout fastest (x is a warp broadcast, w rows stay in L1)
+template <typename T>
+__global__ void __launch_bounds__(CD_THREADS) conv_fprop_direct(const cgat_conv_desc d, const T* __restrict__ x,
+                                                                const T* __restrict__ w,
+                                                                const float* __restrict__ bias, T* __restrict__ y) {
+  const long long total = (long long)d.n * d.ho * d.wo * d.cout;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(idx % d.cout);
+    long long pix = idx / d.cout;
+    const int wo = (int)(pix % d.wo);
+    pix /= d.wo;
+    const int ho = (int)(pix % d.ho);
+    const int n = (int)(pix / d.ho);
+    float acc = bias ? bias[co] : 0.f;
+    for (int kh = 0; kh < d.kh; ++kh) {
+      const int hi = ho * d.stride + kh - d.pad_top;
+      if (hi < 0 || hi >= d.h) continue;
+      for (int kw = 0; kw < d.kw; ++kw) {
+        const int wi = wo * d.stride + kw - d.pad_left;
+        if (wi < 0 || wi >= d.w) continue;
+        const T* xp = x + (((long long)n * d.h + hi) * d.w + wi) * d.cin;
+        const T* wp = w + (((long long)co * d.kh + kh) * d.kw + kw) * d.cin;
+        for (int ci = 0; ci < d.cin; ++ci) acc = fmaf(DT<T>::to_f(xp[ci]), DT<T>::to_f(wp[ci]), acc);
+      }
+    }
+    y[idx] = DT<T>::from_f(apply_act(acc, d.act));
+  }
+}
+
+// one thread per input element, cin fastest
+template <typename T>
+__global__ void __launch_bounds__(CD_THREADS) conv_dgrad_direct(const cgat_conv_desc d, const T* __restrict__ dy,
+                                                                const T* __restrict__ w, T* __restrict__ dx) {
+  const long long total = (long long)d.n * d.h * d.w * d.cin;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % d.cin);
+    long long pix = idx / d.cin;
+    const int wi = (int)(pix % d.w);
+    pix /= d.w;
+    const int hi = (int)(pix % d.h);
+    const int n = (int)(pix / d.h);
+    float acc = 0.f;
+    for (int kh = 0; kh < d.kh; ++kh) {
+      const int hn = hi + d.pad_top - kh;
+      if (hn < 0 || hn % d.stride) continue;
+      const int ho = hn / d.stride;
+      if (ho >= d.ho) continue;
+      for (int kw = 0; kw < d.kw; ++kw) {
+        const int wn = wi + d.pad_left - kw;
+        if (wn < 0 || wn % d.stride) continue;
+        const int wo = wn / d.stride;
+        if (wo >= d.wo) continue;
+        const T* dyp = dy + (((long long)n * d.ho + ho) * d.wo + wo) * d.cout;
+        const T* wp = w + ((long long)kh * d.kw + kw) * d.cin + ci;
+        const long long wstride = (long long)d.kh * d.kw * d.cin;
+        for (int co = 0; co < d.cout; ++co) acc = fmaf(DT<T>::to_f(dyp[co]), DT<T>::to_f(wp[co * wstride]), acc);
+      }
+    }
+    dx[idx] = DT<T>::from_f(acc);
+  }
+}
+
+// one CTA per weight element group: block reduces over all output pixels.  dw is WRITTEN (fp32).
+template <typename T>
+__global__ void __launch_bounds__(CD_THREADS) conv_wgrad_direct(const cgat_conv_desc d, const T* __restrict__ x,
+                                                                const T* __restrict__ dy, float* __restrict__ dw) {
+  // blockIdx.x enumerates (co, kh, kw); threads stride over (pixel, ci-chunk)
+  const int kw = blockIdx.x % d.kw;
+  const int kh = (blockIdx.x / d.kw) % d.kh;
+  const int co = blockIdx.x / (d.kw * d.kh);
+  extern __shared__ float s_acc[];  // [cin]
+  for (int ci = threadIdx.x; ci < d.cin; ci += blockDim.x) s_acc[ci] = 0.f;
+  __syncthreads();
+  const long long M = (long long)d.n * d.ho * d.wo;
+  // thread -> (ci, pixel lane): ci fastest for coalesced x reads
+  const int lanes_ci = d.cin < CD_THREADS ? d.cin : CD_THREADS;
+  const int ci0 = threadIdx.x % lanes_ci;
+  const int prow = threadIdx.x / lanes_ci;
+  const int prows = CD_THREADS / lanes_ci;
+  if (prow < prows) {
+    for (int ci = ci0; ci < d.cin; ci += lanes_ci) {
+      float acc = 0.f;
+      for (long long m = prow; m < M; m += prows) {
+        const int wo = (int)(m % d.wo);
+        const int ho = (int)((m / d.wo) % d.ho);
+        const int n = (int)(m / ((long long)d.wo * d.ho));
+        const int hi = ho * d.stride + kh - d.pad_top;
+        const int wi = wo * d.stride + kw - d.pad_left;
+        if (hi < 0 || hi >= d.h || wi < 0 || wi >= d.w) continue;
+        acc = fmaf(DT<T>::to_f(dy[m * d.cout + co]),
+                   DT<T>::to_f(x[(((long long)n * d.h + hi) * d.w + wi) * d.cin + ci]), acc);
+      }
+      atomicAdd(&s_acc[ci], acc);
+    }
+  }
+  __syncthreads();
+  for (int ci = threadIdx.x; ci < d.cin; ci += blockDim.x)
+    dw[(((long long)co * d.kh + kh) * d.kw + kw) * d.cin + ci] = s_acc[ci];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CD_THREADS) conv_dbias_direct(const T* __restrict__ dy, float* __restrict__ db,
+                                                                long long M, int cout) {
+  const int co = blockIdx.x;
+  float acc = 0.f;
+  for (long long m = threadIdx.x; m < M; m += blockDim.x) acc += DT<T>::to_f(dy[m * cout + co]);
+  __shared__ float s[CD_THREADS / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int i = 0; i < CD_THREADS / 32; ++i) v += s[i];
+    db[co] = v;
+  }
+}
+
+static int grid_for(long long total) {
+  long long g = (total + CD_THREADS - 1) / CD_THREADS;
+  const long long cap = 148LL * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int validate_conv(const cgat_conv_desc* d) {
+  if (!d) return fail(CGAT_EINVAL, "null conv descriptor");
+  if (d->n < 1 || d->h < 1 || d->w < 1 || d->cin < 1 || d->cout < 1 || d->kh < 1 || d->kw < 1 || d->stride < 1 ||
+      d->ho < 1 || d->wo < 1 || d->pad_top < 0 || d->pad_left < 0)
+    return fail(CGAT_EINVAL, "bad conv descriptor");
+  if (d->dtype != CGAT_F32 && d->dtype != CGAT_BF16) return fail(CGAT_EINVAL, "bad conv dtype %d", d->dtype);
+  // the last output row/col must start inside the padded input
+  if ((d->ho - 1) * d->stride - d->pad_top >= d->h || (d->wo - 1) * d->stride - d->pad_left >= d->w)
+    return fail(CGAT_EINVAL, "conv output %dx%d does not fit input %dx%d", d->ho, d->wo, d->h, d->w);
+  return 0;
+}
+
+int conv_fprop_direct_launch(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                             cudaStream_t st) {
+  const long long total = (long long)d->n * d->ho * d->wo * d->cout;
+  if (d->dtype == CGAT_F32)
+    conv_fprop_direct<float><<<grid_for(total), CD_THREADS, 0, st>>>(*d, (const float*)x, (const float*)w, bias, (float*)y);
+  else
+    conv_fprop_direct<__nv_bfloat16><<<grid_for(total), CD_THREADS, 0, st>>>(*d, (const __nv_bfloat16*)x,
+                                                                             (const __nv_bfloat16*)w, bias,
+                                                                             (__nv_bfloat16*)y);
+  return check_launch("conv_fprop_direct");
+}
+
+int conv_dgrad_direct_launch(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, cudaStream_t st) {
+  const long long total = (long long)d->n * d->h * d->w * d->cin;
+  if (d->dtype == CGAT_F32)
+    conv_dgrad_direct<float><<<grid_for(total), CD_THREADS, 0, st>>>(*d, (const float*)dy, (const float*)w, (float*)dx);
+  else
+    conv_dgrad_direct<__nv_bfloat16><<<grid_for(total), CD_THREADS, 0, st>>>(*d, (const __nv_bfloat16*)dy,
+                                                                             (const __nv_bfloat16*)w,
+                                                                             (__nv_bfloat16*)dx);
+  return check_launch("conv_dgrad_direct");
+}
+
+int conv_wgrad_direct_launch(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                             cudaStream_t st) {
+  const int blocks = d->cout * d->kh * d->kw;
+  const size_t smem = sizeof(float) * d->cin;
+  const long long M = (long long)d->n * d->ho * d->wo;
+  if (d->dtype == CGAT_F32) {
+    conv_wgrad_direct<float><<<blocks, CD_THREADS, smem, st>>>(*d, (const float*)x, (const float*)dy, dw);
+    if (dbias) conv_dbias_direct<float><<<d->cout, CD_THREADS, 0, st>>>((const float*)dy, dbias, M, d->cout);
+  } else {
+    conv_wgrad_direct<__nv_bfloat16><<<blocks, CD_THREADS, smem, st>>>(*d, (const __nv_bfloat16*)x,
+                                                                       (const __nv_bfloat16*)dy, dw);
+    if (dbias)
+      conv_dbias_direct<__nv_bfloat16><<<d->cout, CD_THREADS, 0, st>>>((const __nv_bfloat16*)dy, dbias, M, d->cout);
+  }
+  return check_launch("conv_wgrad_direct");
+}
+
+}  // namespace cgat

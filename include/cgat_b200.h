@@ -1,0 +1,142 @@
+/* cgat_b200.h -- C ABI of the B200-native conv-GAT hot path (libcgat_b200.so).
+ *
+ * Drop-in boundary.  The reference has no native boundary of its own: every
+ * op is a stock ATen call made from Python (`convolutional_gat/baseline_model.py`,
+ * `dcgan/model.py`).  Each entry point below therefore cites the reference Python lines whose
+ * arithmetic it replaces; the Python side (`extended-gan_b200/cgat/_lib.py`) binds them with ctypes
+ * exactly as shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain `extern "C"`, raw device pointers, explicit sizes; no torch types.
+ *   - every function returns 0 on success, a negative CGAT_E* code for a rejected argument, or a
+ *     positive cudaError_t; `cgat_last_error()` returns a message for the calling thread.
+ *   - functions never allocate device memory, never synchronise and never throw; all buffers
+ *     (inputs, outputs, workspaces) are owned by the caller and must outlive the stream work.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - dtype tags: CGAT_F32 = 0, CGAT_BF16 = 1.  Parameters and their gradients are always fp32.
+ */
+#ifndef CGAT_B200_H_
+#define CGAT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGAT_F32 0
+#define CGAT_BF16 1
+
+#define CGAT_LAYOUT_SPATIAL 0  /* pixel record element (node, c) at  c*nodes + node   (x[N,H,W,T,V], nodes = V) */
+#define CGAT_LAYOUT_TEMPORAL 1 /* pixel record element (node, c) at  node*C + c       (x[N,H,W,T,V], nodes = T) */
+
+#define CGAT_PROJ_LINEAR 0 /* input = raw node features; Wh = X . W computed in-kernel (baseline_model.py:127) */
+#define CGAT_PROJ_PRE 1    /* input = projected features Wh for all heads, head-major records (conv mapping)  */
+
+#define CGAT_MERGE_CONCAT 0 /* heads concatenated on the channel axis (baseline_model.py:196) */
+#define CGAT_MERGE_MEAN 1   /* heads averaged after ELU (output shape == input shape)          */
+
+#define CGAT_EINVAL (-1)       /* bad argument                              */
+#define CGAT_EUNSUPPORTED (-2) /* shape / dtype combination not implemented */
+#define CGAT_EALIGN (-3)       /* pointer or size not 16-byte aligned       */
+
+typedef struct cgat_attn_desc {
+  int64_t n_pix;          /* number of pixel records = N*H*W                                   */
+  int64_t pix_per_sample; /* H*W (indexes the per-sample pixel-softmax statistics)             */
+  int32_t nodes;          /* graph nodes per pixel (V for spatial, T for temporal)             */
+  int32_t ci;             /* input channels per node  (ignored for CGAT_PROJ_PRE)              */
+  int32_t co;             /* output channels per node                                          */
+  int32_t heads;          /* attention heads (1..8)                                            */
+  int32_t layout;         /* CGAT_LAYOUT_*                                                     */
+  int32_t proj;           /* CGAT_PROJ_*                                                       */
+  int32_t merge;          /* CGAT_MERGE_*                                                      */
+  int32_t dtype;          /* CGAT_F32 / CGAT_BF16 for in/out/grad tensors                      */
+  int32_t apply_elu;      /* 1: out = ELU(z) (baseline_model.py:160); 0: out = z               */
+  float alpha;            /* LeakyReLU slope (0.2, baseline_model.py:111,130)                  */
+} cgat_attn_desc;
+
+const char* cgat_version(void);
+const char* cgat_last_error(void);
+
+/* K4  fused attention forward.
+ * Replaces GraphAttentionLayer2D.forward lines 127-160 of convolutional_gat/baseline_model.py
+ * (projection, all-pairs concat :162-169, LeakyReLU :130, soft-max :131, V x V aggregation loop
+ * :148-152, adjacency mix :158, ELU :160) and the head loop + cat of GATMultiHead2D.forward :194-197.
+ *   in    [n_pix][nodes*ci]            (PROJ_LINEAR)  or  [n_pix][heads][nodes*co]  (PROJ_PRE)
+ *   out   [n_pix][nodes*co]            (MERGE_MEAN)   or  concat layout, see DESIGN.md
+ *   W     [heads][ci][co]  fp32 (PROJ_LINEAR only, else NULL)
+ *   a     [heads][2*co]    fp32
+ *   adj   [heads][nodes][nodes] fp32, normalised adjacency in kernel orientation adj[i][v]
+ *   mask  [nodes][nodes] uint8 or NULL (NULL = all ones = reference behaviour)
+ *   stats NULL -> soft-max over neighbours j;  else [N][heads][2][nodes*nodes] (max plane, 1/sum plane) from
+ *         cgat_attn_pixstats -> soft-max over the pixel axis (baseline_model.py:131)           */
+int cgat_attn_fwd(const cgat_attn_desc* d, const void* in, void* out, const float* W, const float* a,
+                  const float* adj, const uint8_t* mask, const float* stats, void* stream);
+
+/* Pixel-axis soft-max statistics (compat mode of baseline_model.py:131: softmax(e, dim=-1) with the
+ * pixel axis last).  stats [N][heads][2][nodes*nodes].                                          */
+int cgat_attn_pixstats(const cgat_attn_desc* d, const void* in, const float* W, const float* a,
+                       const uint8_t* mask, float* stats, void* stream);
+
+/* K5  fused attention backward (forward recomputed in registers; autograd of the lines above).
+ *   dout  gradient of `out`, same layout as `out`
+ *   din   gradient of `in`,  same layout as `in`
+ *   gW [heads][ci][co], ga [heads][2co], gadj [heads][nodes][nodes]: fp32, ACCUMULATED INTO
+ *   bstats: pixel mode only, [N][heads][nodes*nodes] from cgat_attn_pixstats_bwd, else NULL     */
+int cgat_attn_bwd(const cgat_attn_desc* d, const void* in, const void* dout, void* din, const float* W,
+                  const float* a, const float* adj, const uint8_t* mask, const float* stats,
+                  const float* bstats, float* gW, float* ga, float* gadj, void* stream);
+
+/* Pixel mode: bstats[n][h][i][j] = sum_p att * dAtt (ACCUMULATED INTO; caller zeroes).           */
+int cgat_attn_pixstats_bwd(const cgat_attn_desc* d, const void* in, const void* dout, const float* W,
+                           const float* a, const float* adj, const uint8_t* mask, const float* stats,
+                           float* bstats, void* stream);
+
+/* a5  learnable adjacency normalisation, baseline_model.py:41-50 / :133-142:
+ *   adj = B + I; min-max normalise; A_hat = D^-1/2 adj D^-1/2 with D detached.
+ *   B, adj_hat, gB, gadj: [heads][nodes][nodes] fp32.  transpose=1 writes A_hat^T (the 1-D layer's
+ *   left-multiplication, baseline_model.py:53).  One launch for all heads.                        */
+int cgat_adj_norm_fwd(const float* B, float* adj_hat, int heads, int nodes, int transpose, void* stream);
+int cgat_adj_norm_bwd(const float* B, const float* gadj, float* gB, int heads, int nodes, int transpose,
+                      void* stream);
+
+/* Conv descriptors: NHWC activations, weights [cout][kh][kw][cin] ("KRSC"), fp32 accumulate.
+ * Replaces nn.Conv2d calls of dcgan/model.py:35-43,150-169 and the node conv of the conv mapping. */
+typedef struct cgat_conv_desc {
+  int32_t n, h, w, cin;   /* input  [n][h][w][cin]      */
+  int32_t cout, kh, kw;   /* weight [cout][kh][kw][cin] */
+  int32_t stride;         /* same in both directions    */
+  int32_t pad_top, pad_left; /* leading zero padding (PyTorch padding="same" with even k pads 1 before / 2 after) */
+  int32_t ho, wo;         /* output [n][ho][wo][cout]   */
+  int32_t dtype;          /* activations / weights dtype (CGAT_F32 or CGAT_BF16); bias fp32 */
+  int32_t act;            /* fused epilogue: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 sigmoid     */
+} cgat_conv_desc;
+
+/* K1 fprop / K2 dgrad / K3 wgrad.  `impl`: 0 = direct CUDA-core kernel (any shape),
+ * 1 = tcgen05 implicit GEMM (bf16, see cgat_conv_tc_supported).                                   */
+int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                      int impl, void* stream);
+int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, int impl,
+                      void* stream);
+int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                      int impl, void* stream);
+int cgat_conv_tc_supported(const cgat_conv_desc* d, int which /*0 fprop,1 dgrad,2 wgrad*/);
+
+/* a12  train-step pieces, convolutional_gat/train.py:131 and :212.
+ * loss = mean((yhat-y)^2) - lambda*mean(yhat); writes dloss/dyhat (same dtype as yhat) and
+ * ACCUMULATES the scalar loss into loss_out[0] (fp32; caller zeroes).                              */
+int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_out, int64_t n, float lambda,
+                      float grad_scale, int dtype, void* stream);
+/* torch.optim.Adam(lr, weight_decay) on flat fp32 buffers; `step` is the 1-based step count read
+ * from device memory (so the launch is CUDA-graph replayable); grad is multiplied by grad_scale
+ * (1/world after a sum all-reduce).                                                                 */
+int cgat_adam_step(float* param, const float* grad, float* m, float* v, const int64_t* step_dev, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                   void* stream);
+/* dtype conversion of contiguous buffers (fp32 <-> bf16) */
+int cgat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGAT_B200_H_ */
