@@ -62,10 +62,11 @@ SIGNATURES = {
     "cgat_attn_pixstats_bwd": [ctypes.POINTER(AttnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "cgat_adj_norm_fwd": [_P, _P, _I, _I, _I, _P],
     "cgat_adj_norm_bwd": [_P, _P, _P, _I, _I, _I, _P],
-    "cgat_conv2d_fprop": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P],
-    "cgat_conv2d_dgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _I, _P],
-    "cgat_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P],
+    "cgat_conv2d_fprop": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P],
+    "cgat_conv2d_dgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _I, _P, _P],
+    "cgat_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P],
     "cgat_conv_tc_supported": [ctypes.POINTER(ConvDesc), _I],
+    "cgat_conv_workspace_bytes": [ctypes.POINTER(ConvDesc), _I],
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _I64, _F, _F, _I, _P],
     "cgat_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P],
     "cgat_cast": [_P, _I, _P, _I, _I64, _P],
@@ -88,6 +89,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
+        L.cgat_conv_workspace_bytes.restype = ctypes.c_int64
         L.cgat_version.restype = ctypes.c_char_p
         L.cgat_last_error.restype = ctypes.c_char_p
         _lib = L

@@ -144,6 +144,13 @@ def _pick(d: ConvDesc, which: int, impl: int) -> int:
     return IMPL_TC if lib().cgat_conv_tc_supported(ctypes.byref(d), which) else IMPL_DIRECT
 
 
+def _workspace(d: ConvDesc, which: int, impl: int, device):
+    if impl != IMPL_TC:
+        return None
+    nbytes = lib().cgat_conv_workspace_bytes(ctypes.byref(d), which)
+    return torch.empty(max(16, nbytes), dtype=torch.uint8, device=device) if nbytes else None
+
+
 class _Conv2dNHWC(torch.autograd.Function):
     """``y[n,ho,wo,cout] = act(conv(x[n,h,w,cin], w[cout,kh,kw,cin]) + bias)``.
 
@@ -167,7 +174,10 @@ class _Conv2dNHWC(torch.autograd.Function):
         bk = None if bias is None else bias.detach().float().contiguous()
         d = _conv_desc(n, h, wd, cin, cout, kh, kw, stride, pt, pl, ho, wo, dt, act)
         y = torch.empty(n, ho, wo, cout, device=x.device, dtype=x.dtype)
-        _lib.call("cgat_conv2d_fprop", ctypes.byref(d), ptr(x), ptr(wk), ptr(bk), ptr(y), _pick(d, 0, impl), stream())
+        im = _pick(d, 0, impl)
+        ws = _workspace(d, 0, im, x.device)
+        _lib.call("cgat_conv2d_fprop", ctypes.byref(d), ptr(x), ptr(wk), ptr(bk), ptr(y), im, ptr(ws), stream(),
+                  launches=2 if im == IMPL_TC else 1)
         ctx.d = d
         ctx.impl = impl
         ctx.has_bias = bias is not None
@@ -191,10 +201,15 @@ class _Conv2dNHWC(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _lib.call("cgat_conv2d_dgrad", ctypes.byref(d), ptr(dy), ptr(wk), ptr(dx), _pick(d, 1, ctx.impl), st)
+            im = _pick(d, 1, ctx.impl)
+            ws = _workspace(d, 1, im, x.device)
+            _lib.call("cgat_conv2d_dgrad", ctypes.byref(d), ptr(dy), ptr(wk), ptr(dx), im, ptr(ws), st,
+                      launches=2 if im == IMPL_TC else 1)
         dw = torch.empty(wk.shape, device=x.device, dtype=torch.float32)
         db = torch.empty(d.cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
-        _lib.call("cgat_conv2d_wgrad", ctypes.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), _pick(d, 2, ctx.impl), st,
+        im = _pick(d, 2, ctx.impl)
+        ws = _workspace(d, 2, im, x.device)
+        _lib.call("cgat_conv2d_wgrad", ctypes.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), im, ptr(ws), st,
                   launches=2 if db is not None else 1)
         return dx, dw.to(ctx.w_dtype), db, None, None, None, None
 

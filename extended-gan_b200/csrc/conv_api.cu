@@ -7,41 +7,56 @@ int conv_fprop_direct_launch(const cgat_conv_desc*, const void*, const void*, co
 int conv_dgrad_direct_launch(const cgat_conv_desc*, const void*, const void*, void*, cudaStream_t);
 int conv_wgrad_direct_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
 int conv_tc_supported(const cgat_conv_desc* d, int which);
-int conv_fprop_tc_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
-int conv_dgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, void*, cudaStream_t);
-int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
+size_t conv_tc_workspace(const cgat_conv_desc* d, int which);
+int conv_fprop_tc_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, void*, cudaStream_t);
+int conv_dgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, void*, void*, cudaStream_t);
+int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, void*, cudaStream_t);
 }  // namespace cgat
 
 using namespace cgat;
 
+static const char* kNames[3] = {"fprop", "dgrad", "wgrad"};
+
+static int tc_ready(const cgat_conv_desc* d, int which, void* workspace) {
+  if (!conv_tc_supported(d, which)) return fail(CGAT_EUNSUPPORTED, "tcgen05 %s does not support this conv shape", kNames[which]);
+  if (conv_tc_workspace(d, which) > 0 && !workspace)
+    return fail(CGAT_EINVAL, "tcgen05 %s needs a workspace of %zu bytes", kNames[which], conv_tc_workspace(d, which));
+  return 0;
+}
+
 extern "C" int cgat_conv_tc_supported(const cgat_conv_desc* d, int which) {
-  if (validate_conv(d)) return 0;
+  if (validate_conv(d) || which < 0 || which > 2) return 0;
   return conv_tc_supported(d, which);
 }
 
+extern "C" int64_t cgat_conv_workspace_bytes(const cgat_conv_desc* d, int which) {
+  if (validate_conv(d) || which < 0 || which > 2) return 0;
+  return (int64_t)conv_tc_workspace(d, which);
+}
+
 extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                                 int impl, void* stream) {
+                                 int impl, void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!x || !w || !y) return fail(CGAT_EINVAL, "null x/w/y");
   if (impl == 0) return conv_fprop_direct_launch(d, x, w, bias, y, (cudaStream_t)stream);
-  if (!conv_tc_supported(d, 0)) return fail(CGAT_EUNSUPPORTED, "tcgen05 fprop does not support this conv shape");
-  return conv_fprop_tc_launch(d, x, w, bias, y, (cudaStream_t)stream);
+  if (int rc = tc_ready(d, 0, workspace)) return rc;
+  return conv_fprop_tc_launch(d, x, w, bias, y, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, int impl,
-                                 void* stream) {
+                                 void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!dy || !w || !dx) return fail(CGAT_EINVAL, "null dy/w/dx");
   if (impl == 0) return conv_dgrad_direct_launch(d, dy, w, dx, (cudaStream_t)stream);
-  if (!conv_tc_supported(d, 1)) return fail(CGAT_EUNSUPPORTED, "tcgen05 dgrad does not support this conv shape");
-  return conv_dgrad_tc_launch(d, dy, w, dx, (cudaStream_t)stream);
+  if (int rc = tc_ready(d, 1, workspace)) return rc;
+  return conv_dgrad_tc_launch(d, dy, w, dx, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
-                                 int impl, void* stream) {
+                                 int impl, void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!x || !dy || !dw) return fail(CGAT_EINVAL, "null x/dy/dw");
   if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
-  if (!conv_tc_supported(d, 2)) return fail(CGAT_EUNSUPPORTED, "tcgen05 wgrad does not support this conv shape");
-  return conv_wgrad_tc_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
+  if (int rc = tc_ready(d, 2, workspace)) return rc;
+  return conv_wgrad_tc_launch(d, x, dy, dw, dbias, workspace, (cudaStream_t)stream);
 }

@@ -1,0 +1,105 @@
+// tcgen05 / TMEM / TMA building blocks for the implicit-GEMM convolution kernels (sm_100a only).
+//
+// Everything here is inline PTX written against the PTX ISA for sm_100a; bit layouts of the shared
+// memory ("matrix") descriptor and of the instruction descriptor follow the UMMA definitions
+// (SmemDescriptor / InstrDescriptor, kind::f16).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace cgat {
+
+// ---- TMA (cp.async.bulk.tensor) ------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ---- TMEM allocation (warp-collective) -------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- descriptors -----------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, SWIZZLE_NONE ("interleave") canonical layouts, 16-byte units:
+//   K-major : ((8,n),2):((1,SBO),LBO)   8 rows x 16 B contiguous per core matrix, core matrices at SBO along
+//             M/N, the two 16-byte K-chunks of one K=16 instruction at LBO.
+//   MN-major: ((1,n),(8,k)):((X,SBO),(1,LBO))  8 K-rows x 16 B (8 MN elements) contiguous per core matrix,
+//             core matrices at SBO along M/N, groups of 8 K-rows at LBO.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);        // start address            bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;  // leading byte offset      bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;  // stride byte offset       bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version = 1 (Blackwell), bits [46,48)
+  // base offset 0 (bits 49-51), lbo mode 0 (bit 52), layout type SWIZZLE_NONE = 0 (bits 61-63)
+  return d;
+}
+// Instruction descriptor for kind::f16, bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                       // c_format  = F32
+         | (1u << 7)                     // a_format  = BF16
+         | (1u << 10)                    // b_format  = BF16
+         | ((uint32_t)a_mn_major << 15)  // a_major   (0 = K-major, 1 = MN-major)
+         | ((uint32_t)b_mn_major << 16)  // b_major
+         | ((uint32_t)(N >> 3) << 17)    // n_dim
+         | ((uint32_t)(M >> 4) << 24);   // m_dim
+}
+
+// D[tmem] (+)= A[smem] . B[smem];  issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive on the mbarrier when complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// TMEM -> registers: the calling warp reads 16 consecutive fp32 columns of its 32 lanes
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed) ----------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+// 4-D map over an NHWC bf16 tensor [n][h][w][c] with box (8 channels, bw, bh, 1)
+int make_nhwc_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int bw, int bh);
+
+}  // namespace cgat

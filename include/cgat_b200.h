@@ -112,15 +112,19 @@ typedef struct cgat_conv_desc {
   int32_t act;            /* fused epilogue: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 sigmoid     */
 } cgat_conv_desc;
 
-/* K1 fprop / K2 dgrad / K3 wgrad.  `impl`: 0 = direct CUDA-core kernel (any shape),
- * 1 = tcgen05 implicit GEMM (bf16, see cgat_conv_tc_supported).                                   */
+/* K1 fprop / K2 dgrad / K3 wgrad.  `impl`: 0 = direct CUDA-core kernel (any shape, no workspace),
+ * 1 = tcgen05 implicit GEMM (bf16; cgat_conv_tc_supported tells whether the shape is served).
+ * `workspace`: device scratch of at least cgat_conv_workspace_bytes(d, which) bytes (packed weights /
+ * partial sums), 16-byte aligned, owned by the caller; may be NULL when that size is 0.
+ * wgrad WRITES dw [cout][kh][kw][cin] fp32 and, if dbias != NULL, dbias [cout] fp32.                */
 int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
-                      int impl, void* stream);
+                      int impl, void* workspace, void* stream);
 int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, int impl,
-                      void* stream);
+                      void* workspace, void* stream);
 int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
-                      int impl, void* stream);
+                      int impl, void* workspace, void* stream);
 int cgat_conv_tc_supported(const cgat_conv_desc* d, int which /*0 fprop,1 dgrad,2 wgrad*/);
+int64_t cgat_conv_workspace_bytes(const cgat_conv_desc* d, int which);
 
 /* a12  train-step pieces, convolutional_gat/train.py:131 and :212.
  * loss = mean((yhat-y)^2) - lambda*mean(yhat); writes dloss/dyhat (same dtype as yhat) and
