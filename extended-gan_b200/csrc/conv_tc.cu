@@ -41,9 +41,29 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// The driver entry point needs a current context on the CALLING thread.  Autograd runs backward on worker
+// threads that may not have touched the runtime yet, so bind the primary context of the thread's device.
+static void ensure_context() {
+  using GetCurFn = CUresult (*)(CUcontext*);
+  static GetCurFn get_cur = nullptr;
+  if (!get_cur) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      get_cur = reinterpret_cast<GetCurFn>(p);
+  }
+  CUcontext ctx = nullptr;
+  if (get_cur && get_cur(&ctx) == CUDA_SUCCESS && ctx != nullptr) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaSetDevice(dev);  // CUDA >= 12: initialises the runtime and makes the primary context current
+}
+
 int make_nhwc_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int bw, int bh) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(CGAT_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  ensure_context();
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
   cuuint32_t box[4] = {8, (cuuint32_t)bw, (cuuint32_t)bh, 1};
@@ -281,13 +301,18 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, A.tmem_cols);
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, A.tmem_cols);
+  }
 }
 
 // ---- support matrix / launchers ----------------------------------------------------------------------------
+int conv_wgrad_tc_supported(const cgat_conv_desc* d);
+size_t conv_wgrad_tc_workspace(const cgat_conv_desc* d);
 int conv_tc_supported(const cgat_conv_desc* d, int which) {
   if (d->dtype != CGAT_BF16 || d->stride != 1) return 0;
-  if (which == 2) return 0;  // wgrad: see conv_wgrad_tc (not yet routed here)
+  if (which == 2) return conv_wgrad_tc_supported(d);
   // dgrad of a stride-1 conv is a stride-1 conv with cin/cout swapped and the kernel rotated
   const int gk = which == 0 ? d->cin : d->cout;   // GEMM-K channels
   const int gn = which == 0 ? d->cout : d->cin;   // GEMM-N channels
@@ -303,6 +328,7 @@ int conv_tc_supported(const cgat_conv_desc* d, int which) {
 
 size_t conv_tc_workspace(const cgat_conv_desc* d, int which) {
   if (!conv_tc_supported(d, which)) return 0;
+  if (which == 2) return conv_wgrad_tc_workspace(d);
   const int gk = which == 0 ? d->cin : d->cout;
   const int gn = which == 0 ? d->cout : d->cin;
   return geom(d->n, d->ho, d->wo, gk, gn, d->kh, d->kw).wbytes;
@@ -363,8 +389,247 @@ int conv_dgrad_tc_launch(const cgat_conv_desc* d, const void* dy, const void* w,
                    d->kw - 1 - d->pad_left, d->h, d->w, d->cin, nullptr, 0, dx, workspace, st);
 }
 
-int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, void*, cudaStream_t) {
-  return fail(CGAT_EUNSUPPORTED, "tcgen05 wgrad not built yet");
+// =====================================================================================================
+// K3 wgrad:  dW[cout][tap][cin] = sum over pixels  dY[pix][cout] * X[pix + tap][cin]
+//
+// GEMM view: M = cout (<= 128, the TMEM lanes), N = cin per tap (padded to 16), K = pixels.  Both operands
+// are MN-major in shared memory (pixels are the contraction): dY tiles are loaded as [cout chunk][row][8 px][8 co]
+// and the X halo tile is the very same [cin chunk][halo row][halo col][8 ci] buffer the forward uses; tap
+// (r,s) is again only a shifted descriptor start address.  One tcgen05.mma (K=16) contracts two image rows of
+// 8 pixels.  A persistent CTA keeps ONE accumulator set in TMEM (taps x NT columns, + 16 columns fed by a
+// plane of ones that yield dbias) across all its tiles, then writes its partial sums once; a small kernel
+// reduces the per-CTA partials in a fixed order (deterministic, no atomics).
+// =====================================================================================================
+constexpr int WG_STAGES = 4;
+
+struct WgGeom {
+  int nchunk, ch2, nt;    // cin chunks, even-padded, N per tap = ch2*8
+  int mchunk;             // cout / 8
+  int hp, wp, chb;        // halo tile of x
+  int cols;               // TMEM columns used = taps*nt + 16
+  uint32_t tmem_cols;
+  size_t x_stage, dy_stage, stage_bytes, smem;
+  int tiles_h, tiles_w, tiles;
+};
+
+static WgGeom wgeom(const cgat_conv_desc* d) {
+  WgGeom g;
+  g.nchunk = d->cin / 8;
+  g.ch2 = (g.nchunk + 1) & ~1;
+  g.nt = g.ch2 * 8;
+  g.mchunk = d->cout / 8;
+  g.hp = TC_TH + d->kh - 1;
+  g.wp = TC_TW + d->kw - 1;
+  g.chb = (g.hp * g.wp * 16 + 127) & ~127;
+  g.cols = d->kh * d->kw * g.nt + 16;
+  uint32_t c = 32;
+  while (c < (uint32_t)g.cols) c <<= 1;
+  g.tmem_cols = c;
+  g.x_stage = (size_t)g.ch2 * g.chb;
+  g.dy_stage = (size_t)16 * 2048;  // 16 cout-chunk planes (M = 128) of 16 rows x 8 px x 16 B
+  g.stage_bytes = g.x_stage + g.dy_stage;
+  g.smem = 1024 + 4096 + WG_STAGES * g.stage_bytes;
+  g.tiles_h = (d->ho + TC_TH - 1) / TC_TH;
+  g.tiles_w = (d->wo + TC_TW - 1) / TC_TW;
+  g.tiles = d->n * g.tiles_h * g.tiles_w;
+  return g;
+}
+
+struct WgArgs {
+  float* partial;  // [grid][128][cols]
+  int kh, kw, pad_t, pad_l;
+  int nchunk, ch2, nt, mchunk, hp, wp, chb, cols;
+  int tiles_h, tiles_w, tiles;
+  uint32_t tmem_cols, x_stage, stage_bytes;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                     const WgArgs A) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [WG_STAGES]
+  uint64_t* empty = full + WG_STAGES;                  // [WG_STAGES]
+  uint64_t* done = empty + WG_STAGES;                  // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  unsigned char* s_ones = smem + 1024;  // [2 chunk planes][16 rows][8 px][8 x bf16(1.0)]
+  unsigned char* s_stage = s_ones + 4096;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  {
+    uint32_t* o = reinterpret_cast<uint32_t*>(s_ones);
+    for (int i = threadIdx.x; i < 1024; i += TC_THREADS) o[i] = 0x3f803f80u;  // two bf16 1.0
+    // planes that TMA never writes must hold finite numbers: x padding chunk, dY planes >= mchunk
+    for (int s = 0; s < WG_STAGES; ++s) {
+      unsigned char* st = s_stage + (size_t)s * A.stage_bytes;
+      if (A.ch2 != A.nchunk) {
+        uint4* p = reinterpret_cast<uint4*>(st + (size_t)A.nchunk * A.chb);
+        for (int i = threadIdx.x; i < A.chb / 16; i += TC_THREADS) p[i] = make_uint4(0, 0, 0, 0);
+      }
+      uint4* q = reinterpret_cast<uint4*>(st + A.x_stage + (size_t)A.mchunk * 2048);
+      for (int i = threadIdx.x; i < (16 - A.mchunk) * 128; i += TC_THREADS) q[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, A.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)A.nchunk * A.hp * A.wp * 16 + (uint32_t)A.mchunk * 2048;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
+        const int tw = tile % A.tiles_w;
+        const int th = (tile / A.tiles_w) % A.tiles_h;
+        const int n = tile / (A.tiles_w * A.tiles_h);
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], tx);
+        unsigned char* st = s_stage + (size_t)stage * A.stage_bytes;
+        for (int c = 0; c < A.nchunk; ++c)
+          tma_load_4d(st + (size_t)c * A.chb, &tmap_x, c * 8, tw * TC_TW - A.pad_l, th * TC_TH - A.pad_t, n,
+                      &full[stage]);
+        for (int c = 0; c < A.mchunk; ++c)
+          tma_load_4d(st + A.x_stage + (size_t)c * 2048, &tmap_dy, c * 8, tw * TC_TW, th * TC_TH, n, &full[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_w = make_idesc_bf16(128, A.nt, 1, 1);
+      const uint32_t idesc_b = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t ones_addr = smem_u32(s_ones);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accum = 0;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t x_addr = smem_u32(s_stage + (size_t)stage * A.stage_bytes);
+        const uint32_t dy_addr = x_addr + A.x_stage;
+        for (int j = 0; j < TC_TH / 2; ++j) {  // K step: image rows 2j, 2j+1 of the tile (16 pixels)
+          const uint64_t ad = make_smem_desc(dy_addr + j * 256, /*LBO: next 8 pixels*/ 128, /*SBO: next 8 couts*/ 2048);
+          const uint32_t acc_j = accum | (j > 0);
+          for (int r = 0; r < A.kh; ++r)
+            for (int s = 0; s < A.kw; ++s) {
+              const uint64_t bd = make_smem_desc(x_addr + (uint32_t)(((2 * j + r) * A.wp + s) * 16),
+                                                 /*LBO: next halo row*/ (uint32_t)A.wp * 16, /*SBO: next 8 cin*/ (uint32_t)A.chb);
+              umma_bf16(tmem_base + (uint32_t)((r * A.kw + s) * A.nt), ad, bd, idesc_w, acc_j);
+            }
+          const uint64_t od = make_smem_desc(ones_addr + j * 256, 128, 2048);
+          umma_bf16(tmem_base + (uint32_t)(A.kh * A.kw * A.nt), ad, od, idesc_b, acc_j);
+        }
+        accum = 1;
+        umma_commit(&empty[stage]);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    // epilogue: once, after every MMA of this CTA has retired
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;  // cout index
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* out = A.partial + ((size_t)blockIdx.x * 128 + m) * A.cols;
+    const bool has_work = blockIdx.x < A.tiles;  // always true for grid <= tiles
+    for (int c0 = 0; c0 < A.cols; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
+      if (has_work && m < A.mchunk * 8) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<float4*>(out + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, A.tmem_cols);
+  }
+}
+
+// dw[co][tap][ci] = sum_cta partial[cta][co][tap*nt + ci];  dbias[co] = sum_cta partial[cta][co][taps*nt]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ dbias,
+                                    int ncta, int cout, int taps, int cin, int nt, int cols) {
+  const int total = cout * taps * cin + (dbias ? cout : 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int co, col;
+    if (i < cout * taps * cin) {
+      const int ci = i % cin;
+      const int tap = (i / cin) % taps;
+      co = i / (cin * taps);
+      col = tap * nt + ci;
+    } else {
+      co = i - cout * taps * cin;
+      col = taps * nt;
+    }
+    float acc = 0.f;
+    for (int b = 0; b < ncta; ++b) acc += partial[((size_t)b * 128 + co) * cols + col];
+    if (i < cout * taps * cin) dw[i] = acc; else dbias[co] = acc;
+  }
+}
+
+static int wg_grid(const WgGeom& g) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g.tiles < num_sms ? g.tiles : num_sms;
+}
+
+int conv_wgrad_tc_supported(const cgat_conv_desc* d) {
+  if (d->dtype != CGAT_BF16 || d->stride != 1) return 0;
+  if (d->cin % 8 != 0 || d->cout % 8 != 0 || d->cout > 128) return 0;
+  const WgGeom g = wgeom(d);
+  if (g.nt > 256 || g.cols > 512 || g.smem > 227 * 1024) return 0;
+  return 1;
+}
+
+size_t conv_wgrad_tc_workspace(const cgat_conv_desc* d) {
+  const WgGeom g = wgeom(d);
+  return (size_t)148 * 128 * g.cols * sizeof(float);
+}
+
+int conv_wgrad_tc_launch(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                         void* workspace, cudaStream_t st) {
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(workspace))
+    return fail(CGAT_EALIGN, "conv tensors / workspace must be 16-byte aligned");
+  const WgGeom g = wgeom(d);
+  CUtensorMap mx, mdy;
+  if (int rc = make_nhwc_map(&mx, x, d->n, d->h, d->w, d->cin, g.wp, g.hp)) return rc;
+  if (int rc = make_nhwc_map(&mdy, dy, d->n, d->ho, d->wo, d->cout, TC_TW, TC_TH)) return rc;
+  WgArgs A{};
+  A.partial = (float*)workspace;
+  A.kh = d->kh; A.kw = d->kw; A.pad_t = d->pad_top; A.pad_l = d->pad_left;
+  A.nchunk = g.nchunk; A.ch2 = g.ch2; A.nt = g.nt; A.mchunk = g.mchunk; A.hp = g.hp; A.wp = g.wp; A.chb = g.chb;
+  A.cols = g.cols;
+  A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles;
+  A.tmem_cols = g.tmem_cols; A.x_stage = (uint32_t)g.x_stage; A.stage_bytes = (uint32_t)g.stage_bytes;
+  const int grid = wg_grid(g);
+  if (grid > 148) return fail(CGAT_EUNSUPPORTED, "wgrad workspace sized for <= 148 CTAs");
+  cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  conv_wgrad_tc_kernel<<<grid, TC_THREADS, g.smem, st>>>(mx, mdy, A);
+  if (int rc = check_launch("conv_wgrad_tc_kernel")) return rc;
+  const int taps = d->kh * d->kw;
+  const int total = d->cout * taps * d->cin + (dbias ? d->cout : 0);
+  wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float*)workspace, dw, dbias, grid, d->cout, taps,
+                                                          d->cin, g.nt, g.cols);
+  return check_launch("wgrad_reduce_kernel");
 }
 
 }  // namespace cgat

@@ -31,7 +31,7 @@ def _ref_conv(x_nhwc, w_krsc, bias, pad):
 
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_fprop_dgrad(case):
-    from cgat.functional import IMPL_TC, conv2d_nhwc
+    from cgat.functional import IMPL_AUTO, IMPL_TC, conv2d_nhwc
 
     n, h, w, cin, cout, k, pad = case
     torch.manual_seed(7)
@@ -45,21 +45,25 @@ def test_conv_tc_fprop_dgrad(case):
     xo = x.to(DEV, torch.bfloat16).requires_grad_()
     wo = wt.to(DEV).requires_grad_()
     bo = b.to(DEV).requires_grad_()
-    yo = conv2d_nhwc(xo, wo, bo, stride=1, pad=pad, impl=IMPL_TC)
+    wgrad_cols = k * k * ((cin // 8 + 1) // 2 * 16) + 16  # TMEM columns the wgrad accumulators need
+    tc_bwd = cout % 8 == 0 and cout <= 128 and wgrad_cols <= 512
+    # IMPL_AUTO falls back to the direct wgrad kernel where the tcgen05 one does not serve the shape
+    yo = conv2d_nhwc(xo, wo, bo, stride=1, pad=pad, impl=IMPL_TC if tc_bwd else IMPL_AUTO)
     scale = max(1.0, yr.abs().max().item())
     close(yo, yr.detach(), rtol=2e-2, atol=1e-2 * scale, msg="y")
-    # dgrad through tcgen05, wgrad falls back to what the op supports
-    from cgat import _lib
+    # full backward through tcgen05: dgrad (K2) and wgrad + dbias (K3)
     import ctypes
-    from cgat.functional import _conv_desc, _workspace
+
+    from cgat import _lib
+    from cgat.functional import _conv_desc
 
     ho, wo_ = yr.shape[1], yr.shape[2]
     d = _conv_desc(n, h, w, cin, cout, k, k, 1, pad[0], pad[1], ho, wo_, _lib.BF16, 0)
     assert _lib.lib().cgat_conv_tc_supported(ctypes.byref(d), 1) == 1
-    dy = g.to(DEV, torch.bfloat16).contiguous()
-    wk = wt.to(DEV, torch.bfloat16).contiguous()
-    dx = torch.empty(n, h, w, cin, device=DEV, dtype=torch.bfloat16)
-    ws = _workspace(d, 1, IMPL_TC, DEV)
-    _lib.call("cgat_conv2d_dgrad", ctypes.byref(d), _lib.ptr(dy), _lib.ptr(wk), _lib.ptr(dx), 1, _lib.ptr(ws), _lib.stream())
+    assert _lib.lib().cgat_conv_tc_supported(ctypes.byref(d), 0) == 1
+    assert _lib.lib().cgat_conv_tc_supported(ctypes.byref(d), 2) == int(tc_bwd)
+    yo.backward(g.to(DEV, torch.bfloat16))
     gscale = max(1.0, xr.grad.abs().max().item())
-    close(dx, xr.grad, rtol=2e-2, atol=1e-2 * gscale, msg="dx")
+    close(xo.grad, xr.grad, rtol=2e-2, atol=1e-2 * gscale, msg="dx")
+    close(wo.grad, wr.grad, rtol=2e-2, atol=1e-2 * max(1.0, wr.grad.abs().max().item()), msg="dw")
+    close(bo.grad, br.grad, rtol=2e-2, atol=1e-2 * max(1.0, br.grad.abs().max().item()), msg="db")
