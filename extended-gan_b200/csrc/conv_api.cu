@@ -11,9 +11,13 @@ size_t conv_tc_workspace(const cgat_conv_desc* d, int which);
 int conv_fprop_tc_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, void*, cudaStream_t);
 int conv_dgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, void*, void*, cudaStream_t);
 int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, void*, cudaStream_t);
+void set_debug_buffer(long long* p);
 }  // namespace cgat
 
 using namespace cgat;
+
+// developer aid, not part of the public header: registers a device buffer for the kernel timeline
+extern "C" void cgat_debug_timeline(long long* device_buffer) { set_debug_buffer(device_buffer); }
 
 static const char* kNames[3] = {"fprop", "dgrad", "wgrad"};
 
