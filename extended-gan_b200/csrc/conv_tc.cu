@@ -13,6 +13,10 @@
 //    PyTorch's asymmetric padding="same" for even kernels).  (A first version issued one 16-byte-row box
 //    per 8-channel chunk; ncu showed the TMA unit, not HBM or the tensor pipe, was the limiter.)
 //  * four producer warps re-lay the staged rows into [chunk][halo row][halo col][8 ch] (16-byte units);
+//  * measured on B200 (tools/microbench/mma_rate.cu): one tcgen05.mma costs >= 71 cycles to issue whatever its
+//    N (<= 128) or layout, and ~350 cycles when consecutive instructions switch accumulator, so the kernels
+//    issue FEW, LARGE instructions: fprop packs K densely (chunk-major order, ceil(taps*cin/16) instructions
+//    per tile), wgrad builds an im2col operand in shared memory so one instruction covers all taps;
 //  * no im2col is materialised: every tap's A operand is that SAME buffer addressed through a different
 //    UMMA shared-memory descriptor -- start address shifted by (r*WP+s) pixels, 8 consecutive pixels of an
 //    image row form one core matrix (8 rows x 16 B, SWIZZLE_NONE K-major), core matrices step by one halo
@@ -21,16 +25,17 @@
 //    in shared memory for the whole persistent CTA;
 //  * accumulators live in TMEM (2 stages x NPAD columns); the epilogue warps read them with tcgen05.ld,
 //    add bias, apply the activation and store bf16 NHWC, overlapping the next tile's MMAs.
-// Warp roles: warps 0-3 = TMA issue + re-layout, warp 4 = MMA issuer (one thread) + TMEM allocator,
-// warps 5-8 = epilogue.
+// Warp roles: warps 0-3 = re-layout, warp 4 = MMA issuer (one thread) + TMEM allocator, warps 5-8 = epilogue,
+// warp 9 = TMA issuer (one thread).
 #include "tc_common.cuh"
 
 namespace cgat {
 
 constexpr int TC_TH = 16, TC_TW = 8;  // output tile (rows x cols) -> M = 128
-constexpr int TC_THREADS = 288;
-constexpr int TC_PROD = 128;          // producer threads (warps 0-3)
+constexpr int TC_THREADS = 320;
+constexpr int TC_PROD = 128;          // re-layout threads (warps 0-3)
 constexpr int TC_MMA_WARP = 4;
+constexpr int TC_TMA_WARP = 9;        // issues the TMA row loads (kept off the re-layout warps' critical path)
 constexpr int TC_STAGES = 4;
 
 // ---- host helpers --------------------------------------------------------------------------------
@@ -105,15 +110,16 @@ static RowStage row_stage(int pixels_per_row, int c, int rows) {
   return s;
 }
 
+
 struct TcGeom {
-  int nchunk;  // real 8-channel chunks of the GEMM-K side per tap
-  int ch2;     // chunks per tap rounded up to even (one tcgen05.mma consumes two)
-  int npad;    // GEMM-N padded to a multiple of 16
-  int hp, wp;  // halo tile
-  int chb;     // bytes of one chunk plane (128-byte aligned)
-  int kc;      // total K chunks = taps * ch2
+  int nchunk;   // 8-channel chunks of the GEMM-K side per tap
+  int taps;
+  int npairs;   // tcgen05.mma instructions per tile = ceil(nchunk*taps / 2)
+  int npad;     // GEMM-N padded to a multiple of 16
+  int hp, wp;   // halo tile
+  int chb;      // bytes of one chunk plane (128-byte aligned)
   RowStage xs;
-  size_t wbytes, stage_bytes, smem;
+  size_t wbytes, stage_bytes, out_bytes, smem;
   int tiles_h, tiles_w, tiles;
   uint32_t tmem_cols;
 };
@@ -121,16 +127,17 @@ struct TcGeom {
 static TcGeom geom(int n, int ho, int wo, int cin, int cout, int kh, int kw) {
   TcGeom g;
   g.nchunk = cin / 8;
-  g.ch2 = (g.nchunk + 1) & ~1;
+  g.taps = kh * kw;
+  g.npairs = (g.nchunk * g.taps + 1) / 2;
   g.npad = (cout + 15) & ~15;
   g.hp = TC_TH + kh - 1;
   g.wp = TC_TW + kw - 1;
   g.chb = (g.hp * g.wp * 16 + 127) & ~127;
-  g.kc = kh * kw * g.ch2;
   g.xs = row_stage(g.wp, cin, g.hp);
-  g.wbytes = (size_t)g.kc * g.npad * 16;
-  g.stage_bytes = (size_t)g.ch2 * g.chb;
-  g.smem = 2048 + g.wbytes + 2 * (size_t)g.xs.bytes + TC_STAGES * g.stage_bytes;
+  g.wbytes = (size_t)g.npairs * 2 * g.npad * 16;
+  g.stage_bytes = (size_t)g.nchunk * g.chb + 128;  // +128: the odd last chunk's partner reads one unit further
+  g.out_bytes = ((size_t)128 * cout * 2 + 127) & ~(size_t)127;
+  g.smem = 2048 + 1024 + g.wbytes + 2 * (size_t)g.xs.bytes + TC_STAGES * g.stage_bytes + 2 * g.out_bytes;
   g.tiles_h = (ho + TC_TH - 1) / TC_TH;
   g.tiles_w = (wo + TC_TW - 1) / TC_TW;
   g.tiles = n * g.tiles_h * g.tiles_w;
@@ -141,24 +148,24 @@ static TcGeom geom(int n, int ho, int wo, int cin, int cout, int kh, int kw) {
 }
 
 // ---- weight packing ----------------------------------------------------------------------------------
-// out[(tap*ch2 + c) * npad + row][e]  (bf16, 16 bytes per (chunk,row))
+// K-chunks are ordered CHUNK-MAJOR: i = c*taps + tap.   out[i*npad + row][e]  (bf16, 16 bytes per (i,row))
 //   fprop: row = cout index, value w[row][tap][c*8+e]
 //   dgrad: row = cin index,  value w[c*8+e][flipped tap][row]   (roles of cin/cout swapped, kernel rotated 180 deg)
+// chunks beyond nchunk*taps (odd count) are zero.
 template <typename T>
-__global__ void pack_weights_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin,
-                                    int kh, int kw, int rows, int kdim, int ch2, int npad, int dgrad) {
-  const int taps = kh * kw;
-  const long long total = (long long)taps * ch2 * npad * 8;
+__global__ void pack_weights_kernel(const T* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int taps,
+                                    int rows, int kdim, int nchunk, int kchunks2, int npad, int dgrad) {
+  const long long total = (long long)kchunks2 * npad * 8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int e = (int)(i & 7);
     long long q = i >> 3;
     const int row = (int)(q % npad);
-    q /= npad;
-    const int c = (int)(q % ch2);
-    const int tap = (int)(q / ch2);
+    const int ki = (int)(q / npad);
+    const int c = ki / taps;
+    const int tap = ki - c * taps;
     const int k = c * 8 + e;
     float v = 0.f;
-    if (row < rows && k < kdim) {
+    if (row < rows && c < nchunk && k < kdim) {
       if (!dgrad) {
         v = DT<T>::to_f(w[((long long)row * taps + tap) * cin + k]);
       } else {
@@ -183,21 +190,35 @@ __device__ __forceinline__ void issue_rows(const CUtensorMap* map, const StageDe
     tma_load_3d(dst + (size_t)b * s.rows * s.boxe * 2, map, c0 + b * s.boxe, row0, n, bar);
 }
 
-// staged rows [box][row][boxe] -> planes [chunk][row][col][8 ch]   (one 16-byte unit per (chunk,row,col))
-__device__ __forceinline__ void relayout(const unsigned char* __restrict__ stag, unsigned char* __restrict__ planes,
-                                         const StageDesc& s, int cols, int c_total, int nchunk, int plane_bytes,
-                                         int pwarp, int lane) {
-  const int nq = nchunk * cols;
-  for (int row = pwarp; row < s.rows; row += TC_PROD / 32)
-    for (int q = lane; q < nq; q += 32) {
-      const int c = q / cols;
-      const int col = q - c * cols;
-      const int e = col * c_total + c * 8;
-      const int b = e / s.boxe;
-      const int off = e - b * s.boxe;
-      const uint4 v = *reinterpret_cast<const uint4*>(stag + ((size_t)(b * s.rows + row) * s.boxe + off) * 2);
-      *reinterpret_cast<uint4*>(planes + (size_t)c * plane_bytes + (size_t)(row * cols + col) * 16) = v;
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Copy the `nchunk` 16-byte channel chunks of ONE staged pixel (row, col) to `dst + c*plane_bytes` (c = chunk).
+// staging layout [box][row][boxe elements];  element offset of the pixel inside its row = col*c_total.
+// All addresses are 32-bit shared-space addresses.
+__device__ __forceinline__ void copy_pixel_chunks(uint32_t stag, const StageDesc& s, int row, int col, int c_total,
+                                                  int nchunk, uint32_t dst, uint32_t plane_bytes) {
+  int e = col * c_total;
+  const int b = e / s.boxe;
+  int off = e - b * s.boxe;
+  const uint32_t box_bytes = (uint32_t)s.rows * s.boxe * 2;
+  uint32_t src = stag + (uint32_t)b * box_bytes + (uint32_t)(row * s.boxe + off) * 2;
+  int left = (s.boxe - off) >> 3;  // chunks left in this box row
+  for (int c = 0; c < nchunk; ++c) {
+    sts128(dst, lds128(src));
+    dst += plane_bytes;
+    src += 16;
+    if (--left == 0) {  // continue at the same row of the next box
+      src += box_bytes - (uint32_t)s.boxe * 2;
+      left = s.boxe >> 3;
     }
+  }
 }
 
 // Optional timeline instrumentation (developer aid): when a buffer is registered, CTA 0 records clock64()
@@ -207,8 +228,8 @@ __device__ __forceinline__ void relayout(const unsigned char* __restrict__ stag,
 constexpr int DBG_TILES = 16, DBG_EVENTS = 9;
 static long long* g_dbg = nullptr;
 void set_debug_buffer(long long* p) { g_dbg = p; }
-#define DBG(ev)                                                                                   \
-  do {                                                                                            \
+#define DBG(ev)                                                                                           \
+  do {                                                                                                    \
     if (A.dbg != nullptr && blockIdx.x == 0 && it < DBG_TILES) A.dbg[it * DBG_EVENTS + (ev)] = clock64(); \
   } while (0)
 
@@ -220,11 +241,11 @@ struct ConvTcArgs {
   __nv_bfloat16* y;
   int ho, wo, cin, cout, npad;
   int kh, kw, pad_t, pad_l;
-  int nchunk, ch2, hp, wp, chb, kc;
+  int nchunk, taps, npairs, hp, wp, chb;
   int tiles_h, tiles_w, tiles;
   int act;
   uint32_t tmem_cols;
-  uint32_t wbytes, stage_bytes;
+  uint32_t wbytes, stage_bytes, out_bytes;
   StageDesc xs;
 };
 
@@ -237,39 +258,59 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   }
 }
 
+constexpr int TC_MAX_PAIRS = 120;  // instructions per tile (descriptor table in shared memory)
+constexpr int TC_MAX_OWN = 3;      // halo pixels a producer thread re-lays per tile
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  // [0,1024): barriers + tmem pointer; packed weights; 2 row-staging buffers; TC_STAGES halo stages
+  // [0,1024): barriers + tmem pointer; [1024,2048): bias; [2048,3072): descriptor table; packed weights;
+  // 2 row-staging buffers; TC_STAGES halo stages; 2 output staging tiles
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [TC_STAGES]  producers -> MMA
   uint64_t* empty = full + TC_STAGES;                  // [TC_STAGES]  MMA -> producers
   uint64_t* tfull = empty + TC_STAGES;                 // [2]          MMA -> epilogue
   uint64_t* tempty = tfull + 2;                        // [2]          epilogue -> MMA
   uint64_t* wbar = tempty + 2;                         // [1]          packed weights landed
   uint64_t* sbar = wbar + 1;                           // [2]          TMA rows landed in staging
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sbar + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + 1024);  // [npad <= 256]
-  unsigned char* s_w = smem + 2048;
+  uint64_t* sfree = sbar + 2;                          // [2]          staging buffer re-laid, may be overwritten
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + 1024);       // [npad <= 256]
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem + 2048);  // [npairs][2]: A start offset, A LBO (bytes)
+  unsigned char* s_w = smem + 3072;
   unsigned char* s_stag = s_w + A.wbytes;
   unsigned char* s_halo = s_stag + 2 * (size_t)A.xs.bytes;
+  unsigned char* s_out = s_halo + (size_t)TC_STAGES * A.stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full[i], TC_PROD); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); mbar_init(&sbar[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); mbar_init(&sbar[i], 1); mbar_init(&sfree[i], TC_PROD);
+    }
     mbar_init(wbar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmap_x);
   }
   for (int i = threadIdx.x; i < A.npad; i += TC_THREADS)
     s_bias[i] = (A.bias != nullptr && i < A.cout) ? A.bias[i] : 0.f;
-  // zero the padding chunk planes (never written, multiplied by zero weights but must be finite)
-  if (A.ch2 != A.nchunk) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      uint4* p = reinterpret_cast<uint4*>(s_halo + (size_t)s * A.stage_bytes + (size_t)A.nchunk * A.chb);
-      for (int i = threadIdx.x; i < A.chb / 16; i += TC_THREADS) p[i] = make_uint4(0, 0, 0, 0);
-    }
+  // descriptor table: K-chunk i = c*taps + tap lives at plane c, shifted by the tap's pixel offset
+  for (int p = threadIdx.x; p < A.npairs; p += TC_THREADS) {
+    auto addr = [&](int i) {
+      const int c = i / A.taps, tap = i - c * A.taps;
+      const int r = tap / A.kw, s = tap - r * A.kw;
+      return (uint32_t)(c * A.chb + (r * A.wp + s) * 16);
+    };
+    const uint32_t a0 = addr(2 * p);
+    const bool has2 = 2 * p + 1 < A.nchunk * A.taps;
+    s_tab[2 * p] = a0;
+    s_tab[2 * p + 1] = has2 ? addr(2 * p + 1) - a0 : 16u;  // odd tail: partner weights are zero, data must be finite
+  }
+  // halo stages start zeroed: alignment padding / the odd tail's partner unit must hold finite numbers
+  {
+    uint4* p = reinterpret_cast<uint4*>(s_halo);
+    const int n16 = (int)((size_t)TC_STAGES * A.stage_bytes / 16);
+    for (int i = threadIdx.x; i < n16; i += TC_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   if (warp == TC_MMA_WARP) tmem_alloc(tmem_ptr, A.tmem_cols);
@@ -278,44 +319,49 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < TC_PROD / 32) {
-    // ===================== producers: TMA rows -> staging -> chunk planes =====================
-    const int ptid = threadIdx.x;
-    auto origin = [&](int tile, int& c0, int& row0, int& n) {
-      const int tw = tile % A.tiles_w;
-      const int th = (tile / A.tiles_w) % A.tiles_h;
-      n = tile / (A.tiles_w * A.tiles_h);
-      c0 = (tw * TC_TW - A.pad_l) * A.cin;
-      row0 = th * TC_TH - A.pad_t;
-    };
-    if (ptid == 0) {
+  if (warp == TC_TMA_WARP) {
+    // ===================== TMA issuer: staged rows of tile it -> staging[it & 1] =====================
+    if (lane == 0) {
       mbar_arrive_expect_tx(wbar, A.wbytes);
       bulk_g2s(s_w, A.wpack, A.wbytes, wbar);
-      if ((int)blockIdx.x < A.tiles) {
-        int c0, row0, n;
-        origin(blockIdx.x, c0, row0, n);
-        issue_rows(&tmap_x, A.xs, s_stag, c0, row0, n, &sbar[0]);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+        const int tw = tile % A.tiles_w;
+        const int th = (tile / A.tiles_w) % A.tiles_h;
+        const int n = tile / (A.tiles_w * A.tiles_h);
+        mbar_wait(&sfree[it & 1], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        issue_rows(&tmap_x, A.xs, s_stag + (size_t)(it & 1) * A.xs.bytes, (tw * TC_TW - A.pad_l) * A.cin,
+                   th * TC_TH - A.pad_t, n, &sbar[it & 1]);
       }
+    }
+  } else if (warp < TC_PROD / 32) {
+    // ===================== re-layout: staging -> chunk planes =====================
+    const int ptid = threadIdx.x;
+    // the halo pixels this thread re-lays every tile (fixed): q = ptid + k*128
+    int own_row[TC_MAX_OWN], own_col[TC_MAX_OWN];
+    const int npix = A.hp * A.wp;
+#pragma unroll
+    for (int k = 0; k < TC_MAX_OWN; ++k) {
+      const int q = ptid + k * TC_PROD;
+      own_row[k] = q < npix ? q / A.wp : -1;
+      own_col[k] = q < npix ? q % A.wp : 0;
     }
     int stage = 0, it = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
-      named_bar_sync(1, TC_PROD);  // everyone is done reading staging[(it+1)&1] (tile it-1)
-      if (ptid == 0) {
-        DBG(0);
-        const int next = tile + gridDim.x;
-        if (next < A.tiles) {
-          int c0, row0, n;
-          origin(next, c0, row0, n);
-          issue_rows(&tmap_x, A.xs, s_stag + (size_t)((it + 1) & 1) * A.xs.bytes, c0, row0, n, &sbar[(it + 1) & 1]);
-        }
-      }
+      if (ptid == 0) DBG(0);
       mbar_wait(&empty[stage], phase ^ 1);
       if (ptid == 0) DBG(1);
       mbar_wait(&sbar[it & 1], (uint32_t)(it >> 1) & 1u);
       if (ptid == 0) DBG(2);
-      relayout(s_stag + (size_t)(it & 1) * A.xs.bytes, s_halo + (size_t)stage * A.stage_bytes, A.xs, A.wp, A.cin,
-               A.nchunk, A.chb, warp, lane);
+      const uint32_t sg = smem_u32(s_stag) + (uint32_t)(it & 1) * A.xs.bytes;
+      const uint32_t hs = smem_u32(s_halo) + (uint32_t)stage * A.stage_bytes;
+#pragma unroll
+      for (int k = 0; k < TC_MAX_OWN; ++k)
+        if (own_row[k] >= 0)
+          copy_pixel_chunks(sg, A.xs, own_row[k], own_col[k], A.cin, A.nchunk, hs + (uint32_t)(ptid + k * TC_PROD) * 16,
+                            (uint32_t)A.chb);
+      mbar_arrive(&sfree[it & 1]);  // staging buffer consumed (generic-proxy reads done)
       fence_proxy_async_smem();
       if (ptid == 0) DBG(3);
       mbar_arrive(&full[stage]);
@@ -325,7 +371,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, A.npad, 0, 0);
-      const uint32_t a_sbo = (uint32_t)A.wp * 16, a_lbo = (uint32_t)A.chb;
+      const uint32_t a_sbo = (uint32_t)A.wp * 16;
       const uint32_t b_sbo = 128, b_lbo = (uint32_t)A.npad * 16;
       const uint32_t w_addr = smem_u32(s_w);
       mbar_wait(wbar, 0);
@@ -339,17 +385,14 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
         tc_fence_after();
         const uint32_t h_addr = smem_u32(s_halo + (size_t)stage * A.stage_bytes);
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * A.npad);
-        uint32_t accum = 0;
-        for (int r = 0; r < A.kh; ++r)
-          for (int s = 0; s < A.kw; ++s) {
-            const int tap = r * A.kw + s;
-            for (int kp = 0; kp < A.ch2 / 2; ++kp) {
-              const uint64_t ad = make_smem_desc(h_addr + (uint32_t)((r * A.wp + s) * 16 + 2 * kp * A.chb), a_lbo, a_sbo);
-              const uint64_t bd = make_smem_desc(w_addr + (uint32_t)((tap * A.ch2 + 2 * kp) * A.npad * 16), b_lbo, b_sbo);
-              umma_bf16(d_addr, ad, bd, idesc, accum);
-              accum = 1;
-            }
-          }
+        uint64_t bd = make_smem_desc(w_addr, b_lbo, b_sbo);
+        const uint64_t bstep = (uint64_t)((2 * A.npad * 16) >> 4);  // two K-chunks per instruction
+        for (int p = 0; p < A.npairs; ++p) {
+          const uint2 t = *reinterpret_cast<const uint2*>(&s_tab[2 * p]);
+          const uint64_t ad = make_smem_desc(h_addr + t.x, t.y, a_sbo);
+          umma_bf16(d_addr, ad, bd, idesc, p > 0);
+          bd += bstep;
+        }
         umma_commit(&empty[stage]);  // halo stage reusable once these MMAs retire
         umma_commit(&tfull[acc]);    // accumulator ready for the epilogue
         DBG(6);
@@ -361,7 +404,9 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
     // ===================== epilogue (warps 5..8 -> TMEM lane groups 1,2,3,0) =====================
     const int lg = warp & 3;
     const int m = lg * 32 + lane;  // accumulator row = pixel of the tile
+    const int etid = threadIdx.x - (TC_MMA_WARP + 1) * 32;
     const int hrow = m >> 3, wcol = m & 7;
+    const bool staged = (A.cout & 7) == 0;  // coalesced path: tile -> shared memory -> bulk stores per image row
     int acc = 0, it = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
@@ -370,45 +415,75 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
       const int n = tile / (A.tiles_w * A.tiles_h);
       const int h = th * TC_TH + hrow, w = tw * TC_TW + wcol;
       const bool valid = h < A.ho && w < A.wo;
+      unsigned char* ob = s_out + (size_t)(it & 1) * A.out_bytes;
       mbar_wait(&tfull[acc], aphase);
       if (m == 0) DBG(7);
       tc_fence_after();
       __nv_bfloat16* yp = A.y + (((long long)n * A.ho + h) * A.wo + w) * A.cout;
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ob) + (size_t)m * A.cout;
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * A.npad);
       for (int c0 = 0; c0 < A.npad; c0 += 32) {
-        // two 16-column TMEM loads in flight before the single wait
         float v[32];
         tmem_ld16_nowait(t_addr + c0, *reinterpret_cast<float(*)[16]>(&v[0]));
         if (c0 + 16 < A.npad) tmem_ld16_nowait(t_addr + c0 + 16, *reinterpret_cast<float(*)[16]>(&v[16]));
         tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (int hseg = 0; hseg < 2; ++hseg) {
-            const int cb = c0 + 16 * hseg;
-            if (cb >= A.npad) break;
-            float* u = &v[16 * hseg];
+        for (int hseg = 0; hseg < 2; ++hseg) {
+          const int cb = c0 + 16 * hseg;
+          if (cb >= A.npad) break;
+          float* u = &v[16 * hseg];
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) u[i] = tc_act(u[i] + s_bias[cb + i], A.act);
-            if ((A.cout & 7) == 0 && cb + 16 <= A.cout) {
+            for (int i = 0; i < 4; ++i) {
+              const float4 b = b4[i];
+              u[4 * i] += b.x; u[4 * i + 1] += b.y; u[4 * i + 2] += b.z; u[4 * i + 3] += b.w;
+            }
+            if (A.act != 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) u[i] = tc_act(u[i], A.act);
+            }
+          }
+          if (staged) {
+            if (cb < A.cout) {  // cout % 8 == 0: segments of 8 are all-or-nothing
               uint4 o0, o1;
               __nv_bfloat162 t;
 #define PK(a, b) (t = __floats2bfloat162_rn(a, b), *reinterpret_cast<uint32_t*>(&t))
               o0.x = PK(u[0], u[1]); o0.y = PK(u[2], u[3]); o0.z = PK(u[4], u[5]); o0.w = PK(u[6], u[7]);
               o1.x = PK(u[8], u[9]); o1.y = PK(u[10], u[11]); o1.z = PK(u[12], u[13]); o1.w = PK(u[14], u[15]);
 #undef PK
-              reinterpret_cast<uint4*>(yp + cb)[0] = o0;
-              reinterpret_cast<uint4*>(yp + cb)[1] = o1;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (cb + i < A.cout) yp[cb + i] = __float2bfloat16_rn(u[i]);
+              reinterpret_cast<uint4*>(op + cb)[0] = o0;
+              if (cb + 8 < A.cout) reinterpret_cast<uint4*>(op + cb)[1] = o1;
             }
+          } else if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (cb + i < A.cout) yp[cb + i] = __float2bfloat16_rn(u[i]);
           }
         }
       }
       tc_fence_before();
+      mbar_arrive(&tempty[acc]);  // accumulator drained: the MMA warp may start the tile after next
+      if (staged) {
+        // tile is complete in shared memory: all 128 threads stream it out, one contiguous image row segment
+        // (wvalid * cout bf16) at a time, consecutive threads -> consecutive 16-byte chunks
+        named_bar_sync(2, 128);
+        const int w0 = tw * TC_TW;
+        const int wvalid = min(TC_TW, A.wo - w0);
+        const int row_u4 = wvalid * A.cout / 8;        // uint4 per valid row segment
+        const int rows = min(TC_TH, A.ho - th * TC_TH);
+        const int tile_row_u4 = TC_TW * A.cout / 8;    // uint4 pitch of a tile row in shared memory
+        int r = 0, q = etid;
+        while (q >= row_u4) { q -= row_u4; ++r; }
+        while (r < rows) {
+          const uint4 v = reinterpret_cast<const uint4*>(ob)[r * tile_row_u4 + q];
+          reinterpret_cast<uint4*>(A.y + (((long long)n * A.ho + th * TC_TH + r) * A.wo + w0) * A.cout)[q] = v;
+          q += 128;
+          while (q >= row_u4) { q -= row_u4; ++r; }
+        }
+        // the buffer is reused two tiles later; the barrier at the top of that iteration orders these reads
+      }
       if (m == 0) DBG(8);
-      mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
   }
@@ -436,7 +511,8 @@ int conv_tc_supported(const cgat_conv_desc* d, int which) {
     if (d->kh - 1 - d->pad_top < 0 || d->kw - 1 - d->pad_left < 0) return 0;
   }
   const TcGeom g = geom(d->n, which == 0 ? d->ho : d->h, which == 0 ? d->wo : d->w, gk, gn, d->kh, d->kw);
-  if (g.smem > 227 * 1024 || g.tmem_cols > 512) return 0;
+  if (g.smem > 227 * 1024 || g.tmem_cols > 512 || g.npairs > TC_MAX_PAIRS) return 0;
+  if (g.hp * g.wp > TC_MAX_OWN * TC_PROD) return 0;
   return 1;
 }
 
@@ -451,20 +527,21 @@ size_t conv_tc_workspace(const cgat_conv_desc* d, int which) {
 static StageDesc to_dev(const RowStage& s) { return StageDesc{s.rl, s.boxe, s.nbox, s.rows, s.bytes}; }
 
 // generic stride-1 launch: input [n][hi][wi][gk] -> output [n][hout][wout][gn]
-static int launch_tc(const void* in, int n, int hi, int wi, int gk, const void* w_krsc, int w_cout, int w_cin,
-                     int dgrad, int kh, int kw, int pad_t, int pad_l, int hout, int wout, int gn, const float* bias,
-                     int act, void* out, void* workspace, cudaStream_t st) {
+static int launch_tc(const void* in, int n, int hi, int wi, int gk, const void* w_krsc, int w_cin, int dgrad, int kh,
+                     int kw, int pad_t, int pad_l, int hout, int wout, int gn, const float* bias, int act, void* out,
+                     void* workspace, cudaStream_t st) {
   if (!aligned16(in) || !aligned16(out) || !aligned16(workspace))
     return fail(CGAT_EALIGN, "conv tensors / workspace must be 16-byte aligned");
   const TcGeom g = geom(n, hout, wout, gk, gn, kh, kw);
   CUtensorMap map;
   if (int rc = make_rows_map(&map, in, n, hi, wi, gk, g.xs.boxe, g.xs.rows)) return rc;
   {
-    const long long total = (long long)g.kc * g.npad * 8;
+    const long long total = (long long)g.npairs * 2 * g.npad * 8;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     pack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)w_krsc, (__nv_bfloat16*)workspace,
-                                                              w_cout, w_cin, kh, kw, gn, gk, g.ch2, g.npad, dgrad);
+                                                              w_cin, g.taps, gn, gk, g.nchunk, g.npairs * 2, g.npad,
+                                                              dgrad);
     if (int rc = check_launch("pack_weights_kernel")) return rc;
   }
   ConvTcArgs A{};
@@ -474,12 +551,13 @@ static int launch_tc(const void* in, int n, int hi, int wi, int gk, const void* 
   A.y = (__nv_bfloat16*)out;
   A.ho = hout; A.wo = wout; A.cin = gk; A.cout = gn; A.npad = g.npad;
   A.kh = kh; A.kw = kw; A.pad_t = pad_t; A.pad_l = pad_l;
-  A.nchunk = g.nchunk; A.ch2 = g.ch2; A.hp = g.hp; A.wp = g.wp; A.chb = g.chb; A.kc = g.kc;
+  A.nchunk = g.nchunk; A.taps = g.taps; A.npairs = g.npairs; A.hp = g.hp; A.wp = g.wp; A.chb = g.chb;
   A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles;
   A.act = act;
   A.tmem_cols = g.tmem_cols;
   A.wbytes = (uint32_t)g.wbytes;
   A.stage_bytes = (uint32_t)g.stage_bytes;
+  A.out_bytes = (uint32_t)g.out_bytes;
   A.xs = to_dev(g.xs);
   cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -490,61 +568,64 @@ static int launch_tc(const void* in, int n, int hi, int wi, int gk, const void* 
 
 int conv_fprop_tc_launch(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                          void* workspace, cudaStream_t st) {
-  return launch_tc(x, d->n, d->h, d->w, d->cin, w, d->cout, d->cin, 0, d->kh, d->kw, d->pad_top, d->pad_left, d->ho,
-                   d->wo, d->cout, bias, d->act, y, workspace, st);
+  return launch_tc(x, d->n, d->h, d->w, d->cin, w, d->cin, 0, d->kh, d->kw, d->pad_top, d->pad_left, d->ho, d->wo,
+                   d->cout, bias, d->act, y, workspace, st);
 }
 
 int conv_dgrad_tc_launch(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, void* workspace,
                          cudaStream_t st) {
   // dx = conv(dy, rot180(w)^T) with leading padding k-1-pad
-  return launch_tc(dy, d->n, d->ho, d->wo, d->cout, w, d->cout, d->cin, 1, d->kh, d->kw, d->kh - 1 - d->pad_top,
+  return launch_tc(dy, d->n, d->ho, d->wo, d->cout, w, d->cin, 1, d->kh, d->kw, d->kh - 1 - d->pad_top,
                    d->kw - 1 - d->pad_left, d->h, d->w, d->cin, nullptr, 0, dx, workspace, st);
 }
 
 // =====================================================================================================
-// K3 wgrad:  dW[cout][tap][cin] = sum over pixels  dY[pix][cout] * X[pix + tap][cin]
+// K3 wgrad:  dW[cout][tap][cin] = sum over pixels  dY[pix][cout] * X[pix + tap][cin]   (+ dbias)
 //
-// GEMM view: M = cout (<= 128, the TMEM lanes), N = cin per tap (padded to 16), K = pixels.  Both operands
-// are MN-major in shared memory (pixels are the contraction): dY tiles are re-laid as
-// [cout chunk][row][8 px][8 co] and the X halo tile is the very same [cin chunk][halo row][halo col][8 ci]
-// buffer the forward uses; tap (r,s) is again only a shifted descriptor start address.  One tcgen05.mma
-// (K=16) contracts two image rows of 8 pixels.  A persistent CTA keeps ONE accumulator set in TMEM
-// (taps x NT columns, + 16 columns fed by a plane of ones that yield dbias) across all its tiles, then
-// writes its partial sums once; a small kernel reduces the per-CTA partials in a fixed order
+// GEMM view: M = cout (<= 128, the TMEM lanes), N = taps*cin (+8 columns of ones that yield dbias), K = pixels.
+// Both operands are MN-major in shared memory (pixels are the contraction) as [8-wide chunk][128 px][8 elems]
+// planes: dY is re-laid from its staged rows, and the X side is an IM2COL tile built by the producer warps
+// from the staged halo rows (plane index = tap*nchunk + c, i.e. exactly dW's [tap][cin] column order).  One
+// tcgen05.mma (K = 16 pixels = two image rows of the tile) therefore covers ALL taps: 8 instructions per tile,
+// all accumulating into the same TMEM columns.  A persistent CTA keeps that accumulator across all its tiles,
+// then writes its partial sums once; a small kernel reduces the per-CTA partials in a fixed order
 // (deterministic, no atomics).
 // =====================================================================================================
-constexpr int WG_STAGES = 3;
+constexpr int WG_STAGES = 2;
+constexpr int WG_THREADS = 448;   // warps 0-7 re-layout, 8 MMA, 9-12 epilogue, 13 TMA
+constexpr int WG_PROD = 256;
+constexpr int WG_MMA_WARP = 8;
+constexpr int WG_TMA_WARP = 13;
+constexpr int WG_MAXU = 24;       // 16-byte units one re-layout thread moves per tile
 
 struct WgGeom {
-  int nchunk, ch2, nt;    // cin chunks, even-padded, N per tap = ch2*8
-  int mchunk;             // cout / 8
-  int hp, wp, chb;        // halo tile of x
-  int cols;               // TMEM columns used = taps*nt + 16
+  int nchunk, taps, mchunk;
+  int nt;       // N = round16(taps*cin + 8)
+  int planes;   // planes per stage: mchunk dY planes followed by nt/8 im2col planes (>= 16 in total)
+  int hp, wp;
   uint32_t tmem_cols;
   RowStage xs, ys;
-  size_t x_stage, dy_stage, stage_bytes, smem;
+  size_t stage_bytes, smem;
   int tiles_h, tiles_w, tiles;
 };
 
 static WgGeom wgeom(const cgat_conv_desc* d) {
   WgGeom g;
   g.nchunk = d->cin / 8;
-  g.ch2 = (g.nchunk + 1) & ~1;
-  g.nt = g.ch2 * 8;
+  g.taps = d->kh * d->kw;
   g.mchunk = d->cout / 8;
+  g.nt = (g.taps * d->cin + 8 + 15) & ~15;
+  g.planes = g.mchunk + g.nt / 8;
+  if (g.planes < 16) g.planes = 16;
   g.hp = TC_TH + d->kh - 1;
   g.wp = TC_TW + d->kw - 1;
-  g.chb = (g.hp * g.wp * 16 + 127) & ~127;
-  g.cols = d->kh * d->kw * g.nt + 16;
   uint32_t c = 32;
-  while (c < (uint32_t)g.cols) c <<= 1;
+  while (c < (uint32_t)g.nt) c <<= 1;
   g.tmem_cols = c;
   g.xs = row_stage(g.wp, d->cin, g.hp);
   g.ys = row_stage(TC_TW, d->cout, TC_TH);
-  g.x_stage = (size_t)g.ch2 * g.chb;
-  g.dy_stage = (size_t)16 * 2048;  // 16 cout-chunk planes (M = 128) of 16 rows x 8 px x 16 B
-  g.stage_bytes = g.x_stage + g.dy_stage;
-  g.smem = 1024 + 4096 + 2 * ((size_t)g.xs.bytes + g.ys.bytes) + WG_STAGES * g.stage_bytes;
+  g.stage_bytes = (size_t)g.planes * 2048;
+  g.smem = 1024 + 2 * ((size_t)g.xs.bytes + g.ys.bytes) + WG_STAGES * g.stage_bytes;
   g.tiles_h = (d->ho + TC_TH - 1) / TC_TH;
   g.tiles_w = (d->wo + TC_TW - 1) / TC_TW;
   g.tiles = d->n * g.tiles_h * g.tiles_w;
@@ -552,16 +633,17 @@ static WgGeom wgeom(const cgat_conv_desc* d) {
 }
 
 struct WgArgs {
-  float* partial;  // [grid][128][cols]
+  long long* dbg;
+  float* partial;  // [grid][128][nt]
   int cin, cout;
   int kh, kw, pad_t, pad_l;
-  int nchunk, ch2, nt, mchunk, hp, wp, chb, cols;
+  int nchunk, taps, mchunk, nt, planes;
   int tiles_h, tiles_w, tiles;
-  uint32_t tmem_cols, x_stage, stage_bytes;
+  uint32_t tmem_cols, stage_bytes;
   StageDesc xs, ys;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                      const WgArgs A) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -569,103 +651,143 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   uint64_t* empty = full + WG_STAGES;                  // [WG_STAGES]
   uint64_t* done = empty + WG_STAGES;                  // [1]
   uint64_t* sbar = done + 1;                           // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sbar + 2);
-  unsigned char* s_ones = smem + 1024;  // [2 chunk planes][16 rows][8 px][8 x bf16(1.0)]
-  unsigned char* s_stag = s_ones + 4096;
+  uint64_t* sfree = sbar + 2;                          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfree + 2);
+  unsigned char* s_stag = smem + 1024;
   const size_t stag_bytes = (size_t)A.xs.bytes + A.ys.bytes;
   unsigned char* s_stage = s_stag + 2 * stag_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], TC_PROD); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], WG_PROD); mbar_init(&empty[i], 1); }
     mbar_init(done, 1);
-    mbar_init(&sbar[0], 1);
-    mbar_init(&sbar[1], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sbar[i], 1); mbar_init(&sfree[i], WG_PROD); }
     fence_mbar_init();
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_dy);
   }
   {
-    uint32_t* o = reinterpret_cast<uint32_t*>(s_ones);
-    for (int i = threadIdx.x; i < 1024; i += TC_THREADS) o[i] = 0x3f803f80u;  // two bf16 1.0
-    // planes that are never written must hold finite numbers: x padding chunk, dY planes >= mchunk
+    // every plane starts zeroed (padding planes must be finite), then the plane of ones behind the im2col planes
+    uint4* p = reinterpret_cast<uint4*>(s_stage);
+    const int n16 = (int)((size_t)WG_STAGES * A.stage_bytes / 16);
+    for (int i = threadIdx.x; i < n16; i += WG_THREADS) p[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
     for (int s = 0; s < WG_STAGES; ++s) {
-      unsigned char* st = s_stage + (size_t)s * A.stage_bytes;
-      if (A.ch2 != A.nchunk) {
-        uint4* p = reinterpret_cast<uint4*>(st + (size_t)A.nchunk * A.chb);
-        for (int i = threadIdx.x; i < A.chb / 16; i += TC_THREADS) p[i] = make_uint4(0, 0, 0, 0);
-      }
-      uint4* q = reinterpret_cast<uint4*>(st + A.x_stage + (size_t)A.mchunk * 2048);
-      for (int i = threadIdx.x; i < (16 - A.mchunk) * 128; i += TC_THREADS) q[i] = make_uint4(0, 0, 0, 0);
+      uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)s * A.stage_bytes +
+                                                (size_t)(A.mchunk + A.taps * A.nchunk) * 2048);
+      for (int i = threadIdx.x; i < 512; i += WG_THREADS) o[i] = 0x3f803f80u;  // bf16 1.0 x2
     }
     fence_proxy_async_smem();
   }
-  if (warp == TC_MMA_WARP) tmem_alloc(tmem_ptr, A.tmem_cols);
+  if (warp == WG_MMA_WARP) tmem_alloc(tmem_ptr, A.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < TC_PROD / 32) {
-    const int ptid = threadIdx.x;
-    auto issue = [&](int tile, int buf) {
-      const int tw = tile % A.tiles_w;
-      const int th = (tile / A.tiles_w) % A.tiles_h;
-      const int n = tile / (A.tiles_w * A.tiles_h);
-      unsigned char* dst = s_stag + (size_t)buf * stag_bytes;
-      // one mbarrier phase covers both operands: arm it once with the sum of the bytes
-      const uint32_t ybytes = (uint32_t)A.ys.nbox * A.ys.rows * A.ys.boxe * 2;
-      issue_rows(&tmap_x, A.xs, dst, (tw * TC_TW - A.pad_l) * A.cin, th * TC_TH - A.pad_t, n, &sbar[buf], ybytes);
-      for (int b = 0; b < A.ys.nbox; ++b)
-        tma_load_3d(dst + A.xs.bytes + (size_t)b * A.ys.rows * A.ys.boxe * 2, &tmap_dy,
-                    tw * TC_TW * A.cout + b * A.ys.boxe, th * TC_TH, n, &sbar[buf]);
-    };
-    if (ptid == 0 && (int)blockIdx.x < A.tiles) issue(blockIdx.x, 0);
+  if (warp == WG_TMA_WARP) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+        const int tw = tile % A.tiles_w;
+        const int th = (tile / A.tiles_w) % A.tiles_h;
+        const int n = tile / (A.tiles_w * A.tiles_h);
+        const int buf = it & 1;
+        mbar_wait(&sfree[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        unsigned char* dst = s_stag + (size_t)buf * stag_bytes;
+        // one mbarrier phase covers both operands: arm it once with the sum of the bytes
+        const uint32_t ybytes = (uint32_t)A.ys.nbox * A.ys.rows * A.ys.boxe * 2;
+        issue_rows(&tmap_x, A.xs, dst, (tw * TC_TW - A.pad_l) * A.cin, th * TC_TH - A.pad_t, n, &sbar[buf], ybytes);
+        for (int b = 0; b < A.ys.nbox; ++b)
+          tma_load_3d(dst + A.xs.bytes + (size_t)b * A.ys.rows * A.ys.boxe * 2, &tmap_dy,
+                      tw * TC_TW * A.cout + b * A.ys.boxe, th * TC_TH, n, &sbar[buf]);
+      }
+    }
+  } else if (warp < WG_PROD / 32) {
+    // Two threads per tile pixel.  The 16-byte units a thread moves are the same for every tile, so their
+    // (source, destination) offsets are computed once and kept in registers (packed, 16-byte granularity);
+    // per tile the thread then issues its loads in batches of 8 before the matching stores (ILP: the
+    // re-layout is latency bound at 2 warps per scheduler otherwise).
+    const int ptid = threadIdx.x & 127;
+    const int half = threadIdx.x >> 7;
+    const int hr = ptid >> 3, wc = ptid & 7;
+    uint32_t unit[WG_MAXU];
+    int nunit = 0;
+    {
+      auto add_pixel = [&](uint32_t stag_off, const StageDesc& sd, int row, int col, int c_total, int nch,
+                           uint32_t dst_off) {
+        int e = col * c_total;
+        const int b = e / sd.boxe;
+        int off = e - b * sd.boxe;
+        const uint32_t box_bytes = (uint32_t)sd.rows * sd.boxe * 2;
+        uint32_t src = stag_off + (uint32_t)b * box_bytes + (uint32_t)(row * sd.boxe + off) * 2;
+        int left = (sd.boxe - off) >> 3;
+        for (int c = 0; c < nch; ++c) {
+#pragma unroll
+          for (int k = 0; k < WG_MAXU; ++k)
+            if (k == nunit) unit[k] = ((src >> 4) << 16) | (dst_off >> 4);
+          ++nunit;
+          dst_off += 2048;
+          src += 16;
+          if (--left == 0) { src += box_bytes - (uint32_t)sd.boxe * 2; left = sd.boxe >> 3; }
+        }
+      };
+      const uint32_t st0 = (uint32_t)ptid * 16;
+      if (half == 0) add_pixel(A.xs.bytes, A.ys, hr, wc, A.cout, A.mchunk, st0);
+      for (int tap = 1 - half; tap < A.taps; tap += 2) {
+        const int r = tap / A.kw, s2 = tap - r * A.kw;
+        add_pixel(0, A.xs, hr + r, wc + s2, A.cin, A.nchunk, st0 + (uint32_t)(A.mchunk + tap * A.nchunk) * 2048);
+      }
+    }
     int stage = 0, it = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
-      named_bar_sync(1, TC_PROD);
-      if (ptid == 0) {
-        const int next = tile + gridDim.x;
-        if (next < A.tiles) issue(next, (it + 1) & 1);
-      }
+      if (threadIdx.x == 0) DBG(0);
       mbar_wait(&empty[stage], phase ^ 1);
+      if (threadIdx.x == 0) DBG(1);
       mbar_wait(&sbar[it & 1], (uint32_t)(it >> 1) & 1u);
-      const unsigned char* sg = s_stag + (size_t)(it & 1) * stag_bytes;
-      unsigned char* st = s_stage + (size_t)stage * A.stage_bytes;
-      relayout(sg, st, A.xs, A.wp, A.cin, A.nchunk, A.chb, warp, lane);
-      relayout(sg + A.xs.bytes, st + A.x_stage, A.ys, TC_TW, A.cout, A.mchunk, 2048, warp, lane);
+      if (threadIdx.x == 0) DBG(2);
+      const uint32_t sg = smem_u32(s_stag) + (uint32_t)((it & 1) * stag_bytes);
+      const uint32_t st = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes;
+#pragma unroll
+      for (int k0 = 0; k0 < WG_MAXU; k0 += 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k0 + k < nunit) v[k] = lds128(sg + ((unit[k0 + k] >> 16) << 4));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k0 + k < nunit) sts128(st + ((unit[k0 + k] & 0xffffu) << 4), v[k]);
+      }
+      mbar_arrive(&sfree[it & 1]);
       fence_proxy_async_smem();
+      if (threadIdx.x == 0) DBG(3);
       mbar_arrive(&full[stage]);
       if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == TC_MMA_WARP) {
+  } else if (warp == WG_MMA_WARP) {
     if (lane == 0) {
-      const uint32_t idesc_w = make_idesc_bf16(128, A.nt, 1, 1);
-      const uint32_t idesc_b = make_idesc_bf16(128, 16, 1, 1);
-      const uint32_t ones_addr = smem_u32(s_ones);
-      int stage = 0;
+      const uint32_t idesc = make_idesc_bf16(128, A.nt, 1, 1);
+      int stage = 0, it = 0;
       uint32_t phase = 0;
       uint32_t accum = 0;
-      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+        DBG(4);
         mbar_wait(&full[stage], phase);
+        DBG(5);
         tc_fence_after();
-        const uint32_t x_addr = smem_u32(s_stage + (size_t)stage * A.stage_bytes);
-        const uint32_t dy_addr = x_addr + A.x_stage;
+        const uint32_t dy_addr = smem_u32(s_stage + (size_t)stage * A.stage_bytes);
+        const uint32_t im_addr = dy_addr + (uint32_t)A.mchunk * 2048;
+#pragma unroll
         for (int j = 0; j < TC_TH / 2; ++j) {  // K step: image rows 2j, 2j+1 of the tile (16 pixels)
-          const uint64_t ad = make_smem_desc(dy_addr + j * 256, /*LBO: next 8 pixels*/ 128, /*SBO: next 8 couts*/ 2048);
-          const uint32_t acc_j = accum | (j > 0);
-          for (int r = 0; r < A.kh; ++r)
-            for (int s = 0; s < A.kw; ++s) {
-              const uint64_t bd = make_smem_desc(x_addr + (uint32_t)(((2 * j + r) * A.wp + s) * 16),
-                                                 /*LBO: next halo row*/ (uint32_t)A.wp * 16, /*SBO: next 8 cin*/ (uint32_t)A.chb);
-              umma_bf16(tmem_base + (uint32_t)((r * A.kw + s) * A.nt), ad, bd, idesc_w, acc_j);
-            }
-          const uint64_t od = make_smem_desc(ones_addr + j * 256, 128, 2048);
-          umma_bf16(tmem_base + (uint32_t)(A.kh * A.kw * A.nt), ad, od, idesc_b, acc_j);
+          // LBO: next 8 pixels (128 B);  SBO: next 8 couts / next 8 im2col columns (one 2048 B plane)
+          const uint64_t ad = make_smem_desc(dy_addr + j * 256, 128, 2048);
+          const uint64_t bd = make_smem_desc(im_addr + j * 256, 128, 2048);
+          umma_bf16(tmem_base, ad, bd, idesc, accum | (j > 0));
         }
         accum = 1;
         umma_commit(&empty[stage]);
+        DBG(6);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(done);
@@ -676,8 +798,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
     const int m = lg * 32 + lane;  // cout index
     mbar_wait(done, 0);
     tc_fence_after();
-    float* out = A.partial + ((size_t)blockIdx.x * 128 + m) * A.cols;
-    for (int c0 = 0; c0 < A.cols; c0 += 16) {
+    float* out = A.partial + ((size_t)blockIdx.x * 128 + m) * A.nt;
+    for (int c0 = 0; c0 < A.nt; c0 += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
       if (m < A.cout) {
@@ -689,37 +811,30 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_MMA_WARP) {
+  if (warp == WG_MMA_WARP) {
     __syncwarp();
     tmem_dealloc(tmem_base, A.tmem_cols);
   }
 }
 
-// dw[co][tap][ci] = sum_cta partial[cta][co][tap*nt + ci];  dbias[co] = sum_cta partial[cta][co][taps*nt]
+// dw[co][k] = sum_cta partial[cta][co][k]  (k < taps*cin);  dbias[co] = sum_cta partial[cta][co][taps*cin]
 // 64 outputs x 4 CTA-slices per block; fixed summation order (deterministic).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
-                                                           float* __restrict__ dbias, int ncta, int cout, int taps,
-                                                           int cin, int nt, int cols) {
+                                                           float* __restrict__ dbias, int ncta, int cout, int kdim,
+                                                           int nt) {
   __shared__ float s[4][64];
-  const int nw = cout * taps * cin;
+  const int nw = cout * kdim;
   const int total = nw + (dbias ? cout : 0);
   const int o = blockIdx.x * 64 + (threadIdx.x & 63);
   const int slice = threadIdx.x >> 6;
   float acc = 0.f;
-  int co = 0, col = 0;
+  int co = 0;
   if (o < total) {
-    if (o < nw) {
-      const int ci = o % cin;
-      const int tap = (o / cin) % taps;
-      co = o / (cin * taps);
-      col = tap * nt + ci;
-    } else {
-      co = o - nw;
-      col = taps * nt;
-    }
-    const float* p = partial + (size_t)co * cols + col;
+    int col;
+    if (o < nw) { co = o / kdim; col = o - co * kdim; } else { co = o - nw; col = kdim; }
+    const float* p = partial + (size_t)co * nt + col;
 #pragma unroll 4
-    for (int b = slice; b < ncta; b += 4) acc += p[(size_t)b * 128 * cols];
+    for (int b = slice; b < ncta; b += 4) acc += p[(size_t)b * 128 * nt];
   }
   s[slice][threadIdx.x & 63] = acc;
   __syncthreads();
@@ -733,13 +848,15 @@ int conv_wgrad_tc_supported(const cgat_conv_desc* d) {
   if (d->dtype != CGAT_BF16 || d->stride != 1) return 0;
   if (d->cin % 8 != 0 || d->cout % 8 != 0 || d->cout > 128) return 0;
   const WgGeom g = wgeom(d);
-  if (g.nt > 256 || g.cols > 512 || g.smem > 227 * 1024) return 0;
+  if (g.nt > 256 || g.smem > 227 * 1024) return 0;
+  // units per re-layout thread: the dY pixel plus every other tap (first half) must fit the register table
+  if (g.mchunk + ((g.taps + 1) / 2) * g.nchunk > WG_MAXU) return 0;
   return 1;
 }
 
 size_t conv_wgrad_tc_workspace(const cgat_conv_desc* d) {
   const WgGeom g = wgeom(d);
-  return (size_t)148 * 128 * g.cols * sizeof(float);
+  return (size_t)148 * 128 * g.nt * sizeof(float);
 }
 
 int conv_wgrad_tc_launch(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
@@ -751,24 +868,23 @@ int conv_wgrad_tc_launch(const cgat_conv_desc* d, const void* x, const void* dy,
   if (int rc = make_rows_map(&mx, x, d->n, d->h, d->w, d->cin, g.xs.boxe, g.xs.rows)) return rc;
   if (int rc = make_rows_map(&mdy, dy, d->n, d->ho, d->wo, d->cout, g.ys.boxe, g.ys.rows)) return rc;
   WgArgs A{};
+  A.dbg = g_dbg;
   A.partial = (float*)workspace;
   A.cin = d->cin; A.cout = d->cout;
   A.kh = d->kh; A.kw = d->kw; A.pad_t = d->pad_top; A.pad_l = d->pad_left;
-  A.nchunk = g.nchunk; A.ch2 = g.ch2; A.nt = g.nt; A.mchunk = g.mchunk; A.hp = g.hp; A.wp = g.wp; A.chb = g.chb;
-  A.cols = g.cols;
+  A.nchunk = g.nchunk; A.taps = g.taps; A.mchunk = g.mchunk; A.nt = g.nt; A.planes = g.planes;
   A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles;
-  A.tmem_cols = g.tmem_cols; A.x_stage = (uint32_t)g.x_stage; A.stage_bytes = (uint32_t)g.stage_bytes;
+  A.tmem_cols = g.tmem_cols; A.stage_bytes = (uint32_t)g.stage_bytes;
   A.xs = to_dev(g.xs); A.ys = to_dev(g.ys);
   const int grid = g.tiles < sm_count() ? g.tiles : sm_count();
   if (grid > 148) return fail(CGAT_EUNSUPPORTED, "wgrad workspace sized for <= 148 CTAs");
   cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  conv_wgrad_tc_kernel<<<grid, TC_THREADS, g.smem, st>>>(mx, mdy, A);
+  conv_wgrad_tc_kernel<<<grid, WG_THREADS, g.smem, st>>>(mx, mdy, A);
   if (int rc = check_launch("conv_wgrad_tc_kernel")) return rc;
-  const int taps = d->kh * d->kw;
-  const int total = d->cout * taps * d->cin + (dbias ? d->cout : 0);
-  wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>((const float*)workspace, dw, dbias, grid, d->cout, taps,
-                                                        d->cin, g.nt, g.cols);
+  const int kdim = g.taps * d->cin;
+  const int total = d->cout * kdim + (dbias ? d->cout : 0);
+  wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>((const float*)workspace, dw, dbias, grid, d->cout, kdim, g.nt);
   return check_launch("wgrad_reduce_kernel");
 }
 

@@ -18,7 +18,16 @@ for _ in range(2):
 torch.cuda.synchronize()
 buf = torch.zeros(16 * 9, dtype=torch.int64, device="cuda")
 L.cgat_debug_timeline(ctypes.c_void_p(buf.data_ptr()))
-conv2d_nhwc(x, w, b, pad=(1, 1, 1, 1), impl=IMPL_TC)
+which = sys.argv[1] if len(sys.argv) > 1 else "fprop"
+if which == "fprop":
+    conv2d_nhwc(x, w, b, pad=(1, 1, 1, 1), impl=IMPL_TC)
+else:
+    xg = x.clone().requires_grad_(False)
+    wg = w.clone().requires_grad_()
+    y = conv2d_nhwc(xg, wg, b, pad=(1, 1, 1, 1), impl=IMPL_TC)
+    torch.cuda.synchronize()
+    buf.zero_()
+    y.backward(torch.rand_like(y))
 torch.cuda.synchronize()
 L.cgat_debug_timeline(None)
 t = buf.cpu().view(16, 9)
@@ -28,4 +37,4 @@ print("tile " + " ".join(f"{n:>9s}" for n in names))
 for i in range(16):
     if int(t[i, 0]) == 0:
         continue
-    print(f"{i:4d} " + " ".join(f"{int(v) - t0:9d}" for v in t[i]))
+    print(f"{i:4d} " + " ".join(f"{(int(v) - t0) if int(v) else 0:9d}" for v in t[i]))
