@@ -46,6 +46,7 @@ class ConvDesc(ctypes.Structure):
         ("ho", ctypes.c_int32), ("wo", ctypes.c_int32),
         ("dtype", ctypes.c_int32),
         ("act", ctypes.c_int32),
+        ("groups", ctypes.c_int32),
     ]
 
 

@@ -1,0 +1,63 @@
+"""``nn.Conv2d`` drop-in on the CUDA conv kernels (K1/K2/K3) for the conv stacks around the GAT layer.
+
+API and ``state_dict`` layout are those of ``torch.nn.Conv2d`` (``weight [cout, cin/groups, kh, kw]``, ``bias [cout]``),
+so the DCGAN nets (dcgan/model.py:19-179) and SmaAt-UNet keep their checkpoint keys.  Tensors keep PyTorch's
+NCHW *shape* but live in channels_last memory, which is exactly the NHWC layout the kernels take, so a stack of
+these layers (with BatchNorm / pooling from PyTorch in between) never transposes.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from .functional import IMPL_AUTO, conv2d_nhwc
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class Conv2d(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True, groups=1, act=0,
+                 impl=IMPL_AUTO):
+        super().__init__()
+        kh, kw = _pair(kernel_size)
+        sh, sw = _pair(stride)
+        if sh != sw:
+            raise ValueError("only equal strides are supported")
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, (kh, kw)
+        self.stride, self.groups, self.act, self.impl = sh, groups, act, impl
+        if padding == "same":
+            if sh != 1:
+                raise ValueError("padding='same' needs stride 1")
+            # PyTorch: total k-1, the extra element of an even kernel goes AFTER (left 1 / right 2 for k=4)
+            th, tw = kh - 1, kw - 1
+            self.pad = (th // 2, tw // 2, th - th // 2, tw - tw // 2)  # top, left, bottom, right
+        else:
+            ph, pw = _pair(padding)
+            self.pad = (ph, pw, ph, pw)
+        self.padding = padding
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels // groups, kh, kw))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):  # same init as torch.nn.Conv2d
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.weight.shape[1] * self.weight.shape[2] * self.weight.shape[3]
+            bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """``x[N, C, H, W]`` (any memory format) -> ``[N, C', H', W']`` in channels_last memory."""
+        x_nhwc = x.permute(0, 2, 3, 1)  # a view; contiguous iff x is channels_last
+        w_krsc = self.weight.permute(0, 2, 3, 1)
+        y = conv2d_nhwc(x_nhwc, w_krsc, self.bias, stride=self.stride, pad=self.pad, act=self.act, impl=self.impl,
+                        groups=self.groups)
+        return y.permute(0, 3, 1, 2)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, groups={self.groups}")

@@ -134,8 +134,8 @@ def adjacency_norm(B: torch.Tensor, transpose: bool = False) -> torch.Tensor:
 IMPL_DIRECT, IMPL_TC, IMPL_AUTO = 0, 1, -1
 
 
-def _conv_desc(n, h, w, cin, cout, kh, kw, stride, pad_top, pad_left, ho, wo, dtype, act=0) -> ConvDesc:
-    return ConvDesc(n, h, w, cin, cout, kh, kw, stride, pad_top, pad_left, ho, wo, dtype, act)
+def _conv_desc(n, h, w, cin, cout, kh, kw, stride, pad_top, pad_left, ho, wo, dtype, act=0, groups=1) -> ConvDesc:
+    return ConvDesc(n, h, w, cin, cout, kh, kw, stride, pad_top, pad_left, ho, wo, dtype, act, groups)
 
 
 def _pick(d: ConvDesc, which: int, impl: int) -> int:
@@ -159,20 +159,20 @@ class _Conv2dNHWC(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, pad, act, impl):
+    def forward(ctx, x, w, bias, stride, pad, act, impl, groups=1):
         require_cuda(x, w, bias)
         x = x.contiguous()
         n, h, wd, cin = x.shape
         cout, kh, kw, cin2 = w.shape
-        if cin != cin2:
-            raise RuntimeError(f"conv: input has {cin} channels, weight expects {cin2}")
+        if cin != cin2 * groups or cout % groups:
+            raise RuntimeError(f"conv: input has {cin} channels, weight expects {cin2} x {groups} groups")
         pt, pl, pb, pr = pad
         ho = (h + pt + pb - kh) // stride + 1
         wo = (wd + pl + pr - kw) // stride + 1
         dt = dtype_tag(x)
         wk = w.detach().to(x.dtype).contiguous()
         bk = None if bias is None else bias.detach().float().contiguous()
-        d = _conv_desc(n, h, wd, cin, cout, kh, kw, stride, pt, pl, ho, wo, dt, act)
+        d = _conv_desc(n, h, wd, cin, cout, kh, kw, stride, pt, pl, ho, wo, dt, act, groups)
         y = torch.empty(n, ho, wo, cout, device=x.device, dtype=x.dtype)
         im = _pick(d, 0, impl)
         ws = _workspace(d, 0, im, x.device)
@@ -211,12 +211,12 @@ class _Conv2dNHWC(torch.autograd.Function):
         ws = _workspace(d, 2, im, x.device)
         _lib.call("cgat_conv2d_wgrad", ctypes.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), im, ptr(ws), st,
                   launches=2 if db is not None else 1)
-        return dx, dw.to(ctx.w_dtype), db, None, None, None, None
+        return dx, dw.to(ctx.w_dtype), db, None, None, None, None, None
 
 
-def conv2d_nhwc(x, w_krsc, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, impl=IMPL_AUTO):
-    """NHWC convolution with KRSC weights through the CUDA kernels (no cuDNN)."""
-    return _Conv2dNHWC.apply(x, w_krsc, bias, stride, tuple(pad), act, impl)
+def conv2d_nhwc(x, w_krsc, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, impl=IMPL_AUTO, groups=1):
+    """NHWC convolution with KRSC weights ``[cout, kh, kw, cin/groups]`` through the CUDA kernels (no cuDNN)."""
+    return _Conv2dNHWC.apply(x, w_krsc, bias, stride, tuple(pad), act, impl, groups)
 
 
 # ----------------------------------------------------------------------------------------------

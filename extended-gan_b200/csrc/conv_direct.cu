@@ -36,15 +36,17 @@ __global__ void __launch_bounds__(CD_THREADS) conv_fprop_direct(const cgat_conv_
     const int ho = (int)(pix % d.ho);
     const int n = (int)(pix / d.ho);
     float acc = bias ? bias[co] : 0.f;
+    const int cing = d.cin / d.groups;                 // input channels per group
+    const int ci0 = (co / (d.cout / d.groups)) * cing;  // first input channel of this output's group
     for (int kh = 0; kh < d.kh; ++kh) {
       const int hi = ho * d.stride + kh - d.pad_top;
       if (hi < 0 || hi >= d.h) continue;
       for (int kw = 0; kw < d.kw; ++kw) {
         const int wi = wo * d.stride + kw - d.pad_left;
         if (wi < 0 || wi >= d.w) continue;
-        const T* xp = x + (((long long)n * d.h + hi) * d.w + wi) * d.cin;
-        const T* wp = w + (((long long)co * d.kh + kh) * d.kw + kw) * d.cin;
-        for (int ci = 0; ci < d.cin; ++ci) acc = fmaf(DT<T>::to_f(xp[ci]), DT<T>::to_f(wp[ci]), acc);
+        const T* xp = x + (((long long)n * d.h + hi) * d.w + wi) * d.cin + ci0;
+        const T* wp = w + (((long long)co * d.kh + kh) * d.kw + kw) * cing;
+        for (int ci = 0; ci < cing; ++ci) acc = fmaf(DT<T>::to_f(xp[ci]), DT<T>::to_f(wp[ci]), acc);
       }
     }
     y[idx] = DT<T>::from_f(apply_act(acc, d.act));
@@ -75,10 +77,12 @@ __global__ void __launch_bounds__(CD_THREADS) conv_dgrad_direct(const cgat_conv_
         if (wn < 0 || wn % d.stride) continue;
         const int wo = wn / d.stride;
         if (wo >= d.wo) continue;
-        const T* dyp = dy + (((long long)n * d.ho + ho) * d.wo + wo) * d.cout;
-        const T* wp = w + ((long long)kh * d.kw + kw) * d.cin + ci;
-        const long long wstride = (long long)d.kh * d.kw * d.cin;
-        for (int co = 0; co < d.cout; ++co) acc = fmaf(DT<T>::to_f(dyp[co]), DT<T>::to_f(wp[co * wstride]), acc);
+        const int cing = d.cin / d.groups, coutg = d.cout / d.groups;
+        const int g = ci / cing;
+        const T* dyp = dy + (((long long)n * d.ho + ho) * d.wo + wo) * d.cout + g * coutg;
+        const long long wstride = (long long)d.kh * d.kw * cing;
+        const T* wp = w + (long long)g * coutg * wstride + ((long long)kh * d.kw + kw) * cing + (ci - g * cing);
+        for (int co = 0; co < coutg; ++co) acc = fmaf(DT<T>::to_f(dyp[co]), DT<T>::to_f(wp[co * wstride]), acc);
       }
     }
     dx[idx] = DT<T>::from_f(acc);
@@ -93,17 +97,19 @@ __global__ void __launch_bounds__(CD_THREADS) conv_wgrad_direct(const cgat_conv_
   const int kw = blockIdx.x % d.kw;
   const int kh = (blockIdx.x / d.kw) % d.kh;
   const int co = blockIdx.x / (d.kw * d.kh);
-  extern __shared__ float s_acc[];  // [cin]
-  for (int ci = threadIdx.x; ci < d.cin; ci += blockDim.x) s_acc[ci] = 0.f;
+  extern __shared__ float s_acc[];  // [cin / groups]
+  const int cing = d.cin / d.groups;
+  const int ci_base = (co / (d.cout / d.groups)) * cing;
+  for (int ci = threadIdx.x; ci < cing; ci += blockDim.x) s_acc[ci] = 0.f;
   __syncthreads();
   const long long M = (long long)d.n * d.ho * d.wo;
   // thread -> (ci, pixel lane): ci fastest for coalesced x reads
-  const int lanes_ci = d.cin < CD_THREADS ? d.cin : CD_THREADS;
+  const int lanes_ci = cing < CD_THREADS ? cing : CD_THREADS;
   const int ci0 = threadIdx.x % lanes_ci;
   const int prow = threadIdx.x / lanes_ci;
   const int prows = CD_THREADS / lanes_ci;
   if (prow < prows) {
-    for (int ci = ci0; ci < d.cin; ci += lanes_ci) {
+    for (int ci = ci0; ci < cing; ci += lanes_ci) {
       float acc = 0.f;
       for (long long m = prow; m < M; m += prows) {
         const int wo = (int)(m % d.wo);
@@ -113,14 +119,14 @@ __global__ void __launch_bounds__(CD_THREADS) conv_wgrad_direct(const cgat_conv_
         const int wi = wo * d.stride + kw - d.pad_left;
         if (hi < 0 || hi >= d.h || wi < 0 || wi >= d.w) continue;
         acc = fmaf(DT<T>::to_f(dy[m * d.cout + co]),
-                   DT<T>::to_f(x[(((long long)n * d.h + hi) * d.w + wi) * d.cin + ci]), acc);
+                   DT<T>::to_f(x[(((long long)n * d.h + hi) * d.w + wi) * d.cin + ci_base + ci]), acc);
       }
       atomicAdd(&s_acc[ci], acc);
     }
   }
   __syncthreads();
-  for (int ci = threadIdx.x; ci < d.cin; ci += blockDim.x)
-    dw[(((long long)co * d.kh + kh) * d.kw + kw) * d.cin + ci] = s_acc[ci];
+  for (int ci = threadIdx.x; ci < cing; ci += blockDim.x)
+    dw[(((long long)co * d.kh + kh) * d.kw + kw) * cing + ci] = s_acc[ci];
 }
 
 template <typename T>
@@ -152,6 +158,8 @@ int validate_conv(const cgat_conv_desc* d) {
       d->ho < 1 || d->wo < 1 || d->pad_top < 0 || d->pad_left < 0)
     return fail(CGAT_EINVAL, "bad conv descriptor");
   if (d->dtype != CGAT_F32 && d->dtype != CGAT_BF16) return fail(CGAT_EINVAL, "bad conv dtype %d", d->dtype);
+  if (d->groups < 1 || d->cin % d->groups || d->cout % d->groups)
+    return fail(CGAT_EINVAL, "groups=%d must divide cin=%d and cout=%d", d->groups, d->cin, d->cout);
   // the last output row/col must start inside the padded input
   if ((d->ho - 1) * d->stride - d->pad_top >= d->h || (d->wo - 1) * d->stride - d->pad_left >= d->w)
     return fail(CGAT_EINVAL, "conv output %dx%d does not fit input %dx%d", d->ho, d->wo, d->h, d->w);
@@ -184,7 +192,7 @@ int conv_dgrad_direct_launch(const cgat_conv_desc* d, const void* dy, const void
 int conv_wgrad_direct_launch(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
                              cudaStream_t st) {
   const int blocks = d->cout * d->kh * d->kw;
-  const size_t smem = sizeof(float) * d->cin;
+  const size_t smem = sizeof(float) * (d->cin / d->groups);
   const long long M = (long long)d->n * d->ho * d->wo;
   if (d->dtype == CGAT_F32) {
     conv_wgrad_direct<float><<<blocks, CD_THREADS, smem, st>>>(*d, (const float*)x, (const float*)dy, dw);

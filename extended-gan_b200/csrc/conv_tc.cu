@@ -500,7 +500,7 @@ int conv_wgrad_tc_supported(const cgat_conv_desc* d);
 size_t conv_wgrad_tc_workspace(const cgat_conv_desc* d);
 
 int conv_tc_supported(const cgat_conv_desc* d, int which) {
-  if (d->dtype != CGAT_BF16 || d->stride != 1) return 0;
+  if (d->dtype != CGAT_BF16 || d->stride != 1 || d->groups != 1) return 0;
   if (which == 2) return conv_wgrad_tc_supported(d);
   // dgrad of a stride-1 conv is a stride-1 conv with cin/cout swapped and the kernel rotated
   const int gk = which == 0 ? d->cin : d->cout;   // GEMM-K channels
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 
 int conv_wgrad_tc_supported(const cgat_conv_desc* d) {
-  if (d->dtype != CGAT_BF16 || d->stride != 1) return 0;
+  if (d->dtype != CGAT_BF16 || d->stride != 1 || d->groups != 1) return 0;
   if (d->cin % 8 != 0 || d->cout % 8 != 0 || d->cout > 128) return 0;
   const WgGeom g = wgeom(d);
   if (g.nt > 256 || g.smem > 227 * 1024) return 0;

@@ -110,6 +110,7 @@ typedef struct cgat_conv_desc {
   int32_t ho, wo;         /* output [n][ho][wo][cout]   */
   int32_t dtype;          /* activations / weights dtype (CGAT_F32 or CGAT_BF16); bias fp32 */
   int32_t act;            /* fused epilogue: 0 none, 1 ReLU, 2 LeakyReLU(0.2), 3 sigmoid     */
+  int32_t groups;         /* 1 = dense; cin = cout-groups for depthwise (SmaAt-UNet). weight [cout][kh][kw][cin/groups] */
 } cgat_conv_desc;
 
 /* K1 fprop / K2 dgrad / K3 wgrad.  `impl`: 0 = direct CUDA-core kernel (any shape, no workspace),

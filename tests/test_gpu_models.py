@@ -1,0 +1,111 @@
+"""GPU parity of the conv stacks around the GAT layer: DCGAN nets vs golden vectors of the live reference,
+SmaAt-UNet / UnetModel vs the oracle restatement."""
+import pytest
+import torch
+
+from oracle import spec
+from util import close, golden, sd_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("name", ["G", "FD", "TD"])
+def test_dcgan_net_vs_reference_golden_fp32(name):
+    from dcgan.model import FrameDiscriminator, Generator, TemporalDiscriminator
+
+    fx = golden("dcgan_nets")
+    params = {"nc": fx["params.nc"], "ndf": fx["params.ndf"]}
+    cls = {"G": Generator, "FD": FrameDiscriminator, "TD": TemporalDiscriminator}[name]
+    net = cls(params)
+    net.load_state_dict(sd_of(fx, f"{name}.sd."))  # the reference's own state_dict keys
+    net = net.to(DEV).eval()
+    x, y = fx["x"], fx["y"]
+    inp = {"G": x, "FD": y, "TD": torch.cat((x, y), 1)}[name].to(DEV).requires_grad_()
+    out = net(inp)
+    close(out, fx[f"{name}.out"], rtol=1e-4, atol=1e-5, msg=f"{name} out")
+    out.backward(fx[f"{name}.g"].to(DEV))
+    close(inp.grad, fx[f"{name}.grad_in.inp"], rtol=1e-4, atol=1e-6, msg=f"{name} dx")
+    for k, p in net.named_parameters():
+        ref = fx[f"{name}.grad.{k}"]
+        close(p.grad, ref, rtol=1e-4, atol=1e-5 * max(1.0, ref.abs().max().item()), msg=f"{name} d{k}")
+
+
+def test_dcgan_generator_bf16_tensor_core_path():
+    """bf16 activations: layers with cin % 8 == 0 run on tcgen05 (IMPL_AUTO), the 4-channel ones on the direct kernel."""
+    from dcgan.model import Generator
+
+    fx = golden("dcgan_nets")
+    net = Generator({"nc": 4, "ndf": 8})
+    net.load_state_dict(sd_of(fx, "G.sd."))
+    net = net.to(DEV).eval()
+    x = fx["x"].bfloat16()
+    ref = spec.dcgan_generator(x.float(), sd_of(fx, "G.sd."))
+    out = net(x.to(DEV))
+    assert out.dtype == torch.bfloat16
+    close(out, ref, rtol=2e-2, atol=2e-2, msg="G bf16")
+
+
+def test_dcgan_train_mode_batchnorm_matches_oracle():
+    """Train-mode (batch statistics) forward with dropout disabled: parity with the oracle restatement."""
+    from dcgan.model import FrameDiscriminator
+
+    fx = golden("dcgan_nets")
+    net = FrameDiscriminator({"nc": 4, "ndf": 8})
+    sd = sd_of(fx, "FD.sd.")
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    y = fx["y"]
+    ref = spec.dcgan_frame_disc(y, sd, training=True)
+    close(net(y.to(DEV)), ref, rtol=1e-4, atol=1e-5, msg="FD train-mode")
+
+
+def test_smaat_unet_matches_oracle_fp32():
+    from convolutional_gat.GAT3D.smaat_unet.SmaAt_UNet import SmaAt_UNet
+
+    torch.manual_seed(3)
+    ref = spec.SpecSmaAtUNet(4, 4).eval()
+    ours = SmaAt_UNet(4, 4)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).eval()
+    assert sum(p.numel() for p in ours.parameters()) == 4_032_548  # compare_models/results/results.json:18
+    x = torch.rand(2, 4, 32, 32)
+    with torch.no_grad():
+        close(ours(x.to(DEV)), ref(x), rtol=1e-3, atol=1e-4, msg="SmaAt-UNet out")
+
+
+def test_unet_model_per_vertex_loop_and_grads():
+    from convolutional_gat.unet_model import UnetModel
+
+    torch.manual_seed(4)
+    ref = spec.SpecSmaAtUNet(4, 4).train()
+    ours = UnetModel(image_width=16, image_height=16, n_vertices=3, attention_type="unet")
+    ours.unet.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).train()
+    x = torch.rand(2, 16, 16, 4, 3)
+    xr = x.clone().requires_grad_()
+    out_r = spec.unet_model_forward(ref, xr)  # per-vertex BatchNorm statistics, V sequential running-stat updates
+    g = torch.rand_like(out_r) - 0.5
+    out_r.backward(g)
+    xo = x.to(DEV).requires_grad_()
+    out_o = ours(xo)
+    close(out_o, out_r.detach(), rtol=1e-3, atol=1e-4, msg="UnetModel out")
+    out_o.backward(g.to(DEV))
+    close(xo.grad, xr.grad, rtol=2e-3, atol=1e-5, msg="UnetModel dx")
+    # running statistics saw the same V sequential updates
+    close(ours.unet.inc.double_conv[1].running_mean, ref.inc.double_conv[1].running_mean, rtol=1e-4, atol=1e-6,
+          msg="running_mean")
+
+
+def test_model_registry_and_train_signature():
+    """train.py:198-205: model_classes[model_type](image_width=, image_height=, n_vertices=, attention_type=, mapping_type=)."""
+    from convolutional_gat.utils import model_classes
+
+    for mt in ("temporal", "spatial", "multi_stream"):
+        m = model_classes[mt](image_width=16, image_height=16, n_vertices=6, attention_type=mt, mapping_type="conv").to(DEV)
+        assert m.mapping_type == "conv"
+        x = torch.rand(2, 16, 16, 4, 6, device=DEV)
+        y_hat = m(x)
+        assert y_hat.shape == x.shape  # train.py:131 needs MSE(y_hat, y)
+        sd = m.state_dict()
+        m.load_state_dict(sd)
