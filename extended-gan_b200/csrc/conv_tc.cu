@@ -121,6 +121,7 @@ struct TcGeom {
   RowStage xs;
   size_t wbytes, stage_bytes, out_bytes, smem;
   int tiles_h, tiles_w, tiles;
+  int stages;  // halo stages that fit shared memory (2..TC_STAGES)
   uint32_t tmem_cols;
 };
 
@@ -137,7 +138,11 @@ static TcGeom geom(int n, int ho, int wo, int cin, int cout, int kh, int kw) {
   g.wbytes = (size_t)g.npairs * 2 * g.npad * 16;
   g.stage_bytes = (size_t)g.nchunk * g.chb + 128;  // +128: the odd last chunk's partner reads one unit further
   g.out_bytes = ((size_t)128 * cout * 2 + 127) & ~(size_t)127;
-  g.smem = 2048 + 1024 + g.wbytes + 2 * (size_t)g.xs.bytes + TC_STAGES * g.stage_bytes + 2 * g.out_bytes;
+  g.stages = TC_STAGES;
+  do {
+    g.smem = 2048 + 1024 + g.wbytes + 2 * (size_t)g.xs.bytes + g.stages * g.stage_bytes + 2 * g.out_bytes;
+  } while (g.smem > 227 * 1024 && --g.stages >= 2);
+  if (g.stages < 2) g.stages = 2;
   g.tiles_h = (ho + TC_TH - 1) / TC_TH;
   g.tiles_w = (wo + TC_TW - 1) / TC_TW;
   g.tiles = n * g.tiles_h * g.tiles_w;
@@ -243,7 +248,7 @@ struct ConvTcArgs {
   int kh, kw, pad_t, pad_l;
   int nchunk, taps, npairs, hp, wp, chb;
   int tiles_h, tiles_w, tiles;
-  int act;
+  int act, stages;
   uint32_t tmem_cols;
   uint32_t wbytes, stage_bytes, out_bytes;
   StageDesc xs;
@@ -279,7 +284,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
   unsigned char* s_w = smem + 3072;
   unsigned char* s_stag = s_w + A.wbytes;
   unsigned char* s_halo = s_stag + 2 * (size_t)A.xs.bytes;
-  unsigned char* s_out = s_halo + (size_t)TC_STAGES * A.stage_bytes;
+  unsigned char* s_out = s_halo + (size_t)A.stages * A.stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -309,7 +314,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
   // halo stages start zeroed: alignment padding / the odd tail's partner unit must hold finite numbers
   {
     uint4* p = reinterpret_cast<uint4*>(s_halo);
-    const int n16 = (int)((size_t)TC_STAGES * A.stage_bytes / 16);
+    const int n16 = (int)((size_t)A.stages * A.stage_bytes / 16);
     for (int i = threadIdx.x; i < n16; i += TC_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
@@ -365,7 +370,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
       fence_proxy_async_smem();
       if (ptid == 0) DBG(3);
       mbar_arrive(&full[stage]);
-      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == A.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == TC_MMA_WARP) {
     // ===================== MMA issuer =====================
@@ -396,7 +401,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
         umma_commit(&empty[stage]);  // halo stage reusable once these MMAs retire
         umma_commit(&tfull[acc]);    // accumulator ready for the epilogue
         DBG(6);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == A.stages) { stage = 0; phase ^= 1; }
         if (++acc == 2) { acc = 0; aphase ^= 1; }
       }
     }
@@ -554,6 +559,7 @@ static int launch_tc(const void* in, int n, int hi, int wi, int gk, const void* 
   A.nchunk = g.nchunk; A.taps = g.taps; A.npairs = g.npairs; A.hp = g.hp; A.wp = g.wp; A.chb = g.chb;
   A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles;
   A.act = act;
+  A.stages = g.stages;
   A.tmem_cols = g.tmem_cols;
   A.wbytes = (uint32_t)g.wbytes;
   A.stage_bytes = (uint32_t)g.stage_bytes;
