@@ -11,136 +11,10 @@
 //
 // Parameter gradients (W, a, adjacency) are reduced per CTA through shared memory and added to the
 // fp32 accumulators with one atomicAdd per value per CTA.
-#include "common.cuh"
-#include "attn_math.cuh"
+#include "attn_common.cuh"
+#include <cstdlib>
 
 namespace cgat {
-
-constexpr int TILE = 128;  // pixels per CTA == threads per CTA
-constexpr int MAX_HEADS = 8;
-
-struct AttnArgs {
-  const void* in;
-  void* out;         // fwd: out;  bwd: din
-  const void* dout;  // bwd only
-  const float* W;
-  const float* a;
-  const float* adj;
-  const uint8_t* mask;
-  const float* stats;
-  const float* bstats;
-  float* gW;
-  float* ga;
-  float* gadj;
-  float* stats_out;  // pixstats kernels
-  long long n_pix;
-  long long pix_per_sample;
-  int heads;
-  int merge;
-  int apply_elu;
-  float alpha;
-};
-
-// ---- record <-> register helpers ---------------------------------------------------------------
-// A "record" is NODES*C consecutive elements; (node, c) lives at c*NODES+node (spatial) or node*C+c.
-template <int NODES, int C, bool SPATIAL>
-__device__ __forceinline__ constexpr int rec_off(int node, int c) {
-  return SPATIAL ? (c * NODES + node) : (node * C + c);
-}
-
-template <int N, typename T>
-__device__ __forceinline__ void load_rec(const T* __restrict__ p, float (&r)[N]) {
-  constexpr int PER = 16 / sizeof(T);
-  static_assert(N % PER == 0, "record must be a multiple of 16 bytes");
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < N / PER; ++i) {
-    uint4 v = q[i];
-    if constexpr (sizeof(T) == 4) {
-      r[4 * i + 0] = __uint_as_float(v.x);
-      r[4 * i + 1] = __uint_as_float(v.y);
-      r[4 * i + 2] = __uint_as_float(v.z);
-      r[4 * i + 3] = __uint_as_float(v.w);
-    } else {
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        r[8 * i + 2 * k + 0] = __uint_as_float(w[k] << 16);
-        r[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-template <int N, typename T>
-__device__ __forceinline__ void store_rec(T* __restrict__ p, const float (&r)[N]) {
-  constexpr int PER = 16 / sizeof(T);
-  static_assert(N % PER == 0, "record must be a multiple of 16 bytes");
-  uint4* q = reinterpret_cast<uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < N / PER; ++i) {
-    uint4 v;
-    if constexpr (sizeof(T) == 4) {
-      v.x = __float_as_uint(r[4 * i + 0]);
-      v.y = __float_as_uint(r[4 * i + 1]);
-      v.z = __float_as_uint(r[4 * i + 2]);
-      v.w = __float_as_uint(r[4 * i + 3]);
-    } else {
-      v.x = pack_bf16x2(r[8 * i + 0], r[8 * i + 1]);
-      v.y = pack_bf16x2(r[8 * i + 2], r[8 * i + 3]);
-      v.z = pack_bf16x2(r[8 * i + 4], r[8 * i + 5]);
-      v.w = pack_bf16x2(r[8 * i + 6], r[8 * i + 7]);
-    }
-    q[i] = v;
-  }
-}
-
-template <int NODES, int C, bool SPATIAL>
-__device__ __forceinline__ void rec_to_mat(const float (&r)[NODES * C], float (&m)[NODES][C]) {
-#pragma unroll
-  for (int n = 0; n < NODES; ++n)
-#pragma unroll
-    for (int c = 0; c < C; ++c) m[n][c] = r[rec_off<NODES, C, SPATIAL>(n, c)];
-}
-template <int NODES, int C, bool SPATIAL>
-__device__ __forceinline__ void mat_to_rec(const float (&m)[NODES][C], float (&r)[NODES * C]) {
-#pragma unroll
-  for (int n = 0; n < NODES; ++n)
-#pragma unroll
-    for (int c = 0; c < C; ++c) r[rec_off<NODES, C, SPATIAL>(n, c)] = m[n][c];
-}
-
-// ---- shared-memory carve-up ----------------------------------------------------------------------
-template <int NODES, int CI, int CO>
-struct SmemParams {
-  float W[MAX_HEADS][CI * CO];
-  float a[MAX_HEADS][2 * CO];
-  float adj[MAX_HEADS][NODES * NODES];
-  uint64_t maskrow[NODES];
-};
-
-template <int NODES, int CI, int CO>
-__device__ __forceinline__ void load_params(SmemParams<NODES, CI, CO>& sp, const AttnArgs& A, bool need_W,
-                                            bool need_adj) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (need_W)
-    for (int i = tid; i < A.heads * CI * CO; i += nt) sp.W[i / (CI * CO)][i % (CI * CO)] = A.W[i];
-  for (int i = tid; i < A.heads * 2 * CO; i += nt) sp.a[i / (2 * CO)][i % (2 * CO)] = A.a[i];
-  if (need_adj)
-    for (int i = tid; i < A.heads * NODES * NODES; i += nt)
-      sp.adj[i / (NODES * NODES)][i % (NODES * NODES)] = A.adj[i];
-  if (tid < NODES) {
-    uint64_t m = 0;
-    for (int j = 0; j < NODES; ++j)
-      if (A.mask == nullptr || A.mask[tid * NODES + j] != 0) m |= (1ull << j);
-    sp.maskrow[tid] = m;
-  }
-}
 
 // ===================================================================================================
 // K4 forward
@@ -201,7 +75,7 @@ __global__ void __launch_bounds__(TILE) attn_fwd_kernel(const AttnArgs A) {
         load_rec<NODES * CO, T>(s_in + (size_t)tid * in_rec + k * IN_SUB, r);
         rec_to_mat<NODES, CO, SPATIAL>(r, Wh);
       } else {
-        project_linear<NODES, CI, CO>(X, sp.W[k], Wh);
+        project_linear<F32, NODES, CI, CO>(X, sp.W[k], Wh);
       }
       float z[NODES][CO];
 #pragma unroll
@@ -210,16 +84,16 @@ __global__ void __launch_bounds__(TILE) attn_fwd_kernel(const AttnArgs A) {
         for (int u = 0; u < CO; ++u) z[v][u] = 0.f;
       if (pixel_mode) {
         const float* st = A.stats + ((sample * heads + k) * 2) * (NODES * NODES);
-        attn_forward_pixel<NODES, CO, true>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st,
+        attn_forward_pixel<F32, NODES, CO, true>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st,
                                             st + NODES * NODES, z);
       } else {
-        attn_forward_pixel<NODES, CO, false>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, nullptr, nullptr, z);
+        attn_forward_pixel<F32, NODES, CO, false>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, nullptr, nullptr, z);
       }
       if (A.apply_elu) {
 #pragma unroll
         for (int v = 0; v < NODES; ++v)
 #pragma unroll
-          for (int u = 0; u < CO; ++u) z[v][u] = elu_fwd(z[v][u]);
+          for (int u = 0; u < CO; ++u) z[v][u] = elu_fwd<F32>(z[v][u]);
       }
       if (A.merge == CGAT_MERGE_MEAN) {
 #pragma unroll
@@ -344,7 +218,7 @@ __global__ void __launch_bounds__(TILE) attn_bwd_kernel(const AttnArgs A) {
         load_rec<NODES * CO, T>(s_in + (size_t)tid * in_rec + k * IN_SUB, r);
         rec_to_mat<NODES, CO, SPATIAL>(r, Wh);
       } else {
-        project_linear<NODES, CI, CO>(X, sp.W[k], Wh);
+        project_linear<F32, NODES, CI, CO>(X, sp.W[k], Wh);
       }
       const float* st = pixel_mode ? A.stats + ((sample * heads + k) * 2) * (NODES * NODES) : nullptr;
       // ---- recompute z, then dz = dout * scale * ELU'(z) ----
@@ -354,9 +228,9 @@ __global__ void __launch_bounds__(TILE) attn_bwd_kernel(const AttnArgs A) {
 #pragma unroll
         for (int u = 0; u < CO; ++u) z[v][u] = 0.f;
       if (pixel_mode)
-        attn_forward_pixel<NODES, CO, true>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st, st + NODES * NODES, z);
+        attn_forward_pixel<F32, NODES, CO, true>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st, st + NODES * NODES, z);
       else
-        attn_forward_pixel<NODES, CO, false>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, nullptr, nullptr, z);
+        attn_forward_pixel<F32, NODES, CO, false>(Wh, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, nullptr, nullptr, z);
       {
         float dz[NODES][CO];
         if (A.merge == CGAT_MERGE_MEAN || SPATIAL) {
@@ -375,7 +249,7 @@ __global__ void __launch_bounds__(TILE) attn_bwd_kernel(const AttnArgs A) {
         for (int v = 0; v < NODES; ++v)
 #pragma unroll
           for (int u = 0; u < CO; ++u)
-            z[v][u] = dz[v][u] * gscale * (A.apply_elu ? elu_grad(z[v][u]) : 1.f);
+            z[v][u] = dz[v][u] * gscale * (A.apply_elu ? elu_grad<F32>(z[v][u]) : 1.f);
       }
       // z now holds dz
       if constexpr (MODE == 1) {
@@ -383,7 +257,7 @@ __global__ void __launch_bounds__(TILE) attn_bwd_kernel(const AttnArgs A) {
 #pragma unroll
         for (int i = 0; i < NODES * NODES; ++i) dot[i] = 0.f;
         float dWh_unused[NODES][CO];
-        attn_backward_pixel<NODES, CO, true, 1>(Wh, z, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st,
+        attn_backward_pixel<F32, NODES, CO, true, 1>(Wh, z, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st,
                                                 st + NODES * NODES, nullptr, dWh_unused, nullptr, nullptr, dot);
 #pragma unroll
         for (int i = 0; i < NODES * NODES; ++i) mycol[i * TILE] = dot[i];
@@ -401,10 +275,10 @@ __global__ void __launch_bounds__(TILE) attn_bwd_kernel(const AttnArgs A) {
         for (int i = 0; i < NODES * NODES; ++i) g_adj[i] = 0.f;
         if (pixel_mode) {
           const float* bs = A.bstats + (sample * heads + k) * (NODES * NODES);
-          attn_backward_pixel<NODES, CO, true, 0>(Wh, z, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st,
+          attn_backward_pixel<F32, NODES, CO, true, 0>(Wh, z, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, st,
                                                   st + NODES * NODES, bs, dWh, g_a, g_adj, nullptr);
         } else {
-          attn_backward_pixel<NODES, CO, false, 0>(Wh, z, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, nullptr,
+          attn_backward_pixel<F32, NODES, CO, false, 0>(Wh, z, sp.a[k], sp.adj[k], sp.maskrow, A.alpha, nullptr,
                                                    nullptr, nullptr, dWh, g_a, g_adj, nullptr);
         }
 #pragma unroll
@@ -419,7 +293,7 @@ __global__ void __launch_bounds__(TILE) attn_bwd_kernel(const AttnArgs A) {
           float g_W[CI * CO];
 #pragma unroll
           for (int i = 0; i < CI * CO; ++i) g_W[i] = 0.f;
-          project_linear_bwd<NODES, CI, CO>(X, dWh, sp.W[k], dX, g_W);
+          project_linear_bwd<F32, NODES, CI, CO>(X, dWh, sp.W[k], dX, g_W);
 #pragma unroll
           for (int i = 0; i < CI * CO; ++i) mycol[(RL::WV + i) * TILE] = g_W[i];
         }
@@ -513,7 +387,7 @@ __global__ void __launch_bounds__(256) attn_pixstats_kernel(const AttnArgs A) {
       float X[NODES][CI];
       load_rec<NODES * CI, T>(base + p * in_rec, r);
       rec_to_mat<NODES, CI, SPATIAL>(r, X);
-      project_linear<NODES, CI, CO>(X, sp.W[k], Wh);
+      project_linear<F32, NODES, CI, CO>(X, sp.W[k], Wh);
     }
     float e[NODES][NODES];
     attn_logits_pixel<NODES, CO>(Wh, sp.a[k], sp.maskrow, A.alpha, e);
@@ -595,7 +469,7 @@ static int validate(const cgat_attn_desc* d, const void* in, const float* a) {
   return 0;
 }
 
-enum Op { OP_FWD, OP_BWD, OP_STATS, OP_BSTATS };
+using Op = AttnOp;
 
 template <int NODES, int CI, int CO, bool SPATIAL, bool PRE, typename T>
 static int launch(Op op, const cgat_attn_desc* d, const AttnArgs& A, cudaStream_t st) {
@@ -645,7 +519,17 @@ static int dispatch2(Op op, const cgat_attn_desc* d, const AttnArgs& A, cudaStre
 // Instantiated (nodes, ci, co, layout) combinations.  (6,4,4,spatial) and (4,6,6,temporal) are the
 // reference's KNMI graph (V=6 regions, T=4 frames: kmni_dataset/__main__.py:49-56, kmni_data_loader.py:91-93);
 // (8,4,4) / (4,8,8) cover an 8-node variant.  Other shapes are rejected with CGAT_EUNSUPPORTED.
+static bool h2_enabled() {
+  static int v = -1;
+  if (v < 0) v = std::getenv("CGAT_NO_H2") ? 0 : 1;
+  return v == 1;
+}
+
 static int dispatch(Op op, const cgat_attn_desc* d, const AttnArgs& A, cudaStream_t st) {
+  if (d->dtype == CGAT_BF16 && A.stats == nullptr && (op == OP_FWD || op == OP_BWD) && h2_enabled()) {
+    const int rc = attn_h2_launch(op, d, A, st);
+    if (rc != CGAT_EUNSUPPORTED) return rc;
+  }
   const bool sp = d->layout == CGAT_LAYOUT_SPATIAL;
   const int ci = d->proj == CGAT_PROJ_PRE ? d->co : d->ci;
   if (sp && d->nodes == 6 && ci == 4 && d->co == 4) return dispatch2<6, 4, 4, true>(op, d, A, st);

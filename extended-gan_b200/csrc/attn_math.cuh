@@ -1,14 +1,17 @@
 // Per-pixel graph-attention arithmetic shared by the fused forward (K4) and backward (K5) kernels.
 //
-// Everything here is register-resident math on compile-time sized arrays, written once as
-// __host__ __device__ templates so that the very same code can be compiled by the host compiler
-// into the test harness (tests/host_harness) and checked against the oracle on a CPU-only box
-// before any GPU time is spent.  The host instantiation is test infrastructure; the product
-// kernels live in attn_kernels.cu.
+// Everything here is register-resident math on compile-time sized arrays, written once as templates over an
+// arithmetic policy P:
+//   F32  one pixel per thread in fp32 (exact-parity path; also compiled by the HOST compiler into
+//        tests/host_harness so the CPU-only suite checks this very code against the oracle);
+//   H2   two pixels per thread packed in __half2 lanes (bf16 I/O fast path: the kernels are FP32-issue bound at
+//        V = 6, packing halves the instruction count per pixel; inputs are bf16 so fp16's 11-bit mantissa does
+//        not lose input precision, and the backward rescales every pixel's upstream gradient by a power of two
+//        to stay inside fp16's exponent range).
 //
 // Math (reference convolutional_gat/baseline_model.py:119-160):
 //   s1[i] = sum_u Wh[i][u] a[u]          s2[j] = sum_u Wh[j][u] a[CO+u]            (:128-129,162-169)
-//   e[i][j] = LeakyReLU_alpha(s1[i] + s2[j]);  masked entries -> -9e15             (:130)
+//   e[i][j] = LeakyReLU_alpha(s1[i] + s2[j]);  masked entries -> fill              (:130)
 //   att = softmax_j(e)  (neighbour)   or   exp(e - max_p) / sum_p  (pixel, :131)
 //   hp[i][u] = sum_j att[i][j] Wh[j][u]                                             (:145-152)
 //   z[v][u]  = sum_i hp[i][u] adj[i][v]                                             (:154-158)
@@ -18,14 +21,16 @@
 #include <cmath>
 
 #if defined(__CUDACC__)
+#include <cuda_fp16.h>
 #define CGAT_HD __host__ __device__ __forceinline__
+#define CGAT_D __device__ __forceinline__
 #else
 #define CGAT_HD inline
 #endif
 
 namespace cgat {
 
-constexpr float kMaskFill = -9e15f;
+constexpr float kMaskFill = -9e15f;  // pyGAT convention
 
 CGAT_HD float fast_exp(float x) {
 #if defined(__CUDA_ARCH__)
@@ -35,94 +40,130 @@ CGAT_HD float fast_exp(float x) {
 #endif
 }
 
-CGAT_HD float elu_fwd(float z) { return z > 0.f ? z : (fast_exp(z) - 1.f); }
-// derivative of ELU expressed through z
-CGAT_HD float elu_grad(float z) { return z > 0.f ? 1.f : fast_exp(z); }
-
-// Per-(sample, head) statistics of the pixel-axis soft-max: [i][j] -> (max, 1/sum)
-template <int NODES>
-struct PixelStats {
-  const float* mx;    // [NODES*NODES]
-  const float* rinv;  // [NODES*NODES]
+// ---- arithmetic policies ----------------------------------------------------------------------------------
+struct F32 {
+  using T = float;
+  static CGAT_HD T bc(float v) { return v; }
+  static CGAT_HD T zero() { return 0.f; }
+  static CGAT_HD T neg_inf() { return -INFINITY; }
+  static CGAT_HD T mask_fill() { return kMaskFill; }
+  static CGAT_HD T fma(T a, T b, T c) { return fmaf(a, b, c); }
+  static CGAT_HD T add(T a, T b) { return a + b; }
+  static CGAT_HD T sub(T a, T b) { return a - b; }
+  static CGAT_HD T mul(T a, T b) { return a * b; }
+  static CGAT_HD T max(T a, T b) { return fmaxf(a, b); }
+  static CGAT_HD T min(T a, T b) { return fminf(a, b); }
+  static CGAT_HD T exp(T a) { return fast_exp(a); }
+  static CGAT_HD T rcp(T a) { return 1.f / a; }
+  static CGAT_HD T gt0(T a) { return a > 0.f ? 1.f : 0.f; }  // 1 where a > 0 else 0
 };
 
+#if defined(__CUDACC__)
+struct H2 {
+  using T = __half2;
+  static CGAT_D T bc(float v) { return __float2half2_rn(v); }
+  static CGAT_D T zero() { return __float2half2_rn(0.f); }
+  static CGAT_D T neg_inf() { return __float2half2_rn(-65504.f); }
+  static CGAT_D T mask_fill() { return __float2half2_rn(-60000.f); }  // exp(fill - max) underflows to 0
+  static CGAT_D T fma(T a, T b, T c) { return __hfma2(a, b, c); }
+  static CGAT_D T add(T a, T b) { return __hadd2(a, b); }
+  static CGAT_D T sub(T a, T b) { return __hsub2(a, b); }
+  static CGAT_D T mul(T a, T b) { return __hmul2(a, b); }
+  static CGAT_D T max(T a, T b) { return __hmax2(a, b); }
+  static CGAT_D T min(T a, T b) { return __hmin2(a, b); }
+  static CGAT_D T exp(T a) { return h2exp(a); }
+  static CGAT_D T rcp(T a) { return h2rcp(a); }
+  static CGAT_D T gt0(T a) { return __hgt2(a, __float2half2_rn(0.f)); }
+};
+#endif
+
+// ELU and its derivative, branch-free:  ELU(z) = max(z,0) + exp(min(z,0)) - 1 ;  ELU'(z) = exp(min(z,0))
+template <typename P>
+CGAT_HD typename P::T elu_fwd(typename P::T z) {
+  return P::add(P::max(z, P::zero()), P::sub(P::exp(P::min(z, P::zero())), P::bc(1.f)));
+}
+template <typename P>
+CGAT_HD typename P::T elu_grad(typename P::T z) {
+  return P::exp(P::min(z, P::zero()));
+}
+
 // ---------------------------------------------------------------------------------------------
-// forward of one head on one pixel.  z is ACCUMULATED INTO (caller zeroes it), pre-ELU.
-// adj is row-major [i][v] (already transposed by the caller for the 1-D layer's convention).
-// maskrow[i] bit j set  <=>  edge (i,j) present.
-// att_out (optional, may be nullptr) receives att[i][j] for the backward.
+// forward of one head on one pixel (H2: two pixels).  z is ACCUMULATED INTO (caller zeroes it), pre-ELU.
+// a [2*CO], adj [NODES*NODES] row-major [i][v] (already transposed by the caller for the 1-D layer's
+// convention) are policy-typed broadcasts.  maskrow[i] bit j set  <=>  edge (i,j) present.
+// st_max / st_rinv: pixel-axis soft-max statistics (PIXEL mode only, F32 policy only).
 // ---------------------------------------------------------------------------------------------
-template <int NODES, int CO, bool PIXEL>
-CGAT_HD void attn_forward_pixel(const float (&Wh)[NODES][CO], const float* __restrict__ a,
-                                const float* __restrict__ adj, const uint64_t* __restrict__ maskrow,
-                                float alpha, const float* __restrict__ st_max,
-                                const float* __restrict__ st_rinv, float (&z)[NODES][CO]) {
-  float s1[NODES], s2[NODES];
+template <typename P, int NODES, int CO, bool PIXEL>
+CGAT_HD void attn_forward_pixel(const typename P::T (&Wh)[NODES][CO], const typename P::T* __restrict__ a,
+                                const typename P::T* __restrict__ adj, const uint64_t* __restrict__ maskrow,
+                                typename P::T alpha, const typename P::T* __restrict__ st_max,
+                                const typename P::T* __restrict__ st_rinv, typename P::T (&z)[NODES][CO]) {
+  using T = typename P::T;
+  T s1[NODES], s2[NODES];
 #pragma unroll
   for (int i = 0; i < NODES; ++i) {
-    float p = 0.f, q = 0.f;
+    T p = P::zero(), q = P::zero();
 #pragma unroll
     for (int u = 0; u < CO; ++u) {
-      p = fmaf(Wh[i][u], a[u], p);
-      q = fmaf(Wh[i][u], a[CO + u], q);
+      p = P::fma(Wh[i][u], a[u], p);
+      q = P::fma(Wh[i][u], a[CO + u], q);
     }
     s1[i] = p;
     s2[i] = q;
   }
 #pragma unroll
   for (int i = 0; i < NODES; ++i) {
-    float att[NODES];
+    T att[NODES];
     const uint64_t mrow = maskrow[i];
     if (PIXEL) {
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        float pre = s1[i] + s2[j];
-        float e = pre > 0.f ? pre : alpha * pre;
-        if (!((mrow >> j) & 1ull)) e = kMaskFill;
-        att[j] = fast_exp(e - st_max[i * NODES + j]) * st_rinv[i * NODES + j];
+        const T pre = P::add(s1[i], s2[j]);
+        T e = P::max(pre, P::mul(alpha, pre));
+        if (!((mrow >> j) & 1ull)) e = P::mask_fill();
+        att[j] = P::mul(P::exp(P::sub(e, st_max[i * NODES + j])), st_rinv[i * NODES + j]);
       }
     } else {
-      float m = -INFINITY;
+      T m = P::neg_inf();
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        float pre = s1[i] + s2[j];
-        float e = pre > 0.f ? pre : alpha * pre;
-        if (!((mrow >> j) & 1ull)) e = kMaskFill;
+        const T pre = P::add(s1[i], s2[j]);
+        T e = P::max(pre, P::mul(alpha, pre));
+        if (!((mrow >> j) & 1ull)) e = P::mask_fill();
         att[j] = e;
-        m = fmaxf(m, e);
+        m = P::max(m, e);
       }
-      float sum = 0.f;
+      T sum = P::zero();
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        att[j] = fast_exp(att[j] - m);
-        sum += att[j];
+        att[j] = P::exp(P::sub(att[j], m));
+        sum = P::add(sum, att[j]);
       }
-      const float r = 1.f / sum;
+      const T r = P::rcp(sum);
 #pragma unroll
-      for (int j = 0; j < NODES; ++j) att[j] *= r;
+      for (int j = 0; j < NODES; ++j) att[j] = P::mul(att[j], r);
     }
-    float hp[CO];
+    T hp[CO];
 #pragma unroll
     for (int u = 0; u < CO; ++u) {
-      float acc = 0.f;
+      T acc = P::zero();
 #pragma unroll
-      for (int j = 0; j < NODES; ++j) acc = fmaf(att[j], Wh[j][u], acc);
+      for (int j = 0; j < NODES; ++j) acc = P::fma(att[j], Wh[j][u], acc);
       hp[u] = acc;
     }
 #pragma unroll
     for (int v = 0; v < NODES; ++v) {
-      const float w = adj[i * NODES + v];
+      const T w = adj[i * NODES + v];
 #pragma unroll
-      for (int u = 0; u < CO; ++u) z[v][u] = fmaf(hp[u], w, z[v][u]);
+      for (int u = 0; u < CO; ++u) z[v][u] = P::fma(hp[u], w, z[v][u]);
     }
   }
 }
 
-// logits only (used by the pixel-softmax statistics pre-pass): e[i][j]
+// logits only (pixel-softmax statistics pre-pass, F32): e[i][j]
 template <int NODES, int CO>
 CGAT_HD void attn_logits_pixel(const float (&Wh)[NODES][CO], const float* __restrict__ a,
-                               const uint64_t* __restrict__ maskrow, float alpha,
-                               float (&e)[NODES][NODES]) {
+                               const uint64_t* __restrict__ maskrow, float alpha, float (&e)[NODES][NODES]) {
   float s1[NODES], s2[NODES];
 #pragma unroll
   for (int i = 0; i < NODES; ++i) {
@@ -154,136 +195,151 @@ CGAT_HD void attn_logits_pixel(const float (&Wh)[NODES][CO], const float* __rest
 // pixel mode: st_max/st_rinv as in the forward, st_dot[i][j] = sum_p att[i][j][p] dAtt[i][j][p].
 // MODE 0: full backward.  MODE 1: only accumulate dot[i][j] += att*dAtt (pixel-mode pre-pass).
 // ---------------------------------------------------------------------------------------------
-template <int NODES, int CO, bool PIXEL, int MODE>
-CGAT_HD void attn_backward_pixel(const float (&Wh)[NODES][CO], const float (&dz)[NODES][CO],
-                                 const float* __restrict__ a, const float* __restrict__ adj,
-                                 const uint64_t* __restrict__ maskrow, float alpha,
-                                 const float* __restrict__ st_max, const float* __restrict__ st_rinv,
-                                 const float* __restrict__ st_dot, float (&dWh)[NODES][CO],
-                                 float* __restrict__ g_a, float* __restrict__ g_adj,
-                                 float* __restrict__ dot_out) {
-  float s1[NODES], s2[NODES];
+template <typename P, int NODES, int CO, bool PIXEL, int MODE>
+CGAT_HD void attn_backward_pixel(const typename P::T (&Wh)[NODES][CO], const typename P::T (&dz)[NODES][CO],
+                                 const typename P::T* __restrict__ a, const typename P::T* __restrict__ adj,
+                                 const uint64_t* __restrict__ maskrow, typename P::T alpha,
+                                 const typename P::T* __restrict__ st_max, const typename P::T* __restrict__ st_rinv,
+                                 const typename P::T* __restrict__ st_dot, typename P::T (&dWh)[NODES][CO],
+                                 typename P::T* __restrict__ g_a, typename P::T* __restrict__ g_adj,
+                                 typename P::T* __restrict__ dot_out) {
+  using T = typename P::T;
+  T s1[NODES], s2[NODES];
 #pragma unroll
   for (int i = 0; i < NODES; ++i) {
-    float p = 0.f, q = 0.f;
+    T p = P::zero(), q = P::zero();
 #pragma unroll
     for (int u = 0; u < CO; ++u) {
-      p = fmaf(Wh[i][u], a[u], p);
-      q = fmaf(Wh[i][u], a[CO + u], q);
+      p = P::fma(Wh[i][u], a[u], p);
+      q = P::fma(Wh[i][u], a[CO + u], q);
     }
     s1[i] = p;
     s2[i] = q;
   }
-  float ds2[NODES];
+  T ds2[NODES];
 #pragma unroll
-  for (int j = 0; j < NODES; ++j) ds2[j] = 0.f;
+  for (int j = 0; j < NODES; ++j) ds2[j] = P::zero();
+  const T one_minus_alpha = P::sub(P::bc(1.f), alpha);
 
 #pragma unroll
   for (int i = 0; i < NODES; ++i) {
     // ---- recompute row i of the attention ----
-    float att[NODES];
-    float slope[NODES];
+    T att[NODES];
+    T slope[NODES];
     const uint64_t mrow = maskrow[i];
     if (PIXEL) {
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        float pre = s1[i] + s2[j];
-        slope[j] = pre > 0.f ? 1.f : alpha;
-        float e = pre * slope[j];
-        if (!((mrow >> j) & 1ull)) { e = kMaskFill; slope[j] = 0.f; }
-        att[j] = fast_exp(e - st_max[i * NODES + j]) * st_rinv[i * NODES + j];
+        const T pre = P::add(s1[i], s2[j]);
+        slope[j] = P::fma(one_minus_alpha, P::gt0(pre), alpha);
+        T e = P::mul(pre, slope[j]);
+        if (!((mrow >> j) & 1ull)) { e = P::mask_fill(); slope[j] = P::zero(); }
+        att[j] = P::mul(P::exp(P::sub(e, st_max[i * NODES + j])), st_rinv[i * NODES + j]);
       }
     } else {
-      float m = -INFINITY;
+      T m = P::neg_inf();
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        float pre = s1[i] + s2[j];
-        slope[j] = pre > 0.f ? 1.f : alpha;
-        float e = pre * slope[j];
-        if (!((mrow >> j) & 1ull)) { e = kMaskFill; slope[j] = 0.f; }
+        const T pre = P::add(s1[i], s2[j]);
+        slope[j] = P::fma(one_minus_alpha, P::gt0(pre), alpha);
+        T e = P::mul(pre, slope[j]);
+        if (!((mrow >> j) & 1ull)) { e = P::mask_fill(); slope[j] = P::zero(); }
         att[j] = e;
-        m = fmaxf(m, e);
+        m = P::max(m, e);
       }
-      float sum = 0.f;
+      T sum = P::zero();
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        att[j] = fast_exp(att[j] - m);
-        sum += att[j];
+        att[j] = P::exp(P::sub(att[j], m));
+        sum = P::add(sum, att[j]);
       }
-      const float r = 1.f / sum;
+      const T r = P::rcp(sum);
 #pragma unroll
-      for (int j = 0; j < NODES; ++j) att[j] *= r;
+      for (int j = 0; j < NODES; ++j) att[j] = P::mul(att[j], r);
     }
     // ---- dhp[u] = sum_v dz[v][u] adj[i][v];   g_adj[i][v] += sum_u hp[u] dz[v][u] ----
-    float dhp[CO];
+    T dhp[CO];
 #pragma unroll
-    for (int u = 0; u < CO; ++u) dhp[u] = 0.f;
+    for (int u = 0; u < CO; ++u) dhp[u] = P::zero();
     if (MODE == 0) {
-      float hp[CO];
+      T hp[CO];
 #pragma unroll
       for (int u = 0; u < CO; ++u) {
-        float acc = 0.f;
+        T acc = P::zero();
 #pragma unroll
-        for (int j = 0; j < NODES; ++j) acc = fmaf(att[j], Wh[j][u], acc);
+        for (int j = 0; j < NODES; ++j) acc = P::fma(att[j], Wh[j][u], acc);
         hp[u] = acc;
       }
 #pragma unroll
       for (int v = 0; v < NODES; ++v) {
-        float g = 0.f;
+        T g = g_adj[i * NODES + v];
 #pragma unroll
-        for (int u = 0; u < CO; ++u) g = fmaf(hp[u], dz[v][u], g);
-        g_adj[i * NODES + v] += g;
+        for (int u = 0; u < CO; ++u) g = P::fma(hp[u], dz[v][u], g);
+        g_adj[i * NODES + v] = g;
       }
     }
 #pragma unroll
     for (int v = 0; v < NODES; ++v) {
-      const float w = adj[i * NODES + v];
+      const T w = adj[i * NODES + v];
 #pragma unroll
-      for (int u = 0; u < CO; ++u) dhp[u] = fmaf(dz[v][u], w, dhp[u]);
+      for (int u = 0; u < CO; ++u) dhp[u] = P::fma(dz[v][u], w, dhp[u]);
     }
-    // ---- dAtt[j] = sum_u dhp[u] Wh[j][u] ----
-    float datt[NODES];
+    T de[NODES];
+    if (PIXEL) {
+      // ---- dAtt[j] = sum_u dhp[u] Wh[j][u];  pixel-axis soft-max backward uses the per-sample dot ----
+      T datt[NODES];
 #pragma unroll
-    for (int j = 0; j < NODES; ++j) {
-      float acc = 0.f;
+      for (int j = 0; j < NODES; ++j) {
+        T acc = P::zero();
 #pragma unroll
-      for (int u = 0; u < CO; ++u) acc = fmaf(dhp[u], Wh[j][u], acc);
-      datt[j] = acc;
-    }
-    if (MODE == 1) {
+        for (int u = 0; u < CO; ++u) acc = P::fma(dhp[u], Wh[j][u], acc);
+        datt[j] = acc;
+      }
+      if (MODE == 1) {
 #pragma unroll
-      for (int j = 0; j < NODES; ++j) dot_out[i * NODES + j] += att[j] * datt[j];
-      continue;
+        for (int j = 0; j < NODES; ++j) dot_out[i * NODES + j] = P::fma(att[j], datt[j], dot_out[i * NODES + j]);
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < NODES; ++j) de[j] = P::mul(att[j], P::sub(datt[j], st_dot[i * NODES + j]));
+    } else {
+      // ---- neighbour soft-max backward in CENTRED form:
+      //      de[j] = att[j] (dAtt[j] - sum_j' att[j'] dAtt[j']) = att[j] sum_u dhp[u] (Wh[j][u] - hp[u])
+      //      (hp = sum_j att[j] Wh[j] is the aggregated feature).  Subtracting before the multiply-accumulate
+      //      avoids the cancellation of two large dot products, which matters in the half2 path. ----
+      T hpc[CO];
+#pragma unroll
+      for (int u = 0; u < CO; ++u) {
+        T acc = P::zero();
+#pragma unroll
+        for (int j = 0; j < NODES; ++j) acc = P::fma(att[j], Wh[j][u], acc);
+        hpc[u] = acc;
+      }
+#pragma unroll
+      for (int j = 0; j < NODES; ++j) {
+        T acc = P::zero();
+#pragma unroll
+        for (int u = 0; u < CO; ++u) acc = P::fma(dhp[u], P::sub(Wh[j][u], hpc[u]), acc);
+        de[j] = P::mul(att[j], acc);
+      }
     }
     // ---- dWh[j][u] += att[j] dhp[u] ----
 #pragma unroll
     for (int j = 0; j < NODES; ++j)
 #pragma unroll
-      for (int u = 0; u < CO; ++u) dWh[j][u] = fmaf(att[j], dhp[u], dWh[j][u]);
-    // ---- soft-max backward ----
-    float de[NODES];
-    if (PIXEL) {
-#pragma unroll
-      for (int j = 0; j < NODES; ++j) de[j] = att[j] * (datt[j] - st_dot[i * NODES + j]);
-    } else {
-      float dot = 0.f;
-#pragma unroll
-      for (int j = 0; j < NODES; ++j) dot = fmaf(att[j], datt[j], dot);
-#pragma unroll
-      for (int j = 0; j < NODES; ++j) de[j] = att[j] * (datt[j] - dot);
-    }
+      for (int u = 0; u < CO; ++u) dWh[j][u] = P::fma(att[j], dhp[u], dWh[j][u]);
     // ---- LeakyReLU backward, ds1 / ds2 ----
-    float ds1 = 0.f;
+    T ds1 = P::zero();
 #pragma unroll
     for (int j = 0; j < NODES; ++j) {
-      const float dp = de[j] * slope[j];
-      ds1 += dp;
-      ds2[j] += dp;
+      const T dp = P::mul(de[j], slope[j]);
+      ds1 = P::add(ds1, dp);
+      ds2[j] = P::add(ds2[j], dp);
     }
 #pragma unroll
     for (int u = 0; u < CO; ++u) {
-      dWh[i][u] = fmaf(ds1, a[u], dWh[i][u]);
-      g_a[u] = fmaf(ds1, Wh[i][u], g_a[u]);
+      dWh[i][u] = P::fma(ds1, a[u], dWh[i][u]);
+      g_a[u] = P::fma(ds1, Wh[i][u], g_a[u]);
     }
   }
   if (MODE == 0) {
@@ -291,46 +347,48 @@ CGAT_HD void attn_backward_pixel(const float (&Wh)[NODES][CO], const float (&dz)
     for (int j = 0; j < NODES; ++j)
 #pragma unroll
       for (int u = 0; u < CO; ++u) {
-        dWh[j][u] = fmaf(ds2[j], a[CO + u], dWh[j][u]);
-        g_a[CO + u] = fmaf(ds2[j], Wh[j][u], g_a[CO + u]);
+        dWh[j][u] = P::fma(ds2[j], a[CO + u], dWh[j][u]);
+        g_a[CO + u] = P::fma(ds2[j], Wh[j][u], g_a[CO + u]);
       }
   }
 }
 
 // linear projection helpers (reference baseline_model.py:127  Wh = h @ W, W is [CI][CO] row-major)
-template <int NODES, int CI, int CO>
-CGAT_HD void project_linear(const float (&X)[NODES][CI], const float* __restrict__ W, float (&Wh)[NODES][CO]) {
+template <typename P, int NODES, int CI, int CO>
+CGAT_HD void project_linear(const typename P::T (&X)[NODES][CI], const typename P::T* __restrict__ W,
+                            typename P::T (&Wh)[NODES][CO]) {
 #pragma unroll
   for (int j = 0; j < NODES; ++j)
 #pragma unroll
     for (int u = 0; u < CO; ++u) {
-      float acc = 0.f;
+      typename P::T acc = P::zero();
 #pragma unroll
-      for (int t = 0; t < CI; ++t) acc = fmaf(X[j][t], W[t * CO + u], acc);
+      for (int t = 0; t < CI; ++t) acc = P::fma(X[j][t], W[t * CO + u], acc);
       Wh[j][u] = acc;
     }
 }
 
 // dX[j][t] += sum_u dWh[j][u] W[t][u];   g_W[t][u] += sum_j X[j][t] dWh[j][u]
-template <int NODES, int CI, int CO>
-CGAT_HD void project_linear_bwd(const float (&X)[NODES][CI], const float (&dWh)[NODES][CO],
-                                const float* __restrict__ W, float (&dX)[NODES][CI], float* __restrict__ g_W) {
+template <typename P, int NODES, int CI, int CO>
+CGAT_HD void project_linear_bwd(const typename P::T (&X)[NODES][CI], const typename P::T (&dWh)[NODES][CO],
+                                const typename P::T* __restrict__ W, typename P::T (&dX)[NODES][CI],
+                                typename P::T* __restrict__ g_W) {
 #pragma unroll
   for (int j = 0; j < NODES; ++j)
 #pragma unroll
     for (int t = 0; t < CI; ++t) {
-      float acc = dX[j][t];
+      typename P::T acc = dX[j][t];
 #pragma unroll
-      for (int u = 0; u < CO; ++u) acc = fmaf(dWh[j][u], W[t * CO + u], acc);
+      for (int u = 0; u < CO; ++u) acc = P::fma(dWh[j][u], W[t * CO + u], acc);
       dX[j][t] = acc;
     }
 #pragma unroll
   for (int t = 0; t < CI; ++t)
 #pragma unroll
     for (int u = 0; u < CO; ++u) {
-      float acc = g_W[t * CO + u];
+      typename P::T acc = g_W[t * CO + u];
 #pragma unroll
-      for (int j = 0; j < NODES; ++j) acc = fmaf(X[j][t], dWh[j][u], acc);
+      for (int j = 0; j < NODES; ++j) acc = P::fma(X[j][t], dWh[j][u], acc);
       g_W[t * CO + u] = acc;
     }
 }

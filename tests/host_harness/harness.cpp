@@ -15,13 +15,13 @@ static void run_fwd(int pixel_mode, long n_pix, const float* X, const float* W, 
   for (long p = 0; p < n_pix; ++p) {
     float x[NODES][CI], Wh[NODES][CO], z[NODES][CO];
     std::memcpy(x, X + p * NODES * CI, sizeof(x));
-    project_linear<NODES, CI, CO>(x, W, Wh);
+    project_linear<F32, NODES, CI, CO>(x, W, Wh);
     for (int v = 0; v < NODES; ++v)
       for (int u = 0; u < CO; ++u) z[v][u] = 0.f;
     if (pixel_mode)
-      attn_forward_pixel<NODES, CO, true>(Wh, a, adj, maskrow, alpha, st_max, st_rinv, z);
+      attn_forward_pixel<F32, NODES, CO, true>(Wh, a, adj, maskrow, alpha, st_max, st_rinv, z);
     else
-      attn_forward_pixel<NODES, CO, false>(Wh, a, adj, maskrow, alpha, nullptr, nullptr, z);
+      attn_forward_pixel<F32, NODES, CO, false>(Wh, a, adj, maskrow, alpha, nullptr, nullptr, z);
     std::memcpy(z_out + p * NODES * CO, z, sizeof(z));
   }
 }
@@ -32,7 +32,7 @@ static void run_logits(long n_pix, const float* X, const float* W, const float* 
   for (long p = 0; p < n_pix; ++p) {
     float x[NODES][CI], Wh[NODES][CO], e[NODES][NODES];
     std::memcpy(x, X + p * NODES * CI, sizeof(x));
-    project_linear<NODES, CI, CO>(x, W, Wh);
+    project_linear<F32, NODES, CI, CO>(x, W, Wh);
     attn_logits_pixel<NODES, CO>(Wh, a, maskrow, alpha, e);
     std::memcpy(e_out + p * NODES * NODES, e, sizeof(e));
   }
@@ -48,24 +48,24 @@ static void run_bwd(int pixel_mode, int mode, long n_pix, const float* X, const 
     float x[NODES][CI], Wh[NODES][CO], dz[NODES][CO], dWh[NODES][CO], dX[NODES][CI];
     std::memcpy(x, X + p * NODES * CI, sizeof(x));
     std::memcpy(dz, dZ + p * NODES * CO, sizeof(dz));
-    project_linear<NODES, CI, CO>(x, W, Wh);
+    project_linear<F32, NODES, CI, CO>(x, W, Wh);
     for (int v = 0; v < NODES; ++v)
       for (int u = 0; u < CO; ++u) dWh[v][u] = 0.f;
     for (int v = 0; v < NODES; ++v)
       for (int t = 0; t < CI; ++t) dX[v][t] = 0.f;
     if (mode == 1) {
-      attn_backward_pixel<NODES, CO, true, 1>(Wh, dz, a, adj, maskrow, alpha, st_max, st_rinv, nullptr, dWh, nullptr,
+      attn_backward_pixel<F32, NODES, CO, true, 1>(Wh, dz, a, adj, maskrow, alpha, st_max, st_rinv, nullptr, dWh, nullptr,
                                               nullptr, dot_out);
       continue;
     }
     float g_a[2 * CO] = {0}, g_adj[NODES * NODES] = {0}, g_W[CI * CO] = {0};
     if (pixel_mode)
-      attn_backward_pixel<NODES, CO, true, 0>(Wh, dz, a, adj, maskrow, alpha, st_max, st_rinv, st_dot, dWh, g_a, g_adj,
+      attn_backward_pixel<F32, NODES, CO, true, 0>(Wh, dz, a, adj, maskrow, alpha, st_max, st_rinv, st_dot, dWh, g_a, g_adj,
                                               nullptr);
     else
-      attn_backward_pixel<NODES, CO, false, 0>(Wh, dz, a, adj, maskrow, alpha, nullptr, nullptr, nullptr, dWh, g_a,
+      attn_backward_pixel<F32, NODES, CO, false, 0>(Wh, dz, a, adj, maskrow, alpha, nullptr, nullptr, nullptr, dWh, g_a,
                                                g_adj, nullptr);
-    project_linear_bwd<NODES, CI, CO>(x, dWh, W, dX, g_W);
+    project_linear_bwd<F32, NODES, CI, CO>(x, dWh, W, dX, g_W);
     std::memcpy(dX_out + p * NODES * CI, dX, sizeof(dX));
     for (int i = 0; i < 2 * CO; ++i) ga[i] += g_a[i];
     for (int i = 0; i < NODES * NODES; ++i) gadj[i] += g_adj[i];

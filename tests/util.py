@@ -16,3 +16,17 @@ def sd_of(fx, prefix="sd."):
 
 def close(a, b, rtol=1e-4, atol=1e-5, msg=""):
     torch.testing.assert_close(a.float().cpu(), b.float().cpu(), rtol=rtol, atol=atol, msg=lambda m: f"{msg}: {m}")
+
+
+def close_frac(a, b, rtol, atol, frac=0.999, msg=""):
+    """At least ``frac`` of the elements within ``rtol``/``atol``.
+
+    Used for bf16 GRADIENTS only: LeakyReLU's derivative is discontinuous at 0, so a logit within rounding error
+    of the kink takes the other slope than the fp32 oracle on a handful of pixels (observed < 0.05 %); every other
+    element must meet the north-star tolerance, and no element may be off by more than 25 % of the tensor's scale."""
+    a, b = a.float().cpu(), b.float().cpu()
+    err = (a - b).abs()
+    ok = err <= atol + rtol * b.abs()
+    got = ok.float().mean().item()
+    assert got >= frac, f"{msg}: only {got:.5f} of the elements within rtol={rtol} atol={atol:.3g} (max err {err.max():.4g})"
+    assert err.max().item() <= 0.25 * max(1.0, b.abs().max().item()), f"{msg}: outlier {err.max():.4g}"
