@@ -50,6 +50,13 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class StreamDesc(ctypes.Structure):
+    _fields_ = [
+        ("nodes", ctypes.c_int32), ("ci", ctypes.c_int32), ("co", ctypes.c_int32), ("heads", ctypes.c_int32),
+        ("layout", ctypes.c_int32), ("mapping", ctypes.c_int32), ("transpose_adj", ctypes.c_int32),
+    ]
+
+
 _P = ctypes.c_void_p
 _I = ctypes.c_int
 _I64 = ctypes.c_int64
@@ -68,6 +75,13 @@ SIGNATURES = {
     "cgat_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P],
     "cgat_conv_tc_supported": [ctypes.POINTER(ConvDesc), _I],
     "cgat_conv_workspace_bytes": [ctypes.POINTER(ConvDesc), _I],
+    "cgat_conv2d_fprop_packed": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P],
+    "cgat_conv2d_dgrad_packed": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P],
+    "cgat_conv2d_wgrad_partial": [ctypes.POINTER(ConvDesc), _P, _P, _P, ctypes.POINTER(ctypes.c_int32),
+                                  ctypes.POINTER(ctypes.c_int32), _P],
+    "cgat_stream_wpack_bytes": [ctypes.POINTER(StreamDesc), _I],
+    "cgat_stream_prepare": [ctypes.POINTER(StreamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cgat_stream_param_grads": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _I64, _F, _F, _I, _P],
     "cgat_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P],
     "cgat_cast": [_P, _I, _P, _I, _I64, _P],
@@ -91,6 +105,7 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
             fn.restype = ctypes.c_int
         L.cgat_conv_workspace_bytes.restype = ctypes.c_int64
+        L.cgat_stream_wpack_bytes.restype = ctypes.c_int64
         L.cgat_version.restype = ctypes.c_char_p
         L.cgat_last_error.restype = ctypes.c_char_p
         _lib = L
@@ -163,3 +178,11 @@ def call(name: str, *args, launches: int = 1):
         rc = fn(*args)
     LAUNCHES += launches
     check(rc, name)
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (``const float* const*`` of the C ABI); None entries become NULL."""
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr

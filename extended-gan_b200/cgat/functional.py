@@ -245,3 +245,123 @@ def adam_step_(param, grad, m, v, step_dev, lr, beta1=0.9, beta2=0.999, eps=1e-8
     require_cuda(param, grad, m, v, step_dev)
     _lib.call("cgat_adam_step", ptr(param), ptr(grad), ptr(m), ptr(v), ptr(step_dev), param.numel(), lr, beta1, beta2,
                                eps, weight_decay, grad_scale, stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# one conv-GAT stream end to end (prepare -> [conv fprop] -> attention; attention bwd -> [wgrad] -> param grads)
+# ----------------------------------------------------------------------------------------------
+# When True, parameter gradients are ACCUMULATED straight into the parameters' existing ``.grad`` buffers by the
+# param-grad kernel and autograd receives ``None`` for them (no per-parameter accumulate kernels).  TrainStep turns
+# this on: it owns a zeroed flat gradient buffer whose views are the ``.grad`` tensors.
+DIRECT_GRAD = False
+
+
+class _GATStreamFn(torch.autograd.Function):
+    """All heads of one stream.  ``params`` = per head (w, bias?, a, B): conv -> 4 tensors/head, linear -> 3."""
+
+    @staticmethod
+    def forward(ctx, x, cfg: AttnConfig, mapping: str, mask, *params):
+        require_cuda(x, *params)
+        N, H, W, T, V = x.shape
+        x = x.contiguous()
+        dev = x.device
+        conv = mapping == "conv"
+        per = 4 if conv else 3
+        heads = cfg.heads
+        ws = [params[per * k] for k in range(heads)]
+        bs = [params[per * k + 1] for k in range(heads)] if conv else None
+        as_ = [params[per * k + per - 2] for k in range(heads)]
+        Bs = [params[per * k + per - 1] for k in range(heads)]
+        sd = _lib.StreamDesc(cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, 1 if conv else 0, int(cfg.adj_transpose))
+        st = stream()
+        a_st = torch.empty(heads, 2 * cfg.co, device=dev, dtype=torch.float32)
+        adj = torch.empty(heads, cfg.nodes, cfg.nodes, device=dev, dtype=torch.float32)
+        need_dx = ctx.needs_input_grad[0]
+        wpack = wpack_d = bias_d = w_st = None
+        if conv:
+            wpack = torch.empty(lib().cgat_stream_wpack_bytes(ctypes.byref(sd), 0), dtype=torch.uint8, device=dev)
+            if need_dx:
+                wpack_d = torch.empty(lib().cgat_stream_wpack_bytes(ctypes.byref(sd), 1), dtype=torch.uint8, device=dev)
+            bias_d = torch.empty(heads * cfg.nodes * cfg.co, device=dev, dtype=torch.float32)
+        else:
+            w_st = torch.empty(heads, cfg.ci, cfg.co, device=dev, dtype=torch.float32)
+        _lib.call("cgat_stream_prepare", ctypes.byref(sd), _lib.ptr_array(ws), _lib.ptr_array(bs) if conv else None,
+                  _lib.ptr_array(as_), _lib.ptr_array(Bs), ptr(wpack), ptr(wpack_d), ptr(w_st), ptr(bias_d), ptr(a_st),
+                  ptr(adj), st)
+        n_pix = N * H * W
+        dt = dtype_tag(x)
+        mc = None if mask is None else mask.to(torch.uint8).contiguous()
+        cd = None
+        if conv:
+            cin, cout = T * V, heads * cfg.nodes * cfg.co
+            cd = _conv_desc(N, H, W, cin, cout, 3, 3, 1, 1, 1, H, W, dt, 0)
+            wh = torch.empty(n_pix, cout, device=dev, dtype=x.dtype)
+            _lib.call("cgat_conv2d_fprop_packed", ctypes.byref(cd), ptr(x), ptr(wpack), ptr(bias_d), ptr(wh), st)
+            inp = wh
+        else:
+            inp = x.view(n_pix, T * V)
+        d = cfg.desc(n_pix, dt)
+        out = torch.empty(n_pix, cfg.out_rec, device=dev, dtype=x.dtype)
+        _lib.call("cgat_attn_fwd", ctypes.byref(d), ptr(inp), ptr(out), ptr(w_st), ptr(a_st), ptr(adj), ptr(mc), None, st)
+        ctx.cfg, ctx.sd, ctx.cd, ctx.conv, ctx.shape = cfg, sd, cd, conv, (N, H, W, T, V)
+        ctx.params = params  # raw per-head parameters (pointers for the grad kernel; direct-grad targets)
+        ctx.save_for_backward(x, inp if conv else None, w_st, a_st, adj, mc, wpack_d)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg, sd, cd, conv = ctx.cfg, ctx.sd, ctx.cd, ctx.conv
+        x, wh, w_st, a_st, adj, mc, wpack_d = ctx.saved_tensors
+        N, H, W, T, V = ctx.shape
+        params = ctx.params
+        heads = cfg.heads
+        per = 4 if conv else 3
+        dev = x.device
+        st = stream()
+        dout = dout.contiguous()
+        n_pix = N * H * W
+        d = cfg.desc(n_pix, dtype_tag(x))
+        nW = 0 if conv else heads * cfg.ci * cfg.co
+        na, nadj = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes
+        acc = torch.zeros(nW + na + nadj, device=dev, dtype=torch.float32)
+        gW = acc[:nW] if nW else None
+        ga, gadj = acc[nW:nW + na], acc[nW + na:]
+        inp = wh if conv else x.view(n_pix, T * V)
+        din = torch.empty_like(inp)
+        _lib.call("cgat_attn_bwd", ctypes.byref(d), ptr(inp), ptr(dout), ptr(din), ptr(w_st), ptr(a_st), ptr(adj), ptr(mc),
+                  None, None, ptr(gW), ptr(ga), ptr(gadj), st)
+        dx = None
+        ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
+        wsp = None
+        if conv:
+            nbytes = lib().cgat_conv_workspace_bytes(ctypes.byref(cd), 2)
+            wsp = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("cgat_conv2d_wgrad_partial", ctypes.byref(cd), ptr(x), ptr(din), ptr(wsp), ctypes.byref(ncta),
+                      ctypes.byref(nt), st)
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                _lib.call("cgat_conv2d_dgrad_packed", ctypes.byref(cd), ptr(din), ptr(wpack_d), ptr(dx), st)
+        elif ctx.needs_input_grad[0]:
+            dx = din.view(N, H, W, T, V)
+        # ---- per-head parameter gradients: one launch, optionally straight into the .grad buffers ----
+        direct = DIRECT_GRAD and all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
+                                     for p in params)
+        if direct:
+            tg = [p.grad for p in params]
+        else:
+            tg = [torch.empty(p.shape, device=dev, dtype=torch.float32) for p in params]
+        g_w = [tg[per * k] for k in range(heads)]
+        g_b = [tg[per * k + 1] for k in range(heads)] if conv else None
+        g_a = [tg[per * k + per - 2] for k in range(heads)]
+        g_B = [tg[per * k + per - 1] for k in range(heads)]
+        Bs = [params[per * k + per - 1] for k in range(heads)]
+        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(gW), ptr(ga), ptr(gadj),
+                  _lib.ptr_array(Bs), _lib.ptr_array(g_w), _lib.ptr_array(g_b) if conv else None, _lib.ptr_array(g_a),
+                  _lib.ptr_array(g_B), int(direct), st)
+        grads = [None] * len(params) if direct else [g.to(p.dtype) for g, p in zip(tg, params)]
+        return (dx, None, None, None, *grads)
+
+
+def gat_stream(x, cfg: AttnConfig, mapping: str, mask, params):
+    """Fused stream op: ``x[N,H,W,T,V]`` -> pixel records ``[N*H*W, out_rec]``."""
+    return _GATStreamFn.apply(x, cfg, mapping, mask, *params)

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import AttnConfig, conv2d_nhwc, graph_attention, IMPL_AUTO
+from .functional import AttnConfig, conv2d_nhwc, gat_stream, graph_attention, IMPL_AUTO
 
 
 def _xavier(shape):
@@ -98,21 +98,36 @@ class _GATStream(nn.Module):
                 f"channels={ch}")
         layout = _lib.LAYOUT_SPATIAL if spatial else _lib.LAYOUT_TEMPORAL
         merge = _lib.MERGE_MEAN if self.head_merge == "mean" else _lib.MERGE_CONCAT
-        a = torch.stack([h.a.reshape(-1) for h in self.attentions])
-        B = torch.stack([h.B for h in self.attentions])
-        if self.mapping_type == "linear":
-            Wt = torch.stack([h.W for h in self.attentions])
-            inp = x.reshape(N * H * W, T * V)
-            proj = _lib.PROJ_LINEAR
+        conv = self.mapping_type == "conv"
+        fused = (self.softmax_axis == "neighbour" and all(p.dtype == torch.float32 for p in self.parameters())
+                 and (not conv or (x.dtype == torch.bfloat16 and self.conv_impl in (IMPL_AUTO,))
+                      and (T * V) % 8 == 0 and (self.nheads * nodes * self.co) % 8 == 0
+                      and self.nheads * nodes * self.co <= 128))
+        if fused:
+            # one prepare launch + kernels + one param-grad launch (functional._GATStreamFn)
+            cfg = AttnConfig(nodes=nodes, ci=self.ci, co=self.co, heads=self.nheads, layout=layout,
+                             proj=_lib.PROJ_PRE if conv else _lib.PROJ_LINEAR, merge=merge, pix_per_sample=H * W,
+                             alpha=self.alpha, softmax_axis="neighbour")
+            params = []
+            for h in self.attentions:
+                params += [h.conv.weight, h.conv.bias, h.a, h.B] if conv else [h.W, h.a, h.B]
+            out = gat_stream(x, cfg, self.mapping_type, self.adj_mask, params)
         else:
-            dense, bias = self._dense_conv_params(nodes)
-            wh = conv2d_nhwc(x.reshape(N, H, W, T * V), dense, bias, stride=1, pad=(1, 1, 1, 1), impl=self.conv_impl)
-            inp = wh.reshape(N * H * W, -1)
-            Wt = None
-            proj = _lib.PROJ_PRE
-        cfg = AttnConfig(nodes=nodes, ci=self.ci, co=self.co, heads=self.nheads, layout=layout, proj=proj, merge=merge,
-                         pix_per_sample=H * W, alpha=self.alpha, softmax_axis=self.softmax_axis)
-        out = graph_attention(inp, Wt, a, B, self.adj_mask, cfg)
+            a = torch.stack([h.a.reshape(-1) for h in self.attentions])
+            B = torch.stack([h.B for h in self.attentions])
+            if not conv:
+                Wt = torch.stack([h.W for h in self.attentions])
+                inp = x.reshape(N * H * W, T * V)
+                proj = _lib.PROJ_LINEAR
+            else:
+                dense, bias = self._dense_conv_params(nodes)
+                wh = conv2d_nhwc(x.reshape(N, H, W, T * V), dense, bias, stride=1, pad=(1, 1, 1, 1), impl=self.conv_impl)
+                inp = wh.reshape(N * H * W, -1)
+                Wt = None
+                proj = _lib.PROJ_PRE
+            cfg = AttnConfig(nodes=nodes, ci=self.ci, co=self.co, heads=self.nheads, layout=layout, proj=proj,
+                             merge=merge, pix_per_sample=H * W, alpha=self.alpha, softmax_axis=self.softmax_axis)
+            out = graph_attention(inp, Wt, a, B, self.adj_mask, cfg)
         hm = 1 if self.head_merge == "mean" else self.nheads
         if spatial:
             return out.view(N, H, W, hm * self.co, V)

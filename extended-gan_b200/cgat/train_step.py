@@ -21,6 +21,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from . import functional
 from .functional import adam_step_, loss_and_grad
 from .parallel import FlatParams
 
@@ -67,9 +68,13 @@ class TrainStep:
     def _fwd_bwd(self):
         self.flat_grad.zero_()
         self.loss.zero_()
-        out = self.model(self.x)
-        _, dy = loss_and_grad(out, self.y, self.lam, loss_out=self.loss)
-        out.backward(dy)
+        prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
+        try:
+            out = self.model(self.x)
+            _, dy = loss_and_grad(out, self.y, self.lam, loss_out=self.loss)
+            out.backward(dy)
+        finally:
+            functional.DIRECT_GRAD = prev
 
     def _capture(self):
         s = torch.cuda.Stream()

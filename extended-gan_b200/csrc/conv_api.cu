@@ -10,7 +10,9 @@ int conv_tc_supported(const cgat_conv_desc* d, int which);
 size_t conv_tc_workspace(const cgat_conv_desc* d, int which);
 int conv_fprop_tc_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, void*, cudaStream_t);
 int conv_dgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, void*, void*, cudaStream_t);
-int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, void*, cudaStream_t);
+int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, void*, cudaStream_t,
+                         int* ncta_out = nullptr, int* nt_out = nullptr);
+int conv_tc_packed_launch(const cgat_conv_desc*, int dgrad, const void*, const void*, const float*, void*, cudaStream_t);
 void set_debug_buffer(long long* p);
 }  // namespace cgat
 
@@ -63,4 +65,32 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
   if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 2, workspace)) return rc;
   return conv_wgrad_tc_launch(d, x, dy, dw, dbias, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int cgat_conv2d_fprop_packed(const cgat_conv_desc* d, const void* x, const void* wpack, const float* bias,
+                                        void* y, void* stream) {
+  if (int rc = validate_conv(d)) return rc;
+  if (!x || !wpack || !y) return fail(CGAT_EINVAL, "null x/wpack/y");
+  if (!conv_tc_supported(d, 0)) return fail(CGAT_EUNSUPPORTED, "tcgen05 fprop does not support this conv shape");
+  return conv_tc_packed_launch(d, 0, x, wpack, bias, y, (cudaStream_t)stream);
+}
+
+extern "C" int cgat_conv2d_dgrad_packed(const cgat_conv_desc* d, const void* dy, const void* wpack, void* dx,
+                                        void* stream) {
+  if (int rc = validate_conv(d)) return rc;
+  if (!dy || !wpack || !dx) return fail(CGAT_EINVAL, "null dy/wpack/dx");
+  if (!conv_tc_supported(d, 1)) return fail(CGAT_EUNSUPPORTED, "tcgen05 dgrad does not support this conv shape");
+  return conv_tc_packed_launch(d, 1, dy, wpack, nullptr, dx, (cudaStream_t)stream);
+}
+
+extern "C" int cgat_conv2d_wgrad_partial(const cgat_conv_desc* d, const void* x, const void* dy, void* workspace,
+                                         int32_t* ncta_out, int32_t* nt_out, void* stream) {
+  if (int rc = validate_conv(d)) return rc;
+  if (!x || !dy || !workspace || !ncta_out || !nt_out) return fail(CGAT_EINVAL, "null argument");
+  if (int rc = tc_ready(d, 2, workspace)) return rc;
+  int ncta = 0, nt = 0;
+  const int rc = conv_wgrad_tc_launch(d, x, dy, nullptr, nullptr, workspace, (cudaStream_t)stream, &ncta, &nt);
+  *ncta_out = ncta;
+  *nt_out = nt;
+  return rc;
 }

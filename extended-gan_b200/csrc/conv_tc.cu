@@ -534,13 +534,13 @@ static StageDesc to_dev(const RowStage& s) { return StageDesc{s.rl, s.boxe, s.nb
 // generic stride-1 launch: input [n][hi][wi][gk] -> output [n][hout][wout][gn]
 static int launch_tc(const void* in, int n, int hi, int wi, int gk, const void* w_krsc, int w_cin, int dgrad, int kh,
                      int kw, int pad_t, int pad_l, int hout, int wout, int gn, const float* bias, int act, void* out,
-                     void* workspace, cudaStream_t st) {
+                     void* workspace, cudaStream_t st, bool prepacked = false) {
   if (!aligned16(in) || !aligned16(out) || !aligned16(workspace))
     return fail(CGAT_EALIGN, "conv tensors / workspace must be 16-byte aligned");
   const TcGeom g = geom(n, hout, wout, gk, gn, kh, kw);
   CUtensorMap map;
   if (int rc = make_rows_map(&map, in, n, hi, wi, gk, g.xs.boxe, g.xs.rows)) return rc;
-  {
+  if (!prepacked) {
     const long long total = (long long)g.npairs * 2 * g.npad * 8;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
@@ -576,6 +576,16 @@ int conv_fprop_tc_launch(const cgat_conv_desc* d, const void* x, const void* w, 
                          void* workspace, cudaStream_t st) {
   return launch_tc(x, d->n, d->h, d->w, d->cin, w, d->cin, 0, d->kh, d->kw, d->pad_top, d->pad_left, d->ho, d->wo,
                    d->cout, bias, d->act, y, workspace, st);
+}
+
+// weights already in the packed chunk-major UMMA order (cgat_stream_prepare); `dgrad` selects the geometry
+int conv_tc_packed_launch(const cgat_conv_desc* d, int dgrad, const void* in, const void* wpack, const float* bias,
+                          void* out, cudaStream_t st) {
+  if (!dgrad)
+    return launch_tc(in, d->n, d->h, d->w, d->cin, nullptr, d->cin, 0, d->kh, d->kw, d->pad_top, d->pad_left, d->ho,
+                     d->wo, d->cout, bias, d->act, out, const_cast<void*>(wpack), st, true);
+  return launch_tc(in, d->n, d->ho, d->wo, d->cout, nullptr, d->cin, 1, d->kh, d->kw, d->kh - 1 - d->pad_top,
+                   d->kw - 1 - d->pad_left, d->h, d->w, d->cin, nullptr, 0, out, const_cast<void*>(wpack), st, true);
 }
 
 int conv_dgrad_tc_launch(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, void* workspace,
@@ -866,7 +876,7 @@ size_t conv_wgrad_tc_workspace(const cgat_conv_desc* d) {
 }
 
 int conv_wgrad_tc_launch(const cgat_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
-                         void* workspace, cudaStream_t st) {
+                         void* workspace, cudaStream_t st, int* ncta_out, int* nt_out) {
   if (!aligned16(x) || !aligned16(dy) || !aligned16(workspace))
     return fail(CGAT_EALIGN, "conv tensors / workspace must be 16-byte aligned");
   const WgGeom g = wgeom(d);
@@ -888,6 +898,11 @@ int conv_wgrad_tc_launch(const cgat_conv_desc* d, const void* x, const void* dy,
   if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   conv_wgrad_tc_kernel<<<grid, WG_THREADS, g.smem, st>>>(mx, mdy, A);
   if (int rc = check_launch("conv_wgrad_tc_kernel")) return rc;
+  if (ncta_out != nullptr) {  // caller reduces the partial sums itself
+    *ncta_out = grid;
+    *nt_out = g.nt;
+    return 0;
+  }
   const int kdim = g.taps * d->cin;
   const int total = d->cout * kdim + (dbias ? d->cout : 0);
   wgrad_reduce_kernel<<<(total + 63) / 64, 256, 0, st>>>((const float*)workspace, dw, dbias, grid, d->cout, kdim, g.nt);

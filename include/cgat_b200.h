@@ -127,6 +127,38 @@ int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const void* dy, fl
 int cgat_conv_tc_supported(const cgat_conv_desc* d, int which /*0 fprop,1 dgrad,2 wgrad*/);
 int64_t cgat_conv_workspace_bytes(const cgat_conv_desc* d, int which);
 
+/* Variants used by the fused conv-GAT stream: fprop with weights already packed by cgat_stream_prepare (no
+ * per-call packing launch), and wgrad that leaves its per-CTA partial sums [ncta][128][nt] in `workspace`
+ * (reduced by cgat_stream_param_grads together with the block-diagonal contraction).                         */
+int cgat_conv2d_fprop_packed(const cgat_conv_desc* d, const void* x, const void* wpack, const float* bias, void* y,
+                             void* stream);
+int cgat_conv2d_dgrad_packed(const cgat_conv_desc* d, const void* dy, const void* wpack, void* dx, void* stream);
+int cgat_conv2d_wgrad_partial(const cgat_conv_desc* d, const void* x, const void* dy, void* workspace,
+                              int32_t* ncta_out, int32_t* nt_out, void* stream);
+
+/* One conv-GAT stream's parameter plumbing (heads of baseline_model.py:191-192 style sub-modules `attention_{k}`).
+ * mapping 0: linear (w[k] = W [ci][co]); mapping 1: conv (w[k] = conv.weight [co][ci][3][3], bias[k] = conv.bias).
+ * The arrays w/bias/a/B/g_* are HOST arrays of `heads` device pointers.                                        */
+typedef struct cgat_stream_desc {
+  int32_t nodes, ci, co, heads;
+  int32_t layout;        /* CGAT_LAYOUT_*                                  */
+  int32_t mapping;       /* 0 linear, 1 conv 3x3 pad 1                      */
+  int32_t transpose_adj; /* 1: the 1-D layer's A_hat^T (baseline_model.py:53) */
+} cgat_stream_desc;
+
+/* bytes of the packed bf16 weight buffer of the block-diagonal dense conv (dgrad != 0: the dgrad packing) */
+int64_t cgat_stream_wpack_bytes(const cgat_stream_desc* d, int dgrad);
+/* ONE launch: stack a, normalise the adjacency of every head (baseline_model.py:41-50), and either stack W
+ * (linear) or expand + pack the conv weights and bias (conv).  wpack_dgrad may be NULL.                       */
+int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const float* const* bias,
+                        const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
+                        float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* stream);
+/* ONE launch: per-head parameter gradients from the kernels' accumulators (wgrad partials or gW, ga, gadj);
+ * accumulate != 0 adds into g_* (e.g. the parameters' .grad buffers) instead of overwriting.                  */
+int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* gW_lin,
+                            const float* ga, const float* gadj, const float* const* B, float* const* g_w,
+                            float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate, void* stream);
+
 /* a12  train-step pieces, convolutional_gat/train.py:131 and :212.
  * loss = mean((yhat-y)^2) - lambda*mean(yhat); writes dloss/dyhat (same dtype as yhat) and
  * ACCUMULATES the scalar loss into loss_out[0] (fp32; caller zeroes).                              */

@@ -138,8 +138,10 @@ def test_gat3d_linear_pixel_softmax_fp32(type_):
 @pytest.mark.parametrize("merge", ["mean", "concat"])
 def test_gat3d_linear_bf16(type_, merge):
     ours, ref = _pair(type_, "linear", 3, merge, "neighbour", False, seed=13)
-    x = torch.rand(2, 16, 16, 4, 6).bfloat16().float()  # bf16-representable inputs; oracle runs fp32 on them
-    _check(ours, ref, x, torch.bfloat16, 2e-2, 2e-2, 2e-2)
+    x = torch.rand(4, 32, 32, 4, 6).bfloat16().float()  # bf16-representable inputs; oracle runs fp32 on them
+    # parameter gradients are sums over pixels: LeakyReLU' kink flips on isolated pixels (util.close_frac) move them
+    # by O(1/n_pix) each, hence the slightly wider absolute slack (relative to the largest gradient entry)
+    _check(ours, ref, x, torch.bfloat16, 2e-2, 2e-2, 4e-2)
 
 
 @pytest.mark.parametrize("type_", ["spatial", "temporal", "multi_stream"])
