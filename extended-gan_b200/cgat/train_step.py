@@ -40,6 +40,7 @@ class TrainStep:
         self.loss = torch.zeros(1, device=self.device, dtype=torch.float32)
         self.step_count = torch.zeros(1, device=self.device, dtype=torch.int64)
         self.graph = None
+        self._slots = None  # double-buffered inputs for pipelined host->device loading (enable_prefetch)
         self._flatten()
         if use_graph:
             self._capture()
@@ -108,3 +109,45 @@ class TrainStep:
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.load_batch(x, y)
         return self.run()
+
+    # -- pipelined loading: batch i+1 crosses PCIe on a copy stream while batch i trains ------------------
+    def enable_prefetch(self):
+        """Two input slots, each with its own captured graph, plus a copy stream and the events that order them."""
+        if self._slots is not None:
+            return
+        if self.graph is None:
+            raise RuntimeError("enable_prefetch needs use_graph=True")
+        slot0 = dict(x=self.x, y=self.y, graph=self.graph)
+        self.x, self.y = torch.empty_like(self.x), torch.empty_like(self.y)
+        self.x.copy_(slot0["x"])
+        self.y.copy_(slot0["y"])
+        self._capture()
+        slot1 = dict(x=self.x, y=self.y, graph=self.graph)
+        self._slots = [slot0, slot1]
+        for s in self._slots:
+            s["ready"] = torch.cuda.Event()   # inputs of this slot have landed
+            s["free"] = torch.cuda.Event()    # the step that read this slot has finished
+            s["free"].record()
+        self.copy_stream = torch.cuda.Stream()
+
+    def prefetch(self, x_host: torch.Tensor, y_host: torch.Tensor, slot: int):
+        """Asynchronous pinned-host -> device copy of one batch into ``slot`` on the copy stream."""
+        s = self._slots[slot]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["free"])
+            s["x"].copy_(x_host, non_blocking=True)
+            s["y"].copy_(y_host, non_blocking=True)
+            s["ready"].record(self.copy_stream)
+
+    def run_slot(self, slot: int) -> torch.Tensor:
+        """One optimisation step on the batch previously prefetched into ``slot``."""
+        s = self._slots[slot]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(s["ready"])
+        s["graph"].replay()
+        s["free"].record(cur)
+        self.flat.all_reduce_grads(self.pg)
+        self.step_count += 1
+        adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                   self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        return self.loss
