@@ -71,7 +71,14 @@ struct H2 {
   static CGAT_D T mul(T a, T b) { return __hmul2(a, b); }
   static CGAT_D T max(T a, T b) { return __hmax2(a, b); }
   static CGAT_D T min(T a, T b) { return __hmin2(a, b); }
-  static CGAT_D T exp(T a) { return h2exp(a); }
+  // e^x = 2^(x*log2 e) with ONE ex2.approx.f16x2 (h2exp() wraps the same instruction in ~10 fix-up instructions
+  // for special values that cannot occur here: arguments are <= 0 after the max subtraction / min(z,0))
+  static CGAT_D T exp(T a) {
+    const T y = __hmul2(a, __float2half2_rn(1.4426950408889634f));
+    uint32_t in = *reinterpret_cast<const uint32_t*>(&y), out;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(out) : "r"(in));
+    return *reinterpret_cast<T*>(&out);
+  }
   static CGAT_D T rcp(T a) { return h2rcp(a); }
   static CGAT_D T gt0(T a) { return __hgt2(a, __float2half2_rn(0.f)); }
 };

@@ -25,17 +25,18 @@
 //    in shared memory for the whole persistent CTA;
 //  * accumulators live in TMEM (2 stages x NPAD columns); the epilogue warps read them with tcgen05.ld,
 //    add bias, apply the activation and store bf16 NHWC, overlapping the next tile's MMAs.
-// Warp roles: warps 0-3 = re-layout, warp 4 = MMA issuer (one thread) + TMEM allocator, warps 5-8 = epilogue,
-// warp 9 = TMA issuer (one thread).
+// Warp roles: warps 0-3 = re-layout, warp 4 = MMA issuer (one thread) + TMEM allocator, warps 5-8 and 10-13 = two
+// epilogue groups (one per TMEM accumulator stage), warp 9 = TMA issuer (one thread).
 #include "tc_common.cuh"
 
 namespace cgat {
 
 constexpr int TC_TH = 16, TC_TW = 8;  // output tile (rows x cols) -> M = 128
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;
 constexpr int TC_PROD = 128;          // re-layout threads (warps 0-3)
 constexpr int TC_MMA_WARP = 4;
 constexpr int TC_TMA_WARP = 9;        // issues the TMA row loads (kept off the re-layout warps' critical path)
+// epilogue group 0 = warps 5-8, group 1 = warps 10-13; group g drains accumulator stage g (tiles it % 2 == g)
 constexpr int TC_STAGES = 4;
 
 // ---- host helpers --------------------------------------------------------------------------------
@@ -406,21 +407,24 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
       }
     }
   } else {
-    // ===================== epilogue (warps 5..8 -> TMEM lane groups 1,2,3,0) =====================
+    // ===================== epilogue: group 0 = warps 5..8, group 1 = warps 10..13 =====================
+    // (any 4 consecutive warps cover the 4 TMEM lane quarters: warp % 4)
+    const int grp = warp > TC_TMA_WARP ? 1 : 0;
     const int lg = warp & 3;
     const int m = lg * 32 + lane;  // accumulator row = pixel of the tile
-    const int etid = threadIdx.x - (TC_MMA_WARP + 1) * 32;
+    const int etid = threadIdx.x - (grp ? (TC_TMA_WARP + 1) : (TC_MMA_WARP + 1)) * 32;
     const int hrow = m >> 3, wcol = m & 7;
     const bool staged = (A.cout & 7) == 0;  // coalesced path: tile -> shared memory -> bulk stores per image row
-    int acc = 0, it = 0;
+    const int acc = grp;  // this group's accumulator stage
+    int it = grp;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < A.tiles; tile += 2 * gridDim.x, it += 2) {
       const int tw = tile % A.tiles_w;
       const int th = (tile / A.tiles_w) % A.tiles_h;
       const int n = tile / (A.tiles_w * A.tiles_h);
       const int h = th * TC_TH + hrow, w = tw * TC_TW + wcol;
       const bool valid = h < A.ho && w < A.wo;
-      unsigned char* ob = s_out + (size_t)(it & 1) * A.out_bytes;
+      unsigned char* ob = s_out + (size_t)grp * A.out_bytes;
       mbar_wait(&tfull[acc], aphase);
       if (m == 0) DBG(7);
       tc_fence_after();
@@ -472,7 +476,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
       if (staged) {
         // tile is complete in shared memory: all 128 threads stream it out, one contiguous image row segment
         // (wvalid * cout bf16) at a time, consecutive threads -> consecutive 16-byte chunks
-        named_bar_sync(2, 128);
+        named_bar_sync(2 + grp, 128);
         const int w0 = tw * TC_TW;
         const int wvalid = min(TC_TW, A.wo - w0);
         const int row_u4 = wvalid * A.cout / 8;        // uint4 per valid row segment
@@ -489,7 +493,8 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvTcArg
         // the buffer is reused two tiles later; the barrier at the top of that iteration orders these reads
       }
       if (m == 0) DBG(8);
-      if (++acc == 2) { acc = 0; aphase ^= 1; }
+      aphase ^= 1;
+      if (staged) named_bar_sync(2 + grp, 128);  // everyone has read the staging tile before it is rewritten
     }
   }
   tc_fence_before();
