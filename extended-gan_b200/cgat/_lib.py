@@ -82,6 +82,8 @@ SIGNATURES = {
     "cgat_stream_wpack_bytes": [ctypes.POINTER(StreamDesc), _I],
     "cgat_stream_prepare": [ctypes.POINTER(StreamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "cgat_stream_param_grads": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cgat_gat1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "cgat_gat1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _I64, _F, _F, _I, _P],
     "cgat_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P],
     "cgat_cast": [_P, _I, _P, _I, _I64, _P],

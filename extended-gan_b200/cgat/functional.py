@@ -365,3 +365,76 @@ class _GATStreamFn(torch.autograd.Function):
 def gat_stream(x, cfg: AttnConfig, mapping: str, mask, params):
     """Fused stream op: ``x[N,H,W,T,V]`` -> pixel records ``[N*H*W, out_rec]``."""
     return _GATStreamFn.apply(x, cfg, mapping, mask, *params)
+
+
+# ----------------------------------------------------------------------------------------------
+# the 1-D layer (baseline_model.py:27-56) after its GEMM
+# ----------------------------------------------------------------------------------------------
+class _AdjNorm(torch.autograd.Function):
+    """``A_hat`` of baseline_model.py:41-50 for ``B[heads, V, V]`` with its backward (D detached)."""
+
+    @staticmethod
+    def forward(ctx, B, transpose):
+        require_cuda(B)
+        Bc = B.detach().float().contiguous()
+        out = torch.empty_like(Bc)
+        _lib.call("cgat_adj_norm_fwd", ptr(Bc), ptr(out), Bc.shape[0], Bc.shape[1], int(transpose), stream())
+        ctx.transpose = transpose
+        ctx.save_for_backward(Bc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (Bc,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        gB = torch.empty_like(Bc)
+        _lib.call("cgat_adj_norm_bwd", ptr(Bc), ptr(g), ptr(gB), Bc.shape[0], Bc.shape[1], int(ctx.transpose), stream())
+        return gB, None
+
+
+def adjacency_norm_autograd(B, transpose=False):
+    return _AdjNorm.apply(B, transpose)
+
+
+class _GAT1DCore(torch.autograd.Function):
+    """``out = ELU((A_hat . softmax_j(LeakyReLU(s1_i + s2_j))) . Wh)`` for ``Wh[N, V, F]`` (fp32)."""
+
+    @staticmethod
+    def forward(ctx, Wh, a, adj, mask, alpha):
+        require_cuda(Wh, a, adj)
+        Wh = Wh.contiguous().float()
+        ac = a.detach().reshape(-1).float().contiguous()
+        adjc = adj.detach().float().contiguous()
+        mc = None if mask is None else mask.to(torch.uint8).contiguous()
+        N, V, F_ = Wh.shape
+        dev = Wh.device
+        s12 = torch.empty(2, N, V, device=dev)
+        att = torch.empty(N, V, V, device=dev)
+        M = torch.empty(N, V, V, device=dev)
+        out = torch.empty_like(Wh)
+        _lib.call("cgat_gat1d_fwd", ptr(Wh), ptr(ac), ptr(adjc), ptr(mc), ptr(s12[0]), ptr(s12[1]), ptr(att), ptr(M), ptr(out),
+                  N, V, F_, float(alpha), stream(), launches=3)
+        ctx.alpha = alpha
+        ctx.a_shape = a.shape
+        ctx.save_for_backward(Wh, ac, adjc, mc, s12, att, M, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        Wh, ac, adjc, mc, s12, att, M, out = ctx.saved_tensors
+        N, V, F_ = Wh.shape
+        dev = Wh.device
+        dout = dout.contiguous().float()
+        dWh = torch.empty_like(Wh)
+        da = torch.empty(2 * F_, device=dev)
+        zero = torch.zeros(V * V + N * V * V, device=dev)
+        dadj, dM = zero[:V * V].view(V, V), zero[V * V:].view(N, V, V)
+        ds = torch.empty(2, N, V, device=dev)
+        _lib.call("cgat_gat1d_bwd", ptr(Wh), ptr(ac), ptr(adjc), ptr(mc), ptr(s12[0]), ptr(s12[1]), ptr(att), ptr(M), ptr(out),
+                  ptr(dout), ptr(dWh), ptr(da), ptr(dadj), ptr(dM), ptr(ds[0]), ptr(ds[1]), N, V, F_, float(ctx.alpha),
+                  stream(), launches=3)
+        return dWh, da.view(ctx.a_shape), dadj, None, None
+
+
+def gat1d_core(Wh, a, adj, mask=None, alpha=0.2):
+    return _GAT1DCore.apply(Wh, a, adj, mask, alpha)

@@ -19,7 +19,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import AttnConfig, conv2d_nhwc, gat_stream, graph_attention, IMPL_AUTO
+from .functional import (AttnConfig, adjacency_norm_autograd, conv2d_nhwc, gat1d_core, gat_stream, graph_attention,
+                         IMPL_AUTO)
 
 
 def _xavier(shape):
@@ -218,3 +219,38 @@ class GATMultiHead2D(nn.Module):
 
     def forward(self, x):
         return _gat2d_forward(self.attentions, x)
+
+
+class GraphAttentionLayer(_HeadParams):
+    """``baseline_model.GraphAttentionLayer`` (:13-75): features flattened per vertex, soft-max over neighbours.
+
+    ``Wh = h.W`` runs in the conv kernels as a 1x1 convolution over the ``[N, V]`` grid of rows; everything after it
+    (scores, soft-max, ``A_hat . attention`` (:53), aggregation, ELU) in ``cgat_gat1d_fwd/bwd``.  fp32.
+    """
+
+    def __init__(self, in_features, out_features, n_vertices, alpha):
+        super().__init__(in_features, out_features, n_vertices, alpha, "linear")
+
+    def forward(self, h):
+        if h.dim() == 4:  # :28-30
+            N, C, T, V = h.shape
+            h = h.permute(0, 3, 1, 2).contiguous().view(N, V, C * T)
+        N, V, F_ = h.shape
+        x = h.float().reshape(1, N, V, F_)
+        w_krsc = self.W.t().reshape(self.out_features, 1, 1, F_)
+        Wh = conv2d_nhwc(x, w_krsc).reshape(N, V, self.out_features)  # :35
+        adj = adjacency_norm_autograd(self.B[None])[0]  # :41-50
+        return gat1d_core(Wh, self.a, adj, None, self.alpha)
+
+
+class GATMultiHead(nn.Module):
+    """``baseline_model.GATMultiHead`` (:78-102): heads concatenated on the feature axis."""
+
+    def __init__(self, nfeat, nhid, n_vertices, alpha, nheads):
+        super().__init__()
+        self.attentions = [GraphAttentionLayer(nfeat, nhid, n_vertices, alpha) for _ in range(nheads)]
+        for i, att in enumerate(self.attentions):
+            self.add_module(f"attention_{i}", att)
+
+    def forward(self, x):
+        return torch.cat([att(x) for att in self.attentions], dim=-1)  # :93

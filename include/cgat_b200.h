@@ -159,6 +159,17 @@ int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, 
                             const float* ga, const float* gadj, const float* const* B, float* const* g_w,
                             float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate, void* stream);
 
+/* a8  the 1-D layer after its GEMM: GraphAttentionLayer.forward lines 36-56 of convolutional_gat/baseline_model.py
+ * (scores :36-38 / :58-65, soft-max over neighbours :39, attention <- A_hat . attention :53, aggregation :54,
+ * ELU :56).  fp32.  Wh [n][v][f]; a [2f]; adj = A_hat [v][v]; s1, s2 [n][v]; att, M [n][v][v]; out [n][v][f].
+ * The backward needs dadj [v][v] and dM [n][v][v] ZEROED by the caller; dWh, da, ds1, ds2 are written.            */
+int cgat_gat1d_fwd(const float* Wh, const float* a, const float* adj, const uint8_t* mask, float* s1, float* s2,
+                   float* att, float* M, float* out, int n, int v, int f, float alpha, void* stream);
+int cgat_gat1d_bwd(const float* Wh, const float* a, const float* adj, const uint8_t* mask, const float* s1,
+                   const float* s2, const float* att, const float* M, const float* out, const float* dout, float* dWh,
+                   float* da, float* dadj, float* dM, float* ds1, float* ds2, int n, int v, int f, float alpha,
+                   void* stream);
+
 /* a12  train-step pieces, convolutional_gat/train.py:131 and :212.
  * loss = mean((yhat-y)^2) - lambda*mean(yhat); writes dloss/dyhat (same dtype as yhat) and
  * ACCUMULATES the scalar loss into loss_out[0] (fp32; caller zeroes).                              */

@@ -67,6 +67,39 @@ def test_baseline2d_model_vs_reference_golden():
         close(p.grad, fx[f"grad.{k}"], atol=1e-4, msg=f"d{k}")
 
 
+def test_gat1d_layer_vs_reference_golden():
+    from cgat.layers import GraphAttentionLayer
+
+    fx = golden("gat1d_layer")
+    N, V, F_ = fx["h"].shape
+    lay = GraphAttentionLayer(F_, F_, V, fx["alpha"]).to(DEV)
+    lay.load_state_dict(sd_of(fx))
+    h = fx["h"].to(DEV).requires_grad_()
+    out = lay(h)
+    close(out, fx["out"], msg="out")
+    out.backward(fx["g"].to(DEV))
+    close(h.grad, fx["grad_in.h"], atol=1e-5, msg="dh")
+    close(lay.W.grad, fx["grad.W"], atol=1e-4, msg="dW")
+    close(lay.a.grad, fx["grad.a"], atol=1e-4, msg="da")
+    close(lay.B.grad, fx["grad.B"], atol=1e-4, msg="dB")
+
+
+def test_baseline1d_model_vs_reference_golden():
+    from convolutional_gat.baseline_model import BaselineModel
+
+    fx = golden("baseline1d_model")
+    N, H, W, T, V = fx["x"].shape
+    model = BaselineModel(image_width=W, image_height=H, n_vertices=V).to(DEV)
+    model.load_state_dict(sd_of(fx))
+    x = fx["x"].to(DEV).requires_grad_()
+    out = model(x)
+    close(out, fx["out"], msg="out")
+    out.backward(fx["g"].to(DEV))
+    close(x.grad, fx["grad_in.x"], atol=1e-5, msg="dx")
+    for k, p in model.named_parameters():
+        close(p.grad, fx[f"grad.{k}"], atol=1e-4, msg=f"d{k}")
+
+
 # ---------------------------------------------------------------------------------------------------
 def _pair(type_, mapping, heads, merge, axis, masked, seed, T=4, V=6):
     """(ours on GPU, spec oracle on CPU) with identical parameters."""
