@@ -54,6 +54,16 @@ class StreamDesc(ctypes.Structure):
     _fields_ = [
         ("nodes", ctypes.c_int32), ("ci", ctypes.c_int32), ("co", ctypes.c_int32), ("heads", ctypes.c_int32),
         ("layout", ctypes.c_int32), ("mapping", ctypes.c_int32), ("transpose_adj", ctypes.c_int32),
+        ("wgrad_cols", ctypes.c_int32),
+    ]
+
+
+class LayerDesc(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+        ("nodes", ctypes.c_int32), ("ci", ctypes.c_int32), ("co", ctypes.c_int32), ("heads", ctypes.c_int32),
+        ("layout", ctypes.c_int32), ("merge", ctypes.c_int32), ("apply_elu", ctypes.c_int32),
+        ("alpha", ctypes.c_float),
     ]
 
 
@@ -82,6 +92,11 @@ SIGNATURES = {
     "cgat_stream_wpack_bytes": [ctypes.POINTER(StreamDesc), _I],
     "cgat_stream_prepare": [ctypes.POINTER(StreamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "cgat_stream_param_grads": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cgat_layer_supported": [ctypes.POINTER(LayerDesc)],
+    "cgat_layer_workspace_bytes": [ctypes.POINTER(LayerDesc)],
+    "cgat_layer_fwd": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "cgat_layer_bwd": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                       ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P],
     "cgat_gat1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_gat1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _I64, _F, _F, _I, _P],
@@ -108,6 +123,7 @@ def lib() -> ctypes.CDLL:
             fn.restype = ctypes.c_int
         L.cgat_conv_workspace_bytes.restype = ctypes.c_int64
         L.cgat_stream_wpack_bytes.restype = ctypes.c_int64
+        L.cgat_layer_workspace_bytes.restype = ctypes.c_int64
         L.cgat_version.restype = ctypes.c_char_p
         L.cgat_last_error.restype = ctypes.c_char_p
         _lib = L

@@ -254,6 +254,9 @@ def adam_step_(param, grad, m, v, step_dev, lr, beta1=0.9, beta2=0.999, eps=1e-8
 # param-grad kernel and autograd receives ``None`` for them (no per-parameter accumulate kernels).  TrainStep turns
 # this on: it owns a zeroed flat gradient buffer whose views are the ``.grad`` tensors.
 DIRECT_GRAD = False
+# conv mapping: run node conv + attention as ONE kernel per direction (cgat_layer_fwd / cgat_layer_bwd) when the
+# shape is served; False keeps the separate conv / attention kernels (used by tests to compare the two paths).
+FUSED_LAYER = True
 
 
 class _GATStreamFn(torch.autograd.Function):
@@ -272,7 +275,15 @@ class _GATStreamFn(torch.autograd.Function):
         bs = [params[per * k + 1] for k in range(heads)] if conv else None
         as_ = [params[per * k + per - 2] for k in range(heads)]
         Bs = [params[per * k + per - 1] for k in range(heads)]
-        sd = _lib.StreamDesc(cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, 1 if conv else 0, int(cfg.adj_transpose))
+        dt = dtype_tag(x)
+        ld = None
+        if conv and FUSED_LAYER and dt == _lib.BF16 and cfg.softmax_axis == "neighbour":
+            ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, cfg.merge, int(cfg.apply_elu),
+                                cfg.alpha)
+            if not lib().cgat_layer_supported(ctypes.byref(ld)):
+                ld = None
+        sd = _lib.StreamDesc(cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, 1 if conv else 0, int(cfg.adj_transpose),
+                             1 if ld is not None else 0)
         st = stream()
         a_st = torch.empty(heads, 2 * cfg.co, device=dev, dtype=torch.float32)
         adj = torch.empty(heads, cfg.nodes, cfg.nodes, device=dev, dtype=torch.float32)
@@ -289,9 +300,19 @@ class _GATStreamFn(torch.autograd.Function):
                   _lib.ptr_array(as_), _lib.ptr_array(Bs), ptr(wpack), ptr(wpack_d), ptr(w_st), ptr(bias_d), ptr(a_st),
                   ptr(adj), st)
         n_pix = N * H * W
-        dt = dtype_tag(x)
         mc = None if mask is None else mask.to(torch.uint8).contiguous()
         cd = None
+        if ld is not None:
+            cin, cout = T * V, heads * cfg.nodes * cfg.co
+            cd = _conv_desc(N, H, W, cin, cout, 3, 3, 1, 1, 1, H, W, dt, 0)
+            out = torch.empty(n_pix, cfg.out_rec, device=dev, dtype=x.dtype)
+            _lib.call("cgat_layer_fwd", ctypes.byref(ld), ptr(x), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
+                      ptr(out), st)
+            ctx.cfg, ctx.sd, ctx.cd, ctx.conv, ctx.shape, ctx.ld = cfg, sd, cd, conv, (N, H, W, T, V), ld
+            ctx.params = params
+            ctx.save_for_backward(x, wpack, bias_d, a_st, adj, mc, wpack_d)
+            return out
+        ctx.ld = None
         if conv:
             cin, cout = T * V, heads * cfg.nodes * cfg.co
             cd = _conv_desc(N, H, W, cin, cout, 3, 3, 1, 1, 1, H, W, dt, 0)
@@ -311,6 +332,8 @@ class _GATStreamFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         cfg, sd, cd, conv = ctx.cfg, ctx.sd, ctx.cd, ctx.conv
+        if ctx.ld is not None:
+            return _GATStreamFn._backward_fused(ctx, dout)
         x, wh, w_st, a_st, adj, mc, wpack_d = ctx.saved_tensors
         N, H, W, T, V = ctx.shape
         params = ctx.params
@@ -358,6 +381,43 @@ class _GATStreamFn(torch.autograd.Function):
         _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(gW), ptr(ga), ptr(gadj),
                   _lib.ptr_array(Bs), _lib.ptr_array(g_w), _lib.ptr_array(g_b) if conv else None, _lib.ptr_array(g_a),
                   _lib.ptr_array(g_B), int(direct), st)
+        grads = [None] * len(params) if direct else [g.to(p.dtype) for g, p in zip(tg, params)]
+        return (dx, None, None, None, *grads)
+
+    @staticmethod
+    def _backward_fused(ctx, dout):
+        cfg, sd, cd, ld = ctx.cfg, ctx.sd, ctx.cd, ctx.ld
+        x, wpack, bias_d, a_st, adj, mc, wpack_d = ctx.saved_tensors
+        N, H, W, T, V = ctx.shape
+        params = ctx.params
+        heads, per = cfg.heads, 4
+        dev = x.device
+        st = stream()
+        dout = dout.contiguous()
+        na, nadj = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes
+        acc = torch.zeros(na + nadj, device=dev, dtype=torch.float32)
+        ga, gadj = acc[:na], acc[na:]
+        need_dx = ctx.needs_input_grad[0]
+        dwh = torch.empty(N * H * W, heads * cfg.nodes * cfg.co, device=dev, dtype=x.dtype) if need_dx else None
+        wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
+        ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.call("cgat_layer_bwd", ctypes.byref(ld), ptr(x), ptr(dout), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
+                  ptr(mc), ptr(dwh), ptr(wsp), ptr(ga), ptr(gadj), ctypes.byref(ncta), ctypes.byref(nt), st)
+        dx = None
+        if need_dx:
+            dx = torch.empty_like(x)
+            _lib.call("cgat_conv2d_dgrad_packed", ctypes.byref(cd), ptr(dwh), ptr(wpack_d), ptr(dx), st)
+        direct = DIRECT_GRAD and all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
+                                     for p in params)
+        tg = [p.grad for p in params] if direct else [torch.empty(p.shape, device=dev, dtype=torch.float32) for p in params]
+        g_w = [tg[per * k] for k in range(heads)]
+        g_b = [tg[per * k + 1] for k in range(heads)]
+        g_a = [tg[per * k + 2] for k in range(heads)]
+        g_B = [tg[per * k + 3] for k in range(heads)]
+        Bs = [params[per * k + 3] for k in range(heads)]
+        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),
+                  _lib.ptr_array(Bs), _lib.ptr_array(g_w), _lib.ptr_array(g_b), _lib.ptr_array(g_a), _lib.ptr_array(g_B),
+                  int(direct), st)
         grads = [None] * len(params) if direct else [g.to(p.dtype) for g, p in zip(tg, params)]
         return (dx, None, None, None, *grads)
 

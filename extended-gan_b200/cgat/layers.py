@@ -49,6 +49,25 @@ class _HeadParams(nn.Module):
         return f"{self.__class__.__name__} ({self.in_features} -> {self.out_features})"
 
 
+def _conv_stream_served(N, H, W, nodes, ci, co, heads, layout, merge, alpha) -> bool:
+    """True when the one-launch stream op serves this conv-mapped shape: either the fused layer kernels
+    (cgat_layer_fwd/bwd) or the tcgen05 fprop + wgrad pair on the dense block-diagonal conv."""
+    import ctypes
+
+    from . import functional as F
+
+    L = _lib.lib()
+    if F.FUSED_LAYER:
+        ld = _lib.LayerDesc(N, H, W, nodes, ci, co, heads, layout, merge, 1, alpha)
+        if L.cgat_layer_supported(ctypes.byref(ld)):
+            return True
+    cin, cout = nodes * ci, heads * nodes * co
+    if cin % 8 or cout % 8 or cout > 128:
+        return False
+    cd = _lib.ConvDesc(N, H, W, cin, cout, 3, 3, 1, 1, 1, H, W, _lib.BF16, 0, 1)
+    return bool(L.cgat_conv_tc_supported(ctypes.byref(cd), 0)) and bool(L.cgat_conv_tc_supported(ctypes.byref(cd), 2))
+
+
 class _GATStream(nn.Module):
     """All heads of one stream, one fused kernel launch per direction."""
 
@@ -100,10 +119,10 @@ class _GATStream(nn.Module):
         layout = _lib.LAYOUT_SPATIAL if spatial else _lib.LAYOUT_TEMPORAL
         merge = _lib.MERGE_MEAN if self.head_merge == "mean" else _lib.MERGE_CONCAT
         conv = self.mapping_type == "conv"
-        fused = (self.softmax_axis == "neighbour" and all(p.dtype == torch.float32 for p in self.parameters())
-                 and (not conv or (x.dtype == torch.bfloat16 and self.conv_impl in (IMPL_AUTO,))
-                      and (T * V) % 8 == 0 and (self.nheads * nodes * self.co) % 8 == 0
-                      and self.nheads * nodes * self.co <= 128))
+        fused = self.softmax_axis == "neighbour" and all(p.dtype == torch.float32 for p in self.parameters())
+        if fused and conv:
+            fused = (x.dtype == torch.bfloat16 and self.conv_impl == IMPL_AUTO
+                     and _conv_stream_served(N, H, W, nodes, self.ci, self.co, self.nheads, layout, merge, self.alpha))
         if fused:
             # one prepare launch + kernels + one param-grad launch (functional._GATStreamFn)
             cfg = AttnConfig(nodes=nodes, ci=self.ci, co=self.co, heads=self.nheads, layout=layout,

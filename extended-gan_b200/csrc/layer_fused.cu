@@ -1,0 +1,619 @@
+// K6 / K7: one conv-mapped conv-GAT stream -- node conv AND graph attention -- as ONE kernel per direction.
+//
+// Why: the unfused path (conv_tc.cu -> attn_h2.cu) writes the projected features Wh[N,H,W,heads*nodes*co] to HBM
+// and reads them back (twice in the backward, plus d(Wh) once more for wgrad): 3/4 of the step's HBM traffic is
+// that intermediate.  Here Wh never leaves the SM:
+//
+//   x halo tile --TMA--> staging --4 producer warps--> im2col planes in shared memory
+//        --tcgen05.mma (M = 128 pixels, N = heads*nodes*co, K = 9 taps * cin)--> Wh in TMEM (fp32)
+//        --tcgen05.ld: TMEM lane = pixel, so each thread receives exactly ITS pixel's record-->
+//        per-pixel attention in registers (attn_math.cuh, fp32): logits, LeakyReLU, mask, soft-max over the
+//        neighbours, aggregation, adjacency mix, ELU (reference baseline_model.py:127-160)
+//   forward : head merge through shared memory, coalesced bf16 store of out
+//   backward: the forward is recomputed, then d(Wh) (bf16) goes straight into the shared-memory planes that
+//             are the A operand of the wgrad MMA (M = couts, N = 9*cin + ones column for dbias, K = pixels);
+//             the wgrad accumulator stays in TMEM across all tiles of the persistent CTA.  Only x and d(out)
+//             are read from HBM; only per-CTA partial sums of the parameter gradients are written.
+//
+// One im2col operand serves both GEMMs: planes [k-chunk = c*9 + tap][128 pixels][8 channels] are K-major for
+// the fprop A operand (K = channels x taps) and MN-major for the wgrad B operand (K = pixels).
+//
+// Warp roles (512 threads, 1 CTA / SM): warps 0-1 im2col producers (two pixels each), warp 2 MMA issuer + TMEM
+// allocator, warp 3 TMA issuer, warps 4-15 three attention groups (group g owns heads g, g+3, ...; warp % 4
+// selects the TMEM lane quarter).  The kernel launches with 128 registers per thread; setmaxnreg moves the
+// budget of warpgroup 0 (56) to the attention warpgroups (152 each: 56 + 3 * 152 = 512 = the CTA's pool).
+#include "tc_common.cuh"
+#include "attn_common.cuh"
+
+namespace cgat {
+
+constexpr int LF_TH = 16, LF_TW = 8;  // output tile -> M = 128 pixels
+constexpr int LF_THREADS = 512;
+constexpr int LF_PROD = 64;
+constexpr int LF_ATT_WARP0 = 4;
+constexpr int LF_GROUPS = 3;
+constexpr int LF_MMA_WARP = 2, LF_TMA_WARP = 3;
+constexpr int LF_XSTG = 3;          // x halo staging buffers (TMA prefetch depth; 2 when shared memory is short)
+constexpr int LF_FP_COL0 = 256;     // TMEM: wgrad accumulator at columns [0,256), fprop accumulators at 256 + 128*acc
+constexpr int LF_TAPS = 9, LF_KW = 3;
+constexpr int LF_HDR = 6144;        // barriers + parameters
+
+struct LfArgs {
+  const __nv_bfloat16* wpack;  // [2*npairs][npad][8] chunk-major packed dense weights (cgat_stream_prepare)
+  const float* bias;           // [cout] dense bias
+  const float* a;              // [heads][2co]
+  const float* adj;            // [heads][nodes][nodes]
+  const uint8_t* mask;         // [nodes][nodes] or NULL
+  __nv_bfloat16* out;          // fwd
+  const __nv_bfloat16* dout;   // bwd
+  __nv_bfloat16* dwh;          // bwd, optional: d(Wh) [n][h][w][cout] for a following dgrad
+  float* partial;              // bwd: [grid][128][nt] wgrad partial sums
+  float* ga;                   // bwd: [heads][2co]   accumulated into
+  float* gadj;                 // bwd: [heads][nodes*nodes] accumulated into
+  int h, w, cin, cout, npad, heads, merge, apply_elu;
+  float alpha;
+  int nchunk, npairs, mchunk, nt, hp, wp;
+  int tiles_h, tiles_w, tiles, xstg;
+  uint32_t wbytes, stage_bytes, xs_bytes, im_off;
+};
+
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ uint4 lf_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void lf_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int NODES, int CO, bool SPATIAL, bool BWD>
+__global__ void __launch_bounds__(LF_THREADS, 1)
+layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
+  constexpr int REC = NODES * CO;          // elements of one head's pixel record
+  constexpr int RG = 2 * CO + NODES * NODES;  // a-grad + adjacency-grad values per head
+  static_assert(REC % 8 == 0, "record must be a multiple of 16 bytes");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [2]  producers -> MMA   (im2col planes ready)
+  uint64_t* empty = full + 2;                          // [2]  MMA -> producers   (stage reusable)
+  uint64_t* tfull = empty + 2;                         // [2]  MMA -> attention   (Wh accumulator ready)
+  uint64_t* tempty = tfull + 2;                        // [2]  attention -> MMA   (accumulator drained)
+  uint64_t* dyfull = tempty + 2;                       // [2]  attention -> MMA   (d(Wh) planes written)
+  uint64_t* sbar = dyfull + 2;                         // [3]  TMA landed
+  uint64_t* sfree = sbar + LF_XSTG;                    // [3]  staging consumed
+  uint64_t* wbar = sfree + LF_XSTG;                    // [1]
+  uint64_t* done = wbar + 1;                           // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + 256);          // [128]
+  float* s_a = reinterpret_cast<float*>(smem + 768);             // [MAX_HEADS][2*CO]
+  float* s_adj = reinterpret_cast<float*>(smem + 1280);          // [MAX_HEADS][NODES*NODES]
+  uint64_t* s_mask = reinterpret_cast<uint64_t*>(smem + 3328);   // [NODES]
+  float* s_gacc = reinterpret_cast<float*>(smem + 3392);         // [MAX_HEADS][RG]
+  static_assert(MAX_HEADS * 2 * CO * 4 <= 512 && MAX_HEADS * NODES * NODES * 4 <= 2048 && NODES * 8 <= 64 &&
+                    3392 + MAX_HEADS * RG * 4 <= LF_HDR, "parameter block overflows the header");
+  unsigned char* s_w = smem + LF_HDR;
+  unsigned char* s_stag = s_w + ((A.wbytes + 127u) & ~127u);
+  unsigned char* s_stage = s_stag + (size_t)A.xstg * A.xs_bytes;
+  float4* s_slab = reinterpret_cast<float4*>(s_stage + 2 * (size_t)A.stage_bytes);  // fwd: [group][REC/4][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nact = A.heads < LF_GROUPS ? A.heads : LF_GROUPS;  // attention groups that own at least one head
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], LF_PROD); mbar_init(&empty[i], 1); mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128 * nact); mbar_init(&dyfull[i], 128 * nact);
+    }
+    for (int i = 0; i < LF_XSTG; ++i) { mbar_init(&sbar[i], 1); mbar_init(&sfree[i], LF_PROD); }
+    mbar_init(wbar, 1);
+    mbar_init(done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_x);
+  }
+  for (int i = threadIdx.x; i < 128; i += LF_THREADS) s_bias[i] = (A.bias != nullptr && i < A.cout) ? A.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) s_a[i] = A.a[i];
+  for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) s_adj[i] = A.adj[i];
+  for (int i = threadIdx.x; i < MAX_HEADS * RG; i += LF_THREADS) s_gacc[i] = 0.f;
+  if (threadIdx.x < NODES) {
+    uint64_t mrow = 0;
+    for (int j = 0; j < NODES; ++j)
+      if (A.mask == nullptr || A.mask[threadIdx.x * NODES + j] != 0) mrow |= (1ull << j);
+    s_mask[threadIdx.x] = mrow;
+  }
+  {
+    // every plane starts zeroed (padding planes must hold finite numbers); then the plane of ones that
+    // follows the im2col planes (its wgrad column is dbias; its fprop weights are zero)
+    uint4* p = reinterpret_cast<uint4*>(s_stage);
+    const int n16 = (int)(2 * (size_t)A.stage_bytes / 16);
+    for (int i = threadIdx.x; i < n16; i += LF_THREADS) p[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (BWD) {
+      for (int s = 0; s < 2; ++s) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)s * A.stage_bytes + A.im_off +
+                                                  (size_t)(A.nchunk * LF_TAPS) * 2048);
+        for (int i = threadIdx.x; i < 512; i += LF_THREADS) o[i] = 0x3f803f80u;  // bf16 1.0 x2
+      }
+    }
+    fence_proxy_async_smem();
+  }
+  if (warp == LF_MMA_WARP) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < LF_ATT_WARP0) {
+    setmaxnreg_dec<56>();
+    if (warp < LF_PROD / 32) {
+      // ===================== im2col producers: thread t re-lays tile pixels t and t + 64 =====================
+      const uint32_t pix_bytes = (uint32_t)A.cin * 2;
+      const uint32_t row_bytes = (uint32_t)A.wp * pix_bytes;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1, buf = it % A.xstg;
+        mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        mbar_wait(&sbar[buf], (uint32_t)(it / A.xstg) & 1u);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int m = threadIdx.x + half * LF_PROD;
+          const int hr = m >> 3, wc = m & 7;
+          const uint32_t sg = smem_u32(s_stag) + (uint32_t)buf * A.xs_bytes + ((uint32_t)(hr * A.wp + wc)) * pix_bytes;
+          const uint32_t st = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + A.im_off + (uint32_t)m * 16;
+          for (int c = 0; c < A.nchunk; ++c) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              uint4 v[3];
+#pragma unroll
+              for (int s = 0; s < 3; ++s)
+                v[s] = lf_lds128(sg + (uint32_t)r * row_bytes + (uint32_t)s * pix_bytes + (uint32_t)c * 16);
+#pragma unroll
+              for (int s = 0; s < 3; ++s) lf_sts128(st + (uint32_t)(c * LF_TAPS + r * LF_KW + s) * 2048, v[s]);
+            }
+          }
+        }
+        mbar_arrive(&sfree[buf]);
+        fence_proxy_async_smem();
+        mbar_arrive(&full[stage]);
+      }
+    } else if (warp == LF_TMA_WARP && lane == 0) {
+      // ===================== TMA issuer =====================
+      mbar_arrive_expect_tx(wbar, A.wbytes);
+      bulk_g2s(s_w, A.wpack, A.wbytes, wbar);
+      const uint32_t xbytes = (uint32_t)A.hp * A.wp * A.cin * 2;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+        const int tw = tile % A.tiles_w;
+        const int th = (tile / A.tiles_w) % A.tiles_h;
+        const int n = tile / (A.tiles_w * A.tiles_h);
+        const int buf = it % A.xstg;
+        mbar_wait(&sfree[buf], ((uint32_t)(it / A.xstg) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&sbar[buf], xbytes);
+        tma_load_4d(s_stag + (size_t)buf * A.xs_bytes, &tmap_x, 0, tw * LF_TW - 1, th * LF_TH - 1, n, &sbar[buf]);
+      }
+    } else if (warp == LF_MMA_WARP && lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc_f = make_idesc_bf16(128, A.npad, 0, 0);
+      const uint32_t idesc_w = make_idesc_bf16(128, A.nt, 1, 1);
+      const uint32_t w_addr = smem_u32(s_w);
+      const uint32_t b_lbo = (uint32_t)A.npad * 16;
+      uint32_t wg_accum = 0;
+      auto wgrad = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&dyfull[s], ((uint32_t)j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t dy_addr = smem_u32(s_stage) + (uint32_t)s * A.stage_bytes;
+        const uint32_t im_addr = dy_addr + A.im_off;
+#pragma unroll
+        for (int jj = 0; jj < LF_TH / 2; ++jj) {  // K step: image rows 2jj, 2jj+1 of the tile (16 pixels)
+          const uint64_t ad = make_smem_desc(dy_addr + jj * 256, 128, 2048);
+          const uint64_t bd = make_smem_desc(im_addr + jj * 256, 128, 2048);
+          umma_bf16(tmem_base, ad, bd, idesc_w, wg_accum | (uint32_t)(jj > 0));
+        }
+        wg_accum = 1;
+        umma_commit(&empty[s]);
+      };
+      mbar_wait(wbar, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+        mbar_wait(&full[stage], ph);
+        mbar_wait(&tempty[stage], ph ^ 1u);
+        tc_fence_after();
+        const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + A.im_off;
+        const uint32_t d_addr = tmem_base + LF_FP_COL0 + (uint32_t)stage * 128;
+        for (int p = 0; p < A.npairs; ++p) {
+          const uint64_t ad = make_smem_desc(im_addr + (uint32_t)p * 4096, 2048, 128);
+          const uint64_t bd = make_smem_desc(w_addr + (uint32_t)p * 2 * b_lbo, b_lbo, 128);
+          umma_bf16(d_addr, ad, bd, idesc_f, p > 0);
+        }
+        umma_commit(&tfull[stage]);
+        if constexpr (!BWD) {
+          umma_commit(&empty[stage]);
+        } else if (it > 0) {
+          wgrad(it - 1);
+        }
+      }
+      if constexpr (BWD) {
+        if (it > 0) wgrad(it - 1);
+        umma_commit(done);
+      }
+    }
+  } else if (warp >= LF_ATT_WARP0 && warp < LF_ATT_WARP0 + 4 * LF_GROUPS) {
+    // ===================== attention groups =====================
+    setmaxnreg_inc<152>();
+    const int g = (warp - LF_ATT_WARP0) >> 2;
+    const int lg = warp & 3;
+    const int m = lg * 32 + lane;  // TMEM lane = pixel of the tile
+    const int hrow = m >> 3, wcol = m & 7;
+    const bool concat = A.merge == CGAT_MERGE_CONCAT;
+    const int out_rec = concat ? A.heads * REC : REC;
+    const bool vec_io = !concat || SPATIAL;  // a head's record is contiguous in the output record
+    if (g < nact) {
+      float gacc[BWD ? RG : 1];
+      int cur_head = -1;
+#pragma unroll
+      for (int i = 0; i < (BWD ? RG : 1); ++i) gacc[i] = 0.f;
+      auto flush = [&](int head) {
+        if (!BWD || head < 0) return;
+#pragma unroll
+        for (int i = 0; i < (BWD ? RG : 1); ++i) {
+          const float s = warp_sum(gacc[i]);
+          if (lane == 0) atomicAdd(&s_gacc[head * RG + i], s);
+          gacc[i] = 0.f;
+        }
+      };
+      const float inv_heads = 1.f / (float)A.heads;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+        const int tw = tile % A.tiles_w;
+        const int th = (tile / A.tiles_w) % A.tiles_h;
+        const int n = tile / (A.tiles_w * A.tiles_h);
+        const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
+        const bool valid = h < A.h && w < A.w;
+        const long long pix = ((long long)n * A.h + h) * A.w + w;
+        mbar_wait(&tfull[acc], ph);
+        tc_fence_after();
+        float oacc[(!BWD) ? REC : 1];
+        if (!BWD) {
+#pragma unroll
+          for (int i = 0; i < REC; ++i) oacc[i] = 0.f;
+        }
+        for (int k = g; k < A.heads; k += LF_GROUPS) {
+          float rec[REC];
+          const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + LF_FP_COL0 + acc * 128 + k * REC;
+#pragma unroll
+          for (int q = 0; q < REC / 8; ++q) tmem_ld8_nowait(t_addr + q * 8, &rec[q * 8]);
+          tmem_ld_wait();
+          if (k + LF_GROUPS >= A.heads) {  // last head of this group: the accumulator may be overwritten
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+          }
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + k * REC);
+#pragma unroll
+            for (int i = 0; i < REC / 4; ++i) {
+              const float4 b = b4[i];
+              rec[4 * i] += b.x; rec[4 * i + 1] += b.y; rec[4 * i + 2] += b.z; rec[4 * i + 3] += b.w;
+            }
+          }
+          float Wh[NODES][CO];
+          rec_to_mat<NODES, CO, SPATIAL>(rec, Wh);
+          float z[NODES][CO];
+#pragma unroll
+          for (int v = 0; v < NODES; ++v)
+#pragma unroll
+            for (int u = 0; u < CO; ++u) z[v][u] = 0.f;
+          attn_forward_pixel<F32, NODES, CO, false>(Wh, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask, A.alpha,
+                                                    nullptr, nullptr, z);
+          if constexpr (!BWD) {
+            if (A.apply_elu) {
+#pragma unroll
+              for (int v = 0; v < NODES; ++v)
+#pragma unroll
+                for (int u = 0; u < CO; ++u) z[v][u] = elu_fwd<F32>(z[v][u]);
+            }
+            if (!concat) {
+#pragma unroll
+              for (int v = 0; v < NODES; ++v)
+#pragma unroll
+                for (int u = 0; u < CO; ++u) oacc[rec_off<NODES, CO, SPATIAL>(v, u)] += z[v][u];
+            } else if (valid) {
+              __nv_bfloat16* op = A.out + pix * out_rec;
+              if (vec_io) {
+                mat_to_rec<NODES, CO, SPATIAL>(z, rec);
+                store_rec<REC, __nv_bfloat16>(op + k * REC, rec);
+              } else {
+#pragma unroll
+                for (int v = 0; v < NODES; ++v)
+#pragma unroll
+                  for (int u = 0; u < CO; ++u) op[v * (A.heads * CO) + k * CO + u] = __float2bfloat16_rn(z[v][u]);
+              }
+            }
+          } else {
+            // ---- upstream gradient of this pixel / head, times ELU'(z) ----
+            const float gscale = concat ? 1.f : inv_heads;
+            float dz[NODES][CO];
+            {
+              const __nv_bfloat16* dp = A.dout + pix * out_rec;
+              if (!valid) {
+#pragma unroll
+                for (int i = 0; i < REC; ++i) rec[i] = 0.f;
+              } else if (vec_io) {
+                load_rec<REC, __nv_bfloat16>(dp + (concat ? k * REC : 0), rec);
+              } else {
+#pragma unroll
+                for (int v = 0; v < NODES; ++v)
+#pragma unroll
+                  for (int u = 0; u < CO; ++u)
+                    rec[rec_off<NODES, CO, SPATIAL>(v, u)] = __bfloat162float(dp[v * (A.heads * CO) + k * CO + u]);
+              }
+              rec_to_mat<NODES, CO, SPATIAL>(rec, dz);
+#pragma unroll
+              for (int v = 0; v < NODES; ++v)
+#pragma unroll
+                for (int u = 0; u < CO; ++u)
+                  dz[v][u] = dz[v][u] * gscale * (A.apply_elu ? elu_grad<F32>(z[v][u]) : 1.f);
+            }
+            if (k != cur_head) { flush(cur_head); cur_head = k; }
+#pragma unroll
+            for (int v = 0; v < NODES; ++v)
+#pragma unroll
+              for (int u = 0; u < CO; ++u) z[v][u] = 0.f;  // z is reused as d(Wh)
+            attn_backward_pixel<F32, NODES, CO, false, 0>(Wh, dz, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask,
+                                                          A.alpha, nullptr, nullptr, nullptr, z, &gacc[NODES * NODES],
+                                                          &gacc[0], nullptr);
+            mat_to_rec<NODES, CO, SPATIAL>(z, rec);
+            // d(Wh) -> the MN-major A operand of the wgrad MMA: plane = dense cout / 8, 16 bytes per pixel
+            const uint32_t dy = smem_u32(s_stage) + (uint32_t)acc * A.stage_bytes + (uint32_t)(k * (REC / 8)) * 2048 +
+                                (uint32_t)m * 16;
+#pragma unroll
+            for (int q = 0; q < REC / 8; ++q) {
+              uint4 v;
+              v.x = pack_bf16x2(rec[8 * q + 0], rec[8 * q + 1]);
+              v.y = pack_bf16x2(rec[8 * q + 2], rec[8 * q + 3]);
+              v.z = pack_bf16x2(rec[8 * q + 4], rec[8 * q + 5]);
+              v.w = pack_bf16x2(rec[8 * q + 6], rec[8 * q + 7]);
+              lf_sts128(dy + (uint32_t)q * 2048, v);
+              if (A.dwh != nullptr && valid) reinterpret_cast<uint4*>(A.dwh + pix * A.cout + k * REC)[q] = v;
+            }
+          }
+        }
+        if constexpr (BWD) {
+          fence_proxy_async_smem();
+          mbar_arrive(&dyfull[acc]);
+        } else if (!concat) {
+          // ---- head mean: every group leaves its partial sum in its slab, then all active threads combine ----
+          float4* slab = s_slab + (size_t)g * (REC / 4) * 128;
+#pragma unroll
+          for (int i = 0; i < REC / 4; ++i)
+            slab[i * 128 + m] = make_float4(oacc[4 * i], oacc[4 * i + 1], oacc[4 * i + 2], oacc[4 * i + 3]);
+          named_bar_sync(1, 128 * nact);
+          const int at = g * 128 + m;
+          for (int q = at; q < 128 * (REC / 8); q += 128 * nact) {
+            const int part = q >> 7, p = q & 127;
+            float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+            for (int gg = 0; gg < nact; ++gg) {
+              const float4 a0 = s_slab[((size_t)gg * (REC / 4) + 2 * part) * 128 + p];
+              const float4 a1 = s_slab[((size_t)gg * (REC / 4) + 2 * part + 1) * 128 + p];
+              lo.x += a0.x; lo.y += a0.y; lo.z += a0.z; lo.w += a0.w;
+              hi.x += a1.x; hi.y += a1.y; hi.z += a1.z; hi.w += a1.w;
+            }
+            const int ph2 = th * LF_TH + (p >> 3), pw2 = tw * LF_TW + (p & 7);
+            if (ph2 < A.h && pw2 < A.w) {
+              uint4 v;
+              v.x = pack_bf16x2(lo.x * inv_heads, lo.y * inv_heads);
+              v.y = pack_bf16x2(lo.z * inv_heads, lo.w * inv_heads);
+              v.z = pack_bf16x2(hi.x * inv_heads, hi.y * inv_heads);
+              v.w = pack_bf16x2(hi.z * inv_heads, hi.w * inv_heads);
+              reinterpret_cast<uint4*>(A.out + (((long long)n * A.h + ph2) * A.w + pw2) * REC)[part] = v;
+            }
+          }
+          named_bar_sync(1, 128 * nact);  // slabs are rewritten by the next tile
+        }
+      }
+      if constexpr (BWD) {
+        flush(cur_head);
+        // ---- wgrad accumulator -> per-CTA partial sums (lane = dense cout) ----
+        mbar_wait(done, 0);
+        tc_fence_after();
+        float* prow = A.partial + ((size_t)blockIdx.x * 128 + m) * A.nt;
+        for (int c0 = g * 16; c0 < A.nt; c0 += nact * 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
+          if (m < A.cout) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(prow + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (BWD) {
+    for (int i = threadIdx.x; i < A.heads * RG; i += LF_THREADS) {
+      const int k = i / RG, r = i - k * RG;
+      const float v = s_gacc[i];
+      if (r < NODES * NODES) atomicAdd(A.gadj + (size_t)k * NODES * NODES + r, v);
+      else atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
+    }
+  }
+  if (warp == LF_MMA_WARP) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+struct LfGeom {
+  int cin, cout, rec, nchunk, npairs, npad, mchunk, nt, hp, wp;
+  uint32_t wbytes, xs_bytes, stage_bytes, im_off;
+  size_t smem;
+  int tiles_h, tiles_w, tiles, xstg;
+};
+
+static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
+  LfGeom g;
+  g.rec = d->nodes * d->co;
+  g.cin = d->nodes * d->ci;
+  g.cout = d->heads * g.rec;
+  g.nchunk = g.cin / 8;
+  g.npairs = (g.nchunk * LF_TAPS + 1) / 2;
+  g.npad = (g.cout + 15) & ~15;
+  g.mchunk = g.cout / 8;
+  g.nt = (LF_TAPS * g.cin + 8 + 15) & ~15;
+  g.hp = LF_TH + 2;
+  g.wp = LF_TW + 2;
+  g.wbytes = (uint32_t)g.npairs * 2 * g.npad * 16;
+  g.xs_bytes = (uint32_t)((g.hp * g.wp * g.cin * 2 + 127) & ~127);
+  int im_planes = g.nt / 8;
+  if (2 * g.npairs > im_planes) im_planes = 2 * g.npairs;
+  g.im_off = bwd ? (uint32_t)g.mchunk * 2048 : 0;
+  int planes = (bwd ? g.mchunk : 0) + im_planes;
+  if (planes < 16) planes = 16;  // the wgrad A operand always spans 16 planes (M = 128)
+  g.stage_bytes = (uint32_t)planes * 2048;
+  g.xstg = LF_XSTG;
+  do {
+    g.smem = LF_HDR + ((g.wbytes + 127u) & ~127u) + (size_t)g.xstg * g.xs_bytes + 2 * (size_t)g.stage_bytes +
+             (bwd ? 0 : (size_t)LF_GROUPS * g.rec * 128 * 4);
+  } while (g.smem > 227 * 1024 && --g.xstg >= 2);
+  if (g.xstg < 2) g.xstg = 2;
+  g.tiles_h = (d->h + LF_TH - 1) / LF_TH;
+  g.tiles_w = (d->w + LF_TW - 1) / LF_TW;
+  g.tiles = d->n * g.tiles_h * g.tiles_w;
+  return g;
+}
+
+static int lf_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+int layer_supported(const cgat_layer_desc* d) {
+  if (!d || d->heads < 1 || d->heads > MAX_HEADS || d->n < 1 || d->h < 1 || d->w < 1) return 0;
+  const bool sp = d->layout == CGAT_LAYOUT_SPATIAL;
+  const bool shape_ok = (sp && d->nodes == 6 && d->ci == 4 && d->co == 4) || (!sp && d->nodes == 4 && d->ci == 6 && d->co == 6);
+  if (!shape_ok) return 0;
+  const LfGeom f = lf_geom(d, false), b = lf_geom(d, true);
+  if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.nt > 256) return 0;
+  if (f.smem > 227 * 1024 || b.smem > 227 * 1024) return 0;
+  return 1;
+}
+
+size_t layer_partial_bytes(const cgat_layer_desc* d) {
+  const LfGeom g = lf_geom(d, true);
+  return (size_t)148 * 128 * g.nt * sizeof(float);
+}
+
+// 4-D map over NHWC bf16 [n][h][w][c], box (c, wp, hp, 1): lands as [hp][wp][c]; out-of-image = zero (conv padding)
+static int make_nhwc_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int wp, int hp) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(CGAT_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaFree(nullptr);  // make sure the calling thread has a current context (autograd worker threads)
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)wp, (cuuint32_t)hp, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CGAT_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int NODES, int CO, bool SPATIAL>
+static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const CUtensorMap& map, const LfArgs& A,
+                     cudaStream_t st) {
+  const int grid = g.tiles < lf_sm_count() ? g.tiles : lf_sm_count();
+  if (grid > 148) return fail(CGAT_EUNSUPPORTED, "partial-sum workspace sized for <= 148 CTAs");
+  cudaError_t e;
+  if (bwd) {
+    auto kern = layer_kernel<NODES, CO, SPATIAL, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<grid, LF_THREADS, g.smem, st>>>(map, A);
+  } else {
+    auto kern = layer_kernel<NODES, CO, SPATIAL, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<grid, LF_THREADS, g.smem, st>>>(map, A);
+  }
+  return check_launch(bwd ? "layer_kernel<bwd>" : "layer_kernel<fwd>");
+}
+
+int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias, const float* a,
+                 const float* adj, const uint8_t* mask, void* out, const void* dout, void* dwh, float* partial,
+                 float* ga, float* gadj, int* ncta_out, int* nt_out, cudaStream_t st) {
+  if (!layer_supported(d)) return fail(CGAT_EUNSUPPORTED, "fused conv-GAT layer kernel does not support this shape");
+  if (!aligned16(x) || !aligned16(wpack) || (out && !aligned16(out)) || (dout && !aligned16(dout)) ||
+      (dwh && !aligned16(dwh)) || (partial && !aligned16(partial)))
+    return fail(CGAT_EALIGN, "layer tensors must be 16-byte aligned");
+  const LfGeom g = lf_geom(d, bwd);
+  CUtensorMap map;
+  if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, g.wp, g.hp)) return rc;
+  LfArgs A{};
+  A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
+  A.out = (__nv_bfloat16*)out; A.dout = (const __nv_bfloat16*)dout; A.dwh = (__nv_bfloat16*)dwh;
+  A.partial = partial; A.ga = ga; A.gadj = gadj;
+  A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
+  A.apply_elu = d->apply_elu; A.alpha = d->alpha;
+  A.nchunk = g.nchunk; A.npairs = g.npairs; A.mchunk = g.mchunk; A.nt = g.nt; A.hp = g.hp; A.wp = g.wp;
+  A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.xstg = g.xstg;
+  A.wbytes = g.wbytes; A.stage_bytes = g.stage_bytes; A.xs_bytes = g.xs_bytes; A.im_off = g.im_off;
+  if (ncta_out) *ncta_out = g.tiles < lf_sm_count() ? g.tiles : lf_sm_count();
+  if (nt_out) *nt_out = g.nt;
+  if (d->layout == CGAT_LAYOUT_SPATIAL) return lf_launch<6, 4, true>(bwd, d, g, map, A, st);
+  return lf_launch<4, 6, false>(bwd, d, g, map, A, st);
+}
+
+}  // namespace cgat
+
+using namespace cgat;
+
+extern "C" int cgat_layer_supported(const cgat_layer_desc* d) { return layer_supported(d); }
+
+extern "C" int64_t cgat_layer_workspace_bytes(const cgat_layer_desc* d) {
+  return layer_supported(d) ? (int64_t)layer_partial_bytes(d) : 0;
+}
+
+extern "C" int cgat_layer_fwd(const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias_dense,
+                              const float* a, const float* adj, const uint8_t* mask, void* out, void* stream) {
+  if (!d || !x || !wpack || !a || !adj || !out) return fail(CGAT_EINVAL, "null argument");
+  return layer_launch(false, d, x, wpack, bias_dense, a, adj, mask, out, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, const void* wpack,
+                              const float* bias_dense, const float* a, const float* adj, const uint8_t* mask,
+                              void* dwh, void* workspace, float* ga, float* gadj, int32_t* ncta_out, int32_t* nt_out,
+                              void* stream) {
+  if (!d || !x || !dout || !wpack || !a || !adj || !workspace || !ga || !gadj || !ncta_out || !nt_out)
+    return fail(CGAT_EINVAL, "null argument");
+  int ncta = 0, nt = 0;
+  const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, dout, dwh, (float*)workspace, ga,
+                              gadj, &ncta, &nt, (cudaStream_t)stream);
+  *ncta_out = ncta;
+  *nt_out = nt;
+  return rc;
+}

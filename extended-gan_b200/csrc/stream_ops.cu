@@ -176,7 +176,11 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
     for (int t = lane; t < terms; t += 32) {
       const int node = t / A.ncta, cta = t - node * A.ncta;
       const int row = k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u);
-      const int col = r < nwe ? tap * g.cin + rec_of(g.spatial, g.nodes, g.ci, node, c) : g.taps * g.cin;
+      int col = g.taps * g.cin;
+      if (r < nwe) {
+        const int ci_idx = rec_of(g.spatial, g.nodes, g.ci, node, c);
+        col = A.d.wgrad_cols ? ((ci_idx >> 3) * g.taps + tap) * 8 + (ci_idx & 7) : tap * g.cin + ci_idx;
+      }
       acc += A.wg_partial[((size_t)cta * 128 + row) * A.nt + col];
     }
     acc = warp_sum(acc);

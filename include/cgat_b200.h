@@ -144,6 +144,8 @@ typedef struct cgat_stream_desc {
   int32_t layout;        /* CGAT_LAYOUT_*                                  */
   int32_t mapping;       /* 0 linear, 1 conv 3x3 pad 1                      */
   int32_t transpose_adj; /* 1: the 1-D layer's A_hat^T (baseline_model.py:53) */
+  int32_t wgrad_cols;    /* column order of the wgrad partial sums handed to cgat_stream_param_grads:
+                            0 = [tap][cin] (cgat_conv2d_wgrad_partial), 1 = [cin/8][tap][8] (cgat_layer_bwd) */
 } cgat_stream_desc;
 
 /* bytes of the packed bf16 weight buffer of the block-diagonal dense conv (dgrad != 0: the dgrad packing) */
@@ -158,6 +160,33 @@ int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const 
 int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* gW_lin,
                             const float* ga, const float* gadj, const float* const* B, float* const* g_w,
                             float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate, void* stream);
+
+/* K6 / K7  one conv-mapped stream of the conv-GAT layer (shared 3x3 node conv, pad 1, + graph attention) as ONE
+ * kernel per direction: the projected features never touch HBM (tcgen05 accumulators in TMEM are read by the
+ * attention threads directly).  Replaces, for mapping_type="conv", the node conv at the call sites
+ * convolutional_gat/model.py:21-42 plus baseline_model.py:127-160 (see cgat_attn_fwd).  bf16 activations.
+ *   x      [n][h][w][nodes*ci]                      pixel records (the loaders' [N,H,W,T,V] layout)
+ *   wpack, bias_dense, a, adj                       as produced by cgat_stream_prepare (fprop packing)
+ *   out    [n][h][w][nodes*co] (MERGE_MEAN) or the concat layout of cgat_attn_fwd
+ *   dwh    optional (may be NULL): d(Wh) [n][h][w][heads*nodes*co] for cgat_conv2d_dgrad_packed
+ *   workspace  cgat_layer_workspace_bytes(d) bytes: per-CTA wgrad partial sums [ncta][128][nt], column order
+ *              [cin/8][tap][8] then the dbias column (cgat_stream_desc.wgrad_cols = 1)
+ *   ga [heads][2co], gadj [heads][nodes][nodes]     fp32, ACCUMULATED INTO                                      */
+typedef struct cgat_layer_desc {
+  int32_t n, h, w;
+  int32_t nodes, ci, co, heads;
+  int32_t layout;    /* CGAT_LAYOUT_* */
+  int32_t merge;     /* CGAT_MERGE_*  */
+  int32_t apply_elu;
+  float alpha;
+} cgat_layer_desc;
+int cgat_layer_supported(const cgat_layer_desc* d);
+int64_t cgat_layer_workspace_bytes(const cgat_layer_desc* d);
+int cgat_layer_fwd(const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias_dense, const float* a,
+                   const float* adj, const uint8_t* mask, void* out, void* stream);
+int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, const void* wpack,
+                   const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, void* dwh,
+                   void* workspace, float* ga, float* gadj, int32_t* ncta_out, int32_t* nt_out, void* stream);
 
 /* a8  the 1-D layer after its GEMM: GraphAttentionLayer.forward lines 36-56 of convolutional_gat/baseline_model.py
  * (scores :36-38 / :58-65, soft-max over neighbours :39, attention <- A_hat . attention :53, aggregation :54,
