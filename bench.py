@@ -285,6 +285,12 @@ def run_ours(args):
         "cgat_loss_fwd_bwd": ("hbm", n_pix * rec * 3 * esz),
     }
     if pre:
+        # fused conv + attention kernels: forward reads x and writes out; backward reads x and d(out) (the projected
+        # features never touch HBM).  flops: the dense block-diagonal conv GEMM(s) actually executed on tcgen05.
+        fl = 2.0 * n_pix * rec * heads * rec * 9
+        alg["cgat_layer_fwd"] = ("hbm", n_pix * 2 * rec * esz, fl)
+        alg["cgat_layer_bwd"] = ("hbm", n_pix * 2 * rec * esz, 2 * fl)
+        alg["cgat_layer_train"] = ("hbm", n_pix * 2 * rec * esz, 2 * fl)  # reads x and y; out / d(out) stay on chip
         cin, cout, k = rec, heads * rec, 3
         conv_flops = 2.0 * n_pix * cin * cout * k * k  # dense block-diagonal implicit GEMM actually executed
         conv_bytes = n_pix * (cin + cout) * esz

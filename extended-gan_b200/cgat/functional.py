@@ -422,6 +422,60 @@ class _GATStreamFn(torch.autograd.Function):
         return (dx, None, None, None, *grads)
 
 
+def layer_train_supported(x, cfg: AttnConfig, mapping: str) -> bool:
+    """True when ``gat_stream_train`` serves this stream (conv mapping, bf16, mean merge, <= 3 heads, fused kernel)."""
+    if mapping != "conv" or not FUSED_LAYER or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    if cfg.merge != _lib.MERGE_MEAN or cfg.heads > 3 or cfg.softmax_axis != "neighbour":
+        return False
+    N, H, W, T, V = x.shape
+    ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, cfg.heads, cfg.layout, cfg.merge, int(cfg.apply_elu), cfg.alpha)
+    return bool(lib().cgat_layer_supported(ctypes.byref(ld)))
+
+
+def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor):
+    """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
+    ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
+
+    ``loss_out[0]`` is accumulated into; the parameter gradients are ACCUMULATED into the parameters' existing
+    ``.grad`` buffers (fp32, contiguous).  ``params`` = per head (conv.weight, conv.bias, a, B).
+    """
+    require_cuda(x, y, loss_out, *params)
+    N, H, W, T, V = x.shape
+    x = x.contiguous()
+    y = y.contiguous()
+    dev = x.device
+    heads = cfg.heads
+    ws = [params[4 * k] for k in range(heads)]
+    bs = [params[4 * k + 1] for k in range(heads)]
+    as_ = [params[4 * k + 2] for k in range(heads)]
+    Bs = [params[4 * k + 3] for k in range(heads)]
+    if not all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in params):
+        raise RuntimeError("gat_stream_train accumulates into existing contiguous fp32 .grad buffers")
+    ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, cfg.merge, int(cfg.apply_elu), cfg.alpha)
+    sd = _lib.StreamDesc(cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, 1, int(cfg.adj_transpose), 1)
+    st = stream()
+    a_st = torch.empty(heads, 2 * cfg.co, device=dev, dtype=torch.float32)
+    adj = torch.empty(heads, cfg.nodes, cfg.nodes, device=dev, dtype=torch.float32)
+    wpack = torch.empty(lib().cgat_stream_wpack_bytes(ctypes.byref(sd), 0), dtype=torch.uint8, device=dev)
+    bias_d = torch.empty(heads * cfg.nodes * cfg.co, device=dev, dtype=torch.float32)
+    _lib.call("cgat_stream_prepare", ctypes.byref(sd), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
+              _lib.ptr_array(Bs), ptr(wpack), None, None, ptr(bias_d), ptr(a_st), ptr(adj), st)
+    mc = None if mask is None else mask.to(torch.uint8).contiguous()
+    na, nadj = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes
+    acc = torch.zeros(na + nadj, device=dev, dtype=torch.float32)
+    ga, gadj = acc[:na], acc[na:]
+    wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
+    ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
+    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
+              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(loss_out), ctypes.byref(ncta), ctypes.byref(nt), st)
+    tg = [p.grad for p in params]
+    _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),
+              _lib.ptr_array(Bs), _lib.ptr_array([tg[4 * k] for k in range(heads)]),
+              _lib.ptr_array([tg[4 * k + 1] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 2] for k in range(heads)]),
+              _lib.ptr_array([tg[4 * k + 3] for k in range(heads)]), 1, st)
+
+
 def gat_stream(x, cfg: AttnConfig, mapping: str, mask, params):
     """Fused stream op: ``x[N,H,W,T,V]`` -> pixel records ``[N*H*W, out_rec]``."""
     return _GATStreamFn.apply(x, cfg, mapping, mask, *params)

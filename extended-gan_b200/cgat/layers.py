@@ -105,6 +105,33 @@ class _GATStream(nn.Module):
             bias = b[:, None, :].expand(k, other, co).reshape(-1)
         return dense, bias
 
+    def _train_cfg(self, x):
+        N, H, W, T, V = x.shape
+        spatial = self.type_ == "spatial"
+        nodes = V if spatial else T
+        return AttnConfig(nodes=nodes, ci=self.ci, co=self.co, heads=self.nheads,
+                          layout=_lib.LAYOUT_SPATIAL if spatial else _lib.LAYOUT_TEMPORAL, proj=_lib.PROJ_PRE,
+                          merge=_lib.MERGE_MEAN if self.head_merge == "mean" else _lib.MERGE_CONCAT,
+                          pix_per_sample=H * W, alpha=self.alpha, softmax_axis=self.softmax_axis)
+
+    def train_step_supported(self, x: torch.Tensor) -> bool:
+        """Whether ``fused_train_step`` serves this stream for inputs like ``x`` (see functional.gat_stream_train)."""
+        from .functional import layer_train_supported
+
+        if x.dim() != 5 or not all(p.dtype == torch.float32 for p in self.parameters()):
+            return False
+        return layer_train_supported(x, self._train_cfg(x), self.mapping_type)
+
+    def fused_train_step(self, x, y, lam, loss_out):
+        """forward + ``MSE - lam*mean`` loss + backward of a model that is just this stream (train.py:130-132):
+        accumulates the loss into ``loss_out`` and the gradients into the parameters' ``.grad`` buffers."""
+        from .functional import gat_stream_train
+
+        params = []
+        for h in self.attentions:
+            params += [h.conv.weight, h.conv.bias, h.a, h.B]
+        gat_stream_train(x, y, self._train_cfg(x), self.adj_mask, params, lam, loss_out)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """``x[N,H,W,T,V]`` -> ``[N,H,W,T,V]`` (mean merge) or heads concatenated on the channel axis."""
         if x.dim() != 5:

@@ -29,7 +29,7 @@ from .parallel import FlatParams
 class TrainStep:
     def __init__(self, model: torch.nn.Module, example_x: torch.Tensor, example_y: torch.Tensor, lr: float = 1e-3,
                  weight_decay: float = 0.01, lam: float = 0.0005, betas=(0.9, 0.999), eps: float = 1e-8,
-                 use_graph: bool = True, process_group: Optional[dist.ProcessGroup] = None):
+                 use_graph: bool = True, process_group: Optional[dist.ProcessGroup] = None, fuse_loss: bool = True):
         self.model = model
         self.lr, self.weight_decay, self.lam, self.betas, self.eps = lr, weight_decay, lam, betas, eps
         self.pg = process_group
@@ -41,9 +41,22 @@ class TrainStep:
         self.step_count = torch.zeros(1, device=self.device, dtype=torch.int64)
         self.graph = None
         self._slots = None  # double-buffered inputs for pipelined host->device loading (enable_prefetch)
+        self.fused_stream = self._single_stream(model, example_x) if fuse_loss else None
         self._flatten()
         if use_graph:
             self._capture()
+
+    @staticmethod
+    def _single_stream(model, x):
+        """The model's only stream when its forward is ONE conv-mapped GAT stream (the Spatial/Temporal wrappers of
+        convolutional_gat/model.py:8-88 call just ``hidden_layer``) and the fused train kernel serves it, else None."""
+        m = getattr(model, "net", model)
+        if not hasattr(m, "hidden_layer") or getattr(m, "_use_output", True):
+            return None
+        stream = getattr(m.hidden_layer, "stream", None)
+        if stream is None or not hasattr(stream, "train_step_supported") or not stream.train_step_supported(x):
+            return None
+        return stream
 
     # -- flat buffers ---------------------------------------------------------------------------
     def _flatten(self):
@@ -69,6 +82,9 @@ class TrainStep:
     def _fwd_bwd(self):
         self.flat_grad.zero_()
         self.loss.zero_()
+        if self.fused_stream is not None:  # forward + loss + backward in one kernel (cgat_layer_train)
+            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss)
+            return
         prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
         try:
             out = self.model(self.x)

@@ -54,7 +54,7 @@ EncodeTiledFn get_encode_tiled() {
 
 // The driver entry point needs a current context on the CALLING thread.  Autograd runs backward on worker
 // threads that may not have touched the runtime yet, so bind the primary context of the thread's device.
-static void ensure_context() {
+void ensure_context() {
   using GetCurFn = CUresult (*)(CUcontext*);
   static GetCurFn get_cur = nullptr;
   if (!get_cur) {

@@ -50,6 +50,9 @@ struct LfArgs {
   float* partial;              // bwd: [grid][128][nt] wgrad partial sums
   float* ga;                   // bwd: [heads][2co]   accumulated into
   float* gadj;                 // bwd: [heads][nodes*nodes] accumulated into
+  const __nv_bfloat16* y;      // train mode (bwd kernel): target, same layout as out; d(out) is derived in-kernel
+  float* loss_out;             // train mode: scalar loss, accumulated into
+  float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
   int h, w, cin, cout, npad, heads, merge, apply_elu;
   float alpha;
   int nchunk, npairs, mchunk, nt, hp, wp;
@@ -100,7 +103,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   uint64_t* s_mask = reinterpret_cast<uint64_t*>(smem + 3328);   // [NODES]
   float* s_gacc = reinterpret_cast<float*>(smem + 3392);         // [MAX_HEADS][RG]
   static_assert(MAX_HEADS * 2 * CO * 4 <= 512 && MAX_HEADS * NODES * NODES * 4 <= 2048 && NODES * 8 <= 64 &&
-                    3392 + MAX_HEADS * RG * 4 <= LF_HDR, "parameter block overflows the header");
+                    3392 + (MAX_HEADS * RG + 1) * 4 <= LF_HDR, "parameter block overflows the header");
   unsigned char* s_w = smem + LF_HDR;
   unsigned char* s_stag = s_w + ((A.wbytes + 127u) & ~127u);
   unsigned char* s_stage = s_stag + (size_t)A.xstg * A.xs_bytes;
@@ -123,7 +126,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   for (int i = threadIdx.x; i < 128; i += LF_THREADS) s_bias[i] = (A.bias != nullptr && i < A.cout) ? A.bias[i] : 0.f;
   for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) s_a[i] = A.a[i];
   for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) s_adj[i] = A.adj[i];
-  for (int i = threadIdx.x; i < MAX_HEADS * RG; i += LF_THREADS) s_gacc[i] = 0.f;
+  for (int i = threadIdx.x; i < MAX_HEADS * RG + 1; i += LF_THREADS) s_gacc[i] = 0.f;
   if (threadIdx.x < NODES) {
     uint64_t mrow = 0;
     for (int j = 0; j < NODES; ++j)
@@ -261,6 +264,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     const bool vec_io = !concat || SPATIAL;  // a head's record is contiguous in the output record
     if (g < nact) {
       float gacc[BWD ? RG : 1];
+      float loss_acc = 0.f;
       int cur_head = -1;
 #pragma unroll
       for (int i = 0; i < (BWD ? RG : 1); ++i) gacc[i] = 0.f;
@@ -346,7 +350,61 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
             // ---- upstream gradient of this pixel / head, times ELU'(z) ----
             const float gscale = concat ? 1.f : inv_heads;
             float dz[NODES][CO];
-            {
+            if (A.y != nullptr) {
+              // ---- train mode (mean merge, one head per group): out = mean_k ELU(z_k) needs every head of the
+              //      pixel, so the groups swap their ELU(z) through the (still unused) d(Wh) planes of this stage
+              //      as fp16; d(out) = (2 (out - y) - lambda) / numel   (convolutional_gat/train.py:131) ----
+              const uint32_t exb = smem_u32(s_stage) + (uint32_t)acc * A.stage_bytes + (uint32_t)m * 16;
+#pragma unroll
+              for (int v = 0; v < NODES; ++v)
+#pragma unroll
+                for (int u = 0; u < CO; ++u)
+                  rec[rec_off<NODES, CO, SPATIAL>(v, u)] = A.apply_elu ? elu_fwd<F32>(z[v][u]) : z[v][u];
+#pragma unroll
+              for (int q = 0; q < REC / 8; ++q) {
+                uint4 v;
+                __half2 t;
+#define PKH(a, b) (t = __floats2half2_rn(a, b), *reinterpret_cast<uint32_t*>(&t))
+                v.x = PKH(rec[8 * q + 0], rec[8 * q + 1]); v.y = PKH(rec[8 * q + 2], rec[8 * q + 3]);
+                v.z = PKH(rec[8 * q + 4], rec[8 * q + 5]); v.w = PKH(rec[8 * q + 6], rec[8 * q + 7]);
+#undef PKH
+                lf_sts128(exb + (uint32_t)(k * (REC / 8) + q) * 2048, v);
+              }
+              float yv[REC];
+              if (valid) load_rec<REC, __nv_bfloat16>(A.y + pix * REC, yv);
+              named_bar_sync(1, 128 * nact);
+#pragma unroll
+              for (int i = 0; i < REC; ++i) rec[i] = 0.f;
+              for (int kk = 0; kk < A.heads; ++kk) {
+#pragma unroll
+                for (int q = 0; q < REC / 8; ++q) {
+                  const uint4 v = lf_lds128(exb + (uint32_t)(kk * (REC / 8) + q) * 2048);
+                  const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                    rec[8 * q + 2 * e] += f.x;
+                    rec[8 * q + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+              float lsum = 0.f;
+#pragma unroll
+              for (int i = 0; i < REC; ++i) {
+                const float o = rec[i] * inv_heads;
+                const float dd = o - yv[i];
+                lsum += dd * dd - A.lambda * o;
+                rec[i] = valid ? (2.f * dd - A.lambda) * A.inv_n : 0.f;
+              }
+              if (g == 0 && valid) loss_acc += lsum;
+              named_bar_sync(1, 128 * nact);  // all heads read: the planes may now take d(Wh)
+              rec_to_mat<NODES, CO, SPATIAL>(rec, dz);
+#pragma unroll
+              for (int v = 0; v < NODES; ++v)
+#pragma unroll
+                for (int u = 0; u < CO; ++u)
+                  dz[v][u] = dz[v][u] * gscale * (A.apply_elu ? elu_grad<F32>(z[v][u]) : 1.f);
+            } else {
               const __nv_bfloat16* dp = A.dout + pix * out_rec;
               if (!valid) {
 #pragma unroll
@@ -426,6 +484,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       }
       if constexpr (BWD) {
         flush(cur_head);
+        if (A.y != nullptr && g == 0) {
+          const float s = warp_sum(loss_acc);
+          if (lane == 0) atomicAdd(&s_gacc[MAX_HEADS * RG], s);
+        }
         // ---- wgrad accumulator -> per-CTA partial sums (lane = dense cout) ----
         mbar_wait(done, 0);
         tc_fence_after();
@@ -451,6 +513,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       if (r < NODES * NODES) atomicAdd(A.gadj + (size_t)k * NODES * NODES + r, v);
       else atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
     }
+    if (A.y != nullptr && threadIdx.x == 0) atomicAdd(A.loss_out, s_gacc[MAX_HEADS * RG] * A.inv_n);
   }
   if (warp == LF_MMA_WARP) {
     __syncwarp();
@@ -528,9 +591,7 @@ size_t layer_partial_bytes(const cgat_layer_desc* d) {
 static int make_nhwc_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int wp, int hp) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(CGAT_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaFree(nullptr);  // make sure the calling thread has a current context (autograd worker threads)
+  ensure_context();
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
   cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)wp, (cuuint32_t)hp, 1};
@@ -564,7 +625,8 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
 
 int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias, const float* a,
                  const float* adj, const uint8_t* mask, void* out, const void* dout, void* dwh, float* partial,
-                 float* ga, float* gadj, int* ncta_out, int* nt_out, cudaStream_t st) {
+                 float* ga, float* gadj, int* ncta_out, int* nt_out, cudaStream_t st, const void* y = nullptr,
+                 float* loss_out = nullptr, float lambda = 0.f) {
   if (!layer_supported(d)) return fail(CGAT_EUNSUPPORTED, "fused conv-GAT layer kernel does not support this shape");
   if (!aligned16(x) || !aligned16(wpack) || (out && !aligned16(out)) || (dout && !aligned16(dout)) ||
       (dwh && !aligned16(dwh)) || (partial && !aligned16(partial)))
@@ -576,6 +638,8 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
   A.out = (__nv_bfloat16*)out; A.dout = (const __nv_bfloat16*)dout; A.dwh = (__nv_bfloat16*)dwh;
   A.partial = partial; A.ga = ga; A.gadj = gadj;
+  A.y = (const __nv_bfloat16*)y; A.loss_out = loss_out; A.lambda = lambda;
+  A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
   A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
   A.nchunk = g.nchunk; A.npairs = g.npairs; A.mchunk = g.mchunk; A.nt = g.nt; A.hp = g.hp; A.wp = g.wp;
@@ -613,6 +677,23 @@ extern "C" int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const voi
   int ncta = 0, nt = 0;
   const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, dout, dwh, (float*)workspace, ga,
                               gadj, &ncta, &nt, (cudaStream_t)stream);
+  *ncta_out = ncta;
+  *nt_out = nt;
+  return rc;
+}
+
+extern "C" int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
+                                const float* bias_dense, const float* a, const float* adj, const uint8_t* mask,
+                                float lambda, void* workspace, float* ga, float* gadj, float* loss_out,
+                                int32_t* ncta_out, int32_t* nt_out, void* stream) {
+  if (!d || !x || !y || !wpack || !a || !adj || !workspace || !ga || !gadj || !loss_out || !ncta_out || !nt_out)
+    return fail(CGAT_EINVAL, "null argument");
+  if (d->merge != CGAT_MERGE_MEAN || d->heads > LF_GROUPS)
+    return fail(CGAT_EUNSUPPORTED, "cgat_layer_train serves mean-merged streams with at most %d heads", LF_GROUPS);
+  if (!aligned16(y)) return fail(CGAT_EALIGN, "y must be 16-byte aligned");
+  int ncta = 0, nt = 0;
+  const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, nullptr, nullptr, (float*)workspace,
+                              ga, gadj, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda);
   *ncta_out = ncta;
   *nt_out = nt;
   return rc;

@@ -122,6 +122,8 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
+// binds the primary context on the calling thread if it has none (autograd worker threads); capture-safe
+void ensure_context();
 
 // 3-D map over an NHWC bf16 tensor viewed as [n][h][w*c] (pixel and channel merged into one contiguous row)
 // with box (boxe elements, rows, 1): wide TMA rows instead of one 16-byte row per (pixel, chunk).

@@ -188,6 +188,16 @@ int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, co
                    const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, void* dwh,
                    void* workspace, float* ga, float* gadj, int32_t* ncta_out, int32_t* nt_out, void* stream);
 
+/* The same backward kernel in TRAIN mode: the reference step  loss = MSE(model(x), y) - lambda*mean(model(x));
+ * loss.backward()  (convolutional_gat/train.py:130-132) for a model that is one mean-merged conv stream (the
+ * Spatial/Temporal models of convolutional_gat/model.py:8-88 use only their hidden layer).  The forward is
+ * recomputed in-kernel anyway, so out and d(out) never exist in HBM: reads x and y, writes the parameter-gradient
+ * partial sums and ACCUMULATES the scalar loss into loss_out[0].  heads <= 3, CGAT_MERGE_MEAN.                 */
+int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
+                     const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, float lambda,
+                     void* workspace, float* ga, float* gadj, float* loss_out, int32_t* ncta_out, int32_t* nt_out,
+                     void* stream);
+
 /* a8  the 1-D layer after its GEMM: GraphAttentionLayer.forward lines 36-56 of convolutional_gat/baseline_model.py
  * (scores :36-38 / :58-65, soft-max over neighbours :39, attention <- A_hat . attention :53, aggregation :54,
  * ELU :56).  fp32.  Wh [n][v][f]; a [2f]; adj = A_hat [v][v]; s1, s2 [n][v]; att, M [n][v][v]; out [n][v][f].

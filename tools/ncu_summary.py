@@ -16,6 +16,13 @@ WANT = [
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+    "smsp__inst_executed.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+    "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
+    "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct",
+    "smsp__warp_issue_stalled_sleeping_per_warp_active.pct", "smsp__warp_issue_stalled_membar_per_warp_active.pct",
     "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "launch__waves_per_multiprocessor",
 ]
 
@@ -39,7 +46,7 @@ def launches(src, dst):
         f.write(f"# {len(step)} launches, {tot / 1000:.1f} us total (cold-cache, serialised: compare SHARES)\n")
         for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{v / 1000:9.1f} us  x{c:<3d} {100 * v / tot:5.1f}%  {k}\n")
-    print(open(dst).read())
+    print(f"wrote {dst}")
 
 
 def full(src, dst):
@@ -49,12 +56,16 @@ def full(src, dst):
     idx = {h: i for i, h in enumerate(hdr)}
     with open(dst, "w") as f:
         f.write(f"# ncu --set full --clock-control none, source {src}\n")
+        seen = set()
         for r in rows[2:]:
+            if r[idx['Kernel Name']] in seen:  # one section per kernel (the first captured launch)
+                continue
+            seen.add(r[idx['Kernel Name']])
             f.write(f"== {r[idx['Kernel Name']]}\n")
             for w in WANT:
                 if w in idx:
                     f.write(f"   {w:72s} {r[idx[w]]} {units[idx[w]]}\n")
-    print(open(dst).read())
+    print(f"wrote {dst}")
 
 
 if __name__ == "__main__":
