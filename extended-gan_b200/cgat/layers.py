@@ -105,6 +105,16 @@ class _GATStream(nn.Module):
             bias = b[:, None, :].expand(k, other, co).reshape(-1)
         return dense, bias
 
+    def _mask_arg(self):
+        """The neighbour mask for the kernels, or None while it is all ones (the reference's dense attention: the
+        kernels then skip the mask arithmetic).  Cached on the buffer's version counter (one host sync per change)."""
+        m = self.adj_mask
+        key = (m.data_ptr(), m._version)
+        if getattr(self, "_mask_key", None) != key:
+            self._mask_all_ones = bool(m.all().item())
+            self._mask_key = key
+        return None if self._mask_all_ones else m
+
     def _train_cfg(self, x):
         N, H, W, T, V = x.shape
         spatial = self.type_ == "spatial"
@@ -130,7 +140,7 @@ class _GATStream(nn.Module):
         params = []
         for h in self.attentions:
             params += [h.conv.weight, h.conv.bias, h.a, h.B]
-        gat_stream_train(x, y, self._train_cfg(x), self.adj_mask, params, lam, loss_out)
+        gat_stream_train(x, y, self._train_cfg(x), self._mask_arg(), params, lam, loss_out)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """``x[N,H,W,T,V]`` -> ``[N,H,W,T,V]`` (mean merge) or heads concatenated on the channel axis."""
@@ -158,7 +168,7 @@ class _GATStream(nn.Module):
             params = []
             for h in self.attentions:
                 params += [h.conv.weight, h.conv.bias, h.a, h.B] if conv else [h.W, h.a, h.B]
-            out = gat_stream(x, cfg, self.mapping_type, self.adj_mask, params)
+            out = gat_stream(x, cfg, self.mapping_type, self._mask_arg(), params)
         else:
             a = torch.stack([h.a.reshape(-1) for h in self.attentions])
             B = torch.stack([h.B for h in self.attentions])

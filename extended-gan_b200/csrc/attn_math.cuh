@@ -54,6 +54,15 @@ struct F32 {
   static CGAT_HD T max(T a, T b) { return fmaxf(a, b); }
   static CGAT_HD T min(T a, T b) { return fminf(a, b); }
   static CGAT_HD T exp(T a) { return fast_exp(a); }
+  // e^(a - m) given nml = -m * log2(e): one FMA + one ex2 on the device
+  static CGAT_HD T neg_l2e(T m) { return m * -1.4426950408889634f; }
+  static CGAT_HD T exp_sub(T a, T nml) {
+#if defined(__CUDA_ARCH__)
+    return exp2f(fmaf(a, 1.4426950408889634f, nml));
+#else
+    return exp2f(fmaf(a, 1.4426950408889634f, nml));
+#endif
+  }
   static CGAT_HD T rcp(T a) { return 1.f / a; }
   static CGAT_HD T gt0(T a) { return a > 0.f ? 1.f : 0.f; }  // 1 where a > 0 else 0
 };
@@ -79,15 +88,23 @@ struct H2 {
     asm("ex2.approx.f16x2 %0, %1;" : "=r"(out) : "r"(in));
     return *reinterpret_cast<T*>(&out);
   }
+  static CGAT_D T neg_l2e(T m) { return __hmul2(m, __float2half2_rn(-1.4426950408889634f)); }
+  static CGAT_D T exp_sub(T a, T nml) {
+    const T y = __hfma2(a, __float2half2_rn(1.4426950408889634f), nml);
+    uint32_t in = *reinterpret_cast<const uint32_t*>(&y), out;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(out) : "r"(in));
+    return *reinterpret_cast<T*>(&out);
+  }
   static CGAT_D T rcp(T a) { return h2rcp(a); }
   static CGAT_D T gt0(T a) { return __hgt2(a, __float2half2_rn(0.f)); }
 };
 #endif
 
-// ELU and its derivative, branch-free:  ELU(z) = max(z,0) + exp(min(z,0)) - 1 ;  ELU'(z) = exp(min(z,0))
+// ELU and its derivative, branch-free:  ELU(z) = max(z, exp(min(z,0)) - 1)  (e^t - 1 >= t, with equality of the two
+// branches at 0) ;  ELU'(z) = exp(min(z,0))
 template <typename P>
 CGAT_HD typename P::T elu_fwd(typename P::T z) {
-  return P::add(P::max(z, P::zero()), P::sub(P::exp(P::min(z, P::zero())), P::bc(1.f)));
+  return P::max(z, P::sub(P::exp(P::min(z, P::zero())), P::bc(1.f)));
 }
 template <typename P>
 CGAT_HD typename P::T elu_grad(typename P::T z) {
@@ -100,7 +117,7 @@ CGAT_HD typename P::T elu_grad(typename P::T z) {
 // convention) are policy-typed broadcasts.  maskrow[i] bit j set  <=>  edge (i,j) present.
 // st_max / st_rinv: pixel-axis soft-max statistics (PIXEL mode only, F32 policy only).
 // ---------------------------------------------------------------------------------------------
-template <typename P, int NODES, int CO, bool PIXEL>
+template <typename P, int NODES, int CO, bool PIXEL, bool MASKED = true>
 CGAT_HD void attn_forward_pixel(const typename P::T (&Wh)[NODES][CO], const typename P::T* __restrict__ a,
                                 const typename P::T* __restrict__ adj, const uint64_t* __restrict__ maskrow,
                                 typename P::T alpha, const typename P::T* __restrict__ st_max,
@@ -121,13 +138,13 @@ CGAT_HD void attn_forward_pixel(const typename P::T (&Wh)[NODES][CO], const type
 #pragma unroll
   for (int i = 0; i < NODES; ++i) {
     T att[NODES];
-    const uint64_t mrow = maskrow[i];
+    const uint64_t mrow = MASKED ? maskrow[i] : ~0ull;
     if (PIXEL) {
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
         const T pre = P::add(s1[i], s2[j]);
         T e = P::max(pre, P::mul(alpha, pre));
-        if (!((mrow >> j) & 1ull)) e = P::mask_fill();
+        if (MASKED && !((mrow >> j) & 1ull)) e = P::mask_fill();
         att[j] = P::mul(P::exp(P::sub(e, st_max[i * NODES + j])), st_rinv[i * NODES + j]);
       }
     } else {
@@ -136,15 +153,17 @@ CGAT_HD void attn_forward_pixel(const typename P::T (&Wh)[NODES][CO], const type
       for (int j = 0; j < NODES; ++j) {
         const T pre = P::add(s1[i], s2[j]);
         T e = P::max(pre, P::mul(alpha, pre));
-        if (!((mrow >> j) & 1ull)) e = P::mask_fill();
+        if (MASKED && !((mrow >> j) & 1ull)) e = P::mask_fill();
         att[j] = e;
-        m = P::max(m, e);
+        m = j == 0 ? e : P::max(m, e);
       }
+      const T nml = P::neg_l2e(m);
       T sum = P::zero();
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        att[j] = P::exp(P::sub(att[j], m));
-        sum = P::add(sum, att[j]);
+        // (the FMA form loses exp(fill - fill) = 1 on fully masked rows: masked kernels subtract exactly)
+        att[j] = MASKED ? P::exp(P::sub(att[j], m)) : P::exp_sub(att[j], nml);
+        sum = j == 0 ? att[j] : P::add(sum, att[j]);
       }
       const T r = P::rcp(sum);
 #pragma unroll
@@ -202,7 +221,7 @@ CGAT_HD void attn_logits_pixel(const float (&Wh)[NODES][CO], const float* __rest
 // pixel mode: st_max/st_rinv as in the forward, st_dot[i][j] = sum_p att[i][j][p] dAtt[i][j][p].
 // MODE 0: full backward.  MODE 1: only accumulate dot[i][j] += att*dAtt (pixel-mode pre-pass).
 // ---------------------------------------------------------------------------------------------
-template <typename P, int NODES, int CO, bool PIXEL, int MODE>
+template <typename P, int NODES, int CO, bool PIXEL, int MODE, bool MASKED = true>
 CGAT_HD void attn_backward_pixel(const typename P::T (&Wh)[NODES][CO], const typename P::T (&dz)[NODES][CO],
                                  const typename P::T* __restrict__ a, const typename P::T* __restrict__ adj,
                                  const uint64_t* __restrict__ maskrow, typename P::T alpha,
@@ -233,14 +252,14 @@ CGAT_HD void attn_backward_pixel(const typename P::T (&Wh)[NODES][CO], const typ
     // ---- recompute row i of the attention ----
     T att[NODES];
     T slope[NODES];
-    const uint64_t mrow = maskrow[i];
+    const uint64_t mrow = MASKED ? maskrow[i] : ~0ull;
     if (PIXEL) {
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
         const T pre = P::add(s1[i], s2[j]);
         slope[j] = P::fma(one_minus_alpha, P::gt0(pre), alpha);
         T e = P::mul(pre, slope[j]);
-        if (!((mrow >> j) & 1ull)) { e = P::mask_fill(); slope[j] = P::zero(); }
+        if (MASKED && !((mrow >> j) & 1ull)) { e = P::mask_fill(); slope[j] = P::zero(); }
         att[j] = P::mul(P::exp(P::sub(e, st_max[i * NODES + j])), st_rinv[i * NODES + j]);
       }
     } else {
@@ -250,15 +269,17 @@ CGAT_HD void attn_backward_pixel(const typename P::T (&Wh)[NODES][CO], const typ
         const T pre = P::add(s1[i], s2[j]);
         slope[j] = P::fma(one_minus_alpha, P::gt0(pre), alpha);
         T e = P::mul(pre, slope[j]);
-        if (!((mrow >> j) & 1ull)) { e = P::mask_fill(); slope[j] = P::zero(); }
+        if (MASKED && !((mrow >> j) & 1ull)) { e = P::mask_fill(); slope[j] = P::zero(); }
         att[j] = e;
-        m = P::max(m, e);
+        m = j == 0 ? e : P::max(m, e);
       }
+      const T nml = P::neg_l2e(m);
       T sum = P::zero();
 #pragma unroll
       for (int j = 0; j < NODES; ++j) {
-        att[j] = P::exp(P::sub(att[j], m));
-        sum = P::add(sum, att[j]);
+        // (the FMA form loses exp(fill - fill) = 1 on fully masked rows: masked kernels subtract exactly)
+        att[j] = MASKED ? P::exp(P::sub(att[j], m)) : P::exp_sub(att[j], nml);
+        sum = j == 0 ? att[j] : P::add(sum, att[j]);
       }
       const T r = P::rcp(sum);
 #pragma unroll

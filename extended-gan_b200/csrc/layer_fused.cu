@@ -80,7 +80,21 @@ __device__ __forceinline__ void lf_sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int NODES, int CO, bool SPATIAL, bool BWD>
+// bf16 record held in registers (uint4 per 8 elements) -> fp32
+template <int N>
+__device__ __forceinline__ void unpack_rec(const uint4* __restrict__ p, float (&r)[N]) {
+#pragma unroll
+  for (int i = 0; i < N / 8; ++i) {
+    const uint32_t w[4] = {p[i].x, p[i].y, p[i].z, p[i].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      r[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+      r[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+}
+
+template <int NODES, int CO, bool SPATIAL, bool BWD, bool MASKED>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   constexpr int REC = NODES * CO;          // elements of one head's pixel record
@@ -97,7 +111,6 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   uint64_t* wbar = sfree + LF_XSTG;                    // [1]
   uint64_t* done = wbar + 1;                           // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
-  float* s_bias = reinterpret_cast<float*>(smem + 256);          // [128]
   float* s_a = reinterpret_cast<float*>(smem + 768);             // [MAX_HEADS][2*CO]
   float* s_adj = reinterpret_cast<float*>(smem + 1280);          // [MAX_HEADS][NODES*NODES]
   uint64_t* s_mask = reinterpret_cast<uint64_t*>(smem + 3328);   // [NODES]
@@ -123,7 +136,6 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     fence_mbar_init();
     tma_prefetch_desc(&tmap_x);
   }
-  for (int i = threadIdx.x; i < 128; i += LF_THREADS) s_bias[i] = (A.bias != nullptr && i < A.cout) ? A.bias[i] : 0.f;
   for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) s_a[i] = A.a[i];
   for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) s_adj[i] = A.adj[i];
   for (int i = threadIdx.x; i < MAX_HEADS * RG + 1; i += LF_THREADS) s_gacc[i] = 0.f;
@@ -135,12 +147,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   }
   {
     // every plane starts zeroed (padding planes must hold finite numbers); then the plane of ones that
-    // follows the im2col planes (its wgrad column is dbias; its fprop weights are zero)
+    // follows the im2col planes (its wgrad column is dbias; its fprop K-chunk holds the bias, hi + lo bf16 parts)
     uint4* p = reinterpret_cast<uint4*>(s_stage);
     const int n16 = (int)(2 * (size_t)A.stage_bytes / 16);
     for (int i = threadIdx.x; i < n16; i += LF_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    if (BWD) {
+    {
       for (int s = 0; s < 2; ++s) {
         uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)s * A.stage_bytes + A.im_off +
                                                   (size_t)(A.nchunk * LF_TAPS) * 2048);
@@ -288,6 +300,26 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
         const bool valid = h < A.h && w < A.w;
         const long long pix = ((long long)n * A.h + h) * A.w + w;
+        // upstream record of this pixel (d(out), or y in train mode): requested now, consumed after the forward has
+        // been recomputed, so its HBM latency hides behind the math; the next tile's lines are pulled into L2
+        uint4 pre[BWD ? REC / 8 : 1];
+        if constexpr (BWD) {
+          const __nv_bfloat16* src = A.y != nullptr ? A.y + pix * REC
+                                                    : (vec_io ? A.dout + pix * out_rec + (concat ? g * REC : 0) : nullptr);
+#pragma unroll
+          for (int q = 0; q < REC / 8; ++q)
+            pre[q] = (valid && src != nullptr) ? __ldg(reinterpret_cast<const uint4*>(src) + q) : make_uint4(0, 0, 0, 0);
+          const int ntile = tile + gridDim.x;
+          if (g == 0 && ntile < A.tiles) {
+            const int ntw = ntile % A.tiles_w, nth = (ntile / A.tiles_w) % A.tiles_h, nn = ntile / (A.tiles_w * A.tiles_h);
+            const int nh = nth * LF_TH + hrow, nw = ntw * LF_TW + wcol;
+            if (nh < A.h && nw < A.w) {
+              const long long npix = ((long long)nn * A.h + nh) * A.w + nw;
+              const void* pa = A.y != nullptr ? (const void*)(A.y + npix * REC) : (const void*)(A.dout + npix * out_rec);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            }
+          }
+        }
         mbar_wait(&tfull[acc], ph);
         tc_fence_after();
         float oacc[(!BWD) ? REC : 1];
@@ -305,14 +337,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
           }
-          {
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + k * REC);
-#pragma unroll
-            for (int i = 0; i < REC / 4; ++i) {
-              const float4 b = b4[i];
-              rec[4 * i] += b.x; rec[4 * i + 1] += b.y; rec[4 * i + 2] += b.z; rec[4 * i + 3] += b.w;
-            }
-          }
+          // (the conv bias arrives through the MMA: the plane of ones times the bias K-chunk of the packed weights)
           float Wh[NODES][CO];
           rec_to_mat<NODES, CO, SPATIAL>(rec, Wh);
           float z[NODES][CO];
@@ -320,7 +345,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           for (int v = 0; v < NODES; ++v)
 #pragma unroll
             for (int u = 0; u < CO; ++u) z[v][u] = 0.f;
-          attn_forward_pixel<F32, NODES, CO, false>(Wh, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask, A.alpha,
+          attn_forward_pixel<F32, NODES, CO, false, MASKED>(Wh, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask, A.alpha,
                                                     nullptr, nullptr, z);
           if constexpr (!BWD) {
             if (A.apply_elu) {
@@ -370,9 +395,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
 #undef PKH
                 lf_sts128(exb + (uint32_t)(k * (REC / 8) + q) * 2048, v);
               }
-              float yv[REC];
-              if (valid) load_rec<REC, __nv_bfloat16>(A.y + pix * REC, yv);
               named_bar_sync(1, 128 * nact);
+              float yv[REC];
+              unpack_rec<REC>(pre, yv);
 #pragma unroll
               for (int i = 0; i < REC; ++i) rec[i] = 0.f;
               for (int kk = 0; kk < A.heads; ++kk) {
@@ -406,11 +431,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
                   dz[v][u] = dz[v][u] * gscale * (A.apply_elu ? elu_grad<F32>(z[v][u]) : 1.f);
             } else {
               const __nv_bfloat16* dp = A.dout + pix * out_rec;
-              if (!valid) {
+              if (vec_io && (!concat || k == g)) {
+                unpack_rec<REC>(pre, rec);
+              } else if (!valid) {
 #pragma unroll
                 for (int i = 0; i < REC; ++i) rec[i] = 0.f;
               } else if (vec_io) {
-                load_rec<REC, __nv_bfloat16>(dp + (concat ? k * REC : 0), rec);
+                load_rec<REC, __nv_bfloat16>(dp + k * REC, rec);
               } else {
 #pragma unroll
                 for (int v = 0; v < NODES; ++v)
@@ -430,7 +457,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
             for (int v = 0; v < NODES; ++v)
 #pragma unroll
               for (int u = 0; u < CO; ++u) z[v][u] = 0.f;  // z is reused as d(Wh)
-            attn_backward_pixel<F32, NODES, CO, false, 0>(Wh, dz, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask,
+            attn_backward_pixel<F32, NODES, CO, false, 0, MASKED>(Wh, dz, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask,
                                                           A.alpha, nullptr, nullptr, nullptr, z, &gacc[NODES * NODES],
                                                           &gacc[0], nullptr);
             mat_to_rec<NODES, CO, SPATIAL>(z, rec);
@@ -578,6 +605,7 @@ int layer_supported(const cgat_layer_desc* d) {
   if (!shape_ok) return 0;
   const LfGeom f = lf_geom(d, false), b = lf_geom(d, true);
   if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.nt > 256) return 0;
+  if ((f.nchunk * LF_TAPS) % 2 == 0) return 0;  // the bias / ones K-chunk is the odd tail of the last MMA pair
   if (f.smem > 227 * 1024 || b.smem > 227 * 1024) return 0;
   return 1;
 }
@@ -608,18 +636,17 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
                      cudaStream_t st) {
   const int grid = g.tiles < lf_sm_count() ? g.tiles : lf_sm_count();
   if (grid > 148) return fail(CGAT_EUNSUPPORTED, "partial-sum workspace sized for <= 148 CTAs");
-  cudaError_t e;
-  if (bwd) {
-    auto kern = layer_kernel<NODES, CO, SPATIAL, true>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     kern<<<grid, LF_THREADS, g.smem, st>>>(map, A);
-  } else {
-    auto kern = layer_kernel<NODES, CO, SPATIAL, false>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    kern<<<grid, LF_THREADS, g.smem, st>>>(map, A);
-  }
+    return 0;
+  };
+  int rc;
+  const bool masked = A.mask != nullptr;  // NULL = all ones = the reference's dense attention: no mask arithmetic
+  if (bwd) rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, true, true>) : go(layer_kernel<NODES, CO, SPATIAL, true, false>);
+  else rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, false, true>) : go(layer_kernel<NODES, CO, SPATIAL, false, false>);
+  if (rc) return rc;
   return check_launch(bwd ? "layer_kernel<bwd>" : "layer_kernel<fwd>");
 }
 

@@ -99,7 +99,17 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepA
     const int row = (int)(q % g.npad);
     const int ki = (int)(q / g.npad);
     const int cch = ki / g.taps, tap = ki - cch * g.taps;
-    const float v = cch < g.nchunk ? dense_w(g, A.w, row, tap, cch * 8 + e) : 0.f;
+    float v = cch < g.nchunk ? dense_w(g, A.w, row, tap, cch * 8 + e) : 0.f;
+    if (A.d.wgrad_cols && ki == g.nchunk * g.taps && row < g.cout && e < 2) {
+      // fused layer kernels: this K-chunk multiplies a plane of ones -> the conv bias, as hi + lo bf16 parts
+      const int per_head = g.nodes * g.co;
+      const int k = row / per_head;
+      int node, u;
+      rec_inv(g.spatial, g.nodes, g.co, row - k * per_head, node, u);
+      const float b = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      v = e == 0 ? hi : b - hi;
+    }
     A.wpack[i] = __float2bfloat16_rn(v);
   }
   // dgrad packing: GEMM-K = dense cout, GEMM-N = cin, kernel rotated: value Wd[k][taps-1-tap][row]
