@@ -381,6 +381,155 @@ CGAT_HD void attn_backward_pixel(const typename P::T (&Wh)[NODES][CO], const typ
   }
 }
 
+
+// =============================================================================================
+// Neighbour-soft-max attention restructured through  M = adj^T . att  (used by the fused layer kernels):
+//   z[v][u] = sum_i adj[i][v] sum_j att[i][j] Wh[j][u] = sum_j M[v][j] Wh[j][u],   M[v][j] = sum_i adj[i][v] att[i][j]
+// costs NODES^3 + NODES^2 CO multiply-adds instead of 2 NODES^2 CO, and its backward needs no second pass over
+// the aggregated features:
+//   dM[v][j]   = sum_u dz[v][u] Wh[j][u]            dWh[j][u] = sum_v M[v][j] dz[v][u]   (+ the score terms below)
+//   g_adj[i][v] += sum_j att[i][j] dM[v][j]          dAtt[i][j] = sum_v adj[i][v] dM[v][j]
+//   de[i][j]   = att[i][j] (dAtt[i][j] - sum_j' att[i][j'] dAtt[i][j'])                  (soft-max backward)
+//   dp[i][j]   = de[i][j] LeakyReLU'(s1[i] + s2[j])   (0 on masked edges)
+//   ds1[i] = sum_j dp[i][j]   ds2[j] = sum_i dp[i][j]
+//   dWh[i][u] += ds1[i] a[u] + ds2[i] a[CO+u]        g_a[u] += sum_i ds1[i] Wh[i][u]   g_a[CO+u] += sum_j ds2[j] Wh[j][u]
+// The forward leaves s1, s2, att and M in `st`, so the backward kernel recomputes nothing twice.
+// Same semantics as attn_forward_pixel / attn_backward_pixel with PIXEL = false (reference baseline_model.py:127-160).
+// =============================================================================================
+template <typename P, int NODES>
+struct NbState {
+  typename P::T s1[NODES], s2[NODES];
+  typename P::T att[NODES][NODES];
+  typename P::T M[NODES][NODES];  // [v][j]
+};
+
+template <typename P, int NODES, int CO, bool MASKED>
+CGAT_HD void attn_nb_forward(const typename P::T (&Wh)[NODES][CO], const typename P::T* __restrict__ a,
+                             const typename P::T* __restrict__ adj, const uint64_t* __restrict__ maskrow,
+                             typename P::T alpha, NbState<P, NODES>& st, typename P::T (&z)[NODES][CO]) {
+  using T = typename P::T;
+#pragma unroll
+  for (int i = 0; i < NODES; ++i) {
+    T p = P::mul(Wh[i][0], a[0]), q = P::mul(Wh[i][0], a[CO]);
+#pragma unroll
+    for (int u = 1; u < CO; ++u) {
+      p = P::fma(Wh[i][u], a[u], p);
+      q = P::fma(Wh[i][u], a[CO + u], q);
+    }
+    st.s1[i] = p;
+    st.s2[i] = q;
+  }
+#pragma unroll
+  for (int i = 0; i < NODES; ++i) {
+    const uint64_t mrow = MASKED ? maskrow[i] : ~0ull;
+    T m = P::zero();
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      const T pre = P::add(st.s1[i], st.s2[j]);
+      T e = P::max(pre, P::mul(alpha, pre));
+      if (MASKED && !((mrow >> j) & 1ull)) e = P::mask_fill();
+      st.att[i][j] = e;
+      m = j == 0 ? e : P::max(m, e);
+    }
+    const T nml = P::neg_l2e(m);
+    T sum = P::zero();
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      // (the FMA form loses exp(fill - fill) = 1 on fully masked rows: masked kernels subtract exactly)
+      st.att[i][j] = MASKED ? P::exp(P::sub(st.att[i][j], m)) : P::exp_sub(st.att[i][j], nml);
+      sum = j == 0 ? st.att[i][j] : P::add(sum, st.att[i][j]);
+    }
+    const T r = P::rcp(sum);
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) st.att[i][j] = P::mul(st.att[i][j], r);
+#pragma unroll
+    for (int v = 0; v < NODES; ++v) {
+      const T w = adj[i * NODES + v];
+#pragma unroll
+      for (int j = 0; j < NODES; ++j) st.M[v][j] = i == 0 ? P::mul(w, st.att[i][j]) : P::fma(w, st.att[i][j], st.M[v][j]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NODES; ++v)
+#pragma unroll
+    for (int u = 0; u < CO; ++u) {
+      T acc = P::mul(st.M[v][0], Wh[0][u]);
+#pragma unroll
+      for (int j = 1; j < NODES; ++j) acc = P::fma(st.M[v][j], Wh[j][u], acc);
+      z[v][u] = acc;
+    }
+}
+
+// dz: gradient w.r.t. the pre-ELU z.  dWh is OVERWRITTEN; g_a [2CO] and g_adj [NODES*NODES] are accumulated into.
+template <typename P, int NODES, int CO, bool MASKED>
+CGAT_HD void attn_nb_backward(const typename P::T (&Wh)[NODES][CO], const typename P::T (&dz)[NODES][CO],
+                              const typename P::T* __restrict__ a, const typename P::T* __restrict__ adj,
+                              const uint64_t* __restrict__ maskrow, typename P::T alpha, const NbState<P, NODES>& st,
+                              typename P::T (&dWh)[NODES][CO], typename P::T* __restrict__ g_a,
+                              typename P::T* __restrict__ g_adj) {
+  using T = typename P::T;
+  T datt[NODES][NODES];
+#pragma unroll
+  for (int v = 0; v < NODES; ++v) {
+    T dMv[NODES];
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      T acc = P::mul(dz[v][0], Wh[j][0]);
+#pragma unroll
+      for (int u = 1; u < CO; ++u) acc = P::fma(dz[v][u], Wh[j][u], acc);
+      dMv[j] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < NODES; ++j)
+#pragma unroll
+      for (int u = 0; u < CO; ++u)
+        dWh[j][u] = v == 0 ? P::mul(st.M[v][j], dz[v][u]) : P::fma(st.M[v][j], dz[v][u], dWh[j][u]);
+#pragma unroll
+    for (int i = 0; i < NODES; ++i) {
+      T g = g_adj[i * NODES + v];
+      const T w = adj[i * NODES + v];
+#pragma unroll
+      for (int j = 0; j < NODES; ++j) {
+        g = P::fma(st.att[i][j], dMv[j], g);
+        datt[i][j] = v == 0 ? P::mul(w, dMv[j]) : P::fma(w, dMv[j], datt[i][j]);
+      }
+      g_adj[i * NODES + v] = g;
+    }
+  }
+  const T one_minus_alpha = P::sub(P::bc(1.f), alpha);
+  T ds2[NODES];
+#pragma unroll
+  for (int i = 0; i < NODES; ++i) {
+    const uint64_t mrow = MASKED ? maskrow[i] : ~0ull;
+    T dot = P::mul(st.att[i][0], datt[i][0]);
+#pragma unroll
+    for (int j = 1; j < NODES; ++j) dot = P::fma(st.att[i][j], datt[i][j], dot);
+    T ds1 = P::zero();
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      const T de = P::mul(st.att[i][j], P::sub(datt[i][j], dot));
+      const T pre = P::add(st.s1[i], st.s2[j]);
+      T slope = P::fma(one_minus_alpha, P::gt0(pre), alpha);
+      if (MASKED && !((mrow >> j) & 1ull)) slope = P::zero();
+      const T dp = P::mul(de, slope);
+      ds1 = j == 0 ? dp : P::add(ds1, dp);
+      ds2[j] = i == 0 ? dp : P::add(ds2[j], dp);
+    }
+#pragma unroll
+    for (int u = 0; u < CO; ++u) {
+      dWh[i][u] = P::fma(ds1, a[u], dWh[i][u]);
+      g_a[u] = P::fma(ds1, Wh[i][u], g_a[u]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NODES; ++j)
+#pragma unroll
+    for (int u = 0; u < CO; ++u) {
+      dWh[j][u] = P::fma(ds2[j], a[CO + u], dWh[j][u]);
+      g_a[CO + u] = P::fma(ds2[j], Wh[j][u], g_a[CO + u]);
+    }
+}
+
 // linear projection helpers (reference baseline_model.py:127  Wh = h @ W, W is [CI][CO] row-major)
 template <typename P, int NODES, int CI, int CO>
 CGAT_HD void project_linear(const typename P::T (&X)[NODES][CI], const typename P::T* __restrict__ W,

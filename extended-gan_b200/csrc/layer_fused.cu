@@ -39,6 +39,7 @@ constexpr int LF_TAPS = 9, LF_KW = 3;
 constexpr int LF_HDR = 6144;        // barriers + parameters
 
 struct LfArgs {
+  long long* dbg;              // developer aid: clock64() timeline of CTA 0 (cgat_layer_debug_timeline)
   const __nv_bfloat16* wpack;  // [2*npairs][npad][8] chunk-major packed dense weights (cgat_stream_prepare)
   const float* bias;           // [cout] dense bias
   const float* a;              // [heads][2co]
@@ -59,6 +60,17 @@ struct LfArgs {
   int tiles_h, tiles_w, tiles, xstg;
   uint32_t wbytes, stage_bytes, xs_bytes, im_off;
 };
+
+// timeline events of CTA 0's first LF_DBG_TILES tiles: [tile][event]
+//  0 P:loop top  1 P:stage empty  2 P:x landed  3 P:im2col done | 4 M:im2col full  5 M:acc free  6 M:fprop issued
+//  7 M:dWh planes full  8 M:wgrad issued | 9 A:Wh ready  10 A:Wh in registers  11 A:forward done  12 A:after exchange
+//  13 A:backward done  14 A:tile done           (A = attention group 0, warp 0, lane 0)
+constexpr int LF_DBG_TILES = 16, LF_DBG_EVENTS = 16;
+#define LDBG(ev)                                                                                                 \
+  do {                                                                                                           \
+    if (A.dbg != nullptr && blockIdx.x == 0 && it < LF_DBG_TILES) A.dbg[it * LF_DBG_EVENTS + (ev)] = clock64();   \
+  } while (0)
+static long long* g_lf_dbg = nullptr;
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -176,8 +188,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       int it = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         const int stage = it & 1, buf = it % A.xstg;
+        if (threadIdx.x == 0) LDBG(0);
         mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        if (threadIdx.x == 0) LDBG(1);
         mbar_wait(&sbar[buf], (uint32_t)(it / A.xstg) & 1u);
+        if (threadIdx.x == 0) LDBG(2);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int m = threadIdx.x + half * LF_PROD;
@@ -198,6 +213,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         mbar_arrive(&sfree[buf]);
         fence_proxy_async_smem();
+        if (threadIdx.x == 0) LDBG(3);
         mbar_arrive(&full[stage]);
       }
     } else if (warp == LF_TMA_WARP && lane == 0) {
@@ -225,6 +241,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       auto wgrad = [&](int j) {
         const int s = j & 1;
         mbar_wait(&dyfull[s], ((uint32_t)j >> 1) & 1u);
+        { const int it = j; LDBG(7); }
         tc_fence_after();
         const uint32_t dy_addr = smem_u32(s_stage) + (uint32_t)s * A.stage_bytes;
         const uint32_t im_addr = dy_addr + A.im_off;
@@ -236,6 +253,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         wg_accum = 1;
         umma_commit(&empty[s]);
+        { const int it = j; LDBG(8); }
       };
       mbar_wait(wbar, 0);
       int it = 0;
@@ -243,7 +261,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         const int stage = it & 1;
         const uint32_t ph = ((uint32_t)it >> 1) & 1u;
         mbar_wait(&full[stage], ph);
+        LDBG(4);
         mbar_wait(&tempty[stage], ph ^ 1u);
+        LDBG(5);
         tc_fence_after();
         const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + A.im_off;
         const uint32_t d_addr = tmem_base + LF_FP_COL0 + (uint32_t)stage * 128;
@@ -253,6 +273,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           umma_bf16(d_addr, ad, bd, idesc_f, p > 0);
         }
         umma_commit(&tfull[stage]);
+        LDBG(6);
         if constexpr (!BWD) {
           umma_commit(&empty[stage]);
         } else if (it > 0) {
@@ -322,6 +343,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         mbar_wait(&tfull[acc], ph);
         tc_fence_after();
+        const bool dbg_thread = g == 0 && m == 0;
+        if (dbg_thread) LDBG(9);
         float oacc[(!BWD) ? REC : 1];
         if (!BWD) {
 #pragma unroll
@@ -333,6 +356,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
 #pragma unroll
           for (int q = 0; q < REC / 8; ++q) tmem_ld8_nowait(t_addr + q * 8, &rec[q * 8]);
           tmem_ld_wait();
+          if (dbg_thread) LDBG(10);
           if (k + LF_GROUPS >= A.heads) {  // last head of this group: the accumulator may be overwritten
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
@@ -341,12 +365,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           float Wh[NODES][CO];
           rec_to_mat<NODES, CO, SPATIAL>(rec, Wh);
           float z[NODES][CO];
-#pragma unroll
-          for (int v = 0; v < NODES; ++v)
-#pragma unroll
-            for (int u = 0; u < CO; ++u) z[v][u] = 0.f;
-          attn_forward_pixel<F32, NODES, CO, false, MASKED>(Wh, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask, A.alpha,
-                                                    nullptr, nullptr, z);
+          NbState<F32, NODES> st;
+          attn_nb_forward<F32, NODES, CO, MASKED>(Wh, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask, A.alpha, st, z);
+          if (dbg_thread) LDBG(11);
           if constexpr (!BWD) {
             if (A.apply_elu) {
 #pragma unroll
@@ -423,6 +444,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               }
               if (g == 0 && valid) loss_acc += lsum;
               named_bar_sync(1, 128 * nact);  // all heads read: the planes may now take d(Wh)
+              if (dbg_thread) LDBG(12);
               rec_to_mat<NODES, CO, SPATIAL>(rec, dz);
 #pragma unroll
               for (int v = 0; v < NODES; ++v)
@@ -453,13 +475,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
                   dz[v][u] = dz[v][u] * gscale * (A.apply_elu ? elu_grad<F32>(z[v][u]) : 1.f);
             }
             if (k != cur_head) { flush(cur_head); cur_head = k; }
-#pragma unroll
-            for (int v = 0; v < NODES; ++v)
-#pragma unroll
-              for (int u = 0; u < CO; ++u) z[v][u] = 0.f;  // z is reused as d(Wh)
-            attn_backward_pixel<F32, NODES, CO, false, 0, MASKED>(Wh, dz, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask,
-                                                          A.alpha, nullptr, nullptr, nullptr, z, &gacc[NODES * NODES],
-                                                          &gacc[0], nullptr);
+            attn_nb_backward<F32, NODES, CO, MASKED>(Wh, dz, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask, A.alpha, st,
+                                                     z, &gacc[NODES * NODES], &gacc[0]);  // z now holds d(Wh)
+            if (dbg_thread) LDBG(13);
             mat_to_rec<NODES, CO, SPATIAL>(z, rec);
             // d(Wh) -> the MN-major A operand of the wgrad MMA: plane = dense cout / 8, 16 bytes per pixel
             const uint32_t dy = smem_u32(s_stage) + (uint32_t)acc * A.stage_bytes + (uint32_t)(k * (REC / 8)) * 2048 +
@@ -479,6 +497,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         if constexpr (BWD) {
           fence_proxy_async_smem();
           mbar_arrive(&dyfull[acc]);
+          if (dbg_thread) LDBG(14);
         } else if (!concat) {
           // ---- head mean: every group leaves its partial sum in its slab, then all active threads combine ----
           float4* slab = s_slab + (size_t)g * (REC / 4) * 128;
@@ -662,6 +681,7 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   CUtensorMap map;
   if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, g.wp, g.hp)) return rc;
   LfArgs A{};
+  A.dbg = g_lf_dbg;
   A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
   A.out = (__nv_bfloat16*)out; A.dout = (const __nv_bfloat16*)dout; A.dwh = (__nv_bfloat16*)dwh;
   A.partial = partial; A.ga = ga; A.gadj = gadj;
@@ -681,6 +701,9 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
 }  // namespace cgat
 
 using namespace cgat;
+
+// developer aid, not part of the public header: registers a device buffer [16][16] int64 for the kernel timeline
+extern "C" void cgat_layer_debug_timeline(long long* device_buffer) { g_lf_dbg = device_buffer; }
 
 extern "C" int cgat_layer_supported(const cgat_layer_desc* d) { return layer_supported(d); }
 

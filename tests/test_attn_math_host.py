@@ -90,3 +90,34 @@ def test_forward_backward_match_oracle(host_harness, nodes, ci, co, masked, axis
     torch.testing.assert_close(torch.from_numpy(gW), Wr.grad, rtol=1e-4, atol=2e-4)
     torch.testing.assert_close(torch.from_numpy(ga), ar.grad, rtol=1e-4, atol=2e-4)
     torch.testing.assert_close(torch.from_numpy(gadj), adj.grad, rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("nodes,ci,co", CASES)
+@pytest.mark.parametrize("masked", [False, True])
+def test_restructured_neighbour_math_matches_oracle(host_harness, nodes, ci, co, masked):
+    """attn_nb_forward / attn_nb_backward (M = adj^T.att form used by the fused layer kernels) vs autograd."""
+    hh = host_harness
+    P = 41
+    X, W, a, B, mask, dZ = make(nodes, ci, co, P, 1234 + nodes, masked)
+    Xr, Wr, ar, Br = (t.clone().requires_grad_() for t in (X, W, a, B))
+    adj = spec.adjacency_norm(Br)
+    adj.retain_grad()
+    z = spec.attention_core(Xr @ Wr, ar, adj, alpha=0.2, softmax_axis="neighbour", mask=mask, apply_elu=False)
+    z.backward(dZ)
+    rows = maskrows(mask.numpy())
+    adj_c = adj.detach().contiguous()
+    n_pix = 2 * P
+    zo = torch.zeros(n_pix, nodes, co)
+    dXo = torch.zeros(n_pix, nodes, ci)
+    gW = np.zeros((ci, co), np.float32)
+    ga = np.zeros(2 * co, np.float32)
+    gadj = np.zeros((nodes, nodes), np.float32)
+    # the unmasked instantiation is only valid for an all-ones mask
+    assert hh.hh_nb(nodes, ci, co, int(masked), n_pix, fp(X.reshape(n_pix, nodes, ci)), fp(dZ.reshape(n_pix, nodes, co)),
+                    fp(W), fp(a), fp(adj_c), rows.ctypes.data_as(U64), ctypes.c_float(0.2), fp(zo), fp(dXo),
+                    gW.ctypes.data_as(F), ga.ctypes.data_as(F), gadj.ctypes.data_as(F)) == 0
+    torch.testing.assert_close(zo.reshape(2, P, nodes, co), z.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dXo.reshape(2, P, nodes, ci), Xr.grad, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(torch.from_numpy(gW), Wr.grad, rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(torch.from_numpy(ga), ar.grad, rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(torch.from_numpy(gadj), adj.grad, rtol=1e-4, atol=2e-4)

@@ -1,0 +1,37 @@
+"""Developer aid: clock64() timeline of CTA 0 of the fused layer kernel (train mode) at the bench size."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "extended-gan_b200")]
+import torch
+from cgat import _lib
+from cgat.train_step import TrainStep
+from convolutional_gat.GAT3D.GATMultistream import Model
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "train"
+torch.manual_seed(369)
+dev = "cuda"
+m = Model(image_width=64, image_height=64, n_vertices=6, attention_type="temporal", mapping_type="conv").to(dev)
+x = torch.rand(64, 64, 64, 4, 6, device=dev).bfloat16()
+y = torch.rand(64, 64, 64, 4, 6, device=dev).bfloat16()
+ts = TrainStep(m, x, y, use_graph=False, fuse_loss=(mode == "train"))
+for _ in range(3):
+    ts.run()
+buf = torch.zeros(16, 16, dtype=torch.int64, device=dev)
+L = _lib.lib()
+L.cgat_layer_debug_timeline.argtypes = [ctypes.c_void_p]
+L.cgat_layer_debug_timeline.restype = None
+L.cgat_layer_debug_timeline(ctypes.c_void_p(buf.data_ptr()))
+if mode == "fwd":
+    with torch.no_grad():
+        m(x)
+else:
+    ts.run()
+torch.cuda.synchronize()
+L.cgat_layer_debug_timeline(None)
+t = buf.cpu()
+t0 = int(t[0][t[0] > 0].min())
+names = ["Ptop", "Pempty", "Pxland", "Pdone", "Mfull", "Maccfr", "Mfprop", "Mdyfull", "Mwgrad", "Awh", "Aregs", "Afwd",
+         "Aexch", "Abwd", "Adone"]
+print("tile " + " ".join(f"{n:>8s}" for n in names))
+for i in range(14):
+    print(f"{i:4d} " + " ".join(f"{(int(v) - t0) if v > 0 else -1:8d}" for v in t[i][:15]))
