@@ -58,16 +58,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait is potentially blocking: the thread is suspended until the phase completes or the time hint (ns)
-// elapses, so a LARGE hint costs no wake-up latency and keeps waiting warps from burning issue slots in a spin loop
+// try_wait is potentially blocking (the hardware suspends the thread for a bounded time), so the loop in
+// mbar_wait does not spin hot.  (Measured on B200: test_wait polling and try_wait with a long suspend-time hint
+// give the same kernel times; the plain form is kept.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }

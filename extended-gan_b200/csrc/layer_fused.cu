@@ -4,24 +4,30 @@
 // and reads them back (twice in the backward, plus d(Wh) once more for wgrad): 3/4 of the step's HBM traffic is
 // that intermediate.  Here Wh never leaves the SM:
 //
-//   x halo tile --TMA--> staging --4 producer warps--> im2col planes in shared memory
+//   x --TMA--> "row planes" in shared memory
 //        --tcgen05.mma (M = 128 pixels, N = heads*nodes*co, K = 9 taps * cin)--> Wh in TMEM (fp32)
 //        --tcgen05.ld: TMEM lane = pixel, so each thread receives exactly ITS pixel's record-->
 //        per-pixel attention in registers (attn_math.cuh, fp32): logits, LeakyReLU, mask, soft-max over the
 //        neighbours, aggregation, adjacency mix, ELU (reference baseline_model.py:127-160)
 //   forward : head merge through shared memory, coalesced bf16 store of out
 //   backward: the forward is recomputed, then d(Wh) (bf16) goes straight into the shared-memory planes that
-//             are the A operand of the wgrad MMA (M = couts, N = 9*cin + ones column for dbias, K = pixels);
-//             the wgrad accumulator stays in TMEM across all tiles of the persistent CTA.  Only x and d(out)
-//             are read from HBM; only per-CTA partial sums of the parameter gradients are written.
+//             are the A operand of the wgrad MMA (M = couts, K = pixels); the wgrad accumulators stay in TMEM
+//             across all tiles of the persistent CTA.  Only x and d(out) (train mode: x and y) are read from
+//             HBM; only per-CTA partial sums of the parameter gradients are written.
 //
-// One im2col operand serves both GEMMs: planes [k-chunk = c*9 + tap][128 pixels][8 channels] are K-major for
-// the fprop A operand (K = channels x taps) and MN-major for the wgrad B operand (K = pixels).
+// Row planes (the im2col that is NOT materialised): for vertical tap r and 8-channel chunk c the TMA unit writes the
+// box  x[n][th*16-1+r .. +15][tw*8-1 .. +9][8c .. 8c+7]  as plane P(r,c) = [16 rows][10 cols][16 B]  (zero-filled
+// outside the image = the conv padding).  A horizontal tap s is then just a 16-byte shift of the operand's start
+// address: the 8 pixels of tile row hr are the contiguous 128 bytes at P + (hr*10 + s)*16, tile rows are 160 B
+// apart, planes 2560 B apart -- a legal SWIZZLE_NONE operand both K-major (fprop A: K = (s; r,c) chunks) and
+// MN-major (wgrad B: K = pixels, N = (r,c) chunks, one accumulator per s).  9 boxes per tile replace the producer
+// warps, the staging buffers and 56 KB of im2col; a stage is 25 KB, so 4 tiles are in flight.  A tenth plane of
+// ones per stage carries the bias into the fprop MMA and yields dbias in the wgrad MMA.
 //
-// Warp roles (512 threads, 1 CTA / SM): warps 0-1 im2col producers (two pixels each), warp 2 MMA issuer + TMEM
-// allocator, warp 3 TMA issuer, warps 4-15 three attention groups (group g owns heads g, g+3, ...; warp % 4
-// selects the TMEM lane quarter).  The kernel launches with 128 registers per thread; setmaxnreg moves the
-// budget of warpgroup 0 (56) to the attention warpgroups (152 each: 56 + 3 * 152 = 512 = the CTA's pool).
+// Warp roles (512 threads, 1 CTA / SM): warp 0 TMA issuer, warp 1 MMA issuer + TMEM allocator, warps 4-15 three
+// attention groups (group g owns heads g, g+3, ...; warp % 4 selects the TMEM lane quarter).  The kernel launches
+// with 128 registers per thread; setmaxnreg moves warpgroup 0's budget to the attention warpgroups
+// (24 + 3 * 160 <= 512 = the CTA's pool).
 #include "tc_common.cuh"
 #include "attn_common.cuh"
 
@@ -29,13 +35,14 @@ namespace cgat {
 
 constexpr int LF_TH = 16, LF_TW = 8;  // output tile -> M = 128 pixels
 constexpr int LF_THREADS = 512;
-constexpr int LF_PROD = 64;
 constexpr int LF_ATT_WARP0 = 4;
 constexpr int LF_GROUPS = 3;
-constexpr int LF_MMA_WARP = 2, LF_TMA_WARP = 3;
-constexpr int LF_XSTG = 3;          // x halo staging buffers (TMA prefetch depth; 2 when shared memory is short)
-constexpr int LF_FP_COL0 = 256;     // TMEM: wgrad accumulator at columns [0,256), fprop accumulators at 256 + 128*acc
-constexpr int LF_TAPS = 9, LF_KW = 3;
+constexpr int LF_TMA_WARP = 0, LF_MMA_WARP = 1;
+constexpr int LF_MAXSTG = 4;        // row-plane stages (TMA prefetch depth)
+constexpr int LF_FP_COL0 = 256;     // TMEM: wgrad accumulators at columns [0,256), fprop accumulators at 256 + 128*acc
+constexpr int LF_WP = LF_TW + 2;    // plane columns (halo)
+constexpr int LF_PLANE = LF_TH * LF_WP * 16;  // 2560 B
+constexpr int LF_ROW = LF_WP * 16;            // 160 B between tile rows of a plane
 constexpr int LF_HDR = 6144;        // barriers + parameters
 
 struct LfArgs {
@@ -56,9 +63,9 @@ struct LfArgs {
   float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
   int h, w, cin, cout, npad, heads, merge, apply_elu;
   float alpha;
-  int nchunk, npairs, mchunk, nt, hp, wp;
-  int tiles_h, tiles_w, tiles, xstg;
-  uint32_t wbytes, stage_bytes, xs_bytes, im_off;
+  int nchunk, nq, mchunk, nt;   // nq = 3*nchunk + 1 planes per stage (the last one is all ones); nt = 3 * nq * 8
+  int tiles_h, tiles_w, tiles, nstg;
+  uint32_t wbytes, stage_bytes, im_off;
 };
 
 // timeline events of CTA 0's first LF_DBG_TILES tiles: [tile][event]
@@ -113,14 +120,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   constexpr int RG = 2 * CO + NODES * NODES;  // a-grad + adjacency-grad values per head
   static_assert(REC % 8 == 0, "record must be a multiple of 16 bytes");
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [2]  producers -> MMA   (im2col planes ready)
-  uint64_t* empty = full + 2;                          // [2]  MMA -> producers   (stage reusable)
-  uint64_t* tfull = empty + 2;                         // [2]  MMA -> attention   (Wh accumulator ready)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [4]  TMA -> MMA         (row planes landed)
+  uint64_t* empty = full + LF_MAXSTG;                  // [4]  MMA -> TMA         (stage reusable)
+  uint64_t* dyfull = empty + LF_MAXSTG;                // [4]  attention -> MMA   (d(Wh) planes written)
+  uint64_t* tfull = dyfull + LF_MAXSTG;                // [2]  MMA -> attention   (Wh accumulator ready)
   uint64_t* tempty = tfull + 2;                        // [2]  attention -> MMA   (accumulator drained)
-  uint64_t* dyfull = tempty + 2;                       // [2]  attention -> MMA   (d(Wh) planes written)
-  uint64_t* sbar = dyfull + 2;                         // [3]  TMA landed
-  uint64_t* sfree = sbar + LF_XSTG;                    // [3]  staging consumed
-  uint64_t* wbar = sfree + LF_XSTG;                    // [1]
+  uint64_t* wbar = tempty + 2;                         // [1]
   uint64_t* done = wbar + 1;                           // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
   float* s_a = reinterpret_cast<float*>(smem + 768);             // [MAX_HEADS][2*CO]
@@ -130,19 +135,15 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   static_assert(MAX_HEADS * 2 * CO * 4 <= 512 && MAX_HEADS * NODES * NODES * 4 <= 2048 && NODES * 8 <= 64 &&
                     3392 + (MAX_HEADS * RG + 1) * 4 <= LF_HDR, "parameter block overflows the header");
   unsigned char* s_w = smem + LF_HDR;
-  unsigned char* s_stag = s_w + ((A.wbytes + 127u) & ~127u);
-  unsigned char* s_stage = s_stag + (size_t)A.xstg * A.xs_bytes;
-  float4* s_slab = reinterpret_cast<float4*>(s_stage + 2 * (size_t)A.stage_bytes);  // fwd: [group][REC/4][128]
+  unsigned char* s_stage = s_w + ((A.wbytes + 127u) & ~127u);
+  float4* s_slab = reinterpret_cast<float4*>(s_stage + (size_t)A.nstg * A.stage_bytes);  // fwd: [group][REC/4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nact = A.heads < LF_GROUPS ? A.heads : LF_GROUPS;  // attention groups that own at least one head
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full[i], LF_PROD); mbar_init(&empty[i], 1); mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128 * nact); mbar_init(&dyfull[i], 128 * nact);
-    }
-    for (int i = 0; i < LF_XSTG; ++i) { mbar_init(&sbar[i], 1); mbar_init(&sfree[i], LF_PROD); }
+    for (int i = 0; i < LF_MAXSTG; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&dyfull[i], 128 * nact); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128 * nact); }
     mbar_init(wbar, 1);
     mbar_init(done, 1);
     fence_mbar_init();
@@ -161,15 +162,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     // every plane starts zeroed (padding planes must hold finite numbers); then the plane of ones that
     // follows the im2col planes (its wgrad column is dbias; its fprop K-chunk holds the bias, hi + lo bf16 parts)
     uint4* p = reinterpret_cast<uint4*>(s_stage);
-    const int n16 = (int)(2 * (size_t)A.stage_bytes / 16);
+    const int n16 = (int)((size_t)A.nstg * A.stage_bytes / 16);
     for (int i = threadIdx.x; i < n16; i += LF_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    {
-      for (int s = 0; s < 2; ++s) {
-        uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)s * A.stage_bytes + A.im_off +
-                                                  (size_t)(A.nchunk * LF_TAPS) * 2048);
-        for (int i = threadIdx.x; i < 512; i += LF_THREADS) o[i] = 0x3f803f80u;  // bf16 1.0 x2
-      }
+    for (int st = 0; st < A.nstg; ++st) {
+      uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)st * A.stage_bytes + A.im_off +
+                                                (size_t)(A.nq - 1) * LF_PLANE);
+      for (int i = threadIdx.x; i < LF_PLANE / 4; i += LF_THREADS) o[i] = 0x3f803f80u;  // bf16 1.0 x2
     }
     fence_proxy_async_smem();
   }
@@ -180,105 +179,93 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp < LF_ATT_WARP0) {
-    setmaxnreg_dec<56>();
-    if (warp < LF_PROD / 32) {
-      // ===================== im2col producers: thread t re-lays tile pixels t and t + 64 =====================
-      const uint32_t pix_bytes = (uint32_t)A.cin * 2;
-      const uint32_t row_bytes = (uint32_t)A.wp * pix_bytes;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1, buf = it % A.xstg;
-        if (threadIdx.x == 0) LDBG(0);
-        mbar_wait(&empty[stage], (((uint32_t)it >> 1) & 1u) ^ 1u);
-        if (threadIdx.x == 0) LDBG(1);
-        mbar_wait(&sbar[buf], (uint32_t)(it / A.xstg) & 1u);
-        if (threadIdx.x == 0) LDBG(2);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int m = threadIdx.x + half * LF_PROD;
-          const int hr = m >> 3, wc = m & 7;
-          const uint32_t sg = smem_u32(s_stag) + (uint32_t)buf * A.xs_bytes + ((uint32_t)(hr * A.wp + wc)) * pix_bytes;
-          const uint32_t st = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + A.im_off + (uint32_t)m * 16;
-          for (int c = 0; c < A.nchunk; ++c) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              uint4 v[3];
-#pragma unroll
-              for (int s = 0; s < 3; ++s)
-                v[s] = lf_lds128(sg + (uint32_t)r * row_bytes + (uint32_t)s * pix_bytes + (uint32_t)c * 16);
-#pragma unroll
-              for (int s = 0; s < 3; ++s) lf_sts128(st + (uint32_t)(c * LF_TAPS + r * LF_KW + s) * 2048, v[s]);
-            }
-          }
-        }
-        mbar_arrive(&sfree[buf]);
-        fence_proxy_async_smem();
-        if (threadIdx.x == 0) LDBG(3);
-        mbar_arrive(&full[stage]);
-      }
-    } else if (warp == LF_TMA_WARP && lane == 0) {
-      // ===================== TMA issuer =====================
+    setmaxnreg_dec<24>();
+    if (warp == LF_TMA_WARP && lane == 0) {
+      // ===================== TMA issuer: 9 row-plane boxes per tile =====================
       mbar_arrive_expect_tx(wbar, A.wbytes);
       bulk_g2s(s_w, A.wpack, A.wbytes, wbar);
-      const uint32_t xbytes = (uint32_t)A.hp * A.wp * A.cin * 2;
-      int it = 0;
+      const uint32_t tile_bytes = (uint32_t)(A.nq - 1) * LF_PLANE;
+      int it = 0, stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         const int tw = tile % A.tiles_w;
         const int th = (tile / A.tiles_w) % A.tiles_h;
         const int n = tile / (A.tiles_w * A.tiles_h);
-        const int buf = it % A.xstg;
-        mbar_wait(&sfree[buf], ((uint32_t)(it / A.xstg) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&sbar[buf], xbytes);
-        tma_load_4d(s_stag + (size_t)buf * A.xs_bytes, &tmap_x, 0, tw * LF_TW - 1, th * LF_TH - 1, n, &sbar[buf]);
+        LDBG(0);
+        mbar_wait(&empty[stage], phase ^ 1u);
+        LDBG(1);
+        mbar_arrive_expect_tx(&full[stage], tile_bytes);
+        unsigned char* dst = s_stage + (size_t)stage * A.stage_bytes + A.im_off;
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < A.nchunk; ++c)
+            tma_load_4d(dst + (size_t)(r * A.nchunk + c) * LF_PLANE, &tmap_x, c * 8, tw * LF_TW - 1, th * LF_TH - 1 + r, n,
+                        &full[stage]);
+        if (++stage == A.nstg) { stage = 0; phase ^= 1u; }
       }
     } else if (warp == LF_MMA_WARP && lane == 0) {
       // ===================== MMA issuer =====================
       const uint32_t idesc_f = make_idesc_bf16(128, A.npad, 0, 0);
-      const uint32_t idesc_w = make_idesc_bf16(128, A.nt, 1, 1);
+      const uint32_t idesc_w = make_idesc_bf16(128, A.nq * 8, 1, 1);
       const uint32_t w_addr = smem_u32(s_w);
       const uint32_t b_lbo = (uint32_t)A.npad * 16;
       uint32_t wg_accum = 0;
-      auto wgrad = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&dyfull[s], ((uint32_t)j >> 1) & 1u);
+      int wstage = 0;
+      uint32_t wphase = 0;
+      auto wgrad = [&](int j) {  // tiles are retired in order: (wstage, wphase) follow tile j
+        mbar_wait(&dyfull[wstage], wphase);
         { const int it = j; LDBG(7); }
         tc_fence_after();
-        const uint32_t dy_addr = smem_u32(s_stage) + (uint32_t)s * A.stage_bytes;
+        const uint32_t dy_addr = smem_u32(s_stage) + (uint32_t)wstage * A.stage_bytes;
         const uint32_t im_addr = dy_addr + A.im_off;
+        for (int sh = 0; sh < 3; ++sh) {  // horizontal tap = 16-byte shift of the planes; one accumulator each
 #pragma unroll
-        for (int jj = 0; jj < LF_TH / 2; ++jj) {  // K step: image rows 2jj, 2jj+1 of the tile (16 pixels)
-          const uint64_t ad = make_smem_desc(dy_addr + jj * 256, 128, 2048);
-          const uint64_t bd = make_smem_desc(im_addr + jj * 256, 128, 2048);
-          umma_bf16(tmem_base, ad, bd, idesc_w, wg_accum | (uint32_t)(jj > 0));
+          for (int jj = 0; jj < LF_TH / 2; ++jj) {  // K step: image rows 2jj, 2jj+1 of the tile (16 pixels)
+            const uint64_t ad = make_smem_desc(dy_addr + jj * 256, 128, 2048);
+            const uint64_t bd = make_smem_desc(im_addr + sh * 16 + jj * 2 * LF_ROW, LF_ROW, LF_PLANE);
+            umma_bf16(tmem_base + (uint32_t)(sh * A.nq * 8), ad, bd, idesc_w, wg_accum | (uint32_t)(jj > 0));
+          }
         }
         wg_accum = 1;
-        umma_commit(&empty[s]);
+        umma_commit(&empty[wstage]);
         { const int it = j; LDBG(8); }
+        if (A.dbg != nullptr && A.dbg[255] != 0) {
+          mbar_wait(&empty[wstage], wphase);
+          { const int it = j; LDBG(3); }
+        }
+        if (++wstage == A.nstg) { wstage = 0; wphase ^= 1u; }
       };
       mbar_wait(wbar, 0);
-      int it = 0;
+      int it = 0, stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
-        const uint32_t ph = ((uint32_t)it >> 1) & 1u;
-        mbar_wait(&full[stage], ph);
+        const int acc = it & 1;
+        mbar_wait(&full[stage], phase);
         LDBG(4);
-        mbar_wait(&tempty[stage], ph ^ 1u);
+        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
         LDBG(5);
         tc_fence_after();
         const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + A.im_off;
-        const uint32_t d_addr = tmem_base + LF_FP_COL0 + (uint32_t)stage * 128;
-        for (int p = 0; p < A.npairs; ++p) {
-          const uint64_t ad = make_smem_desc(im_addr + (uint32_t)p * 4096, 2048, 128);
-          const uint64_t bd = make_smem_desc(w_addr + (uint32_t)p * 2 * b_lbo, b_lbo, 128);
-          umma_bf16(d_addr, ad, bd, idesc_f, p > 0);
+        const uint32_t d_addr = tmem_base + LF_FP_COL0 + (uint32_t)acc * 128;
+        uint32_t kk = 0;
+        for (int sh = 0; sh < 3; ++sh) {
+          for (int q = 0; q < A.nq; q += 2, kk += 2) {  // K = 16: planes q, q+1 of horizontal tap sh
+            const uint64_t ad = make_smem_desc(im_addr + (uint32_t)q * LF_PLANE + sh * 16, LF_PLANE, LF_ROW);
+            const uint64_t bd = make_smem_desc(w_addr + kk * b_lbo, b_lbo, 128);
+            umma_bf16(d_addr, ad, bd, idesc_f, kk > 0);
+          }
         }
-        umma_commit(&tfull[stage]);
+        umma_commit(&tfull[acc]);
         LDBG(6);
+        if (A.dbg != nullptr && A.dbg[255] != 0) {  // developer probe: execution time of the fprop MMAs in isolation
+          mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
+          LDBG(2);
+        }
         if constexpr (!BWD) {
           umma_commit(&empty[stage]);
         } else if (it > 0) {
           wgrad(it - 1);
         }
+        if (++stage == A.nstg) { stage = 0; phase ^= 1u; }
       }
       if constexpr (BWD) {
         if (it > 0) wgrad(it - 1);
@@ -287,7 +274,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     }
   } else if (warp >= LF_ATT_WARP0 && warp < LF_ATT_WARP0 + 4 * LF_GROUPS) {
     // ===================== attention groups =====================
-    setmaxnreg_inc<152>();
+    setmaxnreg_inc<160>();
     const int g = (warp - LF_ATT_WARP0) >> 2;
     const int lg = warp & 3;
     const int m = lg * 32 + lane;  // TMEM lane = pixel of the tile
@@ -311,10 +298,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
       };
       const float inv_heads = 1.f / (float)A.heads;
-      int it = 0;
+      int it = 0, stage = -1;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+        if (++stage == A.nstg) stage = 0;
         const int tw = tile % A.tiles_w;
         const int th = (tile / A.tiles_w) % A.tiles_h;
         const int n = tile / (A.tiles_w * A.tiles_h);
@@ -328,8 +316,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           const __nv_bfloat16* src = A.y != nullptr ? A.y + pix * REC
                                                     : (vec_io ? A.dout + pix * out_rec + (concat ? g * REC : 0) : nullptr);
 #pragma unroll
-          for (int q = 0; q < REC / 8; ++q)
-            pre[q] = (valid && src != nullptr) ? __ldg(reinterpret_cast<const uint4*>(src) + q) : make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < REC / 8; ++q) {
+            pre[q] = make_uint4(0, 0, 0, 0);
+            if (valid && src != nullptr)  // volatile: the request must be issued HERE, not sunk to its use
+              asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(pre[q].x), "=r"(pre[q].y), "=r"(pre[q].z), "=r"(pre[q].w)
+                           : "l"(reinterpret_cast<const uint4*>(src) + q));
+          }
           const int ntile = tile + gridDim.x;
           if (g == 0 && ntile < A.tiles) {
             const int ntw = ntile % A.tiles_w, nth = (ntile / A.tiles_w) % A.tiles_h, nn = ntile / (A.tiles_w * A.tiles_h);
@@ -400,7 +393,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               // ---- train mode (mean merge, one head per group): out = mean_k ELU(z_k) needs every head of the
               //      pixel, so the groups swap their ELU(z) through the (still unused) d(Wh) planes of this stage
               //      as fp16; d(out) = (2 (out - y) - lambda) / numel   (convolutional_gat/train.py:131) ----
-              const uint32_t exb = smem_u32(s_stage) + (uint32_t)acc * A.stage_bytes + (uint32_t)m * 16;
+              const uint32_t exb = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + (uint32_t)m * 16;
 #pragma unroll
               for (int v = 0; v < NODES; ++v)
 #pragma unroll
@@ -416,6 +409,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
 #undef PKH
                 lf_sts128(exb + (uint32_t)(k * (REC / 8) + q) * 2048, v);
               }
+              if (m == 0 && g == 0) LDBG(15);
               named_bar_sync(1, 128 * nact);
               float yv[REC];
               unpack_rec<REC>(pre, yv);
@@ -480,7 +474,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
             if (dbg_thread) LDBG(13);
             mat_to_rec<NODES, CO, SPATIAL>(z, rec);
             // d(Wh) -> the MN-major A operand of the wgrad MMA: plane = dense cout / 8, 16 bytes per pixel
-            const uint32_t dy = smem_u32(s_stage) + (uint32_t)acc * A.stage_bytes + (uint32_t)(k * (REC / 8)) * 2048 +
+            const uint32_t dy = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + (uint32_t)(k * (REC / 8)) * 2048 +
                                 (uint32_t)m * 16;
 #pragma unroll
             for (int q = 0; q < REC / 8; ++q) {
@@ -496,7 +490,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         if constexpr (BWD) {
           fence_proxy_async_smem();
-          mbar_arrive(&dyfull[acc]);
+          mbar_arrive(&dyfull[stage]);
           if (dbg_thread) LDBG(14);
         } else if (!concat) {
           // ---- head mean: every group leaves its partial sum in its slab, then all active threads combine ----
@@ -569,10 +563,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
 
 // ---- host side ------------------------------------------------------------------------------------------
 struct LfGeom {
-  int cin, cout, rec, nchunk, npairs, npad, mchunk, nt, hp, wp;
-  uint32_t wbytes, xs_bytes, stage_bytes, im_off;
+  int cin, cout, rec, nchunk, nq, npad, mchunk, nt;
+  uint32_t wbytes, stage_bytes, im_off;
   size_t smem;
-  int tiles_h, tiles_w, tiles, xstg;
+  int tiles_h, tiles_w, tiles, nstg;
 };
 
 static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
@@ -581,26 +575,21 @@ static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
   g.cin = d->nodes * d->ci;
   g.cout = d->heads * g.rec;
   g.nchunk = g.cin / 8;
-  g.npairs = (g.nchunk * LF_TAPS + 1) / 2;
+  g.nq = 3 * g.nchunk + 1;            // row planes per stage, the last one all ones
   g.npad = (g.cout + 15) & ~15;
   g.mchunk = g.cout / 8;
-  g.nt = (LF_TAPS * g.cin + 8 + 15) & ~15;
-  g.hp = LF_TH + 2;
-  g.wp = LF_TW + 2;
-  g.wbytes = (uint32_t)g.npairs * 2 * g.npad * 16;
-  g.xs_bytes = (uint32_t)((g.hp * g.wp * g.cin * 2 + 127) & ~127);
-  int im_planes = g.nt / 8;
-  if (2 * g.npairs > im_planes) im_planes = 2 * g.npairs;
+  g.nt = 3 * g.nq * 8;                // wgrad partial columns: [s][(r,c) | ones][8]
+  g.wbytes = (uint32_t)(3 * g.nq) * g.npad * 16;
   g.im_off = bwd ? (uint32_t)g.mchunk * 2048 : 0;
-  int planes = (bwd ? g.mchunk : 0) + im_planes;
-  if (planes < 16) planes = 16;  // the wgrad A operand always spans 16 planes (M = 128)
-  g.stage_bytes = (uint32_t)planes * 2048;
-  g.xstg = LF_XSTG;
+  g.stage_bytes = g.im_off + (uint32_t)g.nq * LF_PLANE;
+  if (g.stage_bytes < 16 * 2048) g.stage_bytes = 16 * 2048;  // the wgrad A operand always spans 16 planes (M = 128)
+  g.stage_bytes = (g.stage_bytes + 127u) & ~127u;
+  g.nstg = LF_MAXSTG;
   do {
-    g.smem = LF_HDR + ((g.wbytes + 127u) & ~127u) + (size_t)g.xstg * g.xs_bytes + 2 * (size_t)g.stage_bytes +
+    g.smem = LF_HDR + ((g.wbytes + 127u) & ~127u) + (size_t)g.nstg * g.stage_bytes +
              (bwd ? 0 : (size_t)LF_GROUPS * g.rec * 128 * 4);
-  } while (g.smem > 227 * 1024 && --g.xstg >= 2);
-  if (g.xstg < 2) g.xstg = 2;
+  } while (g.smem > 227 * 1024 && --g.nstg >= 2);
+  if (g.nstg < 2) g.nstg = 2;
   g.tiles_h = (d->h + LF_TH - 1) / LF_TH;
   g.tiles_w = (d->w + LF_TW - 1) / LF_TW;
   g.tiles = d->n * g.tiles_h * g.tiles_w;
@@ -624,7 +613,7 @@ int layer_supported(const cgat_layer_desc* d) {
   if (!shape_ok) return 0;
   const LfGeom f = lf_geom(d, false), b = lf_geom(d, true);
   if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.nt > 256) return 0;
-  if ((f.nchunk * LF_TAPS) % 2 == 0) return 0;  // the bias / ones K-chunk is the odd tail of the last MMA pair
+  if (f.nq % 2) return 0;  // fprop consumes the planes (+ the ones plane) in pairs: K = 16 per tcgen05.mma
   if (f.smem > 227 * 1024 || b.smem > 227 * 1024) return 0;
   return 1;
 }
@@ -634,14 +623,14 @@ size_t layer_partial_bytes(const cgat_layer_desc* d) {
   return (size_t)148 * 128 * g.nt * sizeof(float);
 }
 
-// 4-D map over NHWC bf16 [n][h][w][c], box (c, wp, hp, 1): lands as [hp][wp][c]; out-of-image = zero (conv padding)
+// 4-D map over NHWC bf16 [n][h][w][c], box (8, wp, hp, 1): lands as [hp][wp][16 B]; out-of-image = zero (conv padding)
 static int make_nhwc_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int wp, int hp) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(CGAT_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   ensure_context();
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)wp, (cuuint32_t)hp, 1};
+  cuuint32_t box[4] = {8, (cuuint32_t)wp, (cuuint32_t)hp, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -679,7 +668,7 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
     return fail(CGAT_EALIGN, "layer tensors must be 16-byte aligned");
   const LfGeom g = lf_geom(d, bwd);
   CUtensorMap map;
-  if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, g.wp, g.hp)) return rc;
+  if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, LF_WP, LF_TH)) return rc;
   LfArgs A{};
   A.dbg = g_lf_dbg;
   A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
@@ -689,9 +678,9 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
   A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
-  A.nchunk = g.nchunk; A.npairs = g.npairs; A.mchunk = g.mchunk; A.nt = g.nt; A.hp = g.hp; A.wp = g.wp;
-  A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.xstg = g.xstg;
-  A.wbytes = g.wbytes; A.stage_bytes = g.stage_bytes; A.xs_bytes = g.xs_bytes; A.im_off = g.im_off;
+  A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt;
+  A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.nstg = g.nstg;
+  A.wbytes = g.wbytes; A.stage_bytes = g.stage_bytes; A.im_off = g.im_off;
   if (ncta_out) *ncta_out = g.tiles < lf_sm_count() ? g.tiles : lf_sm_count();
   if (nt_out) *nt_out = g.nt;
   if (d->layout == CGAT_LAYOUT_SPATIAL) return lf_launch<6, 4, true>(bwd, d, g, map, A, st);

@@ -91,6 +91,33 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepA
     rec_inv(g.spatial, g.nodes, g.co, (int)i - k * per_head, node, u);
     A.bias_dense[i] = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
   }
+  if (A.d.wgrad_cols) {
+    // fused layer kernels (layer_fused.cu): K-chunk kk = s*nq + q, q = r*nchunk + c for the row plane of vertical tap r
+    // and channel chunk c, horizontal tap s; q = nq-1 multiplies the plane of ones: bias (hi + lo bf16 parts) at s = 0
+    const int nq = 3 * g.nchunk + 1;
+    const long long n_f = (long long)3 * nq * g.npad * 8;
+    for (long long i = tid; i < n_f; i += nt) {
+      const int e = (int)(i & 7);
+      const long long qq = i >> 3;
+      const int row = (int)(qq % g.npad);
+      const int kk = (int)(qq / g.npad);
+      const int s = kk / nq, q = kk - s * nq;
+      float v = 0.f;
+      if (q < nq - 1) {
+        const int r = q / g.nchunk, c = q - r * g.nchunk;
+        v = dense_w(g, A.w, row, r * 3 + s, c * 8 + e);
+      } else if (s == 0 && row < g.cout && e < 2) {
+        const int per_head = g.nodes * g.co;
+        const int k = row / per_head;
+        int node, u;
+        rec_inv(g.spatial, g.nodes, g.co, row - k * per_head, node, u);
+        const float b = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
+        const float hi = __bfloat162float(__float2bfloat16_rn(b));
+        v = e == 0 ? hi : b - hi;
+      }
+      A.wpack[i] = __float2bfloat16_rn(v);
+    }
+  } else {
   // fprop packing: out[(ki*npad + row)*8 + e], ki = cchunk*taps + tap, value Wd[row][tap][cchunk*8+e]
   const long long n_f = (long long)g.npairs * 2 * g.npad * 8;
   for (long long i = tid; i < n_f; i += nt) {
@@ -99,18 +126,9 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepA
     const int row = (int)(q % g.npad);
     const int ki = (int)(q / g.npad);
     const int cch = ki / g.taps, tap = ki - cch * g.taps;
-    float v = cch < g.nchunk ? dense_w(g, A.w, row, tap, cch * 8 + e) : 0.f;
-    if (A.d.wgrad_cols && ki == g.nchunk * g.taps && row < g.cout && e < 2) {
-      // fused layer kernels: this K-chunk multiplies a plane of ones -> the conv bias, as hi + lo bf16 parts
-      const int per_head = g.nodes * g.co;
-      const int k = row / per_head;
-      int node, u;
-      rec_inv(g.spatial, g.nodes, g.co, row - k * per_head, node, u);
-      const float b = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
-      const float hi = __bfloat162float(__float2bfloat16_rn(b));
-      v = e == 0 ? hi : b - hi;
-    }
+    const float v = cch < g.nchunk ? dense_w(g, A.w, row, tap, cch * 8 + e) : 0.f;
     A.wpack[i] = __float2bfloat16_rn(v);
+  }
   }
   // dgrad packing: GEMM-K = dense cout, GEMM-N = cin, kernel rotated: value Wd[k][taps-1-tap][row]
   if (A.wpack_dgrad != nullptr) {
@@ -186,10 +204,17 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
     for (int t = lane; t < terms; t += 32) {
       const int node = t / A.ncta, cta = t - node * A.ncta;
       const int row = k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u);
-      int col = g.taps * g.cin;
-      if (r < nwe) {
-        const int ci_idx = rec_of(g.spatial, g.nodes, g.ci, node, c);
-        col = A.d.wgrad_cols ? ((ci_idx >> 3) * g.taps + tap) * 8 + (ci_idx & 7) : tap * g.cin + ci_idx;
+      int col;
+      if (A.d.wgrad_cols) {  // layer_fused.cu: [s][(r, cin chunk) | ones][8]; dbias is the ones column of s = 0
+        const int nq = 3 * g.nchunk + 1;
+        col = (nq - 1) * 8;
+        if (r < nwe) {
+          const int ci_idx = rec_of(g.spatial, g.nodes, g.ci, node, c);
+          col = ((tap % 3) * nq + (tap / 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
+        }
+      } else {
+        col = g.taps * g.cin;
+        if (r < nwe) col = tap * g.cin + rec_of(g.spatial, g.nodes, g.ci, node, c);
       }
       acc += A.wg_partial[((size_t)cta * 128 + row) * A.nt + col];
     }
@@ -215,6 +240,7 @@ using namespace cgat;
 extern "C" int64_t cgat_stream_wpack_bytes(const cgat_stream_desc* d, int dgrad) {
   if (check_desc(d) || d->mapping != 1) return 0;
   const StreamGeom g = make_geom(*d);
+  if (!dgrad && d->wgrad_cols) return (int64_t)3 * (3 * g.nchunk + 1) * g.npad * 16;
   return dgrad ? (int64_t)g.d_npairs * 2 * g.d_npad * 16 : (int64_t)g.npairs * 2 * g.npad * 16;
 }
 
@@ -240,7 +266,8 @@ extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const
   A.a_stacked = a_stacked;
   A.adj = adj;
   const StreamGeom g = make_geom(*d);
-  const long long work = d->mapping == 1 ? (long long)g.npairs * 2 * g.npad * 8 : (long long)g.heads * g.ci * g.co;
+  long long work = d->mapping == 1 ? (long long)g.npairs * 2 * g.npad * 8 : (long long)g.heads * g.ci * g.co;
+  if (d->mapping == 1 && d->wgrad_cols) work = (long long)3 * (3 * g.nchunk + 1) * g.npad * 8;
   int blocks = (int)((work + ADJ_THREADS - 1) / ADJ_THREADS);
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;

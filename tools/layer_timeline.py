@@ -17,6 +17,8 @@ ts = TrainStep(m, x, y, use_graph=False, fuse_loss=(mode == "train"))
 for _ in range(3):
     ts.run()
 buf = torch.zeros(16, 16, dtype=torch.int64, device=dev)
+if len(sys.argv) > 2:
+    buf[15, 15] = 1  # probe mode: the MMA thread waits for its own MMAs and logs their completion
 L = _lib.lib()
 L.cgat_layer_debug_timeline.argtypes = [ctypes.c_void_p]
 L.cgat_layer_debug_timeline.restype = None
@@ -30,8 +32,8 @@ torch.cuda.synchronize()
 L.cgat_layer_debug_timeline(None)
 t = buf.cpu()
 t0 = int(t[0][t[0] > 0].min())
-names = ["Ptop", "Pempty", "Pxland", "Pdone", "Mfull", "Maccfr", "Mfprop", "Mdyfull", "Mwgrad", "Awh", "Aregs", "Afwd",
-         "Aexch", "Abwd", "Adone"]
+names = ["Ttop", "Tempty", "Mfpdone", "Mwgdone", "Mfull", "Maccfr", "Mfprop", "Mdyfull", "Mwgrad", "Awh", "Aregs", "Afwd",
+         "Aexch", "Abwd", "Adone", "g0bar1"]
 print("tile " + " ".join(f"{n:>8s}" for n in names))
 for i in range(14):
-    print(f"{i:4d} " + " ".join(f"{(int(v) - t0) if v > 0 else -1:8d}" for v in t[i][:15]))
+    print(f"{i:4d} " + " ".join(f"{(int(v) - t0) if v > 0 else -1:8d}" for v in t[i][:16]))
