@@ -307,9 +307,19 @@ def run_ours(args):
         kernels[name] = ent
     dom = max((n for n in prof if n in alg), key=lambda n: prof[n][0] * prof[n][1])
     achieved = alg[dom][1] / (prof[dom][1] * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {}).get("bytes")
+    except (OSError, ValueError):
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": alg[dom][1], "kernel_ms": prof[dom][1]}
+    if len(alg[dom]) > 2:  # the kernel also runs the conv GEMMs on tcgen05: report the tensor-pipe side as well
+        roofline["tensor_tflops"] = alg[dom][2] / (prof[dom][1] * 1e-3) / 1e12
+        roofline["tensor_frac"] = roofline["tensor_tflops"] / pk["bf16_tflops_sustained"]
+        roofline["note"] = ("fused conv+attention kernel: neither HBM- nor tensor-bound; limited by FP32 issue/latency of the "
+                            "per-pixel attention math (profiles/*_sass_hot.txt)")
 
     cpu_rate, cpu_sec, cores = cpu_reference_step_rate(4, 3, 1, args.type, args.mapping) if world == 1 else (None, None, None)
 

@@ -176,6 +176,19 @@ class _GATStream(nn.Module):
                 Wt = torch.stack([h.W for h in self.attentions])
                 inp = x.reshape(N * H * W, T * V)
                 proj = _lib.PROJ_LINEAR
+            elif nodes > 8:
+                # many nodes (BASELINE config 4: V = 32 / 64): the block-diagonal dense conv would be 1/nodes dense, so
+                # the shared conv runs once over the nodes folded into the batch, [N*nodes, H, W, ci] -> [.., co]
+                xn = (x.permute(0, 4, 1, 2, 3) if spatial else x.permute(0, 3, 1, 2, 4)).reshape(N * nodes, H, W, self.ci)
+                per_head = []
+                for h in self.attentions:
+                    y = conv2d_nhwc(xn.contiguous(), h.conv.weight.permute(0, 2, 3, 1), h.conv.bias, stride=1,
+                                    pad=(1, 1, 1, 1), impl=self.conv_impl).view(N, nodes, H, W, self.co)
+                    # head sub-record: (node, c) at c*nodes + node (spatial) or node*co + c (temporal)
+                    per_head.append(y.permute(0, 2, 3, 4, 1) if spatial else y.permute(0, 2, 3, 1, 4))
+                inp = torch.stack(per_head, dim=3).reshape(N * H * W, -1)
+                Wt = None
+                proj = _lib.PROJ_PRE
             else:
                 dense, bias = self._dense_conv_params(nodes)
                 wh = conv2d_nhwc(x.reshape(N, H, W, T * V), dense, bias, stride=1, pad=(1, 1, 1, 1), impl=self.conv_impl)

@@ -136,5 +136,7 @@ enum AttnOp { OP_FWD, OP_BWD, OP_STATS, OP_BSTATS };
 
 // packed-half2 fast path (attn_h2.cu): bf16 I/O, neighbour soft-max.  Returns CGAT_EUNSUPPORTED for other shapes.
 int attn_h2_launch(AttnOp op, const cgat_attn_desc* d, const AttnArgs& A, cudaStream_t st);
+// row-of-threads-per-pixel kernels for any node count <= 64 (attn_generic.cu): neighbour soft-max, fwd / bwd only.
+int attn_generic_launch(AttnOp op, const cgat_attn_desc* d, const AttnArgs& A, cudaStream_t st);
 
 }  // namespace cgat

@@ -536,9 +536,13 @@ static int dispatch(Op op, const cgat_attn_desc* d, const AttnArgs& A, cudaStrea
   if (!sp && d->nodes == 4 && ci == 6 && d->co == 6) return dispatch2<4, 6, 6, false>(op, d, A, st);
   if (sp && d->nodes == 8 && ci == 4 && d->co == 4) return dispatch2<8, 4, 4, true>(op, d, A, st);
   if (!sp && d->nodes == 4 && ci == 8 && d->co == 8) return dispatch2<4, 8, 8, false>(op, d, A, st);
+  {
+    const int rc = attn_generic_launch(op, d, A, st);  // any node count <= 64, neighbour soft-max
+    if (rc != CGAT_EUNSUPPORTED) return rc;
+  }
   return fail(CGAT_EUNSUPPORTED,
-              "attention kernel not instantiated for nodes=%d ci=%d co=%d layout=%d (supported: spatial 6/4/4, "
-              "8/4/4; temporal 4/6/6, 4/8/8)",
+              "attention kernel not instantiated for nodes=%d ci=%d co=%d layout=%d (register-resident kernels: spatial "
+              "6/4/4, 8/4/4; temporal 4/6/6, 4/8/8; generic kernel: nodes <= 64, channels <= 8, neighbour soft-max)",
               d->nodes, ci, d->co, d->layout);
 }
 

@@ -204,9 +204,36 @@ def test_empty_batch_rejected():
 def test_unsupported_shape_fails_loudly():
     from cgat.layers import GATMultiHead3D
 
-    layer = GATMultiHead3D(4, 4, 0.2, 1, type_="spatial", n_vertices=5).to(DEV)
+    layer = GATMultiHead3D(4, 4, 0.2, 1, type_="spatial", n_vertices=65).to(DEV)  # generic kernel serves <= 64 nodes
+    with pytest.raises(RuntimeError):
+        layer(torch.rand(1, 4, 4, 4, 65, device=DEV))
+    layer = GATMultiHead3D(4, 4, 0.2, 1, type_="spatial", n_vertices=5, softmax_axis="pixel").to(DEV)
     with pytest.raises(RuntimeError, match="not instantiated"):
         layer(torch.rand(1, 4, 4, 4, 5, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------------
+# many nodes (BASELINE config 4: V in {32, 64}): the row-of-threads-per-pixel kernels of attn_generic.cu
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V,type_,mapping,heads,merge,masked", [
+    (32, "spatial", "linear", 3, "mean", False),
+    (32, "spatial", "linear", 2, "concat", True),
+    (64, "spatial", "linear", 1, "mean", True),
+    (10, "spatial", "linear", 2, "mean", True),     # a node count that is not a power of two
+    (32, "spatial", "conv", 2, "mean", False),
+    (5, "temporal", "linear", 2, "concat", False),  # nodes = 4 (T), channels = 5
+])
+def test_gat3d_many_nodes_fp32(V, type_, mapping, heads, merge, masked):
+    ours, ref = _pair(type_, mapping, heads, merge, "neighbour", masked, seed=41, V=V)
+    x = torch.rand(2, 9, 7, 4, V)
+    _check(ours, ref, x, torch.float32, 1e-4, 2e-5, 2e-4)
+
+
+def test_gat3d_many_nodes_bf16_stress_shape():
+    """BASELINE config 4's attention shape at reduced batch: 128 x 128 pixels, V = 32 nodes, bf16."""
+    ours, ref = _pair("spatial", "linear", 3, "mean", "neighbour", True, seed=42, V=32)
+    x = torch.rand(1, 128, 128, 4, 32).bfloat16().float()
+    _check(ours, ref, x, torch.bfloat16, 2e-2, 2e-2, 4e-2)
 
 
 # ---------------------------------------------------------------------------------------------------
