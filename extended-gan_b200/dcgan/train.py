@@ -1,0 +1,61 @@
+"""The adversarial step of ``dcgan/train.py`` (reference :97-160) on the B200 nets of ``dcgan/model.py``.
+
+Host logic mirrors the reference line by line (same variable names, same order of backward passes and optimiser
+steps, BCELoss criterion :224, Adam(lr=2e-4, betas=(0.5, 0.999)) :227-236); every convolution of the three nets --
+forward, dgrad and wgrad, nine passes through the discriminators and three through the generator per step -- runs
+in the CUDA conv kernels (tcgen05 implicit GEMM where ``cgat_conv_tc_supported``, the direct kernel otherwise).
+Metrics, printing, checkpointing and the data loader of the reference loop are out of scope.
+"""
+import torch as t
+from torch import nn, optim
+
+
+def make_optimizers(netG, netFD, netTD, lr=0.0002, beta1=0.5):
+    """``optim.Adam(net.parameters(), lr=params["lr"], betas=(params["beta1"], 0.999))`` (reference :227-236)."""
+    mk = lambda net: optim.Adam(net.parameters(), lr=lr, betas=(beta1, 0.999))
+    return mk(netG), mk(netFD), mk(netTD)
+
+
+def adversarial_step(*, netG, netFD, netTD, optimizerG, optimizerFD, optimizerTD, criterion, x, y):
+    """One batch of ``train_single_epoch`` (reference :97-160).  ``x, y`` are ``[N, nc, 64, 64]`` (the reference
+    squeezes a singleton dim 2 first, :98-99).  Returns ``(errFD, errTD, errG, fake_data)`` as device tensors."""
+    data = x
+    b_size = data.size(0)
+    device = data.device
+    netTD.zero_grad()
+    netFD.zero_grad()
+    real_label = t.zeros(b_size, device=device) + 1
+    fake_label = t.zeros(b_size, device=device)
+
+    pred_real_frame_label = netFD(y)
+    pred_real_temp_label = netTD(t.cat((data, y), dim=1))
+    errFD_real = criterion(pred_real_frame_label.float(), real_label)
+    errTD_real = criterion(pred_real_temp_label.float(), real_label)
+    errFD_real.backward()
+    errTD_real.backward()
+
+    fake_data = netG(data)
+    fake_data_detached = fake_data.detach()
+    pred_fake_frame_label = netFD(fake_data_detached)
+    pred_fake_temp_label = netTD(t.cat((data, fake_data_detached), dim=1))
+    errFD_fake = criterion(pred_fake_frame_label.float(), fake_label)
+    errTD_fake = criterion(pred_fake_temp_label.float(), fake_label)
+    errFD_fake.backward()
+    errTD_fake.backward()
+
+    errFD = errFD_real + errFD_fake
+    errTD = errTD_real + errTD_fake
+    optimizerFD.step()
+    optimizerTD.step()
+
+    netG.zero_grad()
+    pred_frame_label = netFD(fake_data).view(-1)
+    pred_temp_label = netTD(t.cat((data, fake_data), dim=1)).view(-1)
+    errG = criterion(pred_frame_label.float(), real_label) + criterion(pred_temp_label.float(), real_label)
+    errG.backward()
+    optimizerG.step()
+    return errFD.detach(), errTD.detach(), errG.detach(), fake_data.detach()
+
+
+def default_criterion():
+    return nn.BCELoss()  # reference :224

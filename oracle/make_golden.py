@@ -151,6 +151,62 @@ def dcgan_nets():
     return fx
 
 
+def dcgan_step():
+    """One adversarial step of dcgan/train.py:97-160 on the reference's own nets (train mode: BatchNorm batch
+    statistics; Dropout2d's p set to 0 on the instantiated modules because its mask is random), with the reference's
+    optimisers (Adam lr 2e-4, betas (0.5, 0.999), :195-236) and criterion (BCELoss, :224)."""
+    dc = ref_loader.dcgan_model()
+    torch.manual_seed(369)
+    params = {"nc": 4, "ndf": 8}
+    N = 4
+    x = torch.rand(N, 4, 64, 64)
+    y = torch.rand(N, 4, 64, 64)
+    netG, netFD, netTD = dc.Generator(params), dc.FrameDiscriminator(params), dc.TemporalDiscriminator(params)
+    for net in (netG, netFD, netTD):
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = 0.0
+        net.train()
+    fx = {"params.nc": 4, "params.ndf": 8, "x": x, "y": y}
+    for name, net in (("G", netG), ("FD", netFD), ("TD", netTD)):
+        for k, v in net.state_dict().items():
+            fx[f"{name}.sd0.{k}"] = v.clone()
+    criterion = torch.nn.BCELoss()
+    opt = {n: torch.optim.Adam(net.parameters(), lr=0.0002, betas=(0.5, 0.999))
+           for n, net in (("G", netG), ("FD", netFD), ("TD", netTD))}
+    data = x
+    # ---- dcgan/train.py:103-160 ----
+    netTD.zero_grad()
+    netFD.zero_grad()
+    real_label = torch.zeros(N) + 1
+    fake_label = torch.zeros(N)
+    errFD_real = criterion(netFD(y), real_label)
+    errTD_real = criterion(netTD(torch.cat((data, y), dim=1)), real_label)
+    errFD_real.backward()
+    errTD_real.backward()
+    fake_data = netG(data)
+    fake_det = fake_data.detach()
+    errFD_fake = criterion(netFD(fake_det), fake_label)
+    errTD_fake = criterion(netTD(torch.cat((data, fake_det), dim=1)), fake_label)
+    errFD_fake.backward()
+    errTD_fake.backward()
+    errFD = errFD_real + errFD_fake
+    errTD = errTD_real + errTD_fake
+    opt["FD"].step()
+    opt["TD"].step()
+    netG.zero_grad()
+    pred_frame = netFD(fake_data).view(-1)
+    pred_temp = netTD(torch.cat((data, fake_data), dim=1)).view(-1)
+    errG = criterion(pred_frame, real_label) + criterion(pred_temp, real_label)
+    errG.backward()
+    opt["G"].step()
+    fx["errFD"], fx["errTD"], fx["errG"] = errFD.detach(), errTD.detach(), errG.detach()
+    for name, net in (("G", netG), ("FD", netFD), ("TD", netTD)):
+        for k, v in net.state_dict().items():
+            fx[f"{name}.sd1.{k}"] = v.clone()
+    return fx
+
+
 def adjacency():
     bm = ref_loader.baseline_model()
     torch.manual_seed(369)
@@ -185,6 +241,7 @@ FIXTURES = {
     "gat1d_layer": gat1d_layer,
     "baseline1d_model": baseline1d_model,
     "dcgan_nets": dcgan_nets,
+    "dcgan_step": dcgan_step,
     "adjacency": adjacency,
 }
 

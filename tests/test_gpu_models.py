@@ -120,3 +120,36 @@ def test_model_registry_and_train_signature():
         assert y_hat.shape == x.shape  # train.py:131 needs MSE(y_hat, y)
         sd = m.state_dict()
         m.load_state_dict(sd)
+
+
+def test_dcgan_adversarial_step_vs_reference_golden():
+    """BASELINE config 5: one adversarial step (dcgan/train.py:97-160) on our nets vs the live reference's step
+    (tests/golden/dcgan_step.pt: same initial state_dicts, batch, optimisers; Dropout2d p = 0)."""
+    from dcgan.model import FrameDiscriminator, Generator, TemporalDiscriminator
+    from dcgan.train import adversarial_step, default_criterion, make_optimizers
+
+    fx = golden("dcgan_step")
+    params = {"nc": fx["params.nc"], "ndf": fx["params.ndf"]}
+    nets = {"G": Generator(params), "FD": FrameDiscriminator(params), "TD": TemporalDiscriminator(params)}
+    for name, net in nets.items():
+        net.load_state_dict(sd_of(fx, f"{name}.sd0."))
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = 0.0
+        net.to(DEV).train()
+    oG, oFD, oTD = make_optimizers(nets["G"], nets["FD"], nets["TD"])
+    errFD, errTD, errG, _ = adversarial_step(netG=nets["G"], netFD=nets["FD"], netTD=nets["TD"], optimizerG=oG,
+                                             optimizerFD=oFD, optimizerTD=oTD, criterion=default_criterion(),
+                                             x=fx["x"].to(DEV), y=fx["y"].to(DEV))
+    close(errFD, fx["errFD"], rtol=1e-4, atol=1e-5, msg="errFD")
+    close(errTD, fx["errTD"], rtol=1e-4, atol=1e-5, msg="errTD")
+    close(errG, fx["errG"], rtol=1e-4, atol=1e-5, msg="errG")
+    # Adam's first step moves every parameter by ~lr * sign(grad): compare the updated state (parameters and
+    # BatchNorm running statistics) -- an entry whose gradient is ~0 may flip its sign, hence the 2*lr slack
+    for name, net in nets.items():
+        sd1 = sd_of(fx, f"{name}.sd1.")
+        for k, v in net.state_dict().items():
+            close(v, sd1[k], rtol=1e-4, atol=4.1e-4 if v.dtype.is_floating_point and "running" not in k else 1e-5,
+                  msg=f"{name}.{k} after the step")
+        moved = sum(int((v.float().cpu() - fx[f"{name}.sd0.{k}"].float()).abs().max() > 0) for k, v in net.state_dict().items())
+        assert moved > 0
