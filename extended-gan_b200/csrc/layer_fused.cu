@@ -43,7 +43,7 @@ constexpr int LF_FP_COL0 = 256;     // TMEM: wgrad accumulators at columns [0,25
 constexpr int LF_WP = LF_TW + 2;    // plane columns (halo)
 constexpr int LF_PLANE = LF_TH * LF_WP * 16;  // 2560 B
 constexpr int LF_ROW = LF_WP * 16;            // 160 B between tile rows of a plane
-constexpr int LF_HDR = 6144;        // barriers + parameters
+constexpr int LF_HDR = 8704;        // barriers + parameters (fp32 and packed-half2 copies)
 
 struct LfArgs {
   long long* dbg;              // developer aid: clock64() timeline of CTA 0 (cgat_layer_debug_timeline)
@@ -60,6 +60,7 @@ struct LfArgs {
   float* gadj;                 // bwd: [heads][nodes*nodes] accumulated into
   const __nv_bfloat16* y;      // train mode (bwd kernel): target, same layout as out; d(out) is derived in-kernel
   float* loss_out;             // train mode: scalar loss, accumulated into
+  float out_scale;             // bwd: factor applied to the gradient sums when they leave the kernel (PAIR: 1/numel)
   float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
   int h, w, cin, cout, npad, heads, merge, apply_elu;
   float alpha;
@@ -113,7 +114,7 @@ __device__ __forceinline__ void unpack_rec(const uint4* __restrict__ p, float (&
   }
 }
 
-template <int NODES, int CO, bool SPATIAL, bool BWD, bool MASKED>
+template <int NODES, int CO, bool SPATIAL, bool BWD, bool MASKED, bool PAIR>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   constexpr int REC = NODES * CO;          // elements of one head's pixel record
@@ -132,8 +133,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   float* s_adj = reinterpret_cast<float*>(smem + 1280);          // [MAX_HEADS][NODES*NODES]
   uint64_t* s_mask = reinterpret_cast<uint64_t*>(smem + 3328);   // [NODES]
   float* s_gacc = reinterpret_cast<float*>(smem + 3392);         // [MAX_HEADS][RG]
+  __half2* s_a2 = reinterpret_cast<__half2*>(smem + 6144);       // [MAX_HEADS][2*CO]       both lanes = the parameter
+  __half2* s_adj2 = reinterpret_cast<__half2*>(smem + 6656);     // [MAX_HEADS][NODES*NODES]
   static_assert(MAX_HEADS * 2 * CO * 4 <= 512 && MAX_HEADS * NODES * NODES * 4 <= 2048 && NODES * 8 <= 64 &&
-                    3392 + (MAX_HEADS * RG + 1) * 4 <= LF_HDR, "parameter block overflows the header");
+                    3392 + (MAX_HEADS * RG + 1) * 4 <= 6144 && 6656 + MAX_HEADS * NODES * NODES * 4 <= LF_HDR, "parameter block overflows the header");
   unsigned char* s_w = smem + LF_HDR;
   unsigned char* s_stage = s_w + ((A.wbytes + 127u) & ~127u);
   float4* s_slab = reinterpret_cast<float4*>(s_stage + (size_t)A.nstg * A.stage_bytes);  // fwd: [group][REC/4][128]
@@ -149,8 +152,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     fence_mbar_init();
     tma_prefetch_desc(&tmap_x);
   }
-  for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) s_a[i] = A.a[i];
-  for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) s_adj[i] = A.adj[i];
+  for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) { s_a[i] = A.a[i]; s_a2[i] = __float2half2_rn(A.a[i]); }
+  for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) {
+    s_adj[i] = A.adj[i];
+    s_adj2[i] = __float2half2_rn(A.adj[i]);
+  }
   for (int i = threadIdx.x; i < MAX_HEADS * RG + 1; i += LF_THREADS) s_gacc[i] = 0.f;
   if (threadIdx.x < NODES) {
     uint64_t mrow = 0;
@@ -209,7 +215,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       const uint32_t w_addr = smem_u32(s_w);
       const uint32_t b_lbo = (uint32_t)A.npad * 16;
       uint32_t wg_accum = 0;
-      int wstage = 0;
+      int wstage = 0, wj = 0;  // wj: next tile whose wgrad is to be issued
       uint32_t wphase = 0;
       auto wgrad = [&](int j) {  // tiles are retired in order: (wstage, wphase) follow tile j
         mbar_wait(&dyfull[wstage], wphase);
@@ -262,13 +268,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         if constexpr (!BWD) {
           umma_commit(&empty[stage]);
-        } else if (it > 0) {
-          wgrad(it - 1);
+        } else if constexpr (PAIR) {
+          // the attention groups work on tile PAIRS: issue both fprops of the next pair before blocking on the
+          // d(Wh) planes of the previous one
+          if (it & 1)
+            while (wj < it - 1) wgrad(wj++);
+        } else {
+          while (wj < it) wgrad(wj++);
         }
         if (++stage == A.nstg) { stage = 0; phase ^= 1u; }
       }
       if constexpr (BWD) {
-        if (it > 0) wgrad(it - 1);
+        while (wj < it) wgrad(wj++);
         umma_commit(done);
       }
     }
@@ -298,6 +309,207 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
       };
       const float inv_heads = 1.f / (float)A.heads;
+      if constexpr (PAIR) {
+        // ============ train mode, two tiles per pass: pixel m of tile A in the low half2 lane, of tile B in the
+        // high lane (A, B = consecutive tiles of this CTA, in the two fprop accumulators).  One head per group.
+        // All quantities are O(1) in fp16: d(out) is carried WITHOUT its 1/numel factor (out_scale re-applies it
+        // to everything that leaves the kernel). ============
+        const int k = g;
+        cur_head = g;
+        const __half2* a2 = s_a2 + k * 2 * CO;
+        const __half2* adj2 = s_adj2 + k * NODES * NODES;
+        const __half2 alpha2 = __float2half2_rn(A.alpha);
+        const __half2 gs2 = __float2half2_rn(inv_heads);
+        int itp = 0;
+        for (int tileA = blockIdx.x; tileA < A.tiles; tileA += 2 * gridDim.x, ++itp) {
+          const int it = 2 * itp;
+          const int tileB = tileA + gridDim.x;
+          const bool hasB = tileB < A.tiles;
+          const int stA = (2 * itp) % A.nstg, stB = (2 * itp + 1) % A.nstg;
+          const uint32_t ph = (uint32_t)itp & 1u;
+          long long pixA, pixB = 0;
+          bool validA, validB = false;
+          {
+            const int tw = tileA % A.tiles_w, th = (tileA / A.tiles_w) % A.tiles_h, n = tileA / (A.tiles_w * A.tiles_h);
+            const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
+            validA = h < A.h && w < A.w;
+            pixA = ((long long)n * A.h + h) * A.w + w;
+          }
+          if (hasB) {
+            const int tw = tileB % A.tiles_w, th = (tileB / A.tiles_w) % A.tiles_h, n = tileB / (A.tiles_w * A.tiles_h);
+            const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
+            validB = h < A.h && w < A.w;
+            pixB = ((long long)n * A.h + h) * A.w + w;
+          }
+          if (g == 0) {  // the targets of this pair: pull their lines into L2 while the forward runs
+            if (validA) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + pixA * REC));
+            if (validB) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + pixB * REC));
+          }
+          mbar_wait(&tfull[0], ph);
+          if (hasB) mbar_wait(&tfull[1], ph);
+          tc_fence_after();
+          const bool dbg_thread = g == 0 && m == 0;
+          if (dbg_thread) LDBG(9);
+          __half2 Wh2[NODES][CO];
+          {
+            float ra[REC], rb[REC];
+            const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + LF_FP_COL0 + k * REC;
+#pragma unroll
+            for (int q = 0; q < REC / 8; ++q) tmem_ld8_nowait(t_addr + q * 8, &ra[q * 8]);
+            if (hasB) {
+#pragma unroll
+              for (int q = 0; q < REC / 8; ++q) tmem_ld8_nowait(t_addr + 128 + q * 8, &rb[q * 8]);
+            }
+            tmem_ld_wait();
+            if (!hasB) {
+#pragma unroll
+              for (int i = 0; i < REC; ++i) rb[i] = 0.f;
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[0]);
+            if (hasB) mbar_arrive(&tempty[1]);
+#pragma unroll
+            for (int v = 0; v < NODES; ++v)
+#pragma unroll
+              for (int u = 0; u < CO; ++u)
+                Wh2[v][u] = __floats2half2_rn(ra[rec_off<NODES, CO, SPATIAL>(v, u)], rb[rec_off<NODES, CO, SPATIAL>(v, u)]);
+          }
+          if (dbg_thread) LDBG(10);
+          NbState<H2, NODES> st;
+          __half2 z2[NODES][CO];
+          attn_nb_forward<H2, NODES, CO, MASKED>(Wh2, a2, adj2, s_mask, alpha2, st, z2);
+          if (dbg_thread) LDBG(11);
+          // ---- swap ELU(z) of the three heads through the d(Wh) planes of the two stages (fp16) ----
+          const uint32_t exA = smem_u32(s_stage) + (uint32_t)stA * A.stage_bytes + (uint32_t)m * 16;
+          const uint32_t exB = smem_u32(s_stage) + (uint32_t)stB * A.stage_bytes + (uint32_t)m * 16;
+          {
+            __half2 o2[REC];
+#pragma unroll
+            for (int v = 0; v < NODES; ++v)
+#pragma unroll
+              for (int u = 0; u < CO; ++u)
+                o2[rec_off<NODES, CO, SPATIAL>(v, u)] = A.apply_elu ? elu_fwd<H2>(z2[v][u]) : z2[v][u];
+#pragma unroll
+            for (int q = 0; q < REC / 8; ++q) {
+              uint4 va, vb;
+              __half2 t;
+#define LO2(i) (t = __lows2half2(o2[8 * q + (i)], o2[8 * q + (i) + 1]), *reinterpret_cast<uint32_t*>(&t))
+#define HI2(i) (t = __highs2half2(o2[8 * q + (i)], o2[8 * q + (i) + 1]), *reinterpret_cast<uint32_t*>(&t))
+              va.x = LO2(0); va.y = LO2(2); va.z = LO2(4); va.w = LO2(6);
+              vb.x = HI2(0); vb.y = HI2(2); vb.z = HI2(4); vb.w = HI2(6);
+#undef LO2
+#undef HI2
+              lf_sts128(exA + (uint32_t)(k * (REC / 8) + q) * 2048, va);
+              if (hasB) lf_sts128(exB + (uint32_t)(k * (REC / 8) + q) * 2048, vb);
+            }
+          }
+          if (dbg_thread) LDBG(15);
+          // the targets of both tiles (L2-resident by now): requested before the barrier, consumed after it
+          uint4 yraw[2][REC / 8];
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int q = 0; q < REC / 8; ++q) {
+              yraw[half][q] = make_uint4(0, 0, 0, 0);
+              if (half ? validB : validA)
+                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(yraw[half][q].x), "=r"(yraw[half][q].y), "=r"(yraw[half][q].z), "=r"(yraw[half][q].w)
+                             : "l"(reinterpret_cast<const uint4*>(A.y + (half ? pixB : pixA) * REC) + q));
+            }
+          named_bar_sync(1, 128 * nact);
+          // ---- d(out) * numel = 2 (out - y) - lambda   per tile (fp32), kept as fp16 pairs of consecutive elements ----
+          __half2 dh[2][REC / 2];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const bool valid = half ? validB : validA;
+            const uint32_t ex = half ? exB : exA;
+            float dd[REC];
+#pragma unroll
+            for (int i = 0; i < REC; ++i) dd[i] = 0.f;
+            if (!(half && !hasB)) {
+              for (int kk = 0; kk < A.heads; ++kk) {
+#pragma unroll
+                for (int q = 0; q < REC / 8; ++q) {
+                  const uint4 v = lf_lds128(ex + (uint32_t)(kk * (REC / 8) + q) * 2048);
+                  const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                    dd[8 * q + 2 * e] += f.x;
+                    dd[8 * q + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+              float yv[REC];
+              unpack_rec<REC>(yraw[half], yv);
+              float lsum = 0.f;
+#pragma unroll
+              for (int i = 0; i < REC; ++i) {
+                const float o = dd[i] * inv_heads;
+                const float df = o - yv[i];
+                lsum += df * df - A.lambda * o;
+                dd[i] = valid ? 2.f * df - A.lambda : 0.f;
+              }
+              if (g == 0 && valid) loss_acc += lsum;
+            }
+#pragma unroll
+            for (int i = 0; i < REC / 2; ++i) dh[half][i] = __floats2half2_rn(dd[2 * i], dd[2 * i + 1]);
+          }
+          named_bar_sync(1, 128 * nact);  // all heads read: the planes may now take d(Wh)
+          if (dbg_thread) LDBG(12);
+          __half2 dz2[NODES][CO];
+#pragma unroll
+          for (int v = 0; v < NODES; ++v)
+#pragma unroll
+            for (int u = 0; u < CO; ++u) {
+              const int o = rec_off<NODES, CO, SPATIAL>(v, u);
+              // lane A = element o of tile A, lane B = element o of tile B
+              const __half2 ab = (o & 1) ? __highs2half2(dh[0][o >> 1], dh[1][o >> 1]) : __lows2half2(dh[0][o >> 1], dh[1][o >> 1]);
+              const __half2 d = __hmul2(ab, gs2);
+              dz2[v][u] = A.apply_elu ? __hmul2(d, elu_grad<H2>(z2[v][u])) : d;
+            }
+          __half2 g2[RG];
+#pragma unroll
+          for (int i = 0; i < RG; ++i) g2[i] = H2::zero();
+          attn_nb_backward<H2, NODES, CO, MASKED>(Wh2, dz2, a2, adj2, s_mask, alpha2, st, z2, &g2[NODES * NODES], &g2[0]);
+#pragma unroll
+          for (int i = 0; i < RG; ++i) {
+            const float2 f = __half22float2(g2[i]);
+            gacc[i] += f.x + f.y;
+          }
+          if (dbg_thread) LDBG(13);
+          // ---- d(Wh) (z2) -> bf16 A planes of the wgrad MMA of both stages ----
+          {
+            const uint32_t dyA = exA + (uint32_t)(k * (REC / 8)) * 2048, dyB = exB + (uint32_t)(k * (REC / 8)) * 2048;
+            __half2 r2[REC];
+#pragma unroll
+            for (int v = 0; v < NODES; ++v)
+#pragma unroll
+              for (int u = 0; u < CO; ++u) r2[rec_off<NODES, CO, SPATIAL>(v, u)] = z2[v][u];
+#pragma unroll
+            for (int q = 0; q < REC / 8; ++q) {
+              float fa[8], fb[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = __half22float2(r2[8 * q + j]);
+                fa[j] = f.x;
+                fb[j] = f.y;
+              }
+              uint4 va, vb;
+              va.x = pack_bf16x2(fa[0], fa[1]); va.y = pack_bf16x2(fa[2], fa[3]);
+              va.z = pack_bf16x2(fa[4], fa[5]); va.w = pack_bf16x2(fa[6], fa[7]);
+              vb.x = pack_bf16x2(fb[0], fb[1]); vb.y = pack_bf16x2(fb[2], fb[3]);
+              vb.z = pack_bf16x2(fb[4], fb[5]); vb.w = pack_bf16x2(fb[6], fb[7]);
+              lf_sts128(dyA + (uint32_t)q * 2048, va);
+              if (hasB) lf_sts128(dyB + (uint32_t)q * 2048, vb);
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&dyfull[stA]);
+          if (hasB) mbar_arrive(&dyfull[stB]);
+          if (dbg_thread) LDBG(14);
+        }
+      } else {
       int it = 0, stage = -1;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -522,6 +734,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           named_bar_sync(1, 128 * nact);  // slabs are rewritten by the next tile
         }
       }
+      }  // !PAIR
       if constexpr (BWD) {
         flush(cur_head);
         if (A.y != nullptr && g == 0) {
@@ -538,7 +751,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           if (m < A.cout) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(prow + c0)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              reinterpret_cast<float4*>(prow + c0)[i] = make_float4(v[4 * i] * A.out_scale, v[4 * i + 1] * A.out_scale,
+                                                                    v[4 * i + 2] * A.out_scale, v[4 * i + 3] * A.out_scale);
           }
         }
       }
@@ -549,7 +763,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   if constexpr (BWD) {
     for (int i = threadIdx.x; i < A.heads * RG; i += LF_THREADS) {
       const int k = i / RG, r = i - k * RG;
-      const float v = s_gacc[i];
+      const float v = s_gacc[i] * A.out_scale;
       if (r < NODES * NODES) atomicAdd(A.gadj + (size_t)k * NODES * NODES + r, v);
       else atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
     }
@@ -652,8 +866,12 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
   };
   int rc;
   const bool masked = A.mask != nullptr;  // NULL = all ones = the reference's dense attention: no mask arithmetic
-  if (bwd) rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, true, true>) : go(layer_kernel<NODES, CO, SPATIAL, true, false>);
-  else rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, false, true>) : go(layer_kernel<NODES, CO, SPATIAL, false, false>);
+  if (bwd && A.y != nullptr && g.nstg == LF_MAXSTG && A.heads <= LF_GROUPS)  // train mode: tile pairs in packed half2
+    rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, true, true, true>) : go(layer_kernel<NODES, CO, SPATIAL, true, false, true>);
+  else if (bwd)
+    rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, true, true, false>) : go(layer_kernel<NODES, CO, SPATIAL, true, false, false>);
+  else
+    rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, false, true, false>) : go(layer_kernel<NODES, CO, SPATIAL, false, false, false>);
   if (rc) return rc;
   return check_launch(bwd ? "layer_kernel<bwd>" : "layer_kernel<fwd>");
 }
@@ -676,6 +894,7 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.partial = partial; A.ga = ga; A.gadj = gadj;
   A.y = (const __nv_bfloat16*)y; A.loss_out = loss_out; A.lambda = lambda;
   A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
+  A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && d->heads <= LF_GROUPS) ? A.inv_n : 1.f;
   A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
   A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt;
