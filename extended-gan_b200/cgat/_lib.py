@@ -104,6 +104,7 @@ SIGNATURES = {
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _I64, _F, _F, _I, _P],
     "cgat_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P],
     "cgat_cast": [_P, _I, _P, _I, _I64, _P],
+    "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
 }
 
 _lib = None

@@ -155,6 +155,26 @@ class TrainStep:
             s["y"].copy_(y_host, non_blocking=True)
             s["ready"].record(self.copy_stream)
 
+    def prefetch_raw(self, frames_host: torch.Tensor, start_host: torch.Tensor, slot: int, *, normalizing_max=254.0,
+                     power=1.0):
+        """The loader's raw format end to end: pinned uint8 frames ``[L, V, H, W]`` and int32 window starts ``[N]`` cross
+        PCIe on the copy stream, then ``cgat_loader_gather`` builds this slot's x and y on the device
+        (kmni_data_loader.py:72-127)."""
+        from convolutional_gat.data_loaders.kmni_data_loader import gather_windows
+
+        s = self._slots[slot]
+        if "frames" not in s:
+            s["frames"] = torch.empty(frames_host.shape, dtype=torch.uint8, device=self.device)
+            s["start"] = torch.empty(start_host.shape, dtype=torch.int32, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["free"])
+            s["frames"].copy_(frames_host, non_blocking=True)
+            s["start"].copy_(start_host, non_blocking=True)
+            N, H, W, T, V = s["x"].shape
+            gather_windows(s["frames"], s["start"], crop=H, steps=T, normalizing_max=normalizing_max, power=power,
+                           out=(s["x"], s["y"]))
+            s["ready"].record(self.copy_stream)
+
     def run_slot(self, slot: int) -> torch.Tensor:
         """One optimisation step on the batch previously prefetched into ``slot``."""
         s = self._slots[slot]

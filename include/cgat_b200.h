@@ -220,6 +220,15 @@ int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_
 int cgat_adam_step(float* param, const float* grad, float* m, float* v, const int64_t* step_dev, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                    void* stream);
+/* f3  the KNMI loader's windowing + normalisation + layout change on the device, replacing
+ * convolutional_gat/data_loaders/kmni_data_loader.py:72-127 (__segmentify and the permute of __next__):
+ *   x[s, h, w, t, v] = pow(frames[start[s] + t, v, h, w] / normalizing_max, power)            t < steps
+ *   y[s, h, w, t, v] = pow(frames[start[s] + steps + t, v, h, w] / normalizing_max, power)
+ * frames [n_frames][vertices][h][w] uint8 (the raw integer frames, 0..254), start [n] int32 window starts (every
+ * start + 2*steps <= n_frames: the caller's responsibility), x, y [n][crop_h][crop_w][steps][vertices] of `dtype`.  */
+int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y, int32_t n,
+                       int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w, int32_t steps,
+                       float normalizing_max, float power, int32_t dtype, void* stream);
 /* dtype conversion of contiguous buffers (fp32 <-> bf16) */
 int cgat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 

@@ -207,6 +207,29 @@ def dcgan_step():
     return fx
 
 
+def kmni_loader():
+    """Batches of the reference's own KNMI ``DataLoader`` (kmni_data_loader.py:15-127) on synthetic files: raw integer
+    frames ``[L, V, H, W]`` in 0..254 as the preprocessing writes them (preprocessing/kmni_dataset/__main__.py:76-110);
+    sliding windows of 8 frames with stride 1, ``/254``, ``pow``, crop, permutation to ``[N, H, W, T, V]``."""
+    import tempfile
+
+    km = ref_loader.kmni_loader()
+    g = torch.Generator().manual_seed(369)
+    fx = {}
+    with tempfile.TemporaryDirectory() as d:
+        files = [torch.randint(0, 255, (L, 6, 12, 12), generator=g, dtype=torch.int64) for L in (17, 10)]
+        for i, f in enumerate(files):
+            torch.save(f, os.path.join(d, f"{i:010d}.pt"))
+            fx[f"file{i}"] = f.to(torch.uint8)
+        for tag, power in (("p1", 1.0), ("p05", 0.5)):
+            dl = km.DataLoader(4, d, "cpu", crop=8, shuffle=False, power=power)
+            # file 0: 17 frames -> truncated to 16 (:74) -> 9 windows: batches of 4, 4, 1; file 1: 10 -> 8 -> 1 window
+            for b in range(4):
+                x, y = next(dl)
+                fx[f"{tag}.x{b}"], fx[f"{tag}.y{b}"] = x.contiguous().clone(), y.contiguous().clone()
+    return fx
+
+
 def adjacency():
     bm = ref_loader.baseline_model()
     torch.manual_seed(369)
@@ -242,6 +265,7 @@ FIXTURES = {
     "baseline1d_model": baseline1d_model,
     "dcgan_nets": dcgan_nets,
     "dcgan_step": dcgan_step,
+    "kmni_loader": kmni_loader,
     "adjacency": adjacency,
 }
 

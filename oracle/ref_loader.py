@@ -55,6 +55,32 @@ def dcgan_model():
     return _cache["dc"]
 
 
+def kmni_loader():
+    """The reference's ``convolutional_gat/data_loaders/kmni_data_loader.py`` as a module object.
+
+    It imports matplotlib / ipdb (absent here; stubbed) and ``..preprocessing.utils`` (loaded from the reference tree
+    under the same package names), so the UNMODIFIED ``DataLoader`` class runs on a folder of synthetic files."""
+    if "kmni" in _cache:
+        return _cache["kmni"]
+    for name in ("ipdb", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    for pkg in ("_refpkg", "_refpkg.preprocessing", "_refpkg.data_loaders"):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+    for name, rel in (("_refpkg.preprocessing.utils", "convolutional_gat/preprocessing/utils.py"),
+                      ("_refpkg.data_loaders.kmni_data_loader", "convolutional_gat/data_loaders/kmni_data_loader.py")):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    _cache["kmni"] = sys.modules["_refpkg.data_loaders.kmni_data_loader"]
+    return _cache["kmni"]
+
+
 @contextlib.contextmanager
 def cpu_shim():
     """Make ``Tensor.cuda`` a no-op so the reference GAT layers run on CPU tensors."""
