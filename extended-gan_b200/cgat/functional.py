@@ -223,7 +223,8 @@ def conv2d_nhwc(x, w_krsc, bias=None, stride=1, pad=(0, 0, 0, 0), act=0, impl=IM
 # train-step pieces (convolutional_gat/train.py:131, :212)
 # ----------------------------------------------------------------------------------------------
 def loss_and_grad(y_hat: torch.Tensor, y: torch.Tensor, lam: float = 0.0005, grad_scale: float = 1.0,
-                  loss_out: Optional[torch.Tensor] = None, dy_out: Optional[torch.Tensor] = None):
+                  loss_out: Optional[torch.Tensor] = None, dy_out: Optional[torch.Tensor] = None,
+                  mse_out: Optional[torch.Tensor] = None):
     """``MSE(y_hat,y) - lam*mean(y_hat)`` and its gradient w.r.t. ``y_hat`` in one launch.
 
     Returns ``(loss[1] fp32 (accumulated into ``loss_out`` if given), d loss / d y_hat)``.
@@ -235,7 +236,7 @@ def loss_and_grad(y_hat: torch.Tensor, y: torch.Tensor, lam: float = 0.0005, gra
         loss_out = torch.zeros(1, device=y_hat.device, dtype=torch.float32)
     if dy_out is None:
         dy_out = torch.empty_like(y_hat)
-    _lib.call("cgat_loss_fwd_bwd", ptr(y_hat), ptr(y), ptr(dy_out), ptr(loss_out), y_hat.numel(), lam, grad_scale,
+    _lib.call("cgat_loss_fwd_bwd", ptr(y_hat), ptr(y), ptr(dy_out), ptr(loss_out), ptr(mse_out), y_hat.numel(), lam, grad_scale,
                                   dtype_tag(y_hat), stream())
     return loss_out, dy_out
 
@@ -433,7 +434,7 @@ def layer_train_supported(x, cfg: AttnConfig, mapping: str) -> bool:
     return bool(lib().cgat_layer_supported(ctypes.byref(ld)))
 
 
-def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor):
+def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None):
     """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
     ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
 
@@ -468,7 +469,7 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
     ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
     _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
-              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(loss_out), ctypes.byref(ncta), ctypes.byref(nt), st)
+              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(loss_out), ptr(mse_out), ctypes.byref(ncta), ctypes.byref(nt), st)
     tg = [p.grad for p in params]
     _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),
               _lib.ptr_array(Bs), _lib.ptr_array([tg[4 * k] for k in range(heads)]),

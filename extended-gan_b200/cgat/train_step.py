@@ -37,7 +37,8 @@ class TrainStep:
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.device = example_x.device
-        self.loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self._loss2 = torch.zeros(2, device=self.device, dtype=torch.float32)  # [loss, plain MSE]
+        self.loss, self.mse = self._loss2[:1], self._loss2[1:]
         self.step_count = torch.zeros(1, device=self.device, dtype=torch.int64)
         self.graph = None
         self._slots = None  # double-buffered inputs for pipelined host->device loading (enable_prefetch)
@@ -81,14 +82,15 @@ class TrainStep:
     # -- one step -------------------------------------------------------------------------------
     def _fwd_bwd(self):
         self.flat_grad.zero_()
-        self.loss.zero_()
-        if self.fused_stream is not None:  # forward + loss + backward in one kernel (cgat_layer_train)
-            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss)
+        self._loss2.zero_()
+        if self.fused_stream is not None and self.fused_stream.train_step_supported(self.x):
+            # forward + loss + backward in one kernel (cgat_layer_train)
+            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse)
             return
         prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
         try:
             out = self.model(self.x)
-            _, dy = loss_and_grad(out, self.y, self.lam, loss_out=self.loss)
+            _, dy = loss_and_grad(out, self.y, self.lam, loss_out=self.loss, mse_out=self.mse)
             out.backward(dy)
         finally:
             functional.DIRECT_GRAD = prev
@@ -123,8 +125,17 @@ class TrainStep:
         return self.loss
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        self.load_batch(x, y)
-        return self.run()
+        """One optimisation step on ``(x, y)``.  A batch of the captured shape replays the graph; any other batch size
+        (the short last batch of a file, kmni_data_loader.py:113) runs the same launches eagerly."""
+        if x.shape == self.x.shape:
+            self.load_batch(x, y)
+            return self.run()
+        keep = (self.x, self.y, self.graph)
+        self.x, self.y, self.graph = x.to(self.x.dtype).contiguous(), y.to(self.y.dtype).contiguous(), None
+        try:
+            return self.run()
+        finally:
+            self.x, self.y, self.graph = keep
 
     # -- pipelined loading: batch i+1 crosses PCIe on a copy stream while batch i trains ------------------
     def enable_prefetch(self):

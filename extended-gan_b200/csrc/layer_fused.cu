@@ -60,6 +60,7 @@ struct LfArgs {
   float* gadj;                 // bwd: [heads][nodes*nodes] accumulated into
   const __nv_bfloat16* y;      // train mode (bwd kernel): target, same layout as out; d(out) is derived in-kernel
   float* loss_out;             // train mode: scalar loss, accumulated into
+  float* mse_out;              // train mode, optional: mean squared error alone (the reference's running train loss)
   float out_scale;             // bwd: factor applied to the gradient sums when they leave the kernel (PAIR: 1/numel)
   float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
   int h, w, cin, cout, npad, heads, merge, apply_elu;
@@ -136,7 +137,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   __half2* s_a2 = reinterpret_cast<__half2*>(smem + 6144);       // [MAX_HEADS][2*CO]       both lanes = the parameter
   __half2* s_adj2 = reinterpret_cast<__half2*>(smem + 6656);     // [MAX_HEADS][NODES*NODES]
   static_assert(MAX_HEADS * 2 * CO * 4 <= 512 && MAX_HEADS * NODES * NODES * 4 <= 2048 && NODES * 8 <= 64 &&
-                    3392 + (MAX_HEADS * RG + 1) * 4 <= 6144 && 6656 + MAX_HEADS * NODES * NODES * 4 <= LF_HDR, "parameter block overflows the header");
+                    3392 + (MAX_HEADS * RG + 2) * 4 <= 6144 && 6656 + MAX_HEADS * NODES * NODES * 4 <= LF_HDR, "parameter block overflows the header");
   unsigned char* s_w = smem + LF_HDR;
   unsigned char* s_stage = s_w + ((A.wbytes + 127u) & ~127u);
   float4* s_slab = reinterpret_cast<float4*>(s_stage + (size_t)A.nstg * A.stage_bytes);  // fwd: [group][REC/4][128]
@@ -157,7 +158,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     s_adj[i] = A.adj[i];
     s_adj2[i] = __float2half2_rn(A.adj[i]);
   }
-  for (int i = threadIdx.x; i < MAX_HEADS * RG + 1; i += LF_THREADS) s_gacc[i] = 0.f;
+  for (int i = threadIdx.x; i < MAX_HEADS * RG + 2; i += LF_THREADS) s_gacc[i] = 0.f;
   if (threadIdx.x < NODES) {
     uint64_t mrow = 0;
     for (int j = 0; j < NODES; ++j)
@@ -295,7 +296,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     const bool vec_io = !concat || SPATIAL;  // a head's record is contiguous in the output record
     if (g < nact) {
       float gacc[BWD ? RG : 1];
-      float loss_acc = 0.f;
+      float loss_acc = 0.f, mse_acc = 0.f;
       int cur_head = -1;
 #pragma unroll
       for (int i = 0; i < (BWD ? RG : 1); ++i) gacc[i] = 0.f;
@@ -442,15 +443,16 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               }
               float yv[REC];
               unpack_rec<REC>(yraw[half], yv);
-              float lsum = 0.f;
+              float lsum = 0.f, msum = 0.f;
 #pragma unroll
               for (int i = 0; i < REC; ++i) {
                 const float o = dd[i] * inv_heads;
                 const float df = o - yv[i];
                 lsum += df * df - A.lambda * o;
+                msum += df * df;
                 dd[i] = valid ? 2.f * df - A.lambda : 0.f;
               }
-              if (g == 0 && valid) loss_acc += lsum;
+              if (g == 0 && valid) { loss_acc += lsum; mse_acc += msum; }
             }
 #pragma unroll
             for (int i = 0; i < REC / 2; ++i) dh[half][i] = __floats2half2_rn(dd[2 * i], dd[2 * i + 1]);
@@ -640,12 +642,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
                   }
                 }
               }
-              float lsum = 0.f;
+              float lsum = 0.f, msum = 0.f;
 #pragma unroll
               for (int i = 0; i < REC; ++i) {
                 const float o = rec[i] * inv_heads;
                 const float dd = o - yv[i];
                 lsum += dd * dd - A.lambda * o;
+                msum += dd * dd;
                 rec[i] = valid ? (2.f * dd - A.lambda) * A.inv_n : 0.f;
               }
               if (g == 0 && valid) loss_acc += lsum;
@@ -738,8 +741,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       if constexpr (BWD) {
         flush(cur_head);
         if (A.y != nullptr && g == 0) {
-          const float s = warp_sum(loss_acc);
-          if (lane == 0) atomicAdd(&s_gacc[MAX_HEADS * RG], s);
+          const float s = warp_sum(loss_acc), s2 = warp_sum(mse_acc);
+          if (lane == 0) { atomicAdd(&s_gacc[MAX_HEADS * RG], s); atomicAdd(&s_gacc[MAX_HEADS * RG + 1], s2); }
         }
         // ---- wgrad accumulator -> per-CTA partial sums (lane = dense cout) ----
         mbar_wait(done, 0);
@@ -767,7 +770,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       if (r < NODES * NODES) atomicAdd(A.gadj + (size_t)k * NODES * NODES + r, v);
       else atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
     }
-    if (A.y != nullptr && threadIdx.x == 0) atomicAdd(A.loss_out, s_gacc[MAX_HEADS * RG] * A.inv_n);
+    if (A.y != nullptr && threadIdx.x == 0) {
+      atomicAdd(A.loss_out, s_gacc[MAX_HEADS * RG] * A.inv_n);
+      if (A.mse_out != nullptr) atomicAdd(A.mse_out, s_gacc[MAX_HEADS * RG + 1] * A.inv_n);
+    }
   }
   if (warp == LF_MMA_WARP) {
     __syncwarp();
@@ -879,7 +885,7 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
 int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias, const float* a,
                  const float* adj, const uint8_t* mask, void* out, const void* dout, void* dwh, float* partial,
                  float* ga, float* gadj, int* ncta_out, int* nt_out, cudaStream_t st, const void* y = nullptr,
-                 float* loss_out = nullptr, float lambda = 0.f) {
+                 float* loss_out = nullptr, float lambda = 0.f, float* mse_out = nullptr) {
   if (!layer_supported(d)) return fail(CGAT_EUNSUPPORTED, "fused conv-GAT layer kernel does not support this shape");
   if (!aligned16(x) || !aligned16(wpack) || (out && !aligned16(out)) || (dout && !aligned16(dout)) ||
       (dwh && !aligned16(dwh)) || (partial && !aligned16(partial)))
@@ -892,7 +898,7 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
   A.out = (__nv_bfloat16*)out; A.dout = (const __nv_bfloat16*)dout; A.dwh = (__nv_bfloat16*)dwh;
   A.partial = partial; A.ga = ga; A.gadj = gadj;
-  A.y = (const __nv_bfloat16*)y; A.loss_out = loss_out; A.lambda = lambda;
+  A.y = (const __nv_bfloat16*)y; A.loss_out = loss_out; A.mse_out = mse_out; A.lambda = lambda;
   A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
   A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && d->heads <= LF_GROUPS) ? A.inv_n : 1.f;
   A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
@@ -942,7 +948,7 @@ extern "C" int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const voi
 
 extern "C" int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
                                 const float* bias_dense, const float* a, const float* adj, const uint8_t* mask,
-                                float lambda, void* workspace, float* ga, float* gadj, float* loss_out,
+                                float lambda, void* workspace, float* ga, float* gadj, float* loss_out, float* mse_out,
                                 int32_t* ncta_out, int32_t* nt_out, void* stream) {
   if (!d || !x || !y || !wpack || !a || !adj || !workspace || !ga || !gadj || !loss_out || !ncta_out || !nt_out)
     return fail(CGAT_EINVAL, "null argument");
@@ -951,7 +957,7 @@ extern "C" int cgat_layer_train(const cgat_layer_desc* d, const void* x, const v
   if (!aligned16(y)) return fail(CGAT_EALIGN, "y must be 16-byte aligned");
   int ncta = 0, nt = 0;
   const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, nullptr, nullptr, (float*)workspace,
-                              ga, gadj, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda);
+                              ga, gadj, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda, mse_out);
   *ncta_out = ncta;
   *nt_out = nt;
   return rc;

@@ -44,10 +44,11 @@ __device__ __forceinline__ void store_vec(T* p, const float* f) {
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) loss_kernel(const T* __restrict__ yhat, const T* __restrict__ y,
                                                           T* __restrict__ dyhat, float* __restrict__ loss_out,
-                                                          long long n, float lambda, float grad_scale) {
+                                                          float* __restrict__ mse_out, long long n, float lambda,
+                                                          float grad_scale) {
   constexpr int V = Vec<T>::N;
   const float inv_n = 1.f / (float)n;
-  float acc = 0.f;
+  float acc = 0.f, acc2 = 0.f;
   const long long nvec = n / V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float a[V], b[V], g[V];
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(EW_THREADS) loss_kernel(const T* __restrict__ 
     for (int k = 0; k < V; ++k) {
       const float d = a[k] - b[k];
       acc += d * d - lambda * a[k];
+      acc2 += d * d;
       g[k] = (2.f * d - lambda) * inv_n * grad_scale;
     }
     store_vec<T>(dyhat + i * V, g);
@@ -65,17 +67,24 @@ __global__ void __launch_bounds__(EW_THREADS) loss_kernel(const T* __restrict__ 
     for (long long i = nvec * V; i < n; ++i) {
       const float a = DT<T>::to_f(yhat[i]), d = a - DT<T>::to_f(y[i]);
       acc += d * d - lambda * a;
+      acc2 += d * d;
       dyhat[i] = DT<T>::from_f((2.f * d - lambda) * inv_n * grad_scale);
     }
   }
-  __shared__ float s[EW_THREADS / 32];
+  __shared__ float s[2][EW_THREADS / 32];
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  acc2 = warp_sum(acc2);
+  if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = acc; s[1][threadIdx.x >> 5] = acc2; }
   __syncthreads();
   if (threadIdx.x < 32) {
-    float v = threadIdx.x < EW_THREADS / 32 ? s[threadIdx.x] : 0.f;
+    float v = threadIdx.x < EW_THREADS / 32 ? s[0][threadIdx.x] : 0.f;
+    float v2 = threadIdx.x < EW_THREADS / 32 ? s[1][threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(loss_out, v * inv_n);
+    v2 = warp_sum(v2);
+    if (threadIdx.x == 0) {
+      atomicAdd(loss_out, v * inv_n);
+      if (mse_out != nullptr) atomicAdd(mse_out, v2 * inv_n);
+    }
   }
 }
 
@@ -118,17 +127,17 @@ static int ew_grid(long long work_items) {
 
 using namespace cgat;
 
-extern "C" int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_out, int64_t n,
-                                 float lambda, float grad_scale, int dtype, void* stream) {
+extern "C" int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_out, float* mse_out,
+                                 int64_t n, float lambda, float grad_scale, int dtype, void* stream) {
   if (!yhat || !y || !dyhat || !loss_out || n <= 0) return fail(CGAT_EINVAL, "null argument or n <= 0");
   if (!aligned16(yhat) || !aligned16(y) || !aligned16(dyhat)) return fail(CGAT_EALIGN, "pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CGAT_F32) {
     loss_kernel<float><<<ew_grid(n / 4 + 1), EW_THREADS, 0, st>>>((const float*)yhat, (const float*)y, (float*)dyhat,
-                                                                   loss_out, n, lambda, grad_scale);
+                                                                   loss_out, mse_out, n, lambda, grad_scale);
   } else if (dtype == CGAT_BF16) {
     loss_kernel<__nv_bfloat16><<<ew_grid(n / 8 + 1), EW_THREADS, 0, st>>>(
-        (const __nv_bfloat16*)yhat, (const __nv_bfloat16*)y, (__nv_bfloat16*)dyhat, loss_out, n, lambda, grad_scale);
+        (const __nv_bfloat16*)yhat, (const __nv_bfloat16*)y, (__nv_bfloat16*)dyhat, loss_out, mse_out, n, lambda, grad_scale);
   } else {
     return fail(CGAT_EINVAL, "bad dtype %d", dtype);
   }

@@ -192,11 +192,12 @@ int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, co
  * loss.backward()  (convolutional_gat/train.py:130-132) for a model that is one mean-merged conv stream (the
  * Spatial/Temporal models of convolutional_gat/model.py:8-88 use only their hidden layer).  The forward is
  * recomputed in-kernel anyway, so out and d(out) never exist in HBM: reads x and y, writes the parameter-gradient
- * partial sums and ACCUMULATES the scalar loss into loss_out[0].  heads <= 3, CGAT_MERGE_MEAN.                 */
+ * partial sums and ACCUMULATES the scalar loss into loss_out[0] and, if mse_out != NULL, the plain mean squared error
+ * (the reference's running train loss, train.py:135-139) into mse_out[0].  heads <= 3, CGAT_MERGE_MEAN.        */
 int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
                      const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, float lambda,
-                     void* workspace, float* ga, float* gadj, float* loss_out, int32_t* ncta_out, int32_t* nt_out,
-                     void* stream);
+                     void* workspace, float* ga, float* gadj, float* loss_out, float* mse_out, int32_t* ncta_out,
+                     int32_t* nt_out, void* stream);
 
 /* a8  the 1-D layer after its GEMM: GraphAttentionLayer.forward lines 36-56 of convolutional_gat/baseline_model.py
  * (scores :36-38 / :58-65, soft-max over neighbours :39, attention <- A_hat . attention :53, aggregation :54,
@@ -211,9 +212,10 @@ int cgat_gat1d_bwd(const float* Wh, const float* a, const float* adj, const uint
 
 /* a12  train-step pieces, convolutional_gat/train.py:131 and :212.
  * loss = mean((yhat-y)^2) - lambda*mean(yhat); writes dloss/dyhat (same dtype as yhat) and
- * ACCUMULATES the scalar loss into loss_out[0] (fp32; caller zeroes).                              */
-int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_out, int64_t n, float lambda,
-                      float grad_scale, int dtype, void* stream);
+ * ACCUMULATES the scalar loss into loss_out[0] and, if mse_out != NULL, mean((yhat-y)^2) into mse_out[0]
+ * (fp32; caller zeroes).                                                                           */
+int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_out, float* mse_out, int64_t n,
+                      float lambda, float grad_scale, int dtype, void* stream);
 /* torch.optim.Adam(lr, weight_decay) on flat fp32 buffers; `step` is the 1-based step count read
  * from device memory (so the launch is CUDA-graph replayable); grad is multiplied by grad_scale
  * (1/world after a sum all-reduce).                                                                 */
@@ -229,6 +231,11 @@ int cgat_adam_step(float* param, const float* grad, float* m, float* v, const in
 int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y, int32_t n,
                        int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w, int32_t steps,
                        float normalizing_max, float power, int32_t dtype, void* stream);
+/* f4  validation metrics of convolutional_gat/train.py:53-75 + utils.py:135-167 in one pass over y, y_hat (n elements of
+ * `dtype`): ACCUMULATES into out6 (double, caller zeroes)  [0] sum (y'-yh')^2  [1] sum ((y'-yh')*normalizing_max)^2
+ * [2] TP [3] FP [4] FN [5] #(bin(y') == bin(yh')),  y' = y^(1/power), bin = the threshold binarisation of utils.py:138-141. */
+int cgat_val_metrics(const void* y, const void* y_hat, int64_t n, float power, float threshold, float normalizing_max,
+                     int32_t dtype, double* out6, void* stream);
 /* dtype conversion of contiguous buffers (fp32 <-> bf16) */
 int cgat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 

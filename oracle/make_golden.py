@@ -230,6 +230,58 @@ def kmni_loader():
     return fx
 
 
+def _ref_functions(relpath, names, namespace):
+    """Compile the named top-level functions of a reference file (whose module cannot be imported: missing GAT3D /
+    matplotlib / torchinfo) from its UNMODIFIED source text into ``namespace``."""
+    import ast
+
+    src = open(os.path.join(ref_loader.REFERENCE_ROOT, relpath)).read()
+    tree = ast.parse(src)
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), relpath, "exec"), namespace)
+    return namespace
+
+
+class _AffineModel(torch.nn.Module):
+    """Stand-in model for the validation loop: y_hat = 0.9 x + 0.02 (positive, so the 1/power root is defined)."""
+
+    def forward(self, x):
+        return 0.9 * x + 0.02
+
+
+def val_metrics():
+    """The reference's own ``test`` loop (convolutional_gat/train.py:28-91) and ``get_metrics`` (utils.py:135-167),
+    compiled from their source, on a stand-in model and synthetic batches (one of size 1: skipped, :52)."""
+    ns = _ref_functions("convolutional_gat/utils.py", ("get_metrics", "accuracy", "precision", "recall"), {"t": torch})
+    ns.update({"nn": torch.nn, "tqdm": lambda it: it})
+    _ref_functions("convolutional_gat/train.py", ("test",), ns)
+    g = torch.Generator().manual_seed(369)
+    fx = {}
+    for tag, power in (("p1", 1.0), ("p05", 0.5)):
+        batches = []
+        for n in (3, 1, 2):
+            x = torch.pow(torch.randint(0, 255, (n, 8, 8, 4, 6), generator=g).float() / 254, power)
+            y = torch.pow(torch.randint(0, 40, (n, 8, 8, 4, 6), generator=g).float() / 254, power)
+            batches.append((x, y))
+
+        class Loader(list):
+            pass
+
+        loader = Loader(batches)
+        loader.power = torch.tensor(power)
+        loader.normalizing_max = 254
+        res = ns["test"](_AffineModel(), "cpu", loader)
+        for i, (x, y) in enumerate(batches):
+            fx[f"{tag}.x{i}"], fx[f"{tag}.y{i}"] = x, y
+        for k, v in res.items():
+            fx[f"{tag}.{k}"] = torch.tensor(v, dtype=torch.float64)
+        # get_metrics alone on the first batch, threshold = an arbitrary level
+        acc, prec, rec = ns["get_metrics"](batches[0][1], _AffineModel()(batches[0][0]), 0.05)
+        fx[f"{tag}.gm"] = torch.stack([acc.double(), prec.double(), rec.double()])
+    return fx
+
+
 def adjacency():
     bm = ref_loader.baseline_model()
     torch.manual_seed(369)
@@ -266,6 +318,7 @@ FIXTURES = {
     "dcgan_nets": dcgan_nets,
     "dcgan_step": dcgan_step,
     "kmni_loader": kmni_loader,
+    "val_metrics": val_metrics,
     "adjacency": adjacency,
 }
 
