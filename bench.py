@@ -272,8 +272,10 @@ def run_ours(args):
         ts.run()
     torch.cuda.synchronize()
     _lib.profile_start()
+    frames_d, start_d = frames_h.to(dev), start_h.to(dev)
     for _ in range(max(3, min(args.steps, 10))):
         flush.zero_()
+        gather_windows(frames_d, start_d, steps=T, out=(ts.x, ts.y))  # the e2e path's per-step loader kernel
         ts.run()
     torch.cuda.synchronize()
     prof = _lib.profile_stop()
@@ -296,6 +298,7 @@ def run_ours(args):
         "cgat_attn_fwd": ("hbm", n_pix * (in_rec + rec) * esz),
         "cgat_attn_bwd": ("hbm", n_pix * (2 * in_rec + rec) * esz),
         "cgat_loss_fwd_bwd": ("hbm", n_pix * rec * 3 * esz),
+        "cgat_loader_gather": ("hbm", n_pix * rec * 2 * esz + frames_h.numel()),  # writes x, y; reads the raw frames once
     }
     if pre:
         # fused conv + attention kernels: forward reads x and writes out; backward reads x and d(out) (the projected

@@ -437,3 +437,40 @@ def unet_model_forward(unet: nn.Module, x: torch.Tensor) -> torch.Tensor:
     xv = x.permute(4, 0, 3, 1, 2)  # [V,B,T,H,W]                       (:24)
     acc = [unet(xv[i]) for i in range(xv.shape[0])]  #                  (:25-26)
     return torch.stack(acc).permute(1, 3, 4, 2, 0)  #                   (:27-28)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# KNMI loader windows (convolutional_gat/data_loaders/kmni_data_loader.py:72-127) and validation metrics
+# (convolutional_gat/train.py:53-75, utils.py:135-167)
+# ----------------------------------------------------------------------------------------------------------------
+def kmni_windows(frames: torch.Tensor, start, *, crop=None, steps: int = 4, normalizing_max: float = 254.0,
+                 power: float = 1.0):
+    """``frames [L, V, H, W]`` raw integers -> ``(x, y)`` ``[N, H', W', steps, V]`` for the windows beginning at ``start``:
+    ``/normalizing_max`` (:75), ``pow`` (:76), window ``i .. i+2*steps-1`` split in two (:79-94), crop (:95-96), permute
+    to ``[N, H, W, T, V]`` (:121)."""
+    data = torch.pow(frames.to(torch.int64) / normalizing_max, torch.tensor(power))
+    xs, ys = [], []
+    for i in start:
+        seg = data[int(i):int(i) + 2 * steps]  # [2*steps, V, H, W]
+        if crop is not None:
+            seg = seg[:, :, :crop, :crop]
+        xs.append(seg[:steps].permute(2, 3, 0, 1))
+        ys.append(seg[steps:].permute(2, 3, 0, 1))
+    return torch.stack(xs), torch.stack(ys)
+
+
+def val_batch_sums(y, y_hat, threshold, *, power=1.0, normalizing_max=254.0):
+    """``[sum sq err, sum denormalised sq err, TP, FP, FN, #equal]`` of one batch (train.py:54-75, utils.py:135-167)."""
+    y = torch.pow(y.double().float(), 1 / torch.tensor(power))
+    y_hat = torch.pow(y_hat.double().float(), 1 / torch.tensor(power))
+    d = (y - y_hat).double()
+    yb, hb = y.clone(), y_hat.clone()
+    for v in (yb, hb):  # utils.py:138-141, the two in-place assignments in their order
+        v[v < threshold] = 0
+        v[v >= threshold] = 1
+    tp = ((hb == 1) & (yb == 1)).sum()
+    fp = ((hb == 1) & (yb == 0)).sum()
+    fn = ((hb == 0) & (yb == 1)).sum()
+    eq = (yb == hb).sum()
+    return torch.stack([(d ** 2).sum(), ((d * normalizing_max) ** 2).sum(), tp.double(), fp.double(), fn.double(),
+                        eq.double()])

@@ -107,3 +107,49 @@ def test_spec_gat3d_degenerates_to_pinned_2d_layer():
     layer.stream.attention_0.load_state_dict(sd)
     out = layer(h.reshape(N, 20, 20, T, V))
     close(out.reshape(N, P, T, V), fx["out"], msg="spec 3D vs reference 2D")
+
+
+@pytest.mark.parametrize("tag,power", [("p1", 1.0), ("p05", 0.5)])
+def test_kmni_windows_match_reference_loader(tag, power):
+    """oracle/spec.kmni_windows against batches of the reference's own DataLoader (shuffle off)."""
+    fx = golden("kmni_loader")
+    # file 0: 17 frames -> 16 -> 9 windows in batches of 4, 4, 1; file 1: 10 -> 8 -> 1 window
+    plan = [("file0", range(0, 4)), ("file0", range(4, 8)), ("file0", range(8, 9)), ("file1", range(0, 1))]
+    for b, (f, starts) in enumerate(plan):
+        x, y = spec.kmni_windows(fx[f], list(starts), crop=8, power=power)
+        assert torch.equal(x, fx[f"{tag}.x{b}"]) and torch.equal(y, fx[f"{tag}.y{b}"])
+
+
+@pytest.mark.parametrize("tag,power", [("p1", 1.0), ("p05", 0.5)])
+def test_val_metrics_match_reference_test_loop(tag, power):
+    """oracle/spec.val_batch_sums, folded as train.py:76-91 does, against the reference's own ``test`` / ``get_metrics``."""
+    fx = golden("val_metrics")
+    tot = torch.zeros(5, dtype=torch.float64)
+    n_seen = 0
+    for i in range(3):
+        x, y = fx[f"{tag}.x{i}"], fx[f"{tag}.y{i}"]
+        if len(x) <= 1:
+            continue
+        y_hat = 0.9 * x + 0.02
+        uniq = torch.unique(torch.pow(y, 1 / torch.tensor(power)))
+        thr = uniq[int(len(uniq) * 0.5)]
+        s = spec.val_batch_sums(y, y_hat, thr, power=power)
+        n, per = len(x), y[0].numel()
+        tot += torch.stack([s[0] / per, s[5] / per, s[2] / (s[2] + s[3]) * n, s[2] / (s[2] + s[4]) * n, s[1] / per])
+        n_seen += n
+    for k, v in zip(("val_loss", "val_acc", "val_prec", "val_rec", "val_denorm_mse"), tot / n_seen):
+        close(v, fx[f"{tag}.{k}"], rtol=2e-5, atol=1e-7, msg=k)
+    s = spec.val_batch_sums(fx[f"{tag}.y0"], 0.9 * fx[f"{tag}.x0"] + 0.02, 0.05)
+    n, per = 3, fx[f"{tag}.y0"][0].numel()
+    close(torch.stack([s[5] / per, s[2] / (s[2] + s[3]) * n, s[2] / (s[2] + s[4]) * n]), fx[f"{tag}.gm"], rtol=1e-6,
+          atol=1e-7, msg="get_metrics")
+
+
+def test_dcgan_step_fixture_is_consistent():
+    """The adversarial-step fixture holds the reference's state before and after its step; the nets moved."""
+    fx = golden("dcgan_step")
+    for name in ("G", "FD", "TD"):
+        sd0, sd1 = sd_of(fx, f"{name}.sd0."), sd_of(fx, f"{name}.sd1.")
+        assert sd0.keys() == sd1.keys()
+        assert any((sd0[k].float() - sd1[k].float()).abs().max() > 0 for k in sd0)
+    assert all(torch.isfinite(fx[k]) for k in ("errFD", "errTD", "errG"))
