@@ -8,9 +8,8 @@
 // copy is 8 x 4 bytes per value of redundancy.  Here the raw frames cross PCIe ONCE as uint8 and one kernel gathers
 //   x[n, h, w, t, v] = pow(frame[start[n] + t    , v, h, w] / 254, power)
 //   y[n, h, w, t, v] = pow(frame[start[n] + 4 + t, v, h, w] / 254, power)
-// straight into the pixel-record layout the conv-GAT kernels read.  One thread per output pixel: its T*V record is
-// written with 16-byte stores; reads are coalesced along w.  fp32 output is bit-exact with the reference for power = 1
-// (IEEE division); bf16 output rounds that value once.
+// straight into the pixel-record layout the conv-GAT kernels read.  fp32 output is bit-exact with the reference for
+// power = 1 (IEEE division); bf16 output rounds that value once.
 #include "common.cuh"
 
 namespace cgat {
@@ -18,67 +17,70 @@ namespace cgat {
 constexpr int LD_THREADS = 128;
 constexpr int LD_MAX_REC = 64;  // T * V elements per pixel record
 
-// REC = steps * V when known at compile time (record kept in registers, 16-byte stores), 0 = generic
-template <typename T, int REC>
+// One CTA = LD_THREADS consecutive output pixels of one sample.  Phase 1: the 2*steps*V source planes of the window
+// are staged in shared memory with 4-byte loads where the 4 pixels lie in one image row (always, for the usual
+// crop_w % 4 == 0), 12 loads per thread instead of 48 single bytes.  A 256-entry table holds pow(k / max, power) in
+// the output dtype (computed once per CTA with the IEEE division the reference's torch ops perform), so phase 2 is
+// two shared-memory reads per element and 16-byte record stores.
+template <typename T>
 __global__ void __launch_bounds__(LD_THREADS)
 loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ start, T* __restrict__ x,
-                     T* __restrict__ y, int n, int V, int H, int W, int crop_h, int crop_w, int steps, float nmax,
-                     float power) {
-  const long long pix = (long long)blockIdx.x * LD_THREADS + threadIdx.x;
-  const long long total = (long long)n * crop_h * crop_w;
-  if (pix >= total) return;
-  const int w = (int)(pix % crop_w);
-  const int h = (int)((pix / crop_w) % crop_h);
-  const int s = (int)(pix / ((long long)crop_w * crop_h));
+                     T* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, int steps, float nmax, float power) {
+  extern __shared__ __align__(16) unsigned char ld_smem[];
+  T* lut = reinterpret_cast<T*>(ld_smem);                       // [256]
+  uint8_t* tile = ld_smem + 256 * sizeof(T);                    // [2*steps*V][LD_THREADS]
+  const int rec = steps * V, planes = 2 * rec;
+  const long long per_sample = (long long)crop_h * crop_w;
+  const long long blocks_per_sample = (per_sample + LD_THREADS - 1) / LD_THREADS;
+  const int s = (int)(blockIdx.x / blocks_per_sample);
+  const long long p0 = (long long)(blockIdx.x % blocks_per_sample) * LD_THREADS;  // first pixel of this CTA in the sample
+  const int npix = (int)min((long long)LD_THREADS, per_sample - p0);
   const int f0 = start[s];
-  const int rec = REC ? REC : steps * V;
   const size_t plane = (size_t)H * W;
-  const bool unit = power == 1.0f;
+  for (int k = threadIdx.x; k < 256; k += LD_THREADS) {
+    float v = __fdiv_rn((float)k, nmax);          // torch: data / 254          (kmni_data_loader.py:75)
+    if (power != 1.0f) v = powf(v, power);        //        t.pow(norm, power)  (:76)
+    lut[k] = DT<T>::from_f(v);
+  }
+  const uint8_t* src0 = frames + (size_t)f0 * V * plane;  // plane e of the window = frame f0 + e / V, vertex e % V
+  for (int idx = threadIdx.x; idx < planes * (LD_THREADS / 4); idx += LD_THREADS) {
+    const int e = idx / (LD_THREADS / 4), q = idx % (LD_THREADS / 4);
+    const int lp = 4 * q;
+    if (lp >= npix) continue;
+    const long long p = p0 + lp;
+    const int h = (int)(p / crop_w), w = (int)(p % crop_w);
+    const uint8_t* sp = src0 + (size_t)e * plane + (size_t)h * W + w;
+    uint32_t word;
+    if (w + 3 < crop_w && lp + 3 < npix && (reinterpret_cast<uintptr_t>(sp) & 3u) == 0) {
+      word = *reinterpret_cast<const uint32_t*>(sp);
+    } else {
+      word = 0;
+      for (int j = 0; j < 4 && lp + j < npix; ++j) {
+        const long long pj = p + j;
+        word |= (uint32_t)src0[(size_t)e * plane + (size_t)(pj / crop_w) * W + (pj % crop_w)] << (8 * j);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(tile + (size_t)e * LD_THREADS + lp) = word;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= npix) return;
+  const long long pix = (long long)s * per_sample + p0 + threadIdx.x;
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     T* dst = (half ? y : x) + pix * rec;
-    // e = t * V + v: frame f0 (+ steps for the target) + t, vertex v  ->  source plane (f0 + ..) * V + e
-    const uint8_t* src = frames + ((size_t)(f0 + half * steps) * V) * plane + (size_t)h * W + w;
-    if constexpr (REC != 0) {
-      float vals[REC];
+    const uint8_t* col = tile + (size_t)(half * rec) * LD_THREADS + threadIdx.x;
+    if ((rec * sizeof(T)) % 16 == 0) {
+      constexpr int PER = 16 / sizeof(T);
+      for (int q = 0; q < rec / PER; ++q) {
+        T v[PER];
 #pragma unroll
-      for (int e = 0; e < REC; ++e) {
-        float v = __fdiv_rn((float)src[(size_t)e * plane], nmax);  // IEEE division, as torch's data / 254 (:75)
-        if (!unit) v = powf(v, power);                              // t.pow(norm_data, power) (:76)
-        vals[e] = v;
-      }
-      if constexpr (sizeof(T) == 4) {
-#pragma unroll
-        for (int q = 0; q < REC / 4; ++q)
-          reinterpret_cast<float4*>(dst)[q] = make_float4(vals[4 * q], vals[4 * q + 1], vals[4 * q + 2], vals[4 * q + 3]);
-      } else {
-#pragma unroll
-        for (int q = 0; q < REC / 8; ++q) {
-          uint4 o;
-          __nv_bfloat162 t2;
-#define PK(a, b) (t2 = __floats2bfloat162_rn(a, b), *reinterpret_cast<uint32_t*>(&t2))
-          o.x = PK(vals[8 * q], vals[8 * q + 1]); o.y = PK(vals[8 * q + 2], vals[8 * q + 3]);
-          o.z = PK(vals[8 * q + 4], vals[8 * q + 5]); o.w = PK(vals[8 * q + 6], vals[8 * q + 7]);
-#undef PK
-          reinterpret_cast<uint4*>(dst)[q] = o;
-        }
+        for (int j = 0; j < PER; ++j) v[j] = lut[col[(size_t)(q * PER + j) * LD_THREADS]];
+        reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<const uint4*>(v);
       }
     } else {
-      for (int e = 0; e < rec; ++e) {
-        float v = __fdiv_rn((float)src[(size_t)e * plane], nmax);
-        if (!unit) v = powf(v, power);
-        dst[e] = DT<T>::from_f(v);
-      }
+      for (int e = 0; e < rec; ++e) dst[e] = lut[col[(size_t)e * LD_THREADS]];
     }
   }
-}
-
-template <typename T>
-static void loader_launch(int rec, unsigned grid, cudaStream_t st, const uint8_t* frames, const int32_t* start, T* x, T* y,
-                          int n, int V, int H, int W, int ch, int cw, int steps, float nmax, float power) {
-  if (rec == 24) loader_gather_kernel<T, 24><<<grid, LD_THREADS, 0, st>>>(frames, start, x, y, n, V, H, W, ch, cw, steps, nmax, power);
-  else if (rec == 32) loader_gather_kernel<T, 32><<<grid, LD_THREADS, 0, st>>>(frames, start, x, y, n, V, H, W, ch, cw, steps, nmax, power);
-  else loader_gather_kernel<T, 0><<<grid, LD_THREADS, 0, st>>>(frames, start, x, y, n, V, H, W, ch, cw, steps, nmax, power);
 }
 
 }  // namespace cgat
@@ -95,14 +97,18 @@ extern "C" int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const
   if (steps * vertices > LD_MAX_REC) return fail(CGAT_EUNSUPPORTED, "pixel record of %d elements (max %d)", steps * vertices, LD_MAX_REC);
   if (dtype != CGAT_F32 && dtype != CGAT_BF16) return fail(CGAT_EINVAL, "bad dtype %d", dtype);
   if (!(normalizing_max > 0.f)) return fail(CGAT_EINVAL, "normalizing_max must be positive");
-  const long long total = (long long)n * crop_h * crop_w;
-  const unsigned grid = (unsigned)((total + LD_THREADS - 1) / LD_THREADS);
+  const long long per_sample = (long long)crop_h * crop_w;
+  const unsigned grid = (unsigned)(n * ((per_sample + LD_THREADS - 1) / LD_THREADS));
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t esz = dtype == CGAT_F32 ? 4 : 2;
+  const size_t smem = 256 * esz + (size_t)2 * steps * vertices * LD_THREADS;
+  if (smem > 48 * 1024) return fail(CGAT_EUNSUPPORTED, "loader tile needs %zu B of shared memory", smem);
   if (dtype == CGAT_F32)
-    loader_launch<float>(steps * vertices, grid, st, frames, start, (float*)x, (float*)y, n, vertices, h, w, crop_h, crop_w,
-                         steps, normalizing_max, power);
+    loader_gather_kernel<float><<<grid, LD_THREADS, smem, st>>>(frames, start, (float*)x, (float*)y, vertices, h, w, crop_h,
+                                                               crop_w, steps, normalizing_max, power);
   else
-    loader_launch<__nv_bfloat16>(steps * vertices, grid, st, frames, start, (__nv_bfloat16*)x, (__nv_bfloat16*)y, n, vertices,
-                                 h, w, crop_h, crop_w, steps, normalizing_max, power);
+    loader_gather_kernel<__nv_bfloat16><<<grid, LD_THREADS, smem, st>>>(frames, start, (__nv_bfloat16*)x, (__nv_bfloat16*)y,
+                                                                       vertices, h, w, crop_h, crop_w, steps,
+                                                                       normalizing_max, power);
   return check_launch("loader_gather_kernel");
 }
