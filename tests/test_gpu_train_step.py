@@ -57,19 +57,23 @@ def test_train_steps_match_oracle(attention_type, mapping, fuse):
     assert all(p.grad is None or not p.grad.any() for p in ours.net.output_layer.parameters())
 
 
-def test_fused_loss_kernel_equals_unfused_step():
-    """Same batch through cgat_layer_train and through layer_fwd + loss + layer_bwd."""
+@pytest.mark.parametrize("N,H,W", [(8, 64, 64), (14, 64, 64), (5, 50, 45), (64, 64, 64)])
+def test_fused_loss_kernel_equals_unfused_step(N, H, W):
+    """Same batch through cgat_layer_train (tile pairs in packed half2) and through layer_fwd + loss + layer_bwd
+    (fp32 math).  The sizes give CTAs with 1-2, 3-4 and 13-14 tiles (odd counts leave a pair half empty) and ragged
+    tiles in both directions."""
     from cgat.train_step import TrainStep
 
     res = {}
     for fuse in (True, False):
         ours, _ = _models("temporal", "conv", seed=33)
         torch.manual_seed(9)
-        x = torch.rand(8, 64, 64, 4, 6, device=DEV).bfloat16()
-        y = torch.rand(8, 64, 64, 4, 6, device=DEV).bfloat16()
+        x = torch.rand(N, H, W, 4, 6, device=DEV).bfloat16()
+        y = torch.rand(N, H, W, 4, 6, device=DEV).bfloat16()
         ts = TrainStep(ours, x, y, use_graph=False, fuse_loss=fuse)
         ts._fwd_bwd()
         torch.cuda.synchronize()
-        res[fuse] = (ts.loss.clone(), ts.flat_grad.clone())
+        res[fuse] = (ts.loss.clone(), ts.flat_grad.clone(), ts.mse.clone())
     close(res[True][0], res[False][0], rtol=2e-3, atol=1e-5, msg="loss")
+    close(res[True][2], res[False][2], rtol=2e-3, atol=1e-5, msg="mse")
     close(res[True][1], res[False][1], rtol=2e-2, atol=3e-2 * res[False][1].abs().max().item(), msg="flat gradient")
