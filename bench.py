@@ -189,6 +189,7 @@ def run_ours(args):
     launches0 = _lib.LAUNCHES
     ts = TrainStep(model, x, y, lr=1e-3, use_graph=True)
     ts.sync_params()
+    p2p = ts.enable_p2p_exchange() if world > 1 else False  # gradient exchange + Adam in one peer-memory kernel
     # launches of one step = those captured in the graph (one fwd+bwd pass) + Adam
     _lib.LAUNCHES = 0
     ts.graph = None
@@ -343,7 +344,10 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": dict(workload_config(args, B), gradient_exchange=("none (1 GPU)" if world == 1 else
+                       "cgat_p2p_allreduce_adam: push + rank-ordered sum + Adam in one kernel over NVLink peer memory"
+                       if p2p else "NCCL all_reduce + cgat_adam_step")),
         "e2e": {"value": world * B / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": frames_h.numel() + start_h.numel() * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,

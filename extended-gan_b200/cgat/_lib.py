@@ -104,6 +104,8 @@ SIGNATURES = {
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _P, _I64, _F, _F, _I, _P],
     "cgat_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P],
     "cgat_cast": [_P, _I, _P, _I, _I64, _P],
+    "cgat_p2p_mailbox_bytes": [_I64, _I],
+    "cgat_p2p_allreduce_adam": [_P, _I, _I, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P],
     "cgat_val_metrics": [_P, _P, _I64, _F, _F, _F, _I, _P, _P],
     "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
 }
@@ -128,6 +130,7 @@ def lib() -> ctypes.CDLL:
         L.cgat_conv_workspace_bytes.restype = ctypes.c_int64
         L.cgat_stream_wpack_bytes.restype = ctypes.c_int64
         L.cgat_layer_workspace_bytes.restype = ctypes.c_int64
+        L.cgat_p2p_mailbox_bytes.restype = ctypes.c_int64
         L.cgat_version.restype = ctypes.c_char_p
         L.cgat_last_error.restype = ctypes.c_char_p
         _lib = L

@@ -55,6 +55,46 @@ class FlatParams:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
         return world
 
+    def enable_p2p(self, group: Optional[dist.ProcessGroup] = None, max_elems: int = 1 << 20) -> bool:
+        """Set up the peer-memory mailboxes of ``cgat_p2p_allreduce_adam`` (one NVLink-mapped buffer per rank, exchanged
+        through torch's symmetric-memory rendezvous).  Returns False -- and leaves the NCCL path in place -- when the
+        job is single-rank, the vector is large, or symmetric memory is unavailable on this system."""
+        import ctypes
+
+        from . import _lib
+
+        self.p2p = None
+        if not (dist.is_initialized() and self.param.is_cuda):
+            return False
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = self.param.numel()
+        if world < 2 or world > 8 or n > max_elems:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            nbytes = _lib.lib().cgat_p2p_mailbox_bytes(n, world)
+            box = symm.empty(nbytes, dtype=torch.uint8, device=self.param.device)
+            box.zero_()
+            hdl = symm.rendezvous(box, group if group is not None else dist.group.WORLD)
+            ptrs = (ctypes.c_uint64 * world)(*[int(p) for p in hdl.buffer_ptrs])
+            torch.cuda.synchronize()
+            dist.barrier(group)  # every mailbox is zeroed before anyone pushes
+        except Exception as e:  # noqa: BLE001 -- any failure here means "no peer memory": keep NCCL
+            self.p2p_error = repr(e)
+            return False
+        self.p2p = dict(box=box, hdl=hdl, ptrs=ptrs, rank=rank, world=world, n=n)
+        return True
+
+    def p2p_timed_out(self) -> bool:
+        """True if the exchange kernel ever gave up waiting for a peer (host sync; for tests / diagnostics)."""
+        p2p = getattr(self, "p2p", None)
+        if p2p is None:
+            return False
+        n_pad = (p2p["n"] + 31) & ~31
+        off = 2 * p2p["world"] * n_pad * 4 + 2 * p2p["world"] * 4
+        return bool(p2p["box"][off:off + 4].view(torch.int32).item())
+
     def broadcast_params(self, src: int = 0, group: Optional[dist.ProcessGroup] = None):
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.broadcast(self.param, src=src, group=group)

@@ -79,6 +79,28 @@ class TrainStep:
         """Broadcast rank 0's parameters (data-parallel start state)."""
         self.flat.broadcast_params(0, self.pg)
 
+    def enable_p2p_exchange(self) -> bool:
+        """Replace all-reduce + Adam by the single peer-memory kernel (``cgat_p2p_allreduce_adam``) where available."""
+        return self.flat.enable_p2p(self.pg)
+
+    def _exchange_and_update(self):
+        """Gradient mean over ranks + Adam(lr, weight_decay): one P2P kernel, or NCCL all-reduce + fused Adam."""
+        self.step_count += 1
+        p2p = getattr(self.flat, "p2p", None)
+        if p2p is not None:
+            import ctypes
+
+            from . import _lib
+
+            _lib.call("cgat_p2p_allreduce_adam", ctypes.cast(p2p["ptrs"], ctypes.c_void_p), p2p["rank"], p2p["world"],
+                      _lib.ptr(self.flat_grad), _lib.ptr(self.flat_param), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                      _lib.ptr(self.step_count), self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.weight_decay, _lib.stream())
+            return
+        self.flat.all_reduce_grads(self.pg)
+        adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+                   self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+
     # -- one step -------------------------------------------------------------------------------
     def _fwd_bwd(self):
         self.flat_grad.zero_()
@@ -118,10 +140,7 @@ class TrainStep:
             self.graph.replay()
         else:
             self._fwd_bwd()
-        self.flat.all_reduce_grads(self.pg)
-        self.step_count += 1
-        adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
-                   self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        self._exchange_and_update()
         return self.loss
 
     def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
@@ -193,8 +212,5 @@ class TrainStep:
         cur.wait_event(s["ready"])
         s["graph"].replay()
         s["free"].record(cur)
-        self.flat.all_reduce_grads(self.pg)
-        self.step_count += 1
-        adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
-                   self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
+        self._exchange_and_update()
         return self.loss
