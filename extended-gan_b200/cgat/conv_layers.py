@@ -12,6 +12,7 @@ import math
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .functional import IMPL_AUTO, conv2d_nhwc
 
 
@@ -50,9 +51,34 @@ class Conv2d(nn.Module):
             bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
             nn.init.uniform_(self.bias, -bound, bound)
 
+    def _space_to_depth_route(self, x_nhwc):
+        """The DCGAN discriminators' ``k=4, stride=2, padding=1`` convs (dcgan/model.py:150-165) as a stride-1 2x2 conv
+        over the zero-padded input regrouped in 2x2 pixel blocks (4*cin channels): window rows ``2i-1 .. 2i+2`` are the
+        blocks ``i, i+1``, so nothing is wasted and the tcgen05 implicit-GEMM kernels (stride 1 only) serve it.  Returns
+        ``None`` when the shape is not of that class or the tensor-core path would not take the regrouped conv."""
+        import ctypes
+
+        N, H, W, C = x_nhwc.shape
+        if not (self.stride == 2 and self.kernel_size == (4, 4) and self.pad == (1, 1, 1, 1) and self.groups == 1
+                and self.impl == IMPL_AUTO and x_nhwc.is_cuda and x_nhwc.dtype == torch.bfloat16 and H % 2 == 0
+                and W % 2 == 0 and (4 * C) % 8 == 0):
+            return None
+        hs, ws = H // 2 + 1, W // 2 + 1
+        d = _lib.ConvDesc(N, hs, ws, 4 * C, self.out_channels, 2, 2, 1, 0, 0, hs - 1, ws - 1, _lib.BF16, self.act, 1)
+        if not _lib.lib().cgat_conv_tc_supported(ctypes.byref(d), 0):
+            return None
+        xp = torch.nn.functional.pad(x_nhwc, (0, 0, 1, 1, 1, 1))  # [N, H+2, W+2, C]
+        xs = xp.view(N, hs, 2, ws, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, hs, ws, 4 * C)  # channel = (a, b, c)
+        # weight[cout, c, 2r+a, 2s+b] -> [cout, r, s, (a, b, c)]
+        w = self.weight.view(self.out_channels, C, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(self.out_channels, 2, 2, 4 * C)
+        return conv2d_nhwc(xs, w, self.bias, stride=1, pad=(0, 0, 0, 0), act=self.act, impl=IMPL_AUTO)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """``x[N, C, H, W]`` (any memory format) -> ``[N, C', H', W']`` in channels_last memory."""
         x_nhwc = x.permute(0, 2, 3, 1)  # a view; contiguous iff x is channels_last
+        y = self._space_to_depth_route(x_nhwc)
+        if y is not None:
+            return y.permute(0, 3, 1, 2)
         w_krsc = self.weight.permute(0, 2, 3, 1)
         y = conv2d_nhwc(x_nhwc, w_krsc, self.bias, stride=self.stride, pad=self.pad, act=self.act, impl=self.impl,
                         groups=self.groups)

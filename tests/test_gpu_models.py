@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import spec
-from util import close, golden, sd_of
+from util import close, close_frac, golden, sd_of
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -153,3 +153,48 @@ def test_dcgan_adversarial_step_vs_reference_golden():
                   msg=f"{name}.{k} after the step")
         moved = sum(int((v.float().cpu() - fx[f"{name}.sd0.{k}"].float()).abs().max() > 0) for k, v in net.state_dict().items())
         assert moved > 0
+
+
+@pytest.mark.parametrize("name", ["FD", "TD"])
+def test_dcgan_discriminators_bf16_stride2_on_tensor_cores(name):
+    """bf16: the k=4 stride-2 convs run as space-to-depth + 2x2 stride-1 convs on the tcgen05 kernels (cgat.conv_layers).
+    Forward against the fp32 golden of the live reference at the bf16 bar; forward and every gradient against the SAME
+    bf16 net on the direct CUDA-core kernels (identical products, different summation order), which isolates the
+    regrouping from the bf16 rounding that five stacked layers accumulate."""
+    from cgat import _lib
+    from cgat.conv_layers import Conv2d
+    from cgat.functional import IMPL_AUTO, IMPL_DIRECT
+    from dcgan.model import FrameDiscriminator, TemporalDiscriminator
+    import cgat.functional as F
+
+    fx = golden("dcgan_nets")
+    params = {"nc": fx["params.nc"], "ndf": fx["params.ndf"]}
+    x, y = fx["x"], fx["y"]
+    res = {}
+    for mode in ("tc", "direct"):
+        net = {"FD": FrameDiscriminator, "TD": TemporalDiscriminator}[name](params)
+        net.load_state_dict(sd_of(fx, f"{name}.sd."))
+        net = net.to(DEV).eval()
+        for m in net.modules():
+            if isinstance(m, Conv2d):
+                m.impl = IMPL_AUTO if mode == "tc" else IMPL_DIRECT
+        inp = {"FD": y, "TD": torch.cat((x, y), 1)}[name].to(DEV).bfloat16().requires_grad_()
+        names, orig = [], _lib.call
+
+        def spy(n, *a, **k):
+            names.append((n, a[5] if n == "cgat_conv2d_fprop" else None))
+            return orig(n, *a, **k)
+
+        F._lib.call = spy
+        try:
+            out = net(inp)
+        finally:
+            F._lib.call = orig
+        n_tc = sum(1 for n, impl in names if n == "cgat_conv2d_fprop" and impl == 1)
+        assert (n_tc >= 3) if mode == "tc" else (n_tc == 0), names
+        out.float().backward(fx[f"{name}.g"].to(DEV))
+        res[mode] = dict({k: p.grad.float() for k, p in net.named_parameters()}, dx=inp.grad.float(), out=out.float())
+    close(res["tc"]["out"], fx[f"{name}.out"], rtol=2e-2, atol=2e-2, msg=f"{name} out vs reference")
+    for k, v in res["tc"].items():
+        r = res["direct"][k]
+        close(v, r, rtol=1e-2, atol=1e-2 * max(1e-9, r.abs().max().item()), msg=f"{name} {k}: tcgen05 vs direct")
