@@ -103,9 +103,10 @@ SIGNATURES = {
     "cgat_gat1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _P, _I64, _F, _F, _I, _P],
     "cgat_adam_step": [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P],
+    "cgat_adam_step_at": [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _F, _P],
     "cgat_cast": [_P, _I, _P, _I, _I64, _P],
     "cgat_p2p_mailbox_bytes": [_I64, _I],
-    "cgat_p2p_allreduce_adam": [_P, _I, _I, _P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P],
+    "cgat_p2p_allreduce_adam": [_P, _I, _I, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _P],
     "cgat_val_metrics": [_P, _P, _I64, _F, _F, _F, _I, _P, _P],
     "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
 }

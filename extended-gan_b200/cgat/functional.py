@@ -242,7 +242,13 @@ def loss_and_grad(y_hat: torch.Tensor, y: torch.Tensor, lam: float = 0.0005, gra
 
 
 def adam_step_(param, grad, m, v, step_dev, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
-    """In-place ``torch.optim.Adam`` update of flat fp32 buffers; ``step_dev`` is an int64 device scalar."""
+    """In-place ``torch.optim.Adam`` update of flat fp32 buffers; ``step_dev`` is an int64 device scalar, or a Python int
+    (the 1-based step count by value: no device counter)."""
+    if isinstance(step_dev, int):
+        require_cuda(param, grad, m, v)
+        _lib.call("cgat_adam_step_at", ptr(param), ptr(grad), ptr(m), ptr(v), step_dev, param.numel(), lr, beta1, beta2, eps,
+                  weight_decay, grad_scale, stream())
+        return
     require_cuda(param, grad, m, v, step_dev)
     _lib.call("cgat_adam_step", ptr(param), ptr(grad), ptr(m), ptr(v), ptr(step_dev), param.numel(), lr, beta1, beta2,
                                eps, weight_decay, grad_scale, stream())
@@ -434,7 +440,7 @@ def layer_train_supported(x, cfg: AttnConfig, mapping: str) -> bool:
     return bool(lib().cgat_layer_supported(ctypes.byref(ld)))
 
 
-def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None):
+def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None, acc=None):
     """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
     ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
 
@@ -464,8 +470,9 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
               _lib.ptr_array(Bs), ptr(wpack), None, None, ptr(bias_d), ptr(a_st), ptr(adj), st)
     mc = None if mask is None else mask.to(torch.uint8).contiguous()
     na, nadj = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes
-    acc = torch.zeros(na + nadj, device=dev, dtype=torch.float32)
-    ga, gadj = acc[:na], acc[na:]
+    if acc is None or acc.numel() < na + nadj:  # ``acc``: a caller-owned, already zeroed fp32 accumulator
+        acc = torch.zeros(na + nadj, device=dev, dtype=torch.float32)
+    ga, gadj = acc[:na], acc[na:na + nadj]
     wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
     ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
     _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),

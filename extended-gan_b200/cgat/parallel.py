@@ -31,7 +31,12 @@ class FlatParams:
         dev = self.named[0][1].device
         total = sum(p.numel() for _, p in self.named)
         self.param = torch.empty(total, device=dev, dtype=dtype)
-        self.grad = torch.zeros(total, device=dev, dtype=dtype)
+        # gradients plus a small scratch tail (loss scalars, per-step accumulators): ONE memset per step clears both
+        self.total = total
+        pad = (-total) % 4
+        self.grad_all = torch.zeros(total + pad + self.SCRATCH, device=dev, dtype=dtype)
+        self.grad = self.grad_all[:total]
+        self.scratch = self.grad_all[total + pad:]
         self.offsets = {}
         off = 0
         with torch.no_grad():
@@ -43,8 +48,10 @@ class FlatParams:
                 self.offsets[name] = (off, n)
                 off += n
 
+    SCRATCH = 512  # floats
+
     def zero_grad(self):
-        self.grad.zero_()
+        self.grad_all.zero_()
 
     def all_reduce_grads(self, group: Optional[dist.ProcessGroup] = None) -> int:
         """ONE sum all-reduce of the whole gradient buffer; returns the world size (the caller scales)."""

@@ -37,9 +37,7 @@ class TrainStep:
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.device = example_x.device
-        self._loss2 = torch.zeros(2, device=self.device, dtype=torch.float32)  # [loss, plain MSE]
-        self.loss, self.mse = self._loss2[:1], self._loss2[1:]
-        self.step_count = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self._step = 0  # optimiser steps taken (host side: Adam and the P2P exchange take it by value)
         self.graph = None
         self._slots = None  # double-buffered inputs for pipelined host->device loading (enable_prefetch)
         self.fused_stream = self._single_stream(model, example_x) if fuse_loss else None
@@ -74,6 +72,14 @@ class TrainStep:
         self.flat_param, self.flat_grad = self.flat.param, self.flat.grad
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        # loss scalars and the fused kernel's a / adjacency accumulators live in the gradient buffer's scratch tail
+        self.loss, self.mse = self.flat.scratch[0:1], self.flat.scratch[1:2]
+        self._acc = self.flat.scratch[8:]
+
+    @property
+    def step_count(self) -> torch.Tensor:
+        """Optimiser steps taken, as a device tensor (kept for checkpoint code written against the earlier attribute)."""
+        return torch.tensor([self._step], device=self.device, dtype=torch.int64)
 
     def sync_params(self):
         """Broadcast rank 0's parameters (data-parallel start state)."""
@@ -85,7 +91,7 @@ class TrainStep:
 
     def _exchange_and_update(self):
         """Gradient mean over ranks + Adam(lr, weight_decay): one P2P kernel, or NCCL all-reduce + fused Adam."""
-        self.step_count += 1
+        self._step += 1
         p2p = getattr(self.flat, "p2p", None)
         if p2p is not None:
             import ctypes
@@ -94,20 +100,19 @@ class TrainStep:
 
             _lib.call("cgat_p2p_allreduce_adam", ctypes.cast(p2p["ptrs"], ctypes.c_void_p), p2p["rank"], p2p["world"],
                       _lib.ptr(self.flat_grad), _lib.ptr(self.flat_param), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                      _lib.ptr(self.step_count), self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                      None, self._step, self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
                       self.weight_decay, _lib.stream())
             return
         self.flat.all_reduce_grads(self.pg)
-        adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr,
+        adam_step_(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._step, self.lr,
                    self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
 
     # -- one step -------------------------------------------------------------------------------
     def _fwd_bwd(self):
-        self.flat_grad.zero_()
-        self._loss2.zero_()
+        self.flat.zero_grad()  # gradients, loss scalars and accumulators: one memset
         if self.fused_stream is not None and self.fused_stream.train_step_supported(self.x):
             # forward + loss + backward in one kernel (cgat_layer_train)
-            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse)
+            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc)
             return
         prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
         try:

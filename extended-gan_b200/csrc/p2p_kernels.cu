@@ -36,8 +36,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(P2P_THREADS)
 p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, long long n_pad, const float* __restrict__ g,
                           float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                          const long long* __restrict__ step_dev, float lr, float b1, float b2, float eps, float wd) {
-  const long long epoch = *step_dev;
+                          const long long* __restrict__ step_dev, long long step_host, float lr, float b1, float b2,
+                          float eps, float wd) {
+  const long long epoch = step_dev != nullptr ? *step_dev : step_host;
   const int par = (int)(epoch & 1);
   const int tid = threadIdx.x;
   // 1. push
@@ -100,9 +101,11 @@ extern "C" int64_t cgat_p2p_mailbox_bytes(int64_t n, int32_t world) {
 }
 
 extern "C" int cgat_p2p_allreduce_adam(const uint64_t* peer_mailboxes, int32_t rank, int32_t world, const float* grad,
-                                       float* param, float* m, float* v, const int64_t* step_dev, int64_t n, float lr,
-                                       float beta1, float beta2, float eps, float weight_decay, void* stream) {
-  if (!peer_mailboxes || !grad || !param || !m || !v || !step_dev) return fail(CGAT_EINVAL, "null argument");
+                                       float* param, float* m, float* v, const int64_t* step_dev, int64_t step_host,
+                                       int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                       void* stream) {
+  if (!peer_mailboxes || !grad || !param || !m || !v) return fail(CGAT_EINVAL, "null argument");
+  if (!step_dev && step_host < 1) return fail(CGAT_EINVAL, "step_dev is NULL and step_host < 1");
   if (world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return fail(CGAT_EINVAL, "bad rank/world %d/%d", rank, world);
   if (n <= 0 || n > (1 << 20)) return fail(CGAT_EUNSUPPORTED, "p2p exchange serves vectors of at most 2^20 floats (n=%lld)", (long long)n);
   if (!aligned16(grad)) return fail(CGAT_EALIGN, "grad must be 16-byte aligned");
@@ -114,7 +117,7 @@ extern "C" int cgat_p2p_allreduce_adam(const uint64_t* peer_mailboxes, int32_t r
     P.flags[q] = reinterpret_cast<uint32_t*>(peer_mailboxes[q] + (uint64_t)2 * world * n_pad * 4);
   }
   p2p_allreduce_adam_kernel<<<1, P2P_THREADS, 0, (cudaStream_t)stream>>>(P, rank, world, n, n_pad, grad, param, m, v,
-                                                                         (const long long*)step_dev, lr, beta1, beta2, eps,
-                                                                         weight_decay);
+                                                                         (const long long*)step_dev, (long long)step_host, lr,
+                                                                         beta1, beta2, eps, weight_decay);
   return check_launch("p2p_allreduce_adam_kernel");
 }

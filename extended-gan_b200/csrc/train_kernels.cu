@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(EW_THREADS) loss_kernel(const T* __restrict__ 
 // torch.optim.Adam semantics (L2 weight decay folded into the gradient, bias-corrected moments).
 __global__ void __launch_bounds__(EW_THREADS) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                           float* __restrict__ m, float* __restrict__ v,
-                                                          const long long* __restrict__ step_dev, long long n,
-                                                          float lr, float b1, float b2, float eps, float wd,
+                                                          const long long* __restrict__ step_dev, long long step_host,
+                                                          long long n, float lr, float b1, float b2, float eps, float wd,
                                                           float gscale) {
-  const float step = (float)(*step_dev);
+  const float step = (float)(step_dev != nullptr ? *step_dev : step_host);
   const float bc1 = 1.f - powf(b1, step);
   const float bc2 = 1.f - powf(b2, step);
   const float step_size = lr / bc1;
@@ -148,8 +148,17 @@ extern "C" int cgat_adam_step(float* param, const float* grad, float* m, float* 
                               float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                               void* stream) {
   if (!param || !grad || !m || !v || !step_dev || n <= 0) return fail(CGAT_EINVAL, "null argument or n <= 0");
-  adam_kernel<<<ew_grid(n), EW_THREADS, 0, (cudaStream_t)stream>>>(param, grad, m, v, (const long long*)step_dev, n, lr,
+  adam_kernel<<<ew_grid(n), EW_THREADS, 0, (cudaStream_t)stream>>>(param, grad, m, v, (const long long*)step_dev, 0, n, lr,
                                                                    beta1, beta2, eps, weight_decay, grad_scale);
+  return check_launch("adam_kernel");
+}
+
+extern "C" int cgat_adam_step_at(float* param, const float* grad, float* m, float* v, int64_t step, int64_t n, float lr,
+                                 float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                 void* stream) {
+  if (!param || !grad || !m || !v || n <= 0 || step < 1) return fail(CGAT_EINVAL, "null argument, n <= 0 or step < 1");
+  adam_kernel<<<ew_grid(n), EW_THREADS, 0, (cudaStream_t)stream>>>(param, grad, m, v, nullptr, (long long)step, n, lr, beta1,
+                                                                   beta2, eps, weight_decay, grad_scale);
   return check_launch("adam_kernel");
 }
 

@@ -240,12 +240,15 @@ int cgat_val_metrics(const void* y, const void* y_hat, int64_t n, float power, f
  * rank owns a mailbox of cgat_p2p_mailbox_bytes(n, world) bytes in peer-mapped (symmetric) memory, ZEROED once before
  * the first step; peer_mailboxes is a HOST array of the `world` device addresses (index = rank).  The kernel pushes
  * `grad` into every peer's mailbox, signals, waits for all sources, sums them in rank order (bit-identical on every
- * rank), and applies torch.optim.Adam with the 1/world mean folded in (train.py:212).  `step_dev` is the 1-based step
- * counter (also the exchange epoch).  n <= 2^20 floats; larger models use an NCCL all-reduce + cgat_adam_step.        */
+ * rank), and applies torch.optim.Adam with the 1/world mean folded in (train.py:212).  The 1-based step count (also the
+ * exchange epoch) is read from `step_dev`, or taken from `step_host` when step_dev is NULL.  n <= 2^20 floats; larger models use an NCCL all-reduce + cgat_adam_step.        */
 int64_t cgat_p2p_mailbox_bytes(int64_t n, int32_t world);
 int cgat_p2p_allreduce_adam(const uint64_t* peer_mailboxes, int32_t rank, int32_t world, const float* grad, float* param,
-                            float* m, float* v, const int64_t* step_dev, int64_t n, float lr, float beta1, float beta2,
-                            float eps, float weight_decay, void* stream);
+                            float* m, float* v, const int64_t* step_dev, int64_t step_host, int64_t n, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* the same update with the 1-based step count passed by value (no device counter, no increment kernel) */
+int cgat_adam_step_at(float* param, const float* grad, float* m, float* v, int64_t step, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 /* dtype conversion of contiguous buffers (fp32 <-> bf16) */
 int cgat_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 
