@@ -22,14 +22,15 @@ constexpr int LD_MAX_REC = 64;  // T * V elements per pixel record
 // crop_w % 4 == 0), 12 loads per thread instead of 48 single bytes.  A 256-entry table holds pow(k / max, power) in
 // the output dtype (computed once per CTA with the IEEE division the reference's torch ops perform), so phase 2 is
 // two shared-memory reads per element and 16-byte record stores.
-template <typename T>
+// RECT = steps * V at compile time (fully unrolled record loops), 0 = generic
+template <typename T, int RECT>
 __global__ void __launch_bounds__(LD_THREADS)
 loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ start, T* __restrict__ x,
                      T* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, int steps, float nmax, float power) {
   extern __shared__ __align__(16) unsigned char ld_smem[];
   T* lut = reinterpret_cast<T*>(ld_smem);                       // [256]
   uint8_t* tile = ld_smem + 256 * sizeof(T);                    // [2*steps*V][LD_THREADS]
-  const int rec = steps * V, planes = 2 * rec;
+  const int rec = RECT ? RECT : steps * V, planes = 2 * rec;
   const long long per_sample = (long long)crop_h * crop_w;
   const long long blocks_per_sample = (per_sample + LD_THREADS - 1) / LD_THREADS;
   const int s = (int)(blockIdx.x / blocks_per_sample);
@@ -43,24 +44,37 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
     lut[k] = DT<T>::from_f(v);
   }
   const uint8_t* src0 = frames + (size_t)f0 * V * plane;  // plane e of the window = frame f0 + e / V, vertex e % V
-  for (int idx = threadIdx.x; idx < planes * (LD_THREADS / 4); idx += LD_THREADS) {
-    const int e = idx / (LD_THREADS / 4), q = idx % (LD_THREADS / 4);
+  {
+    // thread t stages pixels 4q .. 4q+3 (q = t % 32) of planes e = t / 32, t / 32 + 4, ...: the pixel geometry is
+    // computed once, the loop runs over planes only
+    const int q = threadIdx.x % (LD_THREADS / 4), e0 = threadIdx.x / (LD_THREADS / 4);
     const int lp = 4 * q;
-    if (lp >= npix) continue;
-    const long long p = p0 + lp;
-    const int h = (int)(p / crop_w), w = (int)(p % crop_w);
-    const uint8_t* sp = src0 + (size_t)e * plane + (size_t)h * W + w;
-    uint32_t word;
-    if (w + 3 < crop_w && lp + 3 < npix && (reinterpret_cast<uintptr_t>(sp) & 3u) == 0) {
-      word = *reinterpret_cast<const uint32_t*>(sp);
-    } else {
-      word = 0;
-      for (int j = 0; j < 4 && lp + j < npix; ++j) {
-        const long long pj = p + j;
-        word |= (uint32_t)src0[(size_t)e * plane + (size_t)(pj / crop_w) * W + (pj % crop_w)] << (8 * j);
+    if (lp < npix) {
+      const int p = (int)p0 + lp;
+      const int h = p / crop_w, w = p - h * crop_w;
+      const size_t off = (size_t)h * W + w;
+      const bool fast = w + 3 < crop_w && lp + 3 < npix && ((reinterpret_cast<uintptr_t>(src0) + off) & 3u) == 0 &&
+                        (plane & 3u) == 0;
+      int offj[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pj = p + j, hj = pj / crop_w;
+        offj[j] = lp + j < npix ? hj * W + (pj - hj * crop_w) : -1;
+      }
+      for (int e = e0; e < planes; e += LD_THREADS / (LD_THREADS / 4)) {
+        const uint8_t* sp = src0 + (size_t)e * plane;
+        uint32_t word;
+        if (fast) {
+          word = *reinterpret_cast<const uint32_t*>(sp + off);
+        } else {
+          word = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (offj[j] >= 0) word |= (uint32_t)sp[offj[j]] << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(tile + (size_t)e * LD_THREADS + lp) = word;
       }
     }
-    *reinterpret_cast<uint32_t*>(tile + (size_t)e * LD_THREADS + lp) = word;
   }
   __syncthreads();
   if ((int)threadIdx.x >= npix) return;
@@ -69,7 +83,19 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
   for (int half = 0; half < 2; ++half) {
     T* dst = (half ? y : x) + pix * rec;
     const uint8_t* col = tile + (size_t)(half * rec) * LD_THREADS + threadIdx.x;
-    if ((rec * sizeof(T)) % 16 == 0) {
+    if constexpr (RECT != 0 && (RECT * sizeof(T)) % 16 == 0) {
+      constexpr int PER = 16 / sizeof(T);
+      uint8_t k[RECT];
+#pragma unroll
+      for (int e = 0; e < RECT; ++e) k[e] = col[(size_t)e * LD_THREADS];  // all byte loads first, then the table
+#pragma unroll
+      for (int q = 0; q < RECT / PER; ++q) {
+        T v[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) v[j] = lut[k[q * PER + j]];
+        reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<const uint4*>(v);
+      }
+    } else if ((rec * sizeof(T)) % 16 == 0) {
       constexpr int PER = 16 / sizeof(T);
       for (int q = 0; q < rec / PER; ++q) {
         T v[PER];
@@ -103,12 +129,15 @@ extern "C" int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const
   const size_t esz = dtype == CGAT_F32 ? 4 : 2;
   const size_t smem = 256 * esz + (size_t)2 * steps * vertices * LD_THREADS;
   if (smem > 48 * 1024) return fail(CGAT_EUNSUPPORTED, "loader tile needs %zu B of shared memory", smem);
-  if (dtype == CGAT_F32)
-    loader_gather_kernel<float><<<grid, LD_THREADS, smem, st>>>(frames, start, (float*)x, (float*)y, vertices, h, w, crop_h,
-                                                               crop_w, steps, normalizing_max, power);
-  else
-    loader_gather_kernel<__nv_bfloat16><<<grid, LD_THREADS, smem, st>>>(frames, start, (__nv_bfloat16*)x, (__nv_bfloat16*)y,
-                                                                       vertices, h, w, crop_h, crop_w, steps,
-                                                                       normalizing_max, power);
+#define LD_LAUNCH(T, R)                                                                                                   \
+  loader_gather_kernel<T, R><<<grid, LD_THREADS, smem, st>>>(frames, start, (T*)x, (T*)y, vertices, h, w, crop_h, crop_w, steps, \
+                                                             normalizing_max, power)
+  const int rec = steps * vertices;
+  if (dtype == CGAT_F32) {
+    if (rec == 24) LD_LAUNCH(float, 24); else LD_LAUNCH(float, 0);
+  } else {
+    if (rec == 24) LD_LAUNCH(__nv_bfloat16, 24); else LD_LAUNCH(__nv_bfloat16, 0);
+  }
+#undef LD_LAUNCH
   return check_launch("loader_gather_kernel");
 }
