@@ -30,6 +30,7 @@
 // (24 + 3 * 160 <= 512 = the CTA's pool).
 #include "tc_common.cuh"
 #include "attn_common.cuh"
+#include <cstdlib>
 
 namespace cgat {
 
@@ -872,7 +873,7 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
   };
   int rc;
   const bool masked = A.mask != nullptr;  // NULL = all ones = the reference's dense attention: no mask arithmetic
-  if (bwd && A.y != nullptr && g.nstg == LF_MAXSTG && A.heads <= LF_GROUPS)  // train mode: tile pairs in packed half2
+  if (bwd && A.y != nullptr && A.out_scale != 1.f)  // train mode: tile pairs in packed half2 (see layer_launch)
     rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, true, true, true>) : go(layer_kernel<NODES, CO, SPATIAL, true, false, true>);
   else if (bwd)
     rc = masked ? go(layer_kernel<NODES, CO, SPATIAL, true, true, false>) : go(layer_kernel<NODES, CO, SPATIAL, true, false, false>);
@@ -900,7 +901,9 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.partial = partial; A.ga = ga; A.gadj = gadj;
   A.y = (const __nv_bfloat16*)y; A.loss_out = loss_out; A.mse_out = mse_out; A.lambda = lambda;
   A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
-  A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && d->heads <= LF_GROUPS) ? A.inv_n : 1.f;
+  // the paired half2 kernel carries d(out) without its 1/numel factor; CGAT_NO_PAIR=1 keeps the fp32 one-tile kernel
+  static const bool no_pair = std::getenv("CGAT_NO_PAIR") != nullptr;
+  A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && d->heads <= LF_GROUPS && !no_pair) ? A.inv_n : 1.f;
   A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
   A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt;
