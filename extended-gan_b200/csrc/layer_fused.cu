@@ -422,44 +422,51 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
                              : "l"(reinterpret_cast<const uint4*>(A.y + (half ? pixB : pixA) * REC) + q));
             }
           named_bar_sync(1, 128 * nact);
-          // ---- d(out) * numel = 2 (out - y) - lambda   per tile (fp32), kept as fp16 pairs of consecutive elements ----
+          // ---- d(out) * numel = 2 (out - y) - lambda per tile, in packed fp16 on the exchanged words themselves
+          //      (a word = two consecutive record elements of one tile; every quantity is O(1)).  The loss sums are
+          //      needed once per pixel: group 0 forms them, packed, and widens to fp32 once per tile. ----
           __half2 dh[2][REC / 2];
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const bool valid = half ? validB : validA;
             const uint32_t ex = half ? exB : exA;
-            float dd[REC];
+            if (half && !hasB) {
 #pragma unroll
-            for (int i = 0; i < REC; ++i) dd[i] = 0.f;
-            if (!(half && !hasB)) {
-              for (int kk = 0; kk < A.heads; ++kk) {
+              for (int i = 0; i < REC / 2; ++i) dh[half][i] = H2::zero();
+              continue;
+            }
+            __half2 os[REC / 2];
+            for (int kk = 0; kk < A.heads; ++kk) {
 #pragma unroll
-                for (int q = 0; q < REC / 8; ++q) {
-                  const uint4 v = lf_lds128(ex + (uint32_t)(kk * (REC / 8) + q) * 2048);
-                  const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+              for (int q = 0; q < REC / 8; ++q) {
+                const uint4 v = lf_lds128(ex + (uint32_t)(kk * (REC / 8) + q) * 2048);
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
-                    dd[8 * q + 2 * e] += f.x;
-                    dd[8 * q + 2 * e + 1] += f.y;
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 w = *reinterpret_cast<const __half2*>(&w4[e]);
+                  os[4 * q + e] = kk == 0 ? w : __hadd2(os[4 * q + e], w);
                 }
               }
-              float yv[REC];
-              unpack_rec<REC>(yraw[half], yv);
-              float lsum = 0.f, msum = 0.f;
-#pragma unroll
-              for (int i = 0; i < REC; ++i) {
-                const float o = dd[i] * inv_heads;
-                const float df = o - yv[i];
-                lsum += df * df - A.lambda * o;
-                msum += df * df;
-                dd[i] = valid ? 2.f * df - A.lambda : 0.f;
-              }
-              if (g == 0 && valid) { loss_acc += lsum; mse_acc += msum; }
             }
+            const __half2 c2 = __float2half2_rn(valid ? 2.f : 0.f), cl = __float2half2_rn(valid ? -A.lambda : 0.f);
+            __half2 ssq = H2::zero(), so = H2::zero();
 #pragma unroll
-            for (int i = 0; i < REC / 2; ++i) dh[half][i] = __floats2half2_rn(dd[2 * i], dd[2 * i + 1]);
+            for (int i = 0; i < REC / 2; ++i) {
+              const uint32_t yw = reinterpret_cast<const uint32_t*>(&yraw[half][0])[i];  // two bf16 targets
+              const __half2 y2 = __floats2half2_rn(__uint_as_float(yw << 16), __uint_as_float(yw & 0xffff0000u));
+              const __half2 o = __hmul2(os[i], gs2);
+              const __half2 df = __hsub2(o, y2);
+              dh[half][i] = __hfma2(df, c2, cl);
+              if (g == 0) {
+                ssq = __hfma2(df, df, ssq);
+                so = __hadd2(so, o);
+              }
+            }
+            if (g == 0 && valid) {
+              const float2 a = __half22float2(ssq), b = __half22float2(so);
+              loss_acc += (a.x + a.y) - A.lambda * (b.x + b.y);
+              mse_acc += a.x + a.y;
+            }
           }
           named_bar_sync(1, 128 * nact);  // all heads read: the planes may now take d(Wh)
           if (dbg_thread) LDBG(12);
