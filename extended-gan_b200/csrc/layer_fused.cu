@@ -388,12 +388,21 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           const uint32_t exA = smem_u32(s_stage) + (uint32_t)stA * A.stage_bytes + (uint32_t)m * 16;
           const uint32_t exB = smem_u32(s_stage) + (uint32_t)stB * A.stage_bytes + (uint32_t)m * 16;
           {
+            // ELU(z) = max(z, t - 1) with t = exp(min(z, 0)) = ELU'(z): t replaces z (only the derivative is needed later)
             __half2 o2[REC];
 #pragma unroll
             for (int v = 0; v < NODES; ++v)
 #pragma unroll
-              for (int u = 0; u < CO; ++u)
-                o2[rec_off<NODES, CO, SPATIAL>(v, u)] = A.apply_elu ? elu_fwd<H2>(z2[v][u]) : z2[v][u];
+              for (int u = 0; u < CO; ++u) {
+                if (A.apply_elu) {
+                  const __half2 t = H2::exp(H2::min(z2[v][u], H2::zero()));
+                  o2[rec_off<NODES, CO, SPATIAL>(v, u)] = H2::max(z2[v][u], H2::sub(t, H2::bc(1.f)));
+                  z2[v][u] = t;
+                } else {
+                  o2[rec_off<NODES, CO, SPATIAL>(v, u)] = z2[v][u];
+                  z2[v][u] = H2::bc(1.f);
+                }
+              }
 #pragma unroll
             for (int q = 0; q < REC / 8; ++q) {
               uint4 va, vb;
@@ -448,14 +457,16 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
                 }
               }
             }
-            const __half2 c2 = __float2half2_rn(valid ? 2.f : 0.f), cl = __float2half2_rn(valid ? -A.lambda : 0.f);
+            // dz = d(out)/heads: the mean's 1/heads is folded into the constants
+            const __half2 c2 = __float2half2_rn(valid ? 2.f * inv_heads : 0.f);
+            const __half2 cl = __float2half2_rn(valid ? -A.lambda * inv_heads : 0.f);
             __half2 ssq = H2::zero(), so = H2::zero();
 #pragma unroll
             for (int i = 0; i < REC / 2; ++i) {
               const uint32_t yw = reinterpret_cast<const uint32_t*>(&yraw[half][0])[i];  // two bf16 targets
               const __half2 y2 = __floats2half2_rn(__uint_as_float(yw << 16), __uint_as_float(yw & 0xffff0000u));
-              const __half2 o = __hmul2(os[i], gs2);
-              const __half2 df = __hsub2(o, y2);
+              const __half2 df = __hfma2(os[i], gs2, __hneg2(y2));  // out - y,  out = mean over heads
+              const __half2 o = __hadd2(df, y2);
               dh[half][i] = __hfma2(df, c2, cl);
               if (g == 0) {
                 ssq = __hfma2(df, df, ssq);
@@ -478,8 +489,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               const int o = rec_off<NODES, CO, SPATIAL>(v, u);
               // lane A = element o of tile A, lane B = element o of tile B
               const __half2 ab = (o & 1) ? __highs2half2(dh[0][o >> 1], dh[1][o >> 1]) : __lows2half2(dh[0][o >> 1], dh[1][o >> 1]);
-              const __half2 d = __hmul2(ab, gs2);
-              dz2[v][u] = A.apply_elu ? __hmul2(d, elu_grad<H2>(z2[v][u])) : d;
+              dz2[v][u] = __hmul2(ab, z2[v][u]);  // z2 holds ELU'(z); the 1/heads of the mean is folded into d
             }
           // a / adjacency gradient sums of this thread stay packed across its pairs (O(1) terms, <= 8 pairs per CTA:
           // fp16 accumulation error ~1e-3 of a per-thread partial; the 19K partials are then summed in fp32)
