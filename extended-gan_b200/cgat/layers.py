@@ -40,6 +40,11 @@ class _HeadParams(nn.Module):
             self.W = _xavier((ci, co))
         elif mapping_type == "conv":
             self.conv = nn.Conv2d(ci, co, 3, padding=1)  # parameter container only; the math runs in our kernels
+        elif mapping_type == "smaat_unet":
+            # the shared SmaAt-UNet(ci -> co) per node (cf. unet_model.py:20-26); imported here: that module imports us
+            from convolutional_gat.GAT3D.smaat_unet.SmaAt_UNet import SmaAt_UNet
+
+            self.unet = SmaAt_UNet(n_channels=ci, n_classes=co)
         else:
             raise ValueError(f"mapping_type {mapping_type!r} not supported here")
         self.a = _xavier((2 * co, 1))
@@ -155,8 +160,9 @@ class _GATStream(nn.Module):
                 f"channels={ch}")
         layout = _lib.LAYOUT_SPATIAL if spatial else _lib.LAYOUT_TEMPORAL
         merge = _lib.MERGE_MEAN if self.head_merge == "mean" else _lib.MERGE_CONCAT
-        conv = self.mapping_type == "conv"
-        fused = self.softmax_axis == "neighbour" and all(p.dtype == torch.float32 for p in self.parameters())
+        conv = self.mapping_type in ("conv", "smaat_unet")
+        fused = (self.softmax_axis == "neighbour" and self.mapping_type != "smaat_unet"
+                 and all(p.dtype == torch.float32 for p in self.parameters()))
         if fused and conv:
             fused = (x.dtype == torch.bfloat16 and self.conv_impl == IMPL_AUTO
                      and _conv_stream_served(N, H, W, nodes, self.ci, self.co, self.nheads, layout, merge, self.alpha))
@@ -176,6 +182,16 @@ class _GATStream(nn.Module):
                 Wt = torch.stack([h.W for h in self.attentions])
                 inp = x.reshape(N * H * W, T * V)
                 proj = _lib.PROJ_LINEAR
+            elif self.mapping_type == "smaat_unet":
+                # nodes folded into the batch: [N*nodes, ci, H, W] through the head's UNet (its convs run in K1-K3)
+                xn = (x.permute(0, 4, 3, 1, 2) if spatial else x.permute(0, 3, 4, 1, 2)).reshape(N * nodes, self.ci, H, W)
+                per_head = []
+                for h in self.attentions:
+                    yv = h.unet(xn).reshape(N, nodes, self.co, H, W)
+                    per_head.append(yv.permute(0, 3, 4, 2, 1) if spatial else yv.permute(0, 3, 4, 1, 2))
+                inp = torch.stack(per_head, dim=3).reshape(N * H * W, -1).contiguous()
+                Wt = None
+                proj = _lib.PROJ_PRE
             elif nodes > 8:
                 # many nodes (BASELINE config 4: V = 32 / 64): the block-diagonal dense conv would be 1/nodes dense, so
                 # the shared conv runs once over the nodes folded into the batch, [N*nodes, H, W, ci] -> [.., co]
@@ -210,7 +226,8 @@ class GATMultiHead3D(nn.Module):
     ``type_`` "spatial": nodes = V vertices, channels = T frames (``nfeat -> nhid``).
     "temporal": nodes = T frames, channels = V (``n_vertices -> n_vertices``).
     "multi_stream": mean of a spatial and a temporal stream.
-    ``mapping_type`` "linear" (``Wh = X.W``, baseline_model.py:127) or "conv" (shared 3x3 conv per node).
+    ``mapping_type`` "linear" (``Wh = X.W``, baseline_model.py:127), "conv" (shared 3x3 conv per node) or
+    "smaat_unet" (shared SmaAt-UNet(ci -> co) per node, the nodes folded into the batch; cf. unet_model.py:20-26).
     Extra keyword-only knobs (not in the reference call sites): ``softmax_axis`` ("neighbour" | "pixel"),
     ``head_merge`` ("mean" keeps the output shape equal to the input shape, which train.py:131 needs;
     "concat" follows baseline_model.py:196).  The legacy kwarg ``type=`` (model.py:26) is accepted.
@@ -226,8 +243,6 @@ class GATMultiHead3D(nn.Module):
             raise TypeError(f"unexpected kwargs {sorted(kwargs)}")
         if type_ not in ("spatial", "temporal", "multi_stream"):
             raise ValueError(f"type_ must be spatial|temporal|multi_stream, got {type_!r}")
-        if mapping_type == "smaat_unet":
-            raise NotImplementedError("mapping_type='smaat_unet' is served by convolutional_gat.unet_model.UnetModel")
         self.type_, self.mapping_type = type_, mapping_type
         self.image_height, self.image_width, self.n_vertices = image_height, image_width, n_vertices
         T, V = nfeat, n_vertices

@@ -153,6 +153,7 @@ def gat3d_head(
     W=None,
     conv_weight=None,
     conv_bias=None,
+    unet=None,
     alpha=0.2,
     softmax_axis="neighbour",
     mask=None,
@@ -164,6 +165,13 @@ def gat3d_head(
         Wh = feat @ W
     elif mapping_type == "conv":
         Wh = node_conv3x3(feat, conv_weight, conv_bias, H, Wd)
+    elif mapping_type == "smaat_unet":
+        # A.2: the shared SmaAt-UNet(ci -> co) applied to every node's [ci, H, W] map (cf. unet_model.py:25-26); the
+        # nodes are folded into the batch, so train-mode BatchNorm statistics are taken over samples AND nodes
+        nodes, ci = feat.shape[2], feat.shape[3]
+        img = feat.reshape(N, H, Wd, nodes, ci).permute(0, 3, 4, 1, 2).reshape(N * nodes, ci, H, Wd)
+        o = unet(img)
+        Wh = o.reshape(N, nodes, o.shape[1], H * Wd).permute(0, 3, 1, 2)
     else:
         raise ValueError(mapping_type)
     out = attention_core(Wh, a, adjacency_norm(B), alpha=alpha, softmax_axis=softmax_axis, mask=mask)
@@ -180,6 +188,8 @@ class SpecGATHead(nn.Module):
         if mapping_type == "linear":
             self.W = nn.Parameter(torch.empty(ci, co))
             nn.init.xavier_uniform_(self.W.data, gain=1.414)  # baseline_model.py:19-20
+        elif mapping_type == "smaat_unet":
+            self.unet = SpecSmaAtUNet(ci, co)
         else:
             self.conv = nn.Conv2d(ci, co, 3, padding=1)
         self.a = nn.Parameter(torch.empty(2 * co, 1))
@@ -200,9 +210,12 @@ class SpecGATStream(nn.Module):
         outs = []
         for k in range(self.nheads):
             hd = getattr(self, f"attention_{k}")
-            kw = dict(W=hd.W) if self.mapping_type == "linear" else dict(
-                conv_weight=hd.conv.weight, conv_bias=hd.conv.bias
-            )
+            if self.mapping_type == "linear":
+                kw = dict(W=hd.W)
+            elif self.mapping_type == "smaat_unet":
+                kw = dict(unet=hd.unet)
+            else:
+                kw = dict(conv_weight=hd.conv.weight, conv_bias=hd.conv.bias)
             outs.append(
                 gat3d_head(
                     x, type_=self.type_, mapping_type=self.mapping_type, a=hd.a, B=hd.B, alpha=hd.alpha,

@@ -265,3 +265,26 @@ def test_full_size_tile_invariance_and_closed_form():
             want = want + torch.nn.functional.elu(wh.mean(dim=3, keepdim=True).expand_as(wh))
         want = want / 3
     close(out, want, rtol=2e-2, atol=2e-2, msg="closed form at full size")
+
+
+def test_gat3d_smaat_unet_mapping_fp32():
+    """``mapping_type="smaat_unet"`` (the third value the reference's call sites pass, model.py:21-42): the shared
+    SmaAt-UNet per node feeds the attention kernels.  Eval mode (BatchNorm running statistics) against the oracle."""
+    ours, ref = _pair("spatial", "smaat_unet", 1, "mean", "neighbour", False, seed=51)
+    ours.eval()
+    ref.eval()
+    torch.manual_seed(4)
+    x = torch.rand(1, 16, 16, 4, 6)
+    xr = x.clone().requires_grad_()
+    out_r = ref(xr)
+    g = torch.rand_like(out_r) - 0.5
+    out_r.backward(g)
+    xo = x.to(DEV).requires_grad_()
+    out_o = ours(xo)
+    close(out_o, out_r.detach(), rtol=1e-3, atol=1e-4, msg="out")
+    out_o.backward(g.to(DEV))
+    close(xo.grad, xr.grad, rtol=1e-3, atol=1e-4 * max(1.0, xr.grad.abs().max().item()), msg="dx")
+    pr = dict(ref.named_parameters())
+    for k, p in ours.named_parameters():
+        r = pr[k].grad
+        close(p.grad, r, rtol=2e-3, atol=2e-4 * max(1.0, r.abs().max().item()), msg=f"d{k}")
