@@ -14,6 +14,9 @@ int conv_wgrad_tc_launch(const cgat_conv_desc*, const void*, const void*, float*
                          int* ncta_out = nullptr, int* nt_out = nullptr);
 int conv_tc_packed_launch(const cgat_conv_desc*, int dgrad, const void*, const void*, const float*, void*, cudaStream_t);
 void set_debug_buffer(long long* p);
+int conv_is_pointwise(const cgat_conv_desc* d);
+int conv_pointwise_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
+int conv_dbias_launch(const cgat_conv_desc*, const void* dy, float* dbias, cudaStream_t);
 }  // namespace cgat
 
 using namespace cgat;
@@ -44,6 +47,7 @@ extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const v
                                  int impl, void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!x || !w || !y) return fail(CGAT_EINVAL, "null x/w/y");
+  if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0) return conv_fprop_direct_launch(d, x, w, bias, y, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 0, workspace)) return rc;
   return conv_fprop_tc_launch(d, x, w, bias, y, workspace, (cudaStream_t)stream);
@@ -53,6 +57,7 @@ extern "C" int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const 
                                  void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!dy || !w || !dx) return fail(CGAT_EINVAL, "null dy/w/dx");
+  if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
   if (impl == 0) return conv_dgrad_direct_launch(d, dy, w, dx, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 1, workspace)) return rc;
   return conv_dgrad_tc_launch(d, dy, w, dx, workspace, (cudaStream_t)stream);
@@ -62,6 +67,10 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
                                  int impl, void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!x || !dy || !dw) return fail(CGAT_EINVAL, "null x/dy/dw");
+  if (impl == 0 && conv_is_pointwise(d)) {
+    if (int rc = conv_pointwise_launch(2, d, dy, x, dw, nullptr, (cudaStream_t)stream)) return rc;
+    return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
+  }
   if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 2, workspace)) return rc;
   return conv_wgrad_tc_launch(d, x, dy, dw, dbias, workspace, (cudaStream_t)stream);

@@ -129,6 +129,43 @@ __global__ void __launch_bounds__(CD_THREADS) conv_wgrad_direct(const cgat_conv_
     dw[(((long long)co * d.kh + kh) * d.kw + kw) * cing + ci] = s_acc[ci];
 }
 
+// Depthwise wgrad (groups == cin, e.g. the SmaAt-UNet 3x3 depthwise convs): thread = output channel (coalesced along the
+// NHWC channel axis), CTA = a slab of output pixels; kh*kw partial sums per thread in registers, one atomicAdd per
+// (channel, tap, CTA) into the zeroed dw.  (The general kernel above walks every pixel once per output channel.)
+constexpr int DW_MAX_TAPS = 49;
+template <typename T>
+__global__ void __launch_bounds__(CD_THREADS) conv_wgrad_depthwise(const cgat_conv_desc d, const T* __restrict__ x,
+                                                                   const T* __restrict__ dy, float* __restrict__ dw,
+                                                                   long long pix_per_cta) {
+  const int co = blockIdx.x * CD_THREADS + threadIdx.x;
+  if (co >= d.cout) return;
+  const int ci = co / (d.cout / d.groups);  // one input channel per group
+  const int taps = d.kh * d.kw;
+  float acc[DW_MAX_TAPS];
+#pragma unroll
+  for (int t = 0; t < DW_MAX_TAPS; ++t) acc[t] = 0.f;
+  const long long M = (long long)d.n * d.ho * d.wo;
+  const long long p0 = (long long)blockIdx.y * pix_per_cta;
+  const long long p1 = p0 + pix_per_cta < M ? p0 + pix_per_cta : M;
+  for (long long m = p0; m < p1; ++m) {
+    const int wo = (int)(m % d.wo);
+    const int ho = (int)((m / d.wo) % d.ho);
+    const int n = (int)(m / ((long long)d.wo * d.ho));
+    const float g = DT<T>::to_f(dy[m * d.cout + co]);
+#pragma unroll 1
+    for (int kh = 0; kh < d.kh; ++kh) {
+      const int hi = ho * d.stride + kh - d.pad_top;
+      if (hi < 0 || hi >= d.h) continue;
+      for (int kw = 0; kw < d.kw; ++kw) {
+        const int wi = wo * d.stride + kw - d.pad_left;
+        if (wi < 0 || wi >= d.w) continue;
+        acc[kh * d.kw + kw] = fmaf(g, DT<T>::to_f(x[(((long long)n * d.h + hi) * d.w + wi) * d.cin + ci]), acc[kh * d.kw + kw]);
+      }
+    }
+  }
+  for (int t = 0; t < taps; ++t) atomicAdd(&dw[(long long)co * taps + t], acc[t]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(CD_THREADS) conv_dbias_direct(const T* __restrict__ dy, float* __restrict__ db,
                                                                 long long M, int cout) {
@@ -145,6 +182,8 @@ __global__ void __launch_bounds__(CD_THREADS) conv_dbias_direct(const T* __restr
     db[co] = v;
   }
 }
+
+int conv_dbias_launch(const cgat_conv_desc* d, const void* dy, float* dbias, cudaStream_t st);
 
 static int grid_for(long long total) {
   long long g = (total + CD_THREADS - 1) / CD_THREADS;
@@ -194,6 +233,21 @@ int conv_wgrad_direct_launch(const cgat_conv_desc* d, const void* x, const void*
   const int blocks = d->cout * d->kh * d->kw;
   const size_t smem = sizeof(float) * (d->cin / d->groups);
   const long long M = (long long)d->n * d->ho * d->wo;
+  if (d->groups == d->cin && d->groups > 1 && d->kh * d->kw <= DW_MAX_TAPS) {  // depthwise
+    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->cout * d->kh * d->kw, st);
+    const int cblocks = (d->cout + CD_THREADS - 1) / CD_THREADS;
+    long long slabs = (148LL * 8 + cblocks - 1) / cblocks;
+    if (slabs > M) slabs = M;
+    const long long per = (M + slabs - 1) / slabs;
+    dim3 grid(cblocks, (unsigned)((M + per - 1) / per));
+    if (d->dtype == CGAT_F32)
+      conv_wgrad_depthwise<float><<<grid, CD_THREADS, 0, st>>>(*d, (const float*)x, (const float*)dy, dw, per);
+    else
+      conv_wgrad_depthwise<__nv_bfloat16><<<grid, CD_THREADS, 0, st>>>(*d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy,
+                                                                      dw, per);
+    if (int rc = check_launch("conv_wgrad_depthwise")) return rc;
+    return dbias ? conv_dbias_launch(d, dy, dbias, st) : 0;
+  }
   if (d->dtype == CGAT_F32) {
     conv_wgrad_direct<float><<<blocks, CD_THREADS, smem, st>>>(*d, (const float*)x, (const float*)dy, dw);
     if (dbias) conv_dbias_direct<float><<<d->cout, CD_THREADS, 0, st>>>((const float*)dy, dbias, M, d->cout);
@@ -204,6 +258,15 @@ int conv_wgrad_direct_launch(const cgat_conv_desc* d, const void* x, const void*
       conv_dbias_direct<__nv_bfloat16><<<d->cout, CD_THREADS, 0, st>>>((const __nv_bfloat16*)dy, dbias, M, d->cout);
   }
   return check_launch("conv_wgrad_direct");
+}
+
+int conv_dbias_launch(const cgat_conv_desc* d, const void* dy, float* dbias, cudaStream_t st) {
+  const long long M = (long long)d->n * d->ho * d->wo;
+  if (d->dtype == CGAT_F32)
+    conv_dbias_direct<float><<<d->cout, CD_THREADS, 0, st>>>((const float*)dy, dbias, M, d->cout);
+  else
+    conv_dbias_direct<__nv_bfloat16><<<d->cout, CD_THREADS, 0, st>>>((const __nv_bfloat16*)dy, dbias, M, d->cout);
+  return check_launch("conv_dbias_direct");
 }
 
 }  // namespace cgat
