@@ -5,9 +5,10 @@
 // (pixel p, node i) computes row i of the attention (logits, LeakyReLU, mask, soft-max over the neighbours j and the
 // aggregation h'_i = sum_j att_ij Wh_j, two passes over j with Wh and s2 of the pixel staged in shared memory),
 // then thread (p, v) mixes the rows with the normalised adjacency, z_v = sum_i h'_i adj[i][v], and applies ELU.
-// The [V][V] attention is never stored.  The backward recomputes the forward and reduces over the row index i
-// through shared-memory atomics on a per-thread STAGGERED column order j = (i + t) mod V, so that the threads of a
-// warp never hit the same address in the same step.  fp32 math; fp32 or bf16 tensors.
+// The [V][V] attention is never stored.  The backward recomputes the forward; the sums over the row index i that
+// d(Wh_j) and ds2_j need are formed by column j's own thread from per-row statistics (s1, max, 1/sum, soft-max dot)
+// published in shared memory -- one extra exp per (i, j) instead of V*C shared-memory atomics.  fp32 math; fp32 or
+// bf16 tensors.
 #include "attn_common.cuh"
 
 namespace cgat {
@@ -62,8 +63,8 @@ struct GenSmem {
   float* s2;     // [ppb][nodes]
   float* hp;     // [ppb][nodes*co]
   float* dz;     // [ppb][nodes*co]        (backward)
-  float* dWh;    // [ppb][nodes*co]        (backward)
-  float* ds2;    // [ppb][nodes]           (backward)
+  float* dhp;    // [ppb][nodes*co]        (backward: d h'_i)
+  float* st;     // [ppb][4][nodes]        (backward: s1, row max, 1/row sum, soft-max dot of every row)
 };
 
 __host__ __device__ inline size_t gen_carve(const GenGeom& g, bool bwd, unsigned char* base, GenSmem* s) {
@@ -85,13 +86,14 @@ __host__ __device__ inline size_t gen_carve(const GenGeom& g, bool bwd, unsigned
   float* s2 = take((size_t)g.ppb * g.nodes);
   float* hp = take((size_t)g.ppb * nc);
   float* dz = bwd ? take((size_t)g.ppb * nc) : nullptr;
-  float* dWh = bwd ? take((size_t)g.ppb * nc) : nullptr;
-  float* ds2 = bwd ? take((size_t)g.ppb * g.nodes) : nullptr;
-  if (s) *s = GenSmem{a, W, adj, gadj, ga, gW, mask, Wh, s2, hp, dz, dWh, ds2};
+  float* dhp = bwd ? take((size_t)g.ppb * nc) : nullptr;
+  float* st = bwd ? take((size_t)g.ppb * 4 * g.nodes) : nullptr;
+  if (s) *s = GenSmem{a, W, adj, gadj, ga, gW, mask, Wh, s2, hp, dz, dhp, st};
   return off;
 }
 
-template <typename T, bool BWD>
+// COT = channels per node at compile time (per-thread channel arrays stay in registers), 0 = run-time
+template <typename T, bool BWD, int COT>
 __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArgs A, const GenGeom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GenSmem S;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
   const int tid = threadIdx.x;
   const int lp = tid / g.np, i = tid % g.np;  // local pixel, node (row) of this thread
   const bool row = lp < g.ppb && i < g.nodes;
-  const int nodes = g.nodes, co = g.co, ci = g.ci, nc = nodes * co, nn = nodes * nodes;
+  const int nodes = g.nodes, co = COT ? COT : g.co, ci = (COT && !g.pre) ? COT : g.ci, nc = nodes * co, nn = nodes * nodes;
   const float alpha = A.alpha;
   const float inv_heads = 1.f / (float)g.heads;
   const T* in = reinterpret_cast<const T*>(A.in);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
 #pragma unroll
     for (int t = 0; t < GEN_MAX_C; ++t) { X[t] = 0.f; dX[t] = 0.f; oacc[t] = 0.f; }
     if (act && !g.pre)
-      for (int t = 0; t < ci; ++t) X[t] = gen_ld(in + pix * g.in_rec + gen_off(g.spatial, nodes, ci, i, t));
+      _Pragma("unroll") for (int t = 0; t < ci; ++t) X[t] = gen_ld(in + pix * g.in_rec + gen_off(g.spatial, nodes, ci, i, t));
 
     for (int k = 0; k < g.heads; ++k) {
       __syncthreads();  // previous head / group is done with the shared blocks
@@ -141,13 +143,13 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
       float wh[GEN_MAX_C];
       float s1 = 0.f, s2i = 0.f;
       if (act) {
-        for (int u = 0; u < co; ++u) {
+        _Pragma("unroll") for (int u = 0; u < co; ++u) {
           float v;
           if (g.pre) {
             v = gen_ld(in + pix * g.in_rec + (size_t)k * nc + gen_off(g.spatial, nodes, co, i, u));
           } else {
             v = 0.f;
-            for (int t = 0; t < ci; ++t) v = fmaf(X[t], S.W[t * co + u], v);
+            _Pragma("unroll") for (int t = 0; t < ci; ++t) v = fmaf(X[t], S.W[t * co + u], v);
           }
           wh[u] = v;
           Wh[i * co + u] = v;
@@ -177,10 +179,10 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
           if (!((mrow >> j) & 1ull)) e = kMaskFill;
           const float p = fast_exp(e - mx);
           sum += p;
-          for (int u = 0; u < co; ++u) hpi[u] = fmaf(p, Wh[j * co + u], hpi[u]);
+          _Pragma("unroll") for (int u = 0; u < co; ++u) hpi[u] = fmaf(p, Wh[j * co + u], hpi[u]);
         }
         rinv = 1.f / sum;
-        for (int u = 0; u < co; ++u) {
+        _Pragma("unroll") for (int u = 0; u < co; ++u) {
           hpi[u] *= rinv;
           hp[i * co + u] = hpi[u];
         }
@@ -193,13 +195,13 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
       if (act) {
         for (int ii = 0; ii < nodes; ++ii) {
           const float w = S.adj[ii * nodes + i];
-          for (int u = 0; u < co; ++u) z[u] = fmaf(hp[ii * co + u], w, z[u]);
+          _Pragma("unroll") for (int u = 0; u < co; ++u) z[u] = fmaf(hp[ii * co + u], w, z[u]);
         }
       }
       if constexpr (!BWD) {
         if (act) {
           T* out = reinterpret_cast<T*>(A.out) + pix * g.out_rec;
-          for (int u = 0; u < co; ++u) {
+          _Pragma("unroll") for (int u = 0; u < co; ++u) {
             const float o = A.apply_elu ? elu_fwd<F32>(z[u]) : z[u];
             if (g.concat) out[gen_out_off(g, k, i, u)] = DT<T>::from_f(o);
             else oacc[u] += o;
@@ -208,20 +210,18 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
       } else {
         // ---- 4. dz_v = dout * ELU'(z_v) ----
         float* dzs = S.dz + (size_t)lp * nc;
-        float* dWhs = S.dWh + (size_t)lp * nc;
-        float* ds2s = S.ds2 + (size_t)lp * nodes;
+        float* dhps = S.dhp + (size_t)lp * nc;
+        float* sts = S.st + (size_t)lp * 4 * nodes;
         if (act) {
           const T* dout = reinterpret_cast<const T*>(A.dout) + pix * g.out_rec;
           const float gs = g.concat ? 1.f : inv_heads;
-          for (int u = 0; u < co; ++u) {
+          _Pragma("unroll") for (int u = 0; u < co; ++u) {
             const float d = gen_ld(dout + gen_out_off(g, k, i, u)) * gs;
             dzs[i * co + u] = A.apply_elu ? d * elu_grad<F32>(z[u]) : d;
-            dWhs[i * co + u] = 0.f;
           }
-          ds2s[i] = 0.f;
         }
         __syncthreads();
-        // ---- 5. row i backward ----
+        // ---- 5a. row i: d h'_i, adjacency gradient, soft-max dot; publish the row statistics ----
         float ds1 = 0.f;
         if (act) {
           float dhp[GEN_MAX_C];
@@ -229,66 +229,98 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
           for (int u = 0; u < GEN_MAX_C; ++u) dhp[u] = 0.f;
           float* gadj = S.gadj + (size_t)k * nn + (size_t)i * nodes;
           for (int t = 0; t < nodes; ++t) {
-            int v = i + t;
+            int v = i + t;  // staggered: the pixels of a CTA that share the accumulator row hit different columns
             if (v >= nodes) v -= nodes;
             const float w = S.adj[i * nodes + v];
             float ga_iv = 0.f;
-            for (int u = 0; u < co; ++u) {
+            _Pragma("unroll") for (int u = 0; u < co; ++u) {
               const float d = dzs[v * co + u];
               dhp[u] = fmaf(d, w, dhp[u]);
               ga_iv = fmaf(hpi[u], d, ga_iv);
             }
-            atomicAdd(&gadj[v], ga_iv);  // other pixels of the CTA share the accumulator
+            atomicAdd(&gadj[v], ga_iv);
           }
-          // soft-max backward: dot_i = sum_j att_ij dAtt_ij
           float dot = 0.f;
           for (int j = 0; j < nodes; ++j) {
-            const float pre = s1 + s2[j];
-            float e = pre > 0.f ? pre : alpha * pre;
-            if (!((mrow >> j) & 1ull)) e = kMaskFill;
-            const float att = fast_exp(e - mx) * rinv;
-            float datt = 0.f;
-            for (int u = 0; u < co; ++u) datt = fmaf(dhp[u], Wh[j * co + u], datt);
-            dot = fmaf(att, datt, dot);
-          }
-          for (int t = 0; t < nodes; ++t) {
-            int j = i + t;  // staggered: the threads of a warp add to different columns in the same step
-            if (j >= nodes) j -= nodes;
             const float pre = s1 + s2[j];
             const bool on = (mrow >> j) & 1ull;
             float e = pre > 0.f ? pre : alpha * pre;
             if (!on) e = kMaskFill;
             const float att = fast_exp(e - mx) * rinv;
             float datt = 0.f;
-            for (int u = 0; u < co; ++u) datt = fmaf(dhp[u], Wh[j * co + u], datt);
-            const float de = att * (datt - dot);
-            const float dp = on ? de * (pre > 0.f ? 1.f : alpha) : 0.f;
-            ds1 += dp;
-            atomicAdd(&ds2s[j], dp);
-            for (int u = 0; u < co; ++u) atomicAdd(&dWhs[j * co + u], att * dhp[u]);
+            _Pragma("unroll") for (int u = 0; u < co; ++u) datt = fmaf(dhp[u], Wh[j * co + u], datt);
+            dot = fmaf(att, datt, dot);
           }
+          // second pass over the row for ds1 (its own sum); the column sums are formed by the column's thread in 5b
+          for (int j = 0; j < nodes; ++j) {
+            const float pre = s1 + s2[j];
+            const bool on = (mrow >> j) & 1ull;
+            float e = pre > 0.f ? pre : alpha * pre;
+            if (!on) e = kMaskFill;
+            const float att = fast_exp(e - mx) * rinv;
+            float datt = 0.f;
+            _Pragma("unroll") for (int u = 0; u < co; ++u) datt = fmaf(dhp[u], Wh[j * co + u], datt);
+            ds1 += on ? att * (datt - dot) * (pre > 0.f ? 1.f : alpha) : 0.f;
+          }
+          _Pragma("unroll") for (int u = 0; u < co; ++u) dhps[i * co + u] = dhp[u];
+          sts[i] = s1;
+          sts[nodes + i] = mx;
+          sts[2 * nodes + i] = rinv;
+          sts[3 * nodes + i] = dot;
         }
         __syncthreads();
+        // ---- 5b. column j = this thread's node: d(Wh_j) = sum_i att_ij d h'_i and ds2_j = sum_i dp_ij, with att_ij
+        //      recomputed from the published row statistics (no atomics) ----
+        float dwh[GEN_MAX_C];
+#pragma unroll
+        for (int u = 0; u < GEN_MAX_C; ++u) dwh[u] = 0.f;
+        float d2 = 0.f;
+        if (act) {
+          const float s2j = s2[i];
+          for (int r = 0; r < nodes; ++r) {
+            const float pre = sts[r] + s2j;
+            const bool on = (S.mask[r] >> i) & 1ull;
+            float e = pre > 0.f ? pre : alpha * pre;
+            if (!on) e = kMaskFill;
+            const float att = fast_exp(e - sts[nodes + r]) * sts[2 * nodes + r];
+            float datt = 0.f;
+            _Pragma("unroll") for (int u = 0; u < co; ++u) {
+              const float dh = dhps[r * co + u];
+              datt = fmaf(dh, wh[u], datt);
+              dwh[u] = fmaf(att, dh, dwh[u]);
+            }
+            d2 += on ? att * (datt - sts[3 * nodes + r]) * (pre > 0.f ? 1.f : alpha) : 0.f;
+          }
+        }
         // ---- 6. d(Wh_i), parameter-gradient partials ----
         float ga_part[2 * GEN_MAX_C];
 #pragma unroll
         for (int u = 0; u < 2 * GEN_MAX_C; ++u) ga_part[u] = 0.f;
+        float gw_part[GEN_MAX_C * GEN_MAX_C];  // linear projection: this thread's X^T d(Wh) terms, reduced per warp below
+#pragma unroll
+        for (int u = 0; u < GEN_MAX_C * GEN_MAX_C; ++u) gw_part[u] = 0.f;
         if (act) {
-          const float d2 = ds2s[i];
           T* din = reinterpret_cast<T*>(A.out) + pix * g.in_rec;
-          for (int u = 0; u < co; ++u) {
-            const float dw = dWhs[i * co + u] + ds1 * S.a[u] + d2 * S.a[co + u];
+          _Pragma("unroll") for (int u = 0; u < co; ++u) {
+            const float dw = dwh[u] + ds1 * S.a[u] + d2 * S.a[co + u];
             ga_part[u] = ds1 * wh[u];
             ga_part[co + u] = d2 * wh[u];
             if (g.pre) {
               din[(size_t)k * nc + gen_off(g.spatial, nodes, co, i, u)] = DT<T>::from_f(dw);
             } else {
-              for (int t = 0; t < ci; ++t) {
+              _Pragma("unroll") for (int t = 0; t < ci; ++t) {
                 dX[t] = fmaf(dw, S.W[t * co + u], dX[t]);
-                atomicAdd(&S.gW[(size_t)k * ci * co + t * co + u], X[t] * dw);
+                gw_part[t * GEN_MAX_C + u] = X[t] * dw;
               }
             }
           }
+        }
+        if (!g.pre) {
+          _Pragma("unroll") for (int t = 0; t < ci; ++t)
+            _Pragma("unroll") for (int u = 0; u < co; ++u) {
+              const float s = warp_sum(gw_part[t * GEN_MAX_C + u]);
+              if ((tid & 31) == 0) atomicAdd(&S.gW[(size_t)k * ci * co + t * co + u], s);
+            }
         }
         for (int u = 0; u < 2 * co; ++u) {
           const float s = warp_sum(ga_part[u]);
@@ -299,11 +331,11 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
     if constexpr (!BWD) {
       if (act && !g.concat) {
         T* out = reinterpret_cast<T*>(A.out) + pix * g.out_rec;
-        for (int u = 0; u < co; ++u) out[gen_out_off(g, 0, i, u)] = DT<T>::from_f(oacc[u] * inv_heads);
+        _Pragma("unroll") for (int u = 0; u < co; ++u) out[gen_out_off(g, 0, i, u)] = DT<T>::from_f(oacc[u] * inv_heads);
       }
     } else if (act && !g.pre) {
       T* din = reinterpret_cast<T*>(A.out) + pix * g.in_rec;
-      for (int t = 0; t < ci; ++t) din[gen_off(g.spatial, nodes, ci, i, t)] = DT<T>::from_f(dX[t]);
+      _Pragma("unroll") for (int t = 0; t < ci; ++t) din[gen_off(g.spatial, nodes, ci, i, t)] = DT<T>::from_f(dX[t]);
     }
   }
   if constexpr (BWD) {
@@ -331,16 +363,17 @@ static int gen_launch(AttnOp op, const cgat_attn_desc* d, const AttnArgs& A, con
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long grid = (long long)sms * 8;  // persistent grid-stride CTAs: the per-CTA gradient accumulators are flushed once
   if (grid > ngroups) grid = ngroups;
-  cudaError_t e;
-  if (bwd) {
-    e = cudaFuncSetAttribute(attn_generic_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto go = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attn_generic_kernel<T, true><<<(unsigned)grid, GEN_THREADS, smem, st>>>(A, g);
-  } else {
-    e = cudaFuncSetAttribute(attn_generic_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attn_generic_kernel<T, false><<<(unsigned)grid, GEN_THREADS, smem, st>>>(A, g);
-  }
+    kern<<<(unsigned)grid, GEN_THREADS, smem, st>>>(A, g);
+    return 0;
+  };
+  const bool c4 = g.co == 4 && (g.pre || g.ci == 4);  // the reference's T = T' = 4 frames per node
+  int rc;
+  if (bwd) rc = c4 ? go(attn_generic_kernel<T, true, 4>) : go(attn_generic_kernel<T, true, 0>);
+  else rc = c4 ? go(attn_generic_kernel<T, false, 4>) : go(attn_generic_kernel<T, false, 0>);
+  if (rc) return rc;
   return check_launch(bwd ? "attn_generic_kernel<bwd>" : "attn_generic_kernel<fwd>");
 }
 
