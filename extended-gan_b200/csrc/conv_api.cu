@@ -17,6 +17,8 @@ void set_debug_buffer(long long* p);
 int conv_is_pointwise(const cgat_conv_desc* d);
 int conv_pointwise_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 int conv_dbias_launch(const cgat_conv_desc*, const void* dy, float* dbias, cudaStream_t);
+int conv_gemm_served(const cgat_conv_desc* d);
+int conv_gemm_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 }  // namespace cgat
 
 using namespace cgat;
@@ -48,6 +50,7 @@ extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const v
   if (int rc = validate_conv(d)) return rc;
   if (!x || !w || !y) return fail(CGAT_EINVAL, "null x/w/y");
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
+  if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0) return conv_fprop_direct_launch(d, x, w, bias, y, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 0, workspace)) return rc;
   return conv_fprop_tc_launch(d, x, w, bias, y, workspace, (cudaStream_t)stream);
@@ -58,6 +61,7 @@ extern "C" int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const 
   if (int rc = validate_conv(d)) return rc;
   if (!dy || !w || !dx) return fail(CGAT_EINVAL, "null dy/w/dx");
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
+  if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
   if (impl == 0) return conv_dgrad_direct_launch(d, dy, w, dx, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 1, workspace)) return rc;
   return conv_dgrad_tc_launch(d, dy, w, dx, workspace, (cudaStream_t)stream);
@@ -69,6 +73,10 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
   if (!x || !dy || !dw) return fail(CGAT_EINVAL, "null x/dy/dw");
   if (impl == 0 && conv_is_pointwise(d)) {
     if (int rc = conv_pointwise_launch(2, d, dy, x, dw, nullptr, (cudaStream_t)stream)) return rc;
+    return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
+  }
+  if (impl == 0 && conv_gemm_served(d)) {
+    if (int rc = conv_gemm_launch(2, d, dy, x, dw, nullptr, (cudaStream_t)stream)) return rc;
     return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
   }
   if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
