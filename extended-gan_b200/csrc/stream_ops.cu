@@ -184,7 +184,6 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
   const int nwe = g.co * g.ci * g.taps;
   const int lane = threadIdx.x & 31;
   const long long gw = tid >> 5, nw = nt >> 5;
-  const int terms = g.nodes * A.ncta;
   for (long long i = gw; i < (long long)g.heads * (nwe + g.co); i += nw) {
     const int k = (int)(i / (nwe + g.co));
     const int r = (int)(i - (long long)k * (nwe + g.co));
@@ -200,9 +199,10 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
       dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
     }
     if (dst == nullptr) continue;
+    // per node: one (row, column) of the partial tile, summed over the CTAs by the lanes (independent loads, no
+    // per-term index arithmetic); fixed order -> deterministic
     float acc = 0.f;
-    for (int t = lane; t < terms; t += 32) {
-      const int node = t / A.ncta, cta = t - node * A.ncta;
+    for (int node = 0; node < g.nodes; ++node) {
       const int row = k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u);
       int col;
       if (A.d.wgrad_cols) {  // layer_fused.cu: [s][(r, cin chunk) | ones][8]; dbias is the ones column of s = 0
@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
         col = g.taps * g.cin;
         if (r < nwe) col = tap * g.cin + rec_of(g.spatial, g.nodes, g.ci, node, c);
       }
-      acc += A.wg_partial[((size_t)cta * 128 + row) * A.nt + col];
+      const float* src = A.wg_partial + (size_t)row * A.nt + col;
+      const size_t cta_stride = (size_t)128 * A.nt;
+      for (int cta = lane; cta < A.ncta; cta += 32) acc += src[(size_t)cta * cta_stride];
     }
     acc = warp_sum(acc);
     if (lane == 0) *dst = A.accumulate ? *dst + acc : acc;
