@@ -17,6 +17,11 @@ void set_debug_buffer(long long* p);
 int conv_is_pointwise(const cgat_conv_desc* d);
 int conv_pointwise_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 int conv_dbias_launch(const cgat_conv_desc*, const void* dy, float* dbias, cudaStream_t);
+int conv_big_supported(const cgat_conv_desc* d, int which);
+size_t conv_big_workspace(const cgat_conv_desc* d, int which);
+int conv_big_fprop_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int conv_big_dgrad_launch(const cgat_conv_desc*, const void*, const void*, void*, void*, cudaStream_t);
+int conv_big_wgrad_launch(const cgat_conv_desc*, const void*, const void*, float*, void*, cudaStream_t);
 int conv_gemm_served(const cgat_conv_desc* d);
 int conv_gemm_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 }  // namespace cgat
@@ -28,6 +33,10 @@ extern "C" void cgat_debug_timeline(long long* device_buffer) { set_debug_buffer
 
 static const char* kNames[3] = {"fprop", "dgrad", "wgrad"};
 
+// the streamed-operand kernels (conv_tc_big.cu) take every shape with >= 64 channels on the axes they tile;
+// the resident-weight kernels (conv_tc.cu) keep the small-channel convs
+static int use_big(const cgat_conv_desc* d, int which) { return conv_big_supported(d, which); }
+
 static int tc_ready(const cgat_conv_desc* d, int which, void* workspace) {
   if (!conv_tc_supported(d, which)) return fail(CGAT_EUNSUPPORTED, "tcgen05 %s does not support this conv shape", kNames[which]);
   if (conv_tc_workspace(d, which) > 0 && !workspace)
@@ -37,11 +46,12 @@ static int tc_ready(const cgat_conv_desc* d, int which, void* workspace) {
 
 extern "C" int cgat_conv_tc_supported(const cgat_conv_desc* d, int which) {
   if (validate_conv(d) || which < 0 || which > 2) return 0;
-  return conv_tc_supported(d, which);
+  return use_big(d, which) || conv_tc_supported(d, which);
 }
 
 extern "C" int64_t cgat_conv_workspace_bytes(const cgat_conv_desc* d, int which) {
   if (validate_conv(d) || which < 0 || which > 2) return 0;
+  if (use_big(d, which)) return (int64_t)conv_big_workspace(d, which);
   return (int64_t)conv_tc_workspace(d, which);
 }
 
@@ -52,6 +62,7 @@ extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const v
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0) return conv_fprop_direct_launch(d, x, w, bias, y, (cudaStream_t)stream);
+  if (use_big(d, 0)) return conv_big_fprop_launch(d, x, w, bias, y, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 0, workspace)) return rc;
   return conv_fprop_tc_launch(d, x, w, bias, y, workspace, (cudaStream_t)stream);
 }
@@ -63,6 +74,7 @@ extern "C" int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const 
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
   if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
   if (impl == 0) return conv_dgrad_direct_launch(d, dy, w, dx, (cudaStream_t)stream);
+  if (use_big(d, 1)) return conv_big_dgrad_launch(d, dy, w, dx, workspace, (cudaStream_t)stream);
   if (int rc = tc_ready(d, 1, workspace)) return rc;
   return conv_dgrad_tc_launch(d, dy, w, dx, workspace, (cudaStream_t)stream);
 }
@@ -80,6 +92,10 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
     return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
   }
   if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
+  if (use_big(d, 2)) {
+    if (int rc = conv_big_wgrad_launch(d, x, dy, dw, workspace, (cudaStream_t)stream)) return rc;
+    return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
+  }
   if (int rc = tc_ready(d, 2, workspace)) return rc;
   return conv_wgrad_tc_launch(d, x, dy, dw, dbias, workspace, (cudaStream_t)stream);
 }
