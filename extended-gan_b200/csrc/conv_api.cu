@@ -22,6 +22,9 @@ size_t conv_big_workspace(const cgat_conv_desc* d, int which);
 int conv_big_fprop_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int conv_big_dgrad_launch(const cgat_conv_desc*, const void*, const void*, void*, void*, cudaStream_t);
 int conv_big_wgrad_launch(const cgat_conv_desc*, const void*, const void*, float*, void*, cudaStream_t);
+int conv_big_wgrad_small_ok(const cgat_conv_desc* d);
+int conv_is_fullwindow(const cgat_conv_desc* d);
+int conv_fullwindow_fprop_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int conv_gemm_served(const cgat_conv_desc* d);
 int conv_gemm_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 }  // namespace cgat
@@ -35,7 +38,11 @@ static const char* kNames[3] = {"fprop", "dgrad", "wgrad"};
 
 // the streamed-operand kernels (conv_tc_big.cu) take every shape with >= 64 channels on the axes they tile;
 // the resident-weight kernels (conv_tc.cu) keep the small-channel convs
-static int use_big(const cgat_conv_desc* d, int which) { return conv_big_supported(d, which); }
+// (wgrad also falls to them for small-channel shapes the resident kernel does not serve)
+static int use_big(const cgat_conv_desc* d, int which) {
+  if (conv_big_supported(d, which)) return 1;
+  return which == 2 && !conv_tc_supported(d, 2) && conv_big_wgrad_small_ok(d);
+}
 
 static int tc_ready(const cgat_conv_desc* d, int which, void* workspace) {
   if (!conv_tc_supported(d, which)) return fail(CGAT_EUNSUPPORTED, "tcgen05 %s does not support this conv shape", kNames[which]);
@@ -59,6 +66,7 @@ extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const v
                                  int impl, void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!x || !w || !y) return fail(CGAT_EINVAL, "null x/w/y");
+  if (impl == 0 && conv_is_fullwindow(d)) return conv_fullwindow_fprop_launch(d, x, w, bias, y, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0) return conv_fprop_direct_launch(d, x, w, bias, y, (cudaStream_t)stream);

@@ -205,6 +205,50 @@ int validate_conv(const cgat_conv_desc* d) {
   return 0;
 }
 
+// ---- full-window conv: the kernel covers the whole (unpadded) input, one output pixel per image ---------------
+// The last conv of both DCGAN discriminators (dcgan/model.py:166-169: 512 -> 1, k=4 on the 4x4 map) is a plain dot
+// product of length h*w*cin per (image, cout): x[n] and w[co] are contiguous in the same (h, w, c) order.  One block
+// per (image, cout) with a warp-shuffle + shared-memory tree; the tiled GEMM would run it in a single CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) conv_fullwindow_fprop(const cgat_conv_desc d, const T* __restrict__ x,
+                                                            const T* __restrict__ w, const float* __restrict__ bias,
+                                                            T* __restrict__ y) {
+  const int co = blockIdx.x % d.cout, n = blockIdx.x / d.cout;
+  const long long len = (long long)d.h * d.w * d.cin;
+  const T* xr = x + (long long)n * len;
+  const T* wr = w + (long long)co * len;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) acc = fmaf(DT<T>::to_f(xr[i]), DT<T>::to_f(wr[i]), acc);
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = bias ? bias[co] : 0.f;
+    for (int i = 0; i < 8; ++i) v += part[i];
+    if (d.act == 1) v = fmaxf(v, 0.f);
+    else if (d.act == 2) v = v > 0.f ? v : 0.2f * v;
+    else if (d.act == 3) v = 1.f / (1.f + __expf(-v));
+    y[(long long)n * d.cout + co] = DT<T>::from_f(v);
+  }
+}
+
+int conv_is_fullwindow(const cgat_conv_desc* d) {
+  return d->groups == 1 && d->ho == 1 && d->wo == 1 && d->pad_top == 0 && d->pad_left == 0 && d->kh == d->h &&
+         d->kw == d->w && d->cout <= 16;
+}
+
+int conv_fullwindow_fprop_launch(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
+                                 cudaStream_t st) {
+  const int blocks = d->n * d->cout;
+  if (d->dtype == CGAT_F32)
+    conv_fullwindow_fprop<float><<<blocks, 256, 0, st>>>(*d, (const float*)x, (const float*)w, bias, (float*)y);
+  else
+    conv_fullwindow_fprop<__nv_bfloat16><<<blocks, 256, 0, st>>>(*d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                                                bias, (__nv_bfloat16*)y);
+  return check_launch("conv_fullwindow_fprop");
+}
+
 int conv_fprop_direct_launch(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                              cudaStream_t st) {
   const long long total = (long long)d->n * d->ho * d->wo * d->cout;

@@ -241,9 +241,12 @@ conv_big_wgrad_kernel(const __grid_constant__ CUtensorMap ymap, const __grid_con
           const int iw = kb % A.tiles_w, ih = (kb / A.tiles_w) % A.tiles_h, in = kb / (A.tiles_w * A.tiles_h);
           const uint32_t st = it % BIG_STAGES, ph = (it / BIG_STAGES) & 1u;
           mbar_wait(&S->empty[st], ph ^ 1u);
-          mbar_arrive_expect_tx(&S->full[st], stage_bytes);
+          // rows 64..127 of the accumulator are never stored when the cout tile ends before them: their dY box is
+          // not fetched (rows of D are independent, whatever that part of shared memory holds)
+          const int na = A.gk - mt * 128 > 64 ? 2 : 1;
+          mbar_arrive_expect_tx(&S->full[st], (uint32_t)(na + nb) * box_bytes);
           uint8_t* sa = smem + st * stage_bytes;
-          for (int b = 0; b < 2; ++b)
+          for (int b = 0; b < na; ++b)
             tma_load_4d(sa + b * box_bytes, &ymap, mt * 128 + b * 64, iw * A.tw, ih * A.th, in * A.tn, &S->full[st]);
           for (int b = 0; b < nb; ++b)
             tma_load_4d(sa + a_bytes + b * box_bytes, &xmap, nt * A.bn + b * 64, iw * A.tw - A.pad_l + s,
@@ -369,6 +372,19 @@ static int big_sm_count() {
   return num_sms;
 }
 
+// both kernels opt in once (per device) to the largest dynamic shared-memory size any of their shapes uses
+constexpr size_t BIG_MAX_SMEM = (size_t)BIG_STAGES * (128 * 128 + 256 * 128) + sizeof(BigSmem) + 1024;
+static int big_set_smem(const void* kernel, int slot) {
+  static int done[2][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && done[slot][dev]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_MAX_SMEM);
+  if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  if (dev < 64) done[slot][dev] = 1;
+  return 0;
+}
+
 static int pow2_floor(int v) {
   int p = 1;
   while (p * 2 <= v) p *= 2;
@@ -443,8 +459,16 @@ static int wgrad_splits(const cgat_conv_desc* d, int* bn_out) {
   return splits;
 }
 
+// wgrad shapes below the 64-channel bar that the kernel still serves correctly (zero-filled channel blocks): used
+// where the resident-weight wgrad of conv_tc.cu does not take the shape (the DCGAN generator's k=4 convs)
+int conv_big_wgrad_small_ok(const cgat_conv_desc* d) {
+  if (d->dtype != CGAT_BF16 || d->stride != 1 || d->groups != 1) return 0;
+  if (d->cin % 8 || d->cout % 8 || d->kh > 16 || d->kw > 16) return 0;
+  return d->cin >= 16 && d->cout >= 8;
+}
+
 size_t conv_big_workspace(const cgat_conv_desc* d, int which) {
-  if (!conv_big_supported(d, which)) return 0;
+  if (!conv_big_supported(d, which) && !(which == 2 && conv_big_wgrad_small_ok(d))) return 0;
   if (which == 0) return 0;
   if (which == 1) return (size_t)d->kh * d->kw * d->cin * d->cout * 2;
   const int splits = wgrad_splits(d, nullptr);
@@ -480,8 +504,7 @@ static int launch_big_fprop(const void* in, int n, int hi, int wi, int gk, const
     if (int rc = make_map(&bmap, w, 3, dims, strides, box)) return rc;
   }
   const size_t smem = (size_t)BIG_STAGES * (128 * 128 + A.bn * 128) + sizeof(BigSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(conv_big_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  if (int rc = big_set_smem((const void*)conv_big_fprop_kernel, 0)) return rc;
   const int total = A.m_tiles * A.n_tiles;
   const int grid = total < big_sm_count() ? total : big_sm_count();
   conv_big_fprop_kernel<<<grid, BIG_THREADS, smem, st>>>(amap, bmap, A);
@@ -529,8 +552,7 @@ int conv_big_wgrad_launch(const cgat_conv_desc* d, const void* x, const void* dy
   if (int rc = make_nhwc_map(&ymap, dy, d->n, d->ho, d->wo, d->cout, g.tw, g.th, g.tn)) return rc;
   if (int rc = make_nhwc_map(&xmap, x, d->n, d->h, d->w, d->cin, g.tw, g.th, g.tn)) return rc;
   const size_t smem = (size_t)BIG_STAGES * (2 + bn / 64) * 64 * 128 + sizeof(BigSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(conv_big_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  if (int rc = big_set_smem((const void*)conv_big_wgrad_kernel, 1)) return rc;
   const int total = d->kh * d->kw * A.m_tiles * A.n_tiles * splits;
   const int grid = total < big_sm_count() ? total : big_sm_count();
   conv_big_wgrad_kernel<<<grid, BIG_THREADS, smem, st>>>(ymap, xmap, A);

@@ -22,6 +22,8 @@ BIG_CASES = [
     (2, 16, 16, 64, 384, 1, (0, 0, 0, 0)),      # second cout tile half empty
     (2, 16, 16, 64, 64, 4, (1, 1, 2, 2)),       # k=4 padding="same" (dcgan/model.py:61-72)
     (1, 3, 3, 64, 64, 3, (1, 1, 1, 1)),         # image smaller than any tile
+    (2, 16, 16, 32, 16, 4, (1, 1, 2, 2)),       # DCGAN generator layers (dcgan/model.py:61-72): fprop/dgrad on the
+    (2, 16, 16, 16, 8, 4, (1, 1, 2, 2)),        #   resident-weight kernels, wgrad on the streamed one (one dY box)
 ]
 
 
@@ -99,3 +101,27 @@ def test_dcgan_discriminator_conv_routes_to_tensor_cores():
     close(yo, yr.detach(), rtol=2e-2, atol=1e-2 * max(1.0, yr.abs().max().item()), msg="y")
     close(xo.grad, xr.grad, rtol=2e-2, atol=1e-2 * max(1.0, xr.grad.abs().max().item()), msg="dx")
     close(conv.weight.grad, wr.grad, rtol=2e-2, atol=1e-2 * max(1.0, wr.grad.abs().max().item()), msg="dw")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("stride", [1, 4])
+def test_fullwindow_conv(dtype, stride):
+    """Last conv of the DCGAN discriminators (dcgan/model.py:166-169, 512 -> 1, k=4 over the 4x4 map; the temporal one
+    with stride 4): one dot product per image through the full-window kernel."""
+    from cgat.conv_layers import Conv2d
+
+    torch.manual_seed(9)
+    conv = Conv2d(512, 1, 4, stride, 0, bias=False).to(DEV)
+    x = (torch.rand(6, 512, 4, 4) - 0.5).to(dtype)
+    wr = conv.weight.detach().cpu().to(dtype).float().requires_grad_()
+    xr = x.float().clone().requires_grad_()
+    yr = F.conv2d(xr, wr, None, stride, 0)
+    yr.backward(torch.ones_like(yr))
+    xo = x.clone().to(DEV).requires_grad_()
+    yo = conv(xo)
+    assert yo.shape == yr.shape
+    yo.backward(torch.ones_like(yo))
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    close(yo, yr.detach(), rtol=tol, atol=tol, msg="y")
+    close(xo.grad, xr.grad, rtol=tol, atol=tol, msg="dx")
+    close(conv.weight.grad, wr.grad, rtol=tol, atol=tol, msg="dw")

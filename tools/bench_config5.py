@@ -35,5 +35,22 @@ for dtype in (torch.float32, torch.bfloat16):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 3
     _lib.profile_start(); step(); torch.cuda.synchronize(); prof = _lib.profile_stop()
+    # the same step replayed from a CUDA graph (host out of the loop)
+    from dcgan.train import GraphedAdversarialStep
+    torch.manual_seed(369)
+    nets = [Generator(params).to(dev), FrameDiscriminator(params).to(dev), TemporalDiscriminator(params).to(dev)]
+    oG, oFD, oTD = make_optimizers(*nets, capturable=True)
+    gstep = GraphedAdversarialStep(netG=nets[0], netFD=nets[1], netTD=nets[2], optimizerG=oG, optimizerFD=oFD,
+                                   optimizerTD=oTD, criterion=crit, x=x, y=y)
+    for _ in range(2):
+        gstep(x, y)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(10):
+        out = gstep(x, y)
+    b.record()
+    torch.cuda.synchronize()
+    gms = a.elapsed_time(b) / 10
+    print(f"  graph replay: {gms:.2f} ms/step ({N / gms * 1e3:.0f} samples/s), errG {out[2].item():.4f}")
     print(f"DCGAN step N={N} {dtype}: {ms:.1f} ms/step ({N / ms * 1e3:.0f} samples/s); conv kernels (ms):",
           {k: round(c * t, 1) for k, (c, t) in prof.items()})

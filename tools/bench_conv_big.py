@@ -13,6 +13,7 @@ from cgat.functional import _conv_desc, ptr, stream
 dev = "cuda"
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = 20
+only = sys.argv[2] if len(sys.argv) > 2 else ""  # substring filter on the shape name
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
 peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1369.9
 SHAPES = [
@@ -26,6 +27,8 @@ SHAPES = [
 ]
 lib = _lib.lib()
 for name, n, h, w, cin, cout, k, pad in SHAPES:
+    if only not in name:
+        continue
     ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
     d = _conv_desc(n, h, w, cin, cout, k, k, 1, pad, pad, ho, wo, _lib.BF16, 0)
     x = (torch.rand(n, h, w, cin, device=dev) - 0.5).bfloat16()
@@ -45,10 +48,21 @@ for name, n, h, w, cin, cout, k, pad in SHAPES:
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        # the launches are replayed from a CUDA graph: the host side of a call (two cuTensorMapEncodeTiled + ctypes)
+        # costs ~10 us, more than the small shapes run for
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(reps):
+                    fn()
+        torch.cuda.current_stream().wait_stream(side)
+        graph.replay()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(reps):
-            fn()
+        graph.replay()
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / reps
