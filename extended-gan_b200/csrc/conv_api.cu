@@ -25,6 +25,8 @@ int conv_big_wgrad_launch(const cgat_conv_desc*, const void*, const void*, float
 int conv_big_wgrad_small_ok(const cgat_conv_desc* d);
 int conv_is_fullwindow(const cgat_conv_desc* d);
 int conv_fullwindow_fprop_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
+int conv_dw3x3_served(const cgat_conv_desc* d);
+int conv_dw3x3_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, float*, const float*, cudaStream_t);
 int conv_gemm_served(const cgat_conv_desc* d);
 int conv_gemm_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 }  // namespace cgat
@@ -66,6 +68,7 @@ extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const v
                                  int impl, void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!x || !w || !y) return fail(CGAT_EINVAL, "null x/w/y");
+  if (impl == 0 && conv_dw3x3_served(d)) return conv_dw3x3_launch(0, d, x, w, y, nullptr, bias, (cudaStream_t)stream);
   if (impl == 0 && conv_is_fullwindow(d)) return conv_fullwindow_fprop_launch(d, x, w, bias, y, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
@@ -79,6 +82,7 @@ extern "C" int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const 
                                  void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!dy || !w || !dx) return fail(CGAT_EINVAL, "null dy/w/dx");
+  if (impl == 0 && conv_dw3x3_served(d)) return conv_dw3x3_launch(1, d, dy, w, dx, nullptr, nullptr, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
   if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
   if (impl == 0) return conv_dgrad_direct_launch(d, dy, w, dx, (cudaStream_t)stream);
@@ -91,6 +95,7 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
                                  int impl, void* workspace, void* stream) {
   if (int rc = validate_conv(d)) return rc;
   if (!x || !dy || !dw) return fail(CGAT_EINVAL, "null x/dy/dw");
+  if (impl == 0 && conv_dw3x3_served(d)) return conv_dw3x3_launch(2, d, x, dy, dw, dbias, nullptr, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) {
     if (int rc = conv_pointwise_launch(2, d, dy, x, dw, nullptr, (cudaStream_t)stream)) return rc;
     return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;

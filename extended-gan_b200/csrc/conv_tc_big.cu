@@ -17,6 +17,7 @@
 //
 // 4-stage mbarrier pipeline, one TMA warp, one MMA-issuing thread, four epilogue warps; two TMEM accumulators
 // so the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, one per SM.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace cgat {
@@ -451,7 +452,8 @@ static int wgrad_splits(const cgat_conv_desc* d, int* bn_out) {
   const BigGeom g = pixel_tiles(d->n, d->ho, d->wo, 64);
   const int kblocks = g.tiles_w * g.tiles_h * g.tiles_n;
   const int ot = d->kh * d->kw * ((d->cout + 127) / 128) * ((d->cin + bn - 1) / bn);
-  int splits = (2 * big_sm_count()) / ot;  // up to two waves of work items
+  static const int waves = getenv("CGAT_BIG_WAVES") ? atoi(getenv("CGAT_BIG_WAVES")) : 1;  // developer knob
+  int splits = (waves * big_sm_count()) / ot;  // one wave of work items (measured: two waves cost 7-35 % more)
   if (splits > kblocks / 2) splits = kblocks / 2;  // at least two pixel blocks per item
   if (splits < 1) splits = 1;
   if (splits > 64) splits = 64;
@@ -485,9 +487,13 @@ static int launch_big_fprop(const void* in, int n, int hi, int wi, int gk, const
   A.n = n; A.ho = hout; A.wo = wout; A.gk = gk; A.gn = gn;
   A.kh = kh; A.kw = kw; A.pad_t = pad_t; A.pad_l = pad_l;
   A.tw = g.tw; A.th = g.th; A.tn = g.tn; A.tiles_w = g.tiles_w; A.tiles_h = g.tiles_h; A.tiles_n = g.tiles_n;
-  A.bn = round_up(gn, 16) < 256 ? round_up(gn, 16) : 256;
-  A.n_tiles = (gn + A.bn - 1) / A.bn;
+  static const int bn_cap = getenv("CGAT_BIG_BN") ? atoi(getenv("CGAT_BIG_BN")) : 256;  // developer knob
+  A.bn = round_up(gn, 16) < bn_cap ? round_up(gn, 16) : bn_cap;
   A.m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  // small problems: narrower cout tiles until at least half of the SMs have a tile (measured on the DCGAN
+  // discriminator convs at N = 64: conv3 21.6 -> 15.4 us, conv4 30 -> 23.7 us)
+  while (A.bn > 64 && A.bn % 32 == 0 && A.m_tiles * ((gn + A.bn - 1) / A.bn) < big_sm_count() / 2) A.bn /= 2;
+  A.n_tiles = (gn + A.bn - 1) / A.bn;
   A.kchunks = (gk + BIG_KC - 1) / BIG_KC;
   A.splits = 1;
   A.act = act;

@@ -37,13 +37,12 @@ for V in (32, 64):
     _lib.profile_start(); step(); torch.cuda.synchronize(); prof = _lib.profile_stop()
     print(f"GAT layer V={V} linear, x[4,128,128,4,{V}] bf16: fwd+bwd {ms:.3f} ms ->", {k: round(v[1], 3) for k, v in prof.items()})
 
-for V, N in ((8, 2),):
-    m = UnetModel(image_width=128, image_height=128, n_vertices=V, attention_type="unet").to(dev)
-    x = torch.rand(N, 128, 128, 4, V, device=dev).bfloat16().requires_grad_()
-    m = m.bfloat16() if False else m
+for V, N, dt in ((8, 2, torch.float32), (8, 2, torch.bfloat16), (8, 16, torch.bfloat16)):
+    m = UnetModel(image_width=128, image_height=128, n_vertices=V, attention_type="unet").to(dev).to(dt)
+    x = torch.rand(N, 128, 128, 4, V, device=dev).to(dt).requires_grad_()
 
     def step():
-        out = m(x.float())
+        out = m(x)
         out.backward(torch.ones_like(out))
 
     ms = timeit(step, 2)
@@ -51,4 +50,4 @@ for V, N in ((8, 2),):
     tot = {}
     for k, (c, t) in prof.items():
         tot[k] = round(c * t, 2)
-    print(f"UnetModel V={V}, x[{N},128,128,4,{V}] fp32: fwd+bwd {ms:.1f} ms; our kernels (ms total):", tot)
+    print(f"UnetModel V={V}, x[{N},128,128,4,{V}] {dt}: fwd+bwd {ms:.1f} ms; our kernels (ms total):", tot)
