@@ -113,8 +113,11 @@ typedef struct cgat_conv_desc {
   int32_t groups;         /* 1 = dense; cin = cout-groups for depthwise (SmaAt-UNet). weight [cout][kh][kw][cin/groups] */
 } cgat_conv_desc;
 
-/* K1 fprop / K2 dgrad / K3 wgrad.  `impl`: 0 = direct CUDA-core kernel (any shape, no workspace),
- * 1 = tcgen05 implicit GEMM (bf16; cgat_conv_tc_supported tells whether the shape is served).
+/* K1 fprop / K2 dgrad / K3 wgrad.  `impl`: 0 = CUDA-core kernels (any shape, no workspace: vectorised depthwise 3x3,
+ * full-window dot, pointwise / implicit-GEMM tiles, generic direct),
+ * 1 = tcgen05 implicit GEMM (bf16, stride 1; cgat_conv_tc_supported tells whether the shape is served): operands
+ *     streamed by TMA for >= 64 channels (csrc/conv_tc_big.cu), weights resident in shared memory below that
+ *     (csrc/conv_tc.cu).
  * `workspace`: device scratch of at least cgat_conv_workspace_bytes(d, which) bytes (packed weights /
  * partial sums), 16-byte aligned, owned by the caller; may be NULL when that size is 0.
  * wgrad WRITES dw [cout][kh][kw][cin] fp32 and, if dbias != NULL, dbias [cout] fp32.                */
