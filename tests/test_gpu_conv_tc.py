@@ -47,6 +47,8 @@ def test_conv_tc_fprop_dgrad(case):
     bo = b.to(DEV).requires_grad_()
     wgrad_cols = k * k * ((cin // 8 + 1) // 2 * 16) + 16  # TMEM columns the wgrad accumulators need
     tc_bwd = cout % 8 == 0 and cout <= 128 and wgrad_cols <= 512
+    # shapes the resident-weight wgrad does not take fall to the streamed one (conv_tc_big.cu) from 16 x 8 channels up
+    tc_bwd = tc_bwd or (cin % 8 == 0 and cout % 8 == 0 and cin >= 16 and cout >= 8)
     # IMPL_AUTO falls back to the direct wgrad kernel where the tcgen05 one does not serve the shape
     yo = conv2d_nhwc(xo, wo, bo, stride=1, pad=pad, impl=IMPL_TC if tc_bwd else IMPL_AUTO)
     scale = max(1.0, yr.abs().max().item())
