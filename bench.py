@@ -204,7 +204,7 @@ def run_reference(args):
                                    "the reference's own GAT3D layer is absent from its tree)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, per_gpu_batch):
@@ -230,7 +230,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL prints its version banner on stdout at any debug level >= VERSION; main() has pointed fd 1 at stderr, so
+        # whatever native libraries print, rank 0's stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from cgat import _lib
@@ -431,12 +433,28 @@ def run_ours(args):
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "4 samples/step x 3 steps of the same model (fp32 torch CPU, oracle/spec.py)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # keep the real stdout for the JSON line only: everything else (NCCL's version banner, warnings of native libraries,
+    # stray prints) goes to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -179,12 +179,16 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
     }
     return;
   }
-  // conv.weight grad [k][u][c][tap] = sum over nodes and CTAs of the dense partials (the block-diagonal's delta);
-  // one WARP per output, lanes stride over the (node, CTA) pairs, fixed order -> deterministic
+  // conv.weight grad [k][u][c][tap] = sum over nodes and CTAs of the dense partials (the block-diagonal's delta).
+  // One BLOCK per output: warp w takes the CTAs w, w+8, ... -- with 148 partial tiles that is at most one load per
+  // lane and node, all issued before anything is added, so a block pays the L2 latency once (a warp per output walked
+  // it once per node and 32-CTA batch: 10.6 us under ncu) -- then the 8 warp sums are added in a fixed order:
+  // deterministic, identical on every rank.
+  __shared__ float wsum[ADJ_THREADS / 32];
   const int nwe = g.co * g.ci * g.taps;
-  const int lane = threadIdx.x & 31;
-  const long long gw = tid >> 5, nw = nt >> 5;
-  for (long long i = gw; i < (long long)g.heads * (nwe + g.co); i += nw) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = ADJ_THREADS / 32;
+  for (long long i = b; i < (long long)g.heads * (nwe + g.co); i += nb) {
     const int k = (int)(i / (nwe + g.co));
     const int r = (int)(i - (long long)k * (nwe + g.co));
     int u, c = 0, tap = 0;
@@ -198,30 +202,44 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
       u = r - nwe;
       dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
     }
-    if (dst == nullptr) continue;
-    // per node: one (row, column) of the partial tile, summed over the CTAs by the lanes (independent loads, no
-    // per-term index arithmetic); fixed order -> deterministic
+    if (dst == nullptr) continue;  // block-uniform
     float acc = 0.f;
-    for (int node = 0; node < g.nodes; ++node) {
-      const int row = k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u);
-      int col;
-      if (A.d.wgrad_cols) {  // layer_fused.cu: [s][(r, cin chunk) | ones][8]; dbias is the ones column of s = 0
-        const int nq = 3 * g.nchunk + 1;
-        col = (nq - 1) * 8;
-        if (r < nwe) {
-          const int ci_idx = rec_of(g.spatial, g.nodes, g.ci, node, c);
-          col = ((tap % 3) * nq + (tap / 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
+    const size_t cta_stride = (size_t)128 * A.nt;
+    for (int node0 = 0; node0 < g.nodes; node0 += 4) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = 0.f;
+        const int node = node0 + j;
+        if (node >= g.nodes) continue;
+        const int row = k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u);
+        int col;
+        if (A.d.wgrad_cols) {  // layer_fused.cu: [s][(r, cin chunk) | ones][8]; dbias is the ones column of s = 0
+          const int nq = 3 * g.nchunk + 1;
+          col = (nq - 1) * 8;
+          if (r < nwe) {
+            const int ci_idx = rec_of(g.spatial, g.nodes, g.ci, node, c);
+            col = ((tap % 3) * nq + (tap / 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
+          }
+        } else {
+          col = g.taps * g.cin;
+          if (r < nwe) col = tap * g.cin + rec_of(g.spatial, g.nodes, g.ci, node, c);
         }
-      } else {
-        col = g.taps * g.cin;
-        if (r < nwe) col = tap * g.cin + rec_of(g.spatial, g.nodes, g.ci, node, c);
+        const float* src = A.wg_partial + (size_t)row * A.nt + col;
+        for (int cta = warp + NW * lane; cta < A.ncta; cta += NW * 32) v[j] += __ldcg(src + (size_t)cta * cta_stride);
       }
-      const float* src = A.wg_partial + (size_t)row * A.nt + col;
-      const size_t cta_stride = (size_t)128 * A.nt;
-      for (int cta = lane; cta < A.ncta; cta += 32) acc += src[(size_t)cta * cta_stride];
+      acc += (v[0] + v[1]) + (v[2] + v[3]);
     }
     acc = warp_sum(acc);
-    if (lane == 0) *dst = A.accumulate ? *dst + acc : acc;
+    if (lane == 0) wsum[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += wsum[w];
+      *dst = A.accumulate ? *dst + t : t;
+    }
+    __syncthreads();
   }
 }
 
@@ -298,9 +316,10 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
   A.accumulate = accumulate;
   const StreamGeom g = make_geom(*d);
   const long long work = d->mapping == 1 ? (long long)g.heads * (g.co * g.ci * g.taps + g.co) : (long long)g.heads * g.ci * g.co;
-  int blocks = (int)((work * (d->mapping == 1 ? 32 : 1) + ADJ_THREADS - 1) / ADJ_THREADS);
+  // conv mapping: one block per output (see the kernel); linear: one thread per element
+  int blocks = d->mapping == 1 ? (int)work : (int)((work + ADJ_THREADS - 1) / ADJ_THREADS);
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;  // 8 resident blocks of 256 threads per SM: one wave
   stream_param_grads_kernel<<<d->heads + blocks, ADJ_THREADS, 0, (cudaStream_t)stream>>>(A);
   return check_launch("stream_param_grads_kernel");
 }
