@@ -99,7 +99,7 @@ class FlatParams:
         if p2p is None:
             return False
         n_pad = (p2p["n"] + 31) & ~31
-        off = 2 * p2p["world"] * n_pad * 4 + 2 * p2p["world"] * 4
+        off = 2 * p2p["world"] * n_pad * 8  # the marker follows the {value, epoch} words
         return bool(p2p["box"][off:off + 4].view(torch.int32).item())
 
     def broadcast_params(self, src: int = 0, group: Optional[dist.ProcessGroup] = None):

@@ -163,22 +163,26 @@ class TrainStep:
             self.x, self.y, self.graph = keep
 
     # -- pipelined loading: batch i+1 crosses PCIe on a copy stream while batch i trains ------------------
-    def enable_prefetch(self):
-        """Two input slots, each with its own captured graph, plus a copy stream and the events that order them."""
+    def enable_prefetch(self, n_slots: int = 2):
+        """``n_slots`` input slots, each with its own captured graph, plus a copy stream and the events that order them."""
         if self._slots is not None:
-            return
+            if len(self._slots) >= n_slots:
+                return
+            raise RuntimeError("enable_prefetch was already called with fewer slots")
         if self.graph is None:
             raise RuntimeError("enable_prefetch needs use_graph=True")
-        slot0 = dict(x=self.x, y=self.y, graph=self.graph)
-        self.x, self.y = torch.empty_like(self.x), torch.empty_like(self.y)
-        self.x.copy_(slot0["x"])
-        self.y.copy_(slot0["y"])
-        self._capture()
-        slot1 = dict(x=self.x, y=self.y, graph=self.graph)
-        self._slots = [slot0, slot1]
+        slots = [dict(x=self.x, y=self.y, graph=self.graph)]
+        for _ in range(1, n_slots):
+            self.x, self.y = torch.empty_like(self.x), torch.empty_like(self.y)
+            self.x.copy_(slots[0]["x"])
+            self.y.copy_(slots[0]["y"])
+            self._capture()
+            slots.append(dict(x=self.x, y=self.y, graph=self.graph))
+        self._slots = slots
         for s in self._slots:
             s["ready"] = torch.cuda.Event()   # inputs of this slot have landed
             s["free"] = torch.cuda.Event()    # the step that read this slot has finished
+            s["ready"].record()
             s["free"].record()
         self.copy_stream = torch.cuda.Stream()
 

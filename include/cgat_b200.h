@@ -242,7 +242,8 @@ int cgat_val_metrics(const void* y, const void* y_hat, int64_t n, float power, f
 /* Data-parallel gradient exchange + Adam as ONE kernel over NVLink peer memory (small models).  Every
  * rank owns a mailbox of cgat_p2p_mailbox_bytes(n, world) bytes in peer-mapped (symmetric) memory, ZEROED once before
  * the first step; peer_mailboxes is a HOST array of the `world` device addresses (index = rank).  The kernel pushes
- * `grad` into every peer's mailbox, signals, waits for all sources, sums them in rank order (bit-identical on every
+ * `grad` into every peer's mailbox as {value, epoch} words (the flag travels with the data: no fence, no flag hop),
+ * waits per element for all sources, sums them in rank order (bit-identical on every
  * rank), and applies torch.optim.Adam with the 1/world mean folded in (train.py:212).  The 1-based step count (also the
  * exchange epoch) is read from `step_dev`, or taken from `step_host` when step_dev is NULL.  n <= 2^20 floats; larger models use an NCCL all-reduce + cgat_adam_step.        */
 int64_t cgat_p2p_mailbox_bytes(int64_t n, int32_t world);
