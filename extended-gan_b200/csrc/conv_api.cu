@@ -27,6 +27,8 @@ int conv_is_fullwindow(const cgat_conv_desc* d);
 int conv_fullwindow_fprop_launch(const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int conv_dw3x3_served(const cgat_conv_desc* d);
 int conv_dw3x3_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, float*, const float*, cudaStream_t);
+int conv_wgrad_small_served(const cgat_conv_desc* d);
+int conv_wgrad_small_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
 int conv_gemm_served(const cgat_conv_desc* d);
 int conv_gemm_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 }  // namespace cgat
@@ -43,7 +45,8 @@ static const char* kNames[3] = {"fprop", "dgrad", "wgrad"};
 // (wgrad also falls to them for small-channel shapes the resident kernel does not serve)
 static int use_big(const cgat_conv_desc* d, int which) {
   if (conv_big_supported(d, which)) return 1;
-  return which == 2 && !conv_tc_supported(d, 2) && conv_big_wgrad_small_ok(d);
+  // ... unless the CUDA-core small-channel wgrad (conv_wgrad_small.cu) serves them better
+  return which == 2 && !conv_tc_supported(d, 2) && conv_big_wgrad_small_ok(d) && !conv_wgrad_small_served(d);
 }
 
 static int tc_ready(const cgat_conv_desc* d, int which, void* workspace) {
@@ -96,6 +99,7 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
   if (int rc = validate_conv(d)) return rc;
   if (!x || !dy || !dw) return fail(CGAT_EINVAL, "null x/dy/dw");
   if (impl == 0 && conv_dw3x3_served(d)) return conv_dw3x3_launch(2, d, x, dy, dw, dbias, nullptr, (cudaStream_t)stream);
+  if (impl == 0 && conv_wgrad_small_served(d)) return conv_wgrad_small_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) {
     if (int rc = conv_pointwise_launch(2, d, dy, x, dw, nullptr, (cudaStream_t)stream)) return rc;
     return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;

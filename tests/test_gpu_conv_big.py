@@ -22,8 +22,8 @@ BIG_CASES = [
     (2, 16, 16, 64, 384, 1, (0, 0, 0, 0)),      # second cout tile half empty
     (2, 16, 16, 64, 64, 4, (1, 1, 2, 2)),       # k=4 padding="same" (dcgan/model.py:61-72)
     (1, 3, 3, 64, 64, 3, (1, 1, 1, 1)),         # image smaller than any tile
-    (2, 16, 16, 32, 16, 4, (1, 1, 2, 2)),       # DCGAN generator layers (dcgan/model.py:61-72): fprop/dgrad on the
-    (2, 16, 16, 16, 8, 4, (1, 1, 2, 2)),        #   resident-weight kernels, wgrad on the streamed one (one dY box)
+    (2, 16, 16, 32, 16, 4, (1, 1, 2, 2)),       # DCGAN generator layers (dcgan/model.py:61-72) on few pixels: fprop/dgrad
+    (2, 16, 16, 16, 8, 4, (1, 1, 2, 2)),        #   on the resident-weight kernels, wgrad on the streamed one (one dY box)
 ]
 
 

@@ -48,7 +48,9 @@ def test_conv_tc_fprop_dgrad(case):
     wgrad_cols = k * k * ((cin // 8 + 1) // 2 * 16) + 16  # TMEM columns the wgrad accumulators need
     tc_bwd = cout % 8 == 0 and cout <= 128 and wgrad_cols <= 512
     # shapes the resident-weight wgrad does not take fall to the streamed one (conv_tc_big.cu) from 16 x 8 channels up
-    tc_bwd = tc_bwd or (cin % 8 == 0 and cout % 8 == 0 and cin >= 16 and cout >= 8)
+    # (unless the CUDA-core small-channel wgrad takes them: <= 32 channels and at least 4096 output pixels)
+    small = cin <= 32 and cout in (4, 8, 16, 32) and k * k * cin <= 512 and n * yr.shape[1] * yr.shape[2] >= 4096
+    tc_bwd = tc_bwd or (cin % 8 == 0 and cout % 8 == 0 and cin >= 16 and cout >= 8 and not small)
     # IMPL_AUTO falls back to the direct wgrad kernel where the tcgen05 one does not serve the shape
     yo = conv2d_nhwc(xo, wo, bo, stride=1, pad=pad, impl=IMPL_TC if tc_bwd else IMPL_AUTO)
     scale = max(1.0, yr.abs().max().item())
