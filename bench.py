@@ -309,14 +309,18 @@ def run_ours(args):
             sl["y"].copy_(torch.roll(y, i, 0))
         torch.cuda.synchronize()
 
+        host_enqueue = [None]
+
         def timed_rotate(K, Wm):
             for i in range(Wm):
                 ts.run_slot(i % NS)
             barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
+            h0 = time.perf_counter()
             for i in range(K):
                 ts.run_slot(i % NS)
+            host_enqueue[0] = (time.perf_counter() - h0) / K * 1e3  # ms of host time per step to enqueue (no sync)
             b.record()
             barrier()
             t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
@@ -324,7 +328,19 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
 
+        dbg = None
+        if os.environ.get("CGAT_P2P_TIMELINE") and world > 1:  # developer knob: where the exchange's time goes (stderr)
+            import ctypes
+            dbg = torch.zeros(4096 * 4, dtype=torch.int64, device=dev)
+            _lib.lib().cgat_debug_timeline(ctypes.c_void_p(dbg.data_ptr()))
         total_ms = timed_rotate(args.steps, max(3, args.warmup))
+        if dbg is not None:
+            _lib.lib().cgat_debug_timeline(None)
+            t = dbg.view(4096, 4)[ts._step - args.steps + 1:ts._step + 1].cpu().double() / 1e3
+            med = lambda v: float(v.median())
+            print(f"[p2p timeline] rank {rank}: step {med(t[1:, 0] - t[:-1, 0]):.1f} us = exchange kernel "
+                  f"{med(t[:, 3] - t[:, 0]):.1f} (push {med(t[:, 1] - t[:, 0]):.1f}, wait {med(t[:, 2] - t[:, 1]):.1f}, "
+                  f"adam {med(t[:, 3] - t[:, 2]):.1f}) + rest {med(t[1:, 0] - t[:-1, 3]):.1f}", file=sys.stderr, flush=True)
     else:
         total_ms = timed(lambda: ts.run(), args.steps, max(3, args.warmup))
     # ---- end to end: every step copies its x, y from pinned host memory and reads the loss back to the host.
@@ -456,6 +472,8 @@ def run_ours(args):
         "gpu_launches": per_step_launches * args.steps, "gpu_launches_per_step": per_step_launches,
         "roofline": roofline, "kernels": kernels, "clocks": clocks, "final_loss": final_loss,
     }
+    if args.l2 == "rotate":
+        line["host_enqueue_ms_per_step"] = host_enqueue[0]  # host time to enqueue one step: below ms_per_step = not host-bound
     if world == 1:
         try:
             line["conv_roofline"] = conv_tensor_roofline(pk, batch=B)

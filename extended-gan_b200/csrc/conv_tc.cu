@@ -234,6 +234,7 @@ __device__ __forceinline__ void copy_pixel_chunks(uint32_t stag, const StageDesc
 constexpr int DBG_TILES = 16, DBG_EVENTS = 9;
 static long long* g_dbg = nullptr;
 void set_debug_buffer(long long* p) { g_dbg = p; }
+long long* get_debug_buffer() { return g_dbg; }
 #define DBG(ev)                                                                                           \
   do {                                                                                                    \
     if (A.dbg != nullptr && blockIdx.x == 0 && it < DBG_TILES) A.dbg[it * DBG_EVENTS + (ev)] = clock64(); \

@@ -21,6 +21,14 @@ namespace cgat {
 constexpr int P2P_THREADS = 1024;
 constexpr int P2P_MAX_WORLD = 8;
 
+long long* get_debug_buffer();  // developer timeline (cgat_debug_timeline): 4 globaltimer stamps per step when set
+
+__device__ __forceinline__ long long p2p_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct P2pPeers {
   uint2* mailbox[P2P_MAX_WORLD];   // peer p's mailbox base
 };
@@ -38,8 +46,10 @@ __global__ void __launch_bounds__(P2P_THREADS)
 p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, long long n_pad, const float* __restrict__ g,
                           float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                           const long long* __restrict__ step_dev, long long step_host, float lr, float b1, float b2,
-                          float eps, float wd, uint32_t* timeout_marker) {
+                          float eps, float wd, uint32_t* timeout_marker, long long* dbg) {
   const long long epoch = step_dev != nullptr ? *step_dev : step_host;
+  const bool stamp = dbg != nullptr && threadIdx.x == 0 && epoch < 4096;
+  if (stamp) dbg[epoch * 4 + 0] = p2p_now();
   const uint32_t ep = (uint32_t)epoch;
   const int par = (int)(epoch & 1);
   const int tid = threadIdx.x;
@@ -48,6 +58,7 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
     const uint32_t bits = __float_as_uint(g[i]);
     for (int q = 0; q < world; ++q) st_word_sys(P.mailbox[q] + ((size_t)par * world + rank) * n_pad + i, bits, ep);
   }
+  if (stamp) dbg[epoch * 4 + 1] = p2p_now();
   // 2. + 3. per element: wait for every source, rank-ordered sum, Adam
   const float step = (float)epoch;
   const float bc1 = 1.f - powf(b1, step);
@@ -71,6 +82,7 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
       }
       gs += __uint_as_float(w.x);
     }
+    if (stamp && i == 0) dbg[epoch * 4 + 2] = p2p_now();
     const float pi = p[i];
     const float gi = fmaf(wd, pi, gs * gscale);
     const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
@@ -80,6 +92,7 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] = pi - step_size * (mi / denom);
   }
+  if (stamp) dbg[epoch * 4 + 3] = p2p_now();
 }
 
 }  // namespace cgat
@@ -110,6 +123,6 @@ extern "C" int cgat_p2p_allreduce_adam(const uint64_t* peer_mailboxes, int32_t r
   uint32_t* marker = reinterpret_cast<uint32_t*>(peer_mailboxes[rank] + (uint64_t)2 * world * n_pad * 8);
   p2p_allreduce_adam_kernel<<<1, P2P_THREADS, 0, (cudaStream_t)stream>>>(P, rank, world, n, n_pad, grad, param, m, v,
                                                                          (const long long*)step_dev, (long long)step_host, lr,
-                                                                         beta1, beta2, eps, weight_decay, marker);
+                                                                         beta1, beta2, eps, weight_decay, marker, get_debug_buffer());
   return check_launch("p2p_allreduce_adam_kernel");
 }
