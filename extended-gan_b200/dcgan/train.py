@@ -65,21 +65,36 @@ class GraphedAdversarialStep:
     three Adam steps); with the convs on tensor cores the GPU finishes them faster than Python can enqueue them, so
     the step is host-bound.  Replay removes the host from the loop; the arithmetic is the same launches in the same
     order.  Inputs are copied into static buffers; the returned tensors are the graph's static outputs (clone them
-    to keep a value across steps).  Optimisers must be built with ``make_optimizers(..., capturable=True)``."""
+    to keep a value across steps).  Optimisers must be built with ``make_optimizers(..., capturable=True)`` and be
+    fresh (no steps taken): construction runs warm-up steps on the example batch and then puts the nets and the Adam
+    state back where they were."""
 
     def __init__(self, *, netG, netFD, netTD, optimizerG, optimizerFD, optimizerTD, criterion, x, y, warmup=3):
         self.x, self.y = x.clone(), y.clone()
         kw = dict(netG=netG, netFD=netFD, netTD=netTD, optimizerG=optimizerG, optimizerFD=optimizerFD,
                   optimizerTD=optimizerTD, criterion=criterion, x=self.x, y=self.y)
+        # the warm-up steps (they allocate gradients and optimiser state before capture) must not count as training:
+        # parameters and BatchNorm statistics are restored and the Adam state is reset IN PLACE afterwards (the graph
+        # holds the addresses), so the first replay is the first optimisation step from the caller's state
+        nets, opts = (netG, netFD, netTD), (optimizerG, optimizerFD, optimizerTD)
+        saved = [(v, v.clone()) for net in nets for v in net.state_dict().values()]
         side = t.cuda.Stream()
         side.wait_stream(t.cuda.current_stream())
         with t.cuda.stream(side):
-            for _ in range(warmup):  # allocates gradients and optimiser state before capture
+            for _ in range(max(1, warmup)):
                 adversarial_step(**kw)
         t.cuda.current_stream().wait_stream(side)
         self.graph = t.cuda.CUDAGraph()
         with t.cuda.graph(self.graph):
             self.out = adversarial_step(**kw)
+        with t.no_grad():
+            for v, c in saved:
+                v.copy_(c)
+            for opt in opts:
+                for st in opt.state.values():
+                    for v in st.values():
+                        if t.is_tensor(v):
+                            v.zero_()
 
     def __call__(self, x, y):
         self.x.copy_(x, non_blocking=True)

@@ -155,6 +155,39 @@ def test_dcgan_adversarial_step_vs_reference_golden():
         assert moved > 0
 
 
+def test_dcgan_graphed_step_vs_reference_golden():
+    """The CUDA-graph replay of the adversarial step (dcgan.train.GraphedAdversarialStep) is the same first step from the
+    same state as the live reference's (tests/golden/dcgan_step.pt): construction's warm-up steps leave no trace."""
+    from dcgan.model import FrameDiscriminator, Generator, TemporalDiscriminator
+    from dcgan.train import GraphedAdversarialStep, default_criterion, make_optimizers
+
+    fx = golden("dcgan_step")
+    params = {"nc": fx["params.nc"], "ndf": fx["params.ndf"]}
+    nets = {"G": Generator(params), "FD": FrameDiscriminator(params), "TD": TemporalDiscriminator(params)}
+    for name, net in nets.items():
+        net.load_state_dict(sd_of(fx, f"{name}.sd0."))
+        for m in net.modules():
+            if isinstance(m, torch.nn.Dropout2d):
+                m.p = 0.0
+        net.to(DEV).train()
+    oG, oFD, oTD = make_optimizers(nets["G"], nets["FD"], nets["TD"], capturable=True)
+    x, y = fx["x"].to(DEV), fx["y"].to(DEV)
+    step = GraphedAdversarialStep(netG=nets["G"], netFD=nets["FD"], netTD=nets["TD"], optimizerG=oG, optimizerFD=oFD,
+                                  optimizerTD=oTD, criterion=default_criterion(), x=x, y=y)
+    for name, net in nets.items():  # construction restored the caller's state
+        for k, v in net.state_dict().items():
+            assert torch.equal(v.cpu(), fx[f"{name}.sd0.{k}"]), f"{name}.{k} changed by construction"
+    errFD, errTD, errG, _ = step(x, y)
+    close(errFD, fx["errFD"], rtol=1e-4, atol=1e-5, msg="errFD")
+    close(errTD, fx["errTD"], rtol=1e-4, atol=1e-5, msg="errTD")
+    close(errG, fx["errG"], rtol=1e-4, atol=1e-5, msg="errG")
+    for name, net in nets.items():
+        sd1 = sd_of(fx, f"{name}.sd1.")
+        for k, v in net.state_dict().items():
+            close(v, sd1[k], rtol=1e-4, atol=4.1e-4 if v.dtype.is_floating_point and "running" not in k else 1e-5,
+                  msg=f"{name}.{k} after the replayed step")
+
+
 @pytest.mark.parametrize("name", ["FD", "TD"])
 def test_dcgan_discriminators_bf16_stride2_on_tensor_cores(name):
     """bf16: the k=4 stride-2 convs run as space-to-depth + 2x2 stride-1 convs on the tcgen05 kernels (cgat.conv_layers).

@@ -51,3 +51,15 @@ for V, N, dt in ((8, 2, torch.float32), (8, 2, torch.bfloat16), (8, 16, torch.bf
     for k, (c, t) in prof.items():
         tot[k] = round(c * t, 2)
     print(f"UnetModel V={V}, x[{N},128,128,4,{V}] {dt}: fwd+bwd {ms:.1f} ms; our kernels (ms total):", tot)
+
+# the same model the way train(**cfg) runs it: TrainStep captures forward + loss + backward in one CUDA graph, so the
+# host's ~3 000 launches per step (per-vertex loop, BatchNorm / CBAM / pooling glue) drop out of the step time
+from cgat.train_step import TrainStep
+for V, N, dt in ((8, 2, torch.float32),):  # TrainStep keeps fp32 master parameters: the PyTorch glue layers need fp32 inputs
+    torch.manual_seed(369)
+    m = UnetModel(image_width=128, image_height=128, n_vertices=V, attention_type="unet").to(dev).to(dt)
+    x = torch.rand(N, 128, 128, 4, V, device=dev).to(dt)
+    y = torch.rand(N, 128, 128, 4, V, device=dev).to(dt)
+    ts = TrainStep(m, x, y, lr=1e-3, use_graph=True)
+    ms = timeit(lambda: ts.run(), 5)
+    print(f"UnetModel V={V}, x[{N},128,128,4,{V}] {dt}: full train step from a CUDA graph {ms:.1f} ms ({N / ms * 1e3:.1f} samples/s)")
