@@ -22,6 +22,8 @@ BIG_CASES = [
     (2, 16, 16, 64, 384, 1, (0, 0, 0, 0)),      # second cout tile half empty
     (2, 16, 16, 64, 64, 4, (1, 1, 2, 2)),       # k=4 padding="same" (dcgan/model.py:61-72)
     (1, 3, 3, 64, 64, 3, (1, 1, 1, 1)),         # image smaller than any tile
+    (1, 20, 36, 192, 640, 3, (1, 1, 1, 1)),     # three cout tiles (the last half empty), 3 channel blocks, ragged rows
+    (130, 5, 5, 128, 64, 2, (0, 0, 0, 0)),      # 4x4 outputs, 8 images per pixel tile, batch not a multiple of 8
     (2, 16, 16, 32, 16, 4, (1, 1, 2, 2)),       # DCGAN generator layers (dcgan/model.py:61-72) on few pixels: fprop/dgrad
     (2, 16, 16, 16, 8, 4, (1, 1, 2, 2)),        #   on the resident-weight kernels, wgrad on the streamed one (one dY box)
 ]
@@ -125,3 +127,25 @@ def test_fullwindow_conv(dtype, stride):
     close(yo, yr.detach(), rtol=tol, atol=tol, msg="y")
     close(xo.grad, xr.grad, rtol=tol, atol=tol, msg="dx")
     close(conv.weight.grad, wr.grad, rtol=tol, atol=tol, msg="dw")
+
+
+def test_conv_big_rectangular_kernel():
+    """1x3 and 3x1 kernels (kh != kw) through the tap-shifted TMA boxes: fprop, dgrad, wgrad."""
+    from cgat.functional import IMPL_TC, conv2d_nhwc
+
+    torch.manual_seed(21)
+    for kh, kw, pad in ((1, 3, (0, 1, 0, 1)), (3, 1, (1, 0, 1, 0))):
+        x = (torch.rand(2, 12, 14, 64) - 0.5).bfloat16().float()
+        wt = (torch.rand(96, kh, kw, 64) - 0.5).bfloat16().float()
+        xr, wr = x.clone().requires_grad_(), wt.clone().requires_grad_()
+        pt, pl, pb, pr = pad
+        yr = F.conv2d(F.pad(xr.permute(0, 3, 1, 2), (pl, pr, pt, pb)), wr.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+        g = (torch.rand_like(yr) - 0.5).bfloat16().float()
+        yr.backward(g)
+        xo = x.to(DEV, torch.bfloat16).requires_grad_()
+        wo = wt.to(DEV).requires_grad_()
+        yo = conv2d_nhwc(xo, wo, None, stride=1, pad=pad, impl=IMPL_TC)
+        yo.backward(g.to(DEV, torch.bfloat16))
+        close(yo, yr.detach(), rtol=2e-2, atol=1e-2 * max(1.0, yr.abs().max().item()), msg=f"y {kh}x{kw}")
+        close(xo.grad, xr.grad, rtol=2e-2, atol=1e-2 * max(1.0, xr.grad.abs().max().item()), msg=f"dx {kh}x{kw}")
+        close(wo.grad, wr.grad, rtol=1e-3, atol=1e-3 * max(1.0, wr.grad.abs().max().item()), msg=f"dw {kh}x{kw}")
