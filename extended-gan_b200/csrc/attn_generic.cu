@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
       for (int u = 0; u < GEN_MAX_C; ++u) hpi[u] = 0.f;
       const uint64_t mrow = act ? S.mask[i] : 0;
       if (act) {
+#pragma unroll 4
         for (int j = 0; j < nodes; ++j) {
           const float pre = s1 + s2[j];
           float e = pre > 0.f ? pre : alpha * pre;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
           mx = fmaxf(mx, e);
         }
         float sum = 0.f;
+#pragma unroll 4
         for (int j = 0; j < nodes; ++j) {
           const float pre = s1 + s2[j];
           float e = pre > 0.f ? pre : alpha * pre;
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
 #pragma unroll
       for (int u = 0; u < GEN_MAX_C; ++u) z[u] = 0.f;
       if (act) {
+#pragma unroll 4
         for (int ii = 0; ii < nodes; ++ii) {
           const float w = S.adj[ii * nodes + i];
           _Pragma("unroll") for (int u = 0; u < co; ++u) z[u] = fmaf(hp[ii * co + u], w, z[u]);
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
 #pragma unroll
           for (int u = 0; u < GEN_MAX_C; ++u) dhp[u] = 0.f;
           float* gadj = S.gadj + (size_t)k * nn + (size_t)i * nodes;
+#pragma unroll 4
           for (int t = 0; t < nodes; ++t) {
             int v = i + t;  // staggered: the pixels of a CTA that share the accumulator row hit different columns
             if (v >= nodes) v -= nodes;
@@ -241,6 +245,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
             atomicAdd(&gadj[v], ga_iv);
           }
           float dot = 0.f;
+#pragma unroll 4
           for (int j = 0; j < nodes; ++j) {
             const float pre = s1 + s2[j];
             const bool on = (mrow >> j) & 1ull;
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
             dot = fmaf(att, datt, dot);
           }
           // second pass over the row for ds1 (its own sum); the column sums are formed by the column's thread in 5b
+#pragma unroll 4
           for (int j = 0; j < nodes; ++j) {
             const float pre = s1 + s2[j];
             const bool on = (mrow >> j) & 1ull;
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
         float d2 = 0.f;
         if (act) {
           const float s2j = s2[i];
+#pragma unroll 4
           for (int r = 0; r < nodes; ++r) {
             const float pre = sts[r] + s2j;
             const bool on = (S.mask[r] >> i) & 1ull;
