@@ -244,7 +244,10 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
             }
             atomicAdd(&gadj[v], ga_iv);
           }
-          float dot = 0.f;
+          // one pass over the row: dot = sum_j att_ij datt_ij and, with l_ij = att_ij * LeakyReLU'(pre_ij) on the unmasked
+          // entries, ds1 = sum_j l_ij (datt_ij - dot) = sum_j l_ij datt_ij - dot * sum_j l_ij  (the column sums are formed
+          // by the column's thread in 5b)
+          float dot = 0.f, la = 0.f, lb = 0.f;
 #pragma unroll 4
           for (int j = 0; j < nodes; ++j) {
             const float pre = s1 + s2[j];
@@ -255,19 +258,11 @@ __global__ void __launch_bounds__(GEN_THREADS) attn_generic_kernel(const AttnArg
             float datt = 0.f;
             _Pragma("unroll") for (int u = 0; u < co; ++u) datt = fmaf(dhp[u], Wh[j * co + u], datt);
             dot = fmaf(att, datt, dot);
+            const float l = on ? att * (pre > 0.f ? 1.f : alpha) : 0.f;
+            la = fmaf(l, datt, la);
+            lb += l;
           }
-          // second pass over the row for ds1 (its own sum); the column sums are formed by the column's thread in 5b
-#pragma unroll 4
-          for (int j = 0; j < nodes; ++j) {
-            const float pre = s1 + s2[j];
-            const bool on = (mrow >> j) & 1ull;
-            float e = pre > 0.f ? pre : alpha * pre;
-            if (!on) e = kMaskFill;
-            const float att = fast_exp(e - mx) * rinv;
-            float datt = 0.f;
-            _Pragma("unroll") for (int u = 0; u < co; ++u) datt = fmaf(dhp[u], Wh[j * co + u], datt);
-            ds1 += on ? att * (datt - dot) * (pre > 0.f ? 1.f : alpha) : 0.f;
-          }
+          ds1 = fmaf(-dot, lb, la);
           _Pragma("unroll") for (int u = 0; u < co; ++u) dhps[i * co + u] = dhp[u];
           sts[i] = s1;
           sts[nodes + i] = mx;
