@@ -13,7 +13,7 @@
 
 namespace cgat {
 
-constexpr int GEN_THREADS = 128;
+constexpr int GEN_THREADS = 512;  // V = 64: 8 pixels share the CTA's [heads][V^2] adjacency accumulators (49 KB): 2 CTAs = 32 warps per SM (at 128 threads: 8 warps, ncu warps_active 12.5 %)
 constexpr int GEN_MAX_NODES = 64;
 constexpr int GEN_MAX_C = 8;
 
@@ -363,7 +363,7 @@ static int gen_launch(AttnOp op, const cgat_attn_desc* d, const AttnArgs& A, con
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long grid = (long long)sms * 8;  // persistent grid-stride CTAs: the per-CTA gradient accumulators are flushed once
+  long long grid = (long long)sms * 4;  // persistent grid-stride CTAs: the per-CTA gradient accumulators are flushed once
   if (grid > ngroups) grid = ngroups;
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
