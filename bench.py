@@ -188,6 +188,34 @@ def conv_tensor_roofline(pk, batch=64, reps=10):
             "all": out}
 
 
+def ours_rows(dev, batch=64):
+    """Our modules on the workloads of the eager-GPU baseline rows R1, R2, R4 (R3 is the headline line itself)."""
+    from oracle.baselines import fwd_bwd, time_fn  # timing helpers only
+    from convolutional_gat.baseline_model import BaselineModel, BaselineModel2D
+    from dcgan.model import FrameDiscriminator, Generator, TemporalDiscriminator
+    from dcgan.train import GraphedAdversarialStep, default_criterion, make_optimizers
+
+    torch.manual_seed(SEED)
+    rows = {}
+    x20 = torch.rand(4, 20, 20, 4, 6, device=dev)
+    for name, cls in (("R1_BaselineModel2D_20x20_fwd_bwd", BaselineModel2D), ("R2_BaselineModel_20x20_fwd_bwd", BaselineModel)):
+        m = cls(image_width=20, image_height=20, n_vertices=6).to(dev)
+        sec = time_fn(fwd_bwd(m, x20), dev, 3, 10)
+        rows[name] = {"samples_per_s": 4 / sec, "ms_per_step": sec * 1e3, "batch": 4, "dtype": "f32"}
+    for dtype, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        params = {"nc": 4, "ndf": 64}
+        nets = [Generator(params).to(dev), FrameDiscriminator(params).to(dev), TemporalDiscriminator(params).to(dev)]
+        oG, oFD, oTD = make_optimizers(*nets, capturable=True)
+        x = torch.rand(batch, 4, 64, 64, device=dev).to(dtype)
+        y = torch.rand(batch, 4, 64, 64, device=dev).to(dtype)
+        step = GraphedAdversarialStep(netG=nets[0], netFD=nets[1], netTD=nets[2], optimizerG=oG, optimizerFD=oFD,
+                                      optimizerTD=oTD, criterion=default_criterion(), x=x, y=y)
+        sec = time_fn(lambda: step(x, y), dev, 2, 10)
+        rows[f"R4_dcgan_adversarial_step_{tag}"] = {"samples_per_s": batch / sec, "ms_per_step": sec * 1e3, "batch": batch,
+                                                    "dtype": tag, "cuda_graph": True}
+    return rows
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -482,6 +510,25 @@ def run_ours(args):
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "4 samples/step x 3 steps of the same model (fp32 torch CPU, oracle/spec.py)"}
+    if world == 1 and not args.no_baselines:
+        # SURVEY 8(d) last row / BASELINE.md R1-R5: stock PyTorch (ATen / cuDNN / cuBLAS) on THIS B200 for the same
+        # modules -- what a user of the reference would run on the box -- and the same rows on the host cores.  Timed
+        # after, and outside of, our timed region.
+        try:
+            from oracle import baselines
+            eager = {"fp32": baselines.reference_rows(dev, batch_gpu=B),
+                     "bf16_autocast": baselines.reference_rows(dev, batch_gpu=B, autocast=True),
+                     "ours": dict(ours_rows(dev, B), R3_convgat_config2_train_step={
+                         "samples_per_s": line["value"], "ms_per_step": ms_per_step, "batch": B, "dtype": "bf16"}),
+                     "note": "eager PyTorch on the same GPU, CUDA events, batch 64 for R3/R4 and 4 for R1/R2 (the only size the "
+                             "reference's 2-D layer runs at); rows are restatements through oracle/spec.py (pinned to the live "
+                             "reference), which is FASTER than the reference's own diag_embed formulation"}
+            line["eager_gpu_baseline"] = eager
+            line["cpu_baseline"]["rows"] = baselines.reference_rows("cpu")
+            line["cpu_baseline"]["rows_note"] = ("R1-R4 of BASELINE.md section 3 on the host cores, fp32, batch 4; the unmodified "
+                                                 "reference's R1 (diag_embed [N,V,V,P,P]) measured 2.1 samples/s at survey time")
+        except Exception as exc:  # side measurements must not take the headline line down
+            line["eager_gpu_baseline"] = {"error": repr(exc)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -512,6 +559,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
     ap.add_argument("--type", default="temporal", choices=["temporal", "spatial", "multi_stream"])
     ap.add_argument("--mapping", default="conv", choices=["conv", "linear"])
+    ap.add_argument("--no-baselines", action="store_true", help="skip the eager-GPU / CPU baseline rows (R1-R5)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="cold-L2 rule of the timed region: rotate over input slots larger than L2, or flush between steps")
     args = ap.parse_args()

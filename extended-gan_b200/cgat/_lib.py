@@ -85,6 +85,8 @@ SIGNATURES = {
     "cgat_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P],
     "cgat_conv_tc_supported": [ctypes.POINTER(ConvDesc), _I],
     "cgat_conv_workspace_bytes": [ctypes.POINTER(ConvDesc), _I],
+    "cgat_conv_stream_supported": [ctypes.POINTER(ConvDesc), _I],
+    "cgat_conv_stream_workspace_bytes": [ctypes.POINTER(ConvDesc)],
     "cgat_conv2d_fprop_packed": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P],
     "cgat_conv2d_dgrad_packed": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P],
     "cgat_conv2d_wgrad_partial": [ctypes.POINTER(ConvDesc), _P, _P, _P, ctypes.POINTER(ctypes.c_int32),
@@ -129,6 +131,7 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
             fn.restype = ctypes.c_int
         L.cgat_conv_workspace_bytes.restype = ctypes.c_int64
+        L.cgat_conv_stream_workspace_bytes.restype = ctypes.c_int64
         L.cgat_stream_wpack_bytes.restype = ctypes.c_int64
         L.cgat_layer_workspace_bytes.restype = ctypes.c_int64
         L.cgat_p2p_mailbox_bytes.restype = ctypes.c_int64

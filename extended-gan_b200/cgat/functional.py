@@ -364,7 +364,7 @@ class _GATStreamFn(torch.autograd.Function):
         ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
         wsp = None
         if conv:
-            nbytes = lib().cgat_conv_workspace_bytes(ctypes.byref(cd), 2)
+            nbytes = lib().cgat_conv_stream_workspace_bytes(ctypes.byref(cd))
             wsp = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.call("cgat_conv2d_wgrad_partial", ctypes.byref(cd), ptr(x), ptr(din), ptr(wsp), ctypes.byref(ncta),
                       ctypes.byref(nt), st)

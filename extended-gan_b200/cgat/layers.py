@@ -70,7 +70,8 @@ def _conv_stream_served(N, H, W, nodes, ci, co, heads, layout, merge, alpha) -> 
     if cin % 8 or cout % 8 or cout > 128:
         return False
     cd = _lib.ConvDesc(N, H, W, cin, cout, 3, 3, 1, 1, 1, H, W, _lib.BF16, 0, 1)
-    return bool(L.cgat_conv_tc_supported(ctypes.byref(cd), 0)) and bool(L.cgat_conv_tc_supported(ctypes.byref(cd), 2))
+    # exactly what _GATStreamFn calls: the packed (resident-weight) fprop, wgrad and -- for stacked layers -- dgrad
+    return bool(L.cgat_conv_stream_supported(ctypes.byref(cd), 1))
 
 
 class _GATStream(nn.Module):

@@ -90,17 +90,31 @@ class FlatParams:
         except Exception as e:  # noqa: BLE001 -- any failure here means "no peer memory": keep NCCL
             self.p2p_error = repr(e)
             return False
-        self.p2p = dict(box=box, hdl=hdl, ptrs=ptrs, rank=rank, world=world, n=n)
+        n_pad = (n + 31) & ~31
+        off = 2 * world * n_pad * 8  # the time-out marker follows the {value, epoch} words
+        self.p2p = dict(box=box, hdl=hdl, ptrs=ptrs, rank=rank, world=world, n=n,
+                        marker=box[off:off + 4].view(torch.int32),
+                        marker_host=torch.zeros(1, dtype=torch.int32).pin_memory())
         return True
+
+    def p2p_poll_timeout(self, refresh: bool) -> bool:
+        """Non-blocking view of the exchange kernel's time-out marker: ``refresh`` enqueues an asynchronous copy of it
+        into pinned host memory on the current stream; the return value is whatever the LAST completed copy saw (so a
+        time-out surfaces a few steps late, without ever synchronising the training stream)."""
+        p2p = getattr(self, "p2p", None)
+        if p2p is None:
+            return False
+        seen = bool(p2p["marker_host"].item())
+        if refresh:
+            p2p["marker_host"].copy_(p2p["marker"], non_blocking=True)
+        return seen
 
     def p2p_timed_out(self) -> bool:
         """True if the exchange kernel ever gave up waiting for a peer (host sync; for tests / diagnostics)."""
         p2p = getattr(self, "p2p", None)
         if p2p is None:
             return False
-        n_pad = (p2p["n"] + 31) & ~31
-        off = 2 * p2p["world"] * n_pad * 8  # the marker follows the {value, epoch} words
-        return bool(p2p["box"][off:off + 4].view(torch.int32).item())
+        return bool(p2p["marker"].item())
 
     def broadcast_params(self, src: int = 0, group: Optional[dist.ProcessGroup] = None):
         if dist.is_initialized() and dist.get_world_size(group) > 1:

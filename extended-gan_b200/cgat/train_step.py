@@ -16,6 +16,7 @@
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Optional
 
@@ -28,6 +29,8 @@ from .parallel import FlatParams
 
 
 class TrainStep:
+    P2P_POLL_EVERY = 16  # steps between asynchronous reads of the P2P exchange's time-out marker
+
     def __init__(self, model: torch.nn.Module, example_x: torch.Tensor, example_y: torch.Tensor, lr: float = 1e-3,
                  weight_decay: float = 0.01, lam: float = 0.0005, betas=(0.9, 0.999), eps: float = 1e-8,
                  use_graph: bool = True, process_group: Optional[dist.ProcessGroup] = None, fuse_loss: bool = True):
@@ -59,14 +62,34 @@ class TrainStep:
         return stream
 
     # -- flat buffers ---------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def _preserve_module_state(self):
+        """Probe / warm-up passes run the model eagerly before step 1; for stateful modules (BatchNorm running statistics
+        and ``num_batches_tracked`` of UnetModel / SmaAt-UNet, dropout's RNG) that must not count as training: module
+        buffers and the RNG state are put back afterwards, so step 1 starts where the reference loop would."""
+        bufs = [(b, b.detach().clone()) for b in self.model.buffers()]
+        cpu_rng = torch.get_rng_state()
+        cuda_rng = torch.cuda.get_rng_state(self.device) if self.device.type == "cuda" else None
+        try:
+            yield
+        finally:
+            with torch.no_grad():
+                for b, c in bufs:
+                    if not torch.equal(b, c):  # (untouched buffers keep their version counter: caches keyed on it stay valid)
+                        b.copy_(c)
+            torch.set_rng_state(cpu_rng)
+            if cuda_rng is not None:
+                torch.cuda.set_rng_state(cuda_rng, self.device)
+
     def _flatten(self):
         model = self.model
         for p in model.parameters():
             p.grad = None
         # probe which parameters take part in the forward (eager, outside any graph)
-        out = model(self.x)
-        _, dy = loss_and_grad(out, self.y, self.lam)
-        out.backward(dy)
+        with self._preserve_module_state():
+            out = model(self.x)
+            _, dy = loss_and_grad(out, self.y, self.lam)
+            out.backward(dy)
         self.active = [(n, p) for n, p in model.named_parameters() if p.grad is not None and p.requires_grad]
         self.inactive = [n for n, p in model.named_parameters() if p.grad is None]
         self.flat = FlatParams(self.active)
@@ -99,6 +122,14 @@ class TrainStep:
 
             from . import _lib
 
+            # a rank that gave up waiting for a peer skipped its update (csrc/p2p_kernels.cu): that is fatal, not a
+            # warning -- the replicas no longer hold the same parameters.  Polled without a stream sync.
+            if self.flat.p2p_poll_timeout(refresh=self._step % self.P2P_POLL_EVERY == 0):
+                raise RuntimeError(
+                    f"cgat_p2p_allreduce_adam timed out waiting for a peer around step {self._step}: the ranks are out "
+                    "of step (every rank must take the same number of steps) or a peer died; parameters were NOT updated "
+                    "on this rank for that step.  Restart from a checkpoint, or train with the NCCL exchange.")
+
             _lib.call("cgat_p2p_allreduce_adam", ctypes.cast(p2p["ptrs"], ctypes.c_void_p), p2p["rank"], p2p["world"],
                       _lib.ptr(self.flat_grad), _lib.ptr(self.flat_param), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                       None, self._step, self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
@@ -126,10 +157,11 @@ class TrainStep:
     def _capture(self):
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(2):  # warm up allocator / lazy init on the side stream
-                self._fwd_bwd()
-        torch.cuda.current_stream().wait_stream(s)
+        with self._preserve_module_state():
+            with torch.cuda.stream(s):
+                for _ in range(2):  # warm up allocator / lazy init on the side stream
+                    self._fwd_bwd()
+            torch.cuda.current_stream().wait_stream(s)  # (before the buffers are restored on the current stream)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -218,7 +250,11 @@ class TrainStep:
         # A loader that refills the SAME pinned staging buffers every batch (the usual arrangement) gets the two copies
         # and the gather kernel as one captured graph per slot: one launch instead of ~8 host calls per batch -- the
         # end-to-end loop is otherwise bound by the host's enqueue rate, not by PCIe or the GPU.
-        key = (frames_host.data_ptr(), start_host.data_ptr(), float(normalizing_max), float(power))
+        if start_host.numel() != s["x"].shape[0]:
+            raise RuntimeError(f"prefetch_raw: {start_host.numel()} window starts for a slot of {s['x'].shape[0]} samples "
+                               "(short last batches go through TrainStep.step)")
+        key = (frames_host.data_ptr(), start_host.data_ptr(), tuple(frames_host.shape), tuple(start_host.shape),
+               float(normalizing_max), float(power))
         graphable = frames_host.is_pinned() and start_host.is_pinned() and not os.environ.get("CGAT_NO_RAW_GRAPH")
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(s["free"])

@@ -3,7 +3,8 @@
 Same class names, keyword-only constructor arguments, ``hidden_layer`` / ``output_layer`` attribute
 names and ``mapping_type`` attribute.  The reference's quirk of registering an ``output_layer`` whose
 forward is commented out (:44-47, :85-88) is kept: its parameters exist in ``state_dict()`` and in
-``parameters()`` (so Adam's weight decay still touches them) but receive no gradient.
+``parameters()`` but receive no gradient -- ``torch.optim.Adam`` skips parameters whose ``grad`` is ``None`` (weight
+decay included), and so does ``cgat.train_step.TrainStep``: they keep their initial values.
 """
 import torch.nn as nn
 

@@ -117,6 +117,18 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
   return conv_wgrad_tc_launch(d, x, dy, dw, dbias, workspace, (cudaStream_t)stream);
 }
 
+// The one-launch conv-GAT stream path (cgat_conv2d_fprop_packed / _wgrad_partial / _dgrad_packed) runs on the
+// RESIDENT-weight kernels only: cgat_conv_tc_supported also answers 1 for shapes only the streamed kernels serve.
+extern "C" int cgat_conv_stream_supported(const cgat_conv_desc* d, int need_dx) {
+  if (validate_conv(d)) return 0;
+  return conv_tc_supported(d, 0) && conv_tc_supported(d, 2) && (!need_dx || conv_tc_supported(d, 1));
+}
+
+extern "C" int64_t cgat_conv_stream_workspace_bytes(const cgat_conv_desc* d) {
+  if (validate_conv(d) || !conv_tc_supported(d, 2)) return 0;
+  return (int64_t)conv_tc_workspace(d, 2);
+}
+
 extern "C" int cgat_conv2d_fprop_packed(const cgat_conv_desc* d, const void* x, const void* wpack, const float* bias,
                                         void* y, void* stream) {
   if (int rc = validate_conv(d)) return rc;

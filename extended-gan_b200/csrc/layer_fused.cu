@@ -80,6 +80,12 @@ constexpr int LF_DBG_TILES = 16, LF_DBG_EVENTS = 16;
   do {                                                                                                           \
     if (A.dbg != nullptr && blockIdx.x == 0 && it < LF_DBG_TILES) A.dbg[it * LF_DBG_EVENTS + (ev)] = clock64();   \
   } while (0)
+// whole-kernel stamps of CTA 0 in row 14: 0 entry, 1 init done, 2 A:regs granted, 3 A:tiles done, 4 A:sums flushed,
+// 5 A:wgrad complete, 6 A:partials written, 7 all warps joined, 8 exit
+#define LDBGX(ev)                                                                            \
+  do {                                                                                       \
+    if (A.dbg != nullptr && blockIdx.x == 0) A.dbg[14 * LF_DBG_EVENTS + (ev)] = clock64();   \
+  } while (0)
 static long long* g_lf_dbg = nullptr;
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
@@ -146,6 +152,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nact = A.heads < LF_GROUPS ? A.heads : LF_GROUPS;  // attention groups that own at least one head
 
+  if (threadIdx.x == 0) LDBGX(0);
+  if (threadIdx.x == 0 && A.dbg != nullptr) {  // every CTA: start / end on the global timer (ns), entries [256 + 2 * cta]
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    A.dbg[256 + 2 * blockIdx.x] = (long long)t;
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < LF_MAXSTG; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&dyfull[i], 128 * nact); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128 * nact); }
@@ -185,6 +197,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) LDBGX(1);
 
   if (warp < LF_ATT_WARP0) {
     setmaxnreg_dec<24>();
@@ -288,6 +301,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   } else if (warp >= LF_ATT_WARP0 && warp < LF_ATT_WARP0 + 4 * LF_GROUPS) {
     // ===================== attention groups =====================
     setmaxnreg_inc<160>();
+    if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(2);
     const int g = (warp - LF_ATT_WARP0) >> 2;
     const int lg = warp & 3;
     const int m = lg * 32 + lane;  // TMEM lane = pixel of the tile
@@ -759,7 +773,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       }
       }  // !PAIR
       if constexpr (BWD) {
+        if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(3);
         flush(cur_head);
+        if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(4);
         if (A.y != nullptr && g == 0) {
           const float s = warp_sum(loss_acc), s2 = warp_sum(mse_acc);
           if (lane == 0) { atomicAdd(&s_gacc[MAX_HEADS * RG], s); atomicAdd(&s_gacc[MAX_HEADS * RG + 1], s2); }
@@ -767,6 +783,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         // ---- wgrad accumulator -> per-CTA partial sums (lane = dense cout) ----
         mbar_wait(done, 0);
         tc_fence_after();
+        if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(5);
         float* prow = A.partial + ((size_t)blockIdx.x * 128 + m) * A.nt;
         for (int c0 = g * 16; c0 < A.nt; c0 += nact * 16) {
           float v[16];
@@ -778,11 +795,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
                                                                     v[4 * i + 2] * A.out_scale, v[4 * i + 3] * A.out_scale);
           }
         }
+        if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(6);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) LDBGX(7);
   if constexpr (BWD) {
     for (int i = threadIdx.x; i < A.heads * RG; i += LF_THREADS) {
       const int k = i / RG, r = i - k * RG;
@@ -798,6 +817,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   if (warp == LF_MMA_WARP) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) LDBGX(8);
+  if (threadIdx.x == 0 && A.dbg != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    A.dbg[256 + 2 * blockIdx.x + 1] = (long long)t;
   }
 }
 

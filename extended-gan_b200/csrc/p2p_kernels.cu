@@ -14,6 +14,11 @@
 // steps ahead of a peer (step e+1 needs that peer's words of step e+1, sent after it finished e), and a stale word in
 // the same parity slot carries epoch e-2.  The mailbox is zeroed once (epoch 0 never matches).
 // One CTA (the vector is small); larger models keep the NCCL all-reduce.
+//
+// Contract: every rank takes EXACTLY the same number of steps (the epoch is the step counter).  A rank that waits
+// ~3 s for a peer gives up: the whole CTA then SKIPS the parameter / m / v update of that step (all-or-nothing, so a
+// replica is never updated from a partial or stale sum) and sets the time-out marker behind the mailbox, which
+// cgat.train_step.TrainStep polls and turns into a RuntimeError.
 #include "common.cuh"
 
 namespace cgat {
@@ -33,13 +38,16 @@ struct P2pPeers {
   uint2* mailbox[P2P_MAX_WORLD];   // peer p's mailbox base
 };
 
+// {value bits, epoch} as ONE 64-bit scalar access: single-copy atomic at 8-byte alignment (a .v2.u32 access is two
+// scalar accesses in unspecified order to the PTX memory model -- a reader could see the new epoch with old bits)
 __device__ __forceinline__ void st_word_sys(uint2* p, uint32_t bits, uint32_t epoch) {
-  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(bits), "r"(epoch) : "memory");
+  const unsigned long long w = (unsigned long long)bits | ((unsigned long long)epoch << 32);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ uint2 ld_word_sys(const uint2* p) {
-  uint2 v;
-  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
 }
 
 __global__ void __launch_bounds__(P2P_THREADS)
@@ -68,21 +76,37 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
   const float gscale = 1.f / (float)world;
   const uint2* mine = P.mailbox[rank] + (size_t)par * world * n_pad;
   const long long t0 = clock64();
-  for (long long i = tid; i < n; i += P2P_THREADS) {
+  // 2a. wait for every word of this thread's elements; the rank-ordered sums of its first P2P_CACHE elements stay in
+  //     registers (every conv-GAT model: n <= 4096), later ones are re-read from the (local) mailbox in 2b
+  constexpr int P2P_CACHE = 4;
+  float cache[P2P_CACHE];
+  int timed_out = 0;
+  auto wait_sum = [&](long long i) {
     float gs = 0.f;
     for (int q = 0; q < world; ++q) {
       const uint2* src = mine + (size_t)q * n_pad + i;
       uint2 w = ld_word_sys(src);
-      while (w.y != ep) {
-        if (clock64() - t0 > 6000000000ll) {  // ~3 s: a peer never arrived; record it instead of hanging the GPU
-          atomicExch(timeout_marker, 1u);
-          break;
-        }
-        w = ld_word_sys(src);
+      while (w.y != ep && !timed_out) {
+        if (clock64() - t0 > 6000000000ll) timed_out = 1;  // ~3 s: a peer never arrived
+        else w = ld_word_sys(src);
       }
       gs += __uint_as_float(w.x);
     }
-    if (stamp && i == 0) dbg[epoch * 4 + 2] = p2p_now();
+    return gs;
+  };
+#pragma unroll
+  for (int s = 0; s < P2P_CACHE; ++s) {
+    const long long i = tid + (long long)s * P2P_THREADS;
+    cache[s] = i < n ? wait_sum(i) : 0.f;
+  }
+  for (long long i = tid + (long long)P2P_CACHE * P2P_THREADS; i < n; i += P2P_THREADS) wait_sum(i);
+  // all-or-nothing: one late word anywhere in the vector and NO element of p / m / v is touched this step
+  if (__syncthreads_or(timed_out)) {
+    if (tid == 0) atomicExch(timeout_marker, 1u);
+    return;
+  }
+  if (stamp) dbg[epoch * 4 + 2] = p2p_now();
+  auto adam = [&](long long i, float gs) {
     const float pi = p[i];
     const float gi = fmaf(wd, pi, gs * gscale);
     const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
@@ -91,6 +115,16 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
     v[i] = vi;
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
     p[i] = pi - step_size * (mi / denom);
+  };
+#pragma unroll
+  for (int s = 0; s < P2P_CACHE; ++s) {
+    const long long i = tid + (long long)s * P2P_THREADS;
+    if (i < n) adam(i, cache[s]);
+  }
+  for (long long i = tid + (long long)P2P_CACHE * P2P_THREADS; i < n; i += P2P_THREADS) {
+    float gs = 0.f;
+    for (int q = 0; q < world; ++q) gs += __uint_as_float(ld_word_sys(mine + (size_t)q * n_pad + i).x);
+    adam(i, gs);
   }
   if (stamp) dbg[epoch * 4 + 3] = p2p_now();
 }

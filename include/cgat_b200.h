@@ -129,6 +129,10 @@ int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const void* dy, fl
                       int impl, void* workspace, void* stream);
 int cgat_conv_tc_supported(const cgat_conv_desc* d, int which /*0 fprop,1 dgrad,2 wgrad*/);
 int64_t cgat_conv_workspace_bytes(const cgat_conv_desc* d, int which);
+/* Whether the packed-weight entry points below (the one-launch conv-GAT stream path; resident-weight kernels only) serve
+ * the shape -- fprop and wgrad, plus dgrad when need_dx -- and the size of cgat_conv2d_wgrad_partial's workspace. */
+int cgat_conv_stream_supported(const cgat_conv_desc* d, int need_dx);
+int64_t cgat_conv_stream_workspace_bytes(const cgat_conv_desc* d);
 
 /* Variants used by the fused conv-GAT stream: fprop with weights already packed by cgat_stream_prepare (no
  * per-call packing launch), and wgrad that leaves its per-CTA partial sums [ncta][128][nt] in `workspace`

@@ -136,3 +136,20 @@ def test_fused_layer_unsupported_shapes_take_unfused_path():
     assert _lib.lib().cgat_layer_supported(ctypes.byref(d)) == 0
     d = _lib.LayerDesc(2, 16, 16, 4, 6, 6, 3, _lib.LAYOUT_TEMPORAL, _lib.MERGE_MEAN, 1, 0.2)
     assert _lib.lib().cgat_layer_supported(ctypes.byref(d)) == 1
+
+
+@pytest.mark.parametrize("type_,V,heads", [("temporal", 8, 3), ("spatial", 8, 3), ("spatial", 32, 1)])
+def test_conv_stream_shapes_outside_the_resident_kernels(type_, V, heads):
+    """Shapes whose dense block-diagonal conv (cin = nodes*ci) the resident-weight wgrad cannot hold (9*cin + 8 > 256):
+    V = 8 gives cin = 32 / cout = 96, V = 32 with one head gives cin = cout = 128.  cgat_conv_tc_supported answers 1 for
+    them (streamed kernels), the packed one-launch stream path must NOT be chosen -- forward AND backward have to work
+    (advisor finding, round 1: the backward used to raise 'tcgen05 wgrad does not support this conv shape')."""
+    import ctypes
+    from cgat import _lib
+
+    nodes, ci = (V, 4) if type_ == "spatial" else (4, V)
+    cd = _lib.ConvDesc(2, 16, 16, nodes * ci, heads * nodes * ci, 3, 3, 1, 1, 1, 16, 16, _lib.BF16, 0, 1)
+    assert _lib.lib().cgat_conv_stream_supported(ctypes.byref(cd), 1) == 0
+    ours, ref = _pair(type_, "conv", heads, "mean", "neighbour", False, seed=24, V=V)
+    x = torch.rand(2, 16, 16, 4, V).bfloat16().float()
+    _check(ours, ref, x, torch.bfloat16, 2e-2, 2e-2, 3e-2)

@@ -16,7 +16,9 @@ y = torch.rand(64, 64, 64, 4, 6, device=dev).bfloat16()
 ts = TrainStep(m, x, y, use_graph=False, fuse_loss=(mode == "train"))
 for _ in range(3):
     ts.run()
-buf = torch.zeros(16, 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(16 * 16 + 2 * 148, dtype=torch.int64, device=dev)
+full_buf = buf
+buf = full_buf[:256].view(16, 16)
 if len(sys.argv) > 2:
     buf[15, 15] = 1  # probe mode: the MMA thread waits for its own MMAs and logs their completion
 L = _lib.lib()
@@ -27,7 +29,10 @@ if mode == "fwd":
     with torch.no_grad():
         m(x)
 else:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     ts.run()
+    e1.record()
 torch.cuda.synchronize()
 L.cgat_layer_debug_timeline(None)
 t = buf.cpu()
@@ -37,3 +42,13 @@ names = ["Ttop", "Tempty", "Mfpdone", "Mwgdone", "Mfull", "Maccfr", "Mfprop", "M
 print("tile " + " ".join(f"{n:>8s}" for n in names))
 for i in range(14):
     print(f"{i:4d} " + " ".join(f"{(int(v) - t0) if v > 0 else -1:8d}" for v in t[i][:16]))
+x = t[14]
+print("kernel stamps (cycles from entry): " + " ".join(f"{n}={int(x[i]) - int(x[0])}" for i, n in enumerate(
+    ["entry", "init", "regs", "tiles_done", "flushed", "wgrad_done", "partials", "joined", "exit"])), "first TMA at", t0 - int(x[0]))
+c = full_buf[256:].view(148, 2).cpu()
+if mode != "fwd":
+    g0 = int(c[:, 0].min())
+    st, en = (c[:, 0] - g0).double() / 1e3, (c[:, 1] - g0).double() / 1e3
+    print(f"per-CTA global timer (us): start min {st.min():.2f} median {st.median():.2f} max {st.max():.2f} | end min {en.min():.2f} "
+          f"median {en.median():.2f} max {en.max():.2f} | duration min {(en - st).min():.2f} median {(en - st).median():.2f} max {(en - st).max():.2f}")
+    print(f"whole eager step by CUDA events: {e0.elapsed_time(e1) * 1e3:.1f} us")
