@@ -15,14 +15,20 @@
 //             across all tiles of the persistent CTA.  Only x and d(out) (train mode: x and y) are read from
 //             HBM; only per-CTA partial sums of the parameter gradients are written.
 //
-// Row planes (the im2col that is NOT materialised): for vertical tap r and 8-channel chunk c the TMA unit writes the
-// box  x[n][th*16-1+r .. +15][tw*8-1 .. +9][8c .. 8c+7]  as plane P(r,c) = [16 rows][10 cols][16 B]  (zero-filled
-// outside the image = the conv padding).  A horizontal tap s is then just a 16-byte shift of the operand's start
-// address: the 8 pixels of tile row hr are the contiguous 128 bytes at P + (hr*10 + s)*16, tile rows are 160 B
-// apart, planes 2560 B apart -- a legal SWIZZLE_NONE operand both K-major (fprop A: K = (s; r,c) chunks) and
-// MN-major (wgrad B: K = pixels, N = (r,c) chunks, one accumulator per s).  9 boxes per tile replace the producer
-// warps, the staging buffers and 56 KB of im2col; a stage is 25 KB, so 4 tiles are in flight.  A tenth plane of
-// ones per stage carries the bias into the fprop MMA and yields dbias in the wgrad MMA.
+// Column planes (the im2col that is NOT materialised): for horizontal tap s and 8-channel chunk c the TMA unit writes
+// the box  x[n][th*16-1 .. +17][tw*8-1+s .. +7][8c .. 8c+7]  as plane P(s,c) = [18 rows][8 cols][16 B]  (zero-filled
+// outside the image = the conv padding).  A plane row is the 8 pixels of one tile row = 128 contiguous, 128-byte
+// ALIGNED bytes = exactly one SWIZZLE_NONE core matrix; a vertical tap r is a shift of the operand's start address
+// by r rows (r * 128 B), so every core matrix the tensor core fetches stays 128-byte aligned (the first version of
+// this kernel shifted by 16 bytes per HORIZONTAL tap inside [16][10] row planes: two thirds of its operand fetches
+// straddled two 128-byte lines and an fprop MMA took ~150 cycles instead of ~75).  The same planes are a legal
+// operand both K-major (fprop A: K = (r; s,c) chunks) and MN-major (wgrad B: K = pixels, N = (s,c) chunks, one
+// accumulator per r).  9 boxes per tile replace the producer warps, the staging buffers and 56 KB of im2col.  A tenth
+// plane of ones per stage carries the bias into the fprop MMA and yields dbias in the wgrad MMA.
+//
+// Shared memory: [header | packed weights | d(Wh) buffers (ring of 2-3) | x stages (ring of 4)].  The x planes of a
+// tile live from its TMA load until its wgrad MMAs have read them; a d(Wh) buffer lives from the head exchange of
+// its tile until the same wgrad.  The two rings are independent, which is what lets 4 x stages + 3 d(Wh) buffers fit.
 //
 // Warp roles (512 threads, 1 CTA / SM): warp 0 TMA issuer, warp 1 MMA issuer + TMEM allocator, warps 4-15 three
 // attention groups (group g owns heads g, g+3, ...; warp % 4 selects the TMEM lane quarter).  The kernel launches
@@ -39,12 +45,14 @@ constexpr int LF_THREADS = 512;
 constexpr int LF_ATT_WARP0 = 4;
 constexpr int LF_GROUPS = 3;
 constexpr int LF_TMA_WARP = 0, LF_MMA_WARP = 1;
-constexpr int LF_MAXSTG = 4;        // row-plane stages (TMA prefetch depth)
+constexpr int LF_MAXSTG = 4;        // x-plane stages (TMA prefetch depth)
+constexpr int LF_MAXDW = 3;         // d(Wh) buffers (backward kernels)
 constexpr int LF_FP_COL0 = 256;     // TMEM: wgrad accumulators at columns [0,256), fprop accumulators at 256 + 128*acc
-constexpr int LF_WP = LF_TW + 2;    // plane columns (halo)
-constexpr int LF_PLANE = LF_TH * LF_WP * 16;  // 2560 B
-constexpr int LF_ROW = LF_WP * 16;            // 160 B between tile rows of a plane
+constexpr int LF_PR = LF_TH + 2;    // plane rows (vertical halo)
+constexpr int LF_ROW = LF_TW * 16;  // 128 B: one tile row of a plane = one core matrix
+constexpr int LF_PLANE = LF_PR * LF_ROW;      // 2304 B
 constexpr int LF_HDR = 8704;        // barriers + parameters (fp32 and packed-half2 copies)
+constexpr int LF_SLOT = 64;         // floats per attention warp in the end-of-kernel reduction scratch (>= RG + 3)
 
 struct LfArgs {
   long long* dbg;              // developer aid: clock64() timeline of CTA 0 (cgat_layer_debug_timeline)
@@ -67,8 +75,8 @@ struct LfArgs {
   int h, w, cin, cout, npad, heads, merge, apply_elu;
   float alpha;
   int nchunk, nq, mchunk, nt;   // nq = 3*nchunk + 1 planes per stage (the last one is all ones); nt = 3 * nq * 8
-  int tiles_h, tiles_w, tiles, nstg;
-  uint32_t wbytes, stage_bytes, im_off;
+  int tiles_h, tiles_w, tiles, nstg, ndw;
+  uint32_t wbytes, stage_bytes, dw_bytes;  // bytes of one x stage / of one d(Wh) buffer (0 in the forward kernel)
 };
 
 // timeline events of CTA 0's first LF_DBG_TILES tiles: [tile][event]
@@ -128,11 +136,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   constexpr int REC = NODES * CO;          // elements of one head's pixel record
   constexpr int RG = 2 * CO + NODES * NODES;  // a-grad + adjacency-grad values per head
   static_assert(REC % 8 == 0, "record must be a multiple of 16 bytes");
+  static_assert(RG + 3 <= LF_SLOT, "reduction slot too small");
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [4]  TMA -> MMA         (row planes landed)
-  uint64_t* empty = full + LF_MAXSTG;                  // [4]  MMA -> TMA         (stage reusable)
-  uint64_t* dyfull = empty + LF_MAXSTG;                // [4]  attention -> MMA   (d(Wh) planes written)
-  uint64_t* tfull = dyfull + LF_MAXSTG;                // [2]  MMA -> attention   (Wh accumulator ready)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [4]  TMA -> MMA         (x planes landed)
+  uint64_t* empty = full + LF_MAXSTG;                  // [4]  MMA -> TMA         (x stage reusable)
+  uint64_t* dyfull = empty + LF_MAXSTG;                // [3]  attention -> MMA   (d(Wh) buffer written)
+  uint64_t* dwfree = dyfull + LF_MAXDW;                // [3]  MMA -> attention   (d(Wh) buffer consumed by its wgrad)
+  uint64_t* tfull = dwfree + LF_MAXDW;                 // [2]  MMA -> attention   (Wh accumulator ready)
   uint64_t* tempty = tfull + 2;                        // [2]  attention -> MMA   (accumulator drained)
   uint64_t* wbar = tempty + 2;                         // [1]
   uint64_t* done = wbar + 1;                           // [1]
@@ -146,7 +156,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   static_assert(MAX_HEADS * 2 * CO * 4 <= 512 && MAX_HEADS * NODES * NODES * 4 <= 2048 && NODES * 8 <= 64 &&
                     3392 + (MAX_HEADS * RG + 2) * 4 <= 6144 && 6656 + MAX_HEADS * NODES * NODES * 4 <= LF_HDR, "parameter block overflows the header");
   unsigned char* s_w = smem + LF_HDR;
-  unsigned char* s_stage = s_w + ((A.wbytes + 127u) & ~127u);
+  // d(Wh) buffers come BEFORE the x stages: the wgrad A operand always spans 16 planes (M = 128 rows), so the last
+  // buffer's unused rows read on into the x stages (finite data; those accumulator rows are never stored)
+  unsigned char* s_dw = s_w + ((A.wbytes + 127u) & ~127u);
+  unsigned char* s_stage = s_dw + (size_t)A.ndw * A.dw_bytes;
   float4* s_slab = reinterpret_cast<float4*>(s_stage + (size_t)A.nstg * A.stage_bytes);  // fwd: [group][REC/4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,12 +172,35 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     A.dbg[256 + 2 * blockIdx.x] = (long long)t;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < LF_MAXSTG; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&dyfull[i], 128 * nact); }
+    for (int i = 0; i < LF_MAXSTG; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < LF_MAXDW; ++i) { mbar_init(&dyfull[i], 128 * nact); mbar_init(&dwfree[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128 * nact); }
     mbar_init(wbar, 1);
     mbar_init(done, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmap_x);
+  }
+  __syncthreads();  // barriers are live: the TMA thread starts fetching while everyone else initialises shared memory
+
+  const uint32_t tile_bytes = (uint32_t)(A.nq - 1) * LF_PLANE;
+  auto issue_tile = [&](int tile, int stage) {  // 9 column-plane boxes of one tile (TMA thread only)
+    const int tw = tile % A.tiles_w;
+    const int th = (tile / A.tiles_w) % A.tiles_h;
+    const int n = tile / (A.tiles_w * A.tiles_h);
+    mbar_arrive_expect_tx(&full[stage], tile_bytes);
+    unsigned char* dst = s_stage + (size_t)stage * A.stage_bytes;
+    for (int sh = 0; sh < 3; ++sh)
+      for (int c = 0; c < A.nchunk; ++c)
+        tma_load_4d(dst + (size_t)(sh * A.nchunk + c) * LF_PLANE, &tmap_x, c * 8, tw * LF_TW - 1 + sh, th * LF_TH - 1, n,
+                    &full[stage]);
+  };
+  if (warp == LF_TMA_WARP && lane == 0) {
+    // the first tile's planes before the (tile-independent) weights: the x planes are written whole by the TMA unit
+    // (padding included), so they need no initialisation and their HBM latency overlaps the set-up below
+    // (only the first tile: a TMA instruction takes ~100 cycles to issue, and everyone waits for this thread below)
+    if ((int)blockIdx.x < A.tiles) issue_tile(blockIdx.x, 0);
+    mbar_arrive_expect_tx(wbar, A.wbytes);
+    bulk_g2s(s_w, A.wpack, A.wbytes, wbar);
   }
   for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) { s_a[i] = A.a[i]; s_a2[i] = __float2half2_rn(A.a[i]); }
   for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) {
@@ -179,15 +215,14 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     s_mask[threadIdx.x] = mrow;
   }
   {
-    // every plane starts zeroed (padding planes must hold finite numbers); then the plane of ones that
-    // follows the im2col planes (its wgrad column is dbias; its fprop K-chunk holds the bias, hi + lo bf16 parts)
-    uint4* p = reinterpret_cast<uint4*>(s_stage);
-    const int n16 = (int)((size_t)A.nstg * A.stage_bytes / 16);
+    // d(Wh) buffers start zeroed (rows the attention groups never write must hold finite numbers); every x stage gets
+    // its plane of ones behind the im2col planes (its wgrad column is dbias; its fprop K-chunk holds the bias, hi + lo
+    // bf16 parts).  The TMA unit may already be writing the OTHER planes of the stages: disjoint addresses.
+    uint4* p = reinterpret_cast<uint4*>(s_dw);
+    const int n16 = (int)((size_t)A.ndw * A.dw_bytes / 16);
     for (int i = threadIdx.x; i < n16; i += LF_THREADS) p[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
     for (int st = 0; st < A.nstg; ++st) {
-      uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)st * A.stage_bytes + A.im_off +
-                                                (size_t)(A.nq - 1) * LF_PLANE);
+      uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)st * A.stage_bytes + (size_t)(A.nq - 1) * LF_PLANE);
       for (int i = threadIdx.x; i < LF_PLANE / 4; i += LF_THREADS) o[i] = 0x3f803f80u;  // bf16 1.0 x2
     }
     fence_proxy_async_smem();
@@ -202,25 +237,16 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   if (warp < LF_ATT_WARP0) {
     setmaxnreg_dec<24>();
     if (warp == LF_TMA_WARP && lane == 0) {
-      // ===================== TMA issuer: 9 row-plane boxes per tile =====================
-      mbar_arrive_expect_tx(wbar, A.wbytes);
-      bulk_g2s(s_w, A.wpack, A.wbytes, wbar);
-      const uint32_t tile_bytes = (uint32_t)(A.nq - 1) * LF_PLANE;
+      // ===================== TMA issuer: 9 column-plane boxes per tile (the first tile is on its way) ====
       int it = 0, stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
-        const int tw = tile % A.tiles_w;
-        const int th = (tile / A.tiles_w) % A.tiles_h;
-        const int n = tile / (A.tiles_w * A.tiles_h);
         LDBG(0);
-        mbar_wait(&empty[stage], phase ^ 1u);
-        LDBG(1);
-        mbar_arrive_expect_tx(&full[stage], tile_bytes);
-        unsigned char* dst = s_stage + (size_t)stage * A.stage_bytes + A.im_off;
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < A.nchunk; ++c)
-            tma_load_4d(dst + (size_t)(r * A.nchunk + c) * LF_PLANE, &tmap_x, c * 8, tw * LF_TW - 1, th * LF_TH - 1 + r, n,
-                        &full[stage]);
+        if (it > 0) {
+          if (it >= A.nstg) mbar_wait(&empty[stage], phase ^ 1u);
+          LDBG(1);
+          issue_tile(tile, stage);
+        }
         if (++stage == A.nstg) { stage = 0; phase ^= 1u; }
       }
     } else if (warp == LF_MMA_WARP && lane == 0) {
@@ -230,30 +256,32 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       const uint32_t w_addr = smem_u32(s_w);
       const uint32_t b_lbo = (uint32_t)A.npad * 16;
       uint32_t wg_accum = 0;
-      int wstage = 0, wj = 0;  // wj: next tile whose wgrad is to be issued
-      uint32_t wphase = 0;
-      auto wgrad = [&](int j) {  // tiles are retired in order: (wstage, wphase) follow tile j
-        mbar_wait(&dyfull[wstage], wphase);
+      int wstage = 0, wbuf = 0, wj = 0;  // wj: next tile whose wgrad is to be issued; its x stage and d(Wh) buffer
+      uint32_t wphase = 0, bphase = 0;
+      auto wgrad = [&](int j) {  // tiles are retired in order: (wstage, wphase), (wbuf, bphase) follow tile j
+        mbar_wait(&dyfull[wbuf], bphase);
         { const int it = j; LDBG(7); }
         tc_fence_after();
-        const uint32_t dy_addr = smem_u32(s_stage) + (uint32_t)wstage * A.stage_bytes;
-        const uint32_t im_addr = dy_addr + A.im_off;
-        for (int sh = 0; sh < 3; ++sh) {  // horizontal tap = 16-byte shift of the planes; one accumulator each
+        const uint32_t dy_addr = smem_u32(s_dw) + (uint32_t)wbuf * A.dw_bytes;
+        const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)wstage * A.stage_bytes;
+        for (int r = 0; r < 3; ++r) {  // vertical tap = the planes shifted by r rows (128 B); one accumulator each
 #pragma unroll
           for (int jj = 0; jj < LF_TH / 2; ++jj) {  // K step: image rows 2jj, 2jj+1 of the tile (16 pixels)
             const uint64_t ad = make_smem_desc(dy_addr + jj * 256, 128, 2048);
-            const uint64_t bd = make_smem_desc(im_addr + sh * 16 + jj * 2 * LF_ROW, LF_ROW, LF_PLANE);
-            umma_bf16(tmem_base + (uint32_t)(sh * A.nq * 8), ad, bd, idesc_w, wg_accum | (uint32_t)(jj > 0));
+            const uint64_t bd = make_smem_desc(im_addr + (uint32_t)(r + 2 * jj) * LF_ROW, LF_ROW, LF_PLANE);
+            umma_bf16(tmem_base + (uint32_t)(r * A.nq * 8), ad, bd, idesc_w, wg_accum | (uint32_t)(jj > 0));
           }
         }
         wg_accum = 1;
         umma_commit(&empty[wstage]);
+        umma_commit(&dwfree[wbuf]);
         { const int it = j; LDBG(8); }
         if (A.dbg != nullptr && A.dbg[255] != 0) {
-          mbar_wait(&empty[wstage], wphase);
+          mbar_wait(&dwfree[wbuf], bphase);
           { const int it = j; LDBG(3); }
         }
         if (++wstage == A.nstg) { wstage = 0; wphase ^= 1u; }
+        if (++wbuf == A.ndw) { wbuf = 0; bphase ^= 1u; }
       };
       mbar_wait(wbar, 0);
       int it = 0, stage = 0;
@@ -265,12 +293,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
         LDBG(5);
         tc_fence_after();
-        const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + A.im_off;
+        const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes;
         const uint32_t d_addr = tmem_base + LF_FP_COL0 + (uint32_t)acc * 128;
         uint32_t kk = 0;
-        for (int sh = 0; sh < 3; ++sh) {
-          for (int q = 0; q < A.nq; q += 2, kk += 2) {  // K = 16: planes q, q+1 of horizontal tap sh
-            const uint64_t ad = make_smem_desc(im_addr + (uint32_t)q * LF_PLANE + sh * 16, LF_PLANE, LF_ROW);
+        for (int r = 0; r < 3; ++r) {
+          for (int q = 0; q < A.nq; q += 2, kk += 2) {  // K = 16: planes q, q+1 shifted by the vertical tap r
+            const uint64_t ad = make_smem_desc(im_addr + (uint32_t)q * LF_PLANE + (uint32_t)r * LF_ROW, LF_PLANE, LF_ROW);
             const uint64_t bd = make_smem_desc(w_addr + kk * b_lbo, b_lbo, 128);
             umma_bf16(d_addr, ad, bd, idesc_f, kk > 0);
           }
@@ -285,7 +313,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           umma_commit(&empty[stage]);
         } else if constexpr (PAIR) {
           // the attention groups work on tile PAIRS: issue both fprops of the next pair before blocking on the
-          // d(Wh) planes of the previous one
+          // d(Wh) buffers of the previous one
           if (it & 1)
             while (wj < it - 1) wgrad(wj++);
         } else {
@@ -344,7 +372,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           const int it = 2 * itp;
           const int tileB = tileA + gridDim.x;
           const bool hasB = tileB < A.tiles;
-          const int stA = (2 * itp) % A.nstg, stB = (2 * itp + 1) % A.nstg;
+          const int bufA = (2 * itp) % A.ndw, bufB = (2 * itp + 1) % A.ndw;  // d(Wh) buffers of the two tiles
+          const int useA = (2 * itp) / A.ndw, useB = (2 * itp + 1) / A.ndw;   // how often each has been used before
           const uint32_t ph = (uint32_t)itp & 1u;
           long long pixA, pixB = 0;
           bool validA, validB = false;
@@ -399,8 +428,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           attn_nb_forward<H2, NODES, CO, MASKED>(Wh2, a2, adj2, s_mask, alpha2, st, z2);
           if (dbg_thread) LDBG(11);
           // ---- swap ELU(z) of the three heads through the d(Wh) planes of the two stages (fp16) ----
-          const uint32_t exA = smem_u32(s_stage) + (uint32_t)stA * A.stage_bytes + (uint32_t)m * 16;
-          const uint32_t exB = smem_u32(s_stage) + (uint32_t)stB * A.stage_bytes + (uint32_t)m * 16;
+          const uint32_t exA = smem_u32(s_dw) + (uint32_t)bufA * A.dw_bytes + (uint32_t)m * 16;
+          const uint32_t exB = smem_u32(s_dw) + (uint32_t)bufB * A.dw_bytes + (uint32_t)m * 16;
+          // the wgrad MMAs that read these buffers last time round must have completed
+          if (useA > 0) mbar_wait(&dwfree[bufA], (uint32_t)(useA - 1) & 1u);
+          if (hasB && useB > 0) mbar_wait(&dwfree[bufB], (uint32_t)(useB - 1) & 1u);
           {
             // ELU(z) = max(z, t - 1) with t = exp(min(z, 0)) = ELU'(z): t replaces z (only the derivative is needed later)
             __half2 o2[REC];
@@ -536,8 +568,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
             }
           }
           fence_proxy_async_smem();
-          mbar_arrive(&dyfull[stA]);
-          if (hasB) mbar_arrive(&dyfull[stB]);
+          mbar_arrive(&dyfull[bufA]);
+          if (hasB) mbar_arrive(&dyfull[bufB]);
           if (dbg_thread) LDBG(14);
         }
 #pragma unroll
@@ -546,11 +578,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           gacc[i] += f.x + f.y;
         }
       } else {
-      int it = 0, stage = -1;
+      int it = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t ph = ((uint32_t)it >> 1) & 1u;
-        if (++stage == A.nstg) stage = 0;
+        const int buf = BWD ? it % A.ndw : 0, use = BWD ? it / A.ndw : 0;  // this tile's d(Wh) buffer (backward kernels)
+        const uint32_t dwb = smem_u32(s_dw) + (uint32_t)buf * A.dw_bytes + (uint32_t)m * 16;
         const int tw = tile % A.tiles_w;
         const int th = (tile / A.tiles_w) % A.tiles_h;
         const int n = tile / (A.tiles_w * A.tiles_h);
@@ -583,6 +616,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           }
         }
         mbar_wait(&tfull[acc], ph);
+        if (BWD && use > 0) mbar_wait(&dwfree[buf], (uint32_t)(use - 1) & 1u);  // the buffer's previous wgrad has completed
         tc_fence_after();
         const bool dbg_thread = g == 0 && m == 0;
         if (dbg_thread) LDBG(9);
@@ -641,7 +675,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               // ---- train mode (mean merge, one head per group): out = mean_k ELU(z_k) needs every head of the
               //      pixel, so the groups swap their ELU(z) through the (still unused) d(Wh) planes of this stage
               //      as fp16; d(out) = (2 (out - y) - lambda) / numel   (convolutional_gat/train.py:131) ----
-              const uint32_t exb = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + (uint32_t)m * 16;
+              const uint32_t exb = dwb;
 #pragma unroll
               for (int v = 0; v < NODES; ++v)
 #pragma unroll
@@ -723,8 +757,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
             if (dbg_thread) LDBG(13);
             mat_to_rec<NODES, CO, SPATIAL>(z, rec);
             // d(Wh) -> the MN-major A operand of the wgrad MMA: plane = dense cout / 8, 16 bytes per pixel
-            const uint32_t dy = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes + (uint32_t)(k * (REC / 8)) * 2048 +
-                                (uint32_t)m * 16;
+            const uint32_t dy = dwb + (uint32_t)(k * (REC / 8)) * 2048;
 #pragma unroll
             for (int q = 0; q < REC / 8; ++q) {
               uint4 v;
@@ -739,7 +772,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         if constexpr (BWD) {
           fence_proxy_async_smem();
-          mbar_arrive(&dyfull[stage]);
+          mbar_arrive(&dyfull[buf]);
           if (dbg_thread) LDBG(14);
         } else if (!concat) {
           // ---- head mean: every group leaves its partial sum in its slab, then all active threads combine ----
@@ -774,12 +807,26 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       }  // !PAIR
       if constexpr (BWD) {
         if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(3);
-        flush(cur_head);
-        if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(4);
-        if (A.y != nullptr && g == 0) {
-          const float s = warp_sum(loss_acc), s2 = warp_sum(mse_acc);
-          if (lane == 0) { atomicAdd(&s_gacc[MAX_HEADS * RG], s); atomicAdd(&s_gacc[MAX_HEADS * RG + 1], s2); }
+        // ---- this warp's sums -> its slot in the (now idle) weight buffer: butterflies interleaved over all values,
+        //      plain stores, no shared-memory atomics (fp32 ATOMS is a CAS loop: 28 serialised ones cost 8 600 cycles)
+        {
+          float* slot = reinterpret_cast<float*>(s_w) + (warp - LF_ATT_WARP0) * LF_SLOT;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int i = 0; i < RG; ++i) gacc[i] += __shfl_xor_sync(0xffffffffu, gacc[i], off);
+            loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+            mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, off);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < RG; ++i) slot[i] = gacc[i];
+            slot[RG] = loss_acc;
+            slot[RG + 1] = mse_acc;
+            reinterpret_cast<int*>(slot)[RG + 2] = cur_head;
+          }
         }
+        if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(4);
         // ---- wgrad accumulator -> per-CTA partial sums (lane = dense cout) ----
         mbar_wait(done, 0);
         tc_fence_after();
@@ -803,15 +850,21 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   __syncthreads();
   if (threadIdx.x == 0) LDBGX(7);
   if constexpr (BWD) {
+    const float* slots = reinterpret_cast<const float*>(s_w);
     for (int i = threadIdx.x; i < A.heads * RG; i += LF_THREADS) {
       const int k = i / RG, r = i - k * RG;
-      const float v = s_gacc[i] * A.out_scale;
+      float v = s_gacc[i];  // heads a group finished before its last one (more than LF_GROUPS heads)
+      for (int wa = 0; wa < 4 * nact; ++wa)  // fixed order: the CTA's contribution is deterministic
+        if (reinterpret_cast<const int*>(slots + wa * LF_SLOT)[RG + 2] == k) v += slots[wa * LF_SLOT + r];
+      v *= A.out_scale;
       if (r < NODES * NODES) atomicAdd(A.gadj + (size_t)k * NODES * NODES + r, v);
       else atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
     }
     if (A.y != nullptr && threadIdx.x == 0) {
-      atomicAdd(A.loss_out, s_gacc[MAX_HEADS * RG] * A.inv_n);
-      if (A.mse_out != nullptr) atomicAdd(A.mse_out, s_gacc[MAX_HEADS * RG + 1] * A.inv_n);
+      float l = 0.f, q = 0.f;
+      for (int wa = 0; wa < 4 * nact; ++wa) { l += slots[wa * LF_SLOT + RG]; q += slots[wa * LF_SLOT + RG + 1]; }
+      atomicAdd(A.loss_out, l * A.inv_n);
+      if (A.mse_out != nullptr) atomicAdd(A.mse_out, q * A.inv_n);
     }
   }
   if (warp == LF_MMA_WARP) {
@@ -829,9 +882,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
 // ---- host side ------------------------------------------------------------------------------------------
 struct LfGeom {
   int cin, cout, rec, nchunk, nq, npad, mchunk, nt;
-  uint32_t wbytes, stage_bytes, im_off;
+  uint32_t wbytes, stage_bytes, dw_bytes;
   size_t smem;
-  int tiles_h, tiles_w, tiles, nstg;
+  int tiles_h, tiles_w, tiles, nstg, ndw;
 };
 
 static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
@@ -840,21 +893,22 @@ static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
   g.cin = d->nodes * d->ci;
   g.cout = d->heads * g.rec;
   g.nchunk = g.cin / 8;
-  g.nq = 3 * g.nchunk + 1;            // row planes per stage, the last one all ones
+  g.nq = 3 * g.nchunk + 1;            // column planes per stage, the last one all ones
   g.npad = (g.cout + 15) & ~15;
   g.mchunk = g.cout / 8;
-  g.nt = 3 * g.nq * 8;                // wgrad partial columns: [s][(r,c) | ones][8]
+  g.nt = 3 * g.nq * 8;                // wgrad partial columns: [r][(s,c) | ones][8]
   g.wbytes = (uint32_t)(3 * g.nq) * g.npad * 16;
-  g.im_off = bwd ? (uint32_t)g.mchunk * 2048 : 0;
-  g.stage_bytes = g.im_off + (uint32_t)g.nq * LF_PLANE;
-  if (g.stage_bytes < 16 * 2048) g.stage_bytes = 16 * 2048;  // the wgrad A operand always spans 16 planes (M = 128)
-  g.stage_bytes = (g.stage_bytes + 127u) & ~127u;
+  g.stage_bytes = ((uint32_t)g.nq * LF_PLANE + 127u) & ~127u;
+  g.dw_bytes = bwd ? (uint32_t)g.mchunk * 2048 : 0;
   g.nstg = LF_MAXSTG;
-  do {
-    g.smem = LF_HDR + ((g.wbytes + 127u) & ~127u) + (size_t)g.nstg * g.stage_bytes +
-             (bwd ? 0 : (size_t)LF_GROUPS * g.rec * 128 * 4);
-  } while (g.smem > 227 * 1024 && --g.nstg >= 2);
-  if (g.nstg < 2) g.nstg = 2;
+  g.ndw = bwd ? LF_MAXDW : 0;
+  auto total = [&]() {
+    return (size_t)LF_HDR + ((g.wbytes + 127u) & ~127u) + (size_t)g.ndw * g.dw_bytes + (size_t)g.nstg * g.stage_bytes +
+           (bwd ? 0 : (size_t)LF_GROUPS * g.rec * 128 * 4);
+  };
+  // shed a d(Wh) buffer first (two serve a tile pair), then x stages
+  while ((g.smem = total()) > 227 * 1024 && g.ndw > 2) --g.ndw;
+  while ((g.smem = total()) > 227 * 1024 && g.nstg > 2) --g.nstg;
   g.tiles_h = (d->h + LF_TH - 1) / LF_TH;
   g.tiles_w = (d->w + LF_TW - 1) / LF_TW;
   g.tiles = d->n * g.tiles_h * g.tiles_w;
@@ -937,7 +991,7 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
     return fail(CGAT_EALIGN, "layer tensors must be 16-byte aligned");
   const LfGeom g = lf_geom(d, bwd);
   CUtensorMap map;
-  if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, LF_WP, LF_TH)) return rc;
+  if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, LF_TW, LF_PR)) return rc;
   LfArgs A{};
   A.dbg = g_lf_dbg;
   A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
@@ -951,8 +1005,8 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
   A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt;
-  A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.nstg = g.nstg;
-  A.wbytes = g.wbytes; A.stage_bytes = g.stage_bytes; A.im_off = g.im_off;
+  A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.nstg = g.nstg; A.ndw = g.ndw;
+  A.wbytes = g.wbytes; A.stage_bytes = g.stage_bytes; A.dw_bytes = g.dw_bytes;
   if (ncta_out) *ncta_out = g.tiles < lf_sm_count() ? g.tiles : lf_sm_count();
   if (nt_out) *nt_out = g.nt;
   if (d->layout == CGAT_LAYOUT_SPATIAL) return lf_launch<6, 4, true>(bwd, d, g, map, A, st);

@@ -92,8 +92,8 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepA
     A.bias_dense[i] = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
   }
   if (A.d.wgrad_cols) {
-    // fused layer kernels (layer_fused.cu): K-chunk kk = s*nq + q, q = r*nchunk + c for the row plane of vertical tap r
-    // and channel chunk c, horizontal tap s; q = nq-1 multiplies the plane of ones: bias (hi + lo bf16 parts) at s = 0
+    // fused layer kernels (layer_fused.cu): K-chunk kk = r*nq + q, q = s*nchunk + c for the column plane of horizontal
+    // tap s and channel chunk c, vertical tap r; q = nq-1 multiplies the plane of ones: bias (hi + lo bf16 parts) at r = 0
     const int nq = 3 * g.nchunk + 1;
     const long long n_f = (long long)3 * nq * g.npad * 8;
     for (long long i = tid; i < n_f; i += nt) {
@@ -101,12 +101,12 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepA
       const long long qq = i >> 3;
       const int row = (int)(qq % g.npad);
       const int kk = (int)(qq / g.npad);
-      const int s = kk / nq, q = kk - s * nq;
+      const int r = kk / nq, q = kk - r * nq;
       float v = 0.f;
       if (q < nq - 1) {
-        const int r = q / g.nchunk, c = q - r * g.nchunk;
+        const int s = q / g.nchunk, c = q - s * g.nchunk;
         v = dense_w(g, A.w, row, r * 3 + s, c * 8 + e);
-      } else if (s == 0 && row < g.cout && e < 2) {
+      } else if (r == 0 && row < g.cout && e < 2) {
         const int per_head = g.nodes * g.co;
         const int k = row / per_head;
         int node, u;
@@ -214,12 +214,12 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
         if (node >= g.nodes) continue;
         const int row = k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u);
         int col;
-        if (A.d.wgrad_cols) {  // layer_fused.cu: [s][(r, cin chunk) | ones][8]; dbias is the ones column of s = 0
+        if (A.d.wgrad_cols) {  // layer_fused.cu: [r][(s, cin chunk) | ones][8]; dbias is the ones column of r = 0
           const int nq = 3 * g.nchunk + 1;
           col = (nq - 1) * 8;
           if (r < nwe) {
             const int ci_idx = rec_of(g.spatial, g.nodes, g.ci, node, c);
-            col = ((tap % 3) * nq + (tap / 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
+            col = ((tap / 3) * nq + (tap % 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
           }
         } else {
           col = g.taps * g.cin;
