@@ -386,8 +386,8 @@ class _GATStreamFn(torch.autograd.Function):
         g_B = [tg[per * k + per - 1] for k in range(heads)]
         Bs = [params[per * k + per - 1] for k in range(heads)]
         _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(gW), ptr(ga), ptr(gadj),
-                  _lib.ptr_array(Bs), _lib.ptr_array(g_w), _lib.ptr_array(g_b) if conv else None, _lib.ptr_array(g_a),
-                  _lib.ptr_array(g_B), int(direct), st)
+                  _lib.ptr_array(Bs), None, None, None, _lib.ptr_array(g_w), _lib.ptr_array(g_b) if conv else None,
+                  _lib.ptr_array(g_a), _lib.ptr_array(g_B), int(direct), st)
         grads = [None] * len(params) if direct else [g.to(p.dtype) for g, p in zip(tg, params)]
         return (dx, None, None, None, *grads)
 
@@ -423,8 +423,10 @@ class _GATStreamFn(torch.autograd.Function):
         g_B = [tg[per * k + 3] for k in range(heads)]
         Bs = [params[per * k + 3] for k in range(heads)]
         _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),
-                  _lib.ptr_array(Bs), _lib.ptr_array(g_w), _lib.ptr_array(g_b), _lib.ptr_array(g_a), _lib.ptr_array(g_B),
-                  int(direct), st)
+                  _lib.ptr_array(Bs), _lib.ptr_array([params[per * k] for k in range(heads)]),
+                  _lib.ptr_array([params[per * k + 1] for k in range(heads)]),
+                  _lib.ptr_array([params[per * k + 2] for k in range(heads)]), _lib.ptr_array(g_w), _lib.ptr_array(g_b),
+                  _lib.ptr_array(g_a), _lib.ptr_array(g_B), int(direct), st)
         grads = [None] * len(params) if direct else [g.to(p.dtype) for g, p in zip(tg, params)]
         return (dx, None, None, None, *grads)
 
@@ -479,7 +481,8 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
               float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(loss_out), ptr(mse_out), ctypes.byref(ncta), ctypes.byref(nt), st)
     tg = [p.grad for p in params]
     _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),
-              _lib.ptr_array(Bs), _lib.ptr_array([tg[4 * k] for k in range(heads)]),
+              _lib.ptr_array(Bs), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
+              _lib.ptr_array([tg[4 * k] for k in range(heads)]),
               _lib.ptr_array([tg[4 * k + 1] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 2] for k in range(heads)]),
               _lib.ptr_array([tg[4 * k + 3] for k in range(heads)]), 1, st)
 

@@ -65,6 +65,8 @@ struct F32 {
   }
   static CGAT_HD T rcp(T a) { return 1.f / a; }
   static CGAT_HD T gt0(T a) { return a > 0.f ? 1.f : 0.f; }  // 1 where a > 0 else 0
+  static CGAT_HD T abs(T a) { return fabsf(a); }
+  static CGAT_HD T neg_where_neg(T a, T s) { return s < 0.f ? -a : a; }  // a with its sign flipped where s < 0
 };
 
 #if defined(__CUDACC__)
@@ -97,6 +99,12 @@ struct H2 {
   }
   static CGAT_D T rcp(T a) { return h2rcp(a); }
   static CGAT_D T gt0(T a) { return __hgt2(a, __float2half2_rn(0.f)); }
+  static CGAT_D T abs(T a) { return __habs2(a); }
+  static CGAT_D T neg_where_neg(T a, T s) {  // one LOP3 on the integer pipe: a ^ (s & sign bits)
+    const uint32_t ua = *reinterpret_cast<const uint32_t*>(&a), us = *reinterpret_cast<const uint32_t*>(&s);
+    const uint32_t r = ua ^ (us & 0x80008000u);
+    return *reinterpret_cast<const T*>(&r);
+  }
 };
 #endif
 
@@ -403,21 +411,27 @@ struct NbState {
   typename P::T M[NODES][NODES];  // [v][j]
 };
 
-template <typename P, int NODES, int CO, bool MASKED>
+// EXT_S: the scores s1 = Wh.a[:CO], s2 = Wh.a[CO:] are linear in the layer input, so the fused train kernel lets the
+// fprop MMA produce them as extra output columns (conv weights W.a): the caller fills st.s1 / st.s2 and `a` is unused.
+// SIGN_ATT (with EXT_S): st.att leaves the function carrying the SIGN of its logit's pre-activation s1[i] + s2[j]
+// (|att| is the attention; LeakyReLU'(pre) = slope(att > 0)), so the backward needs neither s1 nor s2 nor the add.
+template <typename P, int NODES, int CO, bool MASKED, bool EXT_S = false, bool SIGN_ATT = false>
 CGAT_HD void attn_nb_forward(const typename P::T (&Wh)[NODES][CO], const typename P::T* __restrict__ a,
                              const typename P::T* __restrict__ adj, const uint64_t* __restrict__ maskrow,
                              typename P::T alpha, NbState<P, NODES>& st, typename P::T (&z)[NODES][CO]) {
   using T = typename P::T;
+  if (!EXT_S) {
 #pragma unroll
-  for (int i = 0; i < NODES; ++i) {
-    T p = P::mul(Wh[i][0], a[0]), q = P::mul(Wh[i][0], a[CO]);
+    for (int i = 0; i < NODES; ++i) {
+      T p = P::mul(Wh[i][0], a[0]), q = P::mul(Wh[i][0], a[CO]);
 #pragma unroll
-    for (int u = 1; u < CO; ++u) {
-      p = P::fma(Wh[i][u], a[u], p);
-      q = P::fma(Wh[i][u], a[CO + u], q);
+      for (int u = 1; u < CO; ++u) {
+        p = P::fma(Wh[i][u], a[u], p);
+        q = P::fma(Wh[i][u], a[CO + u], q);
+      }
+      st.s1[i] = p;
+      st.s2[i] = q;
     }
-    st.s1[i] = p;
-    st.s2[i] = q;
   }
 #pragma unroll
   for (int i = 0; i < NODES; ++i) {
@@ -448,6 +462,10 @@ CGAT_HD void attn_nb_forward(const typename P::T (&Wh)[NODES][CO], const typenam
 #pragma unroll
       for (int j = 0; j < NODES; ++j) st.M[v][j] = i == 0 ? P::mul(w, st.att[i][j]) : P::fma(w, st.att[i][j], st.M[v][j]);
     }
+    if (SIGN_ATT) {
+#pragma unroll
+      for (int j = 0; j < NODES; ++j) st.att[i][j] = P::neg_where_neg(st.att[i][j], P::add(st.s1[i], st.s2[j]));
+    }
   }
 #pragma unroll
   for (int v = 0; v < NODES; ++v)
@@ -461,12 +479,15 @@ CGAT_HD void attn_nb_forward(const typename P::T (&Wh)[NODES][CO], const typenam
 }
 
 // dz: gradient w.r.t. the pre-ELU z.  dWh is OVERWRITTEN; g_a [2CO] and g_adj [NODES*NODES] are accumulated into.
-template <typename P, int NODES, int CO, bool MASKED>
+// EXT_S: the score gradients are RETURNED in ds_out[0..NODES) = ds1, ds_out[NODES..2 NODES) = ds2 instead of being
+// folded into dWh and g_a (the wgrad MMA takes them as extra rows: d(W.a) = ds^T . im2col(x); the parameter-gradient
+// kernel then forms dW += a (x) d(W.a) and g_a = <W, d(W.a)>); `a` and `g_a` are unused.
+template <typename P, int NODES, int CO, bool MASKED, bool EXT_S = false>
 CGAT_HD void attn_nb_backward(const typename P::T (&Wh)[NODES][CO], const typename P::T (&dz)[NODES][CO],
                               const typename P::T* __restrict__ a, const typename P::T* __restrict__ adj,
                               const uint64_t* __restrict__ maskrow, typename P::T alpha, const NbState<P, NODES>& st,
                               typename P::T (&dWh)[NODES][CO], typename P::T* __restrict__ g_a,
-                              typename P::T* __restrict__ g_adj) {
+                              typename P::T* __restrict__ g_adj, typename P::T* __restrict__ ds_out = nullptr) {
   using T = typename P::T;
   T datt[NODES][NODES];
 #pragma unroll
@@ -515,19 +536,101 @@ CGAT_HD void attn_nb_backward(const typename P::T (&Wh)[NODES][CO], const typena
       ds1 = j == 0 ? dp : P::add(ds1, dp);
       ds2[j] = i == 0 ? dp : P::add(ds2[j], dp);
     }
+    if (EXT_S) {
+      ds_out[i] = ds1;
+    } else {
 #pragma unroll
-    for (int u = 0; u < CO; ++u) {
-      dWh[i][u] = P::fma(ds1, a[u], dWh[i][u]);
-      g_a[u] = P::fma(ds1, Wh[i][u], g_a[u]);
+      for (int u = 0; u < CO; ++u) {
+        dWh[i][u] = P::fma(ds1, a[u], dWh[i][u]);
+        g_a[u] = P::fma(ds1, Wh[i][u], g_a[u]);
+      }
     }
   }
+  if (EXT_S) {
 #pragma unroll
-  for (int j = 0; j < NODES; ++j)
+    for (int j = 0; j < NODES; ++j) ds_out[NODES + j] = ds2[j];
+  } else {
 #pragma unroll
-    for (int u = 0; u < CO; ++u) {
-      dWh[j][u] = P::fma(ds2[j], a[CO + u], dWh[j][u]);
-      g_a[CO + u] = P::fma(ds2[j], Wh[j][u], g_a[CO + u]);
+    for (int j = 0; j < NODES; ++j)
+#pragma unroll
+      for (int u = 0; u < CO; ++u) {
+        dWh[j][u] = P::fma(ds2[j], a[CO + u], dWh[j][u]);
+        g_a[CO + u] = P::fma(ds2[j], Wh[j][u], g_a[CO + u]);
+      }
+  }
+}
+
+// The EXT_S backward with a small register footprint (the fused train kernel runs two pixels per thread in 160
+// registers; its CTA's shared memory leaves ~8 KB of L1, so every spilled word is an L2 round trip):
+//   * dz is overwritten IN PLACE by d(Wh) -- column u of d(Wh) needs only column u of dz once dM is known;
+//   * the attention-gradient rows datt[i][.] exist one row at a time.
+//   * st.att carries the sign of the pre-activation (attn_nb_forward<..., SIGN_ATT>): st.s1 / st.s2 are not read.
+// dzw: in dz (gradient w.r.t. the pre-ELU z), out d(Wh) WITHOUT the score terms; ds_out[0..NODES) = ds1,
+// ds_out[NODES..2 NODES) = ds2; g_adj [NODES*NODES] accumulated into.  Masked edges have att = 0, hence de = 0.
+template <typename P, int NODES, int CO, bool MASKED>
+CGAT_HD void attn_nb_backward_inplace(const typename P::T (&Wh)[NODES][CO], typename P::T (&dzw)[NODES][CO],
+                                      const typename P::T* __restrict__ adj, const uint64_t* __restrict__ maskrow,
+                                      typename P::T alpha, const NbState<P, NODES>& st,
+                                      typename P::T* __restrict__ g_adj, typename P::T* __restrict__ ds_out) {
+  using T = typename P::T;
+  T dM[NODES][NODES];  // [v][j] = sum_u dz[v][u] Wh[j][u]
+#pragma unroll
+  for (int v = 0; v < NODES; ++v)
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      T acc = P::mul(dzw[v][0], Wh[j][0]);
+#pragma unroll
+      for (int u = 1; u < CO; ++u) acc = P::fma(dzw[v][u], Wh[j][u], acc);
+      dM[v][j] = acc;
     }
+#pragma unroll
+  for (int u = 0; u < CO; ++u) {  // d(Wh)[j][u] = sum_v M[v][j] dz[v][u], one column at a time, in place
+    T col[NODES];
+#pragma unroll
+    for (int v = 0; v < NODES; ++v) col[v] = dzw[v][u];
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      T acc = P::mul(st.M[0][j], col[0]);
+#pragma unroll
+      for (int v = 1; v < NODES; ++v) acc = P::fma(st.M[v][j], col[v], acc);
+      dzw[j][u] = acc;
+    }
+  }
+  const T one_minus_alpha = P::sub(P::bc(1.f), alpha);
+#pragma unroll
+  for (int i = 0; i < NODES; ++i) {
+    const uint64_t mrow = MASKED ? maskrow[i] : ~0ull;
+    (void)mrow;
+    T datt[NODES], att[NODES];
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      T acc = P::mul(adj[i * NODES], dM[0][j]);
+#pragma unroll
+      for (int v = 1; v < NODES; ++v) acc = P::fma(adj[i * NODES + v], dM[v][j], acc);
+      datt[j] = acc;
+      att[j] = P::abs(st.att[i][j]);
+    }
+#pragma unroll
+    for (int v = 0; v < NODES; ++v) {
+      T gsum = g_adj[i * NODES + v];
+#pragma unroll
+      for (int j = 0; j < NODES; ++j) gsum = P::fma(att[j], dM[v][j], gsum);
+      g_adj[i * NODES + v] = gsum;
+    }
+    T dot = P::mul(att[0], datt[0]);
+#pragma unroll
+    for (int j = 1; j < NODES; ++j) dot = P::fma(att[j], datt[j], dot);
+    T ds1 = P::zero();
+#pragma unroll
+    for (int j = 0; j < NODES; ++j) {
+      const T de = P::mul(att[j], P::sub(datt[j], dot));
+      const T slope = P::fma(one_minus_alpha, P::gt0(st.att[i][j]), alpha);
+      const T dp = P::mul(de, slope);
+      ds1 = j == 0 ? dp : P::add(ds1, dp);
+      ds_out[NODES + j] = i == 0 ? dp : P::add(ds_out[NODES + j], dp);
+    }
+    ds_out[i] = ds1;
+  }
 }
 
 // linear projection helpers (reference baseline_model.py:127  Wh = h @ W, W is [CI][CO] row-major)

@@ -101,4 +101,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 #endif
 
+// Fused conv-GAT layer (layer_fused.cu / stream_ops.cu): the attention scores s1 = Wh.a[:co], s2 = Wh.a[co:] are linear
+// in the layer input, so the dense conv gets extra output rows  W.a  per (head, node) -- `sph` rows per head (2*nodes
+// padded to a 16-byte chunk) behind the heads*nodes*co feature rows -- whenever everything still fits one M = 128 /
+// N <= 128 tcgen05 tile.  Both translation units must agree on this rule.
+__host__ __device__ inline int lf_score_rows_per_head(int nodes) { return (2 * nodes + 7) & ~7; }
+__host__ __device__ inline int lf_score_rows(int nodes, int co, int heads) {
+  const int ext = heads * lf_score_rows_per_head(nodes);
+  return heads * nodes * co + ext <= 128 ? ext : 0;
+}
+
 }  // namespace cgat

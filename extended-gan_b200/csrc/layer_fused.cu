@@ -33,10 +33,11 @@
 // Warp roles (512 threads, 1 CTA / SM): warp 0 TMA issuer, warp 1 MMA issuer + TMEM allocator, warps 4-15 three
 // attention groups (group g owns heads g, g+3, ...; warp % 4 selects the TMEM lane quarter).  The kernel launches
 // with 128 registers per thread; setmaxnreg moves warpgroup 0's budget to the attention warpgroups
-// (24 + 3 * 160 <= 512 = the CTA's pool).
+// (128 * 32 + 384 * 160 = 65 536 = the CTA's pool, exactly).
 #include "tc_common.cuh"
 #include "attn_common.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace cgat {
 
@@ -56,7 +57,8 @@ constexpr int LF_SLOT = 64;         // floats per attention warp in the end-of-k
 
 struct LfArgs {
   long long* dbg;              // developer aid: clock64() timeline of CTA 0 (cgat_layer_debug_timeline)
-  const __nv_bfloat16* wpack;  // [2*npairs][npad][8] chunk-major packed dense weights (cgat_stream_prepare)
+  const __nv_bfloat16* x;      // input records [n][h][w][cin] (read through the tensor map; the pointer serves L2 prefetches)
+  const __nv_bfloat16* wpack;  // [3*nq][npad][8] chunk-major packed dense weights (cgat_stream_prepare)
   const float* bias;           // [cout] dense bias
   const float* a;              // [heads][2co]
   const float* adj;            // [heads][nodes][nodes]
@@ -72,7 +74,7 @@ struct LfArgs {
   float* mse_out;              // train mode, optional: mean squared error alone (the reference's running train loss)
   float out_scale;             // bwd: factor applied to the gradient sums when they leave the kernel (PAIR: 1/numel)
   float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
-  int h, w, cin, cout, npad, heads, merge, apply_elu;
+  int h, w, cin, cout, ext, npad, heads, merge, apply_elu;  // ext: score rows behind the cout feature rows (0: none)
   float alpha;
   int nchunk, nq, mchunk, nt;   // nq = 3*nchunk + 1 planes per stage (the last one is all ones); nt = 3 * nq * 8
   int tiles_h, tiles_w, tiles, nstg, ndw;
@@ -84,16 +86,26 @@ struct LfArgs {
 //  7 M:dWh planes full  8 M:wgrad issued | 9 A:Wh ready  10 A:Wh in registers  11 A:forward done  12 A:after exchange
 //  13 A:backward done  14 A:tile done           (A = attention group 0, warp 0, lane 0)
 constexpr int LF_DBG_TILES = 16, LF_DBG_EVENTS = 16;
+// The stamps cost registers in the 32-register TMA / MMA warps (their spills go to L2: the CTA's shared memory leaves
+// ~8 KB of L1), so they are compiled in only with -DCGAT_LF_TIMELINE (make TIMELINE=1; tools/layer_timeline.py).
+#ifdef CGAT_LF_TIMELINE
 #define LDBG(ev)                                                                                                 \
   do {                                                                                                           \
     if (A.dbg != nullptr && blockIdx.x == 0 && it < LF_DBG_TILES) A.dbg[it * LF_DBG_EVENTS + (ev)] = clock64();   \
   } while (0)
+#else
+#define LDBG(ev) do { (void)it; } while (0)
+#endif
 // whole-kernel stamps of CTA 0 in row 14: 0 entry, 1 init done, 2 A:regs granted, 3 A:tiles done, 4 A:sums flushed,
 // 5 A:wgrad complete, 6 A:partials written, 7 all warps joined, 8 exit
+#ifdef CGAT_LF_TIMELINE
 #define LDBGX(ev)                                                                            \
   do {                                                                                       \
     if (A.dbg != nullptr && blockIdx.x == 0) A.dbg[14 * LF_DBG_EVENTS + (ev)] = clock64();   \
   } while (0)
+#else
+#define LDBGX(ev) do { } while (0)
+#endif
 static long long* g_lf_dbg = nullptr;
 
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
@@ -146,7 +158,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   uint64_t* tempty = tfull + 2;                        // [2]  attention -> MMA   (accumulator drained)
   uint64_t* wbar = tempty + 2;                         // [1]
   uint64_t* done = wbar + 1;                           // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* dhread = done + 1;                         // [1]  attention -> attention (d(out) read by every group; PAIR)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dhread + 1);
   float* s_a = reinterpret_cast<float*>(smem + 768);             // [MAX_HEADS][2*CO]
   float* s_adj = reinterpret_cast<float*>(smem + 1280);          // [MAX_HEADS][NODES*NODES]
   uint64_t* s_mask = reinterpret_cast<uint64_t*>(smem + 3328);   // [NODES]
@@ -166,17 +179,20 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   const int nact = A.heads < LF_GROUPS ? A.heads : LF_GROUPS;  // attention groups that own at least one head
 
   if (threadIdx.x == 0) LDBGX(0);
+#ifdef CGAT_LF_TIMELINE
   if (threadIdx.x == 0 && A.dbg != nullptr) {  // every CTA: start / end on the global timer (ns), entries [256 + 2 * cta]
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     A.dbg[256 + 2 * blockIdx.x] = (long long)t;
   }
+#endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < LF_MAXSTG; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < LF_MAXDW; ++i) { mbar_init(&dyfull[i], 128 * nact); mbar_init(&dwfree[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128 * nact); }
     mbar_init(wbar, 1);
     mbar_init(done, 1);
+    mbar_init(dhread, 128 * nact);
     fence_mbar_init();
     tma_prefetch_desc(&tmap_x);
   }
@@ -198,9 +214,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     // the first tile's planes before the (tile-independent) weights: the x planes are written whole by the TMA unit
     // (padding included), so they need no initialisation and their HBM latency overlaps the set-up below
     // (only the first tile: a TMA instruction takes ~100 cycles to issue, and everyone waits for this thread below)
-    if ((int)blockIdx.x < A.tiles) issue_tile(blockIdx.x, 0);
     mbar_arrive_expect_tx(wbar, A.wbytes);
-    bulk_g2s(s_w, A.wpack, A.wbytes, wbar);
+    bulk_g2s(s_w, A.wpack, A.wbytes, wbar);  // (the larger transfer first: the first fprop needs both)
+    if ((int)blockIdx.x < A.tiles) issue_tile(blockIdx.x, 0);
   }
   for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) { s_a[i] = A.a[i]; s_a2[i] = __float2half2_rn(A.a[i]); }
   for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) {
@@ -235,7 +251,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   if (threadIdx.x == 0) LDBGX(1);
 
   if (warp < LF_ATT_WARP0) {
-    setmaxnreg_dec<24>();
+    setmaxnreg_dec<32>();
     if (warp == LF_TMA_WARP && lane == 0) {
       // ===================== TMA issuer: 9 column-plane boxes per tile (the first tile is on its way) ====
       int it = 0, stage = 0;
@@ -276,10 +292,12 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         umma_commit(&empty[wstage]);
         umma_commit(&dwfree[wbuf]);
         { const int it = j; LDBG(8); }
+#ifdef CGAT_LF_TIMELINE
         if (A.dbg != nullptr && A.dbg[255] != 0) {
           mbar_wait(&dwfree[wbuf], bphase);
           { const int it = j; LDBG(3); }
         }
+#endif
         if (++wstage == A.nstg) { wstage = 0; wphase ^= 1u; }
         if (++wbuf == A.ndw) { wbuf = 0; bphase ^= 1u; }
       };
@@ -288,6 +306,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
+        if constexpr (PAIR) {
+          // tile pairs: fprop(p0) fprop(p1) wgrad(p0) fprop(p2) wgrad(p1) ...  The wgrad of pair p-2 goes BEFORE the fprop
+          // of pair p: its d(Wh) buffers are complete by then (pair p-1 is in its math), and the d(Wh) ring (3 buffers)
+          // needs pair p-2's first buffer back before pair p-1 publishes its head exchange
+          if ((it & 1) == 0)
+            while (wj < it - 2) wgrad(wj++);
+        }
         mbar_wait(&full[stage], phase);
         LDBG(4);
         mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
@@ -305,18 +330,15 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         umma_commit(&tfull[acc]);
         LDBG(6);
+#ifdef CGAT_LF_TIMELINE
         if (A.dbg != nullptr && A.dbg[255] != 0) {  // developer probe: execution time of the fprop MMAs in isolation
           mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
           LDBG(2);
         }
+#endif
         if constexpr (!BWD) {
           umma_commit(&empty[stage]);
-        } else if constexpr (PAIR) {
-          // the attention groups work on tile PAIRS: issue both fprops of the next pair before blocking on the
-          // d(Wh) buffers of the previous one
-          if (it & 1)
-            while (wj < it - 1) wgrad(wj++);
-        } else {
+        } else if constexpr (!PAIR) {
           while (wj < it) wgrad(wj++);
         }
         if (++stage == A.nstg) { stage = 0; phase ^= 1u; }
@@ -357,16 +379,24 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         // ============ train mode, two tiles per pass: pixel m of tile A in the low half2 lane, of tile B in the
         // high lane (A, B = consecutive tiles of this CTA, in the two fprop accumulators).  One head per group.
         // All quantities are O(1) in fp16: d(out) is carried WITHOUT its 1/numel factor (out_scale re-applies it
-        // to everything that leaves the kernel). ============
+        // to everything that leaves the kernel).
+        //   * the scores s1, s2 arrive from the fprop MMA (extra output columns W.a); their gradients leave as extra
+        //     rows of the wgrad A operand: no a-terms in registers, no d(a) accumulators (stream_ops.cu finishes them);
+        //   * head exchange: every group publishes ELU(z) of its head (fp16) in the d(Wh) planes, then forms out, the
+        //     loss terms and d(out) for ONE third of the record and publishes that in the (still unused) score-row
+        //     planes: two named barriers per pair, no redundant work between the groups. ============
+        constexpr int CH = REC / 8;                 // 16-byte chunks of a head's record
+        constexpr int SL = (2 * NODES + 7) / 8;     // 8-column loads / 16-byte chunks of a head's scores
         const int k = g;
         cur_head = g;
-        const __half2* a2 = s_a2 + k * 2 * CO;
         const __half2* adj2 = s_adj2 + k * NODES * NODES;
         const __half2 alpha2 = __float2half2_rn(A.alpha);
         const __half2 gs2 = __float2half2_rn(inv_heads);
-        __half2 g2[RG];
+        __half2 g2[NODES * NODES];
 #pragma unroll
-        for (int i = 0; i < RG; ++i) g2[i] = H2::zero();
+        for (int i = 0; i < NODES * NODES; ++i) g2[i] = H2::zero();
+        const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
+        const uint32_t xplane = (uint32_t)A.mchunk * 2048;  // the score-row planes (after the feature planes)
         int itp = 0;
         for (int tileA = blockIdx.x; tileA < A.tiles; tileA += 2 * gridDim.x, ++itp) {
           const int it = 2 * itp;
@@ -392,6 +422,20 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           if (g == 0) {  // the targets of this pair: pull their lines into L2 while the forward runs
             if (validA) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + pixA * REC));
             if (validB) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + pixB * REC));
+          } else if (g == nact - 1) {
+            // the INPUT records of the pair after next (same pixel of tiles +4 and +5): their TMA boxes are requested
+            // about one pair from now and then find the lines in L2 (the TMA round trip is on the pipeline's critical
+            // path: wgrad -> stage free -> TMA -> fprop)
+#pragma unroll
+            for (int ahead = 4; ahead < 6; ++ahead) {
+              const int tile = tileA + ahead * (int)gridDim.x;
+              if (tile < A.tiles) {
+                const int tw = tile % A.tiles_w, th = (tile / A.tiles_w) % A.tiles_h, n = tile / (A.tiles_w * A.tiles_h);
+                const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
+                if (h < A.h && w < A.w)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + (((long long)n * A.h + h) * A.w + w) * A.cin));
+              }
+            }
           }
           mbar_wait(&tfull[0], ph);
           if (hasB) mbar_wait(&tfull[1], ph);
@@ -399,162 +443,184 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           const bool dbg_thread = g == 0 && m == 0;
           if (dbg_thread) LDBG(9);
           __half2 Wh2[NODES][CO];
+          NbState<H2, NODES> st;
           {
-            float ra[REC], rb[REC];
-            const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + LF_FP_COL0 + k * REC;
+            float ra[REC], rb[REC], sa[8 * SL], sb[8 * SL];
+            const uint32_t t_addr = tmem_base + lane_off + LF_FP_COL0 + k * REC;
+            const uint32_t s_addr = tmem_base + lane_off + LF_FP_COL0 + A.cout + k * (8 * SL);
 #pragma unroll
-            for (int q = 0; q < REC / 8; ++q) tmem_ld8_nowait(t_addr + q * 8, &ra[q * 8]);
+            for (int q = 0; q < CH; ++q) tmem_ld8_nowait(t_addr + q * 8, &ra[q * 8]);
+#pragma unroll
+            for (int q = 0; q < SL; ++q) tmem_ld8_nowait(s_addr + q * 8, &sa[q * 8]);
             if (hasB) {
 #pragma unroll
-              for (int q = 0; q < REC / 8; ++q) tmem_ld8_nowait(t_addr + 128 + q * 8, &rb[q * 8]);
+              for (int q = 0; q < CH; ++q) tmem_ld8_nowait(t_addr + 128 + q * 8, &rb[q * 8]);
+#pragma unroll
+              for (int q = 0; q < SL; ++q) tmem_ld8_nowait(s_addr + 128 + q * 8, &sb[q * 8]);
             }
             tmem_ld_wait();
             if (!hasB) {
 #pragma unroll
               for (int i = 0; i < REC; ++i) rb[i] = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8 * SL; ++i) sb[i] = 0.f;
             }
             tc_fence_before();
             mbar_arrive(&tempty[0]);
             if (hasB) mbar_arrive(&tempty[1]);
 #pragma unroll
-            for (int v = 0; v < NODES; ++v)
+            for (int v = 0; v < NODES; ++v) {
 #pragma unroll
               for (int u = 0; u < CO; ++u)
                 Wh2[v][u] = __floats2half2_rn(ra[rec_off<NODES, CO, SPATIAL>(v, u)], rb[rec_off<NODES, CO, SPATIAL>(v, u)]);
+              st.s1[v] = __floats2half2_rn(sa[v], sb[v]);
+              st.s2[v] = __floats2half2_rn(sa[NODES + v], sb[NODES + v]);
+            }
           }
           if (dbg_thread) LDBG(10);
-          NbState<H2, NODES> st;
           __half2 z2[NODES][CO];
-          attn_nb_forward<H2, NODES, CO, MASKED>(Wh2, a2, adj2, s_mask, alpha2, st, z2);
+          attn_nb_forward<H2, NODES, CO, MASKED, true, true>(Wh2, nullptr, adj2, s_mask, alpha2, st, z2);
           if (dbg_thread) LDBG(11);
-          // ---- swap ELU(z) of the three heads through the d(Wh) planes of the two stages (fp16) ----
+          // ---- swap ELU(z) of the three heads through the d(Wh) buffers of the two tiles (fp16) ----
           const uint32_t exA = smem_u32(s_dw) + (uint32_t)bufA * A.dw_bytes + (uint32_t)m * 16;
           const uint32_t exB = smem_u32(s_dw) + (uint32_t)bufB * A.dw_bytes + (uint32_t)m * 16;
           // the wgrad MMAs that read these buffers last time round must have completed
           if (useA > 0) mbar_wait(&dwfree[bufA], (uint32_t)(useA - 1) & 1u);
           if (hasB && useB > 0) mbar_wait(&dwfree[bufB], (uint32_t)(useB - 1) & 1u);
-          {
-            // ELU(z) = max(z, t - 1) with t = exp(min(z, 0)) = ELU'(z): t replaces z (only the derivative is needed later)
-            __half2 o2[REC];
+          // ELU(z) = max(z, t - 1) with t = exp(min(z, 0)) = ELU'(z): t replaces z (only the derivative is needed
+          // later).  One 16-byte chunk of the record at a time: 8 outputs live, not the whole record.
 #pragma unroll
-            for (int v = 0; v < NODES; ++v)
+          for (int q = 0; q < CH; ++q) {
+            __half2 o2[8];
 #pragma unroll
-              for (int u = 0; u < CO; ++u) {
-                if (A.apply_elu) {
-                  const __half2 t = H2::exp(H2::min(z2[v][u], H2::zero()));
-                  o2[rec_off<NODES, CO, SPATIAL>(v, u)] = H2::max(z2[v][u], H2::sub(t, H2::bc(1.f)));
-                  z2[v][u] = t;
-                } else {
-                  o2[rec_off<NODES, CO, SPATIAL>(v, u)] = z2[v][u];
-                  z2[v][u] = H2::bc(1.f);
-                }
+            for (int e = 0; e < 8; ++e) {
+              constexpr int dummy = 0; (void)dummy;
+              const int idx = 8 * q + e;
+              const int v = SPATIAL ? idx % NODES : idx / CO, u = SPATIAL ? idx / NODES : idx % CO;
+              if (A.apply_elu) {
+                const __half2 t = H2::exp(H2::min(z2[v][u], H2::zero()));
+                o2[e] = H2::max(z2[v][u], H2::sub(t, H2::bc(1.f)));
+                z2[v][u] = t;
+              } else {
+                o2[e] = z2[v][u];
+                z2[v][u] = H2::bc(1.f);
               }
-#pragma unroll
-            for (int q = 0; q < REC / 8; ++q) {
-              uint4 va, vb;
-              __half2 t;
-#define LO2(i) (t = __lows2half2(o2[8 * q + (i)], o2[8 * q + (i) + 1]), *reinterpret_cast<uint32_t*>(&t))
-#define HI2(i) (t = __highs2half2(o2[8 * q + (i)], o2[8 * q + (i) + 1]), *reinterpret_cast<uint32_t*>(&t))
-              va.x = LO2(0); va.y = LO2(2); va.z = LO2(4); va.w = LO2(6);
-              vb.x = HI2(0); vb.y = HI2(2); vb.z = HI2(4); vb.w = HI2(6);
+            }
+            uint4 va, vb;
+            __half2 t;
+#define LO2(i) (t = __lows2half2(o2[(i)], o2[(i) + 1]), *reinterpret_cast<uint32_t*>(&t))
+#define HI2(i) (t = __highs2half2(o2[(i)], o2[(i) + 1]), *reinterpret_cast<uint32_t*>(&t))
+            va.x = LO2(0); va.y = LO2(2); va.z = LO2(4); va.w = LO2(6);
+            vb.x = HI2(0); vb.y = HI2(2); vb.z = HI2(4); vb.w = HI2(6);
 #undef LO2
 #undef HI2
-              lf_sts128(exA + (uint32_t)(k * (REC / 8) + q) * 2048, va);
-              if (hasB) lf_sts128(exB + (uint32_t)(k * (REC / 8) + q) * 2048, vb);
-            }
+            lf_sts128(exA + (uint32_t)(k * CH + q) * 2048, va);
+            if (hasB) lf_sts128(exB + (uint32_t)(k * CH + q) * 2048, vb);
           }
           if (dbg_thread) LDBG(15);
-          // the targets of both tiles (L2-resident by now): requested before the barrier, consumed after it
-          uint4 yraw[2][REC / 8];
+          // ---- this group's share of the record (chunks c = g, g + nact, ...): targets requested before the barrier
+          //      (L2-resident by now), consumed after it;  d(out) * numel = 2 (out - y) - lambda in packed fp16 on the
+          //      exchanged words themselves (a word = two consecutive record elements of one tile; every quantity is
+          //      O(1)); the result goes to the score-row planes for everybody.  NC = chunks per group, compile-time so
+          //      that the usual case (as many heads as chunks: one chunk each) holds 2 target words, not 2 * CH ----
+          auto exchange = [&](auto nc_tag) {
+            constexpr int NC = decltype(nc_tag)::value;
+            uint4 yraw[2][NC];
 #pragma unroll
-          for (int half = 0; half < 2; ++half)
+            for (int half = 0; half < 2; ++half)
 #pragma unroll
-            for (int q = 0; q < REC / 8; ++q) {
-              yraw[half][q] = make_uint4(0, 0, 0, 0);
-              if (half ? validB : validA)
-                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(yraw[half][q].x), "=r"(yraw[half][q].y), "=r"(yraw[half][q].z), "=r"(yraw[half][q].w)
-                             : "l"(reinterpret_cast<const uint4*>(A.y + (half ? pixB : pixA) * REC) + q));
-            }
-          named_bar_sync(1, 128 * nact);
-          // ---- d(out) * numel = 2 (out - y) - lambda per tile, in packed fp16 on the exchanged words themselves
-          //      (a word = two consecutive record elements of one tile; every quantity is O(1)).  The loss sums are
-          //      needed once per pixel: group 0 forms them, packed, and widens to fp32 once per tile. ----
-          __half2 dh[2][REC / 2];
+              for (int j = 0; j < NC; ++j) {
+                const int c = g + j * nact;
+                yraw[half][j] = make_uint4(0, 0, 0, 0);
+                if (c < CH && (half ? validB : validA))
+                  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(yraw[half][j].x), "=r"(yraw[half][j].y), "=r"(yraw[half][j].z), "=r"(yraw[half][j].w)
+                               : "l"(reinterpret_cast<const uint4*>(A.y + (half ? pixB : pixA) * REC) + c));
+              }
+            named_bar_sync(1, 128 * nact);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const bool valid = half ? validB : validA;
-            const uint32_t ex = half ? exB : exA;
-            if (half && !hasB) {
+            for (int half = 0; half < 2; ++half) {
+              const bool valid = half ? validB : validA;
+              const uint32_t ex = half ? exB : exA;
+              if (half && !hasB) continue;
+              // dz = d(out)/heads: the mean's 1/heads is folded into the constants
+              const __half2 c2 = __float2half2_rn(valid ? 2.f * inv_heads : 0.f);
+              const __half2 cl = __float2half2_rn(valid ? -A.lambda * inv_heads : 0.f);
+              __half2 ssq = H2::zero(), so = H2::zero();
 #pragma unroll
-              for (int i = 0; i < REC / 2; ++i) dh[half][i] = H2::zero();
-              continue;
-            }
-            __half2 os[REC / 2];
-            for (int kk = 0; kk < A.heads; ++kk) {
+              for (int j = 0; j < NC; ++j) {
+                const int c = g + j * nact;
+                if (c >= CH) continue;
+                __half2 os[4];
+                for (int kk = 0; kk < A.heads; ++kk) {
+                  const uint4 v = lf_lds128(ex + (uint32_t)(kk * CH + c) * 2048);
+                  const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-              for (int q = 0; q < REC / 8; ++q) {
-                const uint4 v = lf_lds128(ex + (uint32_t)(kk * (REC / 8) + q) * 2048);
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                  for (int e = 0; e < 4; ++e) {
+                    const __half2 w = *reinterpret_cast<const __half2*>(&w4[e]);
+                    os[e] = kk == 0 ? w : __hadd2(os[e], w);
+                  }
+                }
+                const uint32_t y4[4] = {yraw[half][j].x, yraw[half][j].y, yraw[half][j].z, yraw[half][j].w};
+                uint32_t d4[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const __half2 w = *reinterpret_cast<const __half2*>(&w4[e]);
-                  os[4 * q + e] = kk == 0 ? w : __hadd2(os[4 * q + e], w);
+                  const __half2 y2 = __floats2half2_rn(__uint_as_float(y4[e] << 16), __uint_as_float(y4[e] & 0xffff0000u));
+                  const __half2 df = __hfma2(os[e], gs2, __hneg2(y2));  // out - y,  out = mean over heads
+                  const __half2 o = __hadd2(df, y2);
+                  const __half2 dh = __hfma2(df, c2, cl);
+                  d4[e] = *reinterpret_cast<const uint32_t*>(&dh);
+                  ssq = __hfma2(df, df, ssq);
+                  so = __hadd2(so, o);
                 }
+                lf_sts128(ex + xplane + (uint32_t)c * 2048, make_uint4(d4[0], d4[1], d4[2], d4[3]));
+              }
+              if (valid) {
+                const float2 a = __half22float2(ssq), b = __half22float2(so);
+                loss_acc += (a.x + a.y) - A.lambda * (b.x + b.y);
+                mse_acc += a.x + a.y;
               }
             }
-            // dz = d(out)/heads: the mean's 1/heads is folded into the constants
-            const __half2 c2 = __float2half2_rn(valid ? 2.f * inv_heads : 0.f);
-            const __half2 cl = __float2half2_rn(valid ? -A.lambda * inv_heads : 0.f);
-            __half2 ssq = H2::zero(), so = H2::zero();
+          };
+          if (nact == CH) exchange(std::integral_constant<int, 1>{});
+          else exchange(std::integral_constant<int, CH>{});
+          named_bar_sync(1, 128 * nact);  // d(out) complete; all heads' ELU words read: the feature planes may take d(Wh)
+          // ---- dz = d(out)/heads * ELU'(z), in place over z2 (which holds ELU'); one record chunk at a time ----
 #pragma unroll
-            for (int i = 0; i < REC / 2; ++i) {
-              const uint32_t yw = reinterpret_cast<const uint32_t*>(&yraw[half][0])[i];  // two bf16 targets
-              const __half2 y2 = __floats2half2_rn(__uint_as_float(yw << 16), __uint_as_float(yw & 0xffff0000u));
-              const __half2 df = __hfma2(os[i], gs2, __hneg2(y2));  // out - y,  out = mean over heads
-              const __half2 o = __hadd2(df, y2);
-              dh[half][i] = __hfma2(df, c2, cl);
-              if (g == 0) {
-                ssq = __hfma2(df, df, ssq);
-                so = __hadd2(so, o);
-              }
-            }
-            if (g == 0 && valid) {
-              const float2 a = __half22float2(ssq), b = __half22float2(so);
-              loss_acc += (a.x + a.y) - A.lambda * (b.x + b.y);
-              mse_acc += a.x + a.y;
+          for (int c = 0; c < CH; ++c) {
+            const uint4 wa = lf_lds128(exA + xplane + (uint32_t)c * 2048);
+            uint4 wb = make_uint4(0, 0, 0, 0);
+            if (hasB) wb = lf_lds128(exB + xplane + (uint32_t)c * 2048);
+            const uint32_t a4[4] = {wa.x, wa.y, wa.z, wa.w}, b4[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int idx = 8 * c + e;
+              const int v = SPATIAL ? idx % NODES : idx / CO, u = SPATIAL ? idx / NODES : idx % CO;
+              // lane A = element idx of tile A, lane B = element idx of tile B
+              const __half2 da = *reinterpret_cast<const __half2*>(&a4[e >> 1]);
+              const __half2 db = *reinterpret_cast<const __half2*>(&b4[e >> 1]);
+              const __half2 ab = (e & 1) ? __highs2half2(da, db) : __lows2half2(da, db);
+              z2[v][u] = __hmul2(ab, z2[v][u]);
             }
           }
-          named_bar_sync(1, 128 * nact);  // all heads read: the planes may now take d(Wh)
+          mbar_arrive(dhread);  // this thread is done with the score-row planes
           if (dbg_thread) LDBG(12);
-          __half2 dz2[NODES][CO];
-#pragma unroll
-          for (int v = 0; v < NODES; ++v)
-#pragma unroll
-            for (int u = 0; u < CO; ++u) {
-              const int o = rec_off<NODES, CO, SPATIAL>(v, u);
-              // lane A = element o of tile A, lane B = element o of tile B
-              const __half2 ab = (o & 1) ? __highs2half2(dh[0][o >> 1], dh[1][o >> 1]) : __lows2half2(dh[0][o >> 1], dh[1][o >> 1]);
-              dz2[v][u] = __hmul2(ab, z2[v][u]);  // z2 holds ELU'(z); the 1/heads of the mean is folded into d
-            }
-          // a / adjacency gradient sums of this thread stay packed across its pairs (O(1) terms, <= 8 pairs per CTA:
+          // adjacency gradient sums of this thread stay packed across its pairs (O(1) terms, <= 8 pairs per CTA:
           // fp16 accumulation error ~1e-3 of a per-thread partial; the 19K partials are then summed in fp32)
-          attn_nb_backward<H2, NODES, CO, MASKED>(Wh2, dz2, a2, adj2, s_mask, alpha2, st, z2, &g2[NODES * NODES], &g2[0]);
+          __half2 ds[2 * NODES];
+          attn_nb_backward_inplace<H2, NODES, CO, MASKED>(Wh2, z2, adj2, s_mask, alpha2, st, &g2[0], ds);  // z2: dz -> d(Wh)
           if (dbg_thread) LDBG(13);
-          // ---- d(Wh) (z2) -> bf16 A planes of the wgrad MMA of both stages ----
+          // ---- d(Wh) (z2) -> bf16 A planes of the wgrad MMA of both tiles ----
           {
-            const uint32_t dyA = exA + (uint32_t)(k * (REC / 8)) * 2048, dyB = exB + (uint32_t)(k * (REC / 8)) * 2048;
-            __half2 r2[REC];
+            const uint32_t dyA = exA + (uint32_t)(k * CH) * 2048, dyB = exB + (uint32_t)(k * CH) * 2048;
 #pragma unroll
-            for (int v = 0; v < NODES; ++v)
-#pragma unroll
-              for (int u = 0; u < CO; ++u) r2[rec_off<NODES, CO, SPATIAL>(v, u)] = z2[v][u];
-#pragma unroll
-            for (int q = 0; q < REC / 8; ++q) {
+            for (int q = 0; q < CH; ++q) {
               float fa[8], fb[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float2 f = __half22float2(r2[8 * q + j]);
+                const int idx = 8 * q + j;
+                const int v = SPATIAL ? idx % NODES : idx / CO, u = SPATIAL ? idx / NODES : idx % CO;
+                const float2 f = __half22float2(z2[v][u]);
                 fa[j] = f.x;
                 fb[j] = f.y;
               }
@@ -567,13 +633,39 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               if (hasB) lf_sts128(dyB + (uint32_t)q * 2048, vb);
             }
           }
+          // ---- score gradients ds1 | ds2 (| zero padding) -> this head's score-row planes, once every group has read d(out)
+          mbar_wait(dhread, ph);
+          {
+            const uint32_t syA = exA + xplane + (uint32_t)(k * SL) * 2048, syB = exB + xplane + (uint32_t)(k * SL) * 2048;
+#pragma unroll
+            for (int q = 0; q < SL; ++q) {
+              float fa[8], fb[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                fa[j] = 0.f;
+                fb[j] = 0.f;
+                if (8 * q + j < 2 * NODES) {
+                  const float2 f = __half22float2(ds[8 * q + j]);
+                  fa[j] = f.x;
+                  fb[j] = f.y;
+                }
+              }
+              uint4 va, vb;
+              va.x = pack_bf16x2(fa[0], fa[1]); va.y = pack_bf16x2(fa[2], fa[3]);
+              va.z = pack_bf16x2(fa[4], fa[5]); va.w = pack_bf16x2(fa[6], fa[7]);
+              vb.x = pack_bf16x2(fb[0], fb[1]); vb.y = pack_bf16x2(fb[2], fb[3]);
+              vb.z = pack_bf16x2(fb[4], fb[5]); vb.w = pack_bf16x2(fb[6], fb[7]);
+              lf_sts128(syA + (uint32_t)q * 2048, va);
+              if (hasB) lf_sts128(syB + (uint32_t)q * 2048, vb);
+            }
+          }
           fence_proxy_async_smem();
           mbar_arrive(&dyfull[bufA]);
           if (hasB) mbar_arrive(&dyfull[bufB]);
           if (dbg_thread) LDBG(14);
         }
 #pragma unroll
-        for (int i = 0; i < RG; ++i) {
+        for (int i = 0; i < NODES * NODES; ++i) {
           const float2 f = __half22float2(g2[i]);
           gacc[i] += f.x + f.y;
         }
@@ -835,7 +927,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         for (int c0 = g * 16; c0 < A.nt; c0 += nact * 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
-          if (m < A.cout) {
+          if (m < A.cout + A.ext) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               reinterpret_cast<float4*>(prow + c0)[i] = make_float4(v[4 * i] * A.out_scale, v[4 * i + 1] * A.out_scale,
@@ -872,16 +964,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     tmem_dealloc(tmem_base, 512);
   }
   if (threadIdx.x == 0) LDBGX(8);
+#ifdef CGAT_LF_TIMELINE
   if (threadIdx.x == 0 && A.dbg != nullptr) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     A.dbg[256 + 2 * blockIdx.x + 1] = (long long)t;
   }
+#endif
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
 struct LfGeom {
-  int cin, cout, rec, nchunk, nq, npad, mchunk, nt;
+  int cin, cout, ext, rec, nchunk, nq, npad, mchunk, nt;
   uint32_t wbytes, stage_bytes, dw_bytes;
   size_t smem;
   int tiles_h, tiles_w, tiles, nstg, ndw;
@@ -894,12 +988,16 @@ static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
   g.cout = d->heads * g.rec;
   g.nchunk = g.cin / 8;
   g.nq = 3 * g.nchunk + 1;            // column planes per stage, the last one all ones
-  g.npad = (g.cout + 15) & ~15;
+  g.ext = lf_score_rows(d->nodes, d->co, d->heads);  // score rows W.a behind the feature rows (common.cuh)
+  g.npad = (g.cout + g.ext + 15) & ~15;
   g.mchunk = g.cout / 8;
   g.nt = 3 * g.nq * 8;                // wgrad partial columns: [r][(s,c) | ones][8]
   g.wbytes = (uint32_t)(3 * g.nq) * g.npad * 16;
   g.stage_bytes = ((uint32_t)g.nq * LF_PLANE + 127u) & ~127u;
-  g.dw_bytes = bwd ? (uint32_t)g.mchunk * 2048 : 0;
+  // a d(Wh) buffer: feature planes, then the score-row planes -- at least rec/8 of them: the train kernel passes d(out)
+  // between the head groups through them
+  const int xplanes = g.ext / 8 > g.rec / 8 ? g.ext / 8 : g.rec / 8;
+  g.dw_bytes = bwd ? (uint32_t)(g.mchunk + xplanes) * 2048 : 0;
   g.nstg = LF_MAXSTG;
   g.ndw = bwd ? LF_MAXDW : 0;
   auto total = [&]() {
@@ -931,7 +1029,7 @@ int layer_supported(const cgat_layer_desc* d) {
   const bool shape_ok = (sp && d->nodes == 6 && d->ci == 4 && d->co == 4) || (!sp && d->nodes == 4 && d->ci == 6 && d->co == 6);
   if (!shape_ok) return 0;
   const LfGeom f = lf_geom(d, false), b = lf_geom(d, true);
-  if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.nt > 256) return 0;
+  if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.npad > 128 || f.nt > 256) return 0;
   if (f.nq % 2) return 0;  // fprop consumes the planes (+ the ones plane) in pairs: K = 16 per tcgen05.mma
   if (f.smem > 227 * 1024 || b.smem > 227 * 1024) return 0;
   return 1;
@@ -939,7 +1037,8 @@ int layer_supported(const cgat_layer_desc* d) {
 
 size_t layer_partial_bytes(const cgat_layer_desc* d) {
   const LfGeom g = lf_geom(d, true);
-  return (size_t)148 * 128 * g.nt * sizeof(float);
+  // one slot per CTA plus one: cgat_stream_param_grads sums the slots into the one behind them (stream_ops.cu)
+  return (size_t)(148 + 1) * 128 * g.nt * sizeof(float);
 }
 
 // 4-D map over NHWC bf16 [n][h][w][c], box (8, wp, hp, 1): lands as [hp][wp][16 B]; out-of-image = zero (conv padding)
@@ -994,6 +1093,7 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, LF_TW, LF_PR)) return rc;
   LfArgs A{};
   A.dbg = g_lf_dbg;
+  A.x = (const __nv_bfloat16*)x;
   A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
   A.out = (__nv_bfloat16*)out; A.dout = (const __nv_bfloat16*)dout; A.dwh = (__nv_bfloat16*)dwh;
   A.partial = partial; A.ga = ga; A.gadj = gadj;
@@ -1001,8 +1101,9 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
   // the paired half2 kernel carries d(out) without its 1/numel factor; CGAT_NO_PAIR=1 keeps the fp32 one-tile kernel
   static const bool no_pair = std::getenv("CGAT_NO_PAIR") != nullptr;
-  A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && d->heads <= LF_GROUPS && !no_pair) ? A.inv_n : 1.f;
-  A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
+  A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && g.ndw >= 2 && g.ext > 0 && d->heads <= LF_GROUPS && !no_pair)
+                    ? A.inv_n : 1.f;
+  A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.ext = g.ext; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
   A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt;
   A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.nstg = g.nstg; A.ndw = g.ndw;

@@ -18,6 +18,7 @@ struct MutPtrArr { float* p[SO_MAX_HEADS]; };
 struct StreamGeom {
   int nodes, ci, co, heads, spatial;
   int cin, cout;          // dense conv channels: nodes*ci, heads*nodes*co
+  int sph, ext;           // fused layer kernels: score rows per head / in total behind the cout feature rows (0: none)
   int taps;               // 9 (3x3) for the conv mapping
   int nchunk, npairs, npad;        // fprop packing (conv_tc.cu: chunk-major K order)
   int d_nchunk, d_npairs, d_npad;  // dgrad packing (GEMM-K = cout, GEMM-N = cin)
@@ -31,7 +32,9 @@ __host__ __device__ inline StreamGeom make_geom(const cgat_stream_desc& d) {
   g.taps = 9;
   g.nchunk = g.cin / 8;
   g.npairs = (g.nchunk * g.taps + 1) / 2;
-  g.npad = (g.cout + 15) & ~15;
+  g.sph = lf_score_rows_per_head(d.nodes);
+  g.ext = d.wgrad_cols ? lf_score_rows(d.nodes, d.co, d.heads) : 0;
+  g.npad = (g.cout + g.ext + 15) & ~15;
   g.d_nchunk = g.cout / 8;
   g.d_npairs = (g.d_nchunk * g.taps + 1) / 2;
   g.d_npad = (g.cin + 15) & ~15;
@@ -56,6 +59,28 @@ __device__ __forceinline__ float dense_w(const StreamGeom& g, const PtrArr& w, i
   rec_inv(g.spatial, g.nodes, g.ci, cin_idx, node2, c);
   if (node != node2) return 0.f;
   return w.p[k][(u * g.ci + c) * g.taps + tap];  // conv.weight [co][ci][3][3]
+}
+
+// score rows behind the feature rows (fused layer kernels): row = cout + k*sph + j, j < nodes: s1 of node j, else s2 of
+// node j - nodes;  value = sum_u a[k][which*co + u] * w[k][u][c][tap] on the node's own input channels
+__device__ __forceinline__ bool score_row(const StreamGeom& g, int row, int& k, int& which, int& node) {
+  const int rs = row - g.cout;
+  if (rs < 0 || rs >= g.ext) return false;
+  k = rs / g.sph;
+  const int j = rs - k * g.sph;
+  if (j >= 2 * g.nodes) return false;
+  which = j / g.nodes;
+  node = j - which * g.nodes;
+  return true;
+}
+__device__ __forceinline__ float dense_ws(const StreamGeom& g, const PtrArr& w, const PtrArr& a, int row, int tap, int cin_idx) {
+  int k, which, node, node2, c;
+  if (cin_idx >= g.cin || !score_row(g, row, k, which, node)) return 0.f;
+  rec_inv(g.spatial, g.nodes, g.ci, cin_idx, node2, c);
+  if (node != node2) return 0.f;
+  float v = 0.f;
+  for (int u = 0; u < g.co; ++u) v = fmaf(a.p[k][which * g.co + u], w.p[k][(u * g.ci + c) * g.taps + tap], v);
+  return v;
 }
 
 struct PrepArgs {
@@ -105,13 +130,18 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepA
       float v = 0.f;
       if (q < nq - 1) {
         const int s = q / g.nchunk, c = q - s * g.nchunk;
-        v = dense_w(g, A.w, row, r * 3 + s, c * 8 + e);
-      } else if (r == 0 && row < g.cout && e < 2) {
-        const int per_head = g.nodes * g.co;
-        const int k = row / per_head;
-        int node, u;
-        rec_inv(g.spatial, g.nodes, g.co, row - k * per_head, node, u);
-        const float b = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
+        v = row < g.cout ? dense_w(g, A.w, row, r * 3 + s, c * 8 + e) : dense_ws(g, A.w, A.a, row, r * 3 + s, c * 8 + e);
+      } else if (r == 0 && e < 2) {
+        float b = 0.f;
+        int k, which, node, u;
+        if (row < g.cout) {
+          const int per_head = g.nodes * g.co;
+          k = row / per_head;
+          rec_inv(g.spatial, g.nodes, g.co, row - k * per_head, node, u);
+          b = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
+        } else if (score_row(g, row, k, which, node) && A.bias.p[k]) {
+          for (u = 0; u < g.co; ++u) b = fmaf(A.a.p[k][which * g.co + u], A.bias.p[k][u], b);
+        }
         const float hi = __bfloat162float(__float2bfloat16_rn(b));
         v = e == 0 ? hi : b - hi;
       }
@@ -152,7 +182,7 @@ struct GradArgs {
   const float* gW_lin;      // linear: [heads][ci][co]
   const float* ga;          // [heads][2co]
   const float* gadj;        // [heads][nodes][nodes]
-  PtrArr B;
+  PtrArr B, w, bias, a;     // parameters (w, bias, a: only read when the partials carry score rows)
   MutPtrArr g_w, g_bias, g_a, g_B;
   int accumulate;
 };
@@ -168,9 +198,12 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
   const int nb = gridDim.x - g.heads;
   const int b = blockIdx.x - g.heads;
   const long long tid = (long long)b * blockDim.x + threadIdx.x, nt = (long long)nb * blockDim.x;
-  for (long long i = tid; i < g.heads * 2 * g.co; i += nt) {
-    float* dst = A.g_a.p[i / (2 * g.co)] + i % (2 * g.co);
-    *dst = A.accumulate ? *dst + A.ga[i] : A.ga[i];
+  const bool ext = A.d.mapping == 1 && g.ext > 0;  // score rows present: d(a) is finished below, from the partials
+  if (!ext) {
+    for (long long i = tid; i < g.heads * 2 * g.co; i += nt) {
+      float* dst = A.g_a.p[i / (2 * g.co)] + i % (2 * g.co);
+      *dst = A.accumulate ? *dst + A.ga[i] : A.ga[i];
+    }
   }
   if (A.d.mapping == 0) {
     for (long long i = tid; i < (long long)g.heads * g.ci * g.co; i += nt) {
@@ -184,51 +217,109 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
   // lane and node, all issued before anything is added, so a block pays the L2 latency once (a warp per output walked
   // it once per node and 32-CTA batch: 10.6 us under ncu) -- then the 8 warp sums are added in a fixed order:
   // deterministic, identical on every rank.
+  //
+  // Score rows (fused layer kernels, g.ext > 0): the kernel's d(Wh) rows do NOT contain the terms through the scores
+  // s = Wh.a; instead the partials carry  G_which[k][node][tap][c] = d(W.a_which)  in the rows behind the features:
+  //   dW[k][u][c][tap] += a1[k][u] G1 + a2[k][u] G2        (same for the bias with the ones column)
+  //   d(a_which)[k][u]  = sum_{node,tap,c} w[k][u][c][tap] G_which + bias[k][u] G_which(ones)     (+ ga from the kernel)
   __shared__ float wsum[ADJ_THREADS / 32];
   const int nwe = g.co * g.ci * g.taps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = ADJ_THREADS / 32;
-  for (long long i = b; i < (long long)g.heads * (nwe + g.co); i += nb) {
-    const int k = (int)(i / (nwe + g.co));
-    const int r = (int)(i - (long long)k * (nwe + g.co));
-    int u, c = 0, tap = 0;
-    float* dst;
-    if (r < nwe) {
-      tap = r % g.taps;
-      c = (r / g.taps) % g.ci;
-      u = r / (g.taps * g.ci);
-      dst = A.g_w.p[k] + r;
-    } else {
-      u = r - nwe;
-      dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
+  const int per_k = nwe + g.co + (ext ? 2 * g.co : 0);
+  const size_t cta_stride = (size_t)128 * A.nt;
+  const int nq = 3 * g.nchunk + 1;
+  auto column = [&](int tap, int ci_idx) {  // column of (tap, dense input channel); tap < 0: the ones (bias) column
+    if (A.d.wgrad_cols) {  // layer_fused.cu: [r][(s, cin chunk) | ones][8]; dbias is the ones column of r = 0
+      if (tap < 0) return (nq - 1) * 8;
+      return ((tap / 3) * nq + (tap % 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
     }
-    if (dst == nullptr) continue;  // block-uniform
+    return tap < 0 ? g.taps * g.cin : tap * g.cin + ci_idx;
+  };
+  // this thread's CTA (warp w takes the CTAs w, w+8, ...: at most one per lane with <= 256 partial tiles)
+  const int my_cta = warp + NW * lane;
+  const float* my_part = A.wg_partial + (size_t)(my_cta < A.ncta ? my_cta : 0) * cta_stride;
+  const bool have = my_cta < A.ncta;
+  for (long long i = b; i < (long long)g.heads * per_k; i += nb) {
+    const int k = (int)(i / per_k);
+    const int r = (int)(i - (long long)k * per_k);
+    float* dst;
     float acc = 0.f;
-    const size_t cta_stride = (size_t)128 * A.nt;
-    for (int node0 = 0; node0 < g.nodes; node0 += 4) {
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[j] = 0.f;
-        const int node = node0 + j;
-        if (node >= g.nodes) continue;
-        const int row = k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u);
-        int col;
-        if (A.d.wgrad_cols) {  // layer_fused.cu: [r][(s, cin chunk) | ones][8]; dbias is the ones column of r = 0
-          const int nq = 3 * g.nchunk + 1;
-          col = (nq - 1) * 8;
-          if (r < nwe) {
-            const int ci_idx = rec_of(g.spatial, g.nodes, g.ci, node, c);
-            col = ((tap / 3) * nq + (tap % 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
-          }
-        } else {
-          col = g.taps * g.cin;
-          if (r < nwe) col = tap * g.cin + rec_of(g.spatial, g.nodes, g.ci, node, c);
-        }
-        const float* src = A.wg_partial + (size_t)row * A.nt + col;
-        for (int cta = warp + NW * lane; cta < A.ncta; cta += NW * 32) v[j] += __ldcg(src + (size_t)cta * cta_stride);
+    if (r < nwe + g.co) {
+      int u, c = 0, tap = -1;
+      if (r < nwe) {
+        tap = r % g.taps;
+        c = (r / g.taps) % g.ci;
+        u = r / (g.taps * g.ci);
+        dst = A.g_w.p[k] + r;
+      } else {
+        u = r - nwe;
+        dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
       }
-      acc += (v[0] + v[1]) + (v[2] + v[3]);
+      if (dst == nullptr) continue;  // block-uniform
+      const float a1 = ext ? A.a.p[k][u] : 0.f, a2 = ext ? A.a.p[k][g.co + u] : 0.f;
+      // all loads of a batch of 4 nodes are issued before anything is added: a block pays the L2 latency once
+      for (int node0 = 0; node0 < g.nodes; node0 += 4) {
+        float v[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j][0] = v[j][1] = v[j][2] = 0.f;
+          const int node = node0 + j;
+          if (node >= g.nodes || !have) continue;
+          const int col = column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c));
+          v[j][0] = __ldcg(my_part + (size_t)(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u)) * A.nt + col);
+          if (ext) {
+            const int rs = g.cout + k * g.sph + node;
+            v[j][1] = __ldcg(my_part + (size_t)rs * A.nt + col);
+            v[j][2] = __ldcg(my_part + (size_t)(rs + g.nodes) * A.nt + col);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc += fmaf(a2, v[j][2], fmaf(a1, v[j][1], v[j][0]));
+      }
+      for (int cta = my_cta + NW * 32; cta < A.ncta; cta += NW * 32) {  // more than 256 partial tiles (not on B200)
+        for (int node = 0; node < g.nodes; ++node) {
+          const float* part = A.wg_partial + (size_t)cta * cta_stride;
+          const int col = column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c));
+          acc += __ldcg(part + (size_t)(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u)) * A.nt + col);
+          if (ext) {
+            const int rs = g.cout + k * g.sph + node;
+            acc = fmaf(a1, __ldcg(part + (size_t)rs * A.nt + col), acc);
+            acc = fmaf(a2, __ldcg(part + (size_t)(rs + g.nodes) * A.nt + col), acc);
+          }
+        }
+      }
+    } else {
+      // d(a)[which*co + u] = sum_{node, tap, c} w[k][u][c][tap] G_which[k][node][tap][c] + bias[k][u] G_which(ones):
+      // taps*ci + 1 terms per node and CTA, loaded in batches of 8 before they are used
+      const int j0 = r - nwe - g.co, which = j0 / g.co, u = j0 - which * g.co;
+      dst = A.g_a.p[k] + j0;
+      const int nterm = g.taps * g.ci + 1;
+      for (int cta = my_cta; cta < A.ncta; cta += NW * 32) {
+        const float* part = A.wg_partial + (size_t)cta * cta_stride;
+        for (int node = 0; node < g.nodes; ++node) {
+          const float* prow = part + (size_t)(g.cout + k * g.sph + which * g.nodes + node) * A.nt;
+          for (int t0 = 0; t0 < nterm; t0 += 8) {
+            float v[8], wv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int t = t0 + j;
+              v[j] = 0.f;
+              wv[j] = 0.f;
+              if (t < nterm - 1) {
+                const int tap = t % g.taps, c = t / g.taps;
+                v[j] = __ldcg(prow + column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c)));
+                wv[j] = A.w.p[k][(u * g.ci + c) * g.taps + tap];
+              } else if (t == nterm - 1 && A.bias.p[k]) {
+                v[j] = __ldcg(prow + column(-1, 0));
+                wv[j] = A.bias.p[k][u];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(wv[j], v[j], acc);
+          }
+        }
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) wsum[warp] = acc;
@@ -237,9 +328,108 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < NW; ++w) t += wsum[w];
+      if (r >= nwe + g.co) t += A.ga[k * 2 * g.co + (r - nwe - g.co)];  // whatever the kernel accumulated itself
       *dst = A.accumulate ? *dst + t : t;
     }
     __syncthreads();
+  }
+}
+
+// ---- fused layer kernels (wgrad_cols = 1): the partial sums are first added over the CTAs, coalesced and in a fixed
+// order, into the slot behind them; the parameter gradients are then finished from that one [128][nt] matrix ----------
+constexpr int RED_OUT = 64, RED_SPLIT = 4;  // outputs per block x CTA groups per output (256 threads)
+__global__ void __launch_bounds__(RED_OUT * RED_SPLIT)
+wgrad_partial_reduce_kernel(const float* __restrict__ part, int ncta, int n, size_t cta_stride, float* __restrict__ out) {
+  __shared__ float s[RED_SPLIT][RED_OUT];
+  const int o = threadIdx.x % RED_OUT, grp = threadIdx.x / RED_OUT;
+  const int i = blockIdx.x * RED_OUT + o;
+  float acc = 0.f;
+  if (i < n) {
+    const int per = (ncta + RED_SPLIT - 1) / RED_SPLIT;
+    const int c0 = grp * per, c1 = min(ncta, c0 + per);
+    const float* p = part + i;
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {  // 8 independent loads in flight
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcg(p + (size_t)(c + j) * cta_stride);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    for (; c < c1; ++c) acc += __ldcg(p + (size_t)c * cta_stride);
+  }
+  s[grp][o] = acc;
+  __syncthreads();
+  if (grp == 0 && i < n) out[i] = (s[0][o] + s[1][o]) + (s[2][o] + s[3][o]);
+}
+
+// One WARP per output from the reduced matrix R [128][nt]; same algebra as stream_param_grads_kernel (see there).
+__global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel(const GradArgs A) {
+  const StreamGeom g = make_geom(A.d);
+  if ((int)blockIdx.x < g.heads) {
+    const int k = blockIdx.x;
+    adj_norm_bwd_block(A.B.p[k], A.gadj + (size_t)k * g.nodes * g.nodes, A.g_B.p[k], g.nodes, A.d.transpose_adj, 0,
+                       A.accumulate);
+    return;
+  }
+  const bool ext = g.ext > 0;
+  const int nwe = g.co * g.ci * g.taps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per_k = nwe + g.co + 2 * g.co;
+  const int nq = 3 * g.nchunk + 1;
+  const float* R = A.wg_partial;
+  auto column = [&](int tap, int ci_idx) {  // [r][(s, cin chunk) | ones][8]; tap < 0: the ones (bias) column of r = 0
+    if (tap < 0) return (nq - 1) * 8;
+    return ((tap / 3) * nq + (tap % 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
+  };
+  const long long nout = (long long)g.heads * per_k;
+  for (long long i = (long long)(blockIdx.x - g.heads) * (ADJ_THREADS / 32) + warp; i < nout;
+       i += (long long)(gridDim.x - g.heads) * (ADJ_THREADS / 32)) {
+    const int k = (int)(i / per_k);
+    const int r = (int)(i - (long long)k * per_k);
+    float* dst;
+    float acc = 0.f;
+    if (r < nwe + g.co) {
+      int u, c = 0, tap = -1;
+      if (r < nwe) {
+        tap = r % g.taps;
+        c = (r / g.taps) % g.ci;
+        u = r / (g.taps * g.ci);
+        dst = A.g_w.p[k] + r;
+      } else {
+        u = r - nwe;
+        dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
+      }
+      if (dst == nullptr) continue;  // warp-uniform
+      if (lane < g.nodes) {  // lane = node
+        const int col = column(tap, rec_of(g.spatial, g.nodes, g.ci, lane, c));
+        acc = R[(size_t)(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, lane, u)) * A.nt + col];
+        if (ext) {
+          const int rs = g.cout + k * g.sph + lane;
+          acc = fmaf(A.a.p[k][u], R[(size_t)rs * A.nt + col], acc);
+          acc = fmaf(A.a.p[k][g.co + u], R[(size_t)(rs + g.nodes) * A.nt + col], acc);
+        }
+      }
+    } else {
+      const int j0 = r - nwe - g.co, which = j0 / g.co, u = j0 - which * g.co;  // d(a)[which*co + u]
+      dst = A.g_a.p[k] + j0;
+      if (ext) {
+        const int nterm = g.taps * g.ci + 1;
+        for (int t = lane; t < g.nodes * nterm; t += 32) {
+          const int node = t / nterm, tt = t - node * nterm;
+          const float* prow = R + (size_t)(g.cout + k * g.sph + which * g.nodes + node) * A.nt;
+          if (tt < nterm - 1) {
+            const int tap = tt % g.taps, c = tt / g.taps;
+            acc = fmaf(A.w.p[k][(u * g.ci + c) * g.taps + tap], prow[column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c))], acc);
+          } else if (A.bias.p[k]) {
+            acc = fmaf(A.bias.p[k][u], prow[column(-1, 0)], acc);
+          }
+        }
+      }
+      if (lane == 0) acc += A.ga[k * 2 * g.co + j0];  // whatever the kernel accumulated itself (no score rows: all of it)
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) *dst = A.accumulate ? *dst + acc : acc;
   }
 }
 
@@ -297,10 +487,13 @@ extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const
 
 extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt,
                                        const float* gW_lin, const float* ga, const float* gadj, const float* const* B,
+                                       const float* const* w, const float* const* bias, const float* const* a,
                                        float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
                                        int accumulate, void* stream) {
   if (int rc = check_desc(d)) return rc;
   if (!ga || !gadj || !B || !g_w || !g_a || !g_B) return fail(CGAT_EINVAL, "null argument");
+  const bool ext = d->mapping == 1 && make_geom(*d).ext > 0;
+  if (ext && (!w || !a)) return fail(CGAT_EINVAL, "the fused layer kernels' partials carry score rows: w and a are needed");
   if (d->mapping == 1 && (!wg_partial || ncta < 1 || nt < 1)) return fail(CGAT_EINVAL, "conv mapping needs wgrad partials");
   if (d->mapping == 0 && !gW_lin) return fail(CGAT_EINVAL, "linear mapping needs gW");
   GradArgs A{};
@@ -308,6 +501,9 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
   A.wg_partial = wg_partial; A.ncta = ncta; A.nt = nt; A.gW_lin = gW_lin; A.ga = ga; A.gadj = gadj;
   for (int k = 0; k < d->heads; ++k) {
     A.B.p[k] = B[k];
+    A.w.p[k] = w ? w[k] : nullptr;
+    A.bias.p[k] = bias ? bias[k] : nullptr;
+    A.a.p[k] = a ? a[k] : nullptr;
     A.g_w.p[k] = g_w[k];
     A.g_bias.p[k] = g_bias ? g_bias[k] : nullptr;
     A.g_a.p[k] = g_a[k];
@@ -315,7 +511,25 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
   }
   A.accumulate = accumulate;
   const StreamGeom g = make_geom(*d);
-  const long long work = d->mapping == 1 ? (long long)g.heads * (g.co * g.ci * g.taps + g.co) : (long long)g.heads * g.ci * g.co;
+  if (d->mapping == 1 && d->wgrad_cols) {
+    // fused layer kernels: sum the CTA slots into the slot behind them (the workspace of cgat_layer_* has it), then
+    // one warp per output from the reduced matrix
+    const size_t cta_stride = (size_t)128 * nt;
+    const int nred = (g.cout + g.ext) * nt;
+    float* R = const_cast<float*>(wg_partial) + (size_t)ncta * cta_stride;
+    wgrad_partial_reduce_kernel<<<(nred + RED_OUT - 1) / RED_OUT, RED_OUT * RED_SPLIT, 0, (cudaStream_t)stream>>>(
+        wg_partial, ncta, nred, cta_stride, R);
+    if (int rc = check_launch("wgrad_partial_reduce_kernel")) return rc;
+    A.wg_partial = R;
+    A.ncta = 1;
+    const long long nout = (long long)g.heads * (g.co * g.ci * g.taps + 3 * g.co);
+    int blocks = (int)((nout + ADJ_THREADS / 32 - 1) / (ADJ_THREADS / 32));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    stream_param_grads_reduced_kernel<<<d->heads + blocks, ADJ_THREADS, 0, (cudaStream_t)stream>>>(A);
+    return check_launch("stream_param_grads_reduced_kernel");
+  }
+  const long long work = d->mapping == 1 ? (long long)g.heads * (g.co * g.ci * g.taps + g.co + (ext ? 2 * g.co : 0))
+                                         : (long long)g.heads * g.ci * g.co;
   // conv mapping: one block per output (see the kernel); linear: one thread per element
   int blocks = d->mapping == 1 ? (int)work : (int)((work + ADJ_THREADS - 1) / ADJ_THREADS);
   if (blocks < 1) blocks = 1;

@@ -151,8 +151,10 @@ typedef struct cgat_stream_desc {
   int32_t layout;        /* CGAT_LAYOUT_*                                  */
   int32_t mapping;       /* 0 linear, 1 conv 3x3 pad 1                      */
   int32_t transpose_adj; /* 1: the 1-D layer's A_hat^T (baseline_model.py:53) */
-  int32_t wgrad_cols;    /* column order of the wgrad partial sums handed to cgat_stream_param_grads:
-                            0 = [tap][cin] (cgat_conv2d_wgrad_partial), 1 = [cin/8][tap][8] (cgat_layer_bwd) */
+  int32_t wgrad_cols;    /* 0: conv_tc packing, wgrad partial columns [tap][cin] (cgat_conv2d_wgrad_partial);
+                            1: fused layer kernels (cgat_layer_*): K order (r; s, cin/8), partial columns
+                               [r][(s, cin/8) | ones][8], and -- while heads*(nodes*co + 2*nodes rounded up to 8) <= 128 --
+                               score rows W.a behind the heads*nodes*co feature rows (see cgat_stream_param_grads)  */
 } cgat_stream_desc;
 
 /* bytes of the packed bf16 weight buffer of the block-diagonal dense conv (dgrad != 0: the dgrad packing) */
@@ -163,9 +165,13 @@ int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const 
                         const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
                         float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* stream);
 /* ONE launch: per-head parameter gradients from the kernels' accumulators (wgrad partials or gW, ga, gadj);
- * accumulate != 0 adds into g_* (e.g. the parameters' .grad buffers) instead of overwriting.                  */
+ * accumulate != 0 adds into g_* (e.g. the parameters' .grad buffers) instead of overwriting.  w, bias, a: the same
+ * per-head parameter pointers cgat_stream_prepare took; read only when wgrad_cols = 1 and the partials carry the score
+ * rows d(W.a) of the fused layer kernels (then  dW += a (x) d(W.a)  and  d(a) = <W, d(W.a)>  are formed here); may be
+ * NULL otherwise.                                                                                               */
 int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* gW_lin,
-                            const float* ga, const float* gadj, const float* const* B, float* const* g_w,
+                            const float* ga, const float* gadj, const float* const* B, const float* const* w,
+                            const float* const* bias, const float* const* a, float* const* g_w,
                             float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate, void* stream);
 
 /* K6 / K7  one conv-mapped stream of the conv-GAT layer (shared 3x3 node conv, pad 1, + graph attention) as ONE
@@ -177,7 +183,8 @@ int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, 
  *   out    [n][h][w][nodes*co] (MERGE_MEAN) or the concat layout of cgat_attn_fwd
  *   dwh    optional (may be NULL): d(Wh) [n][h][w][heads*nodes*co] for cgat_conv2d_dgrad_packed
  *   workspace  cgat_layer_workspace_bytes(d) bytes: per-CTA wgrad partial sums [ncta][128][nt], column order
- *              [cin/8][tap][8] then the dbias column (cgat_stream_desc.wgrad_cols = 1)
+ *              [r][(s, cin/8) | ones][8] (cgat_stream_desc.wgrad_cols = 1), plus one more [128][nt] slot that
+ *              cgat_stream_param_grads uses as its reduction scratch (it WRITES slot `ncta` of this buffer)
  *   ga [heads][2co], gadj [heads][nodes][nodes]     fp32, ACCUMULATED INTO                                      */
 typedef struct cgat_layer_desc {
   int32_t n, h, w;
