@@ -242,8 +242,9 @@ def workload_config(args, per_gpu_batch):
                     f"3 heads, x,y [{per_gpu_batch},{H},{W},{T},{V}] per GPU (BASELINE.json configs[1])",
         "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "image": [H, W], "time_steps": T,
         "n_vertices": V, "parallelism": f"dp{args.gpus}",
-        "l2": ("inputs larger than L2: the steps rotate over 4 input slots of x, y (4 x 50 MB = 201 MB > 126 MB L2), K steps "
-               "inside ONE event pair, no flush" if args.l2 == "rotate" else
+        "l2": ("inputs larger than L2: the steps rotate over 8 input slots of x, y (8 x 25.2 MB = 201 MB > 126 MB L2), K steps "
+               "inside ONE event pair, no flush; x resident chunk-planar [N,T*V/8,H,W,8] as the loader kernel writes it, "
+               "y [N,H,W,T,V]" if args.l2 == "rotate" else
                "flushed between timed steps (256 MiB memset outside the per-step event pairs)"),
         "optimizer": "Adam(lr=1e-3, weight_decay=0.01) fused, flat fp32 buffers", "cuda_graph": True,
     }
@@ -326,15 +327,16 @@ def run_ours(args):
         sampler.start()
     # ---- device-resident throughput ----
     if args.l2 == "rotate":
-        # inputs larger than L2: four slots of x, y (own buffers, own captured graph each); by the time a slot comes
-        # round again 150 MB of other inputs have passed through the 126 MB L2.  One event pair around the K steps: the
+        # inputs larger than L2: eight slots of x, y (own buffers, own captured graph each; 25.2 MB of bf16 per slot); by
+        # the time a slot comes round again 176 MB of other inputs have passed through the 126 MB L2.  One event pair around the K steps: the
         # ranks of a data-parallel run stay in step through the gradient exchange alone (per-step flushes end at
         # slightly different times on every rank, and the max over ranks then counts that jitter as step time).
-        NS = 4
+        NS = 8
         ts.enable_prefetch(NS)
         for i, sl in enumerate(ts._slots[1:], 1):
             sl["x"].copy_(torch.roll(x, i, 0))
             sl["y"].copy_(torch.roll(y, i, 0))
+            ts.refresh_planar(i)  # the resident input format of the train kernel (what the loader kernel writes)
         torch.cuda.synchronize()
 
         host_enqueue = [None]
@@ -404,7 +406,7 @@ def run_ours(args):
     e2e_xy_ms = e2e_time(False)
     e2e_ms = e2e_time(True)
     ts.graph = ts._slots[0]["graph"]
-    ts.x, ts.y = ts._slots[0]["x"], ts._slots[0]["y"]
+    ts.x, ts.y, ts.xp = ts._slots[0]["x"], ts._slots[0]["y"], ts._slots[0]["xp"]
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss_host[args.steps - 1].item())
 
@@ -417,7 +419,10 @@ def run_ours(args):
     frames_d, start_d = frames_h.to(dev), start_h.to(dev)
     for _ in range(max(3, min(args.steps, 10))):
         flush.zero_()
-        gather_windows(frames_d, start_d, steps=T, out=(ts.x, ts.y))  # the e2e path's per-step loader kernel
+        if ts.xp is not None:  # the e2e path's per-step loader kernel
+            gather_windows(frames_d, start_d, steps=T, out=(ts.xp, ts.y), planar=True)
+        else:
+            gather_windows(frames_d, start_d, steps=T, out=(ts.x, ts.y))
         ts.run()
     torch.cuda.synchronize()
     prof = _lib.profile_stop()
@@ -441,6 +446,7 @@ def run_ours(args):
         "cgat_attn_bwd": ("hbm", n_pix * (2 * in_rec + rec) * esz),
         "cgat_loss_fwd_bwd": ("hbm", n_pix * rec * 3 * esz),
         "cgat_loader_gather": ("hbm", n_pix * rec * 2 * esz + frames_h.numel()),  # writes x, y; reads the raw frames once
+        "cgat_loader_gather_planar": ("hbm", n_pix * rec * 2 * esz + frames_h.numel()),
     }
     if pre:
         # fused conv + attention kernels: forward reads x and writes out; backward reads x and d(out) (the projected
@@ -493,7 +499,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": frames_h.numel() + start_h.numel() * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
                 "input": "raw uint8 frames [B+7,V,H,W] + int32 window starts from pinned host memory (the KNMI loader's "
-                         "on-disk format); sliding windows, /254 and [N,H,W,T,V] layout by cgat_loader_gather on the device",
+                         "on-disk format); sliding windows, /254 and the layouts the train kernel reads (x chunk-planar [N,T*V/8,H,W,8], "
+                         "y [N,H,W,T,V]) by cgat_loader_gather_planar on the device",
                 "xy_tensor_copy": {"value": world * B / (e2e_xy_ms / args.steps * 1e-3), "ms_per_step": e2e_xy_ms / args.steps,
                                    "h2d_bytes_per_step": xh.numel() * xh.element_size() + yh.numel() * yh.element_size(),
                                    "input": "finished x, y bf16 tensors copied per step (PCIe-bound)"}},

@@ -64,7 +64,11 @@ class LayerDesc(ctypes.Structure):
         ("nodes", ctypes.c_int32), ("ci", ctypes.c_int32), ("co", ctypes.c_int32), ("heads", ctypes.c_int32),
         ("layout", ctypes.c_int32), ("merge", ctypes.c_int32), ("apply_elu", ctypes.c_int32),
         ("alpha", ctypes.c_float),
+        ("x_layout", ctypes.c_int32),  # X_RECORDS (default) or X_PLANAR
     ]
+
+
+X_RECORDS, X_PLANAR = 0, 1
 
 
 _P = ctypes.c_void_p
@@ -111,6 +115,8 @@ SIGNATURES = {
     "cgat_p2p_allreduce_adam": [_P, _I, _I, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _P],
     "cgat_val_metrics": [_P, _P, _I64, _F, _F, _F, _I, _P, _P],
     "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
+    "cgat_loader_gather_planar": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
+    "cgat_records_to_planar": [_P, _P, _I64, _I64, _I, _P],
 }
 
 _lib = None

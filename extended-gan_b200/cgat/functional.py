@@ -442,17 +442,47 @@ def layer_train_supported(x, cfg: AttnConfig, mapping: str) -> bool:
     return bool(lib().cgat_layer_supported(ctypes.byref(ld)))
 
 
-def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None, acc=None):
+def planar_shape(x_shape):
+    """Shape of the chunk-planar copy of ``x[N,H,W,T,V]``: ``[N, T*V/8, H, W, 8]`` (include/cgat_b200.h, CGAT_X_PLANAR)."""
+    N, H, W, T, V = x_shape
+    if (T * V) % 8:
+        raise RuntimeError(f"chunk-planar x needs T*V to be a multiple of 8, got {T}*{V}")
+    return (N, T * V // 8, H, W, 8)
+
+
+def records_to_planar(x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """``x[N,H,W,T,V]`` bf16 pixel records -> chunk-planar ``[N, T*V/8, H, W, 8]`` (``cgat_records_to_planar``): the
+    fused layer kernels' fast input format, for tensors that did not come from ``cgat_loader_gather_planar``."""
+    require_cuda(x)
+    if x.dtype != torch.bfloat16:
+        raise RuntimeError("records_to_planar takes bf16 records")
+    x = x.contiguous()
+    N, H, W, T, V = x.shape
+    if out is None:
+        out = torch.empty(planar_shape(x.shape), device=x.device, dtype=x.dtype)
+    elif tuple(out.shape) != planar_shape(x.shape) or out.dtype != x.dtype or not out.is_contiguous():
+        raise RuntimeError("records_to_planar: out must be a contiguous bf16 [N, T*V/8, H, W, 8] tensor")
+    _lib.call("cgat_records_to_planar", ptr(x), ptr(out), N, H * W, T * V, stream())
+    return out
+
+
+def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None, acc=None,
+                     x_planar=None):
     """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
     ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
 
     ``loss_out[0]`` is accumulated into; the parameter gradients are ACCUMULATED into the parameters' existing
-    ``.grad`` buffers (fp32, contiguous).  ``params`` = per head (conv.weight, conv.bias, a, B).
+    ``.grad`` buffers (fp32, contiguous).  ``params`` = per head (conv.weight, conv.bias, a, B).  ``x_planar``: the
+    chunk-planar copy of ``x`` (``records_to_planar`` / the loader kernel); the kernel then reads it instead of ``x``.
     """
     require_cuda(x, y, loss_out, *params)
     N, H, W, T, V = x.shape
     x = x.contiguous()
     y = y.contiguous()
+    if x_planar is not None:
+        require_cuda(x_planar)
+        if tuple(x_planar.shape) != planar_shape(x.shape) or x_planar.dtype != x.dtype or not x_planar.is_contiguous():
+            raise RuntimeError("gat_stream_train: x_planar must be the contiguous [N, T*V/8, H, W, 8] copy of x")
     dev = x.device
     heads = cfg.heads
     ws = [params[4 * k] for k in range(heads)]
@@ -461,7 +491,8 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     Bs = [params[4 * k + 3] for k in range(heads)]
     if not all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in params):
         raise RuntimeError("gat_stream_train accumulates into existing contiguous fp32 .grad buffers")
-    ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, cfg.merge, int(cfg.apply_elu), cfg.alpha)
+    ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, cfg.merge, int(cfg.apply_elu), cfg.alpha,
+                        _lib.X_RECORDS if x_planar is None else _lib.X_PLANAR)
     sd = _lib.StreamDesc(cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, 1, int(cfg.adj_transpose), 1)
     st = stream()
     a_st = torch.empty(heads, 2 * cfg.co, device=dev, dtype=torch.float32)
@@ -477,7 +508,7 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     ga, gadj = acc[:na], acc[na:na + nadj]
     wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
     ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
-    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
+    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x if x_planar is None else x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
               float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(loss_out), ptr(mse_out), ctypes.byref(ncta), ctypes.byref(nt), st)
     tg = [p.grad for p in params]
     _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),

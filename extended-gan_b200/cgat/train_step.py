@@ -45,6 +45,10 @@ class TrainStep:
         self.graph = None
         self._slots = None  # double-buffered inputs for pipelined host->device loading (enable_prefetch)
         self.fused_stream = self._single_stream(model, example_x) if fuse_loss else None
+        # the fused train kernel reads x CHUNK-PLANAR ([N, T*V/8, H, W, 8]: TMA boxes with 128-byte rows); ``xp`` is that
+        # copy of ``x``.  The loader kernel writes it directly (prefetch_raw); record tensors handed to load_batch / step /
+        # prefetch are converted by one small kernel outside the captured graph.
+        self.xp = functional.records_to_planar(self.x) if self.fused_stream is not None else None
         self._flatten()
         if use_graph:
             self._capture()
@@ -144,7 +148,7 @@ class TrainStep:
         self.flat.zero_grad()  # gradients, loss scalars and accumulators: one memset
         if self.fused_stream is not None and self.fused_stream.train_step_supported(self.x):
             # forward + loss + backward in one kernel (cgat_layer_train)
-            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc)
+            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc, x_planar=self.xp)
             return
         prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
         try:
@@ -171,6 +175,16 @@ class TrainStep:
         """Copy one batch (host-pinned or device) into the static input buffers."""
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
+        self.refresh_planar()
+
+    def refresh_planar(self, slot: Optional[int] = None):
+        """Rebuild the chunk-planar copy after ``x`` (of ``slot``, or the current buffers) was written in record layout."""
+        if self.xp is None:
+            return
+        if slot is None:
+            functional.records_to_planar(self.x, out=self.xp)
+        else:
+            functional.records_to_planar(self._slots[slot]["x"], out=self._slots[slot]["xp"])
 
     def run(self) -> torch.Tensor:
         """One optimisation step on the loaded batch; returns the (device) loss of this rank's shard."""
@@ -187,12 +201,14 @@ class TrainStep:
         if x.shape == self.x.shape:
             self.load_batch(x, y)
             return self.run()
-        keep = (self.x, self.y, self.graph)
+        keep = (self.x, self.y, self.graph, self.xp)
         self.x, self.y, self.graph = x.to(self.x.dtype).contiguous(), y.to(self.y.dtype).contiguous(), None
+        if self.xp is not None:
+            self.xp = functional.records_to_planar(self.x)
         try:
             return self.run()
         finally:
-            self.x, self.y, self.graph = keep
+            self.x, self.y, self.graph, self.xp = keep
 
     # -- pipelined loading: batch i+1 crosses PCIe on a copy stream while batch i trains ------------------
     def enable_prefetch(self, n_slots: int = 2):
@@ -203,13 +219,15 @@ class TrainStep:
             raise RuntimeError("enable_prefetch was already called with fewer slots")
         if self.graph is None:
             raise RuntimeError("enable_prefetch needs use_graph=True")
-        slots = [dict(x=self.x, y=self.y, graph=self.graph)]
+        slots = [dict(x=self.x, y=self.y, graph=self.graph, xp=self.xp)]
         for _ in range(1, n_slots):
             self.x, self.y = torch.empty_like(self.x), torch.empty_like(self.y)
             self.x.copy_(slots[0]["x"])
             self.y.copy_(slots[0]["y"])
+            if self.xp is not None:
+                self.xp = slots[0]["xp"].clone()
             self._capture()
-            slots.append(dict(x=self.x, y=self.y, graph=self.graph))
+            slots.append(dict(x=self.x, y=self.y, graph=self.graph, xp=self.xp))
         self._slots = slots
         for s in self._slots:
             s["ready"] = torch.cuda.Event()   # inputs of this slot have landed
@@ -225,6 +243,8 @@ class TrainStep:
             self.copy_stream.wait_event(s["free"])
             s["x"].copy_(x_host, non_blocking=True)
             s["y"].copy_(y_host, non_blocking=True)
+            if s["xp"] is not None:
+                functional.records_to_planar(s["x"], out=s["xp"])
             s["ready"].record(self.copy_stream)
 
     def prefetch_raw(self, frames_host: torch.Tensor, start_host: torch.Tensor, slot: int, *, normalizing_max=254.0,
@@ -244,8 +264,12 @@ class TrainStep:
             s["frames"].copy_(frames_host, non_blocking=True)
             s["start"].copy_(start_host, non_blocking=True)
             N, H, W, T, V = s["x"].shape
-            gather_windows(s["frames"], s["start"], crop=H, steps=T, normalizing_max=normalizing_max, power=power,
-                           out=(s["x"], s["y"]))
+            if s["xp"] is not None:  # x straight into the train kernel's chunk-planar format (the record copy is not needed)
+                gather_windows(s["frames"], s["start"], crop=H, steps=T, normalizing_max=normalizing_max, power=power,
+                               out=(s["xp"], s["y"]), planar=True)
+            else:
+                gather_windows(s["frames"], s["start"], crop=H, steps=T, normalizing_max=normalizing_max, power=power,
+                               out=(s["x"], s["y"]))
 
         # A loader that refills the SAME pinned staging buffers every batch (the usual arrangement) gets the two copies
         # and the gather kernel as one captured graph per slot: one launch instead of ~8 host calls per batch -- the

@@ -110,5 +110,13 @@ __host__ __device__ inline int lf_score_rows(int nodes, int co, int heads) {
   const int ext = heads * lf_score_rows_per_head(nodes);
   return heads * nodes * co + ext <= 128 ? ext : 0;
 }
+// rows of a CTA's wgrad partial-sum slot (layer_fused.cu writes, stream_ops.cu reads): feature + score rows, rounded up
+// to a TMEM lane quarter.  Slot layout: [nt / 16 column blocks][rows][16 columns]  (coalesced writes, see layer_fused.cu)
+__host__ __device__ inline int lf_partial_rows(int nodes, int co, int heads) {
+  return (heads * nodes * co + lf_score_rows(nodes, co, heads) + 31) & ~31;
+}
+__host__ __device__ inline size_t lf_partial_index(int row, int col, int rows) {
+  return ((size_t)(col >> 4) * rows + row) * 16 + (col & 15);
+}
 
 }  // namespace cgat

@@ -78,6 +78,8 @@ struct LfArgs {
   float alpha;
   int nchunk, nq, mchunk, nt;   // nq = 3*nchunk + 1 planes per stage (the last one is all ones); nt = 3 * nq * 8
   int tiles_h, tiles_w, tiles, nstg, ndw;
+  int x_planar;                 // x is chunk-planar [n][cin/8][h][w][8] (CGAT_X_PLANAR): 3 boxes of 128-byte rows per tile
+  int rows_pad;                 // rows of a CTA's partial-sum slot: cout + ext rounded up to a lane quarter (32)
   uint32_t wbytes, stage_bytes, dw_bytes;  // bytes of one x stage / of one d(Wh) buffer (0 in the forward kernel)
 };
 
@@ -118,6 +120,14 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// mbarrier wait of a CONVERGED warp: the vote makes the loop condition warp-uniform, so the compiler still knows the warp
+// is converged afterwards (a per-lane `while (!try_wait)` ends that knowledge: every tcgen05.mma behind it is then wrapped
+// in ELECT / VOTEU / R2UR sequences)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+  }
+}
 
 __device__ __forceinline__ uint4 lf_lds128(uint32_t addr) {
   uint4 v;
@@ -175,7 +185,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   unsigned char* s_stage = s_dw + (size_t)A.ndw * A.dw_bytes;
   float4* s_slab = reinterpret_cast<float4*>(s_stage + (size_t)A.nstg * A.stage_bytes);  // fwd: [group][REC/4][128]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (the shuffle makes the warp index provably warp-uniform: role branches and everything computed under them can then
+  // use the uniform datapath -- what CUTLASS calls canonical_warp_idx_sync)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nact = A.heads < LF_GROUPS ? A.heads : LF_GROUPS;  // attention groups that own at least one head
 
   if (threadIdx.x == 0) LDBGX(0);
@@ -205,6 +217,16 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     const int n = tile / (A.tiles_w * A.tiles_h);
     mbar_arrive_expect_tx(&full[stage], tile_bytes);
     unsigned char* dst = s_stage + (size_t)stage * A.stage_bytes;
+    if (A.x_planar) {
+      // chunk-planar x: the box (8 pixels x 8 channels = one 128-byte row, 18 rows, all chunks) of horizontal tap sh IS
+      // the planes q = sh * nchunk + c, c = 0 .. nchunk-1, in order.  The TMA unit works per box ROW: 54 rows of 128 B
+      // per box here against 144 rows of 16 B per (sh, c) box of the record layout (measured: ~3 500 cycles per tile
+      // for the 9 small-row boxes, which put the x ring on the kernel's critical path)
+      for (int sh = 0; sh < 3; ++sh)
+        tma_load_4d(dst + (size_t)(sh * A.nchunk) * LF_PLANE, &tmap_x, (tw * LF_TW - 1 + sh) * 8, th * LF_TH - 1, 0, n,
+                    &full[stage]);
+      return;
+    }
     for (int sh = 0; sh < 3; ++sh)
       for (int c = 0; c < A.nchunk; ++c)
         tma_load_4d(dst + (size_t)(sh * A.nchunk + c) * LF_PLANE, &tmap_x, c * 8, tw * LF_TW - 1 + sh, th * LF_TH - 1, n,
@@ -217,29 +239,33 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     mbar_arrive_expect_tx(wbar, A.wbytes);
     bulk_g2s(s_w, A.wpack, A.wbytes, wbar);  // (the larger transfer first: the first fprop needs both)
     if ((int)blockIdx.x < A.tiles) issue_tile(blockIdx.x, 0);
+    if (A.x_planar && A.nstg > 1 && (int)(blockIdx.x + gridDim.x) < A.tiles) issue_tile(blockIdx.x + gridDim.x, 1);
   }
-  for (int i = threadIdx.x; i < A.heads * 2 * CO; i += LF_THREADS) { s_a[i] = A.a[i]; s_a2[i] = __float2half2_rn(A.a[i]); }
-  for (int i = threadIdx.x; i < A.heads * NODES * NODES; i += LF_THREADS) {
-    s_adj[i] = A.adj[i];
-    s_adj2[i] = __float2half2_rn(A.adj[i]);
-  }
-  for (int i = threadIdx.x; i < MAX_HEADS * RG + 2; i += LF_THREADS) s_gacc[i] = 0.f;
-  if (threadIdx.x < NODES) {
-    uint64_t mrow = 0;
-    for (int j = 0; j < NODES; ++j)
-      if (A.mask == nullptr || A.mask[threadIdx.x * NODES + j] != 0) mrow |= (1ull << j);
-    s_mask[threadIdx.x] = mrow;
-  }
-  {
+  if (warp != LF_TMA_WARP) {
+    // (warp 0 is busy issuing TMA instructions, ~100 cycles each: the other 15 warps initialise shared memory)
+    constexpr int NI = LF_THREADS - 32;
+    const int ti = threadIdx.x - 32;
+    for (int i = ti; i < A.heads * 2 * CO; i += NI) { s_a[i] = A.a[i]; s_a2[i] = __float2half2_rn(A.a[i]); }
+    for (int i = ti; i < A.heads * NODES * NODES; i += NI) {
+      s_adj[i] = A.adj[i];
+      s_adj2[i] = __float2half2_rn(A.adj[i]);
+    }
+    for (int i = ti; i < MAX_HEADS * RG + 2; i += NI) s_gacc[i] = 0.f;
+    if (ti < NODES) {
+      uint64_t mrow = 0;
+      for (int j = 0; j < NODES; ++j)
+        if (A.mask == nullptr || A.mask[ti * NODES + j] != 0) mrow |= (1ull << j);
+      s_mask[ti] = mrow;
+    }
     // d(Wh) buffers start zeroed (rows the attention groups never write must hold finite numbers); every x stage gets
     // its plane of ones behind the im2col planes (its wgrad column is dbias; its fprop K-chunk holds the bias, hi + lo
     // bf16 parts).  The TMA unit may already be writing the OTHER planes of the stages: disjoint addresses.
     uint4* p = reinterpret_cast<uint4*>(s_dw);
     const int n16 = (int)((size_t)A.ndw * A.dw_bytes / 16);
-    for (int i = threadIdx.x; i < n16; i += LF_THREADS) p[i] = make_uint4(0, 0, 0, 0);
+    for (int i = ti; i < n16; i += NI) p[i] = make_uint4(0, 0, 0, 0);
     for (int st = 0; st < A.nstg; ++st) {
-      uint32_t* o = reinterpret_cast<uint32_t*>(s_stage + (size_t)st * A.stage_bytes + (size_t)(A.nq - 1) * LF_PLANE);
-      for (int i = threadIdx.x; i < LF_PLANE / 4; i += LF_THREADS) o[i] = 0x3f803f80u;  // bf16 1.0 x2
+      uint4* o = reinterpret_cast<uint4*>(s_stage + (size_t)st * A.stage_bytes + (size_t)(A.nq - 1) * LF_PLANE);
+      for (int i = ti; i < LF_PLANE / 16; i += NI) o[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0
     }
     fence_proxy_async_smem();
   }
@@ -258,15 +284,21 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         LDBG(0);
-        if (it > 0) {
-          if (it >= A.nstg) mbar_wait(&empty[stage], phase ^ 1u);
+        if (it > (A.x_planar && A.nstg > 1 ? 1 : 0)) {  // (the first tile or two went out during set-up)
+          if (it >= A.nstg) {
+#ifdef CGAT_LF_SLEEPY_TMA
+            while (!mbar_try_wait(&empty[stage], phase ^ 1u)) __nanosleep(64);
+#else
+            mbar_wait(&empty[stage], phase ^ 1u);
+#endif
+          }
           LDBG(1);
           issue_tile(tile, stage);
         }
         if (++stage == A.nstg) { stage = 0; phase ^= 1u; }
       }
-    } else if (warp == LF_MMA_WARP && lane == 0) {
-      // ===================== MMA issuer =====================
+    } else if (warp == LF_MMA_WARP) {
+      // ===================== MMA issuer: the whole warp runs this converged, one elected lane issues (tc_common.cuh) ====
       const uint32_t idesc_f = make_idesc_bf16(128, A.npad, 0, 0);
       const uint32_t idesc_w = make_idesc_bf16(128, A.nq * 8, 1, 1);
       const uint32_t w_addr = smem_u32(s_w);
@@ -275,33 +307,35 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       int wstage = 0, wbuf = 0, wj = 0;  // wj: next tile whose wgrad is to be issued; its x stage and d(Wh) buffer
       uint32_t wphase = 0, bphase = 0;
       auto wgrad = [&](int j) {  // tiles are retired in order: (wstage, wphase), (wbuf, bphase) follow tile j
-        mbar_wait(&dyfull[wbuf], bphase);
+        mbar_wait_warp(&dyfull[wbuf], bphase);
         { const int it = j; LDBG(7); }
         tc_fence_after();
         const uint32_t dy_addr = smem_u32(s_dw) + (uint32_t)wbuf * A.dw_bytes;
         const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)wstage * A.stage_bytes;
+        const uint64_t ad0 = make_smem_desc(dy_addr, 128, 2048);
+        const uint64_t bd0 = make_smem_desc(im_addr, LF_ROW, LF_PLANE);
+#pragma unroll
         for (int r = 0; r < 3; ++r) {  // vertical tap = the planes shifted by r rows (128 B); one accumulator each
 #pragma unroll
           for (int jj = 0; jj < LF_TH / 2; ++jj) {  // K step: image rows 2jj, 2jj+1 of the tile (16 pixels)
-            const uint64_t ad = make_smem_desc(dy_addr + jj * 256, 128, 2048);
-            const uint64_t bd = make_smem_desc(im_addr + (uint32_t)(r + 2 * jj) * LF_ROW, LF_ROW, LF_PLANE);
-            umma_bf16(tmem_base + (uint32_t)(r * A.nq * 8), ad, bd, idesc_w, wg_accum | (uint32_t)(jj > 0));
+            umma_bf16_warp(tmem_base + (uint32_t)(r * A.nq * 8), ad0 + (uint64_t)((jj * 256) >> 4),
+                           bd0 + (uint64_t)(((r + 2 * jj) * LF_ROW) >> 4), idesc_w, wg_accum | (uint32_t)(jj > 0));
           }
         }
         wg_accum = 1;
-        umma_commit(&empty[wstage]);
-        umma_commit(&dwfree[wbuf]);
+        umma_commit_warp(&empty[wstage]);
+        umma_commit_warp(&dwfree[wbuf]);
         { const int it = j; LDBG(8); }
 #ifdef CGAT_LF_TIMELINE
         if (A.dbg != nullptr && A.dbg[255] != 0) {
-          mbar_wait(&dwfree[wbuf], bphase);
+          mbar_wait_warp(&dwfree[wbuf], bphase);
           { const int it = j; LDBG(3); }
         }
 #endif
         if (++wstage == A.nstg) { wstage = 0; wphase ^= 1u; }
         if (++wbuf == A.ndw) { wbuf = 0; bphase ^= 1u; }
       };
-      mbar_wait(wbar, 0);
+      mbar_wait_warp(wbar, 0);
       int it = 0, stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
@@ -313,31 +347,38 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           if ((it & 1) == 0)
             while (wj < it - 2) wgrad(wj++);
         }
-        mbar_wait(&full[stage], phase);
+        mbar_wait_warp(&full[stage], phase);
         LDBG(4);
-        mbar_wait(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
+        mbar_wait_warp(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
         LDBG(5);
         tc_fence_after();
         const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes;
         const uint32_t d_addr = tmem_base + LF_FP_COL0 + (uint32_t)acc * 128;
-        uint32_t kk = 0;
+        // (the served shapes have ci == co, so the plane count is a compile-time constant and the 15 descriptor pairs
+        // are the first one plus immediates: a handful of uniform-datapath instructions per tcgen05.mma)
+        constexpr int NQ = 3 * (NODES * CO / 8) + 1;
+        const uint64_t ad0 = make_smem_desc(im_addr, LF_PLANE, LF_ROW);
+        const uint64_t bd0 = make_smem_desc(w_addr, b_lbo, 128);
+        const uint32_t b_step = (2 * b_lbo) >> 4;
+#pragma unroll
         for (int r = 0; r < 3; ++r) {
-          for (int q = 0; q < A.nq; q += 2, kk += 2) {  // K = 16: planes q, q+1 shifted by the vertical tap r
-            const uint64_t ad = make_smem_desc(im_addr + (uint32_t)q * LF_PLANE + (uint32_t)r * LF_ROW, LF_PLANE, LF_ROW);
-            const uint64_t bd = make_smem_desc(w_addr + kk * b_lbo, b_lbo, 128);
-            umma_bf16(d_addr, ad, bd, idesc_f, kk > 0);
+#pragma unroll
+          for (int q = 0; q < NQ; q += 2) {  // K = 16: planes q, q+1 shifted by the vertical tap r
+            const int kp = r * (NQ / 2) + q / 2;
+            umma_bf16_warp(d_addr, ad0 + (uint64_t)((q * LF_PLANE + r * LF_ROW) >> 4), bd0 + (uint64_t)(kp * b_step), idesc_f,
+                           kp > 0);
           }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit_warp(&tfull[acc]);
         LDBG(6);
 #ifdef CGAT_LF_TIMELINE
         if (A.dbg != nullptr && A.dbg[255] != 0) {  // developer probe: execution time of the fprop MMAs in isolation
-          mbar_wait(&tfull[acc], ((uint32_t)it >> 1) & 1u);
+          mbar_wait_warp(&tfull[acc], ((uint32_t)it >> 1) & 1u);
           LDBG(2);
         }
 #endif
         if constexpr (!BWD) {
-          umma_commit(&empty[stage]);
+          umma_commit_warp(&empty[stage]);
         } else if constexpr (!PAIR) {
           while (wj < it) wgrad(wj++);
         }
@@ -345,7 +386,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       }
       if constexpr (BWD) {
         while (wj < it) wgrad(wj++);
-        umma_commit(done);
+        umma_commit_warp(done);
       }
     }
   } else if (warp >= LF_ATT_WARP0 && warp < LF_ATT_WARP0 + 4 * LF_GROUPS) {
@@ -431,9 +472,15 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               const int tile = tileA + ahead * (int)gridDim.x;
               if (tile < A.tiles) {
                 const int tw = tile % A.tiles_w, th = (tile / A.tiles_w) % A.tiles_h, n = tile / (A.tiles_w * A.tiles_h);
-                const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
-                if (h < A.h && w < A.w)
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + (((long long)n * A.h + h) * A.w + w) * A.cin));
+                if (A.x_planar) {  // one 128-byte line = the 8 pixels of a tile row in one chunk plane: nchunk * 16 lines
+                  const int c = m >> 4, h = th * LF_TH + (m & 15), w = tw * LF_TW;
+                  if (c < A.nchunk && h < A.h)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + ((((long long)n * A.nchunk + c) * A.h + h) * A.w + w) * 8));
+                } else {
+                  const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
+                  if (h < A.h && w < A.w)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + (((long long)n * A.h + h) * A.w + w) * A.cin));
+                }
               }
             }
           }
@@ -903,19 +950,47 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         //      plain stores, no shared-memory atomics (fp32 ATOMS is a CAS loop: 28 serialised ones cost 8 600 cycles)
         {
           float* slot = reinterpret_cast<float*>(s_w) + (warp - LF_ATT_WARP0) * LF_SLOT;
+          if constexpr (PAIR && NODES * NODES == 16) {
+            // the paired kernel carries adjacency sums only (the score gradients left through the wgrad MMA): 16 values by
+            // recursive halving -- 8 + 4 + 2 + 1 + 1 shuffles instead of 5 per value; lanes 2i, 2i+1 end with value i
 #pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
+            for (int st = 0; st < 4; ++st) {
+              const int off = 16 >> st, nk = 8 >> st;
+              const bool up = (lane & off) != 0;
 #pragma unroll
-            for (int i = 0; i < RG; ++i) gacc[i] += __shfl_xor_sync(0xffffffffu, gacc[i], off);
-            loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
-            mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, off);
-          }
-          if (lane == 0) {
+              for (int i = 0; i < nk; ++i) {
+                const float send = up ? gacc[i] : gacc[i + nk], keep = up ? gacc[i + nk] : gacc[i];
+                gacc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+              }
+            }
+            gacc[0] += __shfl_xor_sync(0xffffffffu, gacc[0], 1);
 #pragma unroll
-            for (int i = 0; i < RG; ++i) slot[i] = gacc[i];
-            slot[RG] = loss_acc;
-            slot[RG + 1] = mse_acc;
-            reinterpret_cast<int*>(slot)[RG + 2] = cur_head;
+            for (int off = 16; off > 0; off >>= 1) {
+              loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+              mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, off);
+            }
+            if ((lane & 1) == 0) slot[lane >> 1] = gacc[0];
+            if (lane < RG - NODES * NODES) slot[NODES * NODES + lane] = 0.f;
+            if (lane == 0) {
+              slot[RG] = loss_acc;
+              slot[RG + 1] = mse_acc;
+              reinterpret_cast<int*>(slot)[RG + 2] = cur_head;
+            }
+          } else {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+              for (int i = 0; i < RG; ++i) gacc[i] += __shfl_xor_sync(0xffffffffu, gacc[i], off);
+              loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
+              mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, off);
+            }
+            if (lane == 0) {
+#pragma unroll
+              for (int i = 0; i < RG; ++i) slot[i] = gacc[i];
+              slot[RG] = loss_acc;
+              slot[RG + 1] = mse_acc;
+              reinterpret_cast<int*>(slot)[RG + 2] = cur_head;
+            }
           }
         }
         if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(4);
@@ -923,15 +998,19 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         mbar_wait(done, 0);
         tc_fence_after();
         if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(5);
-        float* prow = A.partial + ((size_t)blockIdx.x * 128 + m) * A.nt;
-        for (int c0 = g * 16; c0 < A.nt; c0 += nact * 16) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
-          if (m < A.cout + A.ext) {
+        // slot layout [16-column block][row][16]: a thread's 16 columns are 64 contiguous bytes and a warp's rows follow
+        // each other -- 2 KB per warp and column block, fully coalesced (row-major slots made every lane of a store hit its
+        // own 32-byte sector, half used: the 123 KB of a CTA took 6 000 cycles)
+        if (lg * 32 < A.rows_pad) {
+          float* pslot = A.partial + (size_t)blockIdx.x * A.rows_pad * A.nt + (size_t)m * 16;
+          for (int c0 = g * 16; c0 < A.nt; c0 += nact * 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
+            float4* dst = reinterpret_cast<float4*>(pslot + (size_t)(c0 >> 4) * A.rows_pad * 16);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(prow + c0)[i] = make_float4(v[4 * i] * A.out_scale, v[4 * i + 1] * A.out_scale,
-                                                                    v[4 * i + 2] * A.out_scale, v[4 * i + 3] * A.out_scale);
+              dst[i] = make_float4(v[4 * i] * A.out_scale, v[4 * i + 1] * A.out_scale, v[4 * i + 2] * A.out_scale,
+                                   v[4 * i + 3] * A.out_scale);
           }
         }
         if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(6);
@@ -975,7 +1054,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
 
 // ---- host side ------------------------------------------------------------------------------------------
 struct LfGeom {
-  int cin, cout, ext, rec, nchunk, nq, npad, mchunk, nt;
+  int cin, cout, ext, rec, nchunk, nq, npad, mchunk, nt, rows_pad;
   uint32_t wbytes, stage_bytes, dw_bytes;
   size_t smem;
   int tiles_h, tiles_w, tiles, nstg, ndw;
@@ -992,6 +1071,7 @@ static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
   g.npad = (g.cout + g.ext + 15) & ~15;
   g.mchunk = g.cout / 8;
   g.nt = 3 * g.nq * 8;                // wgrad partial columns: [r][(s,c) | ones][8]
+  g.rows_pad = lf_partial_rows(d->nodes, d->co, d->heads);
   g.wbytes = (uint32_t)(3 * g.nq) * g.npad * 16;
   g.stage_bytes = ((uint32_t)g.nq * LF_PLANE + 127u) & ~127u;
   // a d(Wh) buffer: feature planes, then the score-row planes -- at least rec/8 of them: the train kernel passes d(out)
@@ -1031,6 +1111,7 @@ int layer_supported(const cgat_layer_desc* d) {
   const LfGeom f = lf_geom(d, false), b = lf_geom(d, true);
   if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.npad > 128 || f.nt > 256) return 0;
   if (f.nq % 2) return 0;  // fprop consumes the planes (+ the ones plane) in pairs: K = 16 per tcgen05.mma
+  if (d->ci != d->co) return 0;  // (the kernel derives its plane count from nodes * co)
   if (f.smem > 227 * 1024 || b.smem > 227 * 1024) return 0;
   return 1;
 }
@@ -1054,6 +1135,25 @@ static int make_nhwc_map(CUtensorMap* map, const void* base, int n, int h, int w
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAT_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// chunk-planar x [n][c/8][h][w][8] as the 4-D tensor [n][c/8][h][w*8]: box (64 elements = 8 pixels of one chunk = 128 B,
+// hp rows, all chunks, 1) lands as [chunk][hp][128 B] = the column planes of one horizontal tap; a start coordinate of
+// -8 / beyond w*8 is the conv's zero padding
+static int make_planar_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int hp) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(CGAT_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  ensure_context();
+  const int nchunk = c / 8;
+  cuuint64_t dims[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)nchunk, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)nchunk * h * w * 16};
+  cuuint32_t box[4] = {64, (cuuint32_t)hp, (cuuint32_t)nchunk, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CGAT_EINVAL, "cuTensorMapEncodeTiled (planar x) failed with CUresult %d", (int)r);
   return 0;
 }
 
@@ -1090,7 +1190,12 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
     return fail(CGAT_EALIGN, "layer tensors must be 16-byte aligned");
   const LfGeom g = lf_geom(d, bwd);
   CUtensorMap map;
-  if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, LF_TW, LF_PR)) return rc;
+  if (d->x_layout != CGAT_X_RECORDS && d->x_layout != CGAT_X_PLANAR) return fail(CGAT_EINVAL, "bad x_layout %d", d->x_layout);
+  if (d->x_layout == CGAT_X_PLANAR) {
+    if (int rc = make_planar_map(&map, x, d->n, d->h, d->w, g.cin, LF_PR)) return rc;
+  } else if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, LF_TW, LF_PR)) {
+    return rc;
+  }
   LfArgs A{};
   A.dbg = g_lf_dbg;
   A.x = (const __nv_bfloat16*)x;
@@ -1105,7 +1210,8 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
                     ? A.inv_n : 1.f;
   A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.ext = g.ext; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
-  A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt;
+  A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt; A.rows_pad = g.rows_pad;
+  A.x_planar = d->x_layout == CGAT_X_PLANAR;
   A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.nstg = g.nstg; A.ndw = g.ndw;
   A.wbytes = g.wbytes; A.stage_bytes = g.stage_bytes; A.dw_bytes = g.dw_bytes;
   if (ncta_out) *ncta_out = g.tiles < lf_sm_count() ? g.tiles : lf_sm_count();

@@ -28,7 +28,8 @@ constexpr int LD_MAX_REC = 64;  // T * V elements per pixel record
 template <typename T, int RECT>
 __global__ void __launch_bounds__(LD_THREADS, 16)
 loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ start, T* __restrict__ x,
-                     T* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, int steps, float nmax, float power) {
+                     T* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, int steps, float nmax, float power,
+                     int x_planar) {
   extern __shared__ __align__(16) unsigned char ld_smem[];
   T* lut = reinterpret_cast<T*>(ld_smem);                       // [256]
   uint8_t* tile = ld_smem + 256 * sizeof(T);                    // [2*steps*V][LD_THREADS]
@@ -84,6 +85,13 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     T* dst = (half ? y : x) + pix * rec;
+    // chunk-planar x (CGAT_X_PLANAR, the fused layer kernels' fast input format): 16-byte chunk q of the record goes to
+    // plane q of the sample, [n][rec/8][crop_h][crop_w][8] -- consecutive threads write consecutive 16-byte slots
+    size_t qstride = 1;  // distance between a record's 16-byte chunks, in uint4
+    if (half == 0 && x_planar) {
+      dst = x + ((size_t)s * (rec * sizeof(T) / 16) * per_sample + p0 + threadIdx.x) * (16 / sizeof(T));
+      qstride = (size_t)per_sample;
+    }
     const uint8_t* col = tile + (size_t)(half * rec) * LD_THREADS + threadIdx.x;
     if constexpr (RECT != 0 && (RECT * sizeof(T)) % 16 == 0) {
       constexpr int PER = 16 / sizeof(T);
@@ -95,7 +103,7 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
         T v[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) v[j] = lut[k[q * PER + j]];
-        reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<const uint4*>(v);
+        reinterpret_cast<uint4*>(dst)[q * qstride] = *reinterpret_cast<const uint4*>(v);
       }
     } else if ((rec * sizeof(T)) % 16 == 0) {
       constexpr int PER = 16 / sizeof(T);
@@ -103,13 +111,35 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
         T v[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) v[j] = lut[col[(size_t)(q * PER + j) * LD_THREADS]];
-        reinterpret_cast<uint4*>(dst)[q] = *reinterpret_cast<const uint4*>(v);
+        reinterpret_cast<uint4*>(dst)[q * qstride] = *reinterpret_cast<const uint4*>(v);
       }
     } else {
       for (int e = 0; e < rec; ++e) dst[e] = lut[col[(size_t)e * LD_THREADS]];
     }
   }
 }
+
+// pixel records [n][pix][rec] -> chunk-planar [n][rec/8][pix][8] (bf16): for x tensors that did not come from the loader
+// kernel.  One thread per pixel: rec/8 16-byte loads (a warp reads 32 * rec * 2 contiguous bytes), rec/8 coalesced stores.
+__global__ void __launch_bounds__(256) records_to_planar_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
+                                                                  long long n_pix, long long per_sample, int nchunk) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  const long long smp = p / per_sample, q = p - smp * per_sample;
+  uint4 v[8];
+  for (int c0 = 0; c0 < nchunk; c0 += 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c0 + c < nchunk) v[c] = in[p * nchunk + c0 + c];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c0 + c < nchunk) out[(smp * nchunk + c0 + c) * per_sample + q] = v[c];
+  }
+}
+
+static int loader_gather_impl(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y,
+                              int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
+                              int32_t steps, float normalizing_max, float power, int32_t dtype, int x_planar, void* stream);
 
 }  // namespace cgat
 
@@ -118,6 +148,33 @@ using namespace cgat;
 extern "C" int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y,
                                   int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
                                   int32_t steps, float normalizing_max, float power, int32_t dtype, void* stream) {
+  return loader_gather_impl(frames, n_frames, start, x, y, n, vertices, h, w, crop_h, crop_w, steps, normalizing_max, power,
+                            dtype, 0, stream);
+}
+
+extern "C" int cgat_loader_gather_planar(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x_planar,
+                                         void* y, int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h,
+                                         int32_t crop_w, int32_t steps, float normalizing_max, float power, void* stream) {
+  if ((steps * vertices) % 8) return fail(CGAT_EUNSUPPORTED, "chunk-planar x needs steps*vertices to be a multiple of 8");
+  return loader_gather_impl(frames, n_frames, start, x_planar, y, n, vertices, h, w, crop_h, crop_w, steps, normalizing_max,
+                            power, CGAT_BF16, 1, stream);
+}
+
+extern "C" int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int64_t pix_per_sample, int32_t rec,
+                                      void* stream) {
+  if (!x || !x_planar) return fail(CGAT_EINVAL, "null argument");
+  if (n < 1 || pix_per_sample < 1 || rec < 8 || rec % 8) return fail(CGAT_EINVAL, "records_to_planar: rec must be a multiple of 8");
+  if (!aligned16(x) || !aligned16(x_planar)) return fail(CGAT_EALIGN, "records_to_planar: 16-byte aligned tensors");
+  const long long n_pix = (long long)n * pix_per_sample;
+  records_to_planar_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, (uint4*)x_planar, n_pix, pix_per_sample, rec / 8);
+  return check_launch("records_to_planar_kernel");
+}
+
+static int cgat::loader_gather_impl(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y,
+                                    int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
+                                    int32_t steps, float normalizing_max, float power, int32_t dtype, int x_planar,
+                                    void* stream) {
   if (!frames || !start || !x || !y) return fail(CGAT_EINVAL, "null argument");
   if (n < 1 || vertices < 1 || h < 1 || w < 1 || steps < 1 || crop_h < 1 || crop_w < 1 || crop_h > h || crop_w > w ||
       n_frames < 2 * steps)
@@ -133,7 +190,7 @@ extern "C" int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const
   if (smem > 48 * 1024) return fail(CGAT_EUNSUPPORTED, "loader tile needs %zu B of shared memory", smem);
 #define LD_LAUNCH(T, R)                                                                                                   \
   loader_gather_kernel<T, R><<<grid, LD_THREADS, smem, st>>>(frames, start, (T*)x, (T*)y, vertices, h, w, crop_h, crop_w, steps, \
-                                                             normalizing_max, power)
+                                                             normalizing_max, power, x_planar)
   const int rec = steps * vertices;
   if (dtype == CGAT_F32) {
     if (rec == 24) LD_LAUNCH(float, 24); else LD_LAUNCH(float, 0);

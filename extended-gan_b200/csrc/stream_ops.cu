@@ -377,11 +377,13 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per_k = nwe + g.co + 2 * g.co;
   const int nq = 3 * g.nchunk + 1;
-  const float* R = A.wg_partial;
+  const float* Rm = A.wg_partial;
+  const int rows = lf_partial_rows(g.nodes, g.co, g.heads);
   auto column = [&](int tap, int ci_idx) {  // [r][(s, cin chunk) | ones][8]; tap < 0: the ones (bias) column of r = 0
     if (tap < 0) return (nq - 1) * 8;
     return ((tap / 3) * nq + (tap % 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
   };
+  auto R = [&](int row, int col) { return Rm[lf_partial_index(row, col, rows)]; };  // slot layout: common.cuh
   const long long nout = (long long)g.heads * per_k;
   for (long long i = (long long)(blockIdx.x - g.heads) * (ADJ_THREADS / 32) + warp; i < nout;
        i += (long long)(gridDim.x - g.heads) * (ADJ_THREADS / 32)) {
@@ -403,11 +405,11 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
       if (dst == nullptr) continue;  // warp-uniform
       if (lane < g.nodes) {  // lane = node
         const int col = column(tap, rec_of(g.spatial, g.nodes, g.ci, lane, c));
-        acc = R[(size_t)(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, lane, u)) * A.nt + col];
+        acc = R(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, lane, u), col);
         if (ext) {
           const int rs = g.cout + k * g.sph + lane;
-          acc = fmaf(A.a.p[k][u], R[(size_t)rs * A.nt + col], acc);
-          acc = fmaf(A.a.p[k][g.co + u], R[(size_t)(rs + g.nodes) * A.nt + col], acc);
+          acc = fmaf(A.a.p[k][u], R(rs, col), acc);
+          acc = fmaf(A.a.p[k][g.co + u], R(rs + g.nodes, col), acc);
         }
       }
     } else {
@@ -417,12 +419,12 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
         const int nterm = g.taps * g.ci + 1;
         for (int t = lane; t < g.nodes * nterm; t += 32) {
           const int node = t / nterm, tt = t - node * nterm;
-          const float* prow = R + (size_t)(g.cout + k * g.sph + which * g.nodes + node) * A.nt;
+          const int prow = g.cout + k * g.sph + which * g.nodes + node;
           if (tt < nterm - 1) {
             const int tap = tt % g.taps, c = tt / g.taps;
-            acc = fmaf(A.w.p[k][(u * g.ci + c) * g.taps + tap], prow[column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c))], acc);
+            acc = fmaf(A.w.p[k][(u * g.ci + c) * g.taps + tap], R(prow, column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c))), acc);
           } else if (A.bias.p[k]) {
-            acc = fmaf(A.bias.p[k][u], prow[column(-1, 0)], acc);
+            acc = fmaf(A.bias.p[k][u], R(prow, column(-1, 0)), acc);
           }
         }
       }
@@ -514,8 +516,8 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
   if (d->mapping == 1 && d->wgrad_cols) {
     // fused layer kernels: sum the CTA slots into the slot behind them (the workspace of cgat_layer_* has it), then
     // one warp per output from the reduced matrix
-    const size_t cta_stride = (size_t)128 * nt;
-    const int nred = (g.cout + g.ext) * nt;
+    const size_t cta_stride = (size_t)lf_partial_rows(g.nodes, g.co, g.heads) * nt;  // slot layout: common.cuh
+    const int nred = (int)cta_stride;
     float* R = const_cast<float*>(wg_partial) + (size_t)ncta * cta_stride;
     wgrad_partial_reduce_kernel<<<(nred + RED_OUT - 1) / RED_OUT, RED_OUT * RED_SPLIT, 0, (cudaStream_t)stream>>>(
         wg_partial, ncta, nred, cta_stride, R);

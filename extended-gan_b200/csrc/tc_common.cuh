@@ -97,6 +97,32 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// The same two, called by ALL 32 lanes of a converged warp; one elected lane issues.  Inside `if (lane == 0)` the
+// compiler treats every operand as possibly lane-varying: each tcgen05.mma then costs ~17 SASS instructions (descriptor
+// arithmetic in vector registers, R2UR moves, an ELECT / BRA.U.ANY loop) -- ~170 cycles per MMA when the issuing warp
+// shares its scheduler with busy warps.  In converged code the operands live in uniform registers.
+__device__ __forceinline__ void umma_bf16_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // TMEM -> registers: the calling warp reads 16 consecutive fp32 columns of its 32 lanes
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];

@@ -193,7 +193,12 @@ typedef struct cgat_layer_desc {
   int32_t merge;     /* CGAT_MERGE_*  */
   int32_t apply_elu;
   float alpha;
+  int32_t x_layout;  /* CGAT_X_RECORDS (0): x is [n][h][w][nodes*ci] pixel records, the loaders' [N,H,W,T,V];
+                        CGAT_X_PLANAR (1): x is chunk-planar [n][nodes*ci/8][h][w][8] (cgat_loader_gather_planar /
+                        cgat_records_to_planar write it): the kernel's TMA boxes then have 128-byte rows            */
 } cgat_layer_desc;
+#define CGAT_X_RECORDS 0
+#define CGAT_X_PLANAR 1
 int cgat_layer_supported(const cgat_layer_desc* d);
 int64_t cgat_layer_workspace_bytes(const cgat_layer_desc* d);
 int cgat_layer_fwd(const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias_dense, const float* a,
@@ -245,6 +250,15 @@ int cgat_adam_step(float* param, const float* grad, float* m, float* v, const in
 int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y, int32_t n,
                        int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w, int32_t steps,
                        float normalizing_max, float power, int32_t dtype, void* stream);
+/* The same gather with x written CHUNK-PLANAR (CGAT_X_PLANAR): x_planar [n][steps*vertices/8][crop_h][crop_w][8] bf16,
+ * the 16-byte chunk q of every pixel record in plane q; y stays [n][crop_h][crop_w][steps][vertices] bf16.  This is the
+ * input format of the fused layer kernels whose TMA boxes then have 128-byte rows (cgat_layer_desc.x_layout).       */
+int cgat_loader_gather_planar(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x_planar, void* y,
+                              int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
+                              int32_t steps, float normalizing_max, float power, void* stream);
+/* pixel records [n][pix_per_sample][rec] bf16 -> chunk-planar [n][rec/8][pix_per_sample][8] for an x tensor that did
+ * not come from the loader kernel (the reference's own DataLoader, convolutional_gat/train.py:128).                  */
+int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int64_t pix_per_sample, int32_t rec, void* stream);
 /* f4  validation metrics of convolutional_gat/train.py:53-75 + utils.py:135-167 in one pass over y, y_hat (n elements of
  * `dtype`): ACCUMULATES into out6 (double, caller zeroes)  [0] sum (y'-yh')^2  [1] sum ((y'-yh')*normalizing_max)^2
  * [2] TP [3] FP [4] FN [5] #(bin(y') == bin(yh')),  y' = y^(1/power), bin = the threshold binarisation of utils.py:138-141. */

@@ -77,3 +77,28 @@ def test_fused_loss_kernel_equals_unfused_step(N, H, W):
     close(res[True][0], res[False][0], rtol=2e-3, atol=1e-5, msg="loss")
     close(res[True][2], res[False][2], rtol=2e-3, atol=1e-5, msg="mse")
     close(res[True][1], res[False][1], rtol=2e-2, atol=3e-2 * res[False][1].abs().max().item(), msg="flat gradient")
+
+
+@pytest.mark.parametrize("attention_type,N,H,W", [("temporal", 14, 64, 64), ("temporal", 5, 50, 45), ("spatial", 6, 40, 64)])
+def test_train_kernel_planar_x_equals_record_x(attention_type, N, H, W):
+    """cgat_layer_train reading x chunk-planar (CGAT_X_PLANAR: TMA boxes with 128-byte rows, what TrainStep feeds it)
+    against the same kernel reading the pixel records: the tensor core sees identical operands, so everything but the
+    order of the cross-CTA atomics of the scalar sums is identical."""
+    from cgat.train_step import TrainStep
+
+    res = {}
+    for planar in (True, False):
+        ours, _ = _models(attention_type, "conv", seed=35)
+        torch.manual_seed(9)
+        x = torch.rand(N, H, W, 4, 6, device=DEV).bfloat16()
+        y = torch.rand(N, H, W, 4, 6, device=DEV).bfloat16()
+        ts = TrainStep(ours, x, y, use_graph=False)
+        assert ts.fused_stream is not None and ts.xp is not None
+        if not planar:
+            ts.xp = None
+        ts._fwd_bwd()
+        torch.cuda.synchronize()
+        res[planar] = (ts.loss.clone(), ts.flat_grad.clone(), ts.mse.clone())
+    close(res[True][0], res[False][0], rtol=1e-5, atol=1e-7, msg="loss")
+    close(res[True][2], res[False][2], rtol=1e-5, atol=1e-7, msg="mse")
+    close(res[True][1], res[False][1], rtol=1e-5, atol=1e-6 * res[False][1].abs().max().item(), msg="flat gradient")

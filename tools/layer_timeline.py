@@ -7,7 +7,7 @@ import torch
 # the stamps are compiled in only with TIMELINE=1: build that variant of the library next to the product one
 CS = os.path.join(ROOT, "extended-gan_b200", "csrc")
 subprocess.check_call(f"cd {CS} && mkdir -p build_tl && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo "
-                      f"-Xcompiler -fPIC --use_fast_math -DCGAT_LF_TIMELINE -c layer_fused.cu -o build_tl/layer_fused.o && "
+                      f"-Xcompiler -fPIC --use_fast_math -DCGAT_LF_TIMELINE {os.environ.get('CGAT_TL_DEFS', '')} -c layer_fused.cu -o build_tl/layer_fused.o && "
                       f"nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../libcgat_b200_timeline.so "
                       f"$(ls build/*.o | grep -v layer_fused.o) build_tl/layer_fused.o -lcuda", shell=True)
 os.environ["CGAT_B200_LIB"] = os.path.join(ROOT, "extended-gan_b200", "libcgat_b200_timeline.so")

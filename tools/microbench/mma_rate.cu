@@ -78,8 +78,8 @@ int main() {
   cudaMalloc(&out, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   const char* names[8] = {"none/K-major", "SW64/K-major", "SW128/K-major", "none/MN-major", "lf fprop", "lf wgrad", "none/K dense", "lf fprop M64"};
-  for (int mode = 4; mode < 6; ++mode)
-    for (int N : {16, 32, 80, 96, 128, 240, 256})
+  for (int mode = 0; mode < 8; ++mode)
+    for (int N : {32, 96, 128, 240, 256})
       for (int same : {1, 0}) {
         const int iters = 512;
         k<<<148, 128, 160 * 1024>>>(mode, N, iters, same, out);
