@@ -97,13 +97,13 @@ SIGNATURES = {
                                   ctypes.POINTER(ctypes.c_int32), _P],
     "cgat_stream_wpack_bytes": [ctypes.POINTER(StreamDesc), _I],
     "cgat_stream_prepare": [ctypes.POINTER(StreamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "cgat_stream_param_grads": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cgat_stream_param_grads": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "cgat_layer_supported": [ctypes.POINTER(LayerDesc)],
     "cgat_layer_workspace_bytes": [ctypes.POINTER(LayerDesc)],
     "cgat_layer_fwd": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P],
-    "cgat_layer_bwd": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+    "cgat_layer_bwd": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P],
-    "cgat_layer_train": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P,
+    "cgat_layer_train": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P,
                          ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P],
     "cgat_gat1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_gat1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
@@ -116,7 +116,7 @@ SIGNATURES = {
     "cgat_val_metrics": [_P, _P, _I64, _F, _F, _F, _I, _P, _P],
     "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
     "cgat_loader_gather_planar": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
-    "cgat_records_to_planar": [_P, _P, _I64, _I64, _I, _P],
+    "cgat_records_to_planar": [_P, _P, _I64, _I, _I, _I, _P],
 }
 
 _lib = None

@@ -286,7 +286,7 @@ class _GATStreamFn(torch.autograd.Function):
         ld = None
         if conv and FUSED_LAYER and dt == _lib.BF16 and cfg.softmax_axis == "neighbour":
             ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, cfg.merge, int(cfg.apply_elu),
-                                cfg.alpha)
+                                cfg.alpha, _lib.X_PLANAR)
             if not lib().cgat_layer_supported(ctypes.byref(ld)):
                 ld = None
         sd = _lib.StreamDesc(cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, 1 if conv else 0, int(cfg.adj_transpose),
@@ -313,6 +313,7 @@ class _GATStreamFn(torch.autograd.Function):
             cin, cout = T * V, heads * cfg.nodes * cfg.co
             cd = _conv_desc(N, H, W, cin, cout, 3, 3, 1, 1, 1, H, W, dt, 0)
             out = torch.empty(n_pix, cfg.out_rec, device=dev, dtype=x.dtype)
+            x = records_to_planar(x)  # the fused kernels read x padded chunk-planar; the backward keeps this copy
             _lib.call("cgat_layer_fwd", ctypes.byref(ld), ptr(x), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
                       ptr(out), st)
             ctx.cfg, ctx.sd, ctx.cd, ctx.conv, ctx.shape, ctx.ld = cfg, sd, cd, conv, (N, H, W, T, V), ld
@@ -385,7 +386,7 @@ class _GATStreamFn(torch.autograd.Function):
         g_a = [tg[per * k + per - 2] for k in range(heads)]
         g_B = [tg[per * k + per - 1] for k in range(heads)]
         Bs = [params[per * k + per - 1] for k in range(heads)]
-        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(gW), ptr(ga), ptr(gadj),
+        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(gW), ptr(ga), ptr(gadj), None,
                   _lib.ptr_array(Bs), None, None, None, _lib.ptr_array(g_w), _lib.ptr_array(g_b) if conv else None,
                   _lib.ptr_array(g_a), _lib.ptr_array(g_B), int(direct), st)
         grads = [None] * len(params) if direct else [g.to(p.dtype) for g, p in zip(tg, params)]
@@ -401,18 +402,18 @@ class _GATStreamFn(torch.autograd.Function):
         dev = x.device
         st = stream()
         dout = dout.contiguous()
-        na, nadj = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes
-        acc = torch.zeros(na + nadj, device=dev, dtype=torch.float32)
-        ga, gadj = acc[:na], acc[na:]
+        na, nadj, nb = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes, heads * (cfg.co + 2)
+        acc = torch.zeros(na + nadj + nb, device=dev, dtype=torch.float32)
+        ga, gadj, gb = acc[:na], acc[na:na + nadj], acc[na + nadj:]
         need_dx = ctx.needs_input_grad[0]
         dwh = torch.empty(N * H * W, heads * cfg.nodes * cfg.co, device=dev, dtype=x.dtype) if need_dx else None
         wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
         ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
         _lib.call("cgat_layer_bwd", ctypes.byref(ld), ptr(x), ptr(dout), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
-                  ptr(mc), ptr(dwh), ptr(wsp), ptr(ga), ptr(gadj), ctypes.byref(ncta), ctypes.byref(nt), st)
+                  ptr(mc), ptr(dwh), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ctypes.byref(ncta), ctypes.byref(nt), st)
         dx = None
         if need_dx:
-            dx = torch.empty_like(x)
+            dx = torch.empty(N, H, W, T, V, device=dev, dtype=x.dtype)
             _lib.call("cgat_conv2d_dgrad_packed", ctypes.byref(cd), ptr(dwh), ptr(wpack_d), ptr(dx), st)
         direct = DIRECT_GRAD and all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32
                                      for p in params)
@@ -422,7 +423,7 @@ class _GATStreamFn(torch.autograd.Function):
         g_a = [tg[per * k + 2] for k in range(heads)]
         g_B = [tg[per * k + 3] for k in range(heads)]
         Bs = [params[per * k + 3] for k in range(heads)]
-        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),
+        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
                   _lib.ptr_array(Bs), _lib.ptr_array([params[per * k] for k in range(heads)]),
                   _lib.ptr_array([params[per * k + 1] for k in range(heads)]),
                   _lib.ptr_array([params[per * k + 2] for k in range(heads)]), _lib.ptr_array(g_w), _lib.ptr_array(g_b),
@@ -438,31 +439,44 @@ def layer_train_supported(x, cfg: AttnConfig, mapping: str) -> bool:
     if cfg.merge != _lib.MERGE_MEAN or cfg.heads > 3 or cfg.softmax_axis != "neighbour":
         return False
     N, H, W, T, V = x.shape
-    ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, cfg.heads, cfg.layout, cfg.merge, int(cfg.apply_elu), cfg.alpha)
+    ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, cfg.heads, cfg.layout, cfg.merge, int(cfg.apply_elu), cfg.alpha,
+                        _lib.X_PLANAR)
     return bool(lib().cgat_layer_supported(ctypes.byref(ld)))
 
 
+def padded_width(w: int) -> int:
+    """Row length of the padded chunk-planar layout: one zero pixel left, zeros up to the 8-pixel tile grid + one right."""
+    return (w + 7) // 8 * 8 + 2
+
+
 def planar_shape(x_shape):
-    """Shape of the chunk-planar copy of ``x[N,H,W,T,V]``: ``[N, T*V/8, H, W, 8]`` (include/cgat_b200.h, CGAT_X_PLANAR)."""
+    """Shape of the padded chunk-planar copy of ``x[N,H,W,T,V]``: ``[N, T*V/8, H, padded_width(W), 8]``
+    (include/cgat_b200.h, CGAT_X_PLANAR): image column ``i`` at padded column ``i + 1``, every other column zero."""
     N, H, W, T, V = x_shape
     if (T * V) % 8:
         raise RuntimeError(f"chunk-planar x needs T*V to be a multiple of 8, got {T}*{V}")
-    return (N, T * V // 8, H, W, 8)
+    return (N, T * V // 8, H, padded_width(W), 8)
+
+
+def planar_zeros(x_shape, device) -> torch.Tensor:
+    """A zeroed padded chunk-planar buffer for ``x[N,H,W,T,V]``: the kernels that fill it never write the padding."""
+    return torch.zeros(planar_shape(x_shape), device=device, dtype=torch.bfloat16)
 
 
 def records_to_planar(x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-    """``x[N,H,W,T,V]`` bf16 pixel records -> chunk-planar ``[N, T*V/8, H, W, 8]`` (``cgat_records_to_planar``): the
-    fused layer kernels' fast input format, for tensors that did not come from ``cgat_loader_gather_planar``."""
+    """``x[N,H,W,T,V]`` bf16 pixel records -> padded chunk-planar (``cgat_records_to_planar``): the fused layer kernels'
+    input format, for tensors that did not come from ``cgat_loader_gather_planar``.  ``out``: a buffer from
+    ``planar_zeros`` (its padding columns must be zero and stay zero)."""
     require_cuda(x)
     if x.dtype != torch.bfloat16:
         raise RuntimeError("records_to_planar takes bf16 records")
     x = x.contiguous()
     N, H, W, T, V = x.shape
     if out is None:
-        out = torch.empty(planar_shape(x.shape), device=x.device, dtype=x.dtype)
+        out = planar_zeros(x.shape, x.device)
     elif tuple(out.shape) != planar_shape(x.shape) or out.dtype != x.dtype or not out.is_contiguous():
-        raise RuntimeError("records_to_planar: out must be a contiguous bf16 [N, T*V/8, H, W, 8] tensor")
-    _lib.call("cgat_records_to_planar", ptr(x), ptr(out), N, H * W, T * V, stream())
+        raise RuntimeError("records_to_planar: out must be a contiguous bf16 [N, T*V/8, H, padded_width(W), 8] tensor")
+    _lib.call("cgat_records_to_planar", ptr(x), ptr(out), N, H, W, T * V, stream())
     return out
 
 
@@ -479,10 +493,11 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     N, H, W, T, V = x.shape
     x = x.contiguous()
     y = y.contiguous()
-    if x_planar is not None:
-        require_cuda(x_planar)
-        if tuple(x_planar.shape) != planar_shape(x.shape) or x_planar.dtype != x.dtype or not x_planar.is_contiguous():
-            raise RuntimeError("gat_stream_train: x_planar must be the contiguous [N, T*V/8, H, W, 8] copy of x")
+    if x_planar is None:
+        x_planar = records_to_planar(x)
+    require_cuda(x_planar)
+    if tuple(x_planar.shape) != planar_shape(x.shape) or x_planar.dtype != x.dtype or not x_planar.is_contiguous():
+        raise RuntimeError("gat_stream_train: x_planar must be the contiguous padded chunk-planar copy of x")
     dev = x.device
     heads = cfg.heads
     ws = [params[4 * k] for k in range(heads)]
@@ -492,7 +507,7 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     if not all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in params):
         raise RuntimeError("gat_stream_train accumulates into existing contiguous fp32 .grad buffers")
     ld = _lib.LayerDesc(N, H, W, cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, cfg.merge, int(cfg.apply_elu), cfg.alpha,
-                        _lib.X_RECORDS if x_planar is None else _lib.X_PLANAR)
+                        _lib.X_PLANAR)
     sd = _lib.StreamDesc(cfg.nodes, cfg.ci, cfg.co, heads, cfg.layout, 1, int(cfg.adj_transpose), 1)
     st = stream()
     a_st = torch.empty(heads, 2 * cfg.co, device=dev, dtype=torch.float32)
@@ -502,16 +517,17 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     _lib.call("cgat_stream_prepare", ctypes.byref(sd), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
               _lib.ptr_array(Bs), ptr(wpack), None, None, ptr(bias_d), ptr(a_st), ptr(adj), st)
     mc = None if mask is None else mask.to(torch.uint8).contiguous()
-    na, nadj = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes
-    if acc is None or acc.numel() < na + nadj:  # ``acc``: a caller-owned, already zeroed fp32 accumulator
-        acc = torch.zeros(na + nadj, device=dev, dtype=torch.float32)
-    ga, gadj = acc[:na], acc[na:na + nadj]
+    na, nadj, nb = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes, heads * (cfg.co + 2)
+    if acc is None or acc.numel() < na + nadj + nb:  # ``acc``: a caller-owned, already zeroed fp32 accumulator
+        acc = torch.zeros(na + nadj + nb, device=dev, dtype=torch.float32)
+    ga, gadj, gb = acc[:na], acc[na:na + nadj], acc[na + nadj:na + nadj + nb]
     wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
     ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
-    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x if x_planar is None else x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
-              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(loss_out), ptr(mse_out), ctypes.byref(ncta), ctypes.byref(nt), st)
+    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
+              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ptr(loss_out), ptr(mse_out), ctypes.byref(ncta),
+              ctypes.byref(nt), st)
     tg = [p.grad for p in params]
-    _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj),
+    _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
               _lib.ptr_array(Bs), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
               _lib.ptr_array([tg[4 * k] for k in range(heads)]),
               _lib.ptr_array([tg[4 * k + 1] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 2] for k in range(heads)]),

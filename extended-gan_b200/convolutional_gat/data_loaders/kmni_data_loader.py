@@ -25,8 +25,9 @@ def gather_windows(frames_u8: t.Tensor, start: t.Tensor, *, crop=None, steps: in
                    power: float = 1.0, dtype=t.float32, out=None, planar: bool = False):
     """``frames_u8 [L, V, H, W]`` uint8 (device), ``start [N]`` int32 (device) -> ``(x, y)`` ``[N, H', W', steps, V]``.
 
-    ``planar=True`` (bf16 only): x is written chunk-planar ``[N, steps*V/8, H', W', 8]`` -- the fused layer kernels' fast
-    input format (``cgat_loader_gather_planar``); y keeps the record layout."""
+    ``planar=True`` (bf16 only): x is written PADDED CHUNK-PLANAR ``[N, steps*V/8, H', padded_width(W'), 8]`` -- the fused
+    layer kernels' input format (``cgat_loader_gather_planar``; ``cgat.functional.planar_zeros`` allocates it: the padding
+    columns are never written); y keeps the record layout."""
     _lib.require_cuda(frames_u8, start)
     if frames_u8.dtype != t.uint8 or start.dtype != t.int32:
         raise RuntimeError("gather_windows takes uint8 frames and int32 window starts")
@@ -36,13 +37,16 @@ def gather_windows(frames_u8: t.Tensor, start: t.Tensor, *, crop=None, steps: in
     cw = W if crop is None else min(crop, W)
     n = start.numel()
     if planar:
+        from cgat.functional import planar_shape, planar_zeros
+
         if out is None:
-            x = t.empty(n, steps * V // 8, ch, cw, 8, device=frames_u8.device, dtype=t.bfloat16)
+            x = planar_zeros((n, ch, cw, steps, V), frames_u8.device)
             y = t.empty(n, ch, cw, steps, V, device=frames_u8.device, dtype=t.bfloat16)
         else:
             x, y = out
-        if x.dtype != t.bfloat16 or y.dtype != t.bfloat16 or tuple(x.shape) != (n, steps * V // 8, ch, cw, 8):
-            raise RuntimeError("gather_windows(planar=True) writes bf16 x [N, steps*V/8, H, W, 8] and y [N, H, W, steps, V]")
+        if x.dtype != t.bfloat16 or y.dtype != t.bfloat16 or tuple(x.shape) != planar_shape((n, ch, cw, steps, V)):
+            raise RuntimeError("gather_windows(planar=True) writes bf16 x [N, steps*V/8, H, padded_width(W), 8] (zeroed "
+                               "padding) and y [N, H, W, steps, V]")
         _lib.call("cgat_loader_gather_planar", _lib.ptr(frames_u8), L, _lib.ptr(start), _lib.ptr(x), _lib.ptr(y), n, V, H, W,
                   ch, cw, steps, float(normalizing_max), float(power), _lib.stream())
         return x, y

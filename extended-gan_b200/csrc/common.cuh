@@ -111,12 +111,17 @@ __host__ __device__ inline int lf_score_rows(int nodes, int co, int heads) {
   return heads * nodes * co + ext <= 128 ? ext : 0;
 }
 // rows of a CTA's wgrad partial-sum slot (layer_fused.cu writes, stream_ops.cu reads): feature + score rows, rounded up
-// to a TMEM lane quarter.  Slot layout: [nt / 16 column blocks][rows][16 columns]  (coalesced writes, see layer_fused.cu)
+// to a TMEM lane quarter.  Slot layout: [nt / 8 column blocks][rows][8 columns]  (coalesced writes, see layer_fused.cu)
 __host__ __device__ inline int lf_partial_rows(int nodes, int co, int heads) {
   return (heads * nodes * co + lf_score_rows(nodes, co, heads) + 31) & ~31;
 }
 __host__ __device__ inline size_t lf_partial_index(int row, int col, int rows) {
-  return ((size_t)(col >> 4) * rows + row) * 16 + (col & 15);
+  return ((size_t)(col >> 3) * rows + row) * 8 + (col & 7);
 }
+// padded chunk-planar x (CGAT_X_PLANAR): [n][cin/8][h][wp][8]; one zero pixel left of the image, zeros up to the tile grid
+// and one more right of it.  Loader, converter and the layer kernels' tensor map must agree on this.
+__host__ __device__ inline int lf_padded_width(int w) { return ((w + 7) & ~7) + 2; }
+// K-chunks of the packed fprop weights: 9 taps x cin/8, one zero chunk (27 is odd), the bias chunk, one zero chunk
+__host__ __device__ inline int lf_weight_chunks(int cin) { return 9 * (cin / 8) + (9 * (cin / 8)) % 2 + 2; }
 
 }  // namespace cgat

@@ -15,16 +15,24 @@
 //             across all tiles of the persistent CTA.  Only x and d(out) (train mode: x and y) are read from
 //             HBM; only per-CTA partial sums of the parameter gradients are written.
 //
-// Column planes (the im2col that is NOT materialised): for horizontal tap s and 8-channel chunk c the TMA unit writes
-// the box  x[n][th*16-1 .. +17][tw*8-1+s .. +7][8c .. 8c+7]  as plane P(s,c) = [18 rows][8 cols][16 B]  (zero-filled
-// outside the image = the conv padding).  A plane row is the 8 pixels of one tile row = 128 contiguous, 128-byte
-// ALIGNED bytes = exactly one SWIZZLE_NONE core matrix; a vertical tap r is a shift of the operand's start address
-// by r rows (r * 128 B), so every core matrix the tensor core fetches stays 128-byte aligned (the first version of
-// this kernel shifted by 16 bytes per HORIZONTAL tap inside [16][10] row planes: two thirds of its operand fetches
-// straddled two 128-byte lines and an fprop MMA took ~150 cycles instead of ~75).  The same planes are a legal
-// operand both K-major (fprop A: K = (r; s,c) chunks) and MN-major (wgrad B: K = pixels, N = (s,c) chunks, one
-// accumulator per r).  9 boxes per tile replace the producer warps, the staging buffers and 56 KB of im2col.  A tenth
-// plane of ones per stage carries the bias into the fprop MMA and yields dbias in the wgrad MMA.
+// Interleaved planes (the im2col that is NOT materialised).  x arrives PADDED CHUNK-PLANAR, [n][cin/8][h][wp][8] with
+// wp = tiles_w * 8 + 2 (one zero pixel left, zeros right; cgat_loader_gather_planar / cgat_records_to_planar write it).
+// ONE 5-D TMA box per tile -- (8 pixels x 8 channels = 128 B; horizontal tap s: 3, stride ONE pixel, i.e. the dimension
+// overlaps the innermost one; chunk c; 18 rows; 1 image) -- lands as  stage[row 18][plane q = c*3 + s][128 B]:  every
+// 128-byte unit is one SWIZZLE_NONE core matrix (8 pixels of a tile row x 8 channels, 128-byte aligned), a row of the
+// stage holds the 9 planes side by side (1152 B), rows outside the image are zero-filled by the TMA unit and the
+// horizontal padding is the zero columns of the global layout.  Flattening  j = r * 9 + q  (r = vertical tap = one row
+// down) gives address j * 128: BOTH MMAs see uniform strides --
+//   fprop  A (K-major): K-chunk pair (j, j+1) at LBO = 128, pixel rows at SBO = 1152: 14 instructions for the 27 chunks
+//          (chunk 27 meets zero weights) + 1 for the bias (a constant plane of ones against the bias K-chunk);
+//   wgrad  B (MN-major): N = 27 chunks x 8 channels = 216 columns at SBO = 128, K = 16 pixels = two tile rows at
+//          LBO = 1152: ONE accumulator and 8 instructions per tile.
+// The first layout of this kernel kept one plane per (s, c) with 2304-byte plane stride: wgrad then needed one
+// accumulator per vertical tap (24 instructions, N = 80 each, and a ~280-cycle penalty whenever consecutive tcgen05.mma
+// switch accumulators) and the TMA unit 9 boxes per tile; with a ~105-cycle floor per tcgen05.mma whatever N <= 128
+// (tools/microbench/mma_rate.cu) the tensor pipe was the kernel's bottleneck (11 300 of 11 400 cycles per tile pair).
+// dbias no longer comes out of the wgrad MMA (no plane of ones among its columns): the attention threads sum d(Wh)
+// over their pixels themselves.
 //
 // Shared memory: [header | packed weights | d(Wh) buffers (ring of 2-3) | x stages (ring of 4)].  The x planes of a
 // tile live from its TMA load until its wgrad MMAs have read them; a d(Wh) buffer lives from the head exchange of
@@ -49,16 +57,16 @@ constexpr int LF_TMA_WARP = 0, LF_MMA_WARP = 1;
 constexpr int LF_MAXSTG = 4;        // x-plane stages (TMA prefetch depth)
 constexpr int LF_MAXDW = 3;         // d(Wh) buffers (backward kernels)
 constexpr int LF_FP_COL0 = 256;     // TMEM: wgrad accumulators at columns [0,256), fprop accumulators at 256 + 128*acc
-constexpr int LF_PR = LF_TH + 2;    // plane rows (vertical halo)
-constexpr int LF_ROW = LF_TW * 16;  // 128 B: one tile row of a plane = one core matrix
-constexpr int LF_PLANE = LF_PR * LF_ROW;      // 2304 B
+constexpr int LF_PR = LF_TH + 2;    // stage rows (vertical halo)
+constexpr int LF_ROW = LF_TW * 16;  // 128 B: 8 pixels x 8 channels = one core matrix
+constexpr int LF_ONES = 4096;       // constant A operand of the bias MMA: 16 core matrices of ones, then 16 of zeros
 constexpr int LF_HDR = 8704;        // barriers + parameters (fp32 and packed-half2 copies)
 constexpr int LF_SLOT = 64;         // floats per attention warp in the end-of-kernel reduction scratch (>= RG + 3)
 
 struct LfArgs {
   long long* dbg;              // developer aid: clock64() timeline of CTA 0 (cgat_layer_debug_timeline)
   const __nv_bfloat16* x;      // input records [n][h][w][cin] (read through the tensor map; the pointer serves L2 prefetches)
-  const __nv_bfloat16* wpack;  // [3*nq][npad][8] chunk-major packed dense weights (cgat_stream_prepare)
+  const __nv_bfloat16* wpack;  // [nj + 3][npad][8] chunk-major packed dense weights (cgat_stream_prepare)
   const float* bias;           // [cout] dense bias
   const float* a;              // [heads][2co]
   const float* adj;            // [heads][nodes][nodes]
@@ -69,16 +77,17 @@ struct LfArgs {
   float* partial;              // bwd: [grid][128][nt] wgrad partial sums
   float* ga;                   // bwd: [heads][2co]   accumulated into
   float* gadj;                 // bwd: [heads][nodes*nodes] accumulated into
+  float* gbias;                // bwd: [heads][co + 2] accumulated into: sum of d(Wh) per output channel, sum of ds1, of ds2
   const __nv_bfloat16* y;      // train mode (bwd kernel): target, same layout as out; d(out) is derived in-kernel
   float* loss_out;             // train mode: scalar loss, accumulated into
   float* mse_out;              // train mode, optional: mean squared error alone (the reference's running train loss)
   float out_scale;             // bwd: factor applied to the gradient sums when they leave the kernel (PAIR: 1/numel)
   float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
-  int h, w, cin, cout, ext, npad, heads, merge, apply_elu;  // ext: score rows behind the cout feature rows (0: none)
+  int h, w, wp, cin, cout, ext, npad, heads, merge, apply_elu;  // wp: padded row of x, lf_padded_width(w);  // ext: score rows behind the cout feature rows (0: none)
   float alpha;
-  int nchunk, nq, mchunk, nt;   // nq = 3*nchunk + 1 planes per stage (the last one is all ones); nt = 3 * nq * 8
+  int nchunk, np, nj, mchunk, nt;  // np = 3*nchunk planes per stage row, nj = 3*np K-chunks (fprop) = N-chunks (wgrad); nt = nj*8
+  int rowp;                        // bytes of a stage row: np * 128
   int tiles_h, tiles_w, tiles, nstg, ndw;
-  int x_planar;                 // x is chunk-planar [n][cin/8][h][w][8] (CGAT_X_PLANAR): 3 boxes of 128-byte rows per tile
   int rows_pad;                 // rows of a CTA's partial-sum slot: cout + ext rounded up to a lane quarter (32)
   uint32_t wbytes, stage_bytes, dw_bytes;  // bytes of one x stage / of one d(Wh) buffer (0 in the forward kernel)
 };
@@ -156,7 +165,8 @@ template <int NODES, int CO, bool SPATIAL, bool BWD, bool MASKED, bool PAIR>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   constexpr int REC = NODES * CO;          // elements of one head's pixel record
-  constexpr int RG = 2 * CO + NODES * NODES;  // a-grad + adjacency-grad values per head
+  constexpr int RGA = 2 * CO + NODES * NODES;  // adjacency-grad + a-grad values per head ...
+  constexpr int RG = RGA + CO + 2;             // ... + sum of d(Wh) per output channel (dbias), sum of ds1, sum of ds2
   static_assert(REC % 8 == 0, "record must be a multiple of 16 bytes");
   static_assert(RG + 3 <= LF_SLOT, "reduction slot too small");
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -183,7 +193,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   // buffer's unused rows read on into the x stages (finite data; those accumulator rows are never stored)
   unsigned char* s_dw = s_w + ((A.wbytes + 127u) & ~127u);
   unsigned char* s_stage = s_dw + (size_t)A.ndw * A.dw_bytes;
-  float4* s_slab = reinterpret_cast<float4*>(s_stage + (size_t)A.nstg * A.stage_bytes);  // fwd: [group][REC/4][128]
+  // (a stage is 18 rows + 128 zeroed bytes: fprop's K-chunk 27 -- the odd 27th chunk's partner, zero weights -- reads
+  // the first core matrix of "row 18" for the tile's last pixel row, and 0 x garbage may be NaN)
+  unsigned char* s_one = s_stage + (size_t)A.nstg * A.stage_bytes;
+  float4* s_slab = reinterpret_cast<float4*>(s_one + LF_ONES);  // fwd: [group][REC/4][128]
 
   // (the shuffle makes the warp index provably warp-uniform: role branches and everything computed under them can then
   // use the uniform datapath -- what CUTLASS calls canonical_warp_idx_sync)
@@ -210,27 +223,13 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   }
   __syncthreads();  // barriers are live: the TMA thread starts fetching while everyone else initialises shared memory
 
-  const uint32_t tile_bytes = (uint32_t)(A.nq - 1) * LF_PLANE;
-  auto issue_tile = [&](int tile, int stage) {  // 9 column-plane boxes of one tile (TMA thread only)
+  auto issue_tile = [&](int tile, int stage) {  // ONE box per tile: [18 rows][np planes][128 B] (TMA thread only)
     const int tw = tile % A.tiles_w;
     const int th = (tile / A.tiles_w) % A.tiles_h;
     const int n = tile / (A.tiles_w * A.tiles_h);
-    mbar_arrive_expect_tx(&full[stage], tile_bytes);
-    unsigned char* dst = s_stage + (size_t)stage * A.stage_bytes;
-    if (A.x_planar) {
-      // chunk-planar x: the box (8 pixels x 8 channels = one 128-byte row, 18 rows, all chunks) of horizontal tap sh IS
-      // the planes q = sh * nchunk + c, c = 0 .. nchunk-1, in order.  The TMA unit works per box ROW: 54 rows of 128 B
-      // per box here against 144 rows of 16 B per (sh, c) box of the record layout (measured: ~3 500 cycles per tile
-      // for the 9 small-row boxes, which put the x ring on the kernel's critical path)
-      for (int sh = 0; sh < 3; ++sh)
-        tma_load_4d(dst + (size_t)(sh * A.nchunk) * LF_PLANE, &tmap_x, (tw * LF_TW - 1 + sh) * 8, th * LF_TH - 1, 0, n,
-                    &full[stage]);
-      return;
-    }
-    for (int sh = 0; sh < 3; ++sh)
-      for (int c = 0; c < A.nchunk; ++c)
-        tma_load_4d(dst + (size_t)(sh * A.nchunk + c) * LF_PLANE, &tmap_x, c * 8, tw * LF_TW - 1 + sh, th * LF_TH - 1, n,
-                    &full[stage]);
+    mbar_arrive_expect_tx(&full[stage], (uint32_t)(LF_PR * A.rowp));
+    // coordinates (element in the padded row, tap s, chunk c, row, image): padded column tw*8 = image column tw*8 - 1
+    tma_load_5d(s_stage + (size_t)stage * A.stage_bytes, &tmap_x, tw * LF_TW * 8, 0, 0, th * LF_TH - 1, n, &full[stage]);
   };
   if (warp == LF_TMA_WARP && lane == 0) {
     // the first tile's planes before the (tile-independent) weights: the x planes are written whole by the TMA unit
@@ -239,7 +238,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     mbar_arrive_expect_tx(wbar, A.wbytes);
     bulk_g2s(s_w, A.wpack, A.wbytes, wbar);  // (the larger transfer first: the first fprop needs both)
     if ((int)blockIdx.x < A.tiles) issue_tile(blockIdx.x, 0);
-    if (A.x_planar && A.nstg > 1 && (int)(blockIdx.x + gridDim.x) < A.tiles) issue_tile(blockIdx.x + gridDim.x, 1);
+    if (A.nstg > 1 && (int)(blockIdx.x + gridDim.x) < A.tiles) issue_tile(blockIdx.x + gridDim.x, 1);
   }
   if (warp != LF_TMA_WARP) {
     // (warp 0 is busy issuing TMA instructions, ~100 cycles each: the other 15 warps initialise shared memory)
@@ -257,15 +256,17 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         if (A.mask == nullptr || A.mask[ti * NODES + j] != 0) mrow |= (1ull << j);
       s_mask[ti] = mrow;
     }
-    // d(Wh) buffers start zeroed (rows the attention groups never write must hold finite numbers); every x stage gets
-    // its plane of ones behind the im2col planes (its wgrad column is dbias; its fprop K-chunk holds the bias, hi + lo
-    // bf16 parts).  The TMA unit may already be writing the OTHER planes of the stages: disjoint addresses.
+    // d(Wh) buffers start zeroed (rows the attention groups never write must hold finite numbers); the constant
+    // operand of the bias MMA: 2 KB of bf16 ones (its fprop K-chunk holds the bias, hi + lo bf16 parts), 2 KB of zeros
     uint4* p = reinterpret_cast<uint4*>(s_dw);
     const int n16 = (int)((size_t)A.ndw * A.dw_bytes / 16);
     for (int i = ti; i < n16; i += NI) p[i] = make_uint4(0, 0, 0, 0);
-    for (int st = 0; st < A.nstg; ++st) {
-      uint4* o = reinterpret_cast<uint4*>(s_stage + (size_t)st * A.stage_bytes + (size_t)(A.nq - 1) * LF_PLANE);
-      for (int i = ti; i < LF_PLANE / 16; i += NI) o[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 1.0
+    for (int i = ti; i < A.nstg * 8; i += NI)  // the 128 zero bytes behind every stage's 18 rows (never written by the TMA unit)
+      reinterpret_cast<uint4*>(s_stage + (size_t)(i >> 3) * A.stage_bytes + (size_t)LF_PR * A.rowp)[i & 7] = make_uint4(0, 0, 0, 0);
+    uint4* o = reinterpret_cast<uint4*>(s_one);
+    for (int i = ti; i < LF_ONES / 16; i += NI) {
+      const uint32_t v = i < LF_ONES / 32 ? 0x3f803f80u : 0u;  // bf16 1.0 x2
+      o[i] = make_uint4(v, v, v, v);
     }
     fence_proxy_async_smem();
   }
@@ -284,7 +285,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
         LDBG(0);
-        if (it > (A.x_planar && A.nstg > 1 ? 1 : 0)) {  // (the first tile or two went out during set-up)
+        if (it > (A.nstg > 1 ? 1 : 0)) {  // (the first two tiles went out during set-up)
           if (it >= A.nstg) {
 #ifdef CGAT_LF_SLEEPY_TMA
             while (!mbar_try_wait(&empty[stage], phase ^ 1u)) __nanosleep(64);
@@ -300,7 +301,9 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     } else if (warp == LF_MMA_WARP) {
       // ===================== MMA issuer: the whole warp runs this converged, one elected lane issues (tc_common.cuh) ====
       const uint32_t idesc_f = make_idesc_bf16(128, A.npad, 0, 0);
-      const uint32_t idesc_w = make_idesc_bf16(128, A.nq * 8, 1, 1);
+      // wgrad N: the nj chunks rounded up to a multiple of 16 columns (M = 128 needs that); the odd 28th chunk is the x
+      // data one stage row further down -- finite numbers into accumulator columns nobody reads
+      const uint32_t idesc_w = make_idesc_bf16(128, (A.nj * 8 + 15) & ~15, 1, 1);
       const uint32_t w_addr = smem_u32(s_w);
       const uint32_t b_lbo = (uint32_t)A.npad * 16;
       uint32_t wg_accum = 0;
@@ -312,16 +315,15 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         tc_fence_after();
         const uint32_t dy_addr = smem_u32(s_dw) + (uint32_t)wbuf * A.dw_bytes;
         const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)wstage * A.stage_bytes;
+        // A = d(Wh) planes (MN-major: 8-cout chunks 2048 B apart, pixel groups = tile rows 128 B apart); B = the stage
+        // (MN-major: the nj chunks j = r * np + q 128 B apart, pixel groups = stage rows)
+        constexpr int ROWP = 3 * (NODES * CO / 8) * LF_ROW;  // (ci == co: the stage geometry is a compile-time constant)
         const uint64_t ad0 = make_smem_desc(dy_addr, 128, 2048);
-        const uint64_t bd0 = make_smem_desc(im_addr, LF_ROW, LF_PLANE);
+        const uint64_t bd0 = make_smem_desc(im_addr, ROWP, LF_ROW);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {  // vertical tap = the planes shifted by r rows (128 B); one accumulator each
-#pragma unroll
-          for (int jj = 0; jj < LF_TH / 2; ++jj) {  // K step: image rows 2jj, 2jj+1 of the tile (16 pixels)
-            umma_bf16_warp(tmem_base + (uint32_t)(r * A.nq * 8), ad0 + (uint64_t)((jj * 256) >> 4),
-                           bd0 + (uint64_t)(((r + 2 * jj) * LF_ROW) >> 4), idesc_w, wg_accum | (uint32_t)(jj > 0));
-          }
-        }
+        for (int jj = 0; jj < LF_TH / 2; ++jj)  // K step: image rows 2jj, 2jj+1 of the tile (16 pixels)
+          umma_bf16_warp(tmem_base, ad0 + (uint64_t)((jj * 256) >> 4), bd0 + (uint64_t)((2 * jj * ROWP) >> 4), idesc_w,
+                         wg_accum | (uint32_t)(jj > 0));
         wg_accum = 1;
         umma_commit_warp(&empty[wstage]);
         umma_commit_warp(&dwfree[wbuf]);
@@ -354,21 +356,17 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         tc_fence_after();
         const uint32_t im_addr = smem_u32(s_stage) + (uint32_t)stage * A.stage_bytes;
         const uint32_t d_addr = tmem_base + LF_FP_COL0 + (uint32_t)acc * 128;
-        // (the served shapes have ci == co, so the plane count is a compile-time constant and the 15 descriptor pairs
-        // are the first one plus immediates: a handful of uniform-datapath instructions per tcgen05.mma)
-        constexpr int NQ = 3 * (NODES * CO / 8) + 1;
-        const uint64_t ad0 = make_smem_desc(im_addr, LF_PLANE, LF_ROW);
+        // (the served shapes have ci == co, so the chunk count is a compile-time constant and the descriptor pairs are
+        // the first one plus immediates: a handful of uniform-datapath instructions per tcgen05.mma)
+        constexpr int NP = 3 * (NODES * CO / 8), NJ = 3 * NP, ROWP = NP * LF_ROW;
+        const uint64_t ad0 = make_smem_desc(im_addr, LF_ROW, ROWP);  // K-chunk pair (j, j+1) 128 B apart, tile rows ROWP apart
         const uint64_t bd0 = make_smem_desc(w_addr, b_lbo, 128);
         const uint32_t b_step = (2 * b_lbo) >> 4;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-          for (int q = 0; q < NQ; q += 2) {  // K = 16: planes q, q+1 shifted by the vertical tap r
-            const int kp = r * (NQ / 2) + q / 2;
-            umma_bf16_warp(d_addr, ad0 + (uint64_t)((q * LF_PLANE + r * LF_ROW) >> 4), bd0 + (uint64_t)(kp * b_step), idesc_f,
-                           kp > 0);
-          }
-        }
+        for (int i = 0; i < (NJ + 1) / 2; ++i)  // K = 16: chunks 2i, 2i+1 of j = r * NP + q
+          umma_bf16_warp(d_addr, ad0 + (uint64_t)((2 * i * LF_ROW) >> 4), bd0 + (uint64_t)(i * b_step), idesc_f, i > 0);
+        // + bias: a plane of ones (then zeros) against the K-chunk pair behind the last x pair
+        umma_bf16_warp(d_addr, make_smem_desc(smem_u32(s_one), LF_ONES / 2, 128), bd0 + (uint64_t)(((NJ + 1) / 2) * b_step), idesc_f, 1);
         umma_commit_warp(&tfull[acc]);
         LDBG(6);
 #ifdef CGAT_LF_TIMELINE
@@ -433,9 +431,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         const __half2* adj2 = s_adj2 + k * NODES * NODES;
         const __half2 alpha2 = __float2half2_rn(A.alpha);
         const __half2 gs2 = __float2half2_rn(inv_heads);
-        __half2 g2[NODES * NODES];
+        __half2 g2[NODES * NODES], gb2[CO + 2];
 #pragma unroll
         for (int i = 0; i < NODES * NODES; ++i) g2[i] = H2::zero();
+#pragma unroll
+        for (int i = 0; i < CO + 2; ++i) gb2[i] = H2::zero();
         const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
         const uint32_t xplane = (uint32_t)A.mchunk * 2048;  // the score-row planes (after the feature planes)
         int itp = 0;
@@ -472,15 +472,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               const int tile = tileA + ahead * (int)gridDim.x;
               if (tile < A.tiles) {
                 const int tw = tile % A.tiles_w, th = (tile / A.tiles_w) % A.tiles_h, n = tile / (A.tiles_w * A.tiles_h);
-                if (A.x_planar) {  // one 128-byte line = the 8 pixels of a tile row in one chunk plane: nchunk * 16 lines
-                  const int c = m >> 4, h = th * LF_TH + (m & 15), w = tw * LF_TW;
-                  if (c < A.nchunk && h < A.h)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + ((((long long)n * A.nchunk + c) * A.h + h) * A.w + w) * 8));
-                } else {
-                  const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
-                  if (h < A.h && w < A.w)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + (((long long)n * A.h + h) * A.w + w) * A.cin));
-                }
+                // one 128-byte line = the 8 pixels of a tile row in one chunk plane (+ 16 B of padding offset): the two
+                // lines it straddles are the neighbouring tiles' as well -- nchunk * 16 prefetches per tile
+                const int c = m >> 4, h = th * LF_TH + (m & 15), w = tw * LF_TW + 1;
+                if (c < A.nchunk && h < A.h)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + ((((long long)n * A.nchunk + c) * A.h + h) * A.wp + w) * 8));
               }
             }
           }
@@ -657,6 +653,22 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           __half2 ds[2 * NODES];
           attn_nb_backward_inplace<H2, NODES, CO, MASKED>(Wh2, z2, adj2, s_mask, alpha2, st, &g2[0], ds);  // z2: dz -> d(Wh)
           if (dbg_thread) LDBG(13);
+          // bias gradient: d(Wh) summed over this thread's nodes and pixels, and the sums of ds1 / ds2 (the bias terms of
+          // the score rows); packed like the adjacency sums (O(1) terms, <= 8 pairs)
+#pragma unroll
+          for (int u = 0; u < CO; ++u) {
+            __half2 t = z2[0][u];
+#pragma unroll
+            for (int v = 1; v < NODES; ++v) t = __hadd2(t, z2[v][u]);
+            gb2[u] = __hadd2(gb2[u], t);
+          }
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            __half2 t = ds[w * NODES];
+#pragma unroll
+            for (int v = 1; v < NODES; ++v) t = __hadd2(t, ds[w * NODES + v]);
+            gb2[CO + w] = __hadd2(gb2[CO + w], t);
+          }
           // ---- d(Wh) (z2) -> bf16 A planes of the wgrad MMA of both tiles ----
           {
             const uint32_t dyA = exA + (uint32_t)(k * CH) * 2048, dyB = exB + (uint32_t)(k * CH) * 2048;
@@ -715,6 +727,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         for (int i = 0; i < NODES * NODES; ++i) {
           const float2 f = __half22float2(g2[i]);
           gacc[i] += f.x + f.y;
+        }
+#pragma unroll
+        for (int i = 0; i < CO + 2; ++i) {
+          const float2 f = __half22float2(gb2[i]);
+          gacc[RGA + i] += f.x + f.y;
         }
       } else {
       int it = 0;
@@ -894,6 +911,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
             attn_nb_backward<F32, NODES, CO, MASKED>(Wh, dz, s_a + k * 2 * CO, s_adj + k * NODES * NODES, s_mask, A.alpha, st,
                                                      z, &gacc[NODES * NODES], &gacc[0]);  // z now holds d(Wh)
             if (dbg_thread) LDBG(13);
+#pragma unroll
+            for (int u = 0; u < CO; ++u)  // bias gradient: d(Wh) summed over nodes (and, in gacc, over this thread's pixels)
+#pragma unroll
+              for (int v = 0; v < NODES; ++v) gacc[RGA + u] += z[v][u];
             mat_to_rec<NODES, CO, SPATIAL>(z, rec);
             // d(Wh) -> the MN-major A operand of the wgrad MMA: plane = dense cout / 8, 16 bytes per pixel
             const uint32_t dy = dwb + (uint32_t)(k * (REC / 8)) * 2048;
@@ -969,9 +990,15 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
               loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, off);
               mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, off);
             }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+              for (int i = 0; i < CO + 2; ++i) gacc[RGA + i] += __shfl_xor_sync(0xffffffffu, gacc[RGA + i], off);
             if ((lane & 1) == 0) slot[lane >> 1] = gacc[0];
-            if (lane < RG - NODES * NODES) slot[NODES * NODES + lane] = 0.f;
+            if (lane < RGA - NODES * NODES) slot[NODES * NODES + lane] = 0.f;
             if (lane == 0) {
+#pragma unroll
+              for (int i = 0; i < CO + 2; ++i) slot[RGA + i] = gacc[RGA + i];
               slot[RG] = loss_acc;
               slot[RG + 1] = mse_acc;
               reinterpret_cast<int*>(slot)[RG + 2] = cur_head;
@@ -998,17 +1025,18 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         mbar_wait(done, 0);
         tc_fence_after();
         if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(5);
-        // slot layout [16-column block][row][16]: a thread's 16 columns are 64 contiguous bytes and a warp's rows follow
-        // each other -- 2 KB per warp and column block, fully coalesced (row-major slots made every lane of a store hit its
+        // slot layout [8-column block][row][8]: a thread's 8 columns are 32 contiguous bytes and a warp's rows follow each
+        // other -- 1 KB per warp and column block, fully coalesced (row-major slots made every lane of a store hit its
         // own 32-byte sector, half used: the 123 KB of a CTA took 6 000 cycles)
         if (lg * 32 < A.rows_pad) {
-          float* pslot = A.partial + (size_t)blockIdx.x * A.rows_pad * A.nt + (size_t)m * 16;
-          for (int c0 = g * 16; c0 < A.nt; c0 += nact * 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
-            float4* dst = reinterpret_cast<float4*>(pslot + (size_t)(c0 >> 4) * A.rows_pad * 16);
+          float* pslot = A.partial + (size_t)blockIdx.x * A.rows_pad * A.nt + (size_t)m * 8;
+          for (int c0 = g * 8; c0 < A.nt; c0 += nact * 8) {
+            float v[8];
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
+            tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(pslot + (size_t)(c0 >> 3) * A.rows_pad * 8);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2; ++i)
               dst[i] = make_float4(v[4 * i] * A.out_scale, v[4 * i + 1] * A.out_scale, v[4 * i + 2] * A.out_scale,
                                    v[4 * i + 3] * A.out_scale);
           }
@@ -1029,7 +1057,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         if (reinterpret_cast<const int*>(slots + wa * LF_SLOT)[RG + 2] == k) v += slots[wa * LF_SLOT + r];
       v *= A.out_scale;
       if (r < NODES * NODES) atomicAdd(A.gadj + (size_t)k * NODES * NODES + r, v);
-      else atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
+      else if (r < RGA) atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
+      else atomicAdd(A.gbias + (size_t)k * (CO + 2) + (r - RGA), v);
     }
     if (A.y != nullptr && threadIdx.x == 0) {
       float l = 0.f, q = 0.f;
@@ -1054,7 +1083,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
 
 // ---- host side ------------------------------------------------------------------------------------------
 struct LfGeom {
-  int cin, cout, ext, rec, nchunk, nq, npad, mchunk, nt, rows_pad;
+  int cin, cout, ext, rec, nchunk, np, nj, npad, mchunk, nt, rows_pad, rowp;
   uint32_t wbytes, stage_bytes, dw_bytes;
   size_t smem;
   int tiles_h, tiles_w, tiles, nstg, ndw;
@@ -1066,14 +1095,16 @@ static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
   g.cin = d->nodes * d->ci;
   g.cout = d->heads * g.rec;
   g.nchunk = g.cin / 8;
-  g.nq = 3 * g.nchunk + 1;            // column planes per stage, the last one all ones
+  g.np = 3 * g.nchunk;                // planes per stage row: (chunk c, horizontal tap s)
+  g.nj = 3 * g.np;                    // K-chunks of fprop = N-chunks of wgrad: j = r * np + q
+  g.rowp = g.np * LF_ROW;
   g.ext = lf_score_rows(d->nodes, d->co, d->heads);  // score rows W.a behind the feature rows (common.cuh)
   g.npad = (g.cout + g.ext + 15) & ~15;
   g.mchunk = g.cout / 8;
-  g.nt = 3 * g.nq * 8;                // wgrad partial columns: [r][(s,c) | ones][8]
+  g.nt = g.nj * 8;                    // wgrad partial columns: [r][c][s][8]
   g.rows_pad = lf_partial_rows(d->nodes, d->co, d->heads);
-  g.wbytes = (uint32_t)(3 * g.nq) * g.npad * 16;
-  g.stage_bytes = ((uint32_t)g.nq * LF_PLANE + 127u) & ~127u;
+  g.wbytes = (uint32_t)lf_weight_chunks(g.cin) * g.npad * 16;  // nj chunks + a zero one, the bias chunk + a zero one
+  g.stage_bytes = (uint32_t)LF_PR * g.rowp + 128;  // + one zeroed core matrix: the odd last K-chunk's partner, see the kernel
   // a d(Wh) buffer: feature planes, then the score-row planes -- at least rec/8 of them: the train kernel passes d(out)
   // between the head groups through them
   const int xplanes = g.ext / 8 > g.rec / 8 ? g.ext / 8 : g.rec / 8;
@@ -1082,7 +1113,7 @@ static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
   g.ndw = bwd ? LF_MAXDW : 0;
   auto total = [&]() {
     return (size_t)LF_HDR + ((g.wbytes + 127u) & ~127u) + (size_t)g.ndw * g.dw_bytes + (size_t)g.nstg * g.stage_bytes +
-           (bwd ? 0 : (size_t)LF_GROUPS * g.rec * 128 * 4);
+           LF_ONES + (bwd ? 0 : (size_t)LF_GROUPS * g.rec * 128 * 4);
   };
   // shed a d(Wh) buffer first (two serve a tile pair), then x stages
   while ((g.smem = total()) > 227 * 1024 && g.ndw > 2) --g.ndw;
@@ -1109,8 +1140,7 @@ int layer_supported(const cgat_layer_desc* d) {
   const bool shape_ok = (sp && d->nodes == 6 && d->ci == 4 && d->co == 4) || (!sp && d->nodes == 4 && d->ci == 6 && d->co == 6);
   if (!shape_ok) return 0;
   const LfGeom f = lf_geom(d, false), b = lf_geom(d, true);
-  if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.npad > 128 || f.nt > 256) return 0;
-  if (f.nq % 2) return 0;  // fprop consumes the planes (+ the ones plane) in pairs: K = 16 per tcgen05.mma
+  if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.npad > 128 || ((f.nt + 15) & ~15) > 256) return 0;
   if (d->ci != d->co) return 0;  // (the kernel derives its plane count from nodes * co)
   if (f.smem > 227 * 1024 || b.smem > 227 * 1024) return 0;
   return 1;
@@ -1122,35 +1152,21 @@ size_t layer_partial_bytes(const cgat_layer_desc* d) {
   return (size_t)(148 + 1) * 128 * g.nt * sizeof(float);
 }
 
-// 4-D map over NHWC bf16 [n][h][w][c], box (8, wp, hp, 1): lands as [hp][wp][16 B]; out-of-image = zero (conv padding)
-static int make_nhwc_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int wp, int hp) {
-  EncodeTiledFn enc = get_encode_tiled();
-  if (!enc) return fail(CGAT_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-  ensure_context();
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {8, (cuuint32_t)wp, (cuuint32_t)hp, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(CGAT_EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return 0;
-}
-
-// chunk-planar x [n][c/8][h][w][8] as the 4-D tensor [n][c/8][h][w*8]: box (64 elements = 8 pixels of one chunk = 128 B,
-// hp rows, all chunks, 1) lands as [chunk][hp][128 B] = the column planes of one horizontal tap; a start coordinate of
-// -8 / beyond w*8 is the conv's zero padding
+// Padded chunk-planar x [n][c/8][h][wp][8] (wp = lf_padded_width(w)) as the 5-D tensor
+//   (element of the padded row: wp*8 | horizontal tap s: 3, stride ONE pixel = 16 B | chunk | row | image).
+// The tap dimension overlaps the innermost one -- the encoder and the TMA unit accept that (tools/microbench/
+// tma_overlap.cu checks the landing) -- so ONE box (64, 3, nchunk, hp, 1) lands as [row][chunk][tap][8 px][8 ch]:
+// the stage layout of layer_kernel.  Rows outside the image are zero-filled; the horizontal padding is in the data.
 static int make_planar_map(CUtensorMap* map, const void* base, int n, int h, int w, int c, int hp) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(CGAT_EUNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   ensure_context();
-  const int nchunk = c / 8;
-  cuuint64_t dims[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)nchunk, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)nchunk * h * w * 16};
-  cuuint32_t box[4] = {64, (cuuint32_t)hp, (cuuint32_t)nchunk, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  const int nchunk = c / 8, wp = lf_padded_width(w);
+  cuuint64_t dims[5] = {(cuuint64_t)wp * 8, 3, (cuuint64_t)nchunk, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[4] = {16, (cuuint64_t)h * wp * 16, (cuuint64_t)wp * 16, (cuuint64_t)nchunk * h * wp * 16};
+  cuuint32_t box[5] = {64, 3, (cuuint32_t)nchunk, (cuuint32_t)hp, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CGAT_EINVAL, "cuTensorMapEncodeTiled (planar x) failed with CUresult %d", (int)r);
@@ -1182,7 +1198,7 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
 
 int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias, const float* a,
                  const float* adj, const uint8_t* mask, void* out, const void* dout, void* dwh, float* partial,
-                 float* ga, float* gadj, int* ncta_out, int* nt_out, cudaStream_t st, const void* y = nullptr,
+                 float* ga, float* gadj, float* gbias, int* ncta_out, int* nt_out, cudaStream_t st, const void* y = nullptr,
                  float* loss_out = nullptr, float lambda = 0.f, float* mse_out = nullptr) {
   if (!layer_supported(d)) return fail(CGAT_EUNSUPPORTED, "fused conv-GAT layer kernel does not support this shape");
   if (!aligned16(x) || !aligned16(wpack) || (out && !aligned16(out)) || (dout && !aligned16(dout)) ||
@@ -1190,28 +1206,25 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
     return fail(CGAT_EALIGN, "layer tensors must be 16-byte aligned");
   const LfGeom g = lf_geom(d, bwd);
   CUtensorMap map;
-  if (d->x_layout != CGAT_X_RECORDS && d->x_layout != CGAT_X_PLANAR) return fail(CGAT_EINVAL, "bad x_layout %d", d->x_layout);
-  if (d->x_layout == CGAT_X_PLANAR) {
-    if (int rc = make_planar_map(&map, x, d->n, d->h, d->w, g.cin, LF_PR)) return rc;
-  } else if (int rc = make_nhwc_map(&map, x, d->n, d->h, d->w, g.cin, LF_TW, LF_PR)) {
-    return rc;
-  }
+  if (d->x_layout != CGAT_X_PLANAR)
+    return fail(CGAT_EINVAL, "the fused layer kernels read x padded chunk-planar (x_layout = CGAT_X_PLANAR): convert pixel "
+                             "records with cgat_records_to_planar, or let cgat_loader_gather_planar write it");
+  if (int rc = make_planar_map(&map, x, d->n, d->h, d->w, g.cin, LF_PR)) return rc;
   LfArgs A{};
   A.dbg = g_lf_dbg;
   A.x = (const __nv_bfloat16*)x;
   A.wpack = (const __nv_bfloat16*)wpack; A.bias = bias; A.a = a; A.adj = adj; A.mask = mask;
   A.out = (__nv_bfloat16*)out; A.dout = (const __nv_bfloat16*)dout; A.dwh = (__nv_bfloat16*)dwh;
-  A.partial = partial; A.ga = ga; A.gadj = gadj;
+  A.partial = partial; A.ga = ga; A.gadj = gadj; A.gbias = gbias;
   A.y = (const __nv_bfloat16*)y; A.loss_out = loss_out; A.mse_out = mse_out; A.lambda = lambda;
   A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
   // the paired half2 kernel carries d(out) without its 1/numel factor; CGAT_NO_PAIR=1 keeps the fp32 one-tile kernel
   static const bool no_pair = std::getenv("CGAT_NO_PAIR") != nullptr;
   A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && g.ndw >= 2 && g.ext > 0 && d->heads <= LF_GROUPS && !no_pair)
                     ? A.inv_n : 1.f;
-  A.h = d->h; A.w = d->w; A.cin = g.cin; A.cout = g.cout; A.ext = g.ext; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
+  A.h = d->h; A.w = d->w; A.wp = lf_padded_width(d->w); A.cin = g.cin; A.cout = g.cout; A.ext = g.ext; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
-  A.nchunk = g.nchunk; A.nq = g.nq; A.mchunk = g.mchunk; A.nt = g.nt; A.rows_pad = g.rows_pad;
-  A.x_planar = d->x_layout == CGAT_X_PLANAR;
+  A.nchunk = g.nchunk; A.np = g.np; A.nj = g.nj; A.rowp = g.rowp; A.mchunk = g.mchunk; A.nt = g.nt; A.rows_pad = g.rows_pad;
   A.tiles_h = g.tiles_h; A.tiles_w = g.tiles_w; A.tiles = g.tiles; A.nstg = g.nstg; A.ndw = g.ndw;
   A.wbytes = g.wbytes; A.stage_bytes = g.stage_bytes; A.dw_bytes = g.dw_bytes;
   if (ncta_out) *ncta_out = g.tiles < lf_sm_count() ? g.tiles : lf_sm_count();
@@ -1237,18 +1250,18 @@ extern "C" int cgat_layer_fwd(const cgat_layer_desc* d, const void* x, const voi
                               const float* a, const float* adj, const uint8_t* mask, void* out, void* stream) {
   if (!d || !x || !wpack || !a || !adj || !out) return fail(CGAT_EINVAL, "null argument");
   return layer_launch(false, d, x, wpack, bias_dense, a, adj, mask, out, nullptr, nullptr, nullptr, nullptr, nullptr,
-                      nullptr, nullptr, (cudaStream_t)stream);
+                      nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, const void* wpack,
                               const float* bias_dense, const float* a, const float* adj, const uint8_t* mask,
-                              void* dwh, void* workspace, float* ga, float* gadj, int32_t* ncta_out, int32_t* nt_out,
-                              void* stream) {
-  if (!d || !x || !dout || !wpack || !a || !adj || !workspace || !ga || !gadj || !ncta_out || !nt_out)
+                              void* dwh, void* workspace, float* ga, float* gadj, float* gbias, int32_t* ncta_out,
+                              int32_t* nt_out, void* stream) {
+  if (!d || !x || !dout || !wpack || !a || !adj || !workspace || !ga || !gadj || !gbias || !ncta_out || !nt_out)
     return fail(CGAT_EINVAL, "null argument");
   int ncta = 0, nt = 0;
   const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, dout, dwh, (float*)workspace, ga,
-                              gadj, &ncta, &nt, (cudaStream_t)stream);
+                              gadj, gbias, &ncta, &nt, (cudaStream_t)stream);
   *ncta_out = ncta;
   *nt_out = nt;
   return rc;
@@ -1256,16 +1269,16 @@ extern "C" int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const voi
 
 extern "C" int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
                                 const float* bias_dense, const float* a, const float* adj, const uint8_t* mask,
-                                float lambda, void* workspace, float* ga, float* gadj, float* loss_out, float* mse_out,
-                                int32_t* ncta_out, int32_t* nt_out, void* stream) {
-  if (!d || !x || !y || !wpack || !a || !adj || !workspace || !ga || !gadj || !loss_out || !ncta_out || !nt_out)
+                                float lambda, void* workspace, float* ga, float* gadj, float* gbias, float* loss_out,
+                                float* mse_out, int32_t* ncta_out, int32_t* nt_out, void* stream) {
+  if (!d || !x || !y || !wpack || !a || !adj || !workspace || !ga || !gadj || !gbias || !loss_out || !ncta_out || !nt_out)
     return fail(CGAT_EINVAL, "null argument");
   if (d->merge != CGAT_MERGE_MEAN || d->heads > LF_GROUPS)
     return fail(CGAT_EUNSUPPORTED, "cgat_layer_train serves mean-merged streams with at most %d heads", LF_GROUPS);
   if (!aligned16(y)) return fail(CGAT_EALIGN, "y must be 16-byte aligned");
   int ncta = 0, nt = 0;
   const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, nullptr, nullptr, (float*)workspace,
-                              ga, gadj, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda, mse_out);
+                              ga, gadj, gbias, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda, mse_out);
   *ncta_out = ncta;
   *nt_out = nt;
   return rc;

@@ -85,12 +85,14 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     T* dst = (half ? y : x) + pix * rec;
-    // chunk-planar x (CGAT_X_PLANAR, the fused layer kernels' fast input format): 16-byte chunk q of the record goes to
-    // plane q of the sample, [n][rec/8][crop_h][crop_w][8] -- consecutive threads write consecutive 16-byte slots
+    // padded chunk-planar x (CGAT_X_PLANAR, the fused layer kernels' input format): 16-byte chunk q of the record goes
+    // to plane q of the sample, [n][rec/8][crop_h][wp][8], image column w at padded column w + 1 -- consecutive threads
+    // write consecutive 16-byte slots; the padding columns are never written (the buffer is zeroed once)
     size_t qstride = 1;  // distance between a record's 16-byte chunks, in uint4
     if (half == 0 && x_planar) {
-      dst = x + ((size_t)s * (rec * sizeof(T) / 16) * per_sample + p0 + threadIdx.x) * (16 / sizeof(T));
-      qstride = (size_t)per_sample;
+      const int p = (int)p0 + threadIdx.x, hh = p / crop_w, ww = p - hh * crop_w, wp = lf_padded_width(crop_w);
+      qstride = (size_t)crop_h * wp;
+      dst = x + ((size_t)s * (rec * sizeof(T) / 16) * qstride + (size_t)hh * wp + ww + 1) * (16 / sizeof(T));
     }
     const uint8_t* col = tile + (size_t)(half * rec) * LD_THREADS + threadIdx.x;
     if constexpr (RECT != 0 && (RECT * sizeof(T)) % 16 == 0) {
@@ -119,13 +121,17 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
   }
 }
 
-// pixel records [n][pix][rec] -> chunk-planar [n][rec/8][pix][8] (bf16): for x tensors that did not come from the loader
-// kernel.  One thread per pixel: rec/8 16-byte loads (a warp reads 32 * rec * 2 contiguous bytes), rec/8 coalesced stores.
+// pixel records [n][h][w][rec] -> padded chunk-planar [n][rec/8][h][wp][8] (bf16): for x tensors that did not come from
+// the loader kernel.  One thread per pixel: rec/8 16-byte loads (a warp reads 32 * rec * 2 contiguous bytes), rec/8
+// coalesced stores.  Padding columns are not written.
 __global__ void __launch_bounds__(256) records_to_planar_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
-                                                                  long long n_pix, long long per_sample, int nchunk) {
+                                                                  long long n_pix, int h, int w, int nchunk) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pix) return;
-  const long long smp = p / per_sample, q = p - smp * per_sample;
+  const int wp = lf_padded_width(w);
+  const long long per_sample = (long long)h * w, smp = p / per_sample, q = p - smp * per_sample;
+  const int hh = (int)(q / w), ww = (int)(q - (long long)hh * w);
+  const long long plane = (long long)h * wp;
   uint4 v[8];
   for (int c0 = 0; c0 < nchunk; c0 += 8) {
 #pragma unroll
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(256) records_to_planar_kernel(const uint4* __r
       if (c0 + c < nchunk) v[c] = in[p * nchunk + c0 + c];
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-      if (c0 + c < nchunk) out[(smp * nchunk + c0 + c) * per_sample + q] = v[c];
+      if (c0 + c < nchunk) out[(smp * nchunk + c0 + c) * plane + (long long)hh * wp + ww + 1] = v[c];
   }
 }
 
@@ -160,14 +166,14 @@ extern "C" int cgat_loader_gather_planar(const uint8_t* frames, int64_t n_frames
                             power, CGAT_BF16, 1, stream);
 }
 
-extern "C" int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int64_t pix_per_sample, int32_t rec,
+extern "C" int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int32_t h, int32_t w, int32_t rec,
                                       void* stream) {
   if (!x || !x_planar) return fail(CGAT_EINVAL, "null argument");
-  if (n < 1 || pix_per_sample < 1 || rec < 8 || rec % 8) return fail(CGAT_EINVAL, "records_to_planar: rec must be a multiple of 8");
+  if (n < 1 || h < 1 || w < 1 || rec < 8 || rec % 8) return fail(CGAT_EINVAL, "records_to_planar: rec must be a multiple of 8");
   if (!aligned16(x) || !aligned16(x_planar)) return fail(CGAT_EALIGN, "records_to_planar: 16-byte aligned tensors");
-  const long long n_pix = (long long)n * pix_per_sample;
+  const long long n_pix = (long long)n * h * w;
   records_to_planar_kernel<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, (uint4*)x_planar, n_pix, pix_per_sample, rec / 8);
+      (const uint4*)x, (uint4*)x_planar, n_pix, h, w, rec / 8);
   return check_launch("records_to_planar_kernel");
 }
 

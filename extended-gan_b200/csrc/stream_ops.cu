@@ -117,21 +117,21 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepA
     A.bias_dense[i] = A.bias.p[k] ? A.bias.p[k][u] : 0.f;
   }
   if (A.d.wgrad_cols) {
-    // fused layer kernels (layer_fused.cu): K-chunk kk = r*nq + q, q = s*nchunk + c for the column plane of horizontal
-    // tap s and channel chunk c, vertical tap r; q = nq-1 multiplies the plane of ones: bias (hi + lo bf16 parts) at r = 0
-    const int nq = 3 * g.nchunk + 1;
-    const long long n_f = (long long)3 * nq * g.npad * 8;
+    // fused layer kernels (layer_fused.cu): K-chunk kk = (r * nchunk + c) * 3 + s for vertical tap r, channel chunk c,
+    // horizontal tap s (the order of the interleaved stage planes); then one zero chunk when 9 * nchunk is odd, the bias
+    // chunk (hi + lo bf16 parts in elements 0, 1: it multiplies a plane of ones) and one more zero chunk
+    const int nj = 9 * g.nchunk, kbias = nj + (nj & 1);
+    const long long n_f = (long long)lf_weight_chunks(g.cin) * g.npad * 8;
     for (long long i = tid; i < n_f; i += nt) {
       const int e = (int)(i & 7);
       const long long qq = i >> 3;
       const int row = (int)(qq % g.npad);
       const int kk = (int)(qq / g.npad);
-      const int r = kk / nq, q = kk - r * nq;
       float v = 0.f;
-      if (q < nq - 1) {
-        const int s = q / g.nchunk, c = q - s * g.nchunk;
-        v = row < g.cout ? dense_w(g, A.w, row, r * 3 + s, c * 8 + e) : dense_ws(g, A.w, A.a, row, r * 3 + s, c * 8 + e);
-      } else if (r == 0 && e < 2) {
+      if (kk < nj) {
+        const int r = kk / (3 * g.nchunk), rem = kk - r * 3 * g.nchunk, c = rem / 3, sh = rem - c * 3;
+        v = row < g.cout ? dense_w(g, A.w, row, r * 3 + sh, c * 8 + e) : dense_ws(g, A.w, A.a, row, r * 3 + sh, c * 8 + e);
+      } else if (kk == kbias && e < 2) {
         float b = 0.f;
         int k, which, node, u;
         if (row < g.cout) {
@@ -182,6 +182,7 @@ struct GradArgs {
   const float* gW_lin;      // linear: [heads][ci][co]
   const float* ga;          // [heads][2co]
   const float* gadj;        // [heads][nodes][nodes]
+  const float* gbias;       // fused layer kernels: [heads][co + 2]  sum d(Wh) per channel | sum ds1 | sum ds2
   PtrArr B, w, bias, a;     // parameters (w, bias, a: only read when the partials carry score rows)
   MutPtrArr g_w, g_bias, g_a, g_B;
   int accumulate;
@@ -230,10 +231,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
   const size_t cta_stride = (size_t)128 * A.nt;
   const int nq = 3 * g.nchunk + 1;
   auto column = [&](int tap, int ci_idx) {  // column of (tap, dense input channel); tap < 0: the ones (bias) column
-    if (A.d.wgrad_cols) {  // layer_fused.cu: [r][(s, cin chunk) | ones][8]; dbias is the ones column of r = 0
-      if (tap < 0) return (nq - 1) * 8;
-      return ((tap / 3) * nq + (tap % 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
-    }
+    (void)nq;  // (the fused layer kernels' partials, wgrad_cols = 1, never come here: stream_param_grads_reduced_kernel)
     return tap < 0 ? g.taps * g.cin : tap * g.cin + ci_idx;
   };
   // this thread's CTA (warp w takes the CTAs w, w+8, ...: at most one per lane with <= 256 partial tiles)
@@ -376,14 +374,13 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
   const int nwe = g.co * g.ci * g.taps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per_k = nwe + g.co + 2 * g.co;
-  const int nq = 3 * g.nchunk + 1;
   const float* Rm = A.wg_partial;
   const int rows = lf_partial_rows(g.nodes, g.co, g.heads);
-  auto column = [&](int tap, int ci_idx) {  // [r][(s, cin chunk) | ones][8]; tap < 0: the ones (bias) column of r = 0
-    if (tap < 0) return (nq - 1) * 8;
-    return ((tap / 3) * nq + (tap % 3) * g.nchunk + (ci_idx >> 3)) * 8 + (ci_idx & 7);
+  auto column = [&](int tap, int ci_idx) {  // [(r, cin chunk, s)][8]: the K-chunk order of the packed weights
+    return (((tap / 3) * g.nchunk + (ci_idx >> 3)) * 3 + tap % 3) * 8 + (ci_idx & 7);
   };
   auto R = [&](int row, int col) { return Rm[lf_partial_index(row, col, rows)]; };  // slot layout: common.cuh
+  const float* gb = A.gbias;  // [heads][co + 2]
   const long long nout = (long long)g.heads * per_k;
   for (long long i = (long long)(blockIdx.x - g.heads) * (ADJ_THREADS / 32) + warp; i < nout;
        i += (long long)(gridDim.x - g.heads) * (ADJ_THREADS / 32)) {
@@ -403,7 +400,14 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
         dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
       }
       if (dst == nullptr) continue;  // warp-uniform
-      if (lane < g.nodes) {  // lane = node
+      if (tap < 0) {
+        // bias gradient: the kernel's own sum of d(Wh) over pixels and nodes, plus the terms through the scores
+        // s = (Wh + b).a:  a1[u] * sum(ds1) + a2[u] * sum(ds2)
+        if (lane == 0) {
+          acc = gb[k * (g.co + 2) + u];
+          if (ext) acc += A.a.p[k][u] * gb[k * (g.co + 2) + g.co] + A.a.p[k][g.co + u] * gb[k * (g.co + 2) + g.co + 1];
+        }
+      } else if (lane < g.nodes) {  // lane = node
         const int col = column(tap, rec_of(g.spatial, g.nodes, g.ci, lane, c));
         acc = R(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, lane, u), col);
         if (ext) {
@@ -416,17 +420,14 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
       const int j0 = r - nwe - g.co, which = j0 / g.co, u = j0 - which * g.co;  // d(a)[which*co + u]
       dst = A.g_a.p[k] + j0;
       if (ext) {
-        const int nterm = g.taps * g.ci + 1;
+        const int nterm = g.taps * g.ci;
         for (int t = lane; t < g.nodes * nterm; t += 32) {
           const int node = t / nterm, tt = t - node * nterm;
           const int prow = g.cout + k * g.sph + which * g.nodes + node;
-          if (tt < nterm - 1) {
-            const int tap = tt % g.taps, c = tt / g.taps;
-            acc = fmaf(A.w.p[k][(u * g.ci + c) * g.taps + tap], R(prow, column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c))), acc);
-          } else if (A.bias.p[k]) {
-            acc = fmaf(A.bias.p[k][u], R(prow, column(-1, 0)), acc);
-          }
+          const int tap = tt % g.taps, c = tt / g.taps;
+          acc = fmaf(A.w.p[k][(u * g.ci + c) * g.taps + tap], R(prow, column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c))), acc);
         }
+        if (lane == 0 && A.bias.p[k]) acc = fmaf(A.bias.p[k][u], gb[k * (g.co + 2) + g.co + which], acc);  // s = (Wh + b).a
       }
       if (lane == 0) acc += A.ga[k * 2 * g.co + j0];  // whatever the kernel accumulated itself (no score rows: all of it)
     }
@@ -452,7 +453,7 @@ using namespace cgat;
 extern "C" int64_t cgat_stream_wpack_bytes(const cgat_stream_desc* d, int dgrad) {
   if (check_desc(d) || d->mapping != 1) return 0;
   const StreamGeom g = make_geom(*d);
-  if (!dgrad && d->wgrad_cols) return (int64_t)3 * (3 * g.nchunk + 1) * g.npad * 16;
+  if (!dgrad && d->wgrad_cols) return (int64_t)lf_weight_chunks(g.cin) * g.npad * 16;
   return dgrad ? (int64_t)g.d_npairs * 2 * g.d_npad * 16 : (int64_t)g.npairs * 2 * g.npad * 16;
 }
 
@@ -479,7 +480,7 @@ extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const
   A.adj = adj;
   const StreamGeom g = make_geom(*d);
   long long work = d->mapping == 1 ? (long long)g.npairs * 2 * g.npad * 8 : (long long)g.heads * g.ci * g.co;
-  if (d->mapping == 1 && d->wgrad_cols) work = (long long)3 * (3 * g.nchunk + 1) * g.npad * 8;
+  if (d->mapping == 1 && d->wgrad_cols) work = (long long)lf_weight_chunks(g.cin) * g.npad * 8;
   int blocks = (int)((work + ADJ_THREADS - 1) / ADJ_THREADS);
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;
@@ -488,7 +489,8 @@ extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const
 }
 
 extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt,
-                                       const float* gW_lin, const float* ga, const float* gadj, const float* const* B,
+                                       const float* gW_lin, const float* ga, const float* gadj, const float* gbias,
+                                       const float* const* B,
                                        const float* const* w, const float* const* bias, const float* const* a,
                                        float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
                                        int accumulate, void* stream) {
@@ -500,7 +502,8 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
   if (d->mapping == 0 && !gW_lin) return fail(CGAT_EINVAL, "linear mapping needs gW");
   GradArgs A{};
   A.d = *d;
-  A.wg_partial = wg_partial; A.ncta = ncta; A.nt = nt; A.gW_lin = gW_lin; A.ga = ga; A.gadj = gadj;
+  A.wg_partial = wg_partial; A.ncta = ncta; A.nt = nt; A.gW_lin = gW_lin; A.ga = ga; A.gadj = gadj; A.gbias = gbias;
+  if (d->mapping == 1 && d->wgrad_cols && !gbias) return fail(CGAT_EINVAL, "the fused layer kernels' partials need gbias");
   for (int k = 0; k < d->heads; ++k) {
     A.B.p[k] = B[k];
     A.w.p[k] = w ? w[k] : nullptr;

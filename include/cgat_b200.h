@@ -152,9 +152,10 @@ typedef struct cgat_stream_desc {
   int32_t mapping;       /* 0 linear, 1 conv 3x3 pad 1                      */
   int32_t transpose_adj; /* 1: the 1-D layer's A_hat^T (baseline_model.py:53) */
   int32_t wgrad_cols;    /* 0: conv_tc packing, wgrad partial columns [tap][cin] (cgat_conv2d_wgrad_partial);
-                            1: fused layer kernels (cgat_layer_*): K order (r; s, cin/8), partial columns
-                               [r][(s, cin/8) | ones][8], and -- while heads*(nodes*co + 2*nodes rounded up to 8) <= 128 --
-                               score rows W.a behind the heads*nodes*co feature rows (see cgat_stream_param_grads)  */
+                            1: fused layer kernels (cgat_layer_*): K-chunks j = (r*cin/8 + c)*3 + s (vertical tap r, channel
+                               chunk c, horizontal tap s), partial columns [j][8], the bias as a separate K-chunk, and -- while
+                               heads*(nodes*co + 2*nodes rounded up to 8) <= 128 -- score rows W.a behind the heads*nodes*co
+                               feature rows (see cgat_stream_param_grads)                                           */
 } cgat_stream_desc;
 
 /* bytes of the packed bf16 weight buffer of the block-diagonal dense conv (dgrad != 0: the dgrad packing) */
@@ -168,9 +169,10 @@ int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const 
  * accumulate != 0 adds into g_* (e.g. the parameters' .grad buffers) instead of overwriting.  w, bias, a: the same
  * per-head parameter pointers cgat_stream_prepare took; read only when wgrad_cols = 1 and the partials carry the score
  * rows d(W.a) of the fused layer kernels (then  dW += a (x) d(W.a)  and  d(a) = <W, d(W.a)>  are formed here); may be
- * NULL otherwise.                                                                                               */
+ * NULL otherwise.  gbias [heads][co + 2]: the fused layer kernels' sums of d(Wh) per output channel and of ds1, ds2
+ * (wgrad_cols = 1 only: the bias gradient does not come out of their wgrad MMA); NULL otherwise.                 */
 int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* gW_lin,
-                            const float* ga, const float* gadj, const float* const* B, const float* const* w,
+                            const float* ga, const float* gadj, const float* gbias, const float* const* B, const float* const* w,
                             const float* const* bias, const float* const* a, float* const* g_w,
                             float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate, void* stream);
 
@@ -178,14 +180,18 @@ int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, 
  * kernel per direction: the projected features never touch HBM (tcgen05 accumulators in TMEM are read by the
  * attention threads directly).  Replaces, for mapping_type="conv", the node conv at the call sites
  * convolutional_gat/model.py:21-42 plus baseline_model.py:127-160 (see cgat_attn_fwd).  bf16 activations.
- *   x      [n][h][w][nodes*ci]                      pixel records (the loaders' [N,H,W,T,V] layout)
+ *   x      [n][nodes*ci/8][h][wp][8], wp = 8*ceil(w/8) + 2: PADDED CHUNK-PLANAR (x_layout = CGAT_X_PLANAR): 16-byte
+ *          chunk c of the pixel record [T*V] of the loaders' [N,H,W,T,V] layout in plane c, image column i at padded
+ *          column i + 1, every other column ZERO.  cgat_loader_gather_planar writes it directly,
+ *          cgat_records_to_planar converts pixel records; the padding columns are never written by either (allocate
+ *          the buffer zeroed once).  One 5-D TMA box per 16x8-pixel tile then fills a whole pipeline stage.
  *   wpack, bias_dense, a, adj                       as produced by cgat_stream_prepare (fprop packing)
  *   out    [n][h][w][nodes*co] (MERGE_MEAN) or the concat layout of cgat_attn_fwd
  *   dwh    optional (may be NULL): d(Wh) [n][h][w][heads*nodes*co] for cgat_conv2d_dgrad_packed
- *   workspace  cgat_layer_workspace_bytes(d) bytes: per-CTA wgrad partial sums [ncta][128][nt], column order
- *              [r][(s, cin/8) | ones][8] (cgat_stream_desc.wgrad_cols = 1), plus one more [128][nt] slot that
- *              cgat_stream_param_grads uses as its reduction scratch (it WRITES slot `ncta` of this buffer)
- *   ga [heads][2co], gadj [heads][nodes][nodes]     fp32, ACCUMULATED INTO                                      */
+ *   workspace  cgat_layer_workspace_bytes(d) bytes: per-CTA wgrad partial sums (slots of [nt/8][rows][8] floats, rows =
+ *              feature + score rows rounded up to 32; column order as cgat_stream_desc.wgrad_cols = 1), plus one more
+ *              slot that cgat_stream_param_grads uses as its reduction scratch (it WRITES slot `ncta` of this buffer)
+ *   ga [heads][2co], gadj [heads][nodes][nodes], gbias [heads][co+2]     fp32, ACCUMULATED INTO                 */
 typedef struct cgat_layer_desc {
   int32_t n, h, w;
   int32_t nodes, ci, co, heads;
@@ -193,9 +199,8 @@ typedef struct cgat_layer_desc {
   int32_t merge;     /* CGAT_MERGE_*  */
   int32_t apply_elu;
   float alpha;
-  int32_t x_layout;  /* CGAT_X_RECORDS (0): x is [n][h][w][nodes*ci] pixel records, the loaders' [N,H,W,T,V];
-                        CGAT_X_PLANAR (1): x is chunk-planar [n][nodes*ci/8][h][w][8] (cgat_loader_gather_planar /
-                        cgat_records_to_planar write it): the kernel's TMA boxes then have 128-byte rows            */
+  int32_t x_layout;  /* must be CGAT_X_PLANAR (1): x is padded chunk-planar, see above.  CGAT_X_RECORDS (0), the pixel
+                        records themselves, is rejected: convert with cgat_records_to_planar                        */
 } cgat_layer_desc;
 #define CGAT_X_RECORDS 0
 #define CGAT_X_PLANAR 1
@@ -205,7 +210,8 @@ int cgat_layer_fwd(const cgat_layer_desc* d, const void* x, const void* wpack, c
                    const float* adj, const uint8_t* mask, void* out, void* stream);
 int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, const void* wpack,
                    const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, void* dwh,
-                   void* workspace, float* ga, float* gadj, int32_t* ncta_out, int32_t* nt_out, void* stream);
+                   void* workspace, float* ga, float* gadj, float* gbias, int32_t* ncta_out, int32_t* nt_out,
+                   void* stream);
 
 /* The same backward kernel in TRAIN mode: the reference step  loss = MSE(model(x), y) - lambda*mean(model(x));
  * loss.backward()  (convolutional_gat/train.py:130-132) for a model that is one mean-merged conv stream (the
@@ -215,8 +221,8 @@ int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, co
  * (the reference's running train loss, train.py:135-139) into mse_out[0].  heads <= 3, CGAT_MERGE_MEAN.        */
 int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
                      const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, float lambda,
-                     void* workspace, float* ga, float* gadj, float* loss_out, float* mse_out, int32_t* ncta_out,
-                     int32_t* nt_out, void* stream);
+                     void* workspace, float* ga, float* gadj, float* gbias, float* loss_out, float* mse_out,
+                     int32_t* ncta_out, int32_t* nt_out, void* stream);
 
 /* a8  the 1-D layer after its GEMM: GraphAttentionLayer.forward lines 36-56 of convolutional_gat/baseline_model.py
  * (scores :36-38 / :58-65, soft-max over neighbours :39, attention <- A_hat . attention :53, aggregation :54,
@@ -250,15 +256,15 @@ int cgat_adam_step(float* param, const float* grad, float* m, float* v, const in
 int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y, int32_t n,
                        int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w, int32_t steps,
                        float normalizing_max, float power, int32_t dtype, void* stream);
-/* The same gather with x written CHUNK-PLANAR (CGAT_X_PLANAR): x_planar [n][steps*vertices/8][crop_h][crop_w][8] bf16,
- * the 16-byte chunk q of every pixel record in plane q; y stays [n][crop_h][crop_w][steps][vertices] bf16.  This is the
- * input format of the fused layer kernels whose TMA boxes then have 128-byte rows (cgat_layer_desc.x_layout).       */
+/* The same gather with x written PADDED CHUNK-PLANAR (CGAT_X_PLANAR, see cgat_layer_fwd): x_planar
+ * [n][steps*vertices/8][crop_h][wp][8] bf16, wp = 8*ceil(crop_w/8) + 2, image column i at padded column i + 1 (the
+ * padding columns are NOT written: zero the buffer once); y stays [n][crop_h][crop_w][steps][vertices] bf16.        */
 int cgat_loader_gather_planar(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x_planar, void* y,
                               int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
                               int32_t steps, float normalizing_max, float power, void* stream);
-/* pixel records [n][pix_per_sample][rec] bf16 -> chunk-planar [n][rec/8][pix_per_sample][8] for an x tensor that did
- * not come from the loader kernel (the reference's own DataLoader, convolutional_gat/train.py:128).                  */
-int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int64_t pix_per_sample, int32_t rec, void* stream);
+/* pixel records [n][h][w][rec] bf16 -> padded chunk-planar [n][rec/8][h][wp][8] for an x tensor that did not come from
+ * the loader kernel (the reference's own DataLoader, convolutional_gat/train.py:128); padding columns not written.   */
+int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int32_t h, int32_t w, int32_t rec, void* stream);
 /* f4  validation metrics of convolutional_gat/train.py:53-75 + utils.py:135-167 in one pass over y, y_hat (n elements of
  * `dtype`): ACCUMULATES into out6 (double, caller zeroes)  [0] sum (y'-yh')^2  [1] sum ((y'-yh')*normalizing_max)^2
  * [2] TP [3] FP [4] FN [5] #(bin(y') == bin(yh')),  y' = y^(1/power), bin = the threshold binarisation of utils.py:138-141. */

@@ -79,26 +79,28 @@ def test_fused_loss_kernel_equals_unfused_step(N, H, W):
     close(res[True][1], res[False][1], rtol=2e-2, atol=3e-2 * res[False][1].abs().max().item(), msg="flat gradient")
 
 
-@pytest.mark.parametrize("attention_type,N,H,W", [("temporal", 14, 64, 64), ("temporal", 5, 50, 45), ("spatial", 6, 40, 64)])
-def test_train_kernel_planar_x_equals_record_x(attention_type, N, H, W):
-    """cgat_layer_train reading x chunk-planar (CGAT_X_PLANAR: TMA boxes with 128-byte rows, what TrainStep feeds it)
-    against the same kernel reading the pixel records: the tensor core sees identical operands, so everything but the
-    order of the cross-CTA atomics of the scalar sums is identical."""
+@pytest.mark.parametrize("attention_type,N,H,W", [("temporal", 5, 50, 45), ("spatial", 6, 40, 64)])
+def test_train_step_accepts_records_and_loader_planar_x(attention_type, N, H, W):
+    """cgat_layer_train reads x padded chunk-planar.  TrainStep.step(x, y) with record tensors (converted by
+    cgat_records_to_planar) and a slot filled through the loader kernel's planar output must give the same step."""
     from cgat.train_step import TrainStep
+    from convolutional_gat.data_loaders.kmni_data_loader import gather_windows
 
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 255, (N + 7, 6, H, W), generator=g, dtype=torch.uint8).to(DEV)
+    start = torch.arange(N, dtype=torch.int32, device=DEV)
+    x, y = gather_windows(frames, start, dtype=torch.bfloat16)
     res = {}
-    for planar in (True, False):
+    for via_loader in (False, True):
         ours, _ = _models(attention_type, "conv", seed=35)
-        torch.manual_seed(9)
-        x = torch.rand(N, H, W, 4, 6, device=DEV).bfloat16()
-        y = torch.rand(N, H, W, 4, 6, device=DEV).bfloat16()
         ts = TrainStep(ours, x, y, use_graph=False)
         assert ts.fused_stream is not None and ts.xp is not None
-        if not planar:
-            ts.xp = None
+        if via_loader:
+            ts.xp.zero_()
+            gather_windows(frames, start, out=(ts.xp, ts.y), planar=True)
         ts._fwd_bwd()
         torch.cuda.synchronize()
-        res[planar] = (ts.loss.clone(), ts.flat_grad.clone(), ts.mse.clone())
+        res[via_loader] = (ts.loss.clone(), ts.flat_grad.clone(), ts.mse.clone())
     close(res[True][0], res[False][0], rtol=1e-5, atol=1e-7, msg="loss")
     close(res[True][2], res[False][2], rtol=1e-5, atol=1e-7, msg="mse")
     close(res[True][1], res[False][1], rtol=1e-5, atol=1e-6 * res[False][1].abs().max().item(), msg="flat gradient")
