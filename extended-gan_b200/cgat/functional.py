@@ -481,13 +481,20 @@ def records_to_planar(x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor
 
 
 def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None, acc=None,
-                     x_planar=None):
+                     x_planar=None, scratch=None, precision="fp16x2"):
     """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
     ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
 
     ``loss_out[0]`` is accumulated into; the parameter gradients are ACCUMULATED into the parameters' existing
     ``.grad`` buffers (fp32, contiguous).  ``params`` = per head (conv.weight, conv.bias, a, B).  ``x_planar``: the
     chunk-planar copy of ``x`` (``records_to_planar`` / the loader kernel); the kernel then reads it instead of ``x``.
+
+    ``precision``: ``"fp16x2"`` = the paired-half kernel (its per-pixel attention math runs in packed fp16), ``"fp32"`` =
+    the fp32 instantiation of the same kernel.  ``scratch``: a zeroed fp32 buffer of >= 512 floats laid out
+    ``[loss, mse, guard, -, -, -, -, -, acc ... | 256: the same again]`` with ``loss_out``, ``mse_out`` and ``acc`` being its
+    views; the step is then GUARDED: the paired-half kernel raises ``scratch[2]`` when it left the range of fp16 (scores
+    beyond 8, non-finite sums), the fp32 kernel -- a no-op launch otherwise -- recomputes the step into the second half
+    and the parameter-gradient kernel reads whichever set is valid (``cgat_stream_param_grads_sel``).
     """
     require_cuda(x, y, loss_out, *params)
     N, H, W, T, V = x.shape
@@ -523,15 +530,43 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     ga, gadj, gb = acc[:na], acc[na:na + nadj], acc[na + nadj:na + nadj + nb]
     wsp = torch.empty(lib().cgat_layer_workspace_bytes(ctypes.byref(ld)), dtype=torch.uint8, device=dev)
     ncta, nt = ctypes.c_int32(0), ctypes.c_int32(0)
-    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
-              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ptr(loss_out), ptr(mse_out), ctypes.byref(ncta),
-              ctypes.byref(nt), st)
     tg = [p.grad for p in params]
-    _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
-              _lib.ptr_array(Bs), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
-              _lib.ptr_array([tg[4 * k] for k in range(heads)]),
-              _lib.ptr_array([tg[4 * k + 1] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 2] for k in range(heads)]),
-              _lib.ptr_array([tg[4 * k + 3] for k in range(heads)]), 1, st)
+    grads = (_lib.ptr_array([tg[4 * k] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 1] for k in range(heads)]),
+             _lib.ptr_array([tg[4 * k + 2] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 3] for k in range(heads)]))
+    pars = (_lib.ptr_array(Bs), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_))
+    if precision == "fp32":
+        _lib.call("cgat_layer_train_fp32", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
+                  ptr(mc), float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ptr(loss_out), ptr(mse_out), None,
+                  ctypes.byref(ncta), ctypes.byref(nt), st)
+        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
+                  *pars, *grads, 1, st)
+        return
+    if precision != "fp16x2":
+        raise RuntimeError(f"precision must be 'fp16x2' or 'fp32', got {precision!r}")
+    guarded = scratch is not None
+    if guarded:
+        ALT = 256
+        if (scratch.numel() < 2 * ALT or scratch.dtype != torch.float32 or loss_out.data_ptr() != scratch.data_ptr()
+                or mse_out is None or mse_out.data_ptr() != scratch.data_ptr() + 4 or acc.data_ptr() != scratch.data_ptr() + 32
+                or 8 + na + nadj + nb > ALT):
+            raise RuntimeError("gat_stream_train: scratch must be [loss, mse, guard, ..., acc at 8 | the same at 256]")
+        guard = scratch[2:3]
+        alt = scratch[ALT:]
+        ga2, gadj2, gb2 = alt[8:8 + na], alt[8 + na:8 + na + nadj], alt[8 + na + nadj:8 + na + nadj + nb]
+    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
+              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ptr(loss_out), ptr(mse_out), ptr(guard) if guarded else None,
+              ctypes.byref(ncta), ctypes.byref(nt), st)
+    if not guarded:
+        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
+                  *pars, *grads, 1, st)
+        return
+    # the fp32 re-run: a no-op launch unless the guard was raised; same partial-sum workspace (overwritten), second
+    # accumulator set; then the parameter gradients from whichever set is valid
+    _lib.call("cgat_layer_train_fp32", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
+              ptr(mc), float(lam), ptr(wsp), ptr(ga2), ptr(gadj2), ptr(gb2), ptr(alt[0:1]), ptr(alt[1:2]), ptr(guard),
+              ctypes.byref(ncta), ctypes.byref(nt), st)
+    _lib.call("cgat_stream_param_grads_sel", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(ga), ptr(gadj), ptr(gb),
+              *pars, *grads, 1, ptr(guard), ALT, ptr(scratch), st)
 
 
 def gat_stream(x, cfg: AttnConfig, mapping: str, mask, params):

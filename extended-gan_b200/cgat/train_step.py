@@ -33,7 +33,14 @@ class TrainStep:
 
     def __init__(self, model: torch.nn.Module, example_x: torch.Tensor, example_y: torch.Tensor, lr: float = 1e-3,
                  weight_decay: float = 0.01, lam: float = 0.0005, betas=(0.9, 0.999), eps: float = 1e-8,
-                 use_graph: bool = True, process_group: Optional[dist.ProcessGroup] = None, fuse_loss: bool = True):
+                 use_graph: bool = True, process_group: Optional[dist.ProcessGroup] = None, fuse_loss: bool = True,
+                 precision: str = "auto"):
+        """``precision`` of the fused train kernel: ``"auto"`` (default) = packed-fp16 attention math with the in-graph
+        range guard and fp32 re-run (functional.gat_stream_train), ``"fp16x2"`` = unguarded, ``"fp32"`` = the fp32
+        instantiation only."""
+        if precision not in ("auto", "fp16x2", "fp32"):
+            raise ValueError(f"precision must be 'auto', 'fp16x2' or 'fp32', got {precision!r}")
+        self.precision = precision
         self.model = model
         self.lr, self.weight_decay, self.lam, self.betas, self.eps = lr, weight_decay, lam, betas, eps
         self.pg = process_group
@@ -101,8 +108,14 @@ class TrainStep:
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         # loss scalars and the fused kernel's a / adjacency accumulators live in the gradient buffer's scratch tail
+        # (scratch layout: [loss, mse, range guard, -, -, -, -, -, accumulators ... | 256: the fp32 re-run's set])
         self.loss, self.mse = self.flat.scratch[0:1], self.flat.scratch[1:2]
-        self._acc = self.flat.scratch[8:]
+        self._acc = self.flat.scratch[8:256]
+
+    @property
+    def range_guard_fired(self) -> bool:
+        """Whether the LAST step left the packed-fp16 kernel's range and was recomputed in fp32 (host sync; diagnostics)."""
+        return bool(self.flat.scratch[2].item())
 
     @property
     def step_count(self) -> torch.Tensor:
@@ -148,7 +161,9 @@ class TrainStep:
         self.flat.zero_grad()  # gradients, loss scalars and accumulators: one memset
         if self.fused_stream is not None and self.fused_stream.train_step_supported(self.x):
             # forward + loss + backward in one kernel (cgat_layer_train)
-            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc, x_planar=self.xp)
+            self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc, x_planar=self.xp,
+                                               scratch=self.flat.scratch if self.precision == "auto" else None,
+                                               precision="fp32" if self.precision == "fp32" else "fp16x2")
             return
         prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
         try:

@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/cgat_b200.h"
 
@@ -38,6 +40,29 @@ template <> struct DT<__nv_bfloat16> {
 };
 
 #if defined(__CUDACC__)
+// ---- programmatic dependent launch: the kernels of one train step form a chain of small launches; a kernel launched
+// with launch_pdl may START (CTA scheduling, set-up, loads that do not depend on its predecessor) while the previous
+// kernel of the stream still runs, and calls griddep_wait() before it touches anything that kernel produces.  A
+// predecessor that calls griddep_launch() early lets it start even earlier.  Captured into CUDA graphs as programmatic
+// edges.  CGAT_NO_PDL=1 falls back to plain stream order (griddep_wait is then a no-op).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool no_pdl = std::getenv("CGAT_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // ---- shared-memory address / mbarrier / bulk async copy (TMA 1-D) ------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

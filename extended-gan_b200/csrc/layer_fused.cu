@@ -60,6 +60,11 @@ constexpr int LF_FP_COL0 = 256;     // TMEM: wgrad accumulators at columns [0,25
 constexpr int LF_PR = LF_TH + 2;    // stage rows (vertical halo)
 constexpr int LF_ROW = LF_TW * 16;  // 128 B: 8 pixels x 8 channels = one core matrix
 constexpr int LF_ONES = 4096;       // constant A operand of the bias MMA: 16 core matrices of ones, then 16 of zeros
+// Range guard of the paired-half train kernel: largest |s1|, |s2| (attention score halves) it accepts.  The logits
+// s1_i + s2_j then stay below 16, where fp16 resolves 2^-7: e^(logit - max) is good to < 1 %.  Beyond it -- or when any
+// sum the kernel produces is not finite (fp16 overflows at 65 504) -- the kernel raises LfArgs::guard and the step is
+// re-run by the fp32 instantiation (cgat_layer_train_fp32; tests/test_gpu_config2_pinned.py drives it with inputs x 100).
+constexpr float LF_SMAX = 8.f;
 constexpr int LF_HDR = 8704;        // barriers + parameters (fp32 and packed-half2 copies)
 constexpr int LF_SLOT = 64;         // floats per attention warp in the end-of-kernel reduction scratch (>= RG + 3)
 
@@ -81,6 +86,8 @@ struct LfArgs {
   const __nv_bfloat16* y;      // train mode (bwd kernel): target, same layout as out; d(out) is derived in-kernel
   float* loss_out;             // train mode: scalar loss, accumulated into
   float* mse_out;              // train mode, optional: mean squared error alone (the reference's running train loss)
+  float* guard;                // paired-half train kernel, optional: guard[0] := 1 when the step left the fp16 math's range
+  const float* run_if;         // optional: the whole launch is a no-op unless run_if[0] != 0 (the fp32 re-run of such a step)
   float out_scale;             // bwd: factor applied to the gradient sums when they leave the kernel (PAIR: 1/numel)
   float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
   int h, w, wp, cin, cout, ext, npad, heads, merge, apply_elu;  // wp: padded row of x, lf_padded_width(w);  // ext: score rows behind the cout feature rows (0: none)
@@ -169,6 +176,11 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
   constexpr int RG = RGA + CO + 2;             // ... + sum of d(Wh) per output channel (dbias), sum of ds1, sum of ds2
   static_assert(REC % 8 == 0, "record must be a multiple of 16 bytes");
   static_assert(RG + 3 <= LF_SLOT, "reduction slot too small");
+  if (A.run_if != nullptr) {  // the fp32 re-run of a guarded train step: a no-op unless the paired-half kernel asked for it
+    griddep_wait();           // (launched with programmatic serialisation: that kernel may still be running)
+    if (*A.run_if == 0.f) return;  // uniform over the grid; nothing has been set up yet
+  }
+  griddep_launch();  // whatever follows in the stream may be scheduled as soon as this grid's CTAs leave their SMs
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [4]  TMA -> MMA         (x planes landed)
   uint64_t* empty = full + LF_MAXSTG;                  // [4]  MMA -> TMA         (x stage reusable)
@@ -235,15 +247,19 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     // the first tile's planes before the (tile-independent) weights: the x planes are written whole by the TMA unit
     // (padding included), so they need no initialisation and their HBM latency overlaps the set-up below
     // (only the first tile: a TMA instruction takes ~100 cycles to issue, and everyone waits for this thread below)
-    mbar_arrive_expect_tx(wbar, A.wbytes);
-    bulk_g2s(s_w, A.wpack, A.wbytes, wbar);  // (the larger transfer first: the first fprop needs both)
+    // x does not depend on the kernel before this one in the stream (cgat_stream_prepare packs the weights): under
+    // programmatic dependent launch the first two tiles are on their way before that kernel has finished
     if ((int)blockIdx.x < A.tiles) issue_tile(blockIdx.x, 0);
     if (A.nstg > 1 && (int)(blockIdx.x + gridDim.x) < A.tiles) issue_tile(blockIdx.x + gridDim.x, 1);
+    griddep_wait();
+    mbar_arrive_expect_tx(wbar, A.wbytes);
+    bulk_g2s(s_w, A.wpack, A.wbytes, wbar);
   }
   if (warp != LF_TMA_WARP) {
     // (warp 0 is busy issuing TMA instructions, ~100 cycles each: the other 15 warps initialise shared memory)
     constexpr int NI = LF_THREADS - 32;
     const int ti = threadIdx.x - 32;
+    griddep_wait();  // a, adj come from the kernel before this one
     for (int i = ti; i < A.heads * 2 * CO; i += NI) { s_a[i] = A.a[i]; s_a2[i] = __float2half2_rn(A.a[i]); }
     for (int i = ti; i < A.heads * NODES * NODES; i += NI) {
       s_adj[i] = A.adj[i];
@@ -303,6 +319,8 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       const uint32_t idesc_f = make_idesc_bf16(128, A.npad, 0, 0);
       // wgrad N: the nj chunks rounded up to a multiple of 16 columns (M = 128 needs that); the odd 28th chunk is the x
       // data one stage row further down -- finite numbers into accumulator columns nobody reads
+      // (kind::f16 wants both operands in the same format: an fp16 A = d(Wh) against the bf16 x planes is an illegal
+      // instruction, so the train kernel converts its packed-half d(Wh) to bf16)
       const uint32_t idesc_w = make_idesc_bf16(128, (A.nj * 8 + 15) & ~15, 1, 1);
       const uint32_t w_addr = smem_u32(s_w);
       const uint32_t b_lbo = (uint32_t)A.npad * 16;
@@ -338,6 +356,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         if (++wbuf == A.ndw) { wbuf = 0; bphase ^= 1u; }
       };
       mbar_wait_warp(wbar, 0);
+      LDBGX(9);
       int it = 0, stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < A.tiles; tile += gridDim.x, ++it) {
@@ -351,6 +370,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         }
         mbar_wait_warp(&full[stage], phase);
         LDBG(4);
+        if (it == 0) LDBGX(10);
         mbar_wait_warp(&tempty[acc], (((uint32_t)it >> 1) & 1u) ^ 1u);
         LDBG(5);
         tc_fence_after();
@@ -432,53 +452,55 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         const __half2 alpha2 = __float2half2_rn(A.alpha);
         const __half2 gs2 = __float2half2_rn(inv_heads);
         __half2 g2[NODES * NODES], gb2[CO + 2];
+        __half2 smax2 = H2::zero();  // range guard: largest |s1|, |s2| this thread has seen (see LF_SMAX)
 #pragma unroll
         for (int i = 0; i < NODES * NODES; ++i) g2[i] = H2::zero();
 #pragma unroll
         for (int i = 0; i < CO + 2; ++i) gb2[i] = H2::zero();
         const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
         const uint32_t xplane = (uint32_t)A.mchunk * 2048;  // the score-row planes (after the feature planes)
+        // tile coordinates and the d(Wh) ring position are CARRIED from tile to tile (every runtime division or modulo
+        // is ~25 instructions; the loop top used to cost 1 300 cycles per pair)
+        const int d_tw = (int)gridDim.x % A.tiles_w, d_q = (int)gridDim.x / A.tiles_w, d_th = d_q % A.tiles_h, d_n = d_q / A.tiles_h;
+        int c_tw = (int)blockIdx.x % A.tiles_w, c_th = ((int)blockIdx.x / A.tiles_w) % A.tiles_h,
+            c_n = (int)blockIdx.x / (A.tiles_w * A.tiles_h);
+        auto advance = [&](int& tw, int& th, int& n) {  // + gridDim.x tiles
+          tw += d_tw;
+          const int cw = tw >= A.tiles_w ? 1 : 0;
+          tw -= cw ? A.tiles_w : 0;
+          th += d_th + cw;
+          const int ch = th >= A.tiles_h ? 1 : 0;
+          th -= ch ? A.tiles_h : 0;
+          n += d_n + ch;
+        };
+        int c_buf = 0, c_use = 0;  // tile t of this CTA uses d(Wh) buffer t % ndw for the (t / ndw + 1)-th time
         int itp = 0;
         for (int tileA = blockIdx.x; tileA < A.tiles; tileA += 2 * gridDim.x, ++itp) {
           const int it = 2 * itp;
           const int tileB = tileA + gridDim.x;
           const bool hasB = tileB < A.tiles;
-          const int bufA = (2 * itp) % A.ndw, bufB = (2 * itp + 1) % A.ndw;  // d(Wh) buffers of the two tiles
-          const int useA = (2 * itp) / A.ndw, useB = (2 * itp + 1) / A.ndw;   // how often each has been used before
+          const int bufA = c_buf, useA = c_use;
+          if (++c_buf == A.ndw) { c_buf = 0; ++c_use; }
+          const int bufB = c_buf, useB = c_use;
+          if (++c_buf == A.ndw) { c_buf = 0; ++c_use; }
           const uint32_t ph = (uint32_t)itp & 1u;
           long long pixA, pixB = 0;
           bool validA, validB = false;
           {
-            const int tw = tileA % A.tiles_w, th = (tileA / A.tiles_w) % A.tiles_h, n = tileA / (A.tiles_w * A.tiles_h);
-            const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
+            const int h = c_th * LF_TH + hrow, w = c_tw * LF_TW + wcol;
             validA = h < A.h && w < A.w;
-            pixA = ((long long)n * A.h + h) * A.w + w;
+            pixA = ((long long)c_n * A.h + h) * A.w + w;
           }
+          advance(c_tw, c_th, c_n);
           if (hasB) {
-            const int tw = tileB % A.tiles_w, th = (tileB / A.tiles_w) % A.tiles_h, n = tileB / (A.tiles_w * A.tiles_h);
-            const int h = th * LF_TH + hrow, w = tw * LF_TW + wcol;
+            const int h = c_th * LF_TH + hrow, w = c_tw * LF_TW + wcol;
             validB = h < A.h && w < A.w;
-            pixB = ((long long)n * A.h + h) * A.w + w;
+            pixB = ((long long)c_n * A.h + h) * A.w + w;
           }
+          advance(c_tw, c_th, c_n);
           if (g == 0) {  // the targets of this pair: pull their lines into L2 while the forward runs
             if (validA) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + pixA * REC));
             if (validB) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.y + pixB * REC));
-          } else if (g == nact - 1) {
-            // the INPUT records of the pair after next (same pixel of tiles +4 and +5): their TMA boxes are requested
-            // about one pair from now and then find the lines in L2 (the TMA round trip is on the pipeline's critical
-            // path: wgrad -> stage free -> TMA -> fprop)
-#pragma unroll
-            for (int ahead = 4; ahead < 6; ++ahead) {
-              const int tile = tileA + ahead * (int)gridDim.x;
-              if (tile < A.tiles) {
-                const int tw = tile % A.tiles_w, th = (tile / A.tiles_w) % A.tiles_h, n = tile / (A.tiles_w * A.tiles_h);
-                // one 128-byte line = the 8 pixels of a tile row in one chunk plane (+ 16 B of padding offset): the two
-                // lines it straddles are the neighbouring tiles' as well -- nchunk * 16 prefetches per tile
-                const int c = m >> 4, h = th * LF_TH + (m & 15), w = tw * LF_TW + 1;
-                if (c < A.nchunk && h < A.h)
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(A.x + ((((long long)n * A.nchunk + c) * A.h + h) * A.wp + w) * 8));
-              }
-            }
           }
           mbar_wait(&tfull[0], ph);
           if (hasB) mbar_wait(&tfull[1], ph);
@@ -518,6 +540,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
                 Wh2[v][u] = __floats2half2_rn(ra[rec_off<NODES, CO, SPATIAL>(v, u)], rb[rec_off<NODES, CO, SPATIAL>(v, u)]);
               st.s1[v] = __floats2half2_rn(sa[v], sb[v]);
               st.s2[v] = __floats2half2_rn(sa[NODES + v], sb[NODES + v]);
+              smax2 = __hmax2(smax2, __hmax2(__habs2(st.s1[v]), __habs2(st.s2[v])));
             }
           }
           if (dbg_thread) LDBG(10);
@@ -722,6 +745,10 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
           mbar_arrive(&dyfull[bufA]);
           if (hasB) mbar_arrive(&dyfull[bufB]);
           if (dbg_thread) LDBG(14);
+        }
+        if (A.guard != nullptr) {
+          const float2 f = __half22float2(smax2);
+          if (!(fmaxf(f.x, f.y) <= LF_SMAX)) *A.guard = 1.f;  // (NaN fails the comparison too)
         }
 #pragma unroll
         for (int i = 0; i < NODES * NODES; ++i) {
@@ -1056,6 +1083,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
       for (int wa = 0; wa < 4 * nact; ++wa)  // fixed order: the CTA's contribution is deterministic
         if (reinterpret_cast<const int*>(slots + wa * LF_SLOT)[RG + 2] == k) v += slots[wa * LF_SLOT + r];
       v *= A.out_scale;
+      if (A.guard != nullptr && !isfinite(v)) *A.guard = 1.f;
       if (r < NODES * NODES) atomicAdd(A.gadj + (size_t)k * NODES * NODES + r, v);
       else if (r < RGA) atomicAdd(A.ga + (size_t)k * 2 * CO + (r - NODES * NODES), v);
       else atomicAdd(A.gbias + (size_t)k * (CO + 2) + (r - RGA), v);
@@ -1063,6 +1091,7 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
     if (A.y != nullptr && threadIdx.x == 0) {
       float l = 0.f, q = 0.f;
       for (int wa = 0; wa < 4 * nact; ++wa) { l += slots[wa * LF_SLOT + RG]; q += slots[wa * LF_SLOT + RG + 1]; }
+      if (A.guard != nullptr && !(isfinite(l) && isfinite(q))) *A.guard = 1.f;
       atomicAdd(A.loss_out, l * A.inv_n);
       if (A.mse_out != nullptr) atomicAdd(A.mse_out, q * A.inv_n);
     }
@@ -1181,7 +1210,8 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
   auto go = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    kern<<<grid, LF_THREADS, g.smem, st>>>(map, A);
+    e = launch_pdl(kern, dim3(grid), dim3(LF_THREADS), g.smem, st, map, A);
+    if (e != cudaSuccess) return fail((int)e, "layer_kernel launch: %s", cudaGetErrorString(e));
     return 0;
   };
   int rc;
@@ -1199,7 +1229,8 @@ static int lf_launch(bool bwd, const cgat_layer_desc* d, const LfGeom& g, const 
 int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* wpack, const float* bias, const float* a,
                  const float* adj, const uint8_t* mask, void* out, const void* dout, void* dwh, float* partial,
                  float* ga, float* gadj, float* gbias, int* ncta_out, int* nt_out, cudaStream_t st, const void* y = nullptr,
-                 float* loss_out = nullptr, float lambda = 0.f, float* mse_out = nullptr) {
+                 float* loss_out = nullptr, float lambda = 0.f, float* mse_out = nullptr, float* guard = nullptr,
+                 const float* run_if = nullptr, bool force_fp32 = false) {
   if (!layer_supported(d)) return fail(CGAT_EUNSUPPORTED, "fused conv-GAT layer kernel does not support this shape");
   if (!aligned16(x) || !aligned16(wpack) || (out && !aligned16(out)) || (dout && !aligned16(dout)) ||
       (dwh && !aligned16(dwh)) || (partial && !aligned16(partial)))
@@ -1220,8 +1251,10 @@ int layer_launch(bool bwd, const cgat_layer_desc* d, const void* x, const void* 
   A.inv_n = 1.f / ((float)d->n * (float)d->h * (float)d->w * (float)(d->nodes * d->co));
   // the paired half2 kernel carries d(out) without its 1/numel factor; CGAT_NO_PAIR=1 keeps the fp32 one-tile kernel
   static const bool no_pair = std::getenv("CGAT_NO_PAIR") != nullptr;
-  A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && g.ndw >= 2 && g.ext > 0 && d->heads <= LF_GROUPS && !no_pair)
-                    ? A.inv_n : 1.f;
+  A.out_scale = (bwd && y != nullptr && g.nstg == LF_MAXSTG && g.ndw >= 2 && g.ext > 0 && d->heads <= LF_GROUPS && !no_pair &&
+                 !force_fp32) ? A.inv_n : 1.f;
+  A.guard = A.out_scale != 1.f ? guard : nullptr;
+  A.run_if = run_if;
   A.h = d->h; A.w = d->w; A.wp = lf_padded_width(d->w); A.cin = g.cin; A.cout = g.cout; A.ext = g.ext; A.npad = g.npad; A.heads = d->heads; A.merge = d->merge;
   A.apply_elu = d->apply_elu; A.alpha = d->alpha;
   A.nchunk = g.nchunk; A.np = g.np; A.nj = g.nj; A.rowp = g.rowp; A.mchunk = g.mchunk; A.nt = g.nt; A.rows_pad = g.rows_pad;
@@ -1270,7 +1303,7 @@ extern "C" int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const voi
 extern "C" int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
                                 const float* bias_dense, const float* a, const float* adj, const uint8_t* mask,
                                 float lambda, void* workspace, float* ga, float* gadj, float* gbias, float* loss_out,
-                                float* mse_out, int32_t* ncta_out, int32_t* nt_out, void* stream) {
+                                float* mse_out, float* guard, int32_t* ncta_out, int32_t* nt_out, void* stream) {
   if (!d || !x || !y || !wpack || !a || !adj || !workspace || !ga || !gadj || !gbias || !loss_out || !ncta_out || !nt_out)
     return fail(CGAT_EINVAL, "null argument");
   if (d->merge != CGAT_MERGE_MEAN || d->heads > LF_GROUPS)
@@ -1278,7 +1311,25 @@ extern "C" int cgat_layer_train(const cgat_layer_desc* d, const void* x, const v
   if (!aligned16(y)) return fail(CGAT_EALIGN, "y must be 16-byte aligned");
   int ncta = 0, nt = 0;
   const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, nullptr, nullptr, (float*)workspace,
-                              ga, gadj, gbias, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda, mse_out);
+                              ga, gadj, gbias, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda, mse_out, guard);
+  *ncta_out = ncta;
+  *nt_out = nt;
+  return rc;
+}
+
+extern "C" int cgat_layer_train_fp32(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
+                                     const float* bias_dense, const float* a, const float* adj, const uint8_t* mask,
+                                     float lambda, void* workspace, float* ga, float* gadj, float* gbias, float* loss_out,
+                                     float* mse_out, const float* run_if, int32_t* ncta_out, int32_t* nt_out, void* stream) {
+  if (!d || !x || !y || !wpack || !a || !adj || !workspace || !ga || !gadj || !gbias || !loss_out || !ncta_out || !nt_out)
+    return fail(CGAT_EINVAL, "null argument");
+  if (d->merge != CGAT_MERGE_MEAN || d->heads > LF_GROUPS)
+    return fail(CGAT_EUNSUPPORTED, "cgat_layer_train_fp32 serves mean-merged streams with at most %d heads", LF_GROUPS);
+  if (!aligned16(y)) return fail(CGAT_EALIGN, "y must be 16-byte aligned");
+  int ncta = 0, nt = 0;
+  const int rc = layer_launch(true, d, x, wpack, bias_dense, a, adj, mask, nullptr, nullptr, nullptr, (float*)workspace,
+                              ga, gadj, gbias, &ncta, &nt, (cudaStream_t)stream, y, loss_out, lambda, mse_out, nullptr, run_if,
+                              true);
   *ncta_out = ncta;
   *nt_out = nt;
   return rc;

@@ -95,6 +95,8 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepArgs A) {
+  griddep_launch();  // the layer kernel behind this one starts fetching its input tiles right away (common.cuh)
+  griddep_wait();
   const StreamGeom g = make_geom(A.d);
   if ((int)blockIdx.x < g.heads) {  // adjacency normalisation of head blockIdx.x (baseline_model.py:41-50)
     adj_norm_fwd_block(A.B.p[blockIdx.x], A.adj + (size_t)blockIdx.x * g.nodes * g.nodes, g.nodes, A.d.transpose_adj, 0);
@@ -186,6 +188,10 @@ struct GradArgs {
   PtrArr B, w, bias, a;     // parameters (w, bias, a: only read when the partials carry score rows)
   MutPtrArr g_w, g_bias, g_a, g_B;
   int accumulate;
+  // guarded train step (cgat_layer_train + cgat_layer_train_fp32): which accumulator set is valid is decided on the device
+  const float* select;      // NULL, or: select[0] != 0 -> ga, gadj, gbias are read alt_offset floats further on
+  long long alt_offset;
+  float* loss_mse;          // optional: [0..1] := [alt_offset .. alt_offset + 1] when the alternative set is selected
 };
 
 __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const GradArgs A) {
@@ -338,6 +344,8 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
 constexpr int RED_OUT = 64, RED_SPLIT = 4;  // outputs per block x CTA groups per output (256 threads)
 __global__ void __launch_bounds__(RED_OUT * RED_SPLIT)
 wgrad_partial_reduce_kernel(const float* __restrict__ part, int ncta, int n, size_t cta_stride, float* __restrict__ out) {
+  griddep_launch();
+  griddep_wait();
   __shared__ float s[RED_SPLIT][RED_OUT];
   const int o = threadIdx.x % RED_OUT, grp = threadIdx.x / RED_OUT;
   const int i = blockIdx.x * RED_OUT + o;
@@ -363,12 +371,19 @@ wgrad_partial_reduce_kernel(const float* __restrict__ part, int ncta, int n, siz
 
 // One WARP per output from the reduced matrix R [128][nt]; same algebra as stream_param_grads_kernel (see there).
 __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel(const GradArgs A) {
+  griddep_launch();
+  griddep_wait();
   const StreamGeom g = make_geom(A.d);
+  const long long sel = (A.select != nullptr && *A.select != 0.f) ? A.alt_offset : 0;  // the fp32 re-run's accumulators
   if ((int)blockIdx.x < g.heads) {
     const int k = blockIdx.x;
-    adj_norm_bwd_block(A.B.p[k], A.gadj + (size_t)k * g.nodes * g.nodes, A.g_B.p[k], g.nodes, A.d.transpose_adj, 0,
+    adj_norm_bwd_block(A.B.p[k], A.gadj + sel + (size_t)k * g.nodes * g.nodes, A.g_B.p[k], g.nodes, A.d.transpose_adj, 0,
                        A.accumulate);
     return;
+  }
+  if ((int)blockIdx.x == g.heads && threadIdx.x == 0 && sel != 0 && A.loss_mse != nullptr) {
+    A.loss_mse[0] = A.loss_mse[sel];
+    A.loss_mse[1] = A.loss_mse[sel + 1];
   }
   const bool ext = g.ext > 0;
   const int nwe = g.co * g.ci * g.taps;
@@ -380,7 +395,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
     return (((tap / 3) * g.nchunk + (ci_idx >> 3)) * 3 + tap % 3) * 8 + (ci_idx & 7);
   };
   auto R = [&](int row, int col) { return Rm[lf_partial_index(row, col, rows)]; };  // slot layout: common.cuh
-  const float* gb = A.gbias;  // [heads][co + 2]
+  const float* gb = A.gbias + sel;  // [heads][co + 2]
   const long long nout = (long long)g.heads * per_k;
   for (long long i = (long long)(blockIdx.x - g.heads) * (ADJ_THREADS / 32) + warp; i < nout;
        i += (long long)(gridDim.x - g.heads) * (ADJ_THREADS / 32)) {
@@ -429,7 +444,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel
         }
         if (lane == 0 && A.bias.p[k]) acc = fmaf(A.bias.p[k][u], gb[k * (g.co + 2) + g.co + which], acc);  // s = (Wh + b).a
       }
-      if (lane == 0) acc += A.ga[k * 2 * g.co + j0];  // whatever the kernel accumulated itself (no score rows: all of it)
+      if (lane == 0) acc += A.ga[sel + k * 2 * g.co + j0];  // whatever the kernel accumulated itself (no score rows: all of it)
     }
     acc = warp_sum(acc);
     if (lane == 0) *dst = A.accumulate ? *dst + acc : acc;
@@ -484,16 +499,17 @@ extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const
   int blocks = (int)((work + ADJ_THREADS - 1) / ADJ_THREADS);
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;
-  stream_prepare_kernel<<<d->heads + blocks, ADJ_THREADS, 0, (cudaStream_t)stream>>>(A);
+  cudaError_t e = launch_pdl(stream_prepare_kernel, dim3(d->heads + blocks), dim3(ADJ_THREADS), 0, (cudaStream_t)stream, A);
+  if (e != cudaSuccess) return fail((int)e, "stream_prepare_kernel: %s", cudaGetErrorString(e));
   return check_launch("stream_prepare_kernel");
 }
 
-extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt,
-                                       const float* gW_lin, const float* ga, const float* gadj, const float* gbias,
-                                       const float* const* B,
-                                       const float* const* w, const float* const* bias, const float* const* a,
-                                       float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
-                                       int accumulate, void* stream) {
+static int param_grads_impl(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt,
+                            const float* gW_lin, const float* ga, const float* gadj, const float* gbias,
+                            const float* const* B,
+                            const float* const* w, const float* const* bias, const float* const* a,
+                            float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
+                            int accumulate, const float* select, long long alt_offset, float* loss_mse, void* stream) {
   if (int rc = check_desc(d)) return rc;
   if (!ga || !gadj || !B || !g_w || !g_a || !g_B) return fail(CGAT_EINVAL, "null argument");
   const bool ext = d->mapping == 1 && make_geom(*d).ext > 0;
@@ -515,22 +531,26 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
     A.g_B.p[k] = g_B[k];
   }
   A.accumulate = accumulate;
+  A.select = select; A.alt_offset = alt_offset; A.loss_mse = loss_mse;
   const StreamGeom g = make_geom(*d);
+  if (select != nullptr && !(d->mapping == 1 && d->wgrad_cols))
+    return fail(CGAT_EINVAL, "the accumulator selector belongs to the fused layer kernels' train step (wgrad_cols = 1)");
   if (d->mapping == 1 && d->wgrad_cols) {
     // fused layer kernels: sum the CTA slots into the slot behind them (the workspace of cgat_layer_* has it), then
     // one warp per output from the reduced matrix
     const size_t cta_stride = (size_t)lf_partial_rows(g.nodes, g.co, g.heads) * nt;  // slot layout: common.cuh
     const int nred = (int)cta_stride;
     float* R = const_cast<float*>(wg_partial) + (size_t)ncta * cta_stride;
-    wgrad_partial_reduce_kernel<<<(nred + RED_OUT - 1) / RED_OUT, RED_OUT * RED_SPLIT, 0, (cudaStream_t)stream>>>(
-        wg_partial, ncta, nred, cta_stride, R);
-    if (int rc = check_launch("wgrad_partial_reduce_kernel")) return rc;
+    cudaError_t e = launch_pdl(wgrad_partial_reduce_kernel, dim3((nred + RED_OUT - 1) / RED_OUT), dim3(RED_OUT * RED_SPLIT), 0,
+                               (cudaStream_t)stream, wg_partial, ncta, nred, cta_stride, R);
+    if (e != cudaSuccess) return fail((int)e, "wgrad_partial_reduce_kernel: %s", cudaGetErrorString(e));
     A.wg_partial = R;
     A.ncta = 1;
     const long long nout = (long long)g.heads * (g.co * g.ci * g.taps + 3 * g.co);
     int blocks = (int)((nout + ADJ_THREADS / 32 - 1) / (ADJ_THREADS / 32));
     if (blocks > 148 * 8) blocks = 148 * 8;
-    stream_param_grads_reduced_kernel<<<d->heads + blocks, ADJ_THREADS, 0, (cudaStream_t)stream>>>(A);
+    e = launch_pdl(stream_param_grads_reduced_kernel, dim3(d->heads + blocks), dim3(ADJ_THREADS), 0, (cudaStream_t)stream, A);
+    if (e != cudaSuccess) return fail((int)e, "stream_param_grads_reduced_kernel: %s", cudaGetErrorString(e));
     return check_launch("stream_param_grads_reduced_kernel");
   }
   const long long work = d->mapping == 1 ? (long long)g.heads * (g.co * g.ci * g.taps + g.co + (ext ? 2 * g.co : 0))
@@ -541,4 +561,24 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
   if (blocks > 148 * 8) blocks = 148 * 8;  // 8 resident blocks of 256 threads per SM: one wave
   stream_param_grads_kernel<<<d->heads + blocks, ADJ_THREADS, 0, (cudaStream_t)stream>>>(A);
   return check_launch("stream_param_grads_kernel");
+}
+
+extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt,
+                                       const float* gW_lin, const float* ga, const float* gadj, const float* gbias,
+                                       const float* const* B, const float* const* w, const float* const* bias,
+                                       const float* const* a, float* const* g_w, float* const* g_bias, float* const* g_a,
+                                       float* const* g_B, int accumulate, void* stream) {
+  return param_grads_impl(d, wg_partial, ncta, nt, gW_lin, ga, gadj, gbias, B, w, bias, a, g_w, g_bias, g_a, g_B, accumulate,
+                          nullptr, 0, nullptr, stream);
+}
+
+extern "C" int cgat_stream_param_grads_sel(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
+                                           const float* gadj, const float* gbias, const float* const* B,
+                                           const float* const* w, const float* const* bias, const float* const* a,
+                                           float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
+                                           int accumulate, const float* select, int64_t alt_offset, float* loss_mse,
+                                           void* stream) {
+  if (!select) return fail(CGAT_EINVAL, "null selector");
+  return param_grads_impl(d, wg_partial, ncta, nt, nullptr, ga, gadj, gbias, B, w, bias, a, g_w, g_bias, g_a, g_B, accumulate,
+                          select, (long long)alt_offset, loss_mse, stream);
 }

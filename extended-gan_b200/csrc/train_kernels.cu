@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(EW_THREADS) adam_kernel(float* __restrict__ p,
                                                           const long long* __restrict__ step_dev, long long step_host,
                                                           long long n, float lr, float b1, float b2, float eps, float wd,
                                                           float gscale) {
+  griddep_wait();  // (launched with programmatic serialisation behind the parameter-gradient kernel, common.cuh)
   const float step = (float)(step_dev != nullptr ? *step_dev : step_host);
   const float bc1 = 1.f - powf(b1, step);
   const float bc2 = 1.f - powf(b2, step);
@@ -157,8 +158,10 @@ extern "C" int cgat_adam_step_at(float* param, const float* grad, float* m, floa
                                  float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                                  void* stream) {
   if (!param || !grad || !m || !v || n <= 0 || step < 1) return fail(CGAT_EINVAL, "null argument, n <= 0 or step < 1");
-  adam_kernel<<<ew_grid(n), EW_THREADS, 0, (cudaStream_t)stream>>>(param, grad, m, v, nullptr, (long long)step, n, lr, beta1,
-                                                                   beta2, eps, weight_decay, grad_scale);
+  cudaError_t e = launch_pdl(adam_kernel, dim3(ew_grid(n)), dim3(EW_THREADS), 0, (cudaStream_t)stream, param, grad, m, v,
+                             (const long long*)nullptr, (long long)step, (long long)n, lr, beta1, beta2, eps, weight_decay,
+                             grad_scale);
+  if (e != cudaSuccess) return fail((int)e, "adam_kernel: %s", cudaGetErrorString(e));
   return check_launch("adam_kernel");
 }
 

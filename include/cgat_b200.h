@@ -175,6 +175,15 @@ int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, 
                             const float* ga, const float* gadj, const float* gbias, const float* const* B, const float* const* w,
                             const float* const* bias, const float* const* a, float* const* g_w,
                             float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate, void* stream);
+/* The same with a device-side selector (the guarded train step, see cgat_layer_train): when select != NULL and
+ * select[0] != 0 the accumulators are read alt_offset floats further on (ga + alt_offset, gadj + alt_offset, gbias +
+ * alt_offset: the set cgat_layer_train_fp32 filled) and, if loss_mse != NULL, loss_mse[0..1] := loss_mse[alt_offset ..
+ * alt_offset + 1] (the loss / mse scalars of that set become the step's).                                            */
+int cgat_stream_param_grads_sel(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
+                                const float* gadj, const float* gbias, const float* const* B, const float* const* w,
+                                const float* const* bias, const float* const* a, float* const* g_w, float* const* g_bias,
+                                float* const* g_a, float* const* g_B, int accumulate, const float* select,
+                                int64_t alt_offset, float* loss_mse, void* stream);
 
 /* K6 / K7  one conv-mapped stream of the conv-GAT layer (shared 3x3 node conv, pad 1, + graph attention) as ONE
  * kernel per direction: the projected features never touch HBM (tcgen05 accumulators in TMEM are read by the
@@ -221,8 +230,20 @@ int cgat_layer_bwd(const cgat_layer_desc* d, const void* x, const void* dout, co
  * (the reference's running train loss, train.py:135-139) into mse_out[0].  heads <= 3, CGAT_MERGE_MEAN.        */
 int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
                      const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, float lambda,
-                     void* workspace, float* ga, float* gadj, float* gbias, float* loss_out, float* mse_out,
+                     void* workspace, float* ga, float* gadj, float* gbias, float* loss_out, float* mse_out, float* guard,
                      int32_t* ncta_out, int32_t* nt_out, void* stream);
+/* Arithmetic of cgat_layer_train: bf16 operands on the tensor cores (fp32 accumulation), the per-pixel attention math in
+ * PACKED fp16 (two pixels per instruction), every sum that leaves the kernel in fp32.  fp16 resolves the attention logits
+ * only while they are O(10) and overflows at 65 504, so the kernel checks itself: guard (optional, may be NULL) is ONE
+ * float the caller zeroes; the kernel stores 1 there when a score half |s1|, |s2| exceeded 8 or any of its sums is not
+ * finite.  Such a step must be recomputed by cgat_layer_train_fp32 -- the same kernel in its fp32 instantiation (one
+ * tile per pass, ~1.6x the time): same arguments; with run_if != NULL the launch is a no-op unless run_if[0] != 0, so
+ * the pair (train with guard = g; train_fp32 into a second set of accumulators with run_if = g) can sit in one captured
+ * graph, and cgat_stream_param_grads takes the selector (select / alt_offset) to read the set that is valid.           */
+int cgat_layer_train_fp32(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
+                          const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, float lambda,
+                          void* workspace, float* ga, float* gadj, float* gbias, float* loss_out, float* mse_out,
+                          const float* run_if, int32_t* ncta_out, int32_t* nt_out, void* stream);
 
 /* a8  the 1-D layer after its GEMM: GraphAttentionLayer.forward lines 36-56 of convolutional_gat/baseline_model.py
  * (scores :36-38 / :58-65, soft-max over neighbours :39, attention <- A_hat . attention :53, aggregation :54,

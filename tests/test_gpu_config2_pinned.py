@@ -105,6 +105,7 @@ def test_config2_train_kernel_vs_oracle_full_size(attention_type):
         assert torch.equal(p.detach().cpu(), p0[k]), k
     loss_o = ts.step(x.to(DEV), y.to(DEV))
     torch.cuda.synchronize()
+    assert not ts.range_guard_fired, "U[0,1) inputs are well inside the packed-fp16 kernel's range: no fp32 re-run"
     # loss: a mean of 6.3 M non-negative terms, no cancellation -> far inside the bf16 bar
     assert abs(float(loss_o[0]) - loss_r) <= 2e-3 * abs(loss_r), (float(loss_o[0]), loss_r)
     for k, p in ours.net.hidden_layer.named_parameters():
@@ -158,7 +159,9 @@ def test_config2_layer_fwd_bwd_vs_oracle_full_size(attention_type):
 
 def test_config2_train_kernel_large_magnitude_inputs():
     """Range check of the packed-fp16 attention math (fp16 overflows at 65504, bf16 does not): inputs x 100 drive the
-    projected features to O(100) and the attention logits past 50.  The step must stay finite and match the oracle."""
+    projected features to O(100) and the attention logits past 50.  The paired-half kernel must notice (its range guard:
+    score halves beyond 8 / non-finite sums, csrc/layer_fused.cu LF_SMAX), the fp32 instantiation re-runs the step inside
+    the same launch sequence, and the step must match the oracle at the usual bar."""
     from cgat.train_step import TrainStep
 
     ours, ref = _models("temporal", seed=3)
@@ -175,7 +178,23 @@ def test_config2_train_kernel_large_magnitude_inputs():
     assert ts.fused_stream is not None
     ts._fwd_bwd()
     torch.cuda.synchronize()
+    assert ts.range_guard_fired, "inputs x 100 must trip the range guard of the packed-fp16 kernel"
     assert torch.isfinite(ts.loss).all() and torch.isfinite(ts.flat_grad).all(), "overflow in the packed-fp16 math"
     assert abs(float(ts.loss[0]) - loss_r) <= 2e-2 * abs(loss_r), (float(ts.loss[0]), loss_r)
+    for k, p in ours.net.hidden_layer.named_parameters():
+        _assert_grad(k, p.grad, grads_r[k], abs_r[k])
+
+
+def test_config2_moderately_large_inputs_stay_in_fp16_range_or_fall_back():
+    """Inputs x 4 (scores of a few units): whichever kernel the guard picks, the step matches the oracle."""
+    from cgat.train_step import TrainStep
+
+    ours, ref = _models("temporal", seed=4)
+    x, y = _batch(scale=4.0, seed=17)
+    loss_r, grads_r, abs_r, _ = _oracle_step(ref, x, y)
+    ts = TrainStep(ours, x.to(DEV), y.to(DEV), lr=LR, use_graph=False)
+    ts._fwd_bwd()
+    torch.cuda.synchronize()
+    assert abs(float(ts.loss[0]) - loss_r) <= 2e-2 * abs(loss_r), (float(ts.loss[0]), loss_r, ts.range_guard_fired)
     for k, p in ours.net.hidden_layer.named_parameters():
         _assert_grad(k, p.grad, grads_r[k], abs_r[k])

@@ -52,7 +52,8 @@ for i in range(14):
     print(f"{i:4d} " + " ".join(f"{(int(v) - t0) if v > 0 else -1:8d}" for v in t[i][:16]))
 x = t[14]
 print("kernel stamps (cycles from entry): " + " ".join(f"{n}={int(x[i]) - int(x[0])}" for i, n in enumerate(
-    ["entry", "init", "regs", "tiles_done", "flushed", "wgrad_done", "partials", "joined", "exit"])), "first TMA at", t0 - int(x[0]))
+    ["entry", "init", "regs", "tiles_done", "flushed", "wgrad_done", "partials", "joined", "exit", "weights_landed", "x0_landed"])),
+      "first TMA at", t0 - int(x[0]))
 c = full_buf[256:].view(148, 2).cpu()
 if mode != "fwd":
     g0 = int(c[:, 0].min())
