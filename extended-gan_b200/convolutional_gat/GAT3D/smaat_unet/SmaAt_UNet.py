@@ -13,6 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from cgat.conv_layers import Conv2d
+from cgat.norm_act import ACT_RELU, BatchNormAct2d
 
 
 class DepthwiseSeparableConv(nn.Module):
@@ -30,10 +31,12 @@ class DoubleConvDS(nn.Module):
         super().__init__()
         mid = mid or cout
         self.double_conv = nn.Sequential(
+            # (BatchNorm2d + ReLU as one fused op at the BatchNorm's index; an Identity keeps the ReLU's index, so the
+            # state_dict keys double_conv.{0,1,3,4}.* are those of the public SmaAt-UNet)
             DepthwiseSeparableConv(cin, mid, 3, padding=1, kernels_per_layer=kernels_per_layer),
-            nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
+            BatchNormAct2d(mid, act=ACT_RELU), nn.Identity(),
             DepthwiseSeparableConv(mid, cout, 3, padding=1, kernels_per_layer=kernels_per_layer),
-            nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+            BatchNormAct2d(cout, act=ACT_RELU), nn.Identity(),
         )
 
     def forward(self, x):

@@ -268,6 +268,32 @@ int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_
 int cgat_adam_step(float* param, const float* grad, float* m, float* v, const int64_t* step_dev, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                    void* stream);
+/* a11 / f2  BatchNorm2d + activation + Dropout2d around the convs, NHWC (csrc/norm_act_kernels.cu): the rest of the
+ * reference's ConvBlock (dcgan/model.py:35-52: BatchNorm2d -> Dropout2d(0.01) -> activation) and of the SmaAt-UNet double
+ * convs (BatchNorm2d -> ReLU).  x, y, dy, dx [n][hw][c] of `dtype` (fp32 / bf16); statistics and parameters fp32 [c].
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 sigmoid.  mask: optional [n][c] floats (0 or 1/(1-p), Dropout2d: whole
+ * channels of a sample), applied AFTER the activation (identical to the block's order for ReLU / LeakyReLU).
+ *   cgat_bn_stats      train-mode batch statistics: mean, rstd = 1/sqrt(biased var + eps); if running_mean != NULL also
+ *                      running = (1-momentum)*running + momentum*batch (UNBIASED variance, as torch) and
+ *                      ++*num_batches_tracked.  workspace: cgat_bn_workspace_bytes(c) bytes (cleared by the call).
+ *   cgat_bn_act_fwd    y = act((x - mean) * rstd * gamma + beta) * mask;  mean == NULL: no normalisation (z = x).
+ *   cgat_bn_act_bwd    dz = dy * act'(z) * mask (z recomputed from x);  dbeta = sum dz, dgamma = sum dz * xhat (skipped when
+ *                      dgamma == NULL and the statistics are constants);  dx = gamma*rstd*(dz - dbeta/M - xhat*dgamma/M)
+ *                      when training != 0 (batch statistics), gamma*rstd*dz otherwise.  Two launches.
+ *   cgat_dropout2d_mask  mask[i] = Bernoulli(1-p) / (1-p), i < n, Philox4x32-10 keyed by (seed, *counter, i); ++*counter.  */
+int64_t cgat_bn_workspace_bytes(int32_t c);
+int cgat_bn_stats(const void* x, int32_t dtype, int64_t n, int64_t hw, int32_t c, void* workspace, float* mean, float* rstd,
+                  float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, float eps,
+                  void* stream);
+int cgat_bn_act_fwd(const void* x, void* y, int32_t dtype, int64_t n, int64_t hw, int32_t c, const float* mean,
+                    const float* rstd, const float* gamma, const float* beta, const float* mask, int32_t act, float slope,
+                    void* stream);
+int cgat_bn_act_bwd(const void* x, const void* dy, void* dx, int32_t dtype, int64_t n, int64_t hw, int32_t c,
+                    const float* mean, const float* rstd, const float* gamma, const float* beta, const float* mask,
+                    int32_t act, float slope, int32_t training, void* workspace, float* dgamma, float* dbeta,
+                    int32_t accumulate, void* stream);
+int cgat_dropout2d_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t* counter, void* stream);
+
 /* f3  the KNMI loader's windowing + normalisation + layout change on the device, replacing
  * convolutional_gat/data_loaders/kmni_data_loader.py:72-127 (__segmentify and the permute of __next__):
  *   x[s, h, w, t, v] = pow(frames[start[s] + t, v, h, w] / normalizing_max, power)            t < steps

@@ -125,6 +125,7 @@ def test_model_registry_and_train_signature():
 def test_dcgan_adversarial_step_vs_reference_golden():
     """BASELINE config 5: one adversarial step (dcgan/train.py:97-160) on our nets vs the live reference's step
     (tests/golden/dcgan_step.pt: same initial state_dicts, batch, optimisers; Dropout2d p = 0)."""
+    from cgat.norm_act import set_dropout
     from dcgan.model import FrameDiscriminator, Generator, TemporalDiscriminator
     from dcgan.train import adversarial_step, default_criterion, make_optimizers
 
@@ -133,9 +134,7 @@ def test_dcgan_adversarial_step_vs_reference_golden():
     nets = {"G": Generator(params), "FD": FrameDiscriminator(params), "TD": TemporalDiscriminator(params)}
     for name, net in nets.items():
         net.load_state_dict(sd_of(fx, f"{name}.sd0."))
-        for m in net.modules():
-            if isinstance(m, torch.nn.Dropout2d):
-                m.p = 0.0
+        set_dropout(net, 0.0)
         net.to(DEV).train()
     oG, oFD, oTD = make_optimizers(nets["G"], nets["FD"], nets["TD"])
     errFD, errTD, errG, _ = adversarial_step(netG=nets["G"], netFD=nets["FD"], netTD=nets["TD"], optimizerG=oG,
@@ -158,6 +157,7 @@ def test_dcgan_adversarial_step_vs_reference_golden():
 def test_dcgan_graphed_step_vs_reference_golden():
     """The CUDA-graph replay of the adversarial step (dcgan.train.GraphedAdversarialStep) is the same first step from the
     same state as the live reference's (tests/golden/dcgan_step.pt): construction's warm-up steps leave no trace."""
+    from cgat.norm_act import set_dropout
     from dcgan.model import FrameDiscriminator, Generator, TemporalDiscriminator
     from dcgan.train import GraphedAdversarialStep, default_criterion, make_optimizers
 
@@ -166,9 +166,7 @@ def test_dcgan_graphed_step_vs_reference_golden():
     nets = {"G": Generator(params), "FD": FrameDiscriminator(params), "TD": TemporalDiscriminator(params)}
     for name, net in nets.items():
         net.load_state_dict(sd_of(fx, f"{name}.sd0."))
-        for m in net.modules():
-            if isinstance(m, torch.nn.Dropout2d):
-                m.p = 0.0
+        set_dropout(net, 0.0)
         net.to(DEV).train()
     oG, oFD, oTD = make_optimizers(nets["G"], nets["FD"], nets["TD"], capturable=True)
     x, y = fx["x"].to(DEV), fx["y"].to(DEV)
