@@ -126,6 +126,21 @@ SIGNATURES = {
     "cgat_bn_act_fwd": [_P, _P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P, _I, _F, _P],
     "cgat_bn_act_bwd": [_P, _P, _P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _I, _P],
     "cgat_dropout2d_mask": [_P, _I64, _F, ctypes.c_uint64, _P, _P],
+    "cgat_maxpool2_fwd": [_P, _P, _P, _I, _I64, _I, _I, _I, _P],
+    "cgat_maxpool2_bwd": [_P, _P, _P, _I, _I64, _I, _I, _I, _P],
+    "cgat_upcat_fwd": [_P, _P, _P, _I, _I64, _I, _I, _I, _I, _I, _I, _P],
+    "cgat_upcat_bwd": [_P, _P, _P, _I, _I64, _I, _I, _I, _I, _I, _I, _P],
+    "cgat_pool_hw_workspace_bytes": [_I64, _I64, _I],
+    "cgat_pool_hw": [_P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P],
+    "cgat_dot_hw": [_P, _P, _I, _I64, _I64, _I, _P, _P, _P],
+    "cgat_cbam_mlp_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
+    "cgat_cbam_mlp_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cgat_gate_channels_fwd": [_P, _P, _P, _I, _I64, _I64, _I, _P],
+    "cgat_gate_channels_bwd": [_P, _P, _P, _P, _P, _P, _I, _I64, _I64, _I, _P],
+    "cgat_gate_pixels": [_P, _P, _P, _I, _I64, _I64, _I, _P],
+    "cgat_chan_pool_fwd": [_P, _P, _P, _I, _I64, _I, _P],
+    "cgat_chan_pool_bwd": [_P, _P, _P, _I, _I64, _I, _P],
+    "cgat_chan_dot": [_P, _P, _P, _I, _I64, _I, _P],
 }
 
 _lib = None
@@ -151,6 +166,7 @@ def lib() -> ctypes.CDLL:
         L.cgat_layer_workspace_bytes.restype = ctypes.c_int64
         L.cgat_p2p_mailbox_bytes.restype = ctypes.c_int64
         L.cgat_bn_workspace_bytes.restype = ctypes.c_int64
+        L.cgat_pool_hw_workspace_bytes.restype = ctypes.c_int64
         L.cgat_version.restype = ctypes.c_char_p
         L.cgat_last_error.restype = ctypes.c_char_p
         _lib = L

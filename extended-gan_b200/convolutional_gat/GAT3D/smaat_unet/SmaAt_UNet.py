@@ -3,17 +3,19 @@
 The upstream file is missing from the reference tree; this is the public SmaAt-UNet architecture
 (depthwise-separable double convs with kernels_per_layer=2, CBAM with reduction_ratio=16, bilinear up-sampling)
 whose parameter count, 4,032,548 at (n_channels=4, n_classes=4), is the number the reference recorded
-(compare_models/results/results.json:18).  Every convolution (depthwise 3x3, pointwise 1x1, CBAM 7x7, output 1x1)
-runs in the CUDA conv kernels; BatchNorm, pooling, the CBAM MLP and bilinear up-sampling are PyTorch ops on the
-same channels_last tensors (SURVEY.md 8f rank 2 lists their fusion as the next step).  PARITY UNPINNED beyond the
-parameter count; checked against oracle/spec.py SpecSmaAtUNet (same module tree, same state_dict keys).
+(compare_models/results/results.json:18).  Every op runs in our CUDA kernels: the convolutions (depthwise 3x3, pointwise
+1x1, CBAM 7x7, output 1x1) in the conv kernels, BatchNorm + ReLU / sigmoid fused (cgat.norm_act), max-pooling, bilinear
+up-sampling + pad + concat in one pass, and CBAM's channel / spatial gates with their pooling and MLP (cgat.unet_ops;
+SURVEY.md 8f rank 2).  PARITY UNPINNED beyond the parameter count; checked against oracle/spec.py SpecSmaAtUNet (same
+module tree, same state_dict keys).
 """
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from cgat import unet_ops
 from cgat.conv_layers import Conv2d
-from cgat.norm_act import ACT_RELU, BatchNormAct2d
+from cgat.norm_act import ACT_RELU, ACT_SIGMOID, BatchNormAct2d
 
 
 class DepthwiseSeparableConv(nn.Module):
@@ -46,7 +48,7 @@ class DoubleConvDS(nn.Module):
 class DownDS(nn.Module):
     def __init__(self, cin, cout, kernels_per_layer=1):
         super().__init__()
-        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConvDS(cin, cout, kernels_per_layer=kernels_per_layer))
+        self.maxpool_conv = nn.Sequential(unet_ops.MaxPool2d(), DoubleConvDS(cin, cout, kernels_per_layer=kernels_per_layer))
 
     def forward(self, x):
         return self.maxpool_conv(x)
@@ -57,14 +59,11 @@ class UpDS(nn.Module):
         super().__init__()
         if not bilinear:
             raise NotImplementedError("the reference configuration is bilinear")
-        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
         self.conv = DoubleConvDS(cin, cout, cin // 2, kernels_per_layer=kernels_per_layer)
 
     def forward(self, x1, x2):
-        x1 = self.up(x1)
-        dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
-        x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
-        return self.conv(torch.cat([x2, x1], dim=1))
+        # Upsample(scale_factor=2, bilinear, align_corners=True) -> F.pad to x2's size -> cat([x2, x1], dim=1): one kernel
+        return self.conv(unet_ops.upsample_pad_concat(x1, x2))
 
 
 class ChannelAttention(nn.Module):
@@ -74,19 +73,19 @@ class ChannelAttention(nn.Module):
                                  nn.Linear(c // reduction_ratio, c))
 
     def forward(self, x):
-        s = self.MLP(F.adaptive_avg_pool2d(x, 1)) + self.MLP(F.adaptive_max_pool2d(x, 1))
-        return x * torch.sigmoid(s)[:, :, None, None]
+        # x * sigmoid(MLP(avg_pool(x)) + MLP(max_pool(x))): pooling, both MLP passes and the gate in three launches
+        return unet_ops.channel_gate(x, self.MLP[1].weight, self.MLP[1].bias, self.MLP[3].weight, self.MLP[3].bias)
 
 
 class SpatialAttention(nn.Module):
     def __init__(self, kernel_size=7):
         super().__init__()
         self.conv = Conv2d(2, 1, kernel_size, padding=(kernel_size - 1) // 2, bias=False)
-        self.bn = nn.BatchNorm2d(1)
+        self.bn = BatchNormAct2d(1, act=ACT_SIGMOID)  # BatchNorm2d(1) + the sigmoid of the gate
 
     def forward(self, x):
-        o = torch.cat([x.mean(1, keepdim=True), x.max(1, keepdim=True)[0]], 1)
-        return x * torch.sigmoid(self.bn(self.conv(o)))
+        # x * sigmoid(bn(conv7x7(cat(mean_c(x), max_c(x)))))
+        return unet_ops.pixel_gate(x, self.bn(self.conv(unet_ops.channel_pool(x))))
 
 
 class CBAM(nn.Module):

@@ -294,6 +294,54 @@ int cgat_bn_act_bwd(const void* x, const void* dy, void* dx, int32_t dtype, int6
                     int32_t accumulate, void* stream);
 int cgat_dropout2d_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t* counter, void* stream);
 
+/* f2  the non-conv ops of the SmaAt-UNet applied per vertex by convolutional_gat/unet_model.py:20-29 (public
+ * architecture), NHWC, dtype fp32 / bf16 (csrc/unet_glue_kernels.cu).  Tensors [n][h][w][c] unless stated.
+ *   cgat_maxpool2_*      nn.MaxPool2d(2): y [n][h/2][w/2][c], idx one byte per output (position of the first maximum in the
+ *                        window, row-major); backward writes all of dx.
+ *   cgat_upcat_*         out [n][h][w][c2+c1] = cat(x2 [n][h][w][c2], zero_pad(bilinear_x2(x1 [n][h1][w1][c1],
+ *                        align_corners=True))) with pad offsets ((h-2h1)/2, (w-2w1)/2) as UpDS.forward; backward writes
+ *                        dx1 and dx2.
+ *   cgat_pool_hw         avg, mx [n][c] fp32 and the first arg-max pixel (int32) over the hw pixels of every (image,
+ *                        channel): adaptive_avg_pool2d / adaptive_max_pool2d to 1x1.  workspace:
+ *                        cgat_pool_hw_workspace_bytes.  cgat_dot_hw: out[n][c] = sum over pixels of x * dy.
+ *   cgat_cbam_mlp_*      CBAM channel gate: scale = sigmoid(MLP(avg) + MLP(mx)), MLP = Linear(c, hid) - ReLU - Linear(hid,
+ *                        c) with nn.Linear weight layout; pre [n][2][hid] keeps the hidden pre-activations.  The backward
+ *                        takes d(scale) and writes d(pre-sigmoid) ds [n][c], dpre, d(avg), d(mx) and the four parameter
+ *                        gradients (overwritten).
+ *   cgat_gate_channels_* y = x * scale[n][c];  backward: dx = dy * scale + davg/hw + (pixel == argmax ? dmax : 0), i.e. the
+ *                        gate's and both pooling branches' input gradients in one pass (d(scale) itself = cgat_dot_hw).
+ *   cgat_chan_pool_*     pooled [npix][2] = (mean, max over the c channels of a pixel), argmax [npix]; backward:
+ *                        dx = d(mean)/c + (channel == argmax ? d(max) : 0).
+ *   cgat_gate_pixels     y = x * s[pixel] (s of the tensor's dtype; also the backward dx = dy * s); cgat_chan_dot:
+ *                        out[pixel] = sum over channels of x * dy (= d(s)).                                             */
+int cgat_maxpool2_fwd(const void* x, void* y, uint8_t* idx, int32_t dtype, int64_t n, int32_t h, int32_t w, int32_t c,
+                      void* stream);
+int cgat_maxpool2_bwd(const void* dy, const uint8_t* idx, void* dx, int32_t dtype, int64_t n, int32_t h, int32_t w, int32_t c,
+                      void* stream);
+int cgat_upcat_fwd(const void* x1, const void* x2, void* out, int32_t dtype, int64_t n, int32_t h1, int32_t w1, int32_t c1,
+                   int32_t h, int32_t w, int32_t c2, void* stream);
+int cgat_upcat_bwd(const void* dout, void* dx1, void* dx2, int32_t dtype, int64_t n, int32_t h1, int32_t w1, int32_t c1,
+                   int32_t h, int32_t w, int32_t c2, void* stream);
+int64_t cgat_pool_hw_workspace_bytes(int64_t n, int64_t hw, int32_t c);
+int cgat_pool_hw(const void* x, int32_t dtype, int64_t n, int64_t hw, int32_t c, void* workspace, float* avg, float* mx,
+                 int32_t* argmax, void* stream);
+int cgat_dot_hw(const void* x, const void* dy, int32_t dtype, int64_t n, int64_t hw, int32_t c, void* workspace, float* out,
+                void* stream);
+int cgat_cbam_mlp_fwd(const float* avg, const float* mx, const float* w1, const float* b1, const float* w2, const float* b2,
+                      int32_t n, int32_t c, int32_t hid, float* pre, float* scale, void* stream);
+int cgat_cbam_mlp_bwd(const float* dscale, const float* scale, const float* pre, const float* avg, const float* mx,
+                      const float* w1, const float* w2, int32_t n, int32_t c, int32_t hid, float* ds, float* dpre, float* davg,
+                      float* dmax, float* dw1, float* db1, float* dw2, float* db2, void* stream);
+int cgat_gate_channels_fwd(const void* x, const float* scale, void* y, int32_t dtype, int64_t n, int64_t hw, int32_t c,
+                           void* stream);
+int cgat_gate_channels_bwd(const void* dy, const float* scale, const float* davg, const float* dmax, const int32_t* argmax,
+                           void* dx, int32_t dtype, int64_t n, int64_t hw, int32_t c, void* stream);
+int cgat_gate_pixels(const void* x, const void* s, void* y, int32_t dtype, int64_t n, int64_t hw, int32_t c, void* stream);
+int cgat_chan_pool_fwd(const void* x, void* pooled, int32_t* argmax, int32_t dtype, int64_t npix, int32_t c, void* stream);
+int cgat_chan_pool_bwd(const void* dpooled, const int32_t* argmax, void* dx, int32_t dtype, int64_t npix, int32_t c,
+                       void* stream);
+int cgat_chan_dot(const void* x, const void* dy, void* out, int32_t dtype, int64_t npix, int32_t c, void* stream);
+
 /* f3  the KNMI loader's windowing + normalisation + layout change on the device, replacing
  * convolutional_gat/data_loaders/kmni_data_loader.py:72-127 (__segmentify and the permute of __next__):
  *   x[s, h, w, t, v] = pow(frames[start[s] + t, v, h, w] / normalizing_max, power)            t < steps
