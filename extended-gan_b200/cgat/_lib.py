@@ -107,8 +107,8 @@ SIGNATURES = {
                          ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P],
     "cgat_layer_train_fp32": [ctypes.POINTER(LayerDesc), _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P,
                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P],
-    "cgat_stream_param_grads_sel": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P,
-                                    _I64, _P, _P],
+    "cgat_stream_finish": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I64,
+                           _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P],
     "cgat_gat1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_gat1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _P, _I64, _F, _F, _I, _P],

@@ -423,11 +423,13 @@ class _GATStreamFn(torch.autograd.Function):
         g_a = [tg[per * k + 2] for k in range(heads)]
         g_B = [tg[per * k + 3] for k in range(heads)]
         Bs = [params[per * k + 3] for k in range(heads)]
-        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
+        counter = torch.zeros(3, device=dev, dtype=torch.int32)
+        _lib.call("cgat_stream_finish", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(ga), ptr(gadj), ptr(gb),
                   _lib.ptr_array(Bs), _lib.ptr_array([params[per * k] for k in range(heads)]),
                   _lib.ptr_array([params[per * k + 1] for k in range(heads)]),
                   _lib.ptr_array([params[per * k + 2] for k in range(heads)]), _lib.ptr_array(g_w), _lib.ptr_array(g_b),
-                  _lib.ptr_array(g_a), _lib.ptr_array(g_B), int(direct), st)
+                  _lib.ptr_array(g_a), _lib.ptr_array(g_B), int(direct), None, 0, None, ptr(counter), None, None, None, None,
+                  0, None, None, st)
         grads = [None] * len(params) if direct else [g.to(p.dtype) for g, p in zip(tg, params)]
         return (dx, None, None, None, *grads)
 
@@ -481,7 +483,7 @@ def records_to_planar(x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor
 
 
 def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None, acc=None,
-                     x_planar=None, scratch=None, precision="fp16x2"):
+                     x_planar=None, scratch=None, precision="fp16x2", adam=None):
     """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
     ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
 
@@ -494,7 +496,11 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     ``[loss, mse, guard, -, -, -, -, -, acc ... | 256: the same again]`` with ``loss_out``, ``mse_out`` and ``acc`` being its
     views; the step is then GUARDED: the paired-half kernel raises ``scratch[2]`` when it left the range of fp16 (scores
     beyond 8, non-finite sums), the fp32 kernel -- a no-op launch otherwise -- recomputes the step into the second half
-    and the parameter-gradient kernel reads whichever set is valid (``cgat_stream_param_grads_sel``).
+    and the gradient kernel reads whichever set is valid (``cgat_stream_finish``).
+
+    ``adam``: ``None`` (gradients only) or ``(flat_param, flat_grad, exp_avg, exp_avg_sq, step_dev, hyper)`` -- the
+    optimiser step is then applied by the same launch that finishes the gradients (single GPU; the parameters' ``.grad``
+    buffers must be views of ``flat_grad``; ``step_dev`` int64[1] and ``hyper`` float32[6] live on the device).
     """
     require_cuda(x, y, loss_out, *params)
     N, H, W, T, V = x.shape
@@ -534,39 +540,46 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     grads = (_lib.ptr_array([tg[4 * k] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 1] for k in range(heads)]),
              _lib.ptr_array([tg[4 * k + 2] for k in range(heads)]), _lib.ptr_array([tg[4 * k + 3] for k in range(heads)]))
     pars = (_lib.ptr_array(Bs), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_))
+    if precision not in ("fp16x2", "fp16x2-unguarded", "fp32"):
+        raise RuntimeError(f"precision must be 'fp16x2', 'fp16x2-unguarded' or 'fp32', got {precision!r}")
+    guarded = scratch is not None and precision == "fp16x2"
+    ALT = 256
+    if scratch is not None:
+        if (scratch.numel() < 2 * ALT or scratch.dtype != torch.float32 or loss_out.data_ptr() != scratch.data_ptr()
+                or mse_out is None or mse_out.data_ptr() != scratch.data_ptr() + 4 or acc.data_ptr() != scratch.data_ptr() + 32
+                or 8 + na + nadj + nb > ALT):
+            raise RuntimeError("gat_stream_train: scratch must be [loss, mse, guard, counter, ..., acc at 8 | the same at 256]")
+        counter = scratch[3:6]  # (zero bits, cleared with the rest of the scratch every step)
+    else:
+        counter = torch.zeros(3, device=dev, dtype=torch.float32)
+    adam_args = (None, None, None, None, 0, None, None)
+    if adam is not None:
+        fp, fg, m1, m2, step_dev, hyper = adam
+        require_cuda(fp, fg, m1, m2, step_dev, hyper)
+        lo, hi = fg.data_ptr(), fg.data_ptr() + fg.numel() * 4
+        if not all(lo <= g.data_ptr() < hi for g in tg) or step_dev.dtype != torch.int64 or hyper.numel() < 6:
+            raise RuntimeError("gat_stream_train: the fused Adam step needs the .grad buffers to be views of flat_grad")
+        adam_args = (ptr(fp), ptr(fg), ptr(m1), ptr(m2), fp.numel(), ptr(step_dev), ptr(hyper))
     if precision == "fp32":
         _lib.call("cgat_layer_train_fp32", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
                   ptr(mc), float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ptr(loss_out), ptr(mse_out), None,
                   ctypes.byref(ncta), ctypes.byref(nt), st)
-        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
-                  *pars, *grads, 1, st)
-        return
-    if precision != "fp16x2":
-        raise RuntimeError(f"precision must be 'fp16x2' or 'fp32', got {precision!r}")
-    guarded = scratch is not None
+    else:
+        guard = scratch[2:3] if guarded else None
+        _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
+                  ptr(mc), float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ptr(loss_out), ptr(mse_out), ptr(guard),
+                  ctypes.byref(ncta), ctypes.byref(nt), st)
     if guarded:
-        ALT = 256
-        if (scratch.numel() < 2 * ALT or scratch.dtype != torch.float32 or loss_out.data_ptr() != scratch.data_ptr()
-                or mse_out is None or mse_out.data_ptr() != scratch.data_ptr() + 4 or acc.data_ptr() != scratch.data_ptr() + 32
-                or 8 + na + nadj + nb > ALT):
-            raise RuntimeError("gat_stream_train: scratch must be [loss, mse, guard, ..., acc at 8 | the same at 256]")
-        guard = scratch[2:3]
+        # the fp32 re-run: a no-op launch unless the guard was raised; same partial-sum workspace (overwritten), second
+        # accumulator set; the gradient kernel then reads whichever set is valid
         alt = scratch[ALT:]
         ga2, gadj2, gb2 = alt[8:8 + na], alt[8 + na:8 + na + nadj], alt[8 + na + nadj:8 + na + nadj + nb]
-    _lib.call("cgat_layer_train", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj), ptr(mc),
-              float(lam), ptr(wsp), ptr(ga), ptr(gadj), ptr(gb), ptr(loss_out), ptr(mse_out), ptr(guard) if guarded else None,
-              ctypes.byref(ncta), ctypes.byref(nt), st)
-    if not guarded:
-        _lib.call("cgat_stream_param_grads", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, None, ptr(ga), ptr(gadj), ptr(gb),
-                  *pars, *grads, 1, st)
-        return
-    # the fp32 re-run: a no-op launch unless the guard was raised; same partial-sum workspace (overwritten), second
-    # accumulator set; then the parameter gradients from whichever set is valid
-    _lib.call("cgat_layer_train_fp32", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
-              ptr(mc), float(lam), ptr(wsp), ptr(ga2), ptr(gadj2), ptr(gb2), ptr(alt[0:1]), ptr(alt[1:2]), ptr(guard),
-              ctypes.byref(ncta), ctypes.byref(nt), st)
-    _lib.call("cgat_stream_param_grads_sel", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(ga), ptr(gadj), ptr(gb),
-              *pars, *grads, 1, ptr(guard), ALT, ptr(scratch), st)
+        _lib.call("cgat_layer_train_fp32", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
+                  ptr(mc), float(lam), ptr(wsp), ptr(ga2), ptr(gadj2), ptr(gb2), ptr(alt[0:1]), ptr(alt[1:2]), ptr(guard),
+                  ctypes.byref(ncta), ctypes.byref(nt), st)
+    _lib.call("cgat_stream_finish", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(ga), ptr(gadj), ptr(gb), *pars, *grads,
+              1, ptr(guard) if guarded else None, ALT if guarded else 0, ptr(scratch) if guarded else None, ptr(counter),
+              *adam_args, st)
 
 
 def gat_stream(x, cfg: AttnConfig, mapping: str, mask, params):

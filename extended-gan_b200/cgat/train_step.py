@@ -42,7 +42,9 @@ class TrainStep:
             raise ValueError(f"precision must be 'auto', 'fp16x2' or 'fp32', got {precision!r}")
         self.precision = precision
         self.model = model
-        self.lr, self.weight_decay, self.lam, self.betas, self.eps = lr, weight_decay, lam, betas, eps
+        self._hyper = None
+        self._lr = lr
+        self.weight_decay, self.lam, self.betas, self.eps = weight_decay, lam, betas, eps
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
         self.x = example_x.clone()
@@ -57,8 +59,30 @@ class TrainStep:
         # prefetch are converted by one small kernel outside the captured graph.
         self.xp = functional.records_to_planar(self.x) if self.fused_stream is not None else None
         self._flatten()
+        # Single GPU + fused train kernel: Adam is applied by the launch that finishes the gradients (cgat_stream_finish); its
+        # step counter and hyper-parameters live on the device so that the captured graph stays valid when a scheduler
+        # changes lr.  With a gradient exchange (world > 1) the optimiser stays behind it (P2P kernel / all-reduce + Adam).
+        self._adam_in_graph = self.fused_stream is not None and self.world == 1
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._hyper = torch.empty(6, dtype=torch.float32, device=self.device)
+        self._push_hyper()
         if use_graph:
             self._capture()
+
+    @property
+    def lr(self) -> float:
+        return self._lr
+
+    @lr.setter
+    def lr(self, value: float):
+        changed = value != self._lr
+        self._lr = value
+        if changed and self._hyper is not None:
+            self._push_hyper()
+
+    def _push_hyper(self):
+        self._hyper.copy_(torch.tensor([self._lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world],
+                                       dtype=torch.float32), non_blocking=False)
 
     @staticmethod
     def _single_stream(model, x):
@@ -133,6 +157,8 @@ class TrainStep:
     def _exchange_and_update(self):
         """Gradient mean over ranks + Adam(lr, weight_decay): one P2P kernel, or NCCL all-reduce + fused Adam."""
         self._step += 1
+        if self._adam_in_graph:
+            return  # applied by cgat_stream_finish inside the step's launch sequence
         p2p = getattr(self.flat, "p2p", None)
         if p2p is not None:
             import ctypes
@@ -157,13 +183,19 @@ class TrainStep:
                    self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 / self.world)
 
     # -- one step -------------------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd(self, with_adam: bool = False):
+        """Forward + loss + backward into the flat gradient buffer; ``with_adam``: the fused path also applies the optimiser
+        step in its last launch (``run`` asks for it where ``_adam_in_graph``; probes and warm-ups never do)."""
         self.flat.zero_grad()  # gradients, loss scalars and accumulators: one memset
         if self.fused_stream is not None and self.fused_stream.train_step_supported(self.x):
             # forward + loss + backward in one kernel (cgat_layer_train)
+            adam = None
+            if with_adam and self._adam_in_graph:
+                adam = (self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._step_dev, self._hyper)
             self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc, x_planar=self.xp,
-                                               scratch=self.flat.scratch if self.precision == "auto" else None,
-                                               precision="fp32" if self.precision == "fp32" else "fp16x2")
+                                               scratch=self.flat.scratch, adam=adam,
+                                               precision="fp32" if self.precision == "fp32" else
+                                               ("fp16x2" if self.precision == "auto" else "fp16x2-unguarded"))
             return
         prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
         try:
@@ -184,7 +216,7 @@ class TrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._fwd_bwd()
+            self._fwd_bwd(with_adam=True)
 
     def load_batch(self, x: torch.Tensor, y: torch.Tensor):
         """Copy one batch (host-pinned or device) into the static input buffers."""
@@ -206,7 +238,7 @@ class TrainStep:
         if self.graph is not None:
             self.graph.replay()
         else:
-            self._fwd_bwd()
+            self._fwd_bwd(with_adam=True)
         self._exchange_and_update()
         return self.loss
 

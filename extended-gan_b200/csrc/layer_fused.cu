@@ -92,7 +92,7 @@ struct LfArgs {
   float lambda, inv_n;         // train mode: loss = mean((out-y)^2) - lambda*mean(out); inv_n = 1/numel(out)
   int h, w, wp, cin, cout, ext, npad, heads, merge, apply_elu;  // wp: padded row of x, lf_padded_width(w);  // ext: score rows behind the cout feature rows (0: none)
   float alpha;
-  int nchunk, np, nj, mchunk, nt;  // np = 3*nchunk planes per stage row, nj = 3*np K-chunks (fprop) = N-chunks (wgrad); nt = nj*8
+  int nchunk, np, nj, mchunk, nt;  // np = 3*nchunk planes per stage row, nj = 3*np K-chunks (fprop) = N-chunks (wgrad); nt = 9*ci
   int rowp;                        // bytes of a stage row: np * 128
   int tiles_h, tiles_w, tiles, nstg, ndw;
   int rows_pad;                 // rows of a CTA's partial-sum slot: cout + ext rounded up to a lane quarter (32)
@@ -1052,20 +1052,45 @@ layer_kernel(const __grid_constant__ CUtensorMap tmap_x, const LfArgs A) {
         mbar_wait(done, 0);
         tc_fence_after();
         if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(5);
-        // slot layout [8-column block][row][8]: a thread's 8 columns are 32 contiguous bytes and a warp's rows follow each
-        // other -- 1 KB per warp and column block, fully coalesced (row-major slots made every lane of a store hit its
-        // own 32-byte sector, half used: the 123 KB of a CTA took 6 000 cycles)
+        // COMPACT slots [row][vertical tap r][horizontal tap s][ci]: of the 216 accumulator columns of a row only the
+        // 9 * ci that multiply the row's OWN node are gradients of the shared per-node conv (the dense wgrad also holds
+        // every cross-node product): a thread picks those with compile-time (column -> node, ci) tables and stores
+        // 3 * ci floats per vertical tap -- 21 KB per CTA instead of 83 KB (the 148 CTAs' slots leave and re-enter
+        // the L2 at its write bandwidth: 3 300 cycles of this kernel's tail, and as much again in the reduction)
         if (lg * 32 < A.rows_pad) {
-          float* pslot = A.partial + (size_t)blockIdx.x * A.rows_pad * A.nt + (size_t)m * 8;
-          for (int c0 = g * 8; c0 < A.nt; c0 += nact * 8) {
-            float v[8];
-            tmem_ld8_nowait(tmem_base + ((uint32_t)(lg * 32) << 16) + c0, v);
-            tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(pslot + (size_t)(c0 >> 3) * A.rows_pad * 8);
+          constexpr int CI = CO, NCH = NODES * CO / 8, NC = 9 * CI;
+          int node = -1;  // this row's node; -1: a padding row
+          if (m < A.cout) {
+            const int rr = m % REC;
+            node = SPATIAL ? rr % NODES : rr / CO;
+          } else if (m < A.cout + A.ext) {
+            const int j = (m - A.cout) % lf_score_rows_per_head(NODES);
+            if (j < 2 * NODES) node = j % NODES;
+          }
+          float* prow = A.partial + ((size_t)blockIdx.x * A.rows_pad + m) * NC;
+          for (int r = g; r < 3; r += nact) {
+            float sel[3 * CI];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-              dst[i] = make_float4(v[4 * i] * A.out_scale, v[4 * i + 1] * A.out_scale, v[4 * i + 2] * A.out_scale,
-                                   v[4 * i + 3] * A.out_scale);
+            for (int i = 0; i < 3 * CI; ++i) sel[i] = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+              for (int sh = 0; sh < 3; ++sh) {
+                float v[8];
+                tmem_ld8_nowait(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(((r * NCH + c) * 3 + sh) * 8), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  constexpr int dummy = 0; (void)dummy;
+                  const int ch = c * 8 + e;
+                  const int nd = SPATIAL ? ch % NODES : ch / CI, ci = SPATIAL ? ch / NODES : ch % CI;
+                  if (node == nd) sel[sh * CI + ci] = v[e];
+                }
+              }
+            }
+            float2* dst = reinterpret_cast<float2*>(prow + r * 3 * CI);
+#pragma unroll
+            for (int i = 0; i < 3 * CI / 2; ++i) dst[i] = make_float2(sel[2 * i] * A.out_scale, sel[2 * i + 1] * A.out_scale);
           }
         }
         if (threadIdx.x == LF_ATT_WARP0 * 32) LDBGX(6);
@@ -1130,7 +1155,7 @@ static LfGeom lf_geom(const cgat_layer_desc* d, bool bwd) {
   g.ext = lf_score_rows(d->nodes, d->co, d->heads);  // score rows W.a behind the feature rows (common.cuh)
   g.npad = (g.cout + g.ext + 15) & ~15;
   g.mchunk = g.cout / 8;
-  g.nt = g.nj * 8;                    // wgrad partial columns: [r][c][s][8]
+  g.nt = 9 * d->ci;                   // columns of a COMPACT partial-sum slot row: [r][s][ci] (see the kernel's tail)
   g.rows_pad = lf_partial_rows(d->nodes, d->co, d->heads);
   g.wbytes = (uint32_t)lf_weight_chunks(g.cin) * g.npad * 16;  // nj chunks + a zero one, the bias chunk + a zero one
   g.stage_bytes = (uint32_t)LF_PR * g.rowp + 128;  // + one zeroed core matrix: the odd last K-chunk's partner, see the kernel
@@ -1169,7 +1194,7 @@ int layer_supported(const cgat_layer_desc* d) {
   const bool shape_ok = (sp && d->nodes == 6 && d->ci == 4 && d->co == 4) || (!sp && d->nodes == 4 && d->ci == 6 && d->co == 6);
   if (!shape_ok) return 0;
   const LfGeom f = lf_geom(d, false), b = lf_geom(d, true);
-  if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.npad > 128 || ((f.nt + 15) & ~15) > 256) return 0;
+  if (f.cin % 8 || f.cout % 8 || f.cout > 128 || f.npad > 128 || ((f.nj * 8 + 15) & ~15) > 256) return 0;
   if (d->ci != d->co) return 0;  // (the kernel derives its plane count from nodes * co)
   if (f.smem > 227 * 1024 || b.smem > 227 * 1024) return 0;
   return 1;

@@ -339,115 +339,179 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
   }
 }
 
-// ---- fused layer kernels (wgrad_cols = 1): the partial sums are first added over the CTAs, coalesced and in a fixed
-// order, into the slot behind them; the parameter gradients are then finished from that one [128][nt] matrix ----------
-constexpr int RED_OUT = 64, RED_SPLIT = 4;  // outputs per block x CTA groups per output (256 threads)
-__global__ void __launch_bounds__(RED_OUT * RED_SPLIT)
-wgrad_partial_reduce_kernel(const float* __restrict__ part, int ncta, int n, size_t cta_stride, float* __restrict__ out) {
-  griddep_launch();
-  griddep_wait();
-  __shared__ float s[RED_SPLIT][RED_OUT];
-  const int o = threadIdx.x % RED_OUT, grp = threadIdx.x / RED_OUT;
-  const int i = blockIdx.x * RED_OUT + o;
-  float acc = 0.f;
-  if (i < n) {
-    const int per = (ncta + RED_SPLIT - 1) / RED_SPLIT;
-    const int c0 = grp * per, c1 = min(ncta, c0 + per);
-    const float* p = part + i;
-    int c = c0;
-    for (; c + 8 <= c1; c += 8) {  // 8 independent loads in flight
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __ldcg(p + (size_t)(c + j) * cta_stride);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc += v[j];
-    }
-    for (; c < c1; ++c) acc += __ldcg(p + (size_t)c * cta_stride);
-  }
-  s[grp][o] = acc;
+// ---- fused layer kernels (wgrad_cols = 1): ONE launch finishes the step's gradients ---------------------------------------
+// The layer kernel leaves compact per-CTA slots [row][9 * ci] (layer_fused.cu).  Phase A: block `row` adds that row over the
+// CTAs (coalesced, fixed order: deterministic) into R (rows x 9ci floats, ~20 KB, L2-resident).  A grid barrier (all
+// blocks are co-resident: <= 128 blocks of 256 threads), then phase B spread over the whole grid: the conv weight / bias
+// gradients over the block-diagonal (a thread per value), d(a) through the score rows (a warp per value), the
+// adjacency-normalisation backward (a block per head); a second barrier and -- on a single GPU, where no gradient
+// exchange sits in between -- torch.optim.Adam on the flat parameter buffer.  The reduce / parameter-gradient / Adam
+// launches of the earlier chain and their gaps become one launch.  (A first version let the LAST block to finish phase A
+// do all of phase B alone: 30 us of dependent L2 round trips in one block; the earlier three launches took 12.)
+//
+// Score rows: the kernel's d(Wh) rows do NOT contain the terms through the scores s = (Wh + b).a; instead the slots carry
+//   G_which[k][node][tap][c] = d(W.a_which)  in the rows behind the features:
+//   dW[k][u][c][tap] += a1[k][u] G1 + a2[k][u] G2
+//   d(a_which)[k][u]  = sum_{node,tap,c} w[k][u][c][tap] G_which + bias[k][u] sum(ds_which)     (+ ga from the kernel)
+constexpr int FIN_THREADS = 256, FIN_MAX_R = 128 * 64;
+struct AdamArgs {
+  float* p;                 // NULL: no optimiser step in this launch
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  long long* step_dev;      // optimiser steps taken so far (device counter: the launch is replayed from a CUDA graph)
+  const float* hyper;       // device: lr, beta1, beta2, eps, weight_decay, grad_scale (schedulers change lr between replays)
+};
+struct FinishArgs {
+  GradArgs G;
+  unsigned int* counter;    // zeroed by the caller (per step)
+  float* R;                 // [rows][nc] global scratch
+  int rows, nc;
+  AdamArgs adam;
+};
+
+__device__ __forceinline__ void fin_grid_barrier(unsigned int* counter) {
   __syncthreads();
-  if (grp == 0 && i < n) out[i] = (s[0][o] + s[1][o]) + (s[2][o] + s[3][o]);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < gridDim.x);
+  }
+  __syncthreads();
 }
 
-// One WARP per output from the reduced matrix R [128][nt]; same algebra as stream_param_grads_kernel (see there).
-__global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_reduced_kernel(const GradArgs A) {
+__global__ void __launch_bounds__(FIN_THREADS) stream_finish_kernel(const FinishArgs F) {
   griddep_launch();
   griddep_wait();
+  __shared__ float s_part[4][64];
+  const GradArgs& A = F.G;
+  {  // ---- phase A: this block's row, summed over the CTAs ----
+    const int row = blockIdx.x, col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    for (int c0 = 0; c0 < F.nc; c0 += 64) {
+      float acc = 0.f;
+      if (c0 + col < F.nc) {
+        const float* p = A.wg_partial + (size_t)row * F.nc + c0 + col;
+        const size_t cs = (size_t)F.rows * F.nc;
+        int c = grp;
+        for (; c + 28 < A.ncta; c += 32) {  // 8 independent loads in flight
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldcg(p + (size_t)(c + 4 * j) * cs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += v[j];
+        }
+        for (; c < A.ncta; c += 4) acc += __ldcg(p + (size_t)c * cs);
+      }
+      s_part[grp][col] = acc;
+      __syncthreads();
+      if (grp == 0 && c0 + col < F.nc)
+        F.R[(size_t)row * F.nc + c0 + col] = (s_part[0][col] + s_part[1][col]) + (s_part[2][col] + s_part[3][col]);
+      __syncthreads();
+    }
+  }
+  fin_grid_barrier(F.counter);
+  // ---- phase B: everything from the reduced matrix, spread over the grid ----
   const StreamGeom g = make_geom(A.d);
   const long long sel = (A.select != nullptr && *A.select != 0.f) ? A.alt_offset : 0;  // the fp32 re-run's accumulators
-  if ((int)blockIdx.x < g.heads) {
-    const int k = blockIdx.x;
-    adj_norm_bwd_block(A.B.p[k], A.gadj + sel + (size_t)k * g.nodes * g.nodes, A.g_B.p[k], g.nodes, A.d.transpose_adj, 0,
-                       A.accumulate);
-    return;
-  }
-  if ((int)blockIdx.x == g.heads && threadIdx.x == 0 && sel != 0 && A.loss_mse != nullptr) {
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && sel != 0 && A.loss_mse != nullptr) {
     A.loss_mse[0] = A.loss_mse[sel];
     A.loss_mse[1] = A.loss_mse[sel + 1];
   }
   const bool ext = g.ext > 0;
   const int nwe = g.co * g.ci * g.taps;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int per_k = nwe + g.co + 2 * g.co;
-  const float* Rm = A.wg_partial;
-  const int rows = lf_partial_rows(g.nodes, g.co, g.heads);
-  auto column = [&](int tap, int ci_idx) {  // [(r, cin chunk, s)][8]: the K-chunk order of the packed weights
-    return (((tap / 3) * g.nchunk + (ci_idx >> 3)) * 3 + tap % 3) * 8 + (ci_idx & 7);
-  };
-  auto R = [&](int row, int col) { return Rm[lf_partial_index(row, col, rows)]; };  // slot layout: common.cuh
   const float* gb = A.gbias + sel;  // [heads][co + 2]
-  const long long nout = (long long)g.heads * per_k;
-  for (long long i = (long long)(blockIdx.x - g.heads) * (ADJ_THREADS / 32) + warp; i < nout;
-       i += (long long)(gridDim.x - g.heads) * (ADJ_THREADS / 32)) {
-    const int k = (int)(i / per_k);
-    const int r = (int)(i - (long long)k * per_k);
-    float* dst;
-    float acc = 0.f;
-    if (r < nwe + g.co) {
-      int u, c = 0, tap = -1;
+  auto R = [&](int row, int tap, int c) { return __ldcg(F.R + (size_t)row * F.nc + tap * g.ci + c); };
+  if ((int)blockIdx.x < g.heads) {
+    const int k = blockIdx.x;
+    adj_norm_bwd_block(A.B.p[k], A.gadj + sel + (size_t)k * g.nodes * g.nodes, A.g_B.p[k], g.nodes, A.d.transpose_adj, 0,
+                       A.accumulate);
+  } else {
+    const int nb = gridDim.x - g.heads, b = blockIdx.x - g.heads;
+    // conv weights and biases: a thread per value
+    const int per_wb = nwe + g.co;
+    for (int i = b * FIN_THREADS + threadIdx.x; i < g.heads * per_wb; i += nb * FIN_THREADS) {
+      const int k = i / per_wb, r = i - k * per_wb;
+      float* dst;
+      float acc = 0.f;
       if (r < nwe) {
-        tap = r % g.taps;
-        c = (r / g.taps) % g.ci;
-        u = r / (g.taps * g.ci);
+        const int tap = r % g.taps, c = (r / g.taps) % g.ci, u = r / (g.taps * g.ci);
         dst = A.g_w.p[k] + r;
+        const float a1 = ext ? A.a.p[k][u] : 0.f, a2 = ext ? A.a.p[k][g.co + u] : 0.f;
+        float v[ADJ_MAX_NODES > 8 ? 8 : ADJ_MAX_NODES][3];
+        for (int node0 = 0; node0 < g.nodes; node0 += 8) {  // all loads of a batch of nodes before they are used
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j][0] = v[j][1] = v[j][2] = 0.f;
+            const int node = node0 + j;
+            if (node >= g.nodes) continue;
+            v[j][0] = R(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, node, u), tap, c);
+            if (ext) {
+              const int rs = g.cout + k * g.sph + node;
+              v[j][1] = R(rs, tap, c);
+              v[j][2] = R(rs + g.nodes, tap, c);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += fmaf(a2, v[j][2], fmaf(a1, v[j][1], v[j][0]));
+        }
       } else {
-        u = r - nwe;
-        dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
-      }
-      if (dst == nullptr) continue;  // warp-uniform
-      if (tap < 0) {
         // bias gradient: the kernel's own sum of d(Wh) over pixels and nodes, plus the terms through the scores
-        // s = (Wh + b).a:  a1[u] * sum(ds1) + a2[u] * sum(ds2)
-        if (lane == 0) {
-          acc = gb[k * (g.co + 2) + u];
-          if (ext) acc += A.a.p[k][u] * gb[k * (g.co + 2) + g.co] + A.a.p[k][g.co + u] * gb[k * (g.co + 2) + g.co + 1];
-        }
-      } else if (lane < g.nodes) {  // lane = node
-        const int col = column(tap, rec_of(g.spatial, g.nodes, g.ci, lane, c));
-        acc = R(k * g.nodes * g.co + rec_of(g.spatial, g.nodes, g.co, lane, u), col);
-        if (ext) {
-          const int rs = g.cout + k * g.sph + lane;
-          acc = fmaf(A.a.p[k][u], R(rs, col), acc);
-          acc = fmaf(A.a.p[k][g.co + u], R(rs + g.nodes, col), acc);
-        }
+        const int u = r - nwe;
+        dst = A.g_bias.p[k] ? A.g_bias.p[k] + u : nullptr;
+        if (dst == nullptr) continue;
+        acc = gb[k * (g.co + 2) + u];
+        if (ext) acc += A.a.p[k][u] * gb[k * (g.co + 2) + g.co] + A.a.p[k][g.co + u] * gb[k * (g.co + 2) + g.co + 1];
       }
-    } else {
-      const int j0 = r - nwe - g.co, which = j0 / g.co, u = j0 - which * g.co;  // d(a)[which*co + u]
-      dst = A.g_a.p[k] + j0;
-      if (ext) {
-        const int nterm = g.taps * g.ci;
-        for (int t = lane; t < g.nodes * nterm; t += 32) {
-          const int node = t / nterm, tt = t - node * nterm;
-          const int prow = g.cout + k * g.sph + which * g.nodes + node;
-          const int tap = tt % g.taps, c = tt / g.taps;
-          acc = fmaf(A.w.p[k][(u * g.ci + c) * g.taps + tap], R(prow, column(tap, rec_of(g.spatial, g.nodes, g.ci, node, c))), acc);
-        }
-        if (lane == 0 && A.bias.p[k]) acc = fmaf(A.bias.p[k][u], gb[k * (g.co + 2) + g.co + which], acc);  // s = (Wh + b).a
-      }
-      if (lane == 0) acc += A.ga[sel + k * 2 * g.co + j0];  // whatever the kernel accumulated itself (no score rows: all of it)
+      *dst = A.accumulate ? *dst + acc : acc;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) *dst = A.accumulate ? *dst + acc : acc;
+    // d(a): a warp per value (nodes * ci * taps terms)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = FIN_THREADS / 32;
+    const int nterm = g.nodes * g.ci * g.taps;
+    for (int i = (nb - 1 - b) * nw + warp; i < g.heads * 2 * g.co; i += nb * nw) {  // (from the far end: other blocks than above)
+      const int k = i / (2 * g.co), j0 = i - k * 2 * g.co, which = j0 / g.co, u = j0 - which * g.co;
+      float acc = 0.f;
+      if (ext) {
+        for (int t = lane; t < nterm; t += 32) {
+          const int node = t / (g.ci * g.taps), rem = t - node * g.ci * g.taps, c = rem / g.taps, tap = rem - c * g.taps;
+          acc = fmaf(A.w.p[k][(u * g.ci + c) * g.taps + tap], R(g.cout + k * g.sph + which * g.nodes + node, tap, c), acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (ext && A.bias.p[k]) acc = fmaf(A.bias.p[k][u], gb[k * (g.co + 2) + g.co + which], acc);  // s = (Wh + b).a
+        acc += A.ga[sel + k * 2 * g.co + j0];  // whatever the kernel accumulated itself (no score rows: all of it)
+        float* dst = A.g_a.p[k] + j0;
+        *dst = A.accumulate ? *dst + acc : acc;
+      }
+    }
+  }
+  if (F.adam.p == nullptr) return;
+  // ---- torch.optim.Adam (convolutional_gat/train.py:212) on the flat buffers, once every gradient is in place ----
+  fin_grid_barrier(F.counter + 1);
+  const AdamArgs& O = F.adam;
+  const long long step_i = *O.step_dev + 1;
+  const float lr = O.hyper[0], b1 = O.hyper[1], b2 = O.hyper[2], eps = O.hyper[3], wd = O.hyper[4], gscale = O.hyper[5];
+  const float step = (float)step_i;
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  for (long long i = (long long)blockIdx.x * FIN_THREADS + threadIdx.x; i < O.n; i += (long long)gridDim.x * FIN_THREADS) {
+    const float pi = O.p[i];
+    const float gi = fmaf(wd, pi, __ldcg(O.g + i) * gscale);
+    const float mi = fmaf(b1, O.m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, O.v[i], (1.f - b2) * gi * gi);
+    O.m[i] = mi;
+    O.v[i] = vi;
+    O.p[i] = pi - step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+  }
+  // the step counter: bumped by the last block to get here (everyone has read it above)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(F.counter + 2, 1u) == gridDim.x - 1) *O.step_dev = step_i;
   }
 }
 
@@ -509,7 +573,8 @@ static int param_grads_impl(const cgat_stream_desc* d, const float* wg_partial, 
                             const float* const* B,
                             const float* const* w, const float* const* bias, const float* const* a,
                             float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
-                            int accumulate, const float* select, long long alt_offset, float* loss_mse, void* stream) {
+                            int accumulate, const float* select, long long alt_offset, float* loss_mse,
+                            unsigned int* counter, const AdamArgs* adam, void* stream) {
   if (int rc = check_desc(d)) return rc;
   if (!ga || !gadj || !B || !g_w || !g_a || !g_B) return fail(CGAT_EINVAL, "null argument");
   const bool ext = d->mapping == 1 && make_geom(*d).ext > 0;
@@ -536,22 +601,21 @@ static int param_grads_impl(const cgat_stream_desc* d, const float* wg_partial, 
   if (select != nullptr && !(d->mapping == 1 && d->wgrad_cols))
     return fail(CGAT_EINVAL, "the accumulator selector belongs to the fused layer kernels' train step (wgrad_cols = 1)");
   if (d->mapping == 1 && d->wgrad_cols) {
-    // fused layer kernels: sum the CTA slots into the slot behind them (the workspace of cgat_layer_* has it), then
-    // one warp per output from the reduced matrix
-    const size_t cta_stride = (size_t)lf_partial_rows(g.nodes, g.co, g.heads) * nt;  // slot layout: common.cuh
-    const int nred = (int)cta_stride;
-    float* R = const_cast<float*>(wg_partial) + (size_t)ncta * cta_stride;
-    cudaError_t e = launch_pdl(wgrad_partial_reduce_kernel, dim3((nred + RED_OUT - 1) / RED_OUT), dim3(RED_OUT * RED_SPLIT), 0,
-                               (cudaStream_t)stream, wg_partial, ncta, nred, cta_stride, R);
-    if (e != cudaSuccess) return fail((int)e, "wgrad_partial_reduce_kernel: %s", cudaGetErrorString(e));
-    A.wg_partial = R;
-    A.ncta = 1;
-    const long long nout = (long long)g.heads * (g.co * g.ci * g.taps + 3 * g.co);
-    int blocks = (int)((nout + ADJ_THREADS / 32 - 1) / (ADJ_THREADS / 32));
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    e = launch_pdl(stream_param_grads_reduced_kernel, dim3(d->heads + blocks), dim3(ADJ_THREADS), 0, (cudaStream_t)stream, A);
-    if (e != cudaSuccess) return fail((int)e, "stream_param_grads_reduced_kernel: %s", cudaGetErrorString(e));
-    return check_launch("stream_param_grads_reduced_kernel");
+    // fused layer kernels: compact slots [ncta][rows][nt = 9 ci]; the reduced matrix goes to the slot behind them (the
+    // workspace of cgat_layer_* has it)
+    FinishArgs F{};
+    F.G = A;
+    F.rows = lf_partial_rows(g.nodes, g.co, g.heads);
+    F.nc = nt;
+    if (nt != g.taps * g.ci) return fail(CGAT_EINVAL, "partial columns %d, expected 9 * ci = %d", nt, g.taps * g.ci);
+    if (F.rows > 128) return fail(CGAT_EUNSUPPORTED, "%d partial rows: the finishing grid must be co-resident", F.rows);
+    if (!counter) return fail(CGAT_EINVAL, "the fused layer kernels' gradient launch needs three zeroed counter words");
+    F.counter = counter;
+    F.R = const_cast<float*>(wg_partial) + (size_t)ncta * F.rows * F.nc;
+    if (adam) F.adam = *adam;
+    cudaError_t e = launch_pdl(stream_finish_kernel, dim3(F.rows), dim3(FIN_THREADS), 0, (cudaStream_t)stream, F);
+    if (e != cudaSuccess) return fail((int)e, "stream_finish_kernel: %s", cudaGetErrorString(e));
+    return check_launch("stream_finish_kernel");
   }
   const long long work = d->mapping == 1 ? (long long)g.heads * (g.co * g.ci * g.taps + g.co + (ext ? 2 * g.co : 0))
                                          : (long long)g.heads * g.ci * g.co;
@@ -568,17 +632,26 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
                                        const float* const* B, const float* const* w, const float* const* bias,
                                        const float* const* a, float* const* g_w, float* const* g_bias, float* const* g_a,
                                        float* const* g_B, int accumulate, void* stream) {
+  if (d && d->mapping == 1 && d->wgrad_cols)
+    return fail(CGAT_EINVAL, "the fused layer kernels' partials are finished by cgat_stream_finish");
   return param_grads_impl(d, wg_partial, ncta, nt, gW_lin, ga, gadj, gbias, B, w, bias, a, g_w, g_bias, g_a, g_B, accumulate,
-                          nullptr, 0, nullptr, stream);
+                          nullptr, 0, nullptr, nullptr, nullptr, stream);
 }
 
-extern "C" int cgat_stream_param_grads_sel(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
-                                           const float* gadj, const float* gbias, const float* const* B,
-                                           const float* const* w, const float* const* bias, const float* const* a,
-                                           float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
-                                           int accumulate, const float* select, int64_t alt_offset, float* loss_mse,
-                                           void* stream) {
-  if (!select) return fail(CGAT_EINVAL, "null selector");
+extern "C" int cgat_stream_finish(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
+                                  const float* gadj, const float* gbias, const float* const* B, const float* const* w,
+                                  const float* const* bias, const float* const* a, float* const* g_w, float* const* g_bias,
+                                  float* const* g_a, float* const* g_B, int accumulate, const float* select,
+                                  int64_t alt_offset, float* loss_mse, uint32_t* counter, float* adam_param,
+                                  const float* adam_grad, float* adam_m, float* adam_v, int64_t adam_n,
+                                  int64_t* adam_step_dev, const float* adam_hyper, void* stream) {
+  if (!d || d->mapping != 1 || !d->wgrad_cols) return fail(CGAT_EINVAL, "cgat_stream_finish serves the fused layer kernels (wgrad_cols = 1)");
+  AdamArgs O{};
+  if (adam_param != nullptr) {
+    if (!adam_grad || !adam_m || !adam_v || adam_n < 1 || !adam_step_dev || !adam_hyper) return fail(CGAT_EINVAL, "bad Adam arguments");
+    O.p = adam_param; O.g = adam_grad; O.m = adam_m; O.v = adam_v; O.n = adam_n; O.step_dev = (long long*)adam_step_dev;
+    O.hyper = adam_hyper;
+  }
   return param_grads_impl(d, wg_partial, ncta, nt, nullptr, ga, gadj, gbias, B, w, bias, a, g_w, g_bias, g_a, g_B, accumulate,
-                          select, (long long)alt_offset, loss_mse, stream);
+                          select, (long long)alt_offset, loss_mse, counter, adam_param ? &O : nullptr, stream);
 }

@@ -175,15 +175,25 @@ int cgat_stream_param_grads(const cgat_stream_desc* d, const float* wg_partial, 
                             const float* ga, const float* gadj, const float* gbias, const float* const* B, const float* const* w,
                             const float* const* bias, const float* const* a, float* const* g_w,
                             float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate, void* stream);
-/* The same with a device-side selector (the guarded train step, see cgat_layer_train): when select != NULL and
- * select[0] != 0 the accumulators are read alt_offset floats further on (ga + alt_offset, gadj + alt_offset, gbias +
- * alt_offset: the set cgat_layer_train_fp32 filled) and, if loss_mse != NULL, loss_mse[0..1] := loss_mse[alt_offset ..
- * alt_offset + 1] (the loss / mse scalars of that set become the step's).                                            */
-int cgat_stream_param_grads_sel(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
-                                const float* gadj, const float* gbias, const float* const* B, const float* const* w,
-                                const float* const* bias, const float* const* a, float* const* g_w, float* const* g_bias,
-                                float* const* g_a, float* const* g_B, int accumulate, const float* select,
-                                int64_t alt_offset, float* loss_mse, void* stream);
+/* The fused layer kernels' (cgat_layer_bwd / cgat_layer_train, wgrad_cols = 1) side of it, as ONE launch: reduces their
+ * compact per-CTA partial sums (ncta slots of [rows][nt = 9 ci] floats; slot `ncta` of the workspace is scratch), forms every
+ * parameter gradient (conv weight / bias over the block-diagonal, d(a) through the score rows, adjacency backward) and
+ * optionally applies torch.optim.Adam to the flat parameter buffer in the same launch (single GPU: nothing sits between
+ * the gradients and the optimiser).
+ *   counter            THREE uint32 the caller zeroes before every call (grid barriers between the launch's phases)
+ *   select, alt_offset, loss_mse   the guarded train step (see cgat_layer_train): select may be NULL; when select[0] != 0
+ *                      the accumulators are read alt_offset floats further on (the set cgat_layer_train_fp32 filled) and, if
+ *                      loss_mse != NULL, loss_mse[0..1] := loss_mse[alt_offset .. alt_offset + 1]
+ *   adam_param         NULL: gradients only.  Else flat fp32 param / grad / m / v of adam_n elements (every g_* pointer
+ *                      must point into adam_grad), *adam_step_dev = steps taken so far (incremented by the launch),
+ *                      adam_hyper = device floats {lr, beta1, beta2, eps, weight_decay, grad_scale}: both live on the device
+ *                      so that the launch can be replayed from a CUDA graph while schedulers change lr.              */
+int cgat_stream_finish(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
+                       const float* gadj, const float* gbias, const float* const* B, const float* const* w,
+                       const float* const* bias, const float* const* a, float* const* g_w, float* const* g_bias,
+                       float* const* g_a, float* const* g_B, int accumulate, const float* select, int64_t alt_offset,
+                       float* loss_mse, uint32_t* counter, float* adam_param, const float* adam_grad, float* adam_m,
+                       float* adam_v, int64_t adam_n, int64_t* adam_step_dev, const float* adam_hyper, void* stream);
 
 /* K6 / K7  one conv-mapped stream of the conv-GAT layer (shared 3x3 node conv, pad 1, + graph attention) as ONE
  * kernel per direction: the projected features never touch HBM (tcgen05 accumulators in TMEM are read by the
@@ -197,9 +207,9 @@ int cgat_stream_param_grads_sel(const cgat_stream_desc* d, const float* wg_parti
  *   wpack, bias_dense, a, adj                       as produced by cgat_stream_prepare (fprop packing)
  *   out    [n][h][w][nodes*co] (MERGE_MEAN) or the concat layout of cgat_attn_fwd
  *   dwh    optional (may be NULL): d(Wh) [n][h][w][heads*nodes*co] for cgat_conv2d_dgrad_packed
- *   workspace  cgat_layer_workspace_bytes(d) bytes: per-CTA wgrad partial sums (slots of [nt/8][rows][8] floats, rows =
- *              feature + score rows rounded up to 32; column order as cgat_stream_desc.wgrad_cols = 1), plus one more
- *              slot that cgat_stream_param_grads uses as its reduction scratch (it WRITES slot `ncta` of this buffer)
+ *   workspace  cgat_layer_workspace_bytes(d) bytes: per-CTA wgrad partial sums (compact slots of [rows][nt = 9 ci] floats:
+ *              of a dense row only the columns of its own node, order [tap][ci]; rows = feature + score rows rounded up to
+ *              32), plus one more slot that cgat_stream_finish uses as its reduction scratch
  *   ga [heads][2co], gadj [heads][nodes][nodes], gbias [heads][co+2]     fp32, ACCUMULATED INTO                 */
 typedef struct cgat_layer_desc {
   int32_t n, h, w;
@@ -239,7 +249,7 @@ int cgat_layer_train(const cgat_layer_desc* d, const void* x, const void* y, con
  * finite.  Such a step must be recomputed by cgat_layer_train_fp32 -- the same kernel in its fp32 instantiation (one
  * tile per pass, ~1.6x the time): same arguments; with run_if != NULL the launch is a no-op unless run_if[0] != 0, so
  * the pair (train with guard = g; train_fp32 into a second set of accumulators with run_if = g) can sit in one captured
- * graph, and cgat_stream_param_grads takes the selector (select / alt_offset) to read the set that is valid.           */
+ * graph, and cgat_stream_finish takes the selector (select / alt_offset) to read the set that is valid.           */
 int cgat_layer_train_fp32(const cgat_layer_desc* d, const void* x, const void* y, const void* wpack,
                           const float* bias_dense, const float* a, const float* adj, const uint8_t* mask, float lambda,
                           void* workspace, float* ga, float* gadj, float* gbias, float* loss_out, float* mse_out,
