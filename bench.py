@@ -471,19 +471,37 @@ def run_ours(args):
         kernels[name] = ent
     dom = max((n for n in prof if n in alg), key=lambda n: prof[n][0] * prof[n][1])
     achieved = alg[dom][1] / (prof[dom][1] * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_entry = None, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {}).get("bytes")
+        ncu_entry = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom, {})
+        traffic = ncu_entry.get("bytes")
     except (OSError, ValueError):
         pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["source"],
                 "algorithmic_bytes_per_launch": alg[dom][1], "kernel_ms": prof[dom][1]}
     if len(alg[dom]) > 2:  # the kernel also runs the conv GEMMs on tcgen05: report the tensor-pipe side as well
-        roofline["tensor_tflops"] = alg[dom][2] / (prof[dom][1] * 1e-3) / 1e12
+        kms = prof[dom][1]
+        # executed: the dense block-diagonal GEMMs the tensor cores run (3/4 of it multiplies structural zeros);
+        # algorithmic: the shared per-node conv the layer defines (fprop + wgrad), i.e. executed / nodes
+        nodes = T if args.type == "temporal" else V
+        roofline["tensor_tflops_executed"] = alg[dom][2] / (kms * 1e-3) / 1e12
+        roofline["tensor_tflops"] = roofline["tensor_tflops_executed"] / nodes
         roofline["tensor_frac"] = roofline["tensor_tflops"] / pk["bf16_tflops_sustained"]
-        roofline["note"] = ("fused conv+attention kernel: neither HBM- nor tensor-bound; limited by FP32 issue/latency of the "
-                            "per-pixel attention math (profiles/*_sass_hot.txt)")
+        # the bound that applies: warp-instruction issue.  ncu counts the kernel's executed warp instructions
+        # (smsp__inst_executed.sum, profiles/traffic.json); a B200 SM sub-partition issues at most one per cycle
+        # (tools/microbench/fma_rate.cu: FFMA 0.98 / cycle, packed HFMA2 0.50), 148 SMs x 4 sub-partitions.
+        inst = ncu_entry.get("warp_instructions")
+        if inst and clocks and clocks.get("sm_mhz"):
+            bound_ms = inst / (148 * 4) / (clocks["sm_mhz"] * 1e3)
+            roofline["issue_bound"] = {"warp_instructions": inst, "bound_ms": bound_ms, "frac": bound_ms / kms,
+                                       "source": ncu_entry.get("source"),
+                                       "note": "kernel time if every sub-partition issued one warp instruction per cycle at "
+                                               "the sampled SM clock; the packed-half instructions occupy the FP pipe for "
+                                               "two cycles each, so the reachable figure is lower"}
+        roofline["note"] = ("fused conv+attention kernel: neither HBM- nor tensor-bound by design (the projected features never "
+                            "leave the SM); bound by warp-instruction issue of the per-pixel attention math "
+                            "(roofline.issue_bound, profiles/*_sass_hot.txt)")
 
     cpu_rate, cpu_sec, cores = cpu_reference_step_rate(4, 3, 1, args.type, args.mapping) if world == 1 else (None, None, None)
 
@@ -492,6 +510,9 @@ def run_ours(args):
         "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "dtype_detail": "bf16 activations and tensor-core operands, fp32 accumulation and parameter gradients; the per-pixel "
+                        "attention math of cgat_layer_train in packed fp16 (two pixels per instruction) behind a range guard, "
+                        "with an in-graph fp32 re-run of the step when the guard fires",
         "config": dict(workload_config(args, B), gradient_exchange=("none (1 GPU)" if world == 1 else
                        "cgat_p2p_allreduce_adam: push + rank-ordered sum + Adam in one kernel over NVLink peer memory"
                        if p2p else "NCCL all_reduce + cgat_adam_step")),

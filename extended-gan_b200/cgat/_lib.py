@@ -97,6 +97,7 @@ SIGNATURES = {
                                   ctypes.POINTER(ctypes.c_int32), _P],
     "cgat_stream_wpack_bytes": [ctypes.POINTER(StreamDesc), _I],
     "cgat_stream_prepare": [ctypes.POINTER(StreamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cgat_stream_prepare_clear": [ctypes.POINTER(StreamDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P],
     "cgat_stream_param_grads": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "cgat_layer_supported": [ctypes.POINTER(LayerDesc)],
     "cgat_layer_workspace_bytes": [ctypes.POINTER(LayerDesc)],

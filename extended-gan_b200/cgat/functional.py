@@ -483,7 +483,7 @@ def records_to_planar(x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor
 
 
 def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None, acc=None,
-                     x_planar=None, scratch=None, precision="fp16x2", adam=None):
+                     x_planar=None, scratch=None, precision="fp16x2", adam=None, clear=None):
     """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
     ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
 
@@ -501,6 +501,8 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     ``adam``: ``None`` (gradients only) or ``(flat_param, flat_grad, exp_avg, exp_avg_sq, step_dev, hyper)`` -- the
     optimiser step is then applied by the same launch that finishes the gradients (single GPU; the parameters' ``.grad``
     buffers must be views of ``flat_grad``; ``step_dev`` int64[1] and ``hyper`` float32[6] live on the device).
+    ``clear``: a tensor (16-byte aligned, a multiple of 16 bytes) the first launch zeroes -- the caller's gradient buffer
+    and ``scratch`` -- instead of a separate memset in front of the step.
     """
     require_cuda(x, y, loss_out, *params)
     N, H, W, T, V = x.shape
@@ -527,8 +529,13 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     adj = torch.empty(heads, cfg.nodes, cfg.nodes, device=dev, dtype=torch.float32)
     wpack = torch.empty(lib().cgat_stream_wpack_bytes(ctypes.byref(sd), 0), dtype=torch.uint8, device=dev)
     bias_d = torch.empty(heads * cfg.nodes * cfg.co, device=dev, dtype=torch.float32)
-    _lib.call("cgat_stream_prepare", ctypes.byref(sd), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
-              _lib.ptr_array(Bs), ptr(wpack), None, None, ptr(bias_d), ptr(a_st), ptr(adj), st)
+    if clear is not None:
+        _lib.call("cgat_stream_prepare_clear", ctypes.byref(sd), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
+                  _lib.ptr_array(Bs), ptr(wpack), None, None, ptr(bias_d), ptr(a_st), ptr(adj), ptr(clear),
+                  clear.numel() * clear.element_size(), st)
+    else:
+        _lib.call("cgat_stream_prepare", ctypes.byref(sd), _lib.ptr_array(ws), _lib.ptr_array(bs), _lib.ptr_array(as_),
+                  _lib.ptr_array(Bs), ptr(wpack), None, None, ptr(bias_d), ptr(a_st), ptr(adj), st)
     mc = None if mask is None else mask.to(torch.uint8).contiguous()
     na, nadj, nb = heads * 2 * cfg.co, heads * cfg.nodes * cfg.nodes, heads * (cfg.co + 2)
     if acc is None or acc.numel() < na + nadj + nb:  # ``acc``: a caller-owned, already zeroed fp32 accumulator

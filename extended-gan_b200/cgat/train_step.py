@@ -186,17 +186,21 @@ class TrainStep:
     def _fwd_bwd(self, with_adam: bool = False):
         """Forward + loss + backward into the flat gradient buffer; ``with_adam``: the fused path also applies the optimiser
         step in its last launch (``run`` asks for it where ``_adam_in_graph``; probes and warm-ups never do)."""
-        self.flat.zero_grad()  # gradients, loss scalars and accumulators: one memset
         if self.fused_stream is not None and self.fused_stream.train_step_supported(self.x):
-            # forward + loss + backward in one kernel (cgat_layer_train)
+            # forward + loss + backward in one kernel (cgat_layer_train); gradients, loss scalars and accumulators are
+            # cleared by the step's first launch (cgat_stream_prepare_clear), not by a memset node of their own
+            clear = self.flat.grad_all if self.flat.grad_all.data_ptr() % 16 == 0 and self.flat.grad_all.numel() % 4 == 0 else None
+            if clear is None:
+                self.flat.zero_grad()
             adam = None
             if with_adam and self._adam_in_graph:
                 adam = (self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._step_dev, self._hyper)
             self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc, x_planar=self.xp,
-                                               scratch=self.flat.scratch, adam=adam,
+                                               scratch=self.flat.scratch, adam=adam, clear=clear,
                                                precision="fp32" if self.precision == "fp32" else
                                                ("fp16x2" if self.precision == "auto" else "fp16x2-unguarded"))
             return
+        self.flat.zero_grad()  # gradients, loss scalars and accumulators: one memset
         prev, functional.DIRECT_GRAD = functional.DIRECT_GRAD, True  # param-grad kernels add into flat_grad views
         try:
             out = self.model(self.x)

@@ -92,11 +92,15 @@ struct PrepArgs {
   float* bias_dense;           // conv: [cout]
   float* a_stacked;            // [heads][2co]
   float* adj;                  // [heads][nodes][nodes] normalised
+  uint4* zero;                 // optional: a buffer this launch clears (the step's accumulators: no separate memset node)
+  long long zero_n16;          // in 16-byte units
 };
 
 __global__ void __launch_bounds__(ADJ_THREADS) stream_prepare_kernel(const PrepArgs A) {
   griddep_launch();  // the layer kernel behind this one starts fetching its input tiles right away (common.cuh)
   griddep_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < A.zero_n16; i += (long long)gridDim.x * blockDim.x)
+    A.zero[i] = make_uint4(0, 0, 0, 0);
   const StreamGeom g = make_geom(A.d);
   if ((int)blockIdx.x < g.heads) {  // adjacency normalisation of head blockIdx.x (baseline_model.py:41-50)
     adj_norm_fwd_block(A.B.p[blockIdx.x], A.adj + (size_t)blockIdx.x * g.nodes * g.nodes, g.nodes, A.d.transpose_adj, 0);
@@ -536,10 +540,13 @@ extern "C" int64_t cgat_stream_wpack_bytes(const cgat_stream_desc* d, int dgrad)
   return dgrad ? (int64_t)g.d_npairs * 2 * g.d_npad * 16 : (int64_t)g.npairs * 2 * g.npad * 16;
 }
 
-extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const float* const* bias,
-                                   const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
-                                   float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* stream) {
+static int prepare_impl(const cgat_stream_desc* d, const float* const* w, const float* const* bias,
+                        const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
+                        float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* zero, int64_t zero_bytes,
+                        void* stream) {
   if (int rc = check_desc(d)) return rc;
+  if (zero_bytes < 0 || (zero_bytes > 0 && (!zero || !aligned16(zero) || zero_bytes % 16)))
+    return fail(CGAT_EALIGN, "the buffer to clear must be 16-byte aligned and a multiple of 16 bytes");
   if (!w || !a || !B || !a_stacked || !adj) return fail(CGAT_EINVAL, "null argument");
   if (d->mapping == 1 && (!wpack || !bias_dense)) return fail(CGAT_EINVAL, "conv mapping needs wpack and bias_dense");
   if (d->mapping == 0 && !w_stacked) return fail(CGAT_EINVAL, "linear mapping needs w_stacked");
@@ -557,6 +564,8 @@ extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const
   A.bias_dense = bias_dense;
   A.a_stacked = a_stacked;
   A.adj = adj;
+  A.zero = (uint4*)zero;
+  A.zero_n16 = zero_bytes / 16;
   const StreamGeom g = make_geom(*d);
   long long work = d->mapping == 1 ? (long long)g.npairs * 2 * g.npad * 8 : (long long)g.heads * g.ci * g.co;
   if (d->mapping == 1 && d->wgrad_cols) work = (long long)lf_weight_chunks(g.cin) * g.npad * 8;
@@ -654,4 +663,17 @@ extern "C" int cgat_stream_finish(const cgat_stream_desc* d, const float* wg_par
   }
   return param_grads_impl(d, wg_partial, ncta, nt, nullptr, ga, gadj, gbias, B, w, bias, a, g_w, g_bias, g_a, g_B, accumulate,
                           select, (long long)alt_offset, loss_mse, counter, adam_param ? &O : nullptr, stream);
+}
+
+extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const float* const* bias,
+                                   const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
+                                   float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* stream) {
+  return prepare_impl(d, w, bias, a, B, wpack, wpack_dgrad, w_stacked, bias_dense, a_stacked, adj, nullptr, 0, stream);
+}
+
+extern "C" int cgat_stream_prepare_clear(const cgat_stream_desc* d, const float* const* w, const float* const* bias,
+                                         const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
+                                         float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* clear,
+                                         int64_t clear_bytes, void* stream) {
+  return prepare_impl(d, w, bias, a, B, wpack, wpack_dgrad, w_stacked, bias_dense, a_stacked, adj, clear, clear_bytes, stream);
 }

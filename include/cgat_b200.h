@@ -165,6 +165,12 @@ int64_t cgat_stream_wpack_bytes(const cgat_stream_desc* d, int dgrad);
 int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const float* const* bias,
                         const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
                         float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* stream);
+/* The same launch also clears `clear_bytes` bytes at `clear` (16-byte aligned, a multiple of 16): the train step's
+ * accumulators and gradient buffer, so that the step needs no separate memset node in front of it.             */
+int cgat_stream_prepare_clear(const cgat_stream_desc* d, const float* const* w, const float* const* bias,
+                              const float* const* a, const float* const* B, void* wpack, void* wpack_dgrad,
+                              float* w_stacked, float* bias_dense, float* a_stacked, float* adj, void* clear,
+                              int64_t clear_bytes, void* stream);
 /* ONE launch: per-head parameter gradients from the kernels' accumulators (wgrad partials or gW, ga, gadj);
  * accumulate != 0 adds into g_* (e.g. the parameters' .grad buffers) instead of overwriting.  w, bias, a: the same
  * per-head parameter pointers cgat_stream_prepare took; read only when wgrad_cols = 1 and the partials carry the score

@@ -1,0 +1,90 @@
+"""Multi-process GPU check (run under torchrun, one rank per GPU) that DATA-PARALLEL training reproduces single-GPU training:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tests/mp_dp_check.py
+
+A batch of 32 * world samples (config-2 shape: 64x64x4x6) is sharded over the ranks (cgat.parallel.shard_range); every rank
+also trains the WHOLE batch alone (a process group of size one: the single-GPU path with Adam inside cgat_stream_finish).
+  * step-1 gradients: all-reduced mean of the shard gradients == full-batch gradient (the loss is a mean over samples);
+  * three steps with the peer-memory exchange (cgat_p2p_allreduce_adam) and with NCCL: parameters and loss track the
+    single-GPU run (Adam's first steps move every element by ~lr, so the parameter bar is a fraction of lr)."""
+import copy
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "extended-gan_b200")]
+import torch
+import torch.distributed as dist
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    solo = None
+    for r in range(world):  # (new_group is collective: every rank creates every group)
+        grp = dist.new_group([r])
+        if r == rank:
+            solo = grp
+    from cgat.parallel import shard_range
+    from cgat.train_step import TrainStep
+    from convolutional_gat.GAT3D.GATMultistream import Model
+
+    LR, STEPS, PER = 1e-3, 3, 32
+    torch.manual_seed(369)
+    base = Model(image_width=64, image_height=64, n_vertices=6, attention_type="temporal", mapping_type="conv")
+    g = torch.Generator().manual_seed(7)
+    X = torch.rand(PER * world, 64, 64, 4, 6, generator=g).bfloat16().to(dev)
+    Y = torch.rand(PER * world, 64, 64, 4, 6, generator=g).bfloat16().to(dev)
+    lo, hi = shard_range(PER * world, rank, world)
+    x, y = X[lo:hi].contiguous(), Y[lo:hi].contiguous()
+
+    single = TrainStep(copy.deepcopy(base).to(dev), X, Y, lr=LR, process_group=solo)
+    assert single.world == 1 and single._adam_in_graph
+    # ---- step-1 gradients ----
+    dp = TrainStep(copy.deepcopy(base).to(dev), x, y, lr=LR)
+    assert dp.world == world and not dp._adam_in_graph
+    dp._fwd_bwd()
+    dp.flat.all_reduce_grads()
+    single._fwd_bwd()
+    torch.cuda.synchronize()
+    gd, gs = dp.flat_grad / world, single.flat_grad
+    scale = float(gs.abs().max())
+    err = float((gd - gs).abs().max())
+    assert err <= 2e-3 * scale, f"mean of shard gradients vs full-batch gradient: max err {err:.3e} at scale {scale:.3e}"
+    loss_dp = dp.loss.clone()
+    dist.all_reduce(loss_dp)
+    assert abs(float(loss_dp) / world - float(single.loss)) <= 1e-4 * abs(float(single.loss))
+    # ---- three optimiser steps: P2P exchange, NCCL exchange, single GPU ----
+    runs = {}
+    for name in ("p2p", "nccl"):
+        ts = TrainStep(copy.deepcopy(base).to(dev), x, y, lr=LR)
+        ts.sync_params()
+        if name == "p2p":
+            assert ts.enable_p2p_exchange(), getattr(ts.flat, "p2p_error", "p2p setup returned False")
+        runs[name] = ts
+    single = TrainStep(copy.deepcopy(base).to(dev), X, Y, lr=LR, process_group=solo)
+    for _ in range(STEPS):
+        for ts in runs.values():
+            ts.step(x, y)
+        single.step(X, Y)
+    torch.cuda.synchronize()
+    assert not runs["p2p"].flat.p2p_timed_out()
+    for name, ts in runs.items():
+        d = float((ts.flat_param - single.flat_param).abs().max())
+        # every element moves ~lr per step; shard-vs-full differences of the gradient (bf16 kernel noise) may flip the sign of
+        # an element whose gradient is ~0 in one step: allow half a step in total
+        assert d <= 0.5 * LR, f"{name}: parameters after {STEPS} steps differ from the single-GPU run by {d:.3e} (lr {LR})"
+        l = ts.loss.clone()
+        dist.all_reduce(l)
+        assert abs(float(l) / world - float(single.loss)) <= 2e-3 * abs(float(single.loss)), name
+    assert int(single._step_dev.item()) == STEPS
+    if rank == 0:
+        print(f"data-parallel == single-GPU OK on {world} GPUs: grad err {err / scale:.2e} of scale, "
+              f"param drift p2p {float((runs['p2p'].flat_param - single.flat_param).abs().max()):.2e}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

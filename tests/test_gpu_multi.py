@@ -1,5 +1,6 @@
-"""Multi-GPU checks (skipped on boxes with a single GPU): the peer-memory gradient exchange + Adam kernel against the
-NCCL all-reduce path, launched under torchrun with one rank per GPU."""
+"""Multi-GPU checks (run whenever at least 2 GPUs are visible, skipped otherwise), launched under torchrun with one rank
+per GPU: the peer-memory gradient exchange + Adam kernel against the NCCL all-reduce path, and data-parallel training
+(32 samples per rank) against single-GPU training of the whole batch."""
 import os
 import subprocess
 import sys
@@ -18,3 +19,12 @@ def test_p2p_exchange_matches_nccl_two_ranks():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "p2p exchange OK" in res.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_data_parallel_matches_single_gpu_two_ranks():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29543", os.path.join(ROOT, "tests", "mp_dp_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "data-parallel == single-GPU OK" in res.stdout
