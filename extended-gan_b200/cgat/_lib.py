@@ -122,6 +122,11 @@ SIGNATURES = {
     "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
     "cgat_loader_gather_planar": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
     "cgat_records_to_planar": [_P, _P, _I64, _I, _I, _I, _P],
+    "cgat_comm_available": [],
+    "cgat_comm_unique_id": [_P],
+    "cgat_comm_init": [_I, _I, _P, _P],
+    "cgat_flat_allreduce": [_P, _P, _I64, _P],
+    "cgat_comm_destroy": [_P],
     "cgat_bn_workspace_bytes": [_I],
     "cgat_bn_stats": [_P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P, _P, _F, _F, _P],
     "cgat_bn_act_fwd": [_P, _P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P, _I, _F, _P],

@@ -354,3 +354,61 @@ class TrainStep:
         s["free"].record(cur)
         self._exchange_and_update()
         return self.loss
+
+    # -- the raw-frame pipeline as ONE graph launch per step ------------------------------------------------------------
+    def enable_raw_pipeline(self, frames_host: torch.Tensor, start_host: torch.Tensor, *, normalizing_max=254.0, power=1.0):
+        """End-to-end loop for a loader that refills the SAME pinned staging buffers every batch (raw uint8 frames
+        ``[L, V, H, W]`` + int32 window starts ``[N]``, kmni_data_loader.py:72-127).  Two input slots; for each ONE captured
+        graph holding two parallel branches: the train step on this slot's batch, and -- on a forked stream -- the
+        host-to-device copies plus ``cgat_loader_gather_planar`` of the NEXT batch into the other slot.  ``run_pipelined``
+        is then one graph launch per step (the two-graph / event version of ``prefetch_raw`` + ``run_slot`` costs the host
+        more than the GPU needs for the step).  Call ``prime_raw_pipeline()`` after filling the staging buffers with the
+        first batch."""
+        from convolutional_gat.data_loaders.kmni_data_loader import gather_windows
+
+        if not (frames_host.is_pinned() and start_host.is_pinned()):
+            raise RuntimeError("enable_raw_pipeline needs pinned staging buffers")
+        if self.fused_stream is None or self.xp is None:
+            raise RuntimeError("enable_raw_pipeline serves the fused train step (planar x)")
+        if start_host.numel() != self.x.shape[0]:
+            raise RuntimeError(f"{start_host.numel()} window starts for a step of {self.x.shape[0]} samples")
+        self.enable_prefetch(2)
+        N, H, W, T, V = self.x.shape
+        for s in self._slots[:2]:
+            s["frames"] = torch.empty(frames_host.shape, dtype=torch.uint8, device=self.device)
+            s["start"] = torch.empty(start_host.shape, dtype=torch.int32, device=self.device)
+        self._raw_host = (frames_host, start_host, float(normalizing_max), float(power))
+
+        def fill(slot):
+            slot["frames"].copy_(frames_host, non_blocking=True)
+            slot["start"].copy_(start_host, non_blocking=True)
+            gather_windows(slot["frames"], slot["start"], crop=H, steps=T, normalizing_max=normalizing_max, power=power,
+                           out=(slot["xp"], slot["y"]), planar=True)
+
+        self._raw_fill = fill
+        side = torch.cuda.Stream()
+        keep = (self.x, self.y, self.xp, self.graph)
+        torch.cuda.synchronize()
+        for k in range(2):
+            cur_slot, other = self._slots[k], self._slots[1 - k]
+            self.x, self.y, self.xp = cur_slot["x"], cur_slot["y"], cur_slot["xp"]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cur = torch.cuda.current_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    fill(other)
+                self._fwd_bwd(with_adam=True)
+                cur.wait_stream(side)
+            cur_slot["pipe_graph"] = g
+        self.x, self.y, self.xp, self.graph = keep
+
+    def prime_raw_pipeline(self):
+        """Load the batch currently in the staging buffers into slot 0 (before the first ``run_pipelined(0)``)."""
+        self._raw_fill(self._slots[0])
+
+    def run_pipelined(self, slot: int) -> torch.Tensor:
+        """One optimisation step on ``slot``'s batch while the staging buffers' batch is loaded into the other slot."""
+        self._slots[slot]["pipe_graph"].replay()
+        self._exchange_and_update()
+        return self.loss

@@ -284,6 +284,18 @@ int cgat_loss_fwd_bwd(const void* yhat, const void* y, void* dyhat, float* loss_
 int cgat_adam_step(float* param, const float* grad, float* m, float* v, const int64_t* step_dev, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                    void* stream);
+/* 8(b)  gradient exchange for hosts that are not PyTorch: NCCL (ncclAllReduce over NVLink / NVSwitch) bound at run time
+ * with dlopen("libnccl.so.2") -- no link-time dependency.  rank 0 obtains the 128-byte id (cgat_comm_unique_id) and ships
+ * it to the other ranks by its own means; every rank creates ONE communicator (cgat_comm_init) and calls
+ * cgat_flat_allreduce (in-place SUM over the flat fp32 gradient buffer, on `stream`; the 1/world scale is the grad_scale of
+ * the Adam entry points) once per step.  The Python package keeps torch.distributed's communicator; models of <= 2^20
+ * parameters use cgat_p2p_allreduce_adam instead.  cgat_comm_available: 1 when libnccl could be loaded.            */
+int cgat_comm_available(void);
+int cgat_comm_unique_id(void* id128);
+int cgat_comm_init(int32_t rank, int32_t world, const void* id128, void** comm_out);
+int cgat_flat_allreduce(void* comm, float* buf, int64_t n, void* stream);
+int cgat_comm_destroy(void* comm);
+
 /* a11 / f2  BatchNorm2d + activation + Dropout2d around the convs, NHWC (csrc/norm_act_kernels.cu): the rest of the
  * reference's ConvBlock (dcgan/model.py:35-52: BatchNorm2d -> Dropout2d(0.01) -> activation) and of the SmaAt-UNet double
  * convs (BatchNorm2d -> ReLU).  x, y, dy, dx [n][hw][c] of `dtype` (fp32 / bf16); statistics and parameters fp32 [c].

@@ -80,6 +80,29 @@ def main():
         dist.all_reduce(l)
         assert abs(float(l) / world - float(single.loss)) <= 2e-3 * abs(float(single.loss)), name
     assert int(single._step_dev.item()) == STEPS
+    # ---- the C ABI's own NCCL exchange (include/cgat_b200.h, 8(b)): what a host without torch.distributed calls ----
+    import ctypes
+
+    from cgat import _lib
+    L = _lib.lib()
+    assert L.cgat_comm_available() == 1
+    idbuf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        raw = (ctypes.c_char * 128)()
+        assert L.cgat_comm_unique_id(ctypes.cast(raw, ctypes.c_void_p)) == 0
+        idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+    idbuf = idbuf.to(dev)
+    dist.broadcast(idbuf, 0)  # (the id travels by the host's own means: here torch.distributed)
+    raw = (ctypes.c_char * 128).from_buffer_copy(bytes(idbuf.cpu().tolist()))
+    comm = ctypes.c_void_p()
+    assert L.cgat_comm_init(rank, world, ctypes.cast(raw, ctypes.c_void_p), ctypes.byref(comm)) == 0, L.cgat_last_error()
+    buf = torch.arange(1000, dtype=torch.float32, device=dev) * (rank + 1)
+    assert L.cgat_flat_allreduce(comm, ctypes.c_void_p(buf.data_ptr()), buf.numel(),
+                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0, L.cgat_last_error()
+    torch.cuda.synchronize()
+    want = torch.arange(1000, dtype=torch.float32, device=dev) * (world * (world + 1) / 2)
+    assert torch.equal(buf, want), "cgat_flat_allreduce: wrong sum"
+    assert L.cgat_comm_destroy(comm) == 0
     if rank == 0:
         print(f"data-parallel == single-GPU OK on {world} GPUs: grad err {err / scale:.2e} of scale, "
               f"param drift p2p {float((runs['p2p'].flat_param - single.flat_param).abs().max()):.2e}")
