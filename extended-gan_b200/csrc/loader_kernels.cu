@@ -29,7 +29,7 @@ template <typename T, int RECT>
 __global__ void __launch_bounds__(LD_THREADS, 16)
 loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ start, T* __restrict__ x,
                      T* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, int steps, float nmax, float power,
-                     int x_planar) {
+                     int x_planar, int mul_exact) {
   extern __shared__ __align__(16) unsigned char ld_smem[];
   T* lut = reinterpret_cast<T*>(ld_smem);                       // [256]
   uint8_t* tile = ld_smem + 256 * sizeof(T);                    // [2*steps*V][LD_THREADS]
@@ -95,6 +95,28 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
       dst = x + ((size_t)s * (rec * sizeof(T) / 16) * qstride + (size_t)hh * wp + ww + 1) * (16 / sizeof(T));
     }
     const uint8_t* col = tile + (size_t)(half * rec) * LD_THREADS + threadIdx.x;
+    if constexpr (RECT != 0 && sizeof(T) == 2) {
+      if (mul_exact) {
+        // bf16 output, power = 1, and k * (1/max) rounds to the same bf16 as k / max for all 256 byte values (checked on the
+        // host at launch): convert arithmetically -- the table costs one more shared-memory access per element, with bank
+        // conflicts (the kernel was bound by the shared-memory pipe: ncu mio_throttle 4.0 per issue)
+        const float inv = 1.f / nmax;
+        uint8_t k[RECT];
+#pragma unroll
+        for (int e = 0; e < RECT; ++e) k[e] = col[(size_t)e * LD_THREADS];
+#pragma unroll
+        for (int q = 0; q < RECT / 8; ++q) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn((float)k[q * 8 + 2 * j] * inv, (float)k[q * 8 + 2 * j + 1] * inv);
+            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          reinterpret_cast<uint4*>(dst)[q * qstride] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        continue;
+      }
+    }
     if constexpr (RECT != 0 && (RECT * sizeof(T)) % 16 == 0) {
       constexpr int PER = 16 / sizeof(T);
       uint8_t k[RECT];
@@ -194,9 +216,20 @@ static int cgat::loader_gather_impl(const uint8_t* frames, int64_t n_frames, con
   const size_t esz = dtype == CGAT_F32 ? 4 : 2;
   const size_t smem = 256 * esz + (size_t)2 * steps * vertices * LD_THREADS;
   if (smem > 48 * 1024) return fail(CGAT_EUNSUPPORTED, "loader tile needs %zu B of shared memory", smem);
+  // may the bf16 path multiply by the reciprocal?  Only if that is bit-identical to the reference's division (then rounded
+  // to bf16) for every byte value
+  int mul_exact = 0;
+  if (dtype == CGAT_BF16 && power == 1.0f) {
+    mul_exact = 1;
+    const float inv = 1.f / normalizing_max;
+    for (int k = 0; k < 256 && mul_exact; ++k) {
+      const __nv_bfloat16 a = __float2bfloat16_rn((float)k / normalizing_max), b = __float2bfloat16_rn((float)k * inv);
+      if (__bfloat16_as_ushort(a) != __bfloat16_as_ushort(b)) mul_exact = 0;
+    }
+  }
 #define LD_LAUNCH(T, R)                                                                                                   \
   loader_gather_kernel<T, R><<<grid, LD_THREADS, smem, st>>>(frames, start, (T*)x, (T*)y, vertices, h, w, crop_h, crop_w, steps, \
-                                                             normalizing_max, power, x_planar)
+                                                             normalizing_max, power, x_planar, mul_exact)
   const int rec = steps * vertices;
   if (dtype == CGAT_F32) {
     if (rec == 24) LD_LAUNCH(float, 24); else LD_LAUNCH(float, 0);
