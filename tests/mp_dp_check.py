@@ -71,11 +71,24 @@ def main():
         single.step(X, Y)
     torch.cuda.synchronize()
     assert not runs["p2p"].flat.p2p_timed_out()
+    # Compared: every parameter except the adjacency matrices B.  B enters through minmax(B + I) (baseline_model.py:41-50),
+    # whose backward routes the whole min / max gradient to the arg-min / arg-max entry; Adam's first step moves every
+    # off-diagonal entry of B by -+lr from the same start, so after step 1 they are tied to ~1e-10 and WHICH entry receives
+    # that gradient at step 2 depends on the last bit of the gradient sums (measured: 1.7e-7 apart between the sharded and
+    # the full-batch run) -- the reference's own math is chaotic there, on one GPU as well.  The loss, which sees B only
+    # through the normalised matrix, must still track (checked below to 2e-3), and so must every other parameter.
+    keep = torch.ones_like(single.flat_param, dtype=torch.bool)
+    off = 0
+    for n, p_ in single.active:
+        if n.endswith(".B"):
+            keep[off:off + p_.numel()] = False
+        off += p_.numel()
+    assert off <= keep.numel() and int(keep.sum()) < keep.numel()
     for name, ts in runs.items():
-        d = float((ts.flat_param - single.flat_param).abs().max())
-        # every element moves ~lr per step; shard-vs-full differences of the gradient (bf16 kernel noise) may flip the sign of
-        # an element whose gradient is ~0 in one step: allow half a step in total
-        assert d <= 0.5 * LR, f"{name}: parameters after {STEPS} steps differ from the single-GPU run by {d:.3e} (lr {LR})"
+        diff = (ts.flat_param - single.flat_param).abs()
+        d = float(diff[keep].max())
+        assert d <= 0.3 * LR, (f"{name}: parameters after {STEPS} steps differ from the single-GPU run by {d:.3e} "
+                               f"(lr {LR}; adjacency entries: {float(diff[~keep].max()):.3e})")
         l = ts.loss.clone()
         dist.all_reduce(l)
         assert abs(float(l) / world - float(single.loss)) <= 2e-3 * abs(float(single.loss)), name
@@ -105,7 +118,7 @@ def main():
     assert L.cgat_comm_destroy(comm) == 0
     if rank == 0:
         print(f"data-parallel == single-GPU OK on {world} GPUs: grad err {err / scale:.2e} of scale, "
-              f"param drift p2p {float((runs['p2p'].flat_param - single.flat_param).abs().max()):.2e}")
+              f"param drift p2p {float((runs['p2p'].flat_param - single.flat_param).abs()[keep].max()):.2e}")
     dist.destroy_process_group()
 
 
