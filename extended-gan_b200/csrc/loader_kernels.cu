@@ -165,6 +165,45 @@ __global__ void __launch_bounds__(256) records_to_planar_kernel(const uint4* __r
   }
 }
 
+// ARAI loader (convolutional_gat/data_loaders/arai_data_loader.py:57-93,117-119): the preprocessed files hold FLOAT frames
+// data[L][regions][1][H][W]; __batchify cuts windows i .. i+2*steps-1 (stride 1), splits them into steps input and steps
+// target frames, fix_sizes squeezes the singleton axis and permutes to [N, H, W, T, V].  No normalisation (norm_max /
+// norm_min are stored and never applied).  The reference materialises every overlapping window on the host and copies
+// 2*N*steps*V*H*W floats per batch; here a file's frames cross PCIe once and a batch is one launch:
+//   x[n, h, w, t, v] = frames[start[n] + t, v, h, w]        y[...] = frames[start[n] + steps + t, v, h, w]
+// HBM-bound transpose: a CTA stages the rec = steps*V source planes of LD_THREADS consecutive pixels (coalesced along the
+// image row) in shared memory with a one-float skew, then streams its CONTIGUOUS npix*rec output block out with
+// consecutive threads on consecutive elements (fp32: bit-exact copy; bf16: one rounding).
+template <typename T>
+__global__ void __launch_bounds__(LD_THREADS)
+loader_gather_f32_kernel(const float* __restrict__ frames, const int32_t* __restrict__ start, T* __restrict__ x,
+                         T* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, int steps) {
+  extern __shared__ __align__(16) unsigned char ld_smem[];
+  float* tile = reinterpret_cast<float*>(ld_smem);  // [rec][LD_THREADS + 1]
+  const int rec = steps * V;
+  const long long per_sample = (long long)crop_h * crop_w;
+  const long long blocks_per_sample = (per_sample + LD_THREADS - 1) / LD_THREADS;
+  const int s = (int)(blockIdx.x / blocks_per_sample);
+  const long long p0 = (long long)(blockIdx.x % blocks_per_sample) * LD_THREADS;
+  const int npix = (int)min((long long)LD_THREADS, per_sample - p0);
+  const size_t plane = (size_t)H * W;
+  const int p = (int)p0 + threadIdx.x, h = p / crop_w, w = p - h * crop_w;
+  const size_t off = (size_t)h * W + w;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const float* src0 = frames + ((size_t)start[s] + (size_t)half * steps) * V * plane;
+    if ((int)threadIdx.x < npix)
+      for (int e = 0; e < rec; ++e) tile[e * (LD_THREADS + 1) + threadIdx.x] = src0[(size_t)e * plane + off];
+    __syncthreads();
+    T* dst = (half ? y : x) + ((long long)s * per_sample + p0) * rec;
+    for (int i = threadIdx.x; i < npix * rec; i += LD_THREADS) {
+      const int px = i / rec, e = i - px * rec;
+      dst[i] = DT<T>::from_f(tile[e * (LD_THREADS + 1) + px]);
+    }
+    __syncthreads();
+  }
+}
+
 static int loader_gather_impl(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x, void* y,
                               int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
                               int32_t steps, float normalizing_max, float power, int32_t dtype, int x_planar, void* stream);
@@ -186,6 +225,28 @@ extern "C" int cgat_loader_gather_planar(const uint8_t* frames, int64_t n_frames
   if ((steps * vertices) % 8) return fail(CGAT_EUNSUPPORTED, "chunk-planar x needs steps*vertices to be a multiple of 8");
   return loader_gather_impl(frames, n_frames, start, x_planar, y, n, vertices, h, w, crop_h, crop_w, steps, normalizing_max,
                             power, CGAT_BF16, 1, stream);
+}
+
+extern "C" int cgat_loader_gather_f32(const float* frames, int64_t n_frames, const int32_t* start, void* x, void* y,
+                                      int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
+                                      int32_t steps, int32_t dtype, void* stream) {
+  if (!frames || !start || !x || !y) return fail(CGAT_EINVAL, "null argument");
+  if (n < 1 || vertices < 1 || h < 1 || w < 1 || steps < 1 || crop_h < 1 || crop_w < 1 || crop_h > h || crop_w > w ||
+      n_frames < 2 * steps)
+    return fail(CGAT_EINVAL, "bad loader geometry");
+  if (steps * vertices > LD_MAX_REC) return fail(CGAT_EUNSUPPORTED, "pixel record of %d elements (max %d)", steps * vertices, LD_MAX_REC);
+  if (dtype != CGAT_F32 && dtype != CGAT_BF16) return fail(CGAT_EINVAL, "bad dtype %d", dtype);
+  const long long per_sample = (long long)crop_h * crop_w;
+  const unsigned grid = (unsigned)(n * ((per_sample + LD_THREADS - 1) / LD_THREADS));
+  const size_t smem = (size_t)steps * vertices * (LD_THREADS + 1) * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CGAT_F32)
+    loader_gather_f32_kernel<float><<<grid, LD_THREADS, smem, st>>>(frames, start, (float*)x, (float*)y, vertices, h, w,
+                                                                    crop_h, crop_w, steps);
+  else
+    loader_gather_f32_kernel<__nv_bfloat16><<<grid, LD_THREADS, smem, st>>>(frames, start, (__nv_bfloat16*)x,
+                                                                            (__nv_bfloat16*)y, vertices, h, w, crop_h, crop_w, steps);
+  return check_launch("loader_gather_f32_kernel");
 }
 
 extern "C" int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int32_t h, int32_t w, int32_t rec,

@@ -385,6 +385,14 @@ int cgat_loader_gather(const uint8_t* frames, int64_t n_frames, const int32_t* s
 int cgat_loader_gather_planar(const uint8_t* frames, int64_t n_frames, const int32_t* start, void* x_planar, void* y,
                               int32_t n, int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w,
                               int32_t steps, float normalizing_max, float power, void* stream);
+/* f3  the ARAI loader's windowing + layout change on the device, replacing
+ * convolutional_gat/data_loaders/arai_data_loader.py:57-93 (__batchify + fix_sizes): FLOAT frames
+ * [n_frames][vertices][h][w] (the files' [L][regions][1][H][W]), no normalisation:
+ *   x[s, h, w, t, v] = frames[start[s] + t, v, h, w]     y[s, h, w, t, v] = frames[start[s] + steps + t, v, h, w]
+ * x, y [n][crop_h][crop_w][steps][vertices] of `dtype` (fp32: bit-exact copy; bf16: rounded once).                    */
+int cgat_loader_gather_f32(const float* frames, int64_t n_frames, const int32_t* start, void* x, void* y, int32_t n,
+                           int32_t vertices, int32_t h, int32_t w, int32_t crop_h, int32_t crop_w, int32_t steps,
+                           int32_t dtype, void* stream);
 /* pixel records [n][h][w][rec] bf16 -> padded chunk-planar [n][rec/8][h][wp][8] for an x tensor that did not come from
  * the loader kernel (the reference's own DataLoader, convolutional_gat/train.py:128); padding columns not written.   */
 int cgat_records_to_planar(const void* x, void* x_planar, int64_t n, int32_t h, int32_t w, int32_t rec, void* stream);

@@ -230,6 +230,39 @@ def kmni_loader():
     return fx
 
 
+def arai_loader():
+    """Every batch of the reference's own ARAI ``DataLoader`` (arai_data_loader.py:14-191) through ``get_loaders`` on a
+    synthetic preprocessed folder: float frames ``[L, regions, 1, H, W]`` in files ``<k>.pt`` sorted numerically, plus
+    ``metadata.json``.  Three files of 14 / 9 / 12 frames at batch size 3 (of file 2, the last, only the first batch is
+    served: see ``spec.arai_batch_plan``), and a one-file folder (first batch only)."""
+    import json
+    import tempfile
+
+    ar = ref_loader.arai_loader()
+    g = torch.Generator().manual_seed(369)
+    fx = {}
+    lengths = (14, 9, 12)
+    with tempfile.TemporaryDirectory() as d:
+        for sub in ("training", "validation"):
+            os.makedirs(os.path.join(d, sub))
+        for i, L in enumerate(lengths):
+            f = torch.rand(L, 5, 1, 12, 12, generator=g)
+            torch.save(f, os.path.join(d, "training", f"{i}.pt"))
+            fx[f"file{i}"] = f
+        torch.save(fx["file0"], os.path.join(d, "validation", "0.pt"))
+        with open(os.path.join(d, "metadata.json"), "w") as fh:
+            json.dump({"n_regions": 5, "training": {"length": sum(lengths)}, "validation": {"length": lengths[0]}}, fh)
+        train, val, _ = ar.get_loaders(3, 4, d, "cpu", downsample_size=(8, 10))
+        fx["train.len"] = torch.tensor(len(train))
+        for tag, dl in (("train", train), ("val", val)):
+            n = 0
+            for x, y in dl:
+                fx[f"{tag}.x{n}"], fx[f"{tag}.y{n}"] = x.contiguous().clone(), y.contiguous().clone()
+                n += 1
+            fx[f"{tag}.n"] = torch.tensor(n)
+    return fx
+
+
 def _ref_functions(relpath, names, namespace):
     """Compile the named top-level functions of a reference file (whose module cannot be imported: missing GAT3D /
     matplotlib / torchinfo) from its UNMODIFIED source text into ``namespace``."""
@@ -318,6 +351,7 @@ FIXTURES = {
     "dcgan_nets": dcgan_nets,
     "dcgan_step": dcgan_step,
     "kmni_loader": kmni_loader,
+    "arai_loader": arai_loader,
     "val_metrics": val_metrics,
     "adjacency": adjacency,
 }

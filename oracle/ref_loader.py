@@ -81,6 +81,17 @@ def kmni_loader():
     return _cache["kmni"]
 
 
+def arai_loader():
+    """The reference's ``convolutional_gat/data_loaders/arai_data_loader.py`` as a module object (imports ipdb / tqdm:
+    ipdb stubbed); the UNMODIFIED ``DataLoader`` / ``get_loaders`` run on a folder of synthetic files."""
+    if "arai" in _cache:
+        return _cache["arai"]
+    if "ipdb" not in sys.modules:
+        sys.modules["ipdb"] = types.ModuleType("ipdb")
+    _cache["arai"] = _load("_ref_arai_data_loader", "convolutional_gat/data_loaders/arai_data_loader.py")
+    return _cache["arai"]
+
+
 @contextlib.contextmanager
 def cpu_shim():
     """Make ``Tensor.cuda`` a no-op so the reference GAT layers run on CPU tensors."""

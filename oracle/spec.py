@@ -471,6 +471,41 @@ def kmni_windows(frames: torch.Tensor, start, *, crop=None, steps: int = 4, norm
         ys.append(seg[steps:].permute(2, 3, 0, 1))
     return torch.stack(xs), torch.stack(ys)
 
+# ----------------------------------------------------------------------------------------------------------------
+# ARAI loader (convolutional_gat/data_loaders/arai_data_loader.py:57-93, 95-191)
+# ----------------------------------------------------------------------------------------------------------------
+def arai_windows(frames: torch.Tensor, start, *, downsample_size=(256, 256), steps: int = 4):
+    """``frames [L, R, 1, H, W]`` floats -> ``(x, y)`` ``[N, H', W', steps, R]``: crop (:144), window ``i .. i+2*steps-1``
+    split in two (:74-84), ``squeeze(3)`` + ``permute(0, 3, 4, 1, 2)`` (:89-96).  No normalisation."""
+    data = frames[:, :, :, :downsample_size[0], :downsample_size[1]]
+    xs, ys = [], []
+    for i in start:
+        chunk = data[int(i):int(i) + 2 * steps]
+        xs.append(chunk[:steps].squeeze(2).permute(2, 3, 0, 1))
+        ys.append(chunk[steps:].squeeze(2).permute(2, 3, 0, 1))
+    return torch.stack(xs), torch.stack(ys)
+
+
+def arai_batch_plan(file_lengths, batch_size: int, steps: int = 4):
+    """The ``(file index, window starts)`` sequence one pass over an ARAI ``DataLoader`` yields (:98-191).  A file with
+    ``L`` frames gives ``L - 2*steps + 1`` windows served ``batch_size`` at a time, the short tail included, never merged
+    across files (:166-182).  Reading the LAST file raises ``should_stop_iteration`` (:156-157), so no further
+    ``__get_batch`` is scheduled after it (:110-115): of the last file only the FIRST batch exists.  Whether that batch is
+    handed out is a race in the reference -- ``__next__`` tests the flag (:99-101) BEFORE joining the reader thread
+    (:103-104): a consumer that comes back before ``t.load`` of the last file has finished gets the batch, a slower one
+    gets ``StopIteration``.  The plan here is the first outcome (what the reference produced when the golden vectors were
+    generated, and the only one for a one-file folder, whose single read is synchronous, :105-107)."""
+    plan = []
+    n_files = len(file_lengths)
+    for f, L in enumerate(file_lengths):
+        nw = L - (2 * steps - 1)
+        last = f == n_files - 1
+        for b in range(0, nw, batch_size):
+            plan.append((f, list(range(b, min(b + batch_size, nw)))))
+            if last:
+                break
+    return plan
+
 
 def val_batch_sums(y, y_hat, threshold, *, power=1.0, normalizing_max=254.0):
     """``[sum sq err, sum denormalised sq err, TP, FP, FN, #equal]`` of one batch (train.py:54-75, utils.py:135-167)."""

@@ -120,6 +120,20 @@ def test_kmni_windows_match_reference_loader(tag, power):
         assert torch.equal(x, fx[f"{tag}.x{b}"]) and torch.equal(y, fx[f"{tag}.y{b}"])
 
 
+def test_arai_windows_and_batch_plan_match_reference_loader():
+    """oracle/spec.arai_windows + arai_batch_plan against every batch of the reference's own ARAI DataLoader."""
+    fx = golden("arai_loader")
+    plan = spec.arai_batch_plan([14, 9, 12], 3)
+    assert len(plan) == int(fx["train.n"]) == 5
+    for b, (f, starts) in enumerate(plan):
+        x, y = spec.arai_windows(fx[f"file{f}"], starts, downsample_size=(8, 10))
+        assert torch.equal(x, fx[f"train.x{b}"]) and torch.equal(y, fx[f"train.y{b}"])
+    plan = spec.arai_batch_plan([14], 4)  # one-file folder: its first batch only
+    assert len(plan) == int(fx["val.n"]) == 1
+    x, y = spec.arai_windows(fx["file0"], plan[0][1], downsample_size=(8, 10))
+    assert torch.equal(x, fx["val.x0"]) and torch.equal(y, fx["val.y0"])
+
+
 @pytest.mark.parametrize("tag,power", [("p1", 1.0), ("p05", 0.5)])
 def test_val_metrics_match_reference_test_loop(tag, power):
     """oracle/spec.val_batch_sums, folded as train.py:76-91 does, against the reference's own ``test`` / ``get_metrics``."""
