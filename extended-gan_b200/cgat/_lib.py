@@ -132,6 +132,10 @@ SIGNATURES = {
     "cgat_bn_stats": [_P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P, _P, _F, _F, _P],
     "cgat_bn_act_fwd": [_P, _P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P, _I, _F, _P],
     "cgat_bn_act_bwd": [_P, _P, _P, _I, _I64, _I64, _I, _P, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _I, _P],
+    "cgat_bn_workspace_bytes_sets": [_I, _I],
+    "cgat_bn_stats_sets": [_P, _I, _I64, _I64, _I, _I, _P, _P, _P, _P, _P, _P, _F, _F, _P],
+    "cgat_bn_act_fwd_sets": [_P, _P, _I, _I64, _I64, _I, _I, _P, _P, _P, _P, _P, _I, _F, _P],
+    "cgat_bn_act_bwd_sets": [_P, _P, _P, _I, _I64, _I64, _I, _I, _P, _P, _P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _I, _P],
     "cgat_dropout2d_mask": [_P, _I64, _F, ctypes.c_uint64, _P, _P],
     "cgat_maxpool2_fwd": [_P, _P, _P, _I, _I64, _I, _I, _I, _P],
     "cgat_maxpool2_bwd": [_P, _P, _P, _I, _I64, _I, _I, _I, _P],
@@ -173,6 +177,7 @@ def lib() -> ctypes.CDLL:
         L.cgat_layer_workspace_bytes.restype = ctypes.c_int64
         L.cgat_p2p_mailbox_bytes.restype = ctypes.c_int64
         L.cgat_bn_workspace_bytes.restype = ctypes.c_int64
+        L.cgat_bn_workspace_bytes_sets.restype = ctypes.c_int64
         L.cgat_pool_hw_workspace_bytes.restype = ctypes.c_int64
         L.cgat_version.restype = ctypes.c_char_p
         L.cgat_last_error.restype = ctypes.c_char_p

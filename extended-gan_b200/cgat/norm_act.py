@@ -29,7 +29,7 @@ def _nhwc(x: torch.Tensor) -> torch.Tensor:
 
 class _NormActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, momentum, eps, act, slope, mask):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, training, momentum, eps, act, slope, mask, sets):
         require_cuda(x)
         if x.dtype not in (torch.float32, torch.bfloat16):
             raise RuntimeError(f"BatchNormAct2d serves fp32 and bf16 activations, got {x.dtype}")
@@ -42,38 +42,44 @@ class _NormActFn(torch.autograd.Function):
         if norm:
             g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
             if training:
-                ws = torch.empty(2 * C + 2, dtype=torch.float64, device=x.device)
-                mean = torch.empty(C, dtype=torch.float32, device=x.device)
+                if N % sets:
+                    raise RuntimeError(f"BatchNormAct2d: {sets} statistic sets do not divide a batch of {N}")
+                ws = torch.empty(sets * (2 * C + 2) + 2, dtype=torch.float64, device=x.device)
+                mean = torch.empty(sets, C, dtype=torch.float32, device=x.device)
                 rstd = torch.empty_like(mean)
-                _lib.call("cgat_bn_stats", ptr(xh), dt, N, H * W, C, ptr(ws), ptr(mean), ptr(rstd), ptr(running_mean),
-                          ptr(running_var), ptr(nbt), float(momentum), float(eps), st)
+                _lib.call("cgat_bn_stats_sets", ptr(xh), dt, N, H * W, C, sets, ptr(ws), ptr(mean), ptr(rstd),
+                          ptr(running_mean), ptr(running_var), ptr(nbt), float(momentum), float(eps), st)
             else:
+                sets = 1  # constants: one row serves every image
                 mean = running_mean.detach().float().contiguous()
                 rstd = (running_var.detach().float() + eps).rsqrt()
         else:
             g32 = b32 = None
+            sets = 1
         y = torch.empty_like(xh)
-        _lib.call("cgat_bn_act_fwd", ptr(xh), ptr(y), dt, N, H * W, C, ptr(mean), ptr(rstd), ptr(g32), ptr(b32), ptr(mask),
-                  int(act), float(slope), st)
-        ctx.cfg = (act, slope, bool(training), norm)
+        _lib.call("cgat_bn_act_fwd_sets", ptr(xh), ptr(y), dt, N, H * W, C, sets, ptr(mean), ptr(rstd), ptr(g32), ptr(b32),
+                  ptr(mask), int(act), float(slope), st)
+        ctx.cfg = (act, slope, bool(training), norm, sets)
         ctx.save_for_backward(xh, mean, rstd, g32, b32, mask)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
-        act, slope, training, norm = ctx.cfg
+        act, slope, training, norm, sets = ctx.cfg
         xh, mean, rstd, g32, b32, mask = ctx.saved_tensors
         N, H, W, C = xh.shape
         dyh = _nhwc(dy).to(xh.dtype)
         dx = torch.empty_like(xh)
-        dg = db = ws = None
+        dg = db = ws = ss = None
         if norm:
             dg = torch.empty(C, dtype=torch.float32, device=xh.device)
             db = torch.empty_like(dg)
-            ws = torch.empty(2 * C + 2, dtype=torch.float64, device=xh.device)
-        _lib.call("cgat_bn_act_bwd", ptr(xh), ptr(dyh), ptr(dx), _lib.dtype_tag(xh), N, H * W, C, ptr(mean), ptr(rstd), ptr(g32),
-                  ptr(b32), ptr(mask), int(act), float(slope), int(training), ptr(ws), ptr(dg), ptr(db), 0, stream(), launches=2)
-        return (dx.permute(0, 3, 1, 2), dg, db) + (None,) * 9
+            ss = torch.empty(2, sets, C, dtype=torch.float32, device=xh.device)
+            ws = torch.empty(sets * (2 * C + 2) + 2, dtype=torch.float64, device=xh.device)
+        _lib.call("cgat_bn_act_bwd_sets", ptr(xh), ptr(dyh), ptr(dx), _lib.dtype_tag(xh), N, H * W, C, sets, ptr(mean),
+                  ptr(rstd), ptr(g32), ptr(b32), ptr(mask), int(act), float(slope), int(training), ptr(ws), ptr(ss), ptr(dg),
+                  ptr(db), 0, stream(), launches=2)
+        return (dx.permute(0, 3, 1, 2), dg, db) + (None,) * 10
 
 
 class _DropoutMask:
@@ -109,6 +115,7 @@ class BatchNormAct2d(nn.Module):
         self.register_buffer("running_var", torch.ones(num_features))
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
         self._mask = _DropoutMask()
+        self.sets = 1  # statistic sets: consecutive groups of the batch normalised separately (UnetModel's vertices)
 
     def forward(self, x):
         if self.act == ACT_SIGMOID and self.dropout > 0 and self.training:
@@ -117,7 +124,7 @@ class BatchNormAct2d(nn.Module):
         if self.training and self.dropout > 0:
             mask = self._mask.draw(x.shape[0], x.shape[1], self.dropout, x.device)
         return _NormActFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, self.num_batches_tracked,
-                                self.training, self.momentum, self.eps, self.act, self.slope, mask)
+                                self.training, self.momentum, self.eps, self.act, self.slope, mask, self.sets)
 
     def extra_repr(self):
         return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}, act={self.act}, dropout={self.dropout}"
@@ -139,11 +146,11 @@ class ActDropout2d(nn.Module):
             mask = self._mask.draw(x.shape[0], x.shape[1], self.dropout, x.device)
         none = (None,) * 5
         if mask is not None and self.act == ACT_SIGMOID:
-            x = _NormActFn.apply(x, *none, False, 0.0, 0.0, ACT_NONE, 0.0, mask)
+            x = _NormActFn.apply(x, *none, False, 0.0, 0.0, ACT_NONE, 0.0, mask, 1)
             mask = None
         if mask is None and self.act == ACT_NONE:
             return x
-        return _NormActFn.apply(x, *none, False, 0.0, 0.0, self.act, self.slope, mask)
+        return _NormActFn.apply(x, *none, False, 0.0, 0.0, self.act, self.slope, mask, 1)
 
     def extra_repr(self):
         return f"act={self.act}, dropout={self.dropout}"

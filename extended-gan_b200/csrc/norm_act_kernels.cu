@@ -14,6 +14,11 @@
 // before it can apply them.  mean == NULL means "no normalisation" (activation / dropout only blocks).
 // Dropout2d zeroes whole channels of a sample: the mask is [N][C] floats, 0 or 1/(1-p), from a counter-based generator
 // (Philox4x32-10) keyed by (seed, a device-resident call counter, n*C + c): replayable from a CUDA graph.
+//
+// Statistic SETS (the *_sets entry points): the batch is `sets` equal groups of consecutive images, each normalised with ITS
+// OWN batch statistics, the running statistics updated once per set IN SET ORDER -- exactly what the reference's
+// UnetModel does when it pushes one vertex after the other through the same UNet (convolutional_gat/unet_model.py:25-26),
+// but as one launch per pass over all vertices.  mean / rstd / the backward's per-set sums are [sets][C].
 #include "common.cuh"
 #include "ew_vec.cuh"
 
@@ -65,6 +70,10 @@ struct NaArgs {
   float momentum, eps;
   int training;           // bwd apply: 1 = batch statistics took part in the forward (mean terms), 0 = constants
   int accumulate;         // bwd reduce: add into dgamma / dbeta instead of overwriting
+  int sets;               // statistic sets (>= 1): images [s * n_set, (s + 1) * n_set) share statistics; mean, rstd, sum_dz,
+  long long n_set;        //   sum_dzx, out_a, out_b are [sets][C]; sums is [sets][2C + 2] doubles + one counter word
+  float* tot_a;           // bwd reduce, optional: out_a / out_b summed over the sets ([C]; = dbeta, dgamma of the layer)
+  float* tot_b;
 };
 
 // ---- per-channel reductions: a CTA owns a slab of pixels; thread = (pixel lane, channel group) -----------------------
@@ -78,10 +87,13 @@ __global__ void __launch_bounds__(NA_THREADS) na_reduce_kernel(const NaArgs A, i
   const int cg_per_pass = groups >= NA_THREADS ? NA_THREADS : groups;
   int lanes = 1;                                      // pixel lanes per CTA: the largest power of two that fits
   while (2 * lanes * cg_per_pass <= NA_THREADS) lanes *= 2;
-  const long long P = A.n * A.hw;
+  const int set = blockIdx.y;                        // statistic set of this CTA
+  const long long P = A.n_set * A.hw;                // pixels of one set
   const long long p0 = (long long)blockIdx.x * pix_per_cta, p1 = min(P, p0 + pix_per_cta);
-  const T* x = reinterpret_cast<const T*>(A.x);
-  const T* dy = reinterpret_cast<const T*>(A.dy);
+  const T* x = reinterpret_cast<const T*>(A.x) + (long long)set * P * A.c;
+  const T* dy = reinterpret_cast<const T*>(A.dy) + (long long)set * P * A.c;
+  const int so = set * A.c;                          // this set's row of the [sets][C] statistics
+  double* sums = A.sums + (long long)set * (2 * A.c + 2);
   for (int g0 = 0; g0 < groups; g0 += cg_per_pass) {
     const int g = g0 + (int)(threadIdx.x % cg_per_pass), lane = threadIdx.x / cg_per_pass;
     float a0[V], a1[V];
@@ -92,8 +104,8 @@ __global__ void __launch_bounds__(NA_THREADS) na_reduce_kernel(const NaArgs A, i
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int ch = g * V + i;
-        mu[i] = (MODE == 1 && A.mean) ? A.mean[ch] : 0.f;
-        rs[i] = (MODE == 1 && A.mean) ? A.rstd[ch] : 1.f;
+        mu[i] = (MODE == 1 && A.mean) ? A.mean[so + ch] : 0.f;
+        rs[i] = (MODE == 1 && A.mean) ? A.rstd[so + ch] : 1.f;
         ga[i] = (MODE == 1 && A.gamma) ? A.gamma[ch] : 1.f;
         be[i] = (MODE == 1 && A.beta) ? A.beta[ch] : 0.f;
       }
@@ -106,7 +118,7 @@ __global__ void __launch_bounds__(NA_THREADS) na_reduce_kernel(const NaArgs A, i
         } else {
           float dv[V];
           na_load<T, V>(dy + p * A.c + (long long)g * V, dv);
-          const long long img = p / A.hw;
+          const long long img = (long long)set * A.n_set + p / A.hw;
 #pragma unroll
           for (int i = 0; i < V; ++i) {
             const float xh = (xv[i] - mu[i]) * rs[i];
@@ -142,16 +154,17 @@ __global__ void __launch_bounds__(NA_THREADS) na_reduce_kernel(const NaArgs A, i
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int ch = (g0 + threadIdx.x) * V + i;
-        atomicAdd(A.sums + ch, (double)s_part[0][threadIdx.x * V + i]);
-        atomicAdd(A.sums + A.c + ch, (double)s_part[1][threadIdx.x * V + i]);
+        atomicAdd(sums + ch, (double)s_part[0][threadIdx.x * V + i]);
+        atomicAdd(sums + A.c + ch, (double)s_part[1][threadIdx.x * V + i]);
       }
     }
     __syncthreads();
   }
-  // the last CTA to arrive finishes the per-channel results
+  // the last CTA of a set finishes that set's per-channel results; the last SET to finish then does what needs every set
+  // in order: the running statistics (one momentum update per set, set 0 first) / the sums over the sets
   __threadfence();
   if (threadIdx.x == 0) {
-    unsigned long long* counter = reinterpret_cast<unsigned long long*>(A.sums + 2 * A.c);
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(sums + 2 * A.c);
     s_last = atomicAdd(counter, 1ull) == (unsigned long long)gridDim.x - 1;
   }
   __syncthreads();
@@ -159,25 +172,55 @@ __global__ void __launch_bounds__(NA_THREADS) na_reduce_kernel(const NaArgs A, i
   __threadfence();
   const double M = (double)P;
   for (int ch = threadIdx.x; ch < A.c; ch += NA_THREADS) {
-    const double t0 = __ldcg(A.sums + ch), t1 = __ldcg(A.sums + A.c + ch);
+    const double t0 = __ldcg(sums + ch), t1 = __ldcg(sums + A.c + ch);
     if constexpr (MODE == 0) {
       const double mean = t0 / M;
       double var = t1 / M - mean * mean;
       var = var > 0.0 ? var : 0.0;
-      A.out_a[ch] = (float)mean;
-      A.out_b[ch] = (float)(1.0 / sqrt(var + (double)A.eps));
-      if (A.running_mean != nullptr) {
-        const double unbiased = M > 1.0 ? var * M / (M - 1.0) : var;
-        A.running_mean[ch] = (float)((1.0 - A.momentum) * (double)A.running_mean[ch] + A.momentum * mean);
-        A.running_var[ch] = (float)((1.0 - A.momentum) * (double)A.running_var[ch] + A.momentum * unbiased);
-      }
+      A.out_a[so + ch] = (float)mean;
+      A.out_b[so + ch] = (float)(1.0 / sqrt(var + (double)A.eps));
+      sums[ch] = mean;                                            // kept for the in-order running update below
+      sums[A.c + ch] = M > 1.0 ? var * M / (M - 1.0) : var;       // unbiased, as torch's running_var
     } else {
-      A.out_a[ch] = A.accumulate ? A.out_a[ch] + (float)t0 : (float)t0;
-      A.out_b[ch] = A.accumulate ? A.out_b[ch] + (float)t1 : (float)t1;
+      A.out_a[so + ch] = (float)t0;
+      A.out_b[so + ch] = (float)t1;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* gcounter = reinterpret_cast<unsigned long long*>(A.sums + (long long)A.sets * (2 * A.c + 2));
+    s_last = atomicAdd(gcounter, 1ull) == (unsigned long long)A.sets - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int ch = threadIdx.x; ch < A.c; ch += NA_THREADS) {
+    if constexpr (MODE == 0) {
+      if (A.running_mean != nullptr) {
+        double rm = (double)A.running_mean[ch], rv = (double)A.running_var[ch];
+        for (int q = 0; q < A.sets; ++q) {
+          const double* sq = A.sums + (long long)q * (2 * A.c + 2);
+          // (each update rounded to fp32 like the reference's V separate BatchNorm calls)
+          rm = (double)(float)((1.0 - A.momentum) * rm + A.momentum * __ldcg(sq + ch));
+          rv = (double)(float)((1.0 - A.momentum) * rv + A.momentum * __ldcg(sq + A.c + ch));
+        }
+        A.running_mean[ch] = (float)rm;
+        A.running_var[ch] = (float)rv;
+      }
+    } else if (A.tot_a != nullptr) {
+      double ta = 0.0, tb = 0.0;
+      for (int q = 0; q < A.sets; ++q) {
+        const double* sq = A.sums + (long long)q * (2 * A.c + 2);
+        ta += __ldcg(sq + ch);
+        tb += __ldcg(sq + A.c + ch);
+      }
+      A.tot_a[ch] = A.accumulate ? A.tot_a[ch] + (float)ta : (float)ta;
+      A.tot_b[ch] = A.accumulate ? A.tot_b[ch] + (float)tb : (float)tb;
     }
   }
   if constexpr (MODE == 0)
-    if (threadIdx.x == 0 && A.num_batches != nullptr) *A.num_batches += 1;
+    if (threadIdx.x == 0 && A.num_batches != nullptr) *A.num_batches += A.sets;
 }
 
 // ---- elementwise passes ------------------------------------------------------------------------------------------------
@@ -191,7 +234,8 @@ __global__ void __launch_bounds__(NA_THREADS) na_apply_kernel(const NaArgs A) {
   const T* x = reinterpret_cast<const T*>(A.x) + img * A.hw * A.c;
   const T* dy = reinterpret_cast<const T*>(A.dy) + img * A.hw * A.c;
   T* out = reinterpret_cast<T*>(A.out) + img * A.hw * A.c;
-  const float invM = 1.f / (float)(A.n * A.hw);
+  const float invM = 1.f / (float)(A.n_set * A.hw);
+  const int so = (int)(img / A.n_set) * A.c;              // this image's row of the [sets][C] statistics
   for (unsigned i = blockIdx.x * NA_THREADS + threadIdx.x; i < per_img; i += gridDim.x * NA_THREADS) {
     const unsigned p = i / (unsigned)groups;
     const int g = (int)(i - p * (unsigned)groups);
@@ -203,7 +247,7 @@ __global__ void __launch_bounds__(NA_THREADS) na_apply_kernel(const NaArgs A) {
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const int ch = g * V + k;
-      const float mu = A.mean ? A.mean[ch] : 0.f, rs = A.mean ? A.rstd[ch] : 1.f;
+      const float mu = A.mean ? A.mean[so + ch] : 0.f, rs = A.mean ? A.rstd[so + ch] : 1.f;
       const float ga = A.gamma ? A.gamma[ch] : 1.f, be = A.beta ? A.beta[ch] : 0.f;
       const float mk = A.mask ? A.mask[img * A.c + ch] : 1.f;
       const float xh = (xv[k] - mu) * rs;
@@ -212,7 +256,7 @@ __global__ void __launch_bounds__(NA_THREADS) na_apply_kernel(const NaArgs A) {
         ov[k] = na_act(z, A.act, A.slope) * mk;
       } else {
         const float dz = dv[k] * na_act_grad(z, A.act, A.slope) * mk;
-        if (A.training && A.mean) ov[k] = ga * rs * (dz - A.sum_dz[ch] * invM - xh * A.sum_dzx[ch] * invM);
+        if (A.training && A.mean) ov[k] = ga * rs * (dz - A.sum_dz[so + ch] * invM - xh * A.sum_dzx[so + ch] * invM);
         else ov[k] = ga * rs * dz;
       }
     }
@@ -267,16 +311,17 @@ static int na_check(const void* x, int dtype, long long n, long long hw, int c) 
 static int na_vec(int dtype, int c, const void* a, const void* b, const void* o) { return ew_vec(dtype, c, a, b, o); }
 template <int MODE>
 static int na_launch_reduce(const NaArgs& A, int dtype, cudaStream_t st) {
-  const long long P = A.n * A.hw;
-  // at least 64 pixels per CTA, at most two CTAs per SM: every CTA ends with 2C same-address fp64 atomics, and a thousand
-  // CTAs queueing on each address cost more than the reduction itself
+  const long long P = A.n_set * A.hw;
+  // at least 64 pixels per CTA, at most two CTAs per SM (over all sets): every CTA ends with 2C same-address fp64 atomics,
+  // and a thousand CTAs queueing on each address cost more than the reduction itself
   long long ctas = (P + 63) / 64;
-  if (ctas > 148 * 2) ctas = 148 * 2;
+  const long long cap = (148 * 2 + A.sets - 1) / A.sets;
+  if (ctas > cap) ctas = cap;
   const int ppc = (int)((P + ctas - 1) / ctas);
   ctas = (P + ppc - 1) / ppc;
   const int v = na_vec(dtype, A.c, A.x, A.dy, nullptr);
   cudaError_t e;
-#define NA_RED(T, V) e = launch_pdl(na_reduce_kernel<T, V, MODE>, dim3((unsigned)ctas), dim3(NA_THREADS), 0, st, A, ppc)
+#define NA_RED(T, V) e = launch_pdl(na_reduce_kernel<T, V, MODE>, dim3((unsigned)ctas, (unsigned)A.sets), dim3(NA_THREADS), 0, st, A, ppc)
   if (dtype == CGAT_F32) { if (v == 4) NA_RED(float, 4); else NA_RED(float, 1); }
   else { if (v == 8) NA_RED(__nv_bfloat16, 8); else NA_RED(__nv_bfloat16, 1); }
 #undef NA_RED
@@ -304,33 +349,82 @@ static int na_launch_apply(const NaArgs& A, int dtype, cudaStream_t st) {
 
 using namespace cgat;
 
-extern "C" int64_t cgat_bn_workspace_bytes(int32_t c) { return c < 1 ? 0 : (int64_t)(2 * c + 2) * 8; }
+extern "C" int64_t cgat_bn_workspace_bytes_sets(int32_t c, int32_t sets) {
+  return c < 1 || sets < 1 ? 0 : (int64_t)sets * (2 * c + 2) * 8 + 16;
+}
+extern "C" int64_t cgat_bn_workspace_bytes(int32_t c) { return cgat_bn_workspace_bytes_sets(c, 1); }
 
-extern "C" int cgat_bn_stats(const void* x, int32_t dtype, int64_t n, int64_t hw, int32_t c, void* workspace, float* mean,
-                             float* rstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                             float momentum, float eps, void* stream) {
+static int na_sets_check(int64_t n, int32_t sets) {
+  if (sets < 1 || sets > 65535 || n % sets) return fail(CGAT_EINVAL, "statistic sets: %d sets do not divide %lld images", sets, (long long)n);
+  return 0;
+}
+
+extern "C" int cgat_bn_stats_sets(const void* x, int32_t dtype, int64_t n, int64_t hw, int32_t c, int32_t sets, void* workspace,
+                                  float* mean, float* rstd, float* running_mean, float* running_var,
+                                  int64_t* num_batches_tracked, float momentum, float eps, void* stream) {
   if (int rc = na_check(x, dtype, n, hw, c)) return rc;
+  if (int rc = na_sets_check(n, sets)) return rc;
   if (!workspace || !mean || !rstd) return fail(CGAT_EINVAL, "null argument");
   if ((running_mean == nullptr) != (running_var == nullptr)) return fail(CGAT_EINVAL, "running_mean and running_var go together");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)cgat_bn_workspace_bytes(c), st);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)cgat_bn_workspace_bytes_sets(c, sets), st);
   if (e != cudaSuccess) return fail((int)e, "bn workspace memset: %s", cudaGetErrorString(e));
   NaArgs A{};
   A.x = x; A.n = n; A.hw = hw; A.c = c; A.sums = (double*)workspace; A.out_a = mean; A.out_b = rstd;
   A.running_mean = running_mean; A.running_var = running_var; A.num_batches = (long long*)num_batches_tracked;
-  A.momentum = momentum; A.eps = eps;
+  A.momentum = momentum; A.eps = eps; A.sets = sets; A.n_set = n / sets;
   return na_launch_reduce<0>(A, dtype, st);
+}
+
+extern "C" int cgat_bn_stats(const void* x, int32_t dtype, int64_t n, int64_t hw, int32_t c, void* workspace, float* mean,
+                             float* rstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                             float momentum, float eps, void* stream) {
+  return cgat_bn_stats_sets(x, dtype, n, hw, c, 1, workspace, mean, rstd, running_mean, running_var, num_batches_tracked,
+                            momentum, eps, stream);
+}
+
+extern "C" int cgat_bn_act_fwd_sets(const void* x, void* y, int32_t dtype, int64_t n, int64_t hw, int32_t c, int32_t sets,
+                                    const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                    const float* mask, int32_t act, float slope, void* stream) {
+  if (int rc = na_check(x, dtype, n, hw, c)) return rc;
+  if (int rc = na_sets_check(n, sets)) return rc;
+  if (!y || (mean != nullptr && rstd == nullptr)) return fail(CGAT_EINVAL, "null argument");
+  NaArgs A{};
+  A.x = x; A.out = y; A.n = n; A.hw = hw; A.c = c; A.mean = mean; A.rstd = rstd; A.gamma = gamma; A.beta = beta; A.mask = mask;
+  A.act = act; A.slope = slope; A.sets = sets; A.n_set = n / sets;
+  return na_launch_apply<0>(A, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int cgat_bn_act_fwd(const void* x, void* y, int32_t dtype, int64_t n, int64_t hw, int32_t c, const float* mean,
                                const float* rstd, const float* gamma, const float* beta, const float* mask, int32_t act,
                                float slope, void* stream) {
+  return cgat_bn_act_fwd_sets(x, y, dtype, n, hw, c, 1, mean, rstd, gamma, beta, mask, act, slope, stream);
+}
+
+extern "C" int cgat_bn_act_bwd_sets(const void* x, const void* dy, void* dx, int32_t dtype, int64_t n, int64_t hw, int32_t c,
+                                    int32_t sets, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                    const float* mask, int32_t act, float slope, int32_t training, void* workspace,
+                                    float* set_sums, float* dgamma, float* dbeta, int32_t accumulate, void* stream) {
   if (int rc = na_check(x, dtype, n, hw, c)) return rc;
-  if (!y || (mean != nullptr && rstd == nullptr)) return fail(CGAT_EINVAL, "null argument");
+  if (int rc = na_sets_check(n, sets)) return rc;
+  if (!dy || !dx || (mean != nullptr && rstd == nullptr)) return fail(CGAT_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
   NaArgs A{};
-  A.x = x; A.out = y; A.n = n; A.hw = hw; A.c = c; A.mean = mean; A.rstd = rstd; A.gamma = gamma; A.beta = beta; A.mask = mask;
-  A.act = act; A.slope = slope;
-  return na_launch_apply<0>(A, dtype, (cudaStream_t)stream);
+  A.x = x; A.dy = dy; A.out = dx; A.n = n; A.hw = hw; A.c = c; A.mean = mean; A.rstd = rstd; A.gamma = gamma; A.beta = beta;
+  A.mask = mask; A.act = act; A.slope = slope; A.training = training; A.sets = sets; A.n_set = n / sets;
+  const bool need_sums = dgamma != nullptr || (training && mean != nullptr);
+  if (need_sums) {
+    if (!workspace || !set_sums || !dgamma || !dbeta)
+      return fail(CGAT_EINVAL, "the reduction needs workspace, set_sums [2][sets][C], dgamma and dbeta");
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)cgat_bn_workspace_bytes_sets(c, sets), st);
+    if (e != cudaSuccess) return fail((int)e, "bn workspace memset: %s", cudaGetErrorString(e));
+    A.sums = (double*)workspace;
+    A.out_a = set_sums; A.out_b = set_sums + (size_t)sets * c;  // per-set sum dz | sum dz * xhat (the apply pass reads them)
+    A.tot_a = dbeta; A.tot_b = dgamma; A.accumulate = accumulate;
+    if (int rc = na_launch_reduce<1>(A, dtype, st)) return rc;
+  }
+  A.sum_dz = set_sums; A.sum_dzx = set_sums ? set_sums + (size_t)sets * c : nullptr;
+  return na_launch_apply<1>(A, dtype, st);
 }
 
 extern "C" int cgat_bn_act_bwd(const void* x, const void* dy, void* dx, int32_t dtype, int64_t n, int64_t hw, int32_t c,
@@ -342,7 +436,7 @@ extern "C" int cgat_bn_act_bwd(const void* x, const void* dy, void* dx, int32_t 
   cudaStream_t st = (cudaStream_t)stream;
   NaArgs A{};
   A.x = x; A.dy = dy; A.out = dx; A.n = n; A.hw = hw; A.c = c; A.mean = mean; A.rstd = rstd; A.gamma = gamma; A.beta = beta;
-  A.mask = mask; A.act = act; A.slope = slope; A.training = training;
+  A.mask = mask; A.act = act; A.slope = slope; A.training = training; A.sets = 1; A.n_set = n;
   const bool need_sums = dgamma != nullptr || (training && mean != nullptr);
   if (need_sums) {
     if (!workspace || !dgamma || !dbeta) return fail(CGAT_EINVAL, "the reduction needs workspace, dgamma and dbeta");

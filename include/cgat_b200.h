@@ -320,6 +320,23 @@ int cgat_bn_act_bwd(const void* x, const void* dy, void* dx, int32_t dtype, int6
                     const float* mean, const float* rstd, const float* gamma, const float* beta, const float* mask,
                     int32_t act, float slope, int32_t training, void* workspace, float* dgamma, float* dbeta,
                     int32_t accumulate, void* stream);
+/* The same three passes over `sets` statistic sets: images [s*n/sets, (s+1)*n/sets) are normalised with THEIR OWN batch
+ * statistics and the running statistics take one momentum update per set, set 0 first -- the reference's UnetModel
+ * pushing vertex after vertex through one shared UNet (convolutional_gat/unet_model.py:25-26), as one launch per pass.
+ * mean, rstd [sets][c]; workspace cgat_bn_workspace_bytes_sets(c, sets); num_batches_tracked += sets; backward:
+ * set_sums [2][sets][c] receives the per-set sum dz | sum dz*xhat (read by the apply pass), dgamma / dbeta [c] their
+ * totals over the sets (added to when accumulate != 0).                                                              */
+int64_t cgat_bn_workspace_bytes_sets(int32_t c, int32_t sets);
+int cgat_bn_stats_sets(const void* x, int32_t dtype, int64_t n, int64_t hw, int32_t c, int32_t sets, void* workspace,
+                       float* mean, float* rstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                       float momentum, float eps, void* stream);
+int cgat_bn_act_fwd_sets(const void* x, void* y, int32_t dtype, int64_t n, int64_t hw, int32_t c, int32_t sets,
+                         const float* mean, const float* rstd, const float* gamma, const float* beta, const float* mask,
+                         int32_t act, float slope, void* stream);
+int cgat_bn_act_bwd_sets(const void* x, const void* dy, void* dx, int32_t dtype, int64_t n, int64_t hw, int32_t c,
+                         int32_t sets, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         const float* mask, int32_t act, float slope, int32_t training, void* workspace, float* set_sums,
+                         float* dgamma, float* dbeta, int32_t accumulate, void* stream);
 int cgat_dropout2d_mask(float* mask, int64_t n, float p, uint64_t seed, uint64_t* counter, void* stream);
 
 /* f2  the non-conv ops of the SmaAt-UNet applied per vertex by convolutional_gat/unet_model.py:20-29 (public

@@ -108,6 +108,64 @@ def test_unet_model_per_vertex_loop_and_grads():
         close(p.grad, pr[k].grad, rtol=1e-2, atol=1e-3 * max(1.0, pr[k].grad.abs().max().item()), msg=f"d{k}")
 
 
+def test_unet_model_batched_vertices_equal_the_per_vertex_loop():
+    """UnetModel runs its V per-vertex passes (unet_model.py:25-26) as one batched pass with per-vertex BatchNorm statistic
+    sets.  Train-mode gradients of this 40-layer fp32 net carry ~0.5 % of rounding noise (ReLU / arg-max decisions next
+    to a tie flip with the last bit of a batch mean), so the literal loop and the batched pass are both measured against
+    the fp64 oracle: the batched pass must be as close to it as the loop is, and the BatchNorm buffers must agree."""
+    import copy
+
+    from convolutional_gat.unet_model import UnetModel
+
+    torch.manual_seed(5)
+    a = UnetModel(image_width=64, image_height=64, n_vertices=3, attention_type="unet").to(DEV).train()
+    ref = spec.SpecSmaAtUNet(4, 4)
+    ref.load_state_dict({k: v.cpu() for k, v in a.unet.state_dict().items()})
+    ref = ref.double().train()
+    b = copy.deepcopy(a)
+    b.batched = False
+    x = torch.rand(2, 64, 64, 4, 3, device=DEV)
+    g = torch.rand(2, 64, 64, 4, 3, device=DEV) - 0.5
+    xr = x.cpu().double().requires_grad_()
+    out_r = spec.unet_model_forward(ref, xr)
+    out_r.backward(g.cpu().double())
+    res = []
+    for m in (a, b):
+        xi = x.clone().requires_grad_()
+        out = m(xi)
+        out.backward(g)
+        res.append((out.detach(), xi.grad))
+    torch.cuda.synchronize()
+
+    def err(u, v):
+        return ((u.cpu().double() - v).abs().max() / v.abs().max().clamp_min(1e-30)).item()
+
+    e_out = [err(r[0], out_r.detach()) for r in res]
+    e_dx = [err(r[1], xr.grad) for r in res]
+    assert e_out[0] < 1e-4 and e_out[0] <= 2 * e_out[1] + 1e-6, e_out
+    assert e_dx[0] < 2e-2 and e_dx[0] <= 2 * e_dx[1] + 1e-5, e_dx
+    pr, pb = dict(ref.named_parameters()), dict(b.unet.named_parameters())
+    scale = max(p.grad.abs().max().item() for p in pr.values())
+    tot_a = tot_b = 0.0
+    for k, p in a.unet.named_parameters():
+        gr = pr[k].grad
+        if gr.abs().max().item() < 1e-6 * scale:  # biases in front of a BatchNorm: the true gradient is zero
+            continue
+        # absolute noise of a cancelling sum (e.g. the single dgamma of a CBAM spatial BatchNorm2d(1): +-0.05 in either
+        # path, whatever the value) is bounded against the model's gradient scale; the paths are compared in aggregate
+        da = (p.grad.cpu().double() - gr).abs().max().item()
+        db = (pb[k].grad.cpu().double() - gr).abs().max().item()
+        assert da <= 3e-2 * gr.abs().max().item() + 5e-3 * scale, (k, da, db, gr.abs().max().item(), scale)
+        tot_a += da / (gr.abs().max().item() + 1e-2 * scale)
+        tot_b += db / (gr.abs().max().item() + 1e-2 * scale)
+    assert tot_a <= 1.5 * tot_b + 1e-3, (tot_a, tot_b)
+    sb, sr = dict(b.named_buffers()), dict(ref.named_buffers())
+    for k, v in a.named_buffers():
+        close(v.float(), sb[k].float(), rtol=1e-4, atol=1e-6, msg=k)
+        close(v.float(), sr[k[len("unet."):]].float(), rtol=1e-4, atol=1e-6, msg="oracle " + k)
+    assert int(a.unet.inc.double_conv[1].num_batches_tracked) == 3
+
+
 def test_model_registry_and_train_signature():
     """train.py:198-205: model_classes[model_type](image_width=, image_height=, n_vertices=, attention_type=, mapping_type=)."""
     from convolutional_gat.utils import model_classes

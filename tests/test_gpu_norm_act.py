@@ -106,3 +106,47 @@ def test_dropout_before_sigmoid_keeps_the_block_order():
     want = torch.sigmoid(2.0 * x.detach())  # kept channels: sigmoid(x / (1 - p))
     assert torch.allclose(y.detach()[~dropped], want[~dropped], rtol=1e-5, atol=1e-6)
     assert (x.grad[dropped] == 0).all()
+
+
+@pytest.mark.parametrize("C,shape,sets", [(64, (6, 9, 7), 3), (8, (8, 16, 16), 8), (1, (4, 8, 8), 2), (512, (4, 4, 4), 2)])
+@pytest.mark.parametrize("act", [1, 3])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_batchnorm_statistic_sets_match_sequential_torch_calls(C, shape, sets, act, dtype):
+    """``sets`` groups of the batch through ONE launch per pass == the reference's UnetModel calling the same BatchNorm2d
+    once per vertex (unet_model.py:25-26): per-group statistics, `sets` running-stat updates in group order, parameter
+    gradients summed over the groups."""
+    from cgat.norm_act import BatchNormAct2d
+
+    N, H, W = shape
+    torch.manual_seed(C + act + sets)
+    ref = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.uniform_(-0.5, 0.5)
+        ref.running_mean.uniform_(-0.2, 0.2)
+        ref.running_var.uniform_(0.5, 1.5)
+    ours = BatchNormAct2d(C, act=act, slope=0.2)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(DEV).train()
+    ours.sets = sets
+    ref.train()
+    x = (torch.randn(N, C, H, W) * 1.5 + 0.3).to(dtype).float()
+    x = x + torch.arange(sets).repeat_interleave(N // sets).view(N, 1, 1, 1) * 0.7  # the groups differ in mean
+    x = x.to(dtype).float()
+    g = torch.randn(N, C, H, W).to(dtype).float()
+    xr = x.clone().requires_grad_()
+    nb = N // sets
+    yr = torch.cat([_ref_act(ref(xr[i * nb:(i + 1) * nb]), act) for i in range(sets)])
+    yr.backward(g)
+    xo = x.to(DEV).to(dtype).requires_grad_()
+    yo = ours(xo)
+    yo.backward(g.to(DEV).to(dtype))
+    torch.cuda.synchronize()
+    lo = dtype == torch.bfloat16
+    close(yo.float(), yr.detach(), rtol=2e-2 if lo else 1e-4, atol=2e-2 if lo else 1e-5, msg="y")
+    close(xo.grad.float(), xr.grad, rtol=2e-2 if lo else 1e-4, atol=3e-2 if lo else 2e-5, msg="dx")
+    close(ours.weight.grad, ref.weight.grad, rtol=1e-4, atol=1e-4 * N * H * W if lo else 1e-4, msg="dgamma")
+    close(ours.bias.grad, ref.bias.grad, rtol=1e-4, atol=1e-4 * N * H * W if lo else 1e-4, msg="dbeta")
+    for k, v in ours.state_dict().items():
+        close(v, ref.state_dict()[k], rtol=1e-5, atol=1e-6, msg=k)
+    assert int(ours.num_batches_tracked) == sets

@@ -125,8 +125,8 @@ def test_smaat_unet_train_and_eval_passes_use_no_torch_glue():
     prof = _lib.profile_stop()
     for name in ("cgat_maxpool2_fwd", "cgat_maxpool2_bwd", "cgat_upcat_fwd", "cgat_upcat_bwd", "cgat_pool_hw", "cgat_dot_hw",
                  "cgat_cbam_mlp_fwd", "cgat_cbam_mlp_bwd", "cgat_gate_channels_fwd", "cgat_gate_channels_bwd",
-                 "cgat_chan_pool_fwd", "cgat_chan_pool_bwd", "cgat_gate_pixels", "cgat_chan_dot", "cgat_bn_stats",
-                 "cgat_bn_act_fwd", "cgat_bn_act_bwd"):
+                 "cgat_chan_pool_fwd", "cgat_chan_pool_bwd", "cgat_gate_pixels", "cgat_chan_dot", "cgat_bn_stats_sets",
+                 "cgat_bn_act_fwd_sets", "cgat_bn_act_bwd_sets"):
         assert name in prof, (name, sorted(prof))
     close(out_o, out_r.detach(), rtol=1e-3, atol=1e-4, msg="SmaAt-UNet train-mode out")
     sr = ref.state_dict()
