@@ -121,6 +121,7 @@ SIGNATURES = {
     "cgat_val_metrics": [_P, _P, _I64, _F, _F, _F, _I, _P, _P],
     "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
     "cgat_loader_gather_planar": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],
+    "cgat_s2d_pad": [_P, _P, _I, _I64, _I, _I, _I, _I, _P],
     "cgat_loader_gather_f32": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "cgat_records_to_planar": [_P, _P, _I64, _I, _I, _I, _P],
     "cgat_comm_available": [],

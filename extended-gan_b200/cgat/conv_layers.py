@@ -16,6 +16,28 @@ from . import _lib
 from .functional import IMPL_AUTO, conv2d_nhwc
 
 
+class _S2DPad(torch.autograd.Function):
+    """``x [N, H, W, C]`` -> zero-padded by one pixel and regrouped in 2x2 blocks ``[N, H/2+1, W/2+1, 4C]``; the backward is
+    the inverse gather (csrc/layout_kernels.cu)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        xs = torch.empty(N, H // 2 + 1, W // 2 + 1, 4 * C, device=x.device, dtype=x.dtype)
+        _lib.call("cgat_s2d_pad", _lib.ptr(x), _lib.ptr(xs), _lib.dtype_tag(x), N, H, W, C, 0, _lib.stream())
+        ctx.shape = (N, H, W, C)
+        return xs
+
+    @staticmethod
+    def backward(ctx, dxs):
+        N, H, W, C = ctx.shape
+        dxs = dxs.contiguous()
+        dx = torch.empty(N, H, W, C, device=dxs.device, dtype=dxs.dtype)
+        _lib.call("cgat_s2d_pad", _lib.ptr(dxs), _lib.ptr(dx), _lib.dtype_tag(dxs), N, H, W, C, 1, _lib.stream())
+        return dx
+
+
 def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
@@ -67,8 +89,7 @@ class Conv2d(nn.Module):
         d = _lib.ConvDesc(N, hs, ws, 4 * C, self.out_channels, 2, 2, 1, 0, 0, hs - 1, ws - 1, _lib.BF16, self.act, 1)
         if not _lib.lib().cgat_conv_tc_supported(ctypes.byref(d), 0):
             return None
-        xp = torch.nn.functional.pad(x_nhwc, (0, 0, 1, 1, 1, 1))  # [N, H+2, W+2, C]
-        xs = xp.view(N, hs, 2, ws, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, hs, ws, 4 * C)  # channel = (a, b, c)
+        xs = _S2DPad.apply(x_nhwc)  # [N, hs, ws, 4C], channel = (a, b, c): pad + regroup in one pass (cgat_s2d_pad)
         # weight[cout, c, 2r+a, 2s+b] -> [cout, r, s, (a, b, c)]
         w = self.weight.view(self.out_channels, C, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(self.out_channels, 2, 2, 4 * C)
         return conv2d_nhwc(xs, w, self.bias, stride=1, pad=(0, 0, 0, 0), act=self.act, impl=IMPL_AUTO)

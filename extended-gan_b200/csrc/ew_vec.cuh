@@ -22,6 +22,32 @@ __device__ __forceinline__ void na_load(const T* p, float (&v)[V]) {
     }
   }
 }
+// the same access split in two: the raw 16-byte (or scalar) load first, the conversion later -- lets a loop keep several
+// loads in flight per thread at 4 registers each
+template <typename T, int V> struct NaRaw { uint4 q; };
+template <typename T> struct NaRaw<T, 1> { T q; };
+template <typename T, int V>
+__device__ __forceinline__ NaRaw<T, V> na_load_raw(const T* p) {
+  NaRaw<T, V> r;
+  if constexpr (V == 1) r.q = p[0];
+  else r.q = *reinterpret_cast<const uint4*>(p);
+  return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void na_unpack(const NaRaw<T, V>& r, float (&v)[V]) {
+  if constexpr (V == 1) {
+    v[0] = DT<T>::to_f(r.q);
+  } else if constexpr (sizeof(T) == 4) {
+    v[0] = __uint_as_float(r.q.x); v[1] = __uint_as_float(r.q.y); v[2] = __uint_as_float(r.q.z); v[3] = __uint_as_float(r.q.w);
+  } else {
+    const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
 template <typename T, int V>
 __device__ __forceinline__ void na_store(T* p, const float (&v)[V]) {
   if constexpr (V == 1) {

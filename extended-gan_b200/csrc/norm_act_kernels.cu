@@ -25,6 +25,7 @@
 namespace cgat {
 
 constexpr int NA_THREADS = 256;
+constexpr int NA_U = 4;  // pixels a reduction thread loads per trip
 
 __device__ __forceinline__ float na_act(float z, int act, float slope) {
   switch (act) {
@@ -109,24 +110,40 @@ __global__ void __launch_bounds__(NA_THREADS) na_reduce_kernel(const NaArgs A, i
         ga[i] = (MODE == 1 && A.gamma) ? A.gamma[ch] : 1.f;
         be[i] = (MODE == 1 && A.beta) ? A.beta[ch] : 0.f;
       }
-      for (long long p = p0 + lane; p < p1; p += lanes) {
-        float xv[V];
-        na_load<T, V>(x + p * A.c + (long long)g * V, xv);
-        if constexpr (MODE == 0) {
+      // NA_U pixels per lane and trip, every load issued before the first use (a thread otherwise has ONE 16-byte
+      // request in flight and the pass runs at DRAM latency: 31 us for the 1 MB tensor of a 4x4x512 map)
+      for (long long pb = p0 + lane; pb < p1; pb += (long long)lanes * NA_U) {
+        NaRaw<T, V> rx[NA_U], rd[NA_U];
 #pragma unroll
-          for (int i = 0; i < V; ++i) { a0[i] += xv[i]; a1[i] = fmaf(xv[i], xv[i], a1[i]); }
-        } else {
-          float dv[V];
-          na_load<T, V>(dy + p * A.c + (long long)g * V, dv);
-          const long long img = (long long)set * A.n_set + p / A.hw;
+        for (int q = 0; q < NA_U; ++q) {
+          const long long p = pb + (long long)q * lanes;
+          if (p < p1) {
+            rx[q] = na_load_raw<T, V>(x + p * A.c + (long long)g * V);
+            if constexpr (MODE == 1) rd[q] = na_load_raw<T, V>(dy + p * A.c + (long long)g * V);
+          }
+        }
 #pragma unroll
-          for (int i = 0; i < V; ++i) {
-            const float xh = (xv[i] - mu[i]) * rs[i];
-            const float z = fmaf(xh, ga[i], be[i]);
-            float dz = dv[i] * na_act_grad(z, A.act, A.slope);
-            if (A.mask) dz *= A.mask[img * A.c + g * V + i];
-            a0[i] += dz;
-            a1[i] = fmaf(dz, xh, a1[i]);
+        for (int q = 0; q < NA_U; ++q) {
+          const long long p = pb + (long long)q * lanes;
+          if (p >= p1) continue;
+          float xv[V];
+          na_unpack<T, V>(rx[q], xv);
+          if constexpr (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { a0[i] += xv[i]; a1[i] = fmaf(xv[i], xv[i], a1[i]); }
+          } else {
+            float dv[V];
+            na_unpack<T, V>(rd[q], dv);
+            const long long img = (long long)set * A.n_set + p / A.hw;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              const float xh = (xv[i] - mu[i]) * rs[i];
+              const float z = fmaf(xh, ga[i], be[i]);
+              float dz = dv[i] * na_act_grad(z, A.act, A.slope);
+              if (A.mask) dz *= A.mask[img * A.c + g * V + i];
+              a0[i] += dz;
+              a1[i] = fmaf(dz, xh, a1[i]);
+            }
           }
         }
       }
@@ -312,14 +329,18 @@ static int na_vec(int dtype, int c, const void* a, const void* b, const void* o)
 template <int MODE>
 static int na_launch_reduce(const NaArgs& A, int dtype, cudaStream_t st) {
   const long long P = A.n_set * A.hw;
-  // at least 64 pixels per CTA, at most two CTAs per SM (over all sets): every CTA ends with 2C same-address fp64 atomics,
+  // at least one unrolled trip per pixel lane and CTA, at most two CTAs per SM (over all sets): every CTA ends with 2C same-address fp64 atomics,
   // and a thousand CTAs queueing on each address cost more than the reduction itself
-  long long ctas = (P + 63) / 64;
+  const int v = na_vec(dtype, A.c, A.x, A.dy, nullptr);
+  const int cg = A.c / v >= NA_THREADS ? NA_THREADS : A.c / v;  // channel groups per pass (as in the kernel)
+  int lanes = 1;
+  while (2 * lanes * cg <= NA_THREADS) lanes *= 2;
+  const int ppc_min = lanes * NA_U;                             // one unrolled trip per lane
+  long long ctas = (P + ppc_min - 1) / ppc_min;
   const long long cap = (148 * 2 + A.sets - 1) / A.sets;
   if (ctas > cap) ctas = cap;
   const int ppc = (int)((P + ctas - 1) / ctas);
   ctas = (P + ppc - 1) / ppc;
-  const int v = na_vec(dtype, A.c, A.x, A.dy, nullptr);
   cudaError_t e;
 #define NA_RED(T, V) e = launch_pdl(na_reduce_kernel<T, V, MODE>, dim3((unsigned)ctas, (unsigned)A.sets), dim3(NA_THREADS), 0, st, A, ppc)
   if (dtype == CGAT_F32) { if (v == 4) NA_RED(float, 4); else NA_RED(float, 1); }

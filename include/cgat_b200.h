@@ -387,6 +387,13 @@ int cgat_chan_pool_bwd(const void* dpooled, const int32_t* argmax, void* dx, int
                        void* stream);
 int cgat_chan_dot(const void* x, const void* dy, void* out, int32_t dtype, int64_t npix, int32_t c, void* stream);
 
+/* a11  zero-pad (1 pixel) + 2x2 space-to-depth of an NHWC activation in one pass -- the regrouping that serves the DCGAN
+ * discriminators' k=4, stride-2, padding-1 convs (dcgan/model.py:150-165) as stride-1 2x2 convs over 4c channels:
+ *   inverse == 0:  src x [n][h][w][c] -> dst xs [n][h/2+1][w/2+1][2][2][c],  xs[n][i][j][a][b][:] = x[n][2i+a-1][2j+b-1][:] or 0
+ *   inverse != 0:  src dxs (that layout) -> dst dx [n][h][w][c]  (the exact inverse gather = the backward).  h, w even.   */
+int cgat_s2d_pad(const void* src, void* dst, int32_t dtype, int64_t n, int32_t h, int32_t w, int32_t c, int32_t inverse,
+                 void* stream);
+
 /* f3  the KNMI loader's windowing + normalisation + layout change on the device, replacing
  * convolutional_gat/data_loaders/kmni_data_loader.py:72-127 (__segmentify and the permute of __next__):
  *   x[s, h, w, t, v] = pow(frames[start[s] + t, v, h, w] / normalizing_max, power)            t < steps
