@@ -29,6 +29,8 @@ int conv_dw3x3_served(const cgat_conv_desc* d);
 int conv_dw3x3_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, float*, const float*, cudaStream_t);
 int conv_wgrad_small_served(const cgat_conv_desc* d);
 int conv_wgrad_small_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
+int conv_small_served(const cgat_conv_desc* d, int which);
+int conv_small_launch(int which, const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int conv_gemm_served(const cgat_conv_desc* d);
 int conv_gemm_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, const float*, cudaStream_t);
 }  // namespace cgat
@@ -74,6 +76,7 @@ extern "C" int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const v
   if (impl == 0 && conv_dw3x3_served(d)) return conv_dw3x3_launch(0, d, x, w, y, nullptr, bias, (cudaStream_t)stream);
   if (impl == 0 && conv_is_fullwindow(d)) return conv_fullwindow_fprop_launch(d, x, w, bias, y, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
+  if (impl == 0 && conv_small_served(d, 0)) return conv_small_launch(0, d, x, w, bias, y, (cudaStream_t)stream);
   if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(0, d, x, w, y, bias, (cudaStream_t)stream);
   if (impl == 0) return conv_fprop_direct_launch(d, x, w, bias, y, (cudaStream_t)stream);
   if (use_big(d, 0)) return conv_big_fprop_launch(d, x, w, bias, y, (cudaStream_t)stream);
@@ -87,6 +90,7 @@ extern "C" int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const 
   if (!dy || !w || !dx) return fail(CGAT_EINVAL, "null dy/w/dx");
   if (impl == 0 && conv_dw3x3_served(d)) return conv_dw3x3_launch(1, d, dy, w, dx, nullptr, nullptr, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) return conv_pointwise_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
+  if (impl == 0 && conv_small_served(d, 1)) return conv_small_launch(1, d, dy, w, nullptr, dx, (cudaStream_t)stream);
   if (impl == 0 && conv_gemm_served(d)) return conv_gemm_launch(1, d, dy, w, dx, nullptr, (cudaStream_t)stream);
   if (impl == 0) return conv_dgrad_direct_launch(d, dy, w, dx, (cudaStream_t)stream);
   if (use_big(d, 1)) return conv_big_dgrad_launch(d, dy, w, dx, workspace, (cudaStream_t)stream);

@@ -316,8 +316,10 @@ __device__ __forceinline__ void pool_hw_body(const PoolArgs& A) {
     }
     __syncthreads();
   }
-  __threadfence();
-  if (threadIdx.x == 0) s_last = atomicAdd(A.counter + img, 1u) == (unsigned)A.chunks - 1;
+  if (threadIdx.x == 0) {  // one cumulative fence behind the loop's closing __syncthreads, by the signalling thread
+    __threadfence();
+    s_last = atomicAdd(A.counter + img, 1u) == (unsigned)A.chunks - 1;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
