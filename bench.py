@@ -180,11 +180,19 @@ def conv_tensor_roofline(pk, batch=64, reps=10):
             ms = a.elapsed_time(b) / reps
             tf = flops / (ms * 1e-3) / 1e12
             out.append({"shape": name, "n": n, "dir": which, "ms": ms, "tflops": tf, "frac": tf / pk["bf16_tflops"]})
-    best = out[0]
+    # headline entry: the best REFERENCE shape (the synthetic 3x3 256->256 conv, which no reference model contains, shows
+    # what the kernel reaches when the problem fills the machine and is reported beside it)
+    ref = [o for o in out if not o["shape"].startswith("dense 3x3")]
+    best = max(ref, key=lambda o: o["tflops"])
+    synth = out[0]
     return {"kernel": "conv_big_fprop_kernel", "bound": "tensor", "achieved": best["tflops"],
-            "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": best["frac"], "shape": best["shape"],
+            "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": best["frac"], "shape": best["shape"], "dir": best["dir"],
             "frac_of_sustained_peak": best["tflops"] / pk["bf16_tflops_sustained"],
             "peak_source": pk["source"] + " (burst figure: the kernels are timed alone)", "timing": f"{reps} launches replayed from one CUDA graph, CUDA events",
+            "synthetic_full_machine_shape": {"shape": synth["shape"], "dir": synth["dir"], "tflops": synth["tflops"],
+                                             "frac": synth["frac"]},
+            "note": "the reference's dense convs are small problems at its batch (DCGAN conv3 / conv4: 32 / 16 output tiles for "
+                    "148 SMs), bound by occupancy of the machine, not by the tensor pipe of the SMs that work",
             "all": out}
 
 
@@ -213,6 +221,20 @@ def ours_rows(dev, batch=64):
         sec = time_fn(lambda: step(x, y), dev, 2, 10)
         rows[f"R4_dcgan_adversarial_step_{tag}"] = {"samples_per_s": batch / sec, "ms_per_step": sec * 1e3, "batch": batch,
                                                     "dtype": tag, "cuda_graph": True}
+    # BASELINE config 4 (stress): UnetModel [2,128,128,4,8], one full train step from TrainStep's CUDA graph -- the V
+    # per-vertex UNet passes as one batched pass with per-vertex BatchNorm statistic sets; fp32 master parameters
+    from cgat.train_step import TrainStep
+    from convolutional_gat.unet_model import UnetModel
+    for dtype, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16_activations")):
+        torch.manual_seed(SEED)
+        m = UnetModel(image_width=128, image_height=128, n_vertices=8, attention_type="unet").to(dev)
+        xu = torch.rand(2, 128, 128, 4, 8, device=dev).to(dtype)
+        yu = torch.rand(2, 128, 128, 4, 8, device=dev).to(dtype)
+        ts = TrainStep(m, xu, yu, lr=1e-3, use_graph=True)
+        sec = time_fn(lambda: ts.run(), dev, 2, 10)
+        rows[f"config4_unet_model_train_step_{tag}"] = {"samples_per_s": 2 / sec, "ms_per_step": sec * 1e3, "batch": 2,
+                                                        "dtype": tag, "cuda_graph": True}
+        del ts, m
     return rows
 
 
