@@ -309,6 +309,11 @@ def run_ours(args):
     ts = TrainStep(model, x, y, lr=1e-3, use_graph=True)
     ts.sync_params()
     p2p = ts.enable_p2p_exchange() if world > 1 else False  # gradient exchange + Adam in one peer-memory kernel
+    # every step's loss reaches the host as a posted write of the step's last kernel into mapped pinned memory (a ring), not
+    # as a 4-byte memcpy between two steps (--loss-readback memcpy keeps that)
+    mirror = ts.fused_stream is not None and args.loss_readback == "mirror"
+    if mirror:
+        ts.enable_loss_mirror(4096)
     # launches of one step = those captured in the graph (one fwd+bwd pass) + Adam
     _lib.LAUNCHES = 0
     ts.graph = None
@@ -412,7 +417,8 @@ def run_ours(args):
             h0 = time.perf_counter()
             for i in range(K):
                 loss = ts.run_pipelined(i & 1)
-                loss_host[i:i + 1].copy_(loss, non_blocking=True)
+                if not mirror:
+                    loss_host[i:i + 1].copy_(loss, non_blocking=True)
             e2e_host[0] = (time.perf_counter() - h0) / K * 1e3
             return
         pf = (lambda slot: ts.prefetch_raw(frames_h, start_h, slot)) if raw else (lambda slot: ts.prefetch(xh, yh, slot))
@@ -421,7 +427,8 @@ def run_ours(args):
             if i + 1 < K:
                 pf((i + 1) & 1)
             loss = ts.run_slot(i & 1)
-            loss_host[i:i + 1].copy_(loss, non_blocking=True)
+            if not mirror:
+                loss_host[i:i + 1].copy_(loss, non_blocking=True)
 
     def e2e_time(raw):
         e2e_run(3, raw)
@@ -443,7 +450,8 @@ def run_ours(args):
     ts.graph = ts._slots[0]["graph"]
     ts.x, ts.y, ts.xp = ts._slots[0]["x"], ts._slots[0]["y"], ts._slots[0]["xp"]
     clocks = sampler.stop() if rank == 0 else None
-    final_loss = float(loss_host[args.steps - 1].item())
+    torch.cuda.synchronize()
+    final_loss = ts.loss_of_step(int(ts._mirror[1]) - 1) if mirror else float(loss_host[args.steps - 1].item())
 
     # ---- instrumented eager pass: CUDA-event time of every C-ABI kernel (same stream) ----
     ts.graph = None
@@ -554,6 +562,8 @@ def run_ours(args):
         "e2e": {"value": world * B / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": frames_h.numel() + start_h.numel() * 4,
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps, "host_enqueue_ms_per_step": e2e_host[0],
+                "d2h": ("the step's loss (4 bytes) written by the step's last kernel (cgat_stream_finish_mirror) into a ring in "
+                        "mapped pinned host memory, every step" if mirror else "4-byte cudaMemcpyAsync of the loss after every step"),
                 "input": "raw uint8 frames [B+7,V,H,W] + int32 window starts from pinned host memory (the KNMI loader's "
                          "on-disk format); sliding windows, /254 and the layouts the train kernel reads (x chunk-planar [N,T*V/8,H,W,8], "
                          "y [N,H,W,T,V]) by cgat_loader_gather_planar on the device",
@@ -623,6 +633,8 @@ def main():
     ap.add_argument("--type", default="temporal", choices=["temporal", "spatial", "multi_stream"])
     ap.add_argument("--mapping", default="conv", choices=["conv", "linear"])
     ap.add_argument("--no-baselines", action="store_true", help="skip the eager-GPU / CPU baseline rows (R1-R5)")
+    ap.add_argument("--loss-readback", default="mirror", choices=["mirror", "memcpy"],
+                    help="e2e: how each step's loss reaches the host (a posted write of the last kernel, or a memcpy per step)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="cold-L2 rule of the timed region: rotate over input slots larger than L2, or flush between steps")
     args = ap.parse_args()

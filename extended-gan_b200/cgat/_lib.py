@@ -110,6 +110,8 @@ SIGNATURES = {
                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P],
     "cgat_stream_finish": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I64,
                            _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P],
+    "cgat_stream_finish_mirror": [ctypes.POINTER(StreamDesc), _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P,
+                                  _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _I, _P, _P],
     "cgat_gat1d_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_gat1d_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cgat_loss_fwd_bwd": [_P, _P, _P, _P, _P, _I64, _F, _F, _I, _P],
@@ -118,6 +120,7 @@ SIGNATURES = {
     "cgat_cast": [_P, _I, _P, _I, _I64, _P],
     "cgat_p2p_mailbox_bytes": [_I64, _I],
     "cgat_p2p_allreduce_adam": [_P, _I, _I, _P, _P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _F, _P],
+    "cgat_p2p_allreduce_adam_graph": [_P, _I, _I, _P, _P, _P, _P, _P, _P, _I64, _P],
     "cgat_val_metrics": [_P, _P, _I64, _F, _F, _F, _I, _P, _P],
     "cgat_loader_gather": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P],
     "cgat_loader_gather_planar": [_P, _I64, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P],

@@ -483,7 +483,7 @@ def records_to_planar(x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor
 
 
 def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: torch.Tensor, mse_out=None, acc=None,
-                     x_planar=None, scratch=None, precision="fp16x2", adam=None, clear=None):
+                     x_planar=None, scratch=None, precision="fp16x2", adam=None, clear=None, mirror=None):
     """The reference train step's forward + loss + backward (convolutional_gat/train.py:130-132) for a model that is
     ONE conv-mapped stream, as three launches: prepare, ``cgat_layer_train``, parameter gradients.
 
@@ -503,6 +503,8 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
     buffers must be views of ``flat_grad``; ``step_dev`` int64[1] and ``hyper`` float32[6] live on the device).
     ``clear``: a tensor (16-byte aligned, a multiple of 16 bytes) the first launch zeroes -- the caller's gradient buffer
     and ``scratch`` -- instead of a separate memset in front of the step.
+    ``mirror``: ``None`` or ``(ring, cursor)`` -- ``ring`` a pinned HOST float32 tensor the finishing launch writes the
+    step's loss into (position ``cursor % len(ring)``; ``cursor`` int32[1] on the device counts the values written).
     """
     require_cuda(x, y, loss_out, *params)
     N, H, W, T, V = x.shape
@@ -584,6 +586,15 @@ def gat_stream_train(x, y, cfg: AttnConfig, mask, params, lam: float, loss_out: 
         _lib.call("cgat_layer_train_fp32", ctypes.byref(ld), ptr(x_planar), ptr(y), ptr(wpack), ptr(bias_d), ptr(a_st), ptr(adj),
                   ptr(mc), float(lam), ptr(wsp), ptr(ga2), ptr(gadj2), ptr(gb2), ptr(alt[0:1]), ptr(alt[1:2]), ptr(guard),
                   ctypes.byref(ncta), ctypes.byref(nt), st)
+    if mirror is not None:
+        ring, cursor = mirror
+        if not (ring.is_pinned() and ring.dtype == torch.float32 and ring.is_contiguous() and cursor.is_cuda
+                and cursor.dtype == torch.int32):
+            raise RuntimeError("gat_stream_train: mirror = (pinned host float32 ring, int32[1] device cursor)")
+        _lib.call("cgat_stream_finish_mirror", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(ga), ptr(gadj), ptr(gb), *pars,
+                  *grads, 1, ptr(guard) if guarded else None, ALT if guarded else 0, ptr(scratch) if guarded else None,
+                  ptr(counter), *adam_args, ptr(loss_out), ctypes.c_void_p(ring.data_ptr()), ring.numel(), ptr(cursor), st)
+        return
     _lib.call("cgat_stream_finish", ctypes.byref(sd), ptr(wsp), ncta.value, nt.value, ptr(ga), ptr(gadj), ptr(gb), *pars, *grads,
               1, ptr(guard) if guarded else None, ALT if guarded else 0, ptr(scratch) if guarded else None, ptr(counter),
               *adam_args, st)

@@ -139,7 +139,7 @@ class _GATStream(nn.Module):
         return layer_train_supported(x, self._train_cfg(x), self.mapping_type)
 
     def fused_train_step(self, x, y, lam, loss_out, mse_out=None, acc=None, x_planar=None, scratch=None, precision="fp16x2",
-                         adam=None, clear=None):
+                         adam=None, clear=None, mirror=None):
         """forward + ``MSE - lam*mean`` loss + backward of a model that is just this stream (train.py:130-132):
         accumulates the loss into ``loss_out`` and the gradients into the parameters' ``.grad`` buffers."""
         from .functional import gat_stream_train
@@ -148,7 +148,7 @@ class _GATStream(nn.Module):
         for h in self.attentions:
             params += [h.conv.weight, h.conv.bias, h.a, h.B]
         gat_stream_train(x, y, self._train_cfg(x), self._mask_arg(), params, lam, loss_out, mse_out, acc, x_planar=x_planar,
-                         scratch=scratch, precision=precision, adam=adam, clear=clear)
+                         scratch=scratch, precision=precision, adam=adam, clear=clear, mirror=mirror)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """``x[N,H,W,T,V]`` -> ``[N,H,W,T,V]`` (mean merge) or heads concatenated on the channel axis."""

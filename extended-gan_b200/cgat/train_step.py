@@ -50,7 +50,9 @@ class TrainStep:
         self.x = example_x.clone()
         self.y = example_y.clone()
         self.device = example_x.device
-        self._step = 0  # optimiser steps taken (host side: Adam and the P2P exchange take it by value)
+        self._step = 0  # optimiser steps taken (host side: Adam after an NCCL all-reduce takes it by value)
+        self._p2p_in_graph = False
+        self._mirror = None  # (pinned host ring, device cursor): the fused step writes its loss to host memory itself
         self.graph = None
         self._slots = None  # double-buffered inputs for pipelined host->device loading (enable_prefetch)
         self.fused_stream = self._single_stream(model, example_x) if fuse_loss else None
@@ -151,8 +153,52 @@ class TrainStep:
         self.flat.broadcast_params(0, self.pg)
 
     def enable_p2p_exchange(self) -> bool:
-        """Replace all-reduce + Adam by the single peer-memory kernel (``cgat_p2p_allreduce_adam``) where available."""
-        return self.flat.enable_p2p(self.pg)
+        """Replace all-reduce + Adam by the single peer-memory kernel (``cgat_p2p_allreduce_adam``) where available.  The
+        kernel then becomes the LAST NODE of the step's captured graph (``cgat_p2p_allreduce_adam_graph``: step counter and
+        hyper-parameters on the device, programmatic dependent launch behind the gradient kernel), so a data-parallel
+        step stays one graph launch; call it before ``enable_prefetch`` / ``enable_raw_pipeline``."""
+        ok = self.flat.enable_p2p(self.pg)
+        self._p2p_in_graph = bool(ok)
+        if ok:
+            if self._slots is not None:
+                raise RuntimeError("enable_p2p_exchange must be called before enable_prefetch / enable_raw_pipeline")
+            if self.graph is not None:
+                self._capture()  # re-capture with the exchange node
+        return ok
+
+    def enable_loss_mirror(self, n: int = 1024) -> torch.Tensor:
+        """Have the fused step's last launch write each step's loss into a ring of ``n`` floats in pinned HOST memory
+        (``cgat_stream_finish_mirror``) instead of the caller copying ``loss`` back with a memcpy between two steps
+        (train.py:135 reads ``loss.item()`` every batch).  Returns the ring; ``loss_of_step(k)`` reads it (after a
+        synchronisation point of the caller's choice).  Call before ``enable_prefetch`` / ``enable_raw_pipeline``."""
+        if self.fused_stream is None:
+            raise RuntimeError("enable_loss_mirror serves the fused train step")
+        if self._slots is not None:
+            raise RuntimeError("enable_loss_mirror must be called before enable_prefetch / enable_raw_pipeline")
+        ring = torch.zeros(n, dtype=torch.float32).pin_memory()
+        self._mirror = (ring, torch.zeros(1, dtype=torch.int32, device=self.device))
+        if self.graph is not None:
+            self._capture()
+        return ring
+
+    def loss_of_step(self, k: int) -> float:
+        """Loss of the k-th fused step taken since ``enable_loss_mirror`` (0-based), from the host ring."""
+        ring = self._mirror[0]
+        return float(ring[k % ring.numel()])
+
+    def _step_launches(self):
+        """Everything one optimisation step enqueues on the device: forward + loss + backward (+ Adam on one GPU), then
+        -- with the peer-memory exchange -- the exchange + Adam kernel."""
+        self._fwd_bwd(with_adam=True)
+        if self._p2p_in_graph:
+            import ctypes
+
+            from . import _lib
+
+            p2p = self.flat.p2p
+            _lib.call("cgat_p2p_allreduce_adam_graph", ctypes.cast(p2p["ptrs"], ctypes.c_void_p), p2p["rank"], p2p["world"],
+                      _lib.ptr(self.flat_grad), _lib.ptr(self.flat_param), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                      _lib.ptr(self._step_dev), _lib.ptr(self._hyper), self.flat_param.numel(), _lib.stream())
 
     def _exchange_and_update(self):
         """Gradient mean over ranks + Adam(lr, weight_decay): one P2P kernel, or NCCL all-reduce + fused Adam."""
@@ -172,6 +218,8 @@ class TrainStep:
                     f"cgat_p2p_allreduce_adam timed out waiting for a peer around step {self._step}: the ranks are out "
                     "of step (every rank must take the same number of steps) or a peer died; parameters were NOT updated "
                     "on this rank for that step.  Restart from a checkpoint, or train with the NCCL exchange.")
+            if self._p2p_in_graph:
+                return  # the exchange + Adam kernel was the last launch of the step (_step_launches)
 
             _lib.call("cgat_p2p_allreduce_adam", ctypes.cast(p2p["ptrs"], ctypes.c_void_p), p2p["rank"], p2p["world"],
                       _lib.ptr(self.flat_grad), _lib.ptr(self.flat_param), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
@@ -196,7 +244,7 @@ class TrainStep:
             if with_adam and self._adam_in_graph:
                 adam = (self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self._step_dev, self._hyper)
             self.fused_stream.fused_train_step(self.x, self.y, self.lam, self.loss, self.mse, self._acc, x_planar=self.xp,
-                                               scratch=self.flat.scratch, adam=adam, clear=clear,
+                                               scratch=self.flat.scratch, adam=adam, clear=clear, mirror=self._mirror,
                                                precision="fp32" if self.precision == "fp32" else
                                                ("fp16x2" if self.precision == "auto" else "fp16x2-unguarded"))
             return
@@ -210,6 +258,7 @@ class TrainStep:
             functional.DIRECT_GRAD = prev
 
     def _capture(self):
+        cursor0 = self._mirror[1].clone() if self._mirror is not None else None  # warm-ups below must not count as steps
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with self._preserve_module_state():
@@ -220,7 +269,9 @@ class TrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self._fwd_bwd(with_adam=True)
+            self._step_launches()
+        if cursor0 is not None:
+            self._mirror[1].copy_(cursor0)
 
     def load_batch(self, x: torch.Tensor, y: torch.Tensor):
         """Copy one batch (host-pinned or device) into the static input buffers."""
@@ -242,7 +293,7 @@ class TrainStep:
         if self.graph is not None:
             self.graph.replay()
         else:
-            self._fwd_bwd(with_adam=True)
+            self._step_launches()
         self._exchange_and_update()
         return self.loss
 
@@ -398,7 +449,7 @@ class TrainStep:
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     fill(other)
-                self._fwd_bwd(with_adam=True)
+                self._step_launches()
                 cur.wait_stream(side)
             cur_slot["pipe_graph"] = g
         self.x, self.y, self.xp, self.graph = keep

@@ -11,6 +11,7 @@
 // straight into the pixel-record layout the conv-GAT kernels read.  fp32 output is bit-exact with the reference for
 // power = 1 (IEEE division); bf16 output rounds that value once.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace cgat {
 
@@ -140,6 +141,68 @@ loader_gather_kernel(const uint8_t* __restrict__ frames, const int32_t* __restri
     } else {
       for (int e = 0; e < rec; ++e) dst[e] = lut[col[(size_t)e * LD_THREADS]];
     }
+  }
+}
+
+// The bench shape's fast path (bf16 output, power = 1 with the exact reciprocal, whole 16-byte chunks, image rows a multiple
+// of 4 pixels): a CTA still owns LD_THREADS consecutive pixels of a sample, but phase 2 is organised by (pixel QUAD, 16-byte
+// record chunk) instead of by pixel: warp c of the CTA handles chunk c (c < NCH: x, else y) and its lane a quad of 4
+// consecutive pixels, so a thread reads its 8 source planes with EIGHT 4-byte shared-memory loads (4 pixels each; the
+// per-pixel kernel issues 2 * rec single-byte loads per thread), converts the bytes in place (I2F with a byte selector, one
+// multiply, packed bf16 conversion) and writes four 16-byte chunks.  665 -> ~150 instructions per thread; the kernel sits
+// on the critical path of the end-to-end step behind the train kernel (it cannot share the SMs with it).
+template <int NCH>
+__global__ void __launch_bounds__(64 * NCH)
+loader_gather_quads_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ start, __nv_bfloat16* __restrict__ x,
+                           __nv_bfloat16* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, float inv, int x_planar) {
+  constexpr int REC = 8 * NCH, PLANES = 2 * REC, NT = 64 * NCH, QUADS = LD_THREADS / 4;
+  __shared__ __align__(16) uint32_t tile[PLANES][QUADS];  // [plane][pixel quad]: 4 pixel bytes per word
+  const long long per_sample = (long long)crop_h * crop_w;
+  const long long blocks_per_sample = (per_sample + LD_THREADS - 1) / LD_THREADS;
+  const int s = (int)(blockIdx.x / blocks_per_sample);
+  const long long p0 = (long long)(blockIdx.x % blocks_per_sample) * LD_THREADS;
+  const int npix = (int)min((long long)LD_THREADS, per_sample - p0);  // a multiple of 4 (host-checked)
+  const size_t plane = (size_t)H * W;
+  const uint8_t* src0 = frames + (size_t)start[s] * V * plane;
+  const int q = threadIdx.x & (QUADS - 1);
+  const int lp = 4 * q;
+  const int p = (int)p0 + lp, hh = p / crop_w, ww = p - hh * crop_w;  // the quad lies in one image row (crop_w % 4 == 0)
+  if (lp < npix) {
+    const uint8_t* sp = src0 + (size_t)hh * W + ww;
+#pragma unroll
+    for (int i = 0; i < PLANES * QUADS / NT; ++i) {
+      const int e = (int)(threadIdx.x / QUADS) + i * (NT / QUADS);
+      tile[e][q] = *reinterpret_cast<const uint32_t*>(sp + (size_t)e * plane);
+    }
+  }
+  __syncthreads();
+  if (lp >= npix) return;
+  const int c = threadIdx.x / QUADS;  // chunk of this warp: c < NCH -> x, else y
+  const bool is_y = c >= NCH;
+  const int cc = is_y ? c - NCH : c;
+  uint32_t wv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wv[j] = tile[c * 8 + j][q];
+  uint4* dst;  // (inv = 1 / normalizing_max from the host: the value the launch checked for bit-exactness)
+  size_t pstride;  // distance between consecutive pixels' chunks, in uint4
+  if (!is_y && x_planar) {
+    const int wp = lf_padded_width(crop_w);
+    dst = reinterpret_cast<uint4*>(x) + ((size_t)s * NCH + cc) * crop_h * wp + (size_t)hh * wp + ww + 1;
+    pstride = 1;
+  } else {
+    dst = reinterpret_cast<uint4*>(is_y ? y : x) + ((size_t)s * per_sample + p) * NCH + cc;
+    pstride = NCH;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // pixel i of the quad = byte i of every word
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = (float)((wv[2 * j] >> (8 * i)) & 0xffu) * inv, b = (float)((wv[2 * j + 1] >> (8 * i)) & 0xffu) * inv;
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+      o[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    dst[(size_t)i * pstride] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -287,6 +350,20 @@ static int cgat::loader_gather_impl(const uint8_t* frames, int64_t n_frames, con
       const __nv_bfloat16 a = __float2bfloat16_rn((float)k / normalizing_max), b = __float2bfloat16_rn((float)k * inv);
       if (__bfloat16_as_ushort(a) != __bfloat16_as_ushort(b)) mul_exact = 0;
     }
+  }
+  // fast path: (pixel quad, record chunk) work items -- see loader_gather_quads_kernel
+  if (dtype == CGAT_BF16 && mul_exact && (steps * vertices) % 8 == 0 && steps * vertices <= 32 && crop_w % 4 == 0 && w % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(frames) & 3u) == 0 && !getenv("CGAT_LOADER_NO_QUADS")) {
+    const int nch = steps * vertices / 8;
+#define LDQ_LAUNCH(NCH)                                                                                                        \
+  loader_gather_quads_kernel<NCH><<<grid, 64 * NCH, 0, st>>>(frames, start, (__nv_bfloat16*)x, (__nv_bfloat16*)y, vertices, h, w, \
+                                                             crop_h, crop_w, 1.f / normalizing_max, x_planar)
+    if (nch == 1) LDQ_LAUNCH(1);
+    else if (nch == 2) LDQ_LAUNCH(2);
+    else if (nch == 3) LDQ_LAUNCH(3);
+    else LDQ_LAUNCH(4);
+#undef LDQ_LAUNCH
+    return check_launch("loader_gather_quads_kernel");
   }
 #define LD_LAUNCH(T, R)                                                                                                   \
   loader_gather_kernel<T, R><<<grid, LD_THREADS, smem, st>>>(frames, start, (T*)x, (T*)y, vertices, h, w, crop_h, crop_w, steps, \

@@ -54,8 +54,14 @@ __global__ void __launch_bounds__(P2P_THREADS)
 p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, long long n_pad, const float* __restrict__ g,
                           float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                           const long long* __restrict__ step_dev, long long step_host, float lr, float b1, float b2,
-                          float eps, float wd, uint32_t* timeout_marker, long long* dbg) {
-  const long long epoch = step_dev != nullptr ? *step_dev : step_host;
+                          float eps, float wd, uint32_t* timeout_marker, long long* dbg, long long* step_counter,
+                          const float* __restrict__ hyper) {
+  // graph-resident form (cgat_p2p_allreduce_adam_graph): the step comes from a device counter of steps taken so far, which
+  // this launch advances at its end, and the hyper-parameters from device memory (lr, beta1, beta2, eps, weight_decay:
+  // a scheduler changes lr between replays); launched with programmatic dependent launch behind the gradient kernel
+  griddep_wait();
+  if (hyper != nullptr) { lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; }
+  const long long epoch = step_counter != nullptr ? *step_counter + 1 : (step_dev != nullptr ? *step_dev : step_host);
   const bool stamp = dbg != nullptr && threadIdx.x == 0 && epoch < 4096;
   if (stamp) dbg[epoch * 4 + 0] = p2p_now();
   const uint32_t ep = (uint32_t)epoch;
@@ -103,8 +109,9 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
   // all-or-nothing: one late word anywhere in the vector and NO element of p / m / v is touched this step
   if (__syncthreads_or(timed_out)) {
     if (tid == 0) atomicExch(timeout_marker, 1u);
-    return;
+    return;  // (the step counter stays: the host raises on the marker; nothing was updated)
   }
+  if (step_counter != nullptr && tid == 0) *step_counter = epoch;  // every thread has read it (the barrier above)
   if (stamp) dbg[epoch * 4 + 2] = p2p_now();
   auto adam = [&](long long i, float gs) {
     const float pi = p[i];
@@ -157,6 +164,28 @@ extern "C" int cgat_p2p_allreduce_adam(const uint64_t* peer_mailboxes, int32_t r
   uint32_t* marker = reinterpret_cast<uint32_t*>(peer_mailboxes[rank] + (uint64_t)2 * world * n_pad * 8);
   p2p_allreduce_adam_kernel<<<1, P2P_THREADS, 0, (cudaStream_t)stream>>>(P, rank, world, n, n_pad, grad, param, m, v,
                                                                          (const long long*)step_dev, (long long)step_host, lr,
-                                                                         beta1, beta2, eps, weight_decay, marker, get_debug_buffer());
+                                                                         beta1, beta2, eps, weight_decay, marker, get_debug_buffer(),
+                                                                         nullptr, nullptr);
+  return check_launch("p2p_allreduce_adam_kernel");
+}
+
+extern "C" int cgat_p2p_allreduce_adam_graph(const uint64_t* peer_mailboxes, int32_t rank, int32_t world, const float* grad,
+                                             float* param, float* m, float* v, int64_t* step_counter, const float* hyper,
+                                             int64_t n, void* stream) {
+  if (!peer_mailboxes || !grad || !param || !m || !v || !step_counter || !hyper) return fail(CGAT_EINVAL, "null argument");
+  if (world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world) return fail(CGAT_EINVAL, "bad rank/world %d/%d", rank, world);
+  if (n <= 0 || n > (1 << 20)) return fail(CGAT_EUNSUPPORTED, "p2p exchange serves vectors of at most 2^20 floats (n=%lld)", (long long)n);
+  if (!aligned16(grad)) return fail(CGAT_EALIGN, "grad must be 16-byte aligned");
+  const long long n_pad = (n + 31) & ~(long long)31;
+  P2pPeers P{};
+  for (int q = 0; q < world; ++q) {
+    if (!peer_mailboxes[q] || (peer_mailboxes[q] & 15)) return fail(CGAT_EALIGN, "peer mailbox %d null or misaligned", q);
+    P.mailbox[q] = reinterpret_cast<uint2*>(peer_mailboxes[q]);
+  }
+  uint32_t* marker = reinterpret_cast<uint32_t*>(peer_mailboxes[rank] + (uint64_t)2 * world * n_pad * 8);
+  cudaError_t e = launch_pdl(p2p_allreduce_adam_kernel, dim3(1), dim3(P2P_THREADS), 0, (cudaStream_t)stream, P, (int)rank,
+                             (int)world, (long long)n, n_pad, grad, param, m, v, (const long long*)nullptr, (long long)0, 0.f, 0.f,
+                             0.f, 0.f, 0.f, marker, get_debug_buffer(), (long long*)step_counter, hyper);
+  if (e != cudaSuccess) return fail((int)e, "p2p_allreduce_adam_kernel: %s", cudaGetErrorString(e));
   return check_launch("p2p_allreduce_adam_kernel");
 }

@@ -373,6 +373,12 @@ struct FinishArgs {
   float* R;                 // [rows][nc] global scratch
   int rows, nc;
   AdamArgs adam;
+  // optional: the step's scalar loss goes straight to host memory (a ring in mapped pinned memory) -- no memcpy node, no
+  // copy-engine round trip between two steps
+  const float* mirror_src;       // the accumulator set's base: loss at [0] (or at [alt_offset] when the fp32 re-run is valid)
+  float* mirror;                 // ring of mirror_n floats, device-accessible host memory
+  unsigned int mirror_n;
+  unsigned int* mirror_cursor;   // device counter of values written so far
 };
 
 __device__ __forceinline__ void fin_grid_barrier(unsigned int* counter) {
@@ -424,6 +430,11 @@ __global__ void __launch_bounds__(FIN_THREADS) stream_finish_kernel(const Finish
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && sel != 0 && A.loss_mse != nullptr) {
     A.loss_mse[0] = A.loss_mse[sel];
     A.loss_mse[1] = A.loss_mse[sel + 1];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0 && F.mirror != nullptr) {
+    const unsigned int cur = *F.mirror_cursor;
+    F.mirror[cur % F.mirror_n] = __ldcg(F.mirror_src + sel);  // a posted write over PCIe: the kernel does not wait for it
+    *F.mirror_cursor = cur + 1;
   }
   const bool ext = g.ext > 0;
   const int nwe = g.co * g.ci * g.taps;
@@ -583,7 +594,8 @@ static int param_grads_impl(const cgat_stream_desc* d, const float* wg_partial, 
                             const float* const* w, const float* const* bias, const float* const* a,
                             float* const* g_w, float* const* g_bias, float* const* g_a, float* const* g_B,
                             int accumulate, const float* select, long long alt_offset, float* loss_mse,
-                            unsigned int* counter, const AdamArgs* adam, void* stream) {
+                            unsigned int* counter, const AdamArgs* adam, void* stream, const float* mirror_src = nullptr,
+                            float* mirror = nullptr, int mirror_n = 0, unsigned int* mirror_cursor = nullptr) {
   if (int rc = check_desc(d)) return rc;
   if (!ga || !gadj || !B || !g_w || !g_a || !g_B) return fail(CGAT_EINVAL, "null argument");
   const bool ext = d->mapping == 1 && make_geom(*d).ext > 0;
@@ -622,6 +634,10 @@ static int param_grads_impl(const cgat_stream_desc* d, const float* wg_partial, 
     F.counter = counter;
     F.R = const_cast<float*>(wg_partial) + (size_t)ncta * F.rows * F.nc;
     if (adam) F.adam = *adam;
+    if (mirror != nullptr) {
+      if (!mirror_src || mirror_n < 1 || !mirror_cursor) return fail(CGAT_EINVAL, "loss mirror: source, ring size and cursor are needed");
+      F.mirror_src = mirror_src; F.mirror = mirror; F.mirror_n = (unsigned)mirror_n; F.mirror_cursor = mirror_cursor;
+    }
     cudaError_t e = launch_pdl(stream_finish_kernel, dim3(F.rows), dim3(FIN_THREADS), 0, (cudaStream_t)stream, F);
     if (e != cudaSuccess) return fail((int)e, "stream_finish_kernel: %s", cudaGetErrorString(e));
     return check_launch("stream_finish_kernel");
@@ -647,13 +663,15 @@ extern "C" int cgat_stream_param_grads(const cgat_stream_desc* d, const float* w
                           nullptr, 0, nullptr, nullptr, nullptr, stream);
 }
 
-extern "C" int cgat_stream_finish(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
-                                  const float* gadj, const float* gbias, const float* const* B, const float* const* w,
-                                  const float* const* bias, const float* const* a, float* const* g_w, float* const* g_bias,
-                                  float* const* g_a, float* const* g_B, int accumulate, const float* select,
-                                  int64_t alt_offset, float* loss_mse, uint32_t* counter, float* adam_param,
-                                  const float* adam_grad, float* adam_m, float* adam_v, int64_t adam_n,
-                                  int64_t* adam_step_dev, const float* adam_hyper, void* stream) {
+extern "C" int cgat_stream_finish_mirror(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
+                                         const float* gadj, const float* gbias, const float* const* B, const float* const* w,
+                                         const float* const* bias, const float* const* a, float* const* g_w,
+                                         float* const* g_bias, float* const* g_a, float* const* g_B, int accumulate,
+                                         const float* select, int64_t alt_offset, float* loss_mse, uint32_t* counter,
+                                         float* adam_param, const float* adam_grad, float* adam_m, float* adam_v,
+                                         int64_t adam_n, int64_t* adam_step_dev, const float* adam_hyper,
+                                         const float* mirror_src, float* mirror, int32_t mirror_n, uint32_t* mirror_cursor,
+                                         void* stream) {
   if (!d || d->mapping != 1 || !d->wgrad_cols) return fail(CGAT_EINVAL, "cgat_stream_finish serves the fused layer kernels (wgrad_cols = 1)");
   AdamArgs O{};
   if (adam_param != nullptr) {
@@ -662,7 +680,20 @@ extern "C" int cgat_stream_finish(const cgat_stream_desc* d, const float* wg_par
     O.hyper = adam_hyper;
   }
   return param_grads_impl(d, wg_partial, ncta, nt, nullptr, ga, gadj, gbias, B, w, bias, a, g_w, g_bias, g_a, g_B, accumulate,
-                          select, (long long)alt_offset, loss_mse, counter, adam_param ? &O : nullptr, stream);
+                          select, (long long)alt_offset, loss_mse, counter, adam_param ? &O : nullptr, stream, mirror_src, mirror,
+                          mirror_n, mirror_cursor);
+}
+
+extern "C" int cgat_stream_finish(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
+                                  const float* gadj, const float* gbias, const float* const* B, const float* const* w,
+                                  const float* const* bias, const float* const* a, float* const* g_w, float* const* g_bias,
+                                  float* const* g_a, float* const* g_B, int accumulate, const float* select,
+                                  int64_t alt_offset, float* loss_mse, uint32_t* counter, float* adam_param,
+                                  const float* adam_grad, float* adam_m, float* adam_v, int64_t adam_n,
+                                  int64_t* adam_step_dev, const float* adam_hyper, void* stream) {
+  return cgat_stream_finish_mirror(d, wg_partial, ncta, nt, ga, gadj, gbias, B, w, bias, a, g_w, g_bias, g_a, g_B, accumulate,
+                                   select, alt_offset, loss_mse, counter, adam_param, adam_grad, adam_m, adam_v, adam_n,
+                                   adam_step_dev, adam_hyper, nullptr, nullptr, 0, nullptr, stream);
 }
 
 extern "C" int cgat_stream_prepare(const cgat_stream_desc* d, const float* const* w, const float* const* bias,

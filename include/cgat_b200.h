@@ -200,6 +200,17 @@ int cgat_stream_finish(const cgat_stream_desc* d, const float* wg_partial, int n
                        float* const* g_a, float* const* g_B, int accumulate, const float* select, int64_t alt_offset,
                        float* loss_mse, uint32_t* counter, float* adam_param, const float* adam_grad, float* adam_m,
                        float* adam_v, int64_t adam_n, int64_t* adam_step_dev, const float* adam_hyper, void* stream);
+/* The same launch, and the step's scalar loss written straight to HOST memory: mirror = a ring of mirror_n floats in mapped
+ * pinned memory (device-accessible), *mirror_cursor = values written so far (device counter, advanced by the launch),
+ * mirror_src = the base of the accumulator set that holds the loss at [0] (at [alt_offset] when the fp32 re-run is
+ * selected).  Replaces a 4-byte device-to-host memcpy between two steps (train.py:135: loss.item()) by a posted write. */
+int cgat_stream_finish_mirror(const cgat_stream_desc* d, const float* wg_partial, int ncta, int nt, const float* ga,
+                              const float* gadj, const float* gbias, const float* const* B, const float* const* w,
+                              const float* const* bias, const float* const* a, float* const* g_w, float* const* g_bias,
+                              float* const* g_a, float* const* g_B, int accumulate, const float* select, int64_t alt_offset,
+                              float* loss_mse, uint32_t* counter, float* adam_param, const float* adam_grad, float* adam_m,
+                              float* adam_v, int64_t adam_n, int64_t* adam_step_dev, const float* adam_hyper,
+                              const float* mirror_src, float* mirror, int32_t mirror_n, uint32_t* mirror_cursor, void* stream);
 
 /* K6 / K7  one conv-mapped stream of the conv-GAT layer (shared 3x3 node conv, pad 1, + graph attention) as ONE
  * kernel per direction: the projected features never touch HBM (tcgen05 accumulators in TMEM are read by the
@@ -436,6 +447,12 @@ int64_t cgat_p2p_mailbox_bytes(int64_t n, int32_t world);
 int cgat_p2p_allreduce_adam(const uint64_t* peer_mailboxes, int32_t rank, int32_t world, const float* grad, float* param,
                             float* m, float* v, const int64_t* step_dev, int64_t step_host, int64_t n, float lr,
                             float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* The same exchange + Adam as a CUDA-graph node: the step is *step_counter + 1 (steps taken so far, device memory; the launch
+ * stores the new count when it has applied the update, and leaves it on a time-out), hyper = device {lr, beta1, beta2, eps,
+ * weight_decay} (a scheduler rewrites lr between replays).  Launched with programmatic dependent launch: it may be
+ * scheduled while the kernel that produces `grad` still runs and waits for it on the device.                         */
+int cgat_p2p_allreduce_adam_graph(const uint64_t* peer_mailboxes, int32_t rank, int32_t world, const float* grad, float* param,
+                                  float* m, float* v, int64_t* step_counter, const float* hyper, int64_t n, void* stream);
 /* the same update with the 1-based step count passed by value (no device counter, no increment kernel) */
 int cgat_adam_step_at(float* param, const float* grad, float* m, float* v, int64_t step, int64_t n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, float grad_scale, void* stream);

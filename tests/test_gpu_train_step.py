@@ -104,3 +104,24 @@ def test_train_step_accepts_records_and_loader_planar_x(attention_type, N, H, W)
     close(res[True][0], res[False][0], rtol=1e-5, atol=1e-7, msg="loss")
     close(res[True][2], res[False][2], rtol=1e-5, atol=1e-7, msg="mse")
     close(res[True][1], res[False][1], rtol=1e-5, atol=1e-6 * res[False][1].abs().max().item(), msg="flat gradient")
+
+
+def test_loss_mirror_writes_every_steps_loss_to_host_memory():
+    """enable_loss_mirror: the fused step's last launch (cgat_stream_finish_mirror) writes each step's loss into a pinned host
+    ring -- same values as the device-side loss read back step by step, graph replay and eager, warm-ups not counted."""
+    from cgat.train_step import TrainStep
+
+    ours, _ = _models("temporal", "conv")
+    torch.manual_seed(11)
+    x = torch.rand(4, 32, 24, 4, 6, device=DEV).bfloat16()
+    y = torch.rand(4, 32, 24, 4, 6, device=DEV).bfloat16()
+    ts = TrainStep(ours, x, y, lr=1e-3, use_graph=True)
+    ring = ts.enable_loss_mirror(4)
+    assert ring.is_pinned() and ring.numel() == 4
+    seen = []
+    for it in range(6):  # wraps around the ring of 4
+        seen.append(float(ts.run()[0]))  # (.item() synchronises: the posted host write of this step has landed)
+        torch.cuda.synchronize()
+        assert ts.loss_of_step(it) == seen[-1], (it, ts.loss_of_step(it), seen[-1])
+    assert seen[0] != seen[-1]  # the parameters moved
+    assert int(ts._mirror[1]) == 6

@@ -31,9 +31,9 @@ def main():
     y = torch.rand(64, 64, 64, 4, 6, generator=g).bfloat16().to(dev)
     ts = TrainStep(model, x, y, lr=1e-3)
     ts.sync_params()
-    assert ts.enable_p2p_exchange()
     dbg = torch.zeros(4096 * 4, dtype=torch.int64, device=dev)
-    _lib.lib().cgat_debug_timeline(ctypes.c_void_p(dbg.data_ptr()))
+    _lib.lib().cgat_debug_timeline(ctypes.c_void_p(dbg.data_ptr()))  # (before the exchange kernel is captured into the step's graph)
+    assert ts.enable_p2p_exchange()
     K = 200
     for _ in range(K):
         ts.run()
