@@ -17,6 +17,7 @@ namespace cgat {
 
 constexpr int LD_THREADS = 128;
 constexpr int LD_MAX_REC = 64;  // T * V elements per pixel record
+constexpr int LDQ_PIX = 256;    // pixels per CTA of the quad-organised fast path
 
 // One CTA = LD_THREADS consecutive output pixels of one sample.  Phase 1: the 2*steps*V source planes of the window
 // are staged in shared memory with 4-byte loads where the 4 pixels lie in one image row (always, for the usual
@@ -155,54 +156,65 @@ template <int NCH>
 __global__ void __launch_bounds__(64 * NCH)
 loader_gather_quads_kernel(const uint8_t* __restrict__ frames, const int32_t* __restrict__ start, __nv_bfloat16* __restrict__ x,
                            __nv_bfloat16* __restrict__ y, int V, int H, int W, int crop_h, int crop_w, float inv, int x_planar) {
-  constexpr int REC = 8 * NCH, PLANES = 2 * REC, NT = 64 * NCH, QUADS = LD_THREADS / 4;
+  // LDQ_PIX pixels per CTA = QPT quads per lane: the bench shape then runs as 1 024 CTAs of 192 threads, ONE wave at 7 CTAs
+  // per SM (2 048 CTAs of 128 pixels were 1.4 waves of a latency-bound kernel), with 16 loads in flight per thread
+  constexpr int REC = 8 * NCH, PLANES = 2 * REC, NT = 64 * NCH, QUADS = LDQ_PIX / 4, QPT = QUADS / 32;
   __shared__ __align__(16) uint32_t tile[PLANES][QUADS];  // [plane][pixel quad]: 4 pixel bytes per word
   const long long per_sample = (long long)crop_h * crop_w;
-  const long long blocks_per_sample = (per_sample + LD_THREADS - 1) / LD_THREADS;
+  const long long blocks_per_sample = (per_sample + LDQ_PIX - 1) / LDQ_PIX;
   const int s = (int)(blockIdx.x / blocks_per_sample);
-  const long long p0 = (long long)(blockIdx.x % blocks_per_sample) * LD_THREADS;
-  const int npix = (int)min((long long)LD_THREADS, per_sample - p0);  // a multiple of 4 (host-checked)
+  const long long p0 = (long long)(blockIdx.x % blocks_per_sample) * LDQ_PIX;
+  const int npix = (int)min((long long)LDQ_PIX, per_sample - p0);  // a multiple of 4 (host-checked)
   const size_t plane = (size_t)H * W;
   const uint8_t* src0 = frames + (size_t)start[s] * V * plane;
-  const int q = threadIdx.x & (QUADS - 1);
-  const int lp = 4 * q;
-  const int p = (int)p0 + lp, hh = p / crop_w, ww = p - hh * crop_w;  // the quad lies in one image row (crop_w % 4 == 0)
-  if (lp < npix) {
-    const uint8_t* sp = src0 + (size_t)hh * W + ww;
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;  // warp c: chunk c of the record (c < NCH: x, else y)
+  int hh[QPT], ww[QPT];
 #pragma unroll
-    for (int i = 0; i < PLANES * QUADS / NT; ++i) {
-      const int e = (int)(threadIdx.x / QUADS) + i * (NT / QUADS);
-      tile[e][q] = *reinterpret_cast<const uint32_t*>(sp + (size_t)e * plane);
-    }
+  for (int k = 0; k < QPT; ++k) {  // quad lane + 32 k: 4 consecutive pixels of one image row (crop_w % 4 == 0)
+    const int p = (int)p0 + 4 * (lane + 32 * k);
+    hh[k] = p / crop_w;
+    ww[k] = p - hh[k] * crop_w;
+  }
+  // stage: warp c takes planes c, c + 2 NCH, ... (8 of them), each lane its QPT quads of the plane
+#pragma unroll
+  for (int i = 0; i < PLANES / (2 * NCH); ++i) {
+    const int e = c + i * 2 * NCH;
+#pragma unroll
+    for (int k = 0; k < QPT; ++k)
+      if (4 * (lane + 32 * k) < npix)
+        tile[e][lane + 32 * k] = *reinterpret_cast<const uint32_t*>(src0 + (size_t)e * plane + (size_t)hh[k] * W + ww[k]);
   }
   __syncthreads();
-  if (lp >= npix) return;
-  const int c = threadIdx.x / QUADS;  // chunk of this warp: c < NCH -> x, else y
   const bool is_y = c >= NCH;
   const int cc = is_y ? c - NCH : c;
-  uint32_t wv[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) wv[j] = tile[c * 8 + j][q];
-  uint4* dst;  // (inv = 1 / normalizing_max from the host: the value the launch checked for bit-exactness)
-  size_t pstride;  // distance between consecutive pixels' chunks, in uint4
-  if (!is_y && x_planar) {
-    const int wp = lf_padded_width(crop_w);
-    dst = reinterpret_cast<uint4*>(x) + ((size_t)s * NCH + cc) * crop_h * wp + (size_t)hh * wp + ww + 1;
-    pstride = 1;
-  } else {
-    dst = reinterpret_cast<uint4*>(is_y ? y : x) + ((size_t)s * per_sample + p) * NCH + cc;
-    pstride = NCH;
-  }
+  for (int k = 0; k < QPT; ++k) {
+    const int lp = 4 * (lane + 32 * k);
+    if (lp >= npix) continue;
+    uint32_t wv[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {  // pixel i of the quad = byte i of every word
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = (float)((wv[2 * j] >> (8 * i)) & 0xffu) * inv, b = (float)((wv[2 * j + 1] >> (8 * i)) & 0xffu) * inv;
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-      o[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    for (int j = 0; j < 8; ++j) wv[j] = tile[c * 8 + j][lane + 32 * k];
+    uint4* dst;  // (inv = 1 / normalizing_max from the host: the value the launch checked for bit-exactness)
+    size_t pstride;  // distance between consecutive pixels' chunks, in uint4
+    if (!is_y && x_planar) {
+      const int wp = lf_padded_width(crop_w);
+      dst = reinterpret_cast<uint4*>(x) + ((size_t)s * NCH + cc) * crop_h * wp + (size_t)hh[k] * wp + ww[k] + 1;
+      pstride = 1;
+    } else {
+      dst = reinterpret_cast<uint4*>(is_y ? y : x) + ((size_t)s * per_sample + p0 + lp) * NCH + cc;
+      pstride = NCH;
     }
-    dst[(size_t)i * pstride] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // pixel i of the quad = byte i of every word
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = (float)((wv[2 * j] >> (8 * i)) & 0xffu) * inv, b = (float)((wv[2 * j + 1] >> (8 * i)) & 0xffu) * inv;
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+        o[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      dst[(size_t)i * pstride] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -355,8 +367,9 @@ static int cgat::loader_gather_impl(const uint8_t* frames, int64_t n_frames, con
   if (dtype == CGAT_BF16 && mul_exact && (steps * vertices) % 8 == 0 && steps * vertices <= 32 && crop_w % 4 == 0 && w % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(frames) & 3u) == 0 && !getenv("CGAT_LOADER_NO_QUADS")) {
     const int nch = steps * vertices / 8;
+    const unsigned qgrid = (unsigned)(n * ((per_sample + LDQ_PIX - 1) / LDQ_PIX));
 #define LDQ_LAUNCH(NCH)                                                                                                        \
-  loader_gather_quads_kernel<NCH><<<grid, 64 * NCH, 0, st>>>(frames, start, (__nv_bfloat16*)x, (__nv_bfloat16*)y, vertices, h, w, \
+  loader_gather_quads_kernel<NCH><<<qgrid, 64 * NCH, 0, st>>>(frames, start, (__nv_bfloat16*)x, (__nv_bfloat16*)y, vertices, h, w, \
                                                              crop_h, crop_w, 1.f / normalizing_max, x_planar)
     if (nch == 1) LDQ_LAUNCH(1);
     else if (nch == 2) LDQ_LAUNCH(2);
