@@ -206,14 +206,16 @@ __global__ void __launch_bounds__(NA_THREADS) na_reduce_kernel(const NaArgs A, i
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (A.sets > 1) {  // (one set: this CTA is also the last of all -- no second signalling round, ~3 us of fence + atomic latency)
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned long long* gcounter = reinterpret_cast<unsigned long long*>(A.sums + (long long)A.sets * (2 * A.c + 2));
+      s_last = atomicAdd(gcounter, 1ull) == (unsigned long long)A.sets - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
     __threadfence();
-    unsigned long long* gcounter = reinterpret_cast<unsigned long long*>(A.sums + (long long)A.sets * (2 * A.c + 2));
-    s_last = atomicAdd(gcounter, 1ull) == (unsigned long long)A.sets - 1;
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
   for (int ch = threadIdx.x; ch < A.c; ch += NA_THREADS) {
     if constexpr (MODE == 0) {
       if (A.running_mean != nullptr) {
