@@ -269,6 +269,9 @@ def workload_config(args, per_gpu_batch):
                "y [N,H,W,T,V]" if args.l2 == "rotate" else
                "flushed between timed steps (256 MiB memset outside the per-step event pairs)"),
         "optimizer": "Adam(lr=1e-3, weight_decay=0.01) fused, flat fp32 buffers", "cuda_graph": True,
+        "timing": "W warm-up steps, barrier + synchronize, K steps inside one CUDA-event pair, barrier + synchronize, max over ranks"
+                  + ("; N > 1: a device-side all-reduce is enqueued between the barrier and the start event so that the ranks' "
+                     "timed regions start together" if args.gpus > 1 else ""),
     }
 
 
@@ -330,6 +333,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    align_buf = torch.zeros(1, device=dev) if world > 1 else None
+
+    def align():
+        """Device-side rendezvous enqueued (not synchronised) right before a start event: after barrier() the ranks' hosts
+        leave the synchronisation tens of microseconds apart, which the max over ranks would count as step time of a
+        20 x 0.07 ms region; the all-reduce kernel completes on every rank at the same moment."""
+        if world > 1:
+            dist.all_reduce(align_buf)
+
     def timed(step_fn, K, Wm):
         for _ in range(Wm):
             step_fn()
@@ -372,6 +384,7 @@ def run_ours(args):
             for i in range(Wm):
                 ts.run_slot(i % NS)
             barrier()
+            align()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             h0 = time.perf_counter()
@@ -385,19 +398,8 @@ def run_ours(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
 
-        dbg = None
-        if os.environ.get("CGAT_P2P_TIMELINE") and world > 1:  # developer knob: where the exchange's time goes (stderr)
-            import ctypes
-            dbg = torch.zeros(4096 * 4, dtype=torch.int64, device=dev)
-            _lib.lib().cgat_debug_timeline(ctypes.c_void_p(dbg.data_ptr()))
         total_ms = timed_rotate(args.steps, max(3, args.warmup))
-        if dbg is not None:
-            _lib.lib().cgat_debug_timeline(None)
-            t = dbg.view(4096, 4)[ts._step - args.steps + 1:ts._step + 1].cpu().double() / 1e3
-            med = lambda v: float(v.median())
-            print(f"[p2p timeline] rank {rank}: step {med(t[1:, 0] - t[:-1, 0]):.1f} us = exchange kernel "
-                  f"{med(t[:, 3] - t[:, 0]):.1f} (push {med(t[:, 1] - t[:, 0]):.1f}, wait {med(t[:, 2] - t[:, 1]):.1f}, "
-                  f"adam {med(t[:, 3] - t[:, 2]):.1f}) + rest {med(t[1:, 0] - t[:-1, 3]):.1f}", file=sys.stderr, flush=True)
+        # (where the exchange's time goes: tools/p2p_timeline.py -- the kernel is a node of the step's graph now)
     else:
         total_ms = timed(lambda: ts.run(), args.steps, max(3, args.warmup))
     # ---- end to end: every step copies its x, y from pinned host memory and reads the loss back to the host.
@@ -433,6 +435,7 @@ def run_ours(args):
     def e2e_time(raw):
         e2e_run(3, raw)
         barrier()
+        align()
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
         e2e_run(args.steps, raw)
