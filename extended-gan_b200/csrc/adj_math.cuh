@@ -19,23 +19,23 @@ __device__ __forceinline__ float block_reduce(float v, int op, float* scratch) {
   if (lane == 0) scratch[warp] = v;
   __syncthreads();
   float r = scratch[0];
-  for (int w = 1; w < ADJ_THREADS / 32; ++w) {
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
     const float x = scratch[w];
     r = op == 0 ? r + x : (op == 1 ? fminf(r, x) : fmaxf(r, x));
   }
   return r;
 }
 
-// one CTA of ADJ_THREADS threads normalises head `head`
+// one CTA (any multiple of 32 threads up to 1024; every thread must call) normalises head `head`
 __device__ __forceinline__ void adj_norm_fwd_block(const float* __restrict__ B, float* __restrict__ out, int nodes,
                                                    int transpose, int head) {
-  __shared__ float scratch[ADJ_THREADS / 32];
+  __shared__ float scratch[32];  // one slot per warp of a block of up to 1024 threads
   __shared__ float rs[ADJ_MAX_NODES];
   const int nn = nodes * nodes;
   const float* Bh = B + (size_t)head * nn;
   float* oh = out + (size_t)head * nn;
   float mn = INFINITY, mx = -INFINITY;
-  for (int q = threadIdx.x; q < nn; q += ADJ_THREADS) {
+  for (int q = threadIdx.x; q < nn; q += blockDim.x) {
     const float m = Bh[q] + ((q / nodes == q % nodes) ? 1.f : 0.f);
     mn = fminf(mn, m);
     mx = fmaxf(mx, m);
@@ -44,13 +44,13 @@ __device__ __forceinline__ void adj_norm_fwd_block(const float* __restrict__ B, 
   mx = block_reduce(mx, 2, scratch);
   const float inv = 1.f / (mx - mn);
   // row sums -> r_i = sqrt(1/d_i)
-  for (int i = threadIdx.x; i < nodes; i += ADJ_THREADS) {
+  for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
     float d = 0.f;
     for (int k = 0; k < nodes; ++k) d += (Bh[i * nodes + k] + (i == k ? 1.f : 0.f) - mn) * inv;
     rs[i] = sqrtf(1.f / d);
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < nn; q += ADJ_THREADS) {
+  for (int q = threadIdx.x; q < nn; q += blockDim.x) {
     const int i = q / nodes, k = q % nodes;
     const float adj = (Bh[q] + (i == k ? 1.f : 0.f) - mn) * inv;
     const float v = rs[i] * adj * rs[k];
@@ -62,14 +62,14 @@ __device__ __forceinline__ void adj_norm_fwd_block(const float* __restrict__ B, 
 __device__ __forceinline__ void adj_norm_bwd_block(const float* __restrict__ B, const float* __restrict__ g,
                                                    float* __restrict__ gB, int nodes, int transpose, int head,
                                                    int accumulate) {
-  __shared__ float scratch[ADJ_THREADS / 32];
+  __shared__ float scratch[32];  // one slot per warp of a block of up to 1024 threads
   __shared__ float rs[ADJ_MAX_NODES];
   const int nn = nodes * nodes;
   const float* Bh = B + (size_t)head * nn;
   const float* gh = g + (size_t)head * nn;
   float* oh = gB + (size_t)head * nn;
   float mn = INFINITY, mx = -INFINITY;
-  for (int q = threadIdx.x; q < nn; q += ADJ_THREADS) {
+  for (int q = threadIdx.x; q < nn; q += blockDim.x) {
     const float m = Bh[q] + ((q / nodes == q % nodes) ? 1.f : 0.f);
     mn = fminf(mn, m);
     mx = fmaxf(mx, m);
@@ -77,7 +77,7 @@ __device__ __forceinline__ void adj_norm_bwd_block(const float* __restrict__ B, 
   mn = block_reduce(mn, 1, scratch);
   mx = block_reduce(mx, 2, scratch);
   const float inv = 1.f / (mx - mn);
-  for (int i = threadIdx.x; i < nodes; i += ADJ_THREADS) {
+  for (int i = threadIdx.x; i < nodes; i += blockDim.x) {
     float d = 0.f;
     for (int k = 0; k < nodes; ++k) d += (Bh[i * nodes + k] + (i == k ? 1.f : 0.f) - mn) * inv;
     rs[i] = sqrtf(1.f / d);
@@ -85,7 +85,7 @@ __device__ __forceinline__ void adj_norm_bwd_block(const float* __restrict__ B, 
   __syncthreads();
   // d_mn = sum dadj (adj-1)/S ; d_mx = -sum dadj adj / S ; tie counts
   float dmn = 0.f, dmx = 0.f, cmn = 0.f, cmx = 0.f;
-  for (int q = threadIdx.x; q < nn; q += ADJ_THREADS) {
+  for (int q = threadIdx.x; q < nn; q += blockDim.x) {
     const int i = q / nodes, k = q % nodes;
     const float m = Bh[q] + (i == k ? 1.f : 0.f);
     const float adj = (m - mn) * inv;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void adj_norm_bwd_block(const float* __restrict__ B, 
   dmx = block_reduce(dmx, 0, scratch);
   cmn = block_reduce(cmn, 0, scratch);
   cmx = block_reduce(cmx, 0, scratch);
-  for (int q = threadIdx.x; q < nn; q += ADJ_THREADS) {
+  for (int q = threadIdx.x; q < nn; q += blockDim.x) {
     const int i = q / nodes, k = q % nodes;
     const float m = Bh[q] + (i == k ? 1.f : 0.f);
     float v = gh[transpose ? (k * nodes + i) : q] * rs[i] * rs[k] * inv;

@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(ADJ_THREADS) stream_param_grads_kernel(const G
 //   G_which[k][node][tap][c] = d(W.a_which)  in the rows behind the features:
 //   dW[k][u][c][tap] += a1[k][u] G1 + a2[k][u] G2
 //   d(a_which)[k][u]  = sum_{node,tap,c} w[k][u][c][tap] G_which + bias[k][u] sum(ds_which)     (+ ga from the kernel)
-constexpr int FIN_THREADS = 256, FIN_MAX_R = 128 * 64;
+constexpr int FIN_THREADS = 256, FIN_MAX_R = 128 * 64;  // (1024 threads: the block then owns an SM and cannot overlap the loader gather or start under the train kernel's tail: step +3 us, e2e +11 us)
 struct AdamArgs {
   float* p;                 // NULL: no optimiser step in this launch
   const float* g;
@@ -397,29 +397,37 @@ __device__ __forceinline__ void fin_grid_barrier(unsigned int* counter) {
 __global__ void __launch_bounds__(FIN_THREADS) stream_finish_kernel(const FinishArgs F) {
   griddep_launch();
   griddep_wait();
-  __shared__ float s_part[4][64];
+  constexpr int FIN_GROUPS = FIN_THREADS / 64, FIN_PER = (148 + FIN_GROUPS - 1) / FIN_GROUPS;
+  __shared__ float s_part[FIN_GROUPS][64];
   const GradArgs& A = F.G;
-  {  // ---- phase A: this block's row, summed over the CTAs ----
+  {  // ---- phase A: this block's row, summed over the CTAs: 64 columns x FIN_GROUPS groups of slots; a thread has ALL its
+     //      loads (<= FIN_PER for up to 148 slots) in flight at once -- with 4 groups the 37 loads per thread went out in
+     //      five dependent batches of L2 latency ----
     const int row = blockIdx.x, col = threadIdx.x & 63, grp = threadIdx.x >> 6;
     for (int c0 = 0; c0 < F.nc; c0 += 64) {
       float acc = 0.f;
       if (c0 + col < F.nc) {
         const float* p = A.wg_partial + (size_t)row * F.nc + c0 + col;
         const size_t cs = (size_t)F.rows * F.nc;
-        int c = grp;
-        for (; c + 28 < A.ncta; c += 32) {  // 8 independent loads in flight
-          float v[8];
+        for (int cb = grp; cb < A.ncta; cb += FIN_GROUPS * FIN_PER) {
+          float v[FIN_PER];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __ldcg(p + (size_t)(c + 4 * j) * cs);
+          for (int j = 0; j < FIN_PER; ++j) {
+            const int c = cb + j * FIN_GROUPS;
+            v[j] = c < A.ncta ? __ldcg(p + (size_t)c * cs) : 0.f;
+          }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc += v[j];
+          for (int j = 0; j < FIN_PER; ++j) acc += v[j];
         }
-        for (; c < A.ncta; c += 4) acc += __ldcg(p + (size_t)c * cs);
       }
       s_part[grp][col] = acc;
       __syncthreads();
-      if (grp == 0 && c0 + col < F.nc)
-        F.R[(size_t)row * F.nc + c0 + col] = (s_part[0][col] + s_part[1][col]) + (s_part[2][col] + s_part[3][col]);
+      if (grp == 0 && c0 + col < F.nc) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < FIN_GROUPS; ++q) t += s_part[q][col];
+        F.R[(size_t)row * F.nc + c0 + col] = t;
+      }
       __syncthreads();
     }
   }
