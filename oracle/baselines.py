@@ -182,4 +182,17 @@ def reference_rows(device, batch_small=4, batch_gpu=64, autocast=False, seed=369
     oG, oFD, oTD = mk(G), mk(FD), mk(TD)
     xd, yd = torch.rand(nd, 4, 64, 64, device=dev), torch.rand(nd, 4, 64, 64, device=dev)
     rows["R4_dcgan_adversarial_step"] = timed(lambda: dcgan_step(G, FD, TD, oG, oFD, oTD, xd, yd), nd)
+    if cuda:
+        # BASELINE config 4 (stress): UnetModel [2,128,128,4,8] -- one shared SmaAt-UNet per vertex in a Python loop
+        # (convolutional_gat/unet_model.py:22-29), full train step (train.py:129-133, :212), stock torch modules
+        unet = spec.SpecSmaAtUNet(4, 4).to(dev)
+        ou = torch.optim.Adam(unet.parameters(), lr=1e-3, weight_decay=0.01)
+        xu, yu = torch.rand(2, 128, 128, 4, 8, device=dev), torch.rand(2, 128, 128, 4, 8, device=dev)
+
+        def step_u():
+            ou.zero_grad()
+            spec.train_loss(spec.unet_model_forward(unet, xu), yu).backward()
+            ou.step()
+
+        rows["config4_unet_model_train_step"] = timed(step_u, 2)
     return rows
