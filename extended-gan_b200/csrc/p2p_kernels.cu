@@ -13,17 +13,19 @@
 // Epoch = the 1-based step counter; slots alternate by its parity, which is enough because a rank cannot be two
 // steps ahead of a peer (step e+1 needs that peer's words of step e+1, sent after it finished e), and a stale word in
 // the same parity slot carries epoch e-2.  The mailbox is zeroed once (epoch 0 never matches).
-// One CTA (the vector is small); larger models keep the NCCL all-reduce.
+// One cluster of `world` CTAs (the vector is small); larger models keep the NCCL all-reduce.
 //
 // Contract: every rank takes EXACTLY the same number of steps (the epoch is the step counter).  A rank that waits
-// ~3 s for a peer gives up: the whole CTA then SKIPS the parameter / m / v update of that step (all-or-nothing, so a
+// ~3 s for a peer gives up: the whole cluster then SKIPS the parameter / m / v update of that step (all-or-nothing, so a
 // replica is never updated from a partial or stale sum) and sets the time-out marker behind the mailbox, which
 // cgat.train_step.TrainStep polls and turns into a RuntimeError.
 #include "common.cuh"
+#include <cstdlib>
+#include <utility>
 
 namespace cgat {
 
-constexpr int P2P_THREADS = 1024;
+constexpr int P2P_THREADS = 256;  // per CTA; the kernel runs as one cluster of `world` CTAs
 constexpr int P2P_MAX_WORLD = 8;
 
 long long* get_debug_buffer();  // developer timeline (cgat_debug_timeline): 4 globaltimer stamps per step when set
@@ -44,12 +46,29 @@ __device__ __forceinline__ void st_word_sys(uint2* p, uint32_t bits, uint32_t ep
   const unsigned long long w = (unsigned long long)bits | ((unsigned long long)epoch << 32);
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the int at the same shared-memory address in CTA `cta` of this cluster (distributed shared memory)
+__device__ __forceinline__ int ld_dsmem_s32(const int* local, unsigned cta) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+  uint32_t remote;
+  int v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(a), "r"(cta));
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint2 ld_word_sys(const uint2* p) {
   unsigned long long w;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
   return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
 }
 
+// One CLUSTER of `world` CTAs (<= 8: the portable cluster size).  CTA c pushes the whole vector to peer c -- a single SM
+// sustains ~50 GB/s of remote 8-byte stores, so one CTA pushing to 8 peers took 1.8 us and the peer served last saw its
+// words that much later (8-GPU timeline: push 1.8, wait 5.2 us); eight SMs push in parallel -- and owns slice c of the
+// elements for the wait + rank-ordered sum + Adam.  All-or-nothing across the cluster: every CTA publishes whether it
+// timed out in its shared memory, one cluster barrier, every CTA reads all flags through distributed shared memory.
 __global__ void __launch_bounds__(P2P_THREADS)
 p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, long long n_pad, const float* __restrict__ g,
                           float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
@@ -59,27 +78,31 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
   // graph-resident form (cgat_p2p_allreduce_adam_graph): the step comes from a device counter of steps taken so far, which
   // this launch advances at its end, and the hyper-parameters from device memory (lr, beta1, beta2, eps, weight_decay:
   // a scheduler changes lr between replays); launched with programmatic dependent launch behind the gradient kernel
+  __shared__ int s_timed_out;
+  const int c = (int)blockIdx.x;  // = rank of this CTA in the cluster (grid = one cluster of `world` CTAs)
   griddep_wait();
   if (hyper != nullptr) { lr = hyper[0]; b1 = hyper[1]; b2 = hyper[2]; eps = hyper[3]; wd = hyper[4]; }
   const long long epoch = step_counter != nullptr ? *step_counter + 1 : (step_dev != nullptr ? *step_dev : step_host);
-  const bool stamp = dbg != nullptr && threadIdx.x == 0 && epoch < 4096;
+  const bool stamp = dbg != nullptr && c == 0 && threadIdx.x == 0 && epoch < 4096;
   if (stamp) dbg[epoch * 4 + 0] = p2p_now();
   const uint32_t ep = (uint32_t)epoch;
   const int par = (int)(epoch & 1);
   const int tid = threadIdx.x;
-  // 1. push {value, epoch} words: 8-byte stores, coalesced per peer
-  for (long long i = tid; i < n; i += P2P_THREADS) {
-    const uint32_t bits = __float_as_uint(g[i]);
-    for (int q = 0; q < world; ++q) st_word_sys(P.mailbox[q] + ((size_t)par * world + rank) * n_pad + i, bits, ep);
+  // 1. push {value, epoch} words to peer c: 8-byte stores, coalesced
+  {
+    uint2* dst = P.mailbox[c] + ((size_t)par * world + rank) * n_pad;
+    for (long long i = tid; i < n; i += P2P_THREADS) st_word_sys(dst + i, __float_as_uint(g[i]), ep);
   }
   if (stamp) dbg[epoch * 4 + 1] = p2p_now();
-  // 2. + 3. per element: wait for every source, rank-ordered sum, Adam
+  // 2. + 3. per element of this CTA's slice: wait for every source, rank-ordered sum, Adam
   const float step = (float)epoch;
   const float bc1 = 1.f - powf(b1, step);
   const float bc2 = 1.f - powf(b2, step);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const float gscale = 1.f / (float)world;
+  const long long chunk = ((n + world - 1) / world + 31) & ~31ll;
+  const long long lo = min(n, (long long)c * chunk), hi = min(n, lo + chunk);
   const uint2* mine = P.mailbox[rank] + (size_t)par * world * n_pad;
   const long long t0 = clock64();
   // 2a. wait for every word of this thread's elements; the rank-ordered sums of its first P2P_CACHE elements stay in
@@ -102,16 +125,22 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
   };
 #pragma unroll
   for (int s = 0; s < P2P_CACHE; ++s) {
-    const long long i = tid + (long long)s * P2P_THREADS;
-    cache[s] = i < n ? wait_sum(i) : 0.f;
+    const long long i = lo + tid + (long long)s * P2P_THREADS;
+    cache[s] = i < hi ? wait_sum(i) : 0.f;
   }
-  for (long long i = tid + (long long)P2P_CACHE * P2P_THREADS; i < n; i += P2P_THREADS) wait_sum(i);
-  // all-or-nothing: one late word anywhere in the vector and NO element of p / m / v is touched this step
-  if (__syncthreads_or(timed_out)) {
-    if (tid == 0) atomicExch(timeout_marker, 1u);
+  for (long long i = lo + tid + (long long)P2P_CACHE * P2P_THREADS; i < hi; i += P2P_THREADS) wait_sum(i);
+  // all-or-nothing over the whole cluster: one late word anywhere in the vector and NO element of p / m / v is touched
+  const int cta_timed_out = __syncthreads_or(timed_out);
+  if (tid == 0) s_timed_out = cta_timed_out;
+  cluster_sync_all();  // flags written (and: every CTA has read the step counter)
+  int any = 0;
+  for (int r = 0; r < world; ++r) any |= ld_dsmem_s32(&s_timed_out, (unsigned)r);
+  if (any) {
+    if (c == 0 && tid == 0) atomicExch(timeout_marker, 1u);
+    cluster_sync_all();  // (nobody leaves while a peer CTA may still read its flag)
     return;  // (the step counter stays: the host raises on the marker; nothing was updated)
   }
-  if (step_counter != nullptr && tid == 0) *step_counter = epoch;  // every thread has read it (the barrier above)
+  if (step_counter != nullptr && c == 0 && tid == 0) *step_counter = epoch;
   if (stamp) dbg[epoch * 4 + 2] = p2p_now();
   auto adam = [&](long long i, float gs) {
     const float pi = p[i];
@@ -125,15 +154,37 @@ p2p_allreduce_adam_kernel(const P2pPeers P, int rank, int world, long long n, lo
   };
 #pragma unroll
   for (int s = 0; s < P2P_CACHE; ++s) {
-    const long long i = tid + (long long)s * P2P_THREADS;
-    if (i < n) adam(i, cache[s]);
+    const long long i = lo + tid + (long long)s * P2P_THREADS;
+    if (i < hi) adam(i, cache[s]);
   }
-  for (long long i = tid + (long long)P2P_CACHE * P2P_THREADS; i < n; i += P2P_THREADS) {
+  for (long long i = lo + tid + (long long)P2P_CACHE * P2P_THREADS; i < hi; i += P2P_THREADS) {
     float gs = 0.f;
     for (int q = 0; q < world; ++q) gs += __uint_as_float(ld_word_sys(mine + (size_t)q * n_pad + i).x);
     adam(i, gs);
   }
   if (stamp) dbg[epoch * 4 + 3] = p2p_now();
+  cluster_sync_all();  // (nobody leaves while a peer CTA may still read its flag)
+}
+
+// launch as ONE cluster of `world` CTAs, optionally with programmatic dependent launch
+template <typename... Args>
+static cudaError_t p2p_launch(int world, bool pdl, cudaStream_t st, Args&&... args) {
+  static const bool no_pdl = std::getenv("CGAT_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)world);
+  cfg.blockDim = dim3(P2P_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)world;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && !no_pdl) ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, p2p_allreduce_adam_kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace cgat
@@ -162,10 +213,10 @@ extern "C" int cgat_p2p_allreduce_adam(const uint64_t* peer_mailboxes, int32_t r
     P.mailbox[q] = reinterpret_cast<uint2*>(peer_mailboxes[q]);
   }
   uint32_t* marker = reinterpret_cast<uint32_t*>(peer_mailboxes[rank] + (uint64_t)2 * world * n_pad * 8);
-  p2p_allreduce_adam_kernel<<<1, P2P_THREADS, 0, (cudaStream_t)stream>>>(P, rank, world, n, n_pad, grad, param, m, v,
-                                                                         (const long long*)step_dev, (long long)step_host, lr,
-                                                                         beta1, beta2, eps, weight_decay, marker, get_debug_buffer(),
-                                                                         nullptr, nullptr);
+  cudaError_t e = p2p_launch((int)world, false, (cudaStream_t)stream, P, (int)rank, (int)world, (long long)n, n_pad, grad, param, m,
+                             v, (const long long*)step_dev, (long long)step_host, lr, beta1, beta2, eps, weight_decay, marker,
+                             get_debug_buffer(), (long long*)nullptr, (const float*)nullptr);
+  if (e != cudaSuccess) return fail((int)e, "p2p_allreduce_adam_kernel: %s", cudaGetErrorString(e));
   return check_launch("p2p_allreduce_adam_kernel");
 }
 
@@ -183,9 +234,9 @@ extern "C" int cgat_p2p_allreduce_adam_graph(const uint64_t* peer_mailboxes, int
     P.mailbox[q] = reinterpret_cast<uint2*>(peer_mailboxes[q]);
   }
   uint32_t* marker = reinterpret_cast<uint32_t*>(peer_mailboxes[rank] + (uint64_t)2 * world * n_pad * 8);
-  cudaError_t e = launch_pdl(p2p_allreduce_adam_kernel, dim3(1), dim3(P2P_THREADS), 0, (cudaStream_t)stream, P, (int)rank,
-                             (int)world, (long long)n, n_pad, grad, param, m, v, (const long long*)nullptr, (long long)0, 0.f, 0.f,
-                             0.f, 0.f, 0.f, marker, get_debug_buffer(), (long long*)step_counter, hyper);
+  cudaError_t e = p2p_launch((int)world, true, (cudaStream_t)stream, P, (int)rank, (int)world, (long long)n, n_pad, grad, param, m,
+                             v, (const long long*)nullptr, (long long)0, 0.f, 0.f, 0.f, 0.f, 0.f, marker, get_debug_buffer(),
+                             (long long*)step_counter, hyper);
   if (e != cudaSuccess) return fail((int)e, "p2p_allreduce_adam_kernel: %s", cudaGetErrorString(e));
   return check_launch("p2p_allreduce_adam_kernel");
 }
