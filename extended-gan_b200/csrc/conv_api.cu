@@ -29,6 +29,7 @@ int conv_dw3x3_served(const cgat_conv_desc* d);
 int conv_dw3x3_launch(int which, const cgat_conv_desc*, const void*, const void*, void*, float*, const float*, cudaStream_t);
 int conv_wgrad_small_served(const cgat_conv_desc* d);
 int conv_wgrad_small_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
+int conv_dbias_ws_launch(const cgat_conv_desc*, const void*, float*, void*, cudaStream_t);
 int conv_small_served(const cgat_conv_desc* d, int which);
 int conv_small_launch(int which, const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int conv_gemm_served(const cgat_conv_desc* d);
@@ -115,7 +116,7 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
   if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
   if (use_big(d, 2)) {
     if (int rc = conv_big_wgrad_launch(d, x, dy, dw, workspace, (cudaStream_t)stream)) return rc;
-    return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
+    return dbias ? conv_dbias_ws_launch(d, dy, dbias, workspace, (cudaStream_t)stream) : 0;
   }
   if (int rc = tc_ready(d, 2, workspace)) return rc;
   return conv_wgrad_tc_launch(d, x, dy, dw, dbias, workspace, (cudaStream_t)stream);

@@ -7,6 +7,7 @@
 // explicitly so that PyTorch's asymmetric padding="same" for even kernels (left 1 / right 2 for k=4,
 // dcgan/model.py:61-72) is expressible.
 #include "common.cuh"
+#include "ew_vec.cuh"
 
 namespace cgat {
 
@@ -183,7 +184,97 @@ __global__ void __launch_bounds__(CD_THREADS) conv_dbias_direct(const T* __restr
   }
 }
 
+// ---- dbias = column sums of dy [M][cout], coalesced and deterministic: the kernel above walks one channel per block with a
+// stride of cout elements (57 us for the 33 MB dy of a UNet pointwise conv); here a CTA owns a slab of pixels, a thread
+// (pixel lane, group of V channels) keeps DB_U 16-byte loads in flight, the lanes are folded through shared memory, every CTA
+// writes ONE row of partial sums into the caller's workspace and a second tiny launch adds the rows in a fixed order.
+constexpr int DB_THREADS = 256, DB_U = 4, DB_MAX_CTAS = 296;
+
+template <typename T, int V>
+__global__ void __launch_bounds__(DB_THREADS) dbias_partial_kernel(const T* __restrict__ dy, float* __restrict__ part,
+                                                                     long long M, int cout, int pix_per_cta) {
+  __shared__ float s_part[DB_THREADS * (V > 1 ? V : 1)];
+  const int groups = cout / V;
+  const int cg = groups >= DB_THREADS ? DB_THREADS : groups;
+  int lanes = 1;
+  while (2 * lanes * cg <= DB_THREADS) lanes *= 2;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta, p1 = min(M, p0 + pix_per_cta);
+  for (int g0 = 0; g0 < groups; g0 += cg) {
+    const int g = g0 + (int)(threadIdx.x % cg), lane = threadIdx.x / cg;
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    if (g < groups && lane < lanes) {
+      for (long long pb = p0 + lane; pb < p1; pb += (long long)lanes * DB_U) {
+        NaRaw<T, V> r[DB_U];
+#pragma unroll
+        for (int q = 0; q < DB_U; ++q) {
+          const long long p = pb + (long long)q * lanes;
+          if (p < p1) r[q] = na_load_raw<T, V>(dy + p * cout + (long long)g * V);
+        }
+#pragma unroll
+        for (int q = 0; q < DB_U; ++q) {
+          if (pb + (long long)q * lanes >= p1) continue;
+          float v[V];
+          na_unpack<T, V>(r[q], v);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[i] += v[i];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) s_part[threadIdx.x * V + i] = acc[i];
+    __syncthreads();
+    for (int half = lanes >> 1; half > 0; half >>= 1) {
+      if (lane < half) {
+        const int other = (threadIdx.x + half * cg) * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) s_part[threadIdx.x * V + i] += s_part[other + i];
+      }
+      __syncthreads();
+    }
+    if ((int)threadIdx.x < cg && g0 + (int)threadIdx.x < groups) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) part[(long long)blockIdx.x * cout + (g0 + threadIdx.x) * V + i] = s_part[threadIdx.x * V + i];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(DB_THREADS) dbias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int ctas,
+                                                                   int cout) {
+  const int co = blockIdx.x * DB_THREADS + threadIdx.x;
+  if (co >= cout) return;
+  float v = 0.f;
+  for (int c = 0; c < ctas; ++c) v += part[(long long)c * cout + co];
+  db[co] = v;
+}
+
+size_t conv_dbias_workspace(const cgat_conv_desc* d) { return (size_t)DB_MAX_CTAS * d->cout * sizeof(float); }
+
 int conv_dbias_launch(const cgat_conv_desc* d, const void* dy, float* dbias, cudaStream_t st);
+// the same with a caller workspace of conv_dbias_workspace(d) bytes (NULL: the strided kernel)
+int conv_dbias_ws_launch(const cgat_conv_desc* d, const void* dy, float* dbias, void* workspace, cudaStream_t st) {
+  if (!workspace || !aligned16(workspace)) return conv_dbias_launch(d, dy, dbias, st);
+  const long long M = (long long)d->n * d->ho * d->wo;
+  const int v = ew_vec(d->dtype, d->cout, dy);
+  const int groups = d->cout / v, cg = groups >= DB_THREADS ? DB_THREADS : groups;
+  int lanes = 1;
+  while (2 * lanes * cg <= DB_THREADS) lanes *= 2;
+  const int ppc_min = lanes * DB_U;
+  long long ctas = (M + ppc_min - 1) / ppc_min;
+  if (ctas > DB_MAX_CTAS) ctas = DB_MAX_CTAS;
+  const int ppc = (int)((M + ctas - 1) / ctas);
+  ctas = (M + ppc - 1) / ppc;
+  float* part = (float*)workspace;
+#define DB_GO(T, V) dbias_partial_kernel<T, V><<<(unsigned)ctas, DB_THREADS, 0, st>>>((const T*)dy, part, M, d->cout, ppc)
+  if (d->dtype == CGAT_F32) { if (v == 4) DB_GO(float, 4); else DB_GO(float, 1); }
+  else { if (v == 8) DB_GO(__nv_bfloat16, 8); else DB_GO(__nv_bfloat16, 1); }
+#undef DB_GO
+  dbias_final_kernel<<<(d->cout + DB_THREADS - 1) / DB_THREADS, DB_THREADS, 0, st>>>(part, dbias, (int)ctas, d->cout);
+  return check_launch("dbias kernels");
+}
+
 
 static int grid_for(long long total) {
   long long g = (total + CD_THREADS - 1) / CD_THREADS;

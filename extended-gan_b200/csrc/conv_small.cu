@@ -1,5 +1,5 @@
 // Dense stride-1 convs with FEW channels on both sides (the DCGAN generator's ends, dcgan/model.py:19-34: 4 -> 32 and
-// 4 -> 4 channels with k = 4 "same" padding at 64 x 64) -- fprop, and dgrad as the same kernel over dy with the taps
+// 4 -> 4 channels with k = 4 "same" padding at 64 x 64; the 7x7 2 -> 1 conv of the SmaAt-UNet's CBAM spatial gates) -- fprop, and dgrad as the same kernel over dy with the taps
 // flipped and the padding mirrored.  The implicit-GEMM tiles (conv_gemm.cu, 64 pixels x 64 couts x 16) waste 15/16 of a
 // tile on 4 output channels and ran these at 130-165 us per launch; here a thread owns PX consecutive output pixels of a
 // row and ALL output channels: per tap one vector load of the pixel's CI input channels, CI x CO FMAs against weights that
@@ -22,7 +22,15 @@ __device__ __forceinline__ float cs_act(float v, int act) {
 
 template <typename T, int C>
 __device__ __forceinline__ void cs_load(const T* p, float (&v)[C]) {
-  if constexpr (sizeof(T) == 4) {
+  if constexpr (C == 1) {
+    v[0] = DT<T>::to_f(p[0]);
+  } else if constexpr (C == 2 && sizeof(T) == 4) {
+    const float2 f = *reinterpret_cast<const float2*>(p);
+    v[0] = f.x; v[1] = f.y;
+  } else if constexpr (C == 2) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+    v[0] = __uint_as_float(u << 16); v[1] = __uint_as_float(u & 0xffff0000u);
+  } else if constexpr (sizeof(T) == 4) {
 #pragma unroll
     for (int q = 0; q < C / 4; ++q) {
       const float4 f = reinterpret_cast<const float4*>(p)[q];
@@ -47,7 +55,14 @@ __device__ __forceinline__ void cs_load(const T* p, float (&v)[C]) {
 }
 template <typename T, int C>
 __device__ __forceinline__ void cs_store(T* p, const float (&v)[C]) {
-  if constexpr (sizeof(T) == 4) {
+  if constexpr (C == 1) {
+    p[0] = DT<T>::from_f(v[0]);
+  } else if constexpr (C == 2 && sizeof(T) == 4) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  } else if constexpr (C == 2) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&h);
+  } else if constexpr (sizeof(T) == 4) {
 #pragma unroll
     for (int q = 0; q < C / 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   } else {
@@ -115,10 +130,15 @@ __global__ void __launch_bounds__(CS_THREADS) conv_small_kernel(const T* __restr
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci) {
           float wv[CO];
+          if constexpr (CO % 4 == 0) {
 #pragma unroll
-          for (int q = 0; q < CO / 4; ++q) {
-            const float4 f = reinterpret_cast<const float4*>(wt + ci * CO)[q];
-            wv[4 * q] = f.x; wv[4 * q + 1] = f.y; wv[4 * q + 2] = f.z; wv[4 * q + 3] = f.w;
+            for (int q = 0; q < CO / 4; ++q) {
+              const float4 f = reinterpret_cast<const float4*>(wt + ci * CO)[q];
+              wv[4 * q] = f.x; wv[4 * q + 1] = f.y; wv[4 * q + 2] = f.z; wv[4 * q + 3] = f.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < CO; ++q) wv[q] = wt[ci * CO + q];
           }
 #pragma unroll
           for (int p = 0; p < PX; ++p)
@@ -138,6 +158,7 @@ __global__ void __launch_bounds__(CS_THREADS) conv_small_kernel(const T* __restr
 }
 
 static bool cs_pair(int ci, int co) {
+  if ((ci == 2 && co == 1) || (ci == 1 && co == 2)) return true;  // CBAM's 7x7 spatial-gate conv (2 -> 1) and its dgrad
   return (ci == 4 || ci == 8) && (co == 4 || co == 8 || co == 16 || co == 32);
 }
 
@@ -163,7 +184,9 @@ static int cs_launch(int ci, int co, const T* in, const T* w, const float* bias,
     conv_small_kernel<T, CI, CO, PX><<<(unsigned)ctas, CS_THREADS, smem, st>>>(in, w, bias, out, n, hi, wi, ho, wo, kh, kw, pt, \
                                                                                pl, act, flip);                         \
   } while (0)
-  if (ci == 4 && co == 4) CS_GO(4, 4, 4);
+  if (ci == 2 && co == 1) CS_GO(2, 1, 4);
+  else if (ci == 1 && co == 2) CS_GO(1, 2, 4);
+  else if (ci == 4 && co == 4) CS_GO(4, 4, 4);
   else if (ci == 4 && co == 8) CS_GO(4, 8, 4);
   else if (ci == 4 && co == 16) CS_GO(4, 16, 2);
   else if (ci == 4 && co == 32) CS_GO(4, 32, 2);

@@ -469,12 +469,15 @@ int conv_big_wgrad_small_ok(const cgat_conv_desc* d) {
   return d->cin >= 16 && d->cout >= 8;
 }
 
+size_t conv_dbias_workspace(const cgat_conv_desc* d);
 size_t conv_big_workspace(const cgat_conv_desc* d, int which) {
   if (!conv_big_supported(d, which) && !(which == 2 && conv_big_wgrad_small_ok(d))) return 0;
   if (which == 0) return 0;
   if (which == 1) return (size_t)d->kh * d->kw * d->cin * d->cout * 2;
   const int splits = wgrad_splits(d, nullptr);
-  return splits > 1 ? (size_t)splits * d->cout * d->kh * d->kw * d->cin * 4 : 0;
+  const size_t part = splits > 1 ? (size_t)splits * d->cout * d->kh * d->kw * d->cin * 4 : 0;
+  const size_t db = conv_dbias_workspace(d);  // the bias gradient's partial rows reuse the workspace after the wgrad reduction
+  return part > db ? part : db;
 }
 
 // input [n][hi][wi][gk] -> output [n][hout][wout][gn]; weights [gn][taps][gk] bf16

@@ -18,6 +18,8 @@ CASES = [
     (3, 45, 37, 4, 8, 3, (1, 1, 1, 1), 2),    # ragged rows (37 % 4 != 0), LeakyReLU
     (2, 19, 23, 8, 16, 5, (2, 2, 2, 2), 0),
     (1, 9, 7, 4, 16, 1, (0, 0, 0, 0), 0),
+    (3, 32, 32, 2, 1, 7, (3, 3, 3, 3), 0),    # CBAM spatial gate conv (no bias in the model; the kernel takes one)
+    (2, 17, 13, 2, 1, 7, (3, 3, 3, 3), 0),
 ]
 
 
