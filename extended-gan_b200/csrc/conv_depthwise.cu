@@ -12,6 +12,8 @@ namespace cgat {
 
 constexpr int DWK_THREADS = 256;
 constexpr int DWK_TAPS = 9;
+constexpr int DWK_TW = 8;  // pixel-tile width of the fprop / dgrad kernels (the height follows the channel count)
+constexpr int DWK_PX = 4;  // output pixels per thread (a strip of a row)
 
 template <typename T, int N> struct Vec;
 template <int N> struct Vec<float, N> {
@@ -76,76 +78,132 @@ __device__ __forceinline__ void dwk_stage_weights(const T* __restrict__ w, float
   __syncthreads();
 }
 
-template <typename T, int M>
+// IT: the integer type of the index arithmetic -- unsigned when every element offset fits 31 bits (the host checks): the
+// three 64-bit divisions per output octet of the first version cost more instructions than the nine taps.
+//
+// Thread = (channel octet, STRIP of DWK_PX consecutive output pixels of a row): per kernel row the strip's DWK_PX + 2 input
+// pixels are loaded ONCE and every tap's weights once, where the one-pixel-per-thread version issued 9 loads + 18 shared
+// loads per pixel and ran at 97 % of the L1 pipe with DRAM at 7 % (ncu, profiles/r2z_depthwise.txt).  A CTA walks tiles of
+// DWK_TW x th_rows pixels (octets of a strip on consecutive threads, then the strips of a tile row, then the rows).
+template <typename T, int M, typename IT>
 __global__ void __launch_bounds__(DWK_THREADS) dw3x3_fprop_kernel(const cgat_conv_desc d, const T* __restrict__ x,
                                                                   const T* __restrict__ w, const float* __restrict__ bias,
-                                                                  T* __restrict__ y) {
+                                                                  T* __restrict__ y, int th_rows) {
   extern __shared__ float sw[];
   dwk_stage_weights(w, sw, d.cout);
   const int oct = d.cout / 8;
-  const long long total = (long long)d.n * d.ho * d.wo * oct;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(idx % oct);
-    const long long pix = idx / oct;
-    const int wo = (int)(pix % d.wo), ho = (int)((pix / d.wo) % d.ho), n = (int)(pix / ((long long)d.wo * d.ho));
+  constexpr int SPT = DWK_TW / DWK_PX;  // strips per tile row
+  const int tiles_w = (d.wo + DWK_TW - 1) / DWK_TW, tiles_h = (d.ho + th_rows - 1) / th_rows;
+  const IT n_tiles = (IT)d.n * tiles_h * tiles_w, per_tile = (IT)SPT * th_rows * oct;
+  for (IT tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  for (IT r = threadIdx.x; r < per_tile; r += blockDim.x) {
+    const int tw = (int)(tile % (IT)tiles_w);
+    const IT trest = tile / (IT)tiles_w;
+    const int th = (int)(trest % (IT)tiles_h), n = (int)(trest / (IT)tiles_h);
+    const int o = (int)(r % (IT)oct);
+    const int q = (int)(r / (IT)oct);
+    const int wo0 = tw * DWK_TW + (q % SPT) * DWK_PX, ho = th * th_rows + q / SPT;
+    if (wo0 >= d.wo || ho >= d.ho) continue;
     const int co0 = o * 8, ci0 = co0 / M;
-    float acc[8];
+    float acc[DWK_PX][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[co0 + j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float b = bias ? bias[co0 + j] : 0.f;
+#pragma unroll
+      for (int px = 0; px < DWK_PX; ++px) acc[px][j] = b;
+    }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = ho + kh - d.pad_top;
       if (hi < 0 || hi >= d.h) continue;
+      float xv[DWK_PX + 2][8 / M];
+      const T* xrow = x + (((IT)n * d.h + hi) * d.w) * d.cin + ci0;
+#pragma unroll
+      for (int c = 0; c < DWK_PX + 2; ++c) {
+        const int wi = wo0 + c - d.pad_left;
+        if (wi >= 0 && wi < d.w) {
+          Vec<T, 8 / M>::load(xrow + (IT)wi * d.cin, xv[c]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8 / M; ++j) xv[c][j] = 0.f;
+        }
+      }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int wi = wo + kw - d.pad_left;
-        if (wi < 0 || wi >= d.w) continue;
-        float xv[8 / M], wv[8];
-        Vec<T, 8 / M>::load(x + (((long long)n * d.h + hi) * d.w + wi) * d.cin + ci0, xv);
+        float wv[8];
         Vec<float, 8>::load(sw + (kh * 3 + kw) * d.cout + co0, wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv[j / M], wv[j], acc[j]);
+        for (int px = 0; px < DWK_PX; ++px)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[px][j] = fmaf(xv[px + kw][j / M], wv[j], acc[px][j]);
       }
     }
+    T* yrow = y + (((IT)n * d.ho + ho) * d.wo) * d.cout + co0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = dwk_act(acc[j], d.act);
-    Vec<T, 8>::store(y + pix * d.cout + co0, acc);
+    for (int px = 0; px < DWK_PX; ++px) {
+      if (wo0 + px >= d.wo) continue;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[px][j] = dwk_act(acc[px][j], d.act);
+      Vec<T, 8>::store(yrow + (IT)(wo0 + px) * d.cout, acc[px]);
+    }
   }
 }
 
-template <typename T, int M>
+// dgrad: dx[hi][wi][ci] = sum_{kh,kw} dy[hi + pad_top - kh][wi + pad_left - kw][co] * w[co][kh][kw]; same strips over dx
+template <typename T, int M, typename IT>
 __global__ void __launch_bounds__(DWK_THREADS) dw3x3_dgrad_kernel(const cgat_conv_desc d, const T* __restrict__ dy,
-                                                                  const T* __restrict__ w, T* __restrict__ dx) {
+                                                                  const T* __restrict__ w, T* __restrict__ dx, int th_rows) {
   extern __shared__ float sw[];
   dwk_stage_weights(w, sw, d.cout);
   const int oct = d.cout / 8;
-  const long long total = (long long)d.n * d.h * d.w * oct;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int o = (int)(idx % oct);
-    const long long pix = idx / oct;
-    const int wi = (int)(pix % d.w), hi = (int)((pix / d.w) % d.h), n = (int)(pix / ((long long)d.w * d.h));
+  constexpr int SPT = DWK_TW / DWK_PX;
+  const int tiles_w = (d.w + DWK_TW - 1) / DWK_TW, tiles_h = (d.h + th_rows - 1) / th_rows;
+  const IT n_tiles = (IT)d.n * tiles_h * tiles_w, per_tile = (IT)SPT * th_rows * oct;
+  for (IT tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  for (IT r = threadIdx.x; r < per_tile; r += blockDim.x) {
+    const int tw = (int)(tile % (IT)tiles_w);
+    const IT trest = tile / (IT)tiles_w;
+    const int th = (int)(trest % (IT)tiles_h), n = (int)(trest / (IT)tiles_h);
+    const int o = (int)(r % (IT)oct);
+    const int q = (int)(r / (IT)oct);
+    const int wi0 = tw * DWK_TW + (q % SPT) * DWK_PX, hi = th * th_rows + q / SPT;
+    if (wi0 >= d.w || hi >= d.h) continue;
     const int co0 = o * 8, ci0 = co0 / M;
-    float acc[8 / M];
+    float acc[DWK_PX][8 / M];
 #pragma unroll
-    for (int j = 0; j < 8 / M; ++j) acc[j] = 0.f;
+    for (int px = 0; px < DWK_PX; ++px)
+#pragma unroll
+      for (int j = 0; j < 8 / M; ++j) acc[px][j] = 0.f;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int ho = hi + d.pad_top - kh;
       if (ho < 0 || ho >= d.ho) continue;
+      float gv[DWK_PX + 2][8];  // column c: wo = wi0 + pad_left - 2 + c  (pixel px, tap kw reads c = px + 2 - kw)
+      const T* grow = dy + (((IT)n * d.ho + ho) * d.wo) * d.cout + co0;
+#pragma unroll
+      for (int c = 0; c < DWK_PX + 2; ++c) {
+        const int wo = wi0 + d.pad_left - 2 + c;
+        if (wo >= 0 && wo < d.wo) {
+          Vec<T, 8>::load(grow + (IT)wo * d.cout, gv[c]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gv[c][j] = 0.f;
+        }
+      }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int wo = wi + d.pad_left - kw;
-        if (wo < 0 || wo >= d.wo) continue;
-        float gv[8], wv[8];
-        Vec<T, 8>::load(dy + (((long long)n * d.ho + ho) * d.wo + wo) * d.cout + co0, gv);
+        float wv[8];
         Vec<float, 8>::load(sw + (kh * 3 + kw) * d.cout + co0, wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j / M] = fmaf(gv[j], wv[j], acc[j / M]);
+        for (int px = 0; px < DWK_PX; ++px)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[px][j / M] = fmaf(gv[px + 2 - kw][j], wv[j], acc[px][j / M]);
       }
     }
-    Vec<T, 8 / M>::store(dx + pix * d.cin + ci0, acc);
+    T* drow = dx + (((IT)n * d.h + hi) * d.w) * d.cin + ci0;
+#pragma unroll
+    for (int px = 0; px < DWK_PX; ++px)
+      if (wi0 + px < d.w) Vec<T, 8 / M>::store(drow + (IT)(wi0 + px) * d.cin, acc[px]);
   }
 }
 
@@ -173,8 +231,11 @@ __global__ void __launch_bounds__(DWK_THREADS) dw3x3_wgrad_kernel(const cgat_con
     for (int t = 0; t < DWK_TAPS; ++t) acc[t][j] = 0.f;
   }
   if (co0 < d.cout) {
-    for (long long m = p0 + pl; m < p1; m += pl_n) {
-      const int wo = (int)(m % d.wo), ho = (int)((m / d.wo) % d.ho), n = (int)(m / ((long long)d.wo * d.ho));
+    // pixel coordinates are carried from pixel to pixel (one division per thread, not three per pixel)
+    long long m = p0 + pl;
+    int wo = (int)(m % d.wo), ho = (int)((m / d.wo) % d.ho), n = (int)(m / ((long long)d.wo * d.ho));
+    const int s_wo = pl_n % d.wo, s_row = pl_n / d.wo;  // pl_n pixels = s_row rows + s_wo columns
+    for (; m < p1; m += pl_n) {
       float gv[8];
       Vec<T, 8>::load(dy + m * d.cout + co0, gv);
 #pragma unroll
@@ -193,6 +254,10 @@ __global__ void __launch_bounds__(DWK_THREADS) dw3x3_wgrad_kernel(const cgat_con
           for (int j = 0; j < 8; ++j) acc[kh * 3 + kw][j] = fmaf(gv[j], xv[j / M], acc[kh * 3 + kw][j]);
         }
       }
+      wo += s_wo;
+      ho += s_row;
+      if (wo >= d.wo) { wo -= d.wo; ++ho; }
+      while (ho >= d.ho) { ho -= d.ho; ++n; }
     }
   }
   // lanes of a warp that own the same octet (ol < 32: lane = pl*ol + ot) merge by shuffles first, so the shared
@@ -239,24 +304,30 @@ static int dw_launch_t(int which, const cgat_conv_desc* d, const void* a, const 
   const size_t wsm = (size_t)d->cout * DWK_TAPS * sizeof(float);
   const int oct = d->cout / 8;
   if (which == 0 || which == 1) {
-    const long long total = (long long)d->n * (which == 0 ? d->ho * d->wo : d->h * d->w) * oct;
-    long long blocks = (total + DWK_THREADS - 1) / DWK_THREADS;
+    // tile height: at least 4 rows, and at least four passes of the CTA's 256 threads per tile
+    int th_rows = (4 * DWK_THREADS + (DWK_TW / DWK_PX) * oct - 1) / ((DWK_TW / DWK_PX) * oct);
+    th_rows = th_rows < 4 ? 4 : (th_rows > 64 ? 64 : th_rows);
+    const int oh = which == 0 ? d->ho : d->h, ow = which == 0 ? d->wo : d->w;
+    long long blocks = (long long)d->n * ((oh + th_rows - 1) / th_rows) * ((ow + DWK_TW - 1) / DWK_TW);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (which == 0) {
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(dw3x3_fprop_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
-      }
-      dw3x3_fprop_kernel<T, M><<<(int)blocks, DWK_THREADS, wsm, st>>>(*d, (const T*)a, (const T*)b, bias, (T*)c);
-      return check_launch("dw3x3_fprop_kernel");
-    }
+    // 32-bit index arithmetic when every element offset (and the grid-stride overshoot) fits 31 bits
+    const long long elems = (long long)d->n * (d->h > d->ho ? d->h : d->ho) * (d->w > d->wo ? d->w : d->wo) * d->cout;
+    const bool small = elems < (1ll << 31) - (1 << 20);
     static bool attr = false;
     if (!attr) {
-      cudaFuncSetAttribute(dw3x3_dgrad_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(dw3x3_fprop_kernel<T, M, unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(dw3x3_fprop_kernel<T, M, long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(dw3x3_dgrad_kernel<T, M, unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(dw3x3_dgrad_kernel<T, M, long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       attr = true;
     }
-    dw3x3_dgrad_kernel<T, M><<<(int)blocks, DWK_THREADS, wsm, st>>>(*d, (const T*)a, (const T*)b, (T*)c);
+    if (which == 0) {
+      if (small) dw3x3_fprop_kernel<T, M, unsigned><<<(int)blocks, DWK_THREADS, wsm, st>>>(*d, (const T*)a, (const T*)b, bias, (T*)c, th_rows);
+      else dw3x3_fprop_kernel<T, M, long long><<<(int)blocks, DWK_THREADS, wsm, st>>>(*d, (const T*)a, (const T*)b, bias, (T*)c, th_rows);
+      return check_launch("dw3x3_fprop_kernel");
+    }
+    if (small) dw3x3_dgrad_kernel<T, M, unsigned><<<(int)blocks, DWK_THREADS, wsm, st>>>(*d, (const T*)a, (const T*)b, (T*)c, th_rows);
+    else dw3x3_dgrad_kernel<T, M, long long><<<(int)blocks, DWK_THREADS, wsm, st>>>(*d, (const T*)a, (const T*)b, (T*)c, th_rows);
     return check_launch("dw3x3_dgrad_kernel");
   }
   // wgrad: a = x, b = dy, c = dw
