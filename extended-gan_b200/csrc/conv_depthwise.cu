@@ -7,6 +7,7 @@
 // its 8 weights of a tap with vector loads, and the nine taps re-read x through L1/L2.  The generic direct
 // kernels (conv_direct.cu: one thread per output element, 2-byte accesses) stay for every other grouped shape.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace cgat {
 
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(DWK_THREADS) dw3x3_dgrad_kernel(const cgat_con
 // wgrad + dbias: thread = (channel octet o, pixel lane pl); 72 + 8 partial sums in registers over the CTA's pixel
 // slab, merged through shared-memory atomics, one global atomicAdd per value per CTA (dw / dbias zeroed by the
 // launcher).  blockIdx.y walks octet groups when cout/8 > 256.
-template <typename T, int M>
+template <typename T, int M, bool STRIPS>
 __global__ void __launch_bounds__(DWK_THREADS) dw3x3_wgrad_kernel(const cgat_conv_desc d, const T* __restrict__ x,
                                                                   const T* __restrict__ dy, float* __restrict__ dw,
                                                                   float* __restrict__ dbias, int ol, long long per) {
@@ -231,6 +232,49 @@ __global__ void __launch_bounds__(DWK_THREADS) dw3x3_wgrad_kernel(const cgat_con
     for (int t = 0; t < DWK_TAPS; ++t) acc[t][j] = 0.f;
   }
   if (co0 < d.cout) {
+    if constexpr (STRIPS) {
+      // STRIPS of DWK_PX consecutive pixels of a row per lane and trip (host: wo % DWK_PX == 0, slabs strip-aligned): the
+      // strip's DWK_PX + 2 input pixels of a kernel row are loaded once -- 5.5 loads per pixel instead of 10
+      long long m = p0 + (long long)pl * DWK_PX;
+      int wo = (int)(m % d.wo), ho = (int)((m / d.wo) % d.ho), n = (int)(m / ((long long)d.wo * d.ho));
+      const int step = pl_n * DWK_PX, s_wo = step % d.wo, s_row = step / d.wo;
+      for (; m < p1; m += step) {
+        float gv[DWK_PX][8];
+#pragma unroll
+        for (int px = 0; px < DWK_PX; ++px) {
+          Vec<T, 8>::load(dy + (m + px) * d.cout + co0, gv[px]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) accb[j] += gv[px][j];
+        }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int hi = ho + kh - d.pad_top;
+          if (hi < 0 || hi >= d.h) continue;
+          float xv[DWK_PX + 2][8 / M];
+          const T* xrow = x + (((long long)n * d.h + hi) * d.w) * d.cin + ci0;
+#pragma unroll
+          for (int c = 0; c < DWK_PX + 2; ++c) {
+            const int wi = wo + c - d.pad_left;
+            if (wi >= 0 && wi < d.w) {
+              Vec<T, 8 / M>::load(xrow + (long long)wi * d.cin, xv[c]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8 / M; ++j) xv[c][j] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int px = 0; px < DWK_PX; ++px)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[kh * 3 + kw][j] = fmaf(gv[px][j], xv[px + kw][j / M], acc[kh * 3 + kw][j]);
+        }
+        wo += s_wo;
+        ho += s_row;
+        if (wo >= d.wo) { wo -= d.wo; ++ho; }
+        while (ho >= d.ho) { ho -= d.ho; ++n; }
+      }
+    } else {
     // pixel coordinates are carried from pixel to pixel (one division per thread, not three per pixel)
     long long m = p0 + pl;
     int wo = (int)(m % d.wo), ho = (int)((m / d.wo) % d.ho), n = (int)(m / ((long long)d.wo * d.ho));
@@ -258,6 +302,7 @@ __global__ void __launch_bounds__(DWK_THREADS) dw3x3_wgrad_kernel(const cgat_con
       ho += s_row;
       if (wo >= d.wo) { wo -= d.wo; ++ho; }
       while (ho >= d.ho) { ho -= d.ho; ++n; }
+    }
     }
   }
   // lanes of a warp that own the same octet (ol < 32: lane = pl*ol + ot) merge by shuffles first, so the shared
@@ -340,17 +385,27 @@ static int dw_launch_t(int which, const cgat_conv_desc* d, const void* a, const 
   const long long min_per = (long long)pl_n * 16;  // at least 16 pixels per lane before paying the atomics
   if (slabs > (Mpix + min_per - 1) / min_per) slabs = (Mpix + min_per - 1) / min_per;
   if (slabs < 1) slabs = 1;
-  const long long per = (Mpix + slabs - 1) / slabs;
+  long long per = (Mpix + slabs - 1) / slabs;
+  // strips of DWK_PX pixels per lane when the rows allow it (the slabs then hold whole strips) -- for fp32 activations only:
+  // the strip kernel needs 160-250 registers (one CTA per SM); measured on UnetModel [2,128,128,4,8]: fp32 17.9 -> 17.3 ms,
+  // bf16 8.6 -> 9.0 ms (its loads are half the size, the lost occupancy costs more than the saved requests)
+  const bool strips = d->wo % DWK_PX == 0 && sizeof(T) == 4 && !getenv("CGAT_DW_NO_STRIPS");
+  if (strips) per = (per + DWK_PX - 1) / DWK_PX * DWK_PX;
   cudaMemsetAsync(c, 0, sizeof(float) * (size_t)d->cout * DWK_TAPS, st);
   if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)d->cout, st);
   dim3 grid((unsigned)((Mpix + per - 1) / per), (unsigned)ygroups);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(dw3x3_wgrad_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(dw3x3_wgrad_kernel<T, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(dw3x3_wgrad_kernel<T, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
-  dw3x3_wgrad_kernel<T, M><<<grid, DWK_THREADS, (size_t)ol * 80 * sizeof(float), st>>>(*d, (const T*)a, (const T*)b,
-                                                                                      (float*)c, dbias, ol, per);
+  if (strips)
+    dw3x3_wgrad_kernel<T, M, true><<<grid, DWK_THREADS, (size_t)ol * 80 * sizeof(float), st>>>(*d, (const T*)a, (const T*)b,
+                                                                                              (float*)c, dbias, ol, per);
+  else
+    dw3x3_wgrad_kernel<T, M, false><<<grid, DWK_THREADS, (size_t)ol * 80 * sizeof(float), st>>>(*d, (const T*)a, (const T*)b,
+                                                                                               (float*)c, dbias, ol, per);
   return check_launch("dw3x3_wgrad_kernel");
 }
 
