@@ -13,7 +13,13 @@ from torch import nn, optim
 def make_optimizers(netG, netFD, netTD, lr=0.0002, beta1=0.5, capturable=False):
     """``optim.Adam(net.parameters(), lr=params["lr"], betas=(params["beta1"], 0.999))`` (reference :227-236).
     ``capturable=True`` keeps the step counters on the device so the step can live in a CUDA graph."""
-    mk = lambda net: optim.Adam(net.parameters(), lr=lr, betas=(beta1, 0.999), capturable=capturable)
+    def mk(net):
+        params = list(net.parameters())
+        # graph-resident steps on the GPU use torch's FUSED Adam (one multi-tensor kernel per step instead of ~6 foreach
+        # kernels: 0.35 -> 0.06 ms of the 5 ms step for the three optimisers); same update rule
+        fused = bool(capturable and params and all(p.is_cuda for p in params))
+        return optim.Adam(params, lr=lr, betas=(beta1, 0.999), capturable=capturable, **({"fused": True} if fused else {}))
+
     return mk(netG), mk(netFD), mk(netTD)
 
 
