@@ -89,6 +89,7 @@ SIGNATURES = {
     "cgat_conv2d_wgrad": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _I, _P, _P],
     "cgat_conv_tc_supported": [ctypes.POINTER(ConvDesc), _I],
     "cgat_conv_workspace_bytes": [ctypes.POINTER(ConvDesc), _I],
+    "cgat_conv_dbias_workspace_bytes": [ctypes.POINTER(ConvDesc)],
     "cgat_conv_stream_supported": [ctypes.POINTER(ConvDesc), _I],
     "cgat_conv_stream_workspace_bytes": [ctypes.POINTER(ConvDesc)],
     "cgat_conv2d_fprop_packed": [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P],
@@ -176,6 +177,7 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = args
             fn.restype = ctypes.c_int
         L.cgat_conv_workspace_bytes.restype = ctypes.c_int64
+        L.cgat_conv_dbias_workspace_bytes.restype = ctypes.c_int64
         L.cgat_conv_stream_workspace_bytes.restype = ctypes.c_int64
         L.cgat_stream_wpack_bytes.restype = ctypes.c_int64
         L.cgat_layer_workspace_bytes.restype = ctypes.c_int64

@@ -144,8 +144,11 @@ def _pick(d: ConvDesc, which: int, impl: int) -> int:
     return IMPL_TC if lib().cgat_conv_tc_supported(ctypes.byref(d), which) else IMPL_DIRECT
 
 
-def _workspace(d: ConvDesc, which: int, impl: int, device):
+def _workspace(d: ConvDesc, which: int, impl: int, device, dbias: bool = False):
     if impl != IMPL_TC:
+        if which == 2 and dbias:  # optional scratch of the CUDA-core wgrad's bias-gradient reduction
+            nbytes = lib().cgat_conv_dbias_workspace_bytes(ctypes.byref(d))
+            return torch.empty(max(16, nbytes), dtype=torch.uint8, device=device) if nbytes else None
         return None
     nbytes = lib().cgat_conv_workspace_bytes(ctypes.byref(d), which)
     return torch.empty(max(16, nbytes), dtype=torch.uint8, device=device) if nbytes else None
@@ -208,7 +211,7 @@ class _Conv2dNHWC(torch.autograd.Function):
         dw = torch.empty(wk.shape, device=x.device, dtype=torch.float32)
         db = torch.empty(d.cout, device=x.device, dtype=torch.float32) if ctx.has_bias else None
         im = _pick(d, 2, ctx.impl)
-        ws = _workspace(d, 2, im, x.device)
+        ws = _workspace(d, 2, im, x.device, dbias=db is not None)
         _lib.call("cgat_conv2d_wgrad", ctypes.byref(d), ptr(x), ptr(dy), ptr(dw), ptr(db), im, ptr(ws), st,
                   launches=2 if db is not None else 1)
         return dx, dw.to(ctx.w_dtype), db, None, None, None, None, None

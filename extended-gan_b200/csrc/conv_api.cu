@@ -30,6 +30,7 @@ int conv_dw3x3_launch(int which, const cgat_conv_desc*, const void*, const void*
 int conv_wgrad_small_served(const cgat_conv_desc* d);
 int conv_wgrad_small_launch(const cgat_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
 int conv_dbias_ws_launch(const cgat_conv_desc*, const void*, float*, void*, cudaStream_t);
+size_t conv_dbias_workspace(const cgat_conv_desc* d);
 int conv_small_served(const cgat_conv_desc* d, int which);
 int conv_small_launch(int which, const cgat_conv_desc*, const void*, const void*, const float*, void*, cudaStream_t);
 int conv_gemm_served(const cgat_conv_desc* d);
@@ -62,6 +63,10 @@ static int tc_ready(const cgat_conv_desc* d, int which, void* workspace) {
 extern "C" int cgat_conv_tc_supported(const cgat_conv_desc* d, int which) {
   if (validate_conv(d) || which < 0 || which > 2) return 0;
   return use_big(d, which) || conv_tc_supported(d, which);
+}
+
+extern "C" int64_t cgat_conv_dbias_workspace_bytes(const cgat_conv_desc* d) {
+  return validate_conv(d) ? 0 : (int64_t)conv_dbias_workspace(d);
 }
 
 extern "C" int64_t cgat_conv_workspace_bytes(const cgat_conv_desc* d, int which) {
@@ -107,11 +112,11 @@ extern "C" int cgat_conv2d_wgrad(const cgat_conv_desc* d, const void* x, const v
   if (impl == 0 && conv_wgrad_small_served(d)) return conv_wgrad_small_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
   if (impl == 0 && conv_is_pointwise(d)) {
     if (int rc = conv_pointwise_launch(2, d, dy, x, dw, nullptr, (cudaStream_t)stream)) return rc;
-    return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
+    return dbias ? conv_dbias_ws_launch(d, dy, dbias, workspace, (cudaStream_t)stream) : 0;  // (workspace optional here)
   }
   if (impl == 0 && conv_gemm_served(d)) {
     if (int rc = conv_gemm_launch(2, d, dy, x, dw, nullptr, (cudaStream_t)stream)) return rc;
-    return dbias ? conv_dbias_launch(d, dy, dbias, (cudaStream_t)stream) : 0;
+    return dbias ? conv_dbias_ws_launch(d, dy, dbias, workspace, (cudaStream_t)stream) : 0;  // (workspace optional here)
   }
   if (impl == 0) return conv_wgrad_direct_launch(d, x, dy, dw, dbias, (cudaStream_t)stream);
   if (use_big(d, 2)) {

@@ -121,6 +121,9 @@ typedef struct cgat_conv_desc {
  * `workspace`: device scratch of at least cgat_conv_workspace_bytes(d, which) bytes (packed weights /
  * partial sums), 16-byte aligned, owned by the caller; may be NULL when that size is 0.
  * wgrad WRITES dw [cout][kh][kw][cin] fp32 and, if dbias != NULL, dbias [cout] fp32.                */
+/* Optional scratch of the impl = 0 wgrad: with a workspace of this many bytes the bias gradient is reduced by coalesced
+ * per-CTA partial rows + a fixed-order final sum (deterministic); with workspace == NULL by one block per channel.     */
+int64_t cgat_conv_dbias_workspace_bytes(const cgat_conv_desc* d);
 int cgat_conv2d_fprop(const cgat_conv_desc* d, const void* x, const void* w, const float* bias, void* y,
                       int impl, void* workspace, void* stream);
 int cgat_conv2d_dgrad(const cgat_conv_desc* d, const void* dy, const void* w, void* dx, int impl,
