@@ -28,3 +28,12 @@ def test_data_parallel_matches_single_gpu_two_ranks():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "data-parallel == single-GPU OK" in res.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_p2p_exchange_time_out_is_all_or_nothing_and_fatal():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29545", os.path.join(ROOT, "tests", "mp_p2p_timeout_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "p2p time-out OK" in res.stdout
